@@ -1,0 +1,496 @@
+"""
+Explicit (autograd-free) schedule of the SR-GAN / DG-GAN training step on top of the C-ABI kernels.
+
+Replaces, for the supported model families, the bodies of
+    Experiment.dnn_training_step   srgan.py:259-271
+    Experiment.gan_training_step   srgan.py:273-320   (+ the *_loss_calculation hooks :322-391, feature_distance_loss
+                                                        :438-449, gradient_penalty_calculation :360-375)
+    coefficient/dggan.py:22-64     (DG-GAN loss overrides)
+with the de-duplicated schedule of SURVEY.md App. B / C:
+    D step : G fwd (no grad) -> D fwd on the row-concatenated batch [x; u; fake; x_hat] -> feature column sums
+             (-> all-reduce across ranks) -> distance losses + seeds -> gradient-penalty chains on the x_hat rows
+             (g-chain = 'up' ops, tangent u-chain = 'down' ops, App. C.3) -> ONE backward over [x; u; fake; x_hat]
+             with the weight-gradient launches also covering the (u_{l-1}, gamma_l) tangent block -> Adam.
+    G step : G fwd -> D fwd on [fake2; u] with the updated D -> seed -> D data-backward on the fake2 rows only
+             -> G backward -> Adam.
+    DNN    : fwd, seed, backward, Adam.
+All tensors are torch tensors used as device memory handles; all arithmetic is done by `ops` (ops_cuda.CudaOps in the
+product; tests inject tests/torch_ops.py to check this schedule against the oracle on CPU).
+
+Activation layout: row-major [rows = sample-major pixels, channels] (NHWC).  Buffer blocks, in units of the local
+batch B:  acts[l] rows [0,B)=x  [B,2B)=u  [2B,3B)=fake  [3B,4B)=x_hat  [4B,5B)=tangent u_l ;
+          delta[l] rows [0,4B) = dLoss/da_l, [4B,5B) = gamma_l = (ds/da_l) of the gradient-penalty g-chain.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from .nets import Net, Layer, ACT_NONE, ACT_LEAKY, ACT_TANH
+
+EPI_BIAS_ACT, EPI_DACT = 0, 1
+DIST_KINDS = {'abs_mean': 0, 'abs_mean_neg': 1, 'abs_plus_one_sqrt_mean_neg': 2, 'abs_plus_one_log_mean_neg': 3,
+              'square_mean': 4, 'norm_mean': 5}
+# scalar slots (device fp32 buffer, read back only on summary steps: same sync pattern as srgan.py:306-319)
+SC_DNN, SC_LABELED, SC_UNLABELED, SC_FAKE, SC_GP, SC_GNORM, SC_GEN = range(7)
+N_SCALARS = 8
+
+
+def _strides_for(layer_kind: str, dims, Ca, Cb, R, S):
+    """Element strides, per master dim, into the Wd[a][r][s][b] and Wu[b][r][s][a] kernel layouts (nets.py)."""
+    if layer_kind == 'conv':        # master[a][b][r][s]
+        wd = (R * S * Cb, 1, S * Cb, Cb)
+        wu = (1, R * S * Ca, S * Ca, Ca)
+    elif layer_kind == 'fc_up':     # master[zb][c][r][s]; Linear a=(r,s,c), b=zb ; here R=S=1 in the geom, k from dims
+        zb, c, k, _ = dims
+        wd = (1, zb, k * c * zb, c * zb)
+        wu = (Ca, 1, k * c, c)
+    else:
+        raise ValueError(layer_kind)
+    return wd, wu
+
+
+class NetState:
+    """Device-side state of one network: fp32 master parameters (the nn.Parameters themselves, updated in place),
+    kernel-layout weight copies in the activation dtype, one flat fp32 gradient buffer, Adam moments."""
+
+    def __init__(self, net: Net, params: Dict[str, torch.Tensor], act_dtype, device):
+        self.net = net
+        self.params = params
+        self.act_dtype = act_dtype
+        self.device = device
+        n_total = 0
+        self.slices = {}
+        order = []
+        for l in net.layers:
+            order += [l.name + '.weight', l.name + '.bias']
+        if net.head:
+            order += [net.head + '.weight', net.head + '.bias']
+        for k in order:
+            p = params[k]
+            if p.dtype != torch.float32 and p.dtype != torch.float64:
+                raise TypeError(f'{k}: master parameters must be fp32')
+            if not p.is_contiguous():
+                raise ValueError(f'{k}: master parameter must be contiguous')
+            n = p.numel()
+            self.slices[k] = (n_total, n)
+            n_total += (n + 3) // 4 * 4            # keep every tensor 16-byte aligned inside the flat buffers
+        self.order = order
+        mdt = params[order[0]].dtype
+        self.grad = torch.zeros(n_total, dtype=mdt, device=device)
+        self.exp_avg = torch.zeros(n_total, dtype=mdt, device=device)
+        self.exp_avg_sq = torch.zeros(n_total, dtype=mdt, device=device)
+        self.adam_step = 0
+        self.wd_, self.wu_ = {}, {}
+        for l in net.layers:
+            n = params[l.name + '.weight'].numel()
+            self.wd_[l.name] = torch.empty(n, dtype=act_dtype, device=device)
+            self.wu_[l.name] = torch.empty(n, dtype=act_dtype, device=device)
+        if net.head:
+            self.whead = torch.empty(net.head_outputs * net.feature_size, dtype=mdt, device=device)
+
+    def g(self, key):
+        o, n = self.slices[key]
+        return self.grad[o:o + n]
+
+    def m(self, key):
+        o, n = self.slices[key]
+        return self.exp_avg[o:o + n]
+
+    def v(self, key):
+        o, n = self.slices[key]
+        return self.exp_avg_sq[o:o + n]
+
+
+class Engine:
+    def __init__(self, ops, d_net: Net, g_net: Optional[Net], D: Dict[str, torch.Tensor],
+                 G: Optional[Dict[str, torch.Tensor]], DNN: Optional[Dict[str, torch.Tensor]],
+                 act_dtype=torch.float32, device='cuda', comm=None):
+        self.ops = ops
+        self.device = torch.device(device)
+        self.act_dtype = act_dtype
+        self.comm = comm                           # dist.Comm or None (single rank)
+        self.d_net, self.g_net = d_net, g_net
+        self.D = NetState(d_net, D, act_dtype, self.device)
+        self.G = NetState(g_net, G, act_dtype, self.device) if g_net is not None else None
+        self.DNN = NetState(d_net, DNN, act_dtype, self.device) if DNN is not None else None
+        self.mdt = self.D.grad.dtype               # fp32 in the product; tests may run the schedule in fp64
+        self.scalars = torch.zeros(N_SCALARS, dtype=self.mdt, device=self.device)
+        self._buf = {}
+        self.launches = 0
+        for st in (self.D, self.G, self.DNN):
+            if st is not None:
+                self.repack(st)
+
+    # ------------------------------------------------------------------ buffers
+    def buf(self, key, shape, dtype=None):
+        dtype = dtype or self.act_dtype
+        t = self._buf.get(key)
+        n = 1
+        for s in shape:
+            n *= s
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(n, dtype=dtype, device=self.device)
+            self._buf[key] = t
+        return t[:n].view(*shape)
+
+    # ------------------------------------------------------------------ weights
+    def repack(self, st: NetState):
+        """Master (torch layout, fp32) -> kernel layouts.  Also done by the fused Adam after every update."""
+        for l in st.net.layers:
+            w = st.params[l.name + '.weight']
+            g = l.geom
+            wd_s, wu_s = _strides_for(l.master_kind, l.master_dims, g.Ca, g.Cb, g.R, g.S)
+            self.ops.repack(w, l.master_dims, st.wd_[l.name], wd_s, st.wu_[l.name], wu_s)
+        if st.net.head:
+            self._repack_head(st)
+
+    def _head_strides(self, net: Net):
+        F = net.feature_size
+        if net.head_master_kind == 'linear':
+            return (net.head_outputs, F, 1, 1), (F, 1, 0, 0)
+        c, h, w = net.feature_chw
+        return (net.head_outputs, c, h, w), (F, 1, w * c, c)
+
+    def _repack_head(self, st: NetState):
+        dims, s = self._head_strides(st.net)
+        self.ops.repack(st.params[st.net.head + '.weight'], dims, st.whead, s, None, None)
+
+    # ------------------------------------------------------------------ layer ops
+    def _fwd_layer(self, st: NetState, l: Layer, x, y, n, bias=True, href=None, epi=EPI_BIAS_ACT, act=None, slope=None):
+        act = l.act if act is None else act
+        slope = l.slope if slope is None else slope
+        b = st.params[l.name + '.bias'] if bias else None
+        if l.fwd == 'down':
+            self.ops.conv_down(x, st.wd_[l.name], y, n, l.geom, b, l.bias_mod, href, epi, act, slope)
+        else:
+            self.ops.conv_up(x, st.wu_[l.name], y, n, l.geom, b, l.bias_mod, href, epi, act, slope)
+
+    def _bwd_data_layer(self, st: NetState, l: Layer, dy, dx, n, href, act, slope):
+        """dx = (W_l^T dy) * act'(href)   (act = ACT_NONE: no mask)."""
+        if l.fwd == 'down':
+            self.ops.conv_up(dy, st.wu_[l.name], dx, n, l.geom, None, 0, href, EPI_DACT, act, slope)
+        else:
+            self.ops.conv_down(dy, st.wd_[l.name], dx, n, l.geom, None, 0, href, EPI_DACT, act, slope)
+
+    def _wgrad_layer(self, st: NetState, l: Layer, x_in, dy, n):
+        dW = st.g(l.name + '.weight')
+        if l.fwd == 'down':
+            self.ops.conv_wgrad(dy, x_in, dW, n, l.geom)
+        else:
+            self.ops.conv_wgrad(x_in, dy, dW, n, l.geom)
+
+    def _bias_grad(self, st: NetState, l: Layer, dy, rows):
+        self.ops.colsum(dy, rows, l.out_ch, st.g(l.name + '.bias'), l.bias_mod, None)
+
+    # ------------------------------------------------------------------ passes
+    def alloc_acts(self, tag, net: Net, nb_rows):
+        """acts[0] = network input, acts[l] = output of layer l; flat, nb_rows samples of NHWC rows each."""
+        acts = [self.buf((tag, 'a', 0), (nb_rows * net.layers[0].in_elems,))]
+        for i, l in enumerate(net.layers, 1):
+            acts.append(self.buf((tag, 'a', i), (nb_rows * l.out_elems,)))
+        return acts
+
+    def alloc_deltas(self, tag, net: Net, nb_rows):
+        d = [None]
+        for i, l in enumerate(net.layers, 1):
+            d.append(self.buf((tag, 'd', i), (nb_rows * l.out_elems,)))
+        return d
+
+    @staticmethod
+    def rows(t, elems_per_sample, lo, hi):
+        return t[lo * elems_per_sample: hi * elems_per_sample]
+
+    def forward(self, st: NetState, acts, lo, hi):
+        """Runs the stack on sample rows [lo, hi) of the buffers."""
+        net = st.net
+        n = hi - lo
+        for i, l in enumerate(net.layers, 1):
+            self._fwd_layer(st, l, self.rows(acts[i - 1], l.in_elems, lo, hi), self.rows(acts[i], l.out_elems, lo, hi), n)
+
+    def backward(self, st: NetState, acts, deltas, lo, hi, wlo=None, whi=None, need_input_grad=False, dinput=None,
+                 input_href=None, input_act=ACT_NONE, weight_grads=True):
+        """Ordinary reverse pass over sample rows [lo,hi); weight gradients over rows [wlo,whi) (defaults to the
+        same rows; the D step widens it to include the tangent block)."""
+        net = st.net
+        wlo = lo if wlo is None else wlo
+        whi = hi if whi is None else whi
+        for i in range(len(net.layers), 0, -1):
+            l = net.layers[i - 1]
+            if weight_grads:
+                self._wgrad_layer(st, l, self.rows(acts[i - 1], l.in_elems, wlo, whi),
+                                  self.rows(deltas[i], l.out_elems, wlo, whi), whi - wlo)
+                self._bias_grad(st, l, self.rows(deltas[i], l.out_elems, lo, hi), (hi - lo) * l.out_rows)
+            if i > 1:
+                lp = net.layers[i - 2]
+                self._bwd_data_layer(st, l, self.rows(deltas[i], l.out_elems, lo, hi),
+                                     self.rows(deltas[i - 1], lp.out_elems, lo, hi), hi - lo,
+                                     self.rows(acts[i - 1], lp.out_elems, lo, hi), lp.act, lp.slope)
+            elif need_input_grad:
+                self._bwd_data_layer(st, l, self.rows(deltas[i], l.out_elems, lo, hi), dinput, hi - lo,
+                                     input_href, input_act, 0.0)
+
+    # ------------------------------------------------------------------ Adam
+    def adam(self, st: NetState, lr, weight_decay, betas=(0.9, 0.999), eps=1e-8):
+        """torch.optim.Adam semantics, one fused launch per tensor that also rewrites the kernel-
+        layout copies.  Gradients are read from (and then zeroed in) the flat buffer."""
+        if self.comm is not None:
+            self.comm.all_reduce_sum(st.grad)
+        st.adam_step += 1
+        t = st.adam_step
+        bc1 = 1.0 - betas[0] ** t
+        bc2 = 1.0 - betas[1] ** t
+        for l in st.net.layers:
+            g = l.geom
+            wd_s, wu_s = _strides_for(l.master_kind, l.master_dims, g.Ca, g.Cb, g.R, g.S)
+            k = l.name + '.weight'
+            self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), l.master_dims, wd_s, st.wd_[l.name], wd_s,
+                          st.wu_[l.name], wu_s, lr, betas[0], betas[1], eps, weight_decay, bc1, bc2)
+            k = l.name + '.bias'
+            nb = st.params[k].numel()
+            self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), (nb, 1, 1, 1), (1, 0, 0, 0), None, None, None, None,
+                          lr, betas[0], betas[1], eps, weight_decay, bc1, bc2)
+        if st.net.head:
+            dims, s = self._head_strides(st.net)
+            k = st.net.head + '.weight'
+            self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), dims, s, st.whead, s, None, None,
+                          lr, betas[0], betas[1], eps, weight_decay, bc1, bc2)
+            k = st.net.head + '.bias'
+            nb = st.params[k].numel()
+            self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), (nb, 1, 1, 1), (1, 0, 0, 0), None, None, None, None,
+                          lr, betas[0], betas[1], eps, weight_decay, bc1, bc2)
+        st.grad.zero_()
+
+    # ------------------------------------------------------------------ inputs
+    def load_input(self, net: Net, src: torch.Tensor, dst, n):
+        """Reference-side fp32 NCHW (or [B, features]) -> activation dtype NHWC rows."""
+        c, h, w = net.input_chw
+        if src.numel() != n * c * h * w:
+            raise ValueError(f'input has {src.numel()} elements, expected {n}x{c}x{h}x{w}')
+        self.ops.nchw_to_nhwc(src.contiguous(), dst, n, c, h, w)
+
+    def _global_batch(self, B):
+        return B * (self.comm.world_size if self.comm is not None else 1)
+
+    # ------------------------------------------------------------------ head
+    def _head_forward(self, st: NetState, feats, n, out_index, out):
+        F = st.net.feature_size
+        self.ops.rowdot(feats, n, F, st.whead[out_index * F:(out_index + 1) * F], st.params[st.net.head + '.bias'],
+                        out_index, out)
+
+    def _head_grads(self, st: NetState, feats, n, out_index, drow):
+        F = st.net.feature_size
+        gw = st.g(st.net.head + '.weight')[out_index * F:(out_index + 1) * F]
+        self.ops.colsum(feats, n, F, gw, 0, drow)
+        gb = st.g(st.net.head + '.bias')[out_index:out_index + 1]
+        self.ops.colsum(drow, n, 1, gb, 0, None)
+
+    # ------------------------------------------------------------------ DNN step (srgan.py:259-271)
+    def dnn_step(self, x, y, cfg, lr, weight_decay):
+        st, net = self.DNN, self.d_net
+        B = x.shape[0]
+        Bg = self._global_batch(B)
+        L = len(net.layers)
+        F = net.feature_size
+        acts = self.alloc_acts('D', net, 5 * B)
+        deltas = self.alloc_deltas('D', net, 5 * B)
+        self.load_input(net, x, self.rows(acts[0], net.layers[0].in_elems, 0, B), B)
+        self.forward(st, acts, 0, B)
+        lastl = net.layers[-1]
+        feats = self.rows(acts[L], F, 0, B)
+        pred = self.buf('pred', (B,), self.mdt)
+        dpred = self.buf('dpred', (B,), self.mdt)
+        self._head_forward(st, feats, B, 0, pred)
+        self.scalars[SC_DNN:SC_DNN + 1].zero_()
+        self.ops.labeled_loss(pred, y, B, cfg.labeled_loss_order, cfg.labeled_loss_multiplier / Bg,
+                              self.scalars[SC_DNN:SC_DNN + 1], dpred)
+        self.ops.seed_rows(self.rows(deltas[L], F, 0, B), B, F, None, dpred,
+                           st.whead[0:F], feats, lastl.act, lastl.slope)
+        self._head_grads(st, feats, B, 0, dpred)
+        self.backward(st, acts, deltas, 0, B)
+        self.adam(st, lr, weight_decay, cfg.betas, cfg.eps)
+
+    # ------------------------------------------------------------------ GAN step (srgan.py:273-320)
+    def gan_step(self, x, y, u, z, alpha, z2, cfg, train_generator=True):
+        ops, D, G, net, gnet = self.ops, self.D, self.G, self.d_net, self.g_net
+        B = x.shape[0]
+        if u.shape[0] != B or z.shape[0] != B or alpha.numel() != B:
+            # srgan.py:363 draws alpha with settings.batch_size rows: the reference itself requires full batches
+            raise ValueError('labeled, unlabeled and noise batches must have the same size (SURVEY App. E.2)')
+        Bg = self._global_batch(B)
+        L = len(net.layers)
+        lastl = net.layers[-1]
+        F = net.feature_size
+        dggan = cfg.method == 'dggan'
+        acts = self.alloc_acts('D', net, 5 * B)
+        deltas = self.alloc_deltas('D', net, 5 * B)
+        in_rows = net.layers[0].in_rows
+        E = net.layers[0].in_elems
+        sc = self.scalars
+        sc[SC_LABELED:SC_GEN + 1].zero_()
+
+        def blk(t, layer, lo, hi):
+            return self.rows(t, layer.out_elems, lo, hi)
+
+        def fblk(lo, hi):
+            return self.rows(acts[L], F, lo, hi)
+
+        def dblk(lo, hi):
+            return self.rows(deltas[L], F, lo, hi)
+
+        # ---- inputs: x, u, fake = G(z) (no grad, srgan.py:290/352), x_hat (srgan.py:362-366)
+        self.load_input(net, x, self.rows(acts[0], E, 0, B), B)
+        self.load_input(net, u, self.rows(acts[0], E, B, 2 * B), B)
+        gacts = self.alloc_acts('G', gnet, B)
+        gacts[-1] = self.rows(acts[0], E, 2 * B, 3 * B)
+        self.load_input(gnet, z, gacts[0], B)
+        self.forward(G, gacts, 0, B)
+        ops.interpolate(self.rows(acts[0], E, B, 2 * B), self.rows(acts[0], E, 2 * B, 3 * B), alpha,
+                        self.rows(acts[0], E, 3 * B, 4 * B), B, E)
+        # ---- one D forward over [x; u; fake; x_hat]
+        self.forward(D, acts, 0, 4 * B)
+        # ---- labeled loss (srgan.py:329-335, :414-417)
+        pred = self.buf('pred', (B,), self.mdt)
+        dpred = self.buf('dpred', (B,), self.mdt)
+        self._head_forward(D, fblk(0, B), B, 0, pred)
+        ops.labeled_loss(pred, y, B, cfg.labeled_loss_order, cfg.labeled_loss_multiplier / Bg,
+                         sc[SC_LABELED:SC_LABELED + 1], dpred)
+        gamma_L = dblk(4 * B, 5 * B)
+        s_norm = self.buf('s_norm', (B,), self.mdt)
+        if not dggan:
+            # ---- feature sums -> (all-reduce) -> distance losses (srgan.py:337-358, :438-449)
+            sums = self.buf('fsums', (3, F), self.mdt)
+            sums.zero_()
+            for j in range(3):
+                ops.colsum(fblk(j * B, (j + 1) * B), B, F, sums[j], 0, None)
+            if self.comm is not None:
+                self.comm.all_reduce_sum(sums)
+            gvec = self.buf('gvec', (3, F), self.mdt)
+            inv = 1.0 / Bg
+            # unlabeled: base = u, other = x ; writes d/dmean_u and d/dmean_x (already divided by the global batch)
+            ops.distance(sums[1], sums[0], F, inv, DIST_KINDS[cfg.matching_distance_function],
+                         cfg.matching_loss_multiplier * cfg.srgan_loss_multiplier, sc[SC_UNLABELED:SC_UNLABELED + 1],
+                         gvec[1], gvec[0], False)
+            # fake: base = u (accumulates into gvec[1]), other = fake
+            ops.distance(sums[1], sums[2], F, inv, DIST_KINDS[cfg.contrasting_distance_function],
+                         cfg.contrasting_loss_multiplier * cfg.srgan_loss_multiplier, sc[SC_FAKE:SC_FAKE + 1],
+                         gvec[1], gvec[2], True)
+            ops.seed_rows(dblk(0, B), B, F, gvec[0], dpred, D.whead[0:F], fblk(0, B), lastl.act, lastl.slope)
+            ops.seed_rows(dblk(B, 2 * B), B, F, gvec[1], None, None, fblk(B, 2 * B), lastl.act, lastl.slope)
+            ops.seed_rows(dblk(2 * B, 3 * B), B, F, gvec[2], None, None, fblk(2 * B, 3 * B), lastl.act, lastl.slope)
+            # ---- GP target s = ||f(x_hat)||_2 (srgan.py:377-381): gamma_L = (f/s) * act'
+            ops.feature_norm_seed(fblk(3 * B, 4 * B), B, F, s_norm, gamma_L, lastl.act, lastl.slope)
+        else:
+            # ---- DG-GAN (coefficient/dggan.py:36-57): BCE on the second head output; GP target = raw score
+            su = self.buf('score_u', (B,), self.mdt)
+            sf = self.buf('score_f', (B,), self.mdt)
+            dsu = self.buf('dscore_u', (B,), self.mdt)
+            dsf = self.buf('dscore_f', (B,), self.mdt)
+            self._head_forward(D, fblk(B, 2 * B), B, 1, su)
+            self._head_forward(D, fblk(2 * B, 3 * B), B, 1, sf)
+            ops.bce_logits(su, B, 0.0, cfg.matching_loss_multiplier * cfg.dggan_loss_multiplier / Bg,
+                           sc[SC_UNLABELED:SC_UNLABELED + 1], dsu)
+            ops.bce_logits(sf, B, 1.0, cfg.contrasting_loss_multiplier * cfg.dggan_loss_multiplier / Bg,
+                           sc[SC_FAKE:SC_FAKE + 1], dsf)
+            w1 = D.whead[F:2 * F]
+            ops.seed_rows(dblk(0, B), B, F, None, dpred, D.whead[0:F], fblk(0, B), lastl.act, lastl.slope)
+            ops.seed_rows(dblk(B, 2 * B), B, F, None, dsu, w1, fblk(B, 2 * B), lastl.act, lastl.slope)
+            ops.seed_rows(dblk(2 * B, 3 * B), B, F, None, dsf, w1, fblk(2 * B, 3 * B), lastl.act, lastl.slope)
+            self._head_grads(D, fblk(B, 2 * B), B, 1, dsu)
+            self._head_grads(D, fblk(2 * B, 3 * B), B, 1, dsf)
+            ops.seed_rows(gamma_L, B, F, w1, None, None, fblk(3 * B, 4 * B), lastl.act, lastl.slope)
+        self._head_grads(D, fblk(0, B), B, 0, dpred)
+        # ---- gradient penalty (srgan.py:360-375) without autograd: SURVEY App. C.3
+        # g-chain: gamma_{l-1} = up(W_l, gamma_l) * act'(h_{l-1}) on the x_hat rows; g_0 has no mask
+        for i in range(L, 1, -1):
+            l, lp = net.layers[i - 1], net.layers[i - 2]
+            self._bwd_data_layer(D, l, blk(deltas[i], l, 4 * B, 5 * B), blk(deltas[i - 1], lp, 4 * B, 5 * B), B,
+                                 blk(acts[i - 1], lp, 3 * B, 4 * B), lp.act, lp.slope)
+        g0 = self.buf('g0', (B * E,))
+        l1 = net.layers[0]
+        self._bwd_data_layer(D, l1, blk(deltas[1], l1, 4 * B, 5 * B), g0, B, None, ACT_NONE, 0.0)
+        gnorm = self.buf('gnorm', (B,), self.mdt)
+        u0 = self.rows(acts[0], E, 4 * B, 5 * B)
+        ops.gradnorm_penalty(g0, B, E, cfg.gradient_penalty_multiplier / Bg, 1.0 / Bg, gnorm, sc[SC_GP:SC_GP + 1],
+                             sc[SC_GNORM:SC_GNORM + 1], u0)
+        # tangent u-chain: u_l = down(W_l, u_{l-1}) (no bias) * act'(h_l of x_hat)
+        for i, l in enumerate(net.layers, 1):
+            self._fwd_layer(D, l, self.rows(acts[i - 1], l.in_elems, 4 * B, 5 * B), blk(acts[i], l, 4 * B, 5 * B), B,
+                            bias=False, href=blk(acts[i], l, 3 * B, 4 * B), epi=EPI_DACT)
+        if not dggan:
+            ops.gp_feature_seed(fblk(4 * B, 5 * B), fblk(3 * B, 4 * B), s_norm, dblk(3 * B, 4 * B), B, F,
+                                lastl.act, lastl.slope)
+            hi = 4 * B
+        else:
+            # dP/dW_head[1,:] = sum_n u_L,n ; the Jacobian term vanishes (target is linear in the features)
+            ops.colsum(fblk(4 * B, 5 * B), B, F, D.g(net.head + '.weight')[F:2 * F], 0, None)
+            hi = 3 * B
+        # ---- one backward over [x; u; fake; (x_hat)], weight gradients also over the tangent block
+        if hi == 4 * B:
+            self.backward(D, acts, deltas, 0, 4 * B, 0, 5 * B)
+        else:
+            # DG-GAN: rows [3B,4B) carry no ordinary gradient; weight grads = rows [0,3B) + tangent block [4B,5B)
+            self.backward(D, acts, deltas, 0, 3 * B, 0, 3 * B)
+            for i, l in enumerate(net.layers, 1):
+                self._wgrad_layer(D, l, self.rows(acts[i - 1], l.in_elems, 4 * B, 5 * B),
+                                  blk(deltas[i], l, 4 * B, 5 * B), B)
+        self.adam(D, cfg.learning_rate, cfg.weight_decay, cfg.betas, cfg.eps)                     # srgan.py:297
+        if not train_generator:
+            return
+        # ---- generator step (srgan.py:299-305, :383-391) with the UPDATED discriminator
+        gacts = self.alloc_acts('G', gnet, B)
+        fake2 = self.rows(acts[0], E, 0, B)
+        gacts[-1] = fake2
+        self.load_input(gnet, z2, gacts[0], B)
+        self.forward(G, gacts, 0, B)
+        if not dggan:
+            self.forward(D, acts, 0, 2 * B)                     # rows [B,2B) still hold u
+            sums = self.buf('fsums', (3, F), self.mdt)
+            sums.zero_()
+            ops.colsum(fblk(0, B), B, F, sums[0], 0, None)
+            ops.colsum(fblk(B, 2 * B), B, F, sums[1], 0, None)
+            if self.comm is not None:
+                self.comm.all_reduce_sum(sums)
+            gvec = self.buf('gvec', (3, F), self.mdt)
+            ops.distance(sums[1], sums[0], F, 1.0 / Bg, DIST_KINDS[cfg.matching_distance_function],
+                         cfg.matching_loss_multiplier, sc[SC_GEN:SC_GEN + 1], gvec[1], gvec[0], False)
+            ops.seed_rows(dblk(0, B), B, F, gvec[0], None, None, fblk(0, B), lastl.act, lastl.slope)
+        else:
+            self.forward(D, acts, 0, B)
+            sf = self.buf('score_f', (B,), self.mdt)
+            dsf = self.buf('dscore_f', (B,), self.mdt)
+            self._head_forward(D, fblk(0, B), B, 1, sf)
+            ops.bce_logits(sf, B, 0.0, 1.0 / Bg, sc[SC_GEN:SC_GEN + 1], dsf)                      # dggan.py:59-64
+            ops.seed_rows(dblk(0, B), B, F, None, dsf, D.whead[F:2 * F], fblk(0, B), lastl.act, lastl.slope)
+        gl = gnet.layers
+        gdeltas = self.alloc_deltas('G', gnet, B)
+        # D data-backward only (the reference's D weight grads here are discarded), ending in
+        # dLoss/d(pre-activation of G's last layer) = (W_1^T delta_1) * act_G'(fake2)
+        self.backward(D, acts, deltas, 0, B, need_input_grad=True, dinput=gdeltas[len(gl)], input_href=gacts[-1],
+                      input_act=gl[-1].act, weight_grads=False)
+        self.backward(G, gacts, gdeltas, 0, B)
+        self.adam(G, cfg.learning_rate, 0.0, cfg.betas, cfg.eps)                                  # srgan.py:137, :305
+
+    # ------------------------------------------------------------------ inference-style helpers
+    def d_features(self, x, st: Optional[NetState] = None):
+        """D(x) forward only: returns (prediction [B], features rows [B, F] in NHWC order)."""
+        st = st or self.D
+        net = st.net
+        B = x.shape[0]
+        acts = self.alloc_acts('D', net, 5 * B)
+        self.load_input(net, x, self.rows(acts[0], net.layers[0].in_elems, 0, B), B)
+        self.forward(st, acts, 0, B)
+        feats = self.rows(acts[-1], net.feature_size, 0, B)
+        pred = self.buf('pred', (B,), self.mdt)
+        self._head_forward(st, feats, B, 0, pred)
+        return pred, feats
+
+    def g_generate(self, z):
+        gnet = self.g_net
+        B = z.shape[0]
+        gacts = self.alloc_acts('G', gnet, B)
+        self.load_input(gnet, z, gacts[0], B)
+        self.forward(self.G, gacts, 0, B)
+        return gacts[-1]
