@@ -1,0 +1,135 @@
+/*
+ * srgan_b200.h -- C ABI of the B200 (sm_100a) kernels behind the SR-GAN training step.
+ *
+ * This is the drop-in boundary.  The reference (golmschenk/sr-gan) is pure Python/PyTorch and
+ * has no FFI of its own; the seam it offers is method override on `Experiment` (srgan.py:259-391).  Each entry point
+ * below replaces the ATen/cuDNN/cuBLAS call(s) the reference issues at the cited lines; the Python host code in
+ * sr-gan_b200/ (engine.py, mixin.py) binds them with ctypes (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *  - plain C types only; every pointer is a DEVICE pointer owned by the caller (torch tensors on the Python side);
+ *  - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*); it never allocates, frees or
+ *    synchronises; returns 0 on success, <0 on error (message: srgan_last_error(), thread-local);
+ *  - `dtype` selects the activation / kernel-layout-weight element type: SRGAN_F32 (parity mode, SIMT FMA, fp32
+ *    accumulate) or SRGAN_BF16 (tensor-core mode: tcgen05 implicit GEMM where the shape allows, fp32 accumulate);
+ *    master parameters, gradients, Adam moments, losses and reductions are always fp32;
+ *  - activations are NHWC rows: [sample][y][x][channel], contiguous;
+ *  - a "conv pair" relates a SMALL side S[n,Hs,Ws,Ca] and a LARGE side L[n,Hl,Wl,Cb] through taps W[a][r][s][b]:
+ *      down : S[o]  = sum_{t,b} L[stride*o-pad+t, b] * W[a,t,b]     (nn.Conv2d fwd / nn.ConvTranspose2d bwd-data)
+ *      up   : L[i] += sum_a S[o,a] * W[a,t,b],  i = stride*o-pad+t  (nn.ConvTranspose2d fwd / nn.Conv2d bwd-data)
+ *      wgrad: dW[a,t,b] += sum_{n,o} S[o,a] * L[stride*o-pad+t, b]
+ *    nn.Linear is the pair with every spatial extent 1.  Kernel weight layouts: Wd[a][r][s][b], Wu[b][r][s][a].
+ */
+#ifndef SRGAN_B200_H
+#define SRGAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRGAN_F32 0
+#define SRGAN_BF16 1
+
+#define SRGAN_ACT_NONE 0
+#define SRGAN_ACT_LEAKY 1
+#define SRGAN_ACT_TANH 2
+
+#define SRGAN_EPI_BIAS_ACT 0 /* out = act(acc + bias)                                  */
+#define SRGAN_EPI_DACT 1     /* out = acc * act'(href)   (backward / tangent passes)   */
+
+#define SRGAN_OK 0
+#define SRGAN_ERR_ARG -1
+#define SRGAN_ERR_CUDA -2
+#define SRGAN_ERR_UNSUPPORTED -3
+
+typedef struct srgan_geom {
+    int Hs, Ws, Ca; /* small side */
+    int Hl, Wl, Cb; /* large side */
+    int R, S, stride, pad;
+} srgan_geom;
+
+/* library */
+int srgan_version(void);
+const char* srgan_last_error(void);
+/* number of kernels this library has launched since load (the bench reports it as gpu_launches) */
+long long srgan_launch_count(void);
+/* 1 if the last conv call on this thread ran on the tcgen05 path, 0 if SIMT */
+int srgan_last_path_tensor(void);
+/* force the SIMT path even for bf16 (debug / A-B checks): 0 = auto, 1 = SIMT only */
+void srgan_set_force_simt(int on);
+
+/* ---- dense contractions -------------------------------------------------------------------------------------
+ * Replace F.conv2d / F.conv_transpose2d / F.linear forward and their autograd backward (cuDNN fprop/dgrad/wgrad,
+ * cuBLAS addmm) issued from age/models.py:44-52,68-80, coefficient/models.py:22-28,43-50,65-72,
+ * crowd/models.py:139-147 and from `.backward()` / `autograd.grad` at srgan.py:265,280,284,292,295,304,368. */
+int srgan_conv_down(const void* L, const void* Wd, void* S_out, int n, const srgan_geom* g, const float* bias,
+                    int bias_mod, const void* href, int epi, int act, float slope, int dtype, void* stream);
+int srgan_conv_up(const void* S, const void* Wu, void* L_out, int n, const srgan_geom* g, const float* bias,
+                  int bias_mod, const void* href, int epi, int act, float slope, int dtype, void* stream);
+/* dW (fp32, Wd layout) += wgrad(S, L) */
+int srgan_conv_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, int dtype, void* stream);
+
+/* ---- reductions ---------------------------------------------------------------------------------------------
+ * out[c % mod] += sum_r rowscale[r] * X[r,c]  (mod = 0: no folding; rowscale may be NULL).  Replaces
+ * `features.mean(0)` (srgan.py:442-443, the division by the GLOBAL batch happens in srgan_distance) and the bias /
+ * head-weight gradient reductions of autograd. */
+int srgan_colsum(const void* X, long long rows, int cols, float* out, int mod, const float* rowscale, int dtype,
+                 void* stream);
+/* out[r] = sum_c X[r,c] * w[c] + bias[bias_index]: the prediction head (age/models.py:75 layer5 as a full-extent
+ * conv == a dot product per sample; coefficient/models.py:49 linear4). */
+int srgan_rowdot(const void* X, int rows, int cols, const float* w, const float* bias, int bias_index, float* out,
+                 int dtype, void* stream);
+
+/* ---- element-wise / loss kernels ----------------------------------------------------------------------------*/
+/* out[r,c] = (gvec[c] + rowscale[r]*wrow[c]) * act'(href[r,c]); gvec or (rowscale,wrow) may be NULL.
+ * Seeds the backward pass with d(loss)/d(pre-activation of the feature layer). */
+int srgan_seed_rows(void* out, int rows, int cols, const float* gvec, const float* rowscale, const float* wrow,
+                    const void* href, int act, float slope, int dtype, void* stream);
+/* fp32 NCHW -> activation-dtype NHWC (the `.to(gpu)` tensors of srgan.py:110-117 enter here) */
+int srgan_nchw_to_nhwc(const float* src, void* dst, int n, int c, int h, int w, int dtype, void* stream);
+/* activation-dtype NHWC -> fp32 NCHW (results handed back to reference-side code, e.g. Experiment.fake_features) */
+int srgan_nhwc_to_nchw(const void* src, float* dst, int n, int c, int h, int w, int dtype, void* stream);
+/* x_hat = alpha*u + (1-alpha)*fake, alpha per sample: srgan.py:362-366 */
+int srgan_interpolate(const void* u, const void* fake, const float* alpha, void* out, int n, long long per_sample,
+                      int dtype, void* stream);
+/* loss += scale * sum |pred-y|^order ; dpred = scale*order*|d|^(order-1)*sign(d): srgan.py:414-417 */
+int srgan_labeled_loss(const float* pred, const float* y, int n, int order, float scale, float* loss, float* dpred,
+                       void* stream);
+/* BCE-with-logits against a constant target: coefficient/dggan.py:39-40,48-49,62-63 */
+int srgan_bce_logits(const float* scores, int n, float target, float scale, float* loss, float* dscore, void* stream);
+/* feature_distance_loss on global feature sums: srgan.py:438-449 + utility.py:201-243.
+ * d = (sum_base - sum_other)*inv_B ; loss += mult*fn(d) ; gbase (+)= mult*inv_B*dfn/dd ; gother = -that.
+ * kind: 0 abs_mean 1 abs_mean_neg 2 abs_plus_one_sqrt_mean_neg 3 abs_plus_one_log_mean_neg 4 square_mean 5 norm_mean */
+int srgan_distance(const float* sum_base, const float* sum_other, int F, float inv_B, int kind, float mult,
+                   float* loss, float* gbase, float* gother, int accumulate_base, void* stream);
+/* s[r] = ||h[r,:]||_2 ; gamma[r,c] = h[r,c]/s[r] * act'(h[r,c]): seed of the gradient-penalty g-chain,
+ * interpolate_loss_calculation srgan.py:377-381 differentiated by hand */
+int srgan_feature_norm_seed(const void* h, int rows, int cols, float* s_out, void* gamma_out, int act, float slope,
+                            int dtype, void* stream);
+/* r = ||g0[n,:]||_2 ; penalty += lam_over_B*max(r-1,0)^2 ; gnorm_mean += inv_B*r ;
+ * u0 = 2*lam_over_B*max(r-1,0)/r * g0 : srgan.py:371-374 and the seed of its double-backward */
+int srgan_gradnorm_penalty(const void* g0, int n, long long per_sample, float lam_over_B, float inv_B, float* gnorm,
+                           float* penalty, float* gnorm_mean, void* u0, int dtype, void* stream);
+/* out = ((u - g<g,u>)/s) * act'(h), g = h/s : Jacobian of f/||f|| applied to the tangent */
+int srgan_gp_feature_seed(const void* uL, const void* hL, const float* s, void* out, int rows, int cols, int act,
+                          float slope, int dtype, void* stream);
+
+/* ---- optimizer ----------------------------------------------------------------------------------------------
+ * torch.optim.Adam.step (srgan.py:136-138,266,297,305) for one tensor, fused with the rewrite of its kernel-layout
+ * copies.  param/m/v: fp32, torch layout [d0,d1,d2,d3]; grad: fp32, element (i0..i3) at sum i_k*gstride[k];
+ * out1/out2 (may be NULL): activation-dtype (or fp32 when out_dtype == SRGAN_F32) copies at sum i_k*ostride[k].
+ * bc1 = 1-beta1^t, bc2 = 1-beta2^t.  L2 (coupled) weight decay like torch. */
+int srgan_adam(float* param, const float* grad, float* m, float* v, const int* dims4, const long long* gstrides4,
+               void* out1, const long long* o1strides4, void* out2, const long long* o2strides4, int out_dtype,
+               float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2, void* stream);
+/* layout copies only (initial weights / after load_models, srgan.py:221-251) */
+int srgan_repack(const float* param, const int* dims4, void* out1, const long long* o1strides4, void* out2,
+                 const long long* o2strides4, int out_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRGAN_B200_H */

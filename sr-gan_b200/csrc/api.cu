@@ -1,0 +1,98 @@
+// C ABI: library plumbing + dispatch of the dense contractions between the tcgen05 path and the SIMT path.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+std::atomic<long long> g_launches{0};
+static thread_local char t_err[512] = "";
+static thread_local int t_last_tensor = 0;
+static std::atomic<int> g_force_simt{0};
+
+void srgan_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+}
+
+// simt_conv.cu
+int simt_conv(int mode, const void* src, const void* W, void* out, int n, const srgan_geom* g, const float* bias,
+              int bias_mod, const void* href, int epi, int act, float slope, int dtype, cudaStream_t st);
+int simt_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, int dtype, cudaStream_t st);
+// umma_conv.cu : return 1 if the tensor-core path took the call, 0 if the shape is not eligible, <0 on error
+int umma_conv(int mode, const void* src, const void* W, void* out, int n, const srgan_geom* g, const float* bias,
+              int bias_mod, const void* href, int epi, int act, float slope, cudaStream_t st);
+int umma_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, cudaStream_t st);
+
+static int check_geom(const char* who, const srgan_geom* g, int n) {
+    if (!g || n < 0 || g->Hs <= 0 || g->Ws <= 0 || g->Ca <= 0 || g->Hl <= 0 || g->Wl <= 0 || g->Cb <= 0 || g->R <= 0 ||
+        g->S <= 0 || g->stride <= 0 || g->pad < 0) {
+        srgan_set_error("%s: bad geometry", who);
+        return SRGAN_ERR_ARG;
+    }
+    // every small-side position must read inside the padded large side: the pair is a valid strided conv
+    if ((g->Hs - 1) * g->stride - g->pad + g->R - 1 >= g->Hl + g->pad || (g->Ws - 1) * g->stride - g->pad + g->S - 1 >= g->Wl + g->pad) {
+        srgan_set_error("%s: small side %dx%d does not fit large side %dx%d (k%d s%d p%d)", who, g->Hs, g->Ws, g->Hl,
+                        g->Wl, g->R, g->stride, g->pad);
+        return SRGAN_ERR_ARG;
+    }
+    return SRGAN_OK;
+}
+
+extern "C" {
+
+int srgan_version(void) { return 100; }
+const char* srgan_last_error(void) { return t_err; }
+long long srgan_launch_count(void) { return g_launches.load(); }
+int srgan_last_path_tensor(void) { return t_last_tensor; }
+void srgan_set_force_simt(int on) { g_force_simt.store(on); }
+
+static int conv_common(int mode, const char* who, const void* src, const void* W, void* out, int n, const srgan_geom* g,
+                       const float* bias, int bias_mod, const void* href, int epi, int act, float slope, int dtype,
+                       void* stream) {
+    int rc = check_geom(who, g, n);
+    if (rc) return rc;
+    SRGAN_REQUIRE(src && W && out, "%s: null pointer", who);
+    SRGAN_REQUIRE(dtype == SRGAN_F32 || dtype == SRGAN_BF16, "%s: unknown dtype %d", who, dtype);
+    SRGAN_REQUIRE(epi == SRGAN_EPI_BIAS_ACT || epi == SRGAN_EPI_DACT, "%s: unknown epilogue %d", who, epi);
+    SRGAN_REQUIRE(act >= SRGAN_ACT_NONE && act <= SRGAN_ACT_TANH, "%s: unknown activation %d", who, act);
+    int ncols = mode == 0 ? g->Ca : g->Cb;
+    SRGAN_REQUIRE(bias_mod == 0 || ncols % bias_mod == 0, "%s: bias_mod does not divide the channel count", who);
+    if (n == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    t_last_tensor = 0;
+    if (dtype == SRGAN_BF16 && !g_force_simt.load()) {
+        int took = umma_conv(mode, src, W, out, n, g, bias, bias_mod, href, epi, act, slope, st);
+        if (took < 0) return took;
+        if (took == 1) { t_last_tensor = 1; return SRGAN_OK; }
+    }
+    return simt_conv(mode, src, W, out, n, g, bias, bias_mod, href, epi, act, slope, dtype, st);
+}
+
+int srgan_conv_down(const void* L, const void* Wd, void* S_out, int n, const srgan_geom* g, const float* bias,
+                    int bias_mod, const void* href, int epi, int act, float slope, int dtype, void* stream) {
+    return conv_common(0, "srgan_conv_down", L, Wd, S_out, n, g, bias, bias_mod, href, epi, act, slope, dtype, stream);
+}
+
+int srgan_conv_up(const void* S, const void* Wu, void* L_out, int n, const srgan_geom* g, const float* bias,
+                  int bias_mod, const void* href, int epi, int act, float slope, int dtype, void* stream) {
+    return conv_common(1, "srgan_conv_up", S, Wu, L_out, n, g, bias, bias_mod, href, epi, act, slope, dtype, stream);
+}
+
+int srgan_conv_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, int dtype, void* stream) {
+    int rc = check_geom("srgan_conv_wgrad", g, n);
+    if (rc) return rc;
+    SRGAN_REQUIRE(S && L && dW, "srgan_conv_wgrad: null pointer");
+    SRGAN_REQUIRE(dtype == SRGAN_F32 || dtype == SRGAN_BF16, "srgan_conv_wgrad: unknown dtype %d", dtype);
+    if (n == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    t_last_tensor = 0;
+    if (dtype == SRGAN_BF16 && !g_force_simt.load()) {
+        int took = umma_wgrad(S, L, dW, n, g, st);
+        if (took < 0) return took;
+        if (took == 1) { t_last_tensor = 1; return SRGAN_OK; }
+    }
+    return simt_wgrad(S, L, dW, n, g, dtype, st);
+}
+
+}  // extern "C"

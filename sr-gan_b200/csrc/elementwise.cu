@@ -1,0 +1,606 @@
+// Bandwidth-bound kernels of the SR-GAN step: feature column sums, distance losses, seeds, interpolation, gradient-norm
+// penalty, layout conversion, fused Adam.  All are coalesced / 128-bit vectorised where the shape allows, reduce with
+// warp shuffles, and size their grids from the SM count (148).  Reference lines: see include/srgan_b200.h.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------------------
+// colsum: out[c % mod] += sum_r rowscale[r] * X[r, c]
+// block = 32 column-lanes (4 columns each when VEC) x 8 row-lanes; grid.y splits the rows.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, long long rows, int cols,
+                                                     float* __restrict__ out, int mod,
+                                                     const float* __restrict__ rowscale) {
+    constexpr int CPT = VEC ? 4 : 1;
+    __shared__ float red[8][32 * CPT + 1];
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + lx) * CPT;
+    float acc[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) acc[j] = 0.f;
+    if (c < cols) {
+        for (long long r = (long long)blockIdx.y * 8 + ly; r < rows; r += 8LL * gridDim.y) {
+            float s = rowscale ? rowscale[r] : 1.f;
+            if (VEC) {
+                float4 v = ld4(X + r * cols + c);
+                acc[0] = fmaf(s, v.x, acc[0]); acc[1 % CPT] = fmaf(s, v.y, acc[1 % CPT]);
+                acc[2 % CPT] = fmaf(s, v.z, acc[2 % CPT]); acc[3 % CPT] = fmaf(s, v.w, acc[3 % CPT]);
+            } else {
+                acc[0] = fmaf(s, to_f(X[r * cols + c]), acc[0]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) red[ly][lx * CPT + j] = acc[j];
+    __syncthreads();
+    if (ly == 0 && c < cols) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int y = 0; y < 8; ++y) s += red[y][lx * CPT + j];
+            int oc = mod ? (c + j) % mod : (c + j);
+            atomicAdd(out + oc, s);
+        }
+    }
+}
+
+template <typename T>
+static int launch_colsum(const T* X, long long rows, int cols, float* out, int mod, const float* rowscale,
+                         cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return SRGAN_OK;
+    bool vec = (cols % 4 == 0);
+    int cpb = vec ? 128 : 32;
+    int gx = cdiv(cols, cpb);
+    long long want = (4LL * kNumSMs + gx - 1) / gx;
+    long long maxy = (rows + 31) / 32;                 // >= 4 rows per row-lane
+    long long gy = want < maxy ? want : maxy;
+    if (gy < 1) gy = 1;
+    if (gy > 65535) gy = 65535;
+    dim3 grid(gx, (unsigned)gy);
+    if (vec) colsum_kernel<T, true><<<grid, 256, 0, st>>>(X, rows, cols, out, mod, rowscale);
+    else colsum_kernel<T, false><<<grid, 256, 0, st>>>(X, rows, cols, out, mod, rowscale);
+    SRGAN_CHECK_LAUNCH("colsum_kernel");
+    return SRGAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// rowdot: out[r] = sum_c X[r,c]*w[c] + bias[idx]   (TPR threads per row)
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, int TPR>
+__global__ void __launch_bounds__(256) rowdot_kernel(const T* __restrict__ X, int rows, int cols,
+                                                     const float* __restrict__ w, const float* __restrict__ bias,
+                                                     int bias_index, float* __restrict__ out) {
+    __shared__ float red[32];
+    constexpr int RPB = 256 / TPR;
+    const int r = blockIdx.x * RPB + threadIdx.x / TPR;
+    const int t = threadIdx.x % TPR;
+    float acc = 0.f;
+    if (r < rows) {
+        const T* x = X + (long long)r * cols;
+        if (cols % 4 == 0) {
+            for (int c = t * 4; c < cols; c += TPR * 4) {
+                float4 v = ld4(x + c);
+                float4 ww = *reinterpret_cast<const float4*>(w + c);
+                acc += v.x * ww.x + v.y * ww.y + v.z * ww.z + v.w * ww.w;
+            }
+        } else {
+            for (int c = t; c < cols; c += TPR) acc = fmaf(to_f(x[c]), w[c], acc);
+        }
+    }
+    if (TPR == 32) {
+        acc = warp_sum(acc);
+        if (t == 0 && r < rows) out[r] = acc + bias[bias_index];
+    } else {
+        acc = block_sum(acc, red);
+        if (t == 0 && r < rows) out[r] = acc + bias[bias_index];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// seed_rows: out[r,c] = (gvec[c] + rowscale[r]*wrow[c]) * act'(href[r,c])
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) seed_rows_kernel(T* __restrict__ out, int rows, int cols,
+                                                        const float* __restrict__ gvec,
+                                                        const float* __restrict__ rowscale,
+                                                        const float* __restrict__ wrow, const T* __restrict__ href,
+                                                        int act, float slope) {
+    constexpr int V = VEC ? 4 : 1;
+    const long long total = (long long)rows * cols / V;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long e = i * V;
+        int r = (int)(e / cols), c = (int)(e - (long long)r * cols);
+        float rs = rowscale ? rowscale[r] : 0.f;
+        if (VEC) {
+            float4 h = ld4(href + e);
+            float4 g = gvec ? *reinterpret_cast<const float4*>(gvec + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rowscale) {
+                float4 w = *reinterpret_cast<const float4*>(wrow + c);
+                g.x = fmaf(rs, w.x, g.x); g.y = fmaf(rs, w.y, g.y); g.z = fmaf(rs, w.z, g.z); g.w = fmaf(rs, w.w, g.w);
+            }
+            g.x *= act_bwd(h.x, act, slope); g.y *= act_bwd(h.y, act, slope);
+            g.z *= act_bwd(h.z, act, slope); g.w *= act_bwd(h.w, act, slope);
+            st4(out + e, g);
+        } else {
+            float g = gvec ? gvec[c] : 0.f;
+            if (rowscale) g = fmaf(rs, wrow[c], g);
+            out[e] = from_f<T>(g * act_bwd(to_f(href[e]), act, slope));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// layout conversion
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int n,
+                                                           int c, long long hw) {
+    // one thread per (sample, pixel): reads are coalesced per channel plane, writes are c consecutive elements
+    const long long total = (long long)n * hw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long nn = i / hw, px = i - nn * hw;
+        const float* s = src + nn * c * hw + px;
+        T* d = dst + i * c;
+        for (int k = 0; k < c; ++k) d[k] = from_f<T>(s[(long long)k * hw]);
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int n,
+                                                           int c, long long hw) {
+    const long long total = (long long)n * hw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long nn = i / hw, px = i - nn * hw;
+        float* d = dst + nn * c * hw + px;
+        const T* s = src + i * c;
+        for (int k = 0; k < c; ++k) d[(long long)k * hw] = to_f(s[k]);
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ src, T* __restrict__ dst, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x)
+        dst[i] = from_f<T>(src[i]);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) uncast_kernel(const T* __restrict__ src, float* __restrict__ dst, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x)
+        dst[i] = to_f(src[i]);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// interpolate: out[n,e] = alpha[n]*u[n,e] + (1-alpha[n])*fake[n,e]
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) interpolate_kernel(const T* __restrict__ u, const T* __restrict__ f,
+                                                          const float* __restrict__ alpha, T* __restrict__ out,
+                                                          long long total, long long per_sample) {
+    constexpr int V = VEC ? 4 : 1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total / V;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long e = i * V;
+        float a = alpha[e / per_sample];
+        if (VEC) {
+            float4 x = ld4(u + e), y = ld4(f + e);
+            float b = 1.f - a;
+            st4(out + e, make_float4(a * x.x + b * y.x, a * x.y + b * y.y, a * x.z + b * y.z, a * x.w + b * y.w));
+        } else {
+            out[e] = from_f<T>(a * to_f(u[e]) + (1.f - a) * to_f(f[e]));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// scalar losses (single block)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) labeled_loss_kernel(const float* __restrict__ pred, const float* __restrict__ y,
+                                                           int n, int order, float scale, float* loss, float* dpred) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float d = pred[i] - y[i];
+        float ad = fabsf(d);
+        float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+        float pw, dpw;
+        if (order == 2) { pw = ad * ad; dpw = 2.f * ad; }
+        else if (order == 1) { pw = ad; dpw = 1.f; }
+        else { pw = powf(ad, (float)order); dpw = order * powf(ad, (float)(order - 1)); }
+        acc += pw;
+        dpred[i] = scale * dpw * sg;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(loss, scale * acc);
+}
+
+__global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict__ x, int n, float target, float scale,
+                                                         float* loss, float* dscore) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float v = x[i];
+        acc += fmaxf(v, 0.f) - v * target + log1pf(expf(-fabsf(v)));
+        dscore[i] = scale * (1.f / (1.f + expf(-v)) - target);
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(loss, scale * acc);
+}
+
+// feature_distance_loss on the global sums (single block of 1024 threads; F <= a few 10^4)
+__global__ void __launch_bounds__(1024) distance_kernel(const float* __restrict__ sb, const float* __restrict__ so, int F,
+                                                        float inv_B, int kind, float mult, float* loss, float* gbase,
+                                                        float* gother, int accumulate_base) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < F; i += blockDim.x) {
+        float d = (sb[i] - so[i]) * inv_B;
+        float ad = fabsf(d);
+        if (kind == 0) acc += ad;
+        else if (kind == 1) acc -= ad;
+        else if (kind == 2) acc -= sqrtf(ad + 1.f);
+        else if (kind == 3) acc -= logf(ad + 1.f);
+        else acc += d * d;                       // 4: square_mean, 5: norm_mean (sum of squares)
+    }
+    acc = block_sum(acc, red);
+    float nrm = 0.f, lossv;
+    if (kind == 5) { nrm = sqrtf(acc); lossv = nrm; }
+    else lossv = acc / (float)F;
+    if (threadIdx.x == 0) atomicAdd(loss, mult * lossv);
+    const float invF = 1.f / (float)F;
+    const float k = mult * inv_B;
+    for (int i = threadIdx.x; i < F; i += blockDim.x) {
+        float d = (sb[i] - so[i]) * inv_B;
+        float ad = fabsf(d);
+        float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+        float g;
+        if (kind == 0) g = sg * invF;
+        else if (kind == 1) g = -sg * invF;
+        else if (kind == 2) g = -sg * invF * 0.5f * rsqrtf(ad + 1.f);
+        else if (kind == 3) g = -sg * invF / (ad + 1.f);
+        else if (kind == 4) g = 2.f * d * invF;
+        else g = d / nrm;
+        g *= k;
+        if (accumulate_base) gbase[i] += g; else gbase[i] = g;
+        gother[i] = -g;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// gradient-penalty kernels (one block per sample / row)
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) feature_norm_seed_kernel(const T* __restrict__ h, int cols, float* __restrict__ s_out,
+                                                                T* __restrict__ gamma, int act, float slope) {
+    __shared__ float red[32];
+    const T* x = h + (long long)blockIdx.x * cols;
+    T* g = gamma + (long long)blockIdx.x * cols;
+    float acc = 0.f;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) { float v = to_f(x[c]); acc = fmaf(v, v, acc); }
+    acc = block_sum(acc, red);
+    float s = sqrtf(acc);
+    if (threadIdx.x == 0) s_out[blockIdx.x] = s;
+    float inv = 1.f / s;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+        float v = to_f(x[c]);
+        g[c] = from_f<T>(v * inv * act_bwd(v, act, slope));
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gp_feature_seed_kernel(const T* __restrict__ uL, const T* __restrict__ hL,
+                                                              const float* __restrict__ s, T* __restrict__ out, int cols,
+                                                              int act, float slope) {
+    __shared__ float red[32];
+    const T* u = uL + (long long)blockIdx.x * cols;
+    const T* h = hL + (long long)blockIdx.x * cols;
+    T* o = out + (long long)blockIdx.x * cols;
+    const float inv = 1.f / s[blockIdx.x];
+    float acc = 0.f;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) acc = fmaf(to_f(h[c]) * inv, to_f(u[c]), acc);
+    const float dot = block_sum(acc, red);
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+        float hv = to_f(h[c]);
+        float g = hv * inv;
+        o[c] = from_f<T>((to_f(u[c]) - g * dot) * inv * act_bwd(hv, act, slope));
+    }
+}
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(512) gradnorm_penalty_kernel(const T* __restrict__ g0, long long per_sample,
+                                                               float lam_over_B, float inv_B, float* __restrict__ gnorm,
+                                                               float* penalty, float* gnorm_mean, T* __restrict__ u0) {
+    __shared__ float red[32];
+    const T* g = g0 + (long long)blockIdx.x * per_sample;
+    T* u = u0 + (long long)blockIdx.x * per_sample;
+    float acc = 0.f;
+    if (VEC) {
+        for (long long e = (long long)threadIdx.x * 4; e < per_sample; e += (long long)blockDim.x * 4) {
+            float4 v = ld4(g + e);
+            acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+    } else {
+        for (long long e = threadIdx.x; e < per_sample; e += blockDim.x) { float v = to_f(g[e]); acc = fmaf(v, v, acc); }
+    }
+    acc = block_sum(acc, red);
+    const float r = sqrtf(acc);
+    const float ex = fmaxf(r - 1.f, 0.f);
+    if (threadIdx.x == 0) {
+        gnorm[blockIdx.x] = r;
+        atomicAdd(penalty, lam_over_B * ex * ex);
+        atomicAdd(gnorm_mean, inv_B * r);
+    }
+    const float coef = r > 0.f ? 2.f * lam_over_B * ex / r : 0.f;
+    if (VEC) {
+        for (long long e = (long long)threadIdx.x * 4; e < per_sample; e += (long long)blockDim.x * 4) {
+            float4 v = ld4(g + e);      // second pass hits L2 (per-sample slab <= 600 KB)
+            st4(u + e, make_float4(v.x * coef, v.y * coef, v.z * coef, v.w * coef));
+        }
+    } else {
+        for (long long e = threadIdx.x; e < per_sample; e += blockDim.x) u[e] = from_f<T>(to_f(g[e]) * coef);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Adam + kernel-layout rewrite
+// ------------------------------------------------------------------------------------------------------------
+struct Dims4 { int d[4]; long long gs[4], s1[4], s2[4]; };
+
+template <typename TO, bool UPDATE>
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ param, const float* __restrict__ grad,
+                                                   float* __restrict__ m, float* __restrict__ v, Dims4 dm,
+                                                   TO* __restrict__ out1, TO* __restrict__ out2, float step_size,
+                                                   float beta1, float beta2, float eps, float wd, float inv_sqrt_bc2) {
+    const long long total = (long long)dm.d[0] * dm.d[1] * dm.d[2] * dm.d[3];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long t = i;
+        int i3 = (int)(t % dm.d[3]); t /= dm.d[3];
+        int i2 = (int)(t % dm.d[2]); t /= dm.d[2];
+        int i1 = (int)(t % dm.d[1]); t /= dm.d[1];
+        int i0 = (int)t;
+        float p = param[i];
+        if (UPDATE) {
+            float g = grad[i0 * dm.gs[0] + i1 * dm.gs[1] + i2 * dm.gs[2] + i3 * dm.gs[3]];
+            if (wd != 0.f) g = fmaf(wd, p, g);
+            float mm = beta1 * m[i] + (1.f - beta1) * g;
+            float vv = beta2 * v[i] + (1.f - beta2) * g * g;
+            m[i] = mm; v[i] = vv;
+            float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
+            p = p - step_size * (mm / denom);
+            param[i] = p;
+        }
+        if (out1) out1[i0 * dm.s1[0] + i1 * dm.s1[1] + i2 * dm.s1[2] + i3 * dm.s1[3]] = from_f<TO>(p);
+        if (out2) out2[i0 * dm.s2[0] + i1 * dm.s2[1] + i2 * dm.s2[2] + i3 * dm.s2[3]] = from_f<TO>(p);
+    }
+}
+
+static inline int ew_grid(long long work_items, int block) {
+    long long b = (work_items + block - 1) / block;
+    long long cap = 16LL * kNumSMs;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// ============================================================================================================
+// C ABI
+// ============================================================================================================
+extern "C" {
+
+int srgan_colsum(const void* X, long long rows, int cols, float* out, int mod, const float* rowscale, int dtype,
+                 void* stream) {
+    SRGAN_REQUIRE(X && out && cols >= 0 && rows >= 0, "srgan_colsum: bad arguments");
+    SRGAN_REQUIRE(mod == 0 || cols % mod == 0, "srgan_colsum: cols %% mod != 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == SRGAN_F32) return launch_colsum<float>((const float*)X, rows, cols, out, mod, rowscale, st);
+    return launch_colsum<bf16>((const bf16*)X, rows, cols, out, mod, rowscale, st);
+}
+
+int srgan_rowdot(const void* X, int rows, int cols, const float* w, const float* bias, int bias_index, float* out,
+                 int dtype, void* stream) {
+    SRGAN_REQUIRE(X && w && bias && out && rows >= 0 && cols > 0, "srgan_rowdot: bad arguments");
+    if (rows == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cols >= 2048) {
+        if (dtype == SRGAN_F32) rowdot_kernel<float, 256><<<rows, 256, 0, st>>>((const float*)X, rows, cols, w, bias, bias_index, out);
+        else rowdot_kernel<bf16, 256><<<rows, 256, 0, st>>>((const bf16*)X, rows, cols, w, bias, bias_index, out);
+    } else {
+        int grid = cdiv(rows, 8);
+        if (dtype == SRGAN_F32) rowdot_kernel<float, 32><<<grid, 256, 0, st>>>((const float*)X, rows, cols, w, bias, bias_index, out);
+        else rowdot_kernel<bf16, 32><<<grid, 256, 0, st>>>((const bf16*)X, rows, cols, w, bias, bias_index, out);
+    }
+    SRGAN_CHECK_LAUNCH("rowdot_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_seed_rows(void* out, int rows, int cols, const float* gvec, const float* rowscale, const float* wrow,
+                    const void* href, int act, float slope, int dtype, void* stream) {
+    SRGAN_REQUIRE(out && href && rows >= 0 && cols > 0, "srgan_seed_rows: bad arguments");
+    SRGAN_REQUIRE((rowscale == nullptr) == (wrow == nullptr), "srgan_seed_rows: rowscale and wrow go together");
+    if (rows == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    bool vec = cols % 4 == 0;
+    long long items = (long long)rows * cols / (vec ? 4 : 1);
+    int grid = ew_grid(items, 256);
+    if (dtype == SRGAN_F32) {
+        if (vec) seed_rows_kernel<float, true><<<grid, 256, 0, st>>>((float*)out, rows, cols, gvec, rowscale, wrow, (const float*)href, act, slope);
+        else seed_rows_kernel<float, false><<<grid, 256, 0, st>>>((float*)out, rows, cols, gvec, rowscale, wrow, (const float*)href, act, slope);
+    } else {
+        if (vec) seed_rows_kernel<bf16, true><<<grid, 256, 0, st>>>((bf16*)out, rows, cols, gvec, rowscale, wrow, (const bf16*)href, act, slope);
+        else seed_rows_kernel<bf16, false><<<grid, 256, 0, st>>>((bf16*)out, rows, cols, gvec, rowscale, wrow, (const bf16*)href, act, slope);
+    }
+    SRGAN_CHECK_LAUNCH("seed_rows_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_nchw_to_nhwc(const float* src, void* dst, int n, int c, int h, int w, int dtype, void* stream) {
+    SRGAN_REQUIRE(src && dst && n >= 0 && c > 0 && h > 0 && w > 0, "srgan_nchw_to_nhwc: bad arguments");
+    if (n == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    long long hw = (long long)h * w;
+    if (hw == 1 || c == 1) {
+        long long total = (long long)n * c * hw;
+        if (dtype == SRGAN_F32) cast_kernel<float><<<ew_grid(total, 256), 256, 0, st>>>(src, (float*)dst, total);
+        else cast_kernel<bf16><<<ew_grid(total, 256), 256, 0, st>>>(src, (bf16*)dst, total);
+    } else {
+        long long total = (long long)n * hw;
+        if (dtype == SRGAN_F32) nchw_to_nhwc_kernel<float><<<ew_grid(total, 256), 256, 0, st>>>(src, (float*)dst, n, c, hw);
+        else nchw_to_nhwc_kernel<bf16><<<ew_grid(total, 256), 256, 0, st>>>(src, (bf16*)dst, n, c, hw);
+    }
+    SRGAN_CHECK_LAUNCH("nchw_to_nhwc_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_nhwc_to_nchw(const void* src, float* dst, int n, int c, int h, int w, int dtype, void* stream) {
+    SRGAN_REQUIRE(src && dst && n >= 0 && c > 0 && h > 0 && w > 0, "srgan_nhwc_to_nchw: bad arguments");
+    if (n == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    long long hw = (long long)h * w;
+    if (hw == 1 || c == 1) {
+        long long total = (long long)n * c * hw;
+        if (dtype == SRGAN_F32) uncast_kernel<float><<<ew_grid(total, 256), 256, 0, st>>>((const float*)src, dst, total);
+        else uncast_kernel<bf16><<<ew_grid(total, 256), 256, 0, st>>>((const bf16*)src, dst, total);
+    } else {
+        long long total = (long long)n * hw;
+        if (dtype == SRGAN_F32) nhwc_to_nchw_kernel<float><<<ew_grid(total, 256), 256, 0, st>>>((const float*)src, dst, n, c, hw);
+        else nhwc_to_nchw_kernel<bf16><<<ew_grid(total, 256), 256, 0, st>>>((const bf16*)src, dst, n, c, hw);
+    }
+    SRGAN_CHECK_LAUNCH("nhwc_to_nchw_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_interpolate(const void* u, const void* fake, const float* alpha, void* out, int n, long long per_sample,
+                      int dtype, void* stream) {
+    SRGAN_REQUIRE(u && fake && alpha && out && n >= 0 && per_sample > 0, "srgan_interpolate: bad arguments");
+    if (n == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    long long total = (long long)n * per_sample;
+    bool vec = per_sample % 4 == 0;
+    int grid = ew_grid(total / (vec ? 4 : 1), 256);
+    if (dtype == SRGAN_F32) {
+        if (vec) interpolate_kernel<float, true><<<grid, 256, 0, st>>>((const float*)u, (const float*)fake, alpha, (float*)out, total, per_sample);
+        else interpolate_kernel<float, false><<<grid, 256, 0, st>>>((const float*)u, (const float*)fake, alpha, (float*)out, total, per_sample);
+    } else {
+        if (vec) interpolate_kernel<bf16, true><<<grid, 256, 0, st>>>((const bf16*)u, (const bf16*)fake, alpha, (bf16*)out, total, per_sample);
+        else interpolate_kernel<bf16, false><<<grid, 256, 0, st>>>((const bf16*)u, (const bf16*)fake, alpha, (bf16*)out, total, per_sample);
+    }
+    SRGAN_CHECK_LAUNCH("interpolate_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_labeled_loss(const float* pred, const float* y, int n, int order, float scale, float* loss, float* dpred,
+                       void* stream) {
+    SRGAN_REQUIRE(pred && y && loss && dpred && n > 0 && order >= 1, "srgan_labeled_loss: bad arguments");
+    labeled_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pred, y, n, order, scale, loss, dpred);
+    SRGAN_CHECK_LAUNCH("labeled_loss_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_bce_logits(const float* scores, int n, float target, float scale, float* loss, float* dscore, void* stream) {
+    SRGAN_REQUIRE(scores && loss && dscore && n > 0, "srgan_bce_logits: bad arguments");
+    bce_logits_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(scores, n, target, scale, loss, dscore);
+    SRGAN_CHECK_LAUNCH("bce_logits_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_distance(const float* sum_base, const float* sum_other, int F, float inv_B, int kind, float mult,
+                   float* loss, float* gbase, float* gother, int accumulate_base, void* stream) {
+    SRGAN_REQUIRE(sum_base && sum_other && loss && gbase && gother && F > 0, "srgan_distance: bad arguments");
+    SRGAN_REQUIRE(kind >= 0 && kind <= 5, "srgan_distance: unknown distance kind %d", kind);
+    distance_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(sum_base, sum_other, F, inv_B, kind, mult, loss, gbase, gother,
+                                                          accumulate_base);
+    SRGAN_CHECK_LAUNCH("distance_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_feature_norm_seed(const void* h, int rows, int cols, float* s_out, void* gamma_out, int act, float slope,
+                            int dtype, void* stream) {
+    SRGAN_REQUIRE(h && s_out && gamma_out && rows >= 0 && cols > 0, "srgan_feature_norm_seed: bad arguments");
+    if (rows == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == SRGAN_F32) feature_norm_seed_kernel<float><<<rows, 256, 0, st>>>((const float*)h, cols, s_out, (float*)gamma_out, act, slope);
+    else feature_norm_seed_kernel<bf16><<<rows, 256, 0, st>>>((const bf16*)h, cols, s_out, (bf16*)gamma_out, act, slope);
+    SRGAN_CHECK_LAUNCH("feature_norm_seed_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_gp_feature_seed(const void* uL, const void* hL, const float* s, void* out, int rows, int cols, int act,
+                          float slope, int dtype, void* stream) {
+    SRGAN_REQUIRE(uL && hL && s && out && rows >= 0 && cols > 0, "srgan_gp_feature_seed: bad arguments");
+    if (rows == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == SRGAN_F32) gp_feature_seed_kernel<float><<<rows, 256, 0, st>>>((const float*)uL, (const float*)hL, s, (float*)out, cols, act, slope);
+    else gp_feature_seed_kernel<bf16><<<rows, 256, 0, st>>>((const bf16*)uL, (const bf16*)hL, s, (bf16*)out, cols, act, slope);
+    SRGAN_CHECK_LAUNCH("gp_feature_seed_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_gradnorm_penalty(const void* g0, int n, long long per_sample, float lam_over_B, float inv_B, float* gnorm,
+                           float* penalty, float* gnorm_mean, void* u0, int dtype, void* stream) {
+    SRGAN_REQUIRE(g0 && gnorm && penalty && gnorm_mean && u0 && n >= 0 && per_sample > 0,
+                  "srgan_gradnorm_penalty: bad arguments");
+    if (n == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    bool vec = per_sample % 4 == 0;
+    if (dtype == SRGAN_F32) {
+        if (vec) gradnorm_penalty_kernel<float, true><<<n, 512, 0, st>>>((const float*)g0, per_sample, lam_over_B, inv_B, gnorm, penalty, gnorm_mean, (float*)u0);
+        else gradnorm_penalty_kernel<float, false><<<n, 512, 0, st>>>((const float*)g0, per_sample, lam_over_B, inv_B, gnorm, penalty, gnorm_mean, (float*)u0);
+    } else {
+        if (vec) gradnorm_penalty_kernel<bf16, true><<<n, 512, 0, st>>>((const bf16*)g0, per_sample, lam_over_B, inv_B, gnorm, penalty, gnorm_mean, (bf16*)u0);
+        else gradnorm_penalty_kernel<bf16, false><<<n, 512, 0, st>>>((const bf16*)g0, per_sample, lam_over_B, inv_B, gnorm, penalty, gnorm_mean, (bf16*)u0);
+    }
+    SRGAN_CHECK_LAUNCH("gradnorm_penalty_kernel");
+    return SRGAN_OK;
+}
+
+static int fill_dims(Dims4& dm, const int* dims4, const long long* gs, const long long* s1, const long long* s2) {
+    for (int i = 0; i < 4; ++i) {
+        if (dims4[i] <= 0) return -1;
+        dm.d[i] = dims4[i];
+        dm.gs[i] = gs ? gs[i] : 0;
+        dm.s1[i] = s1 ? s1[i] : 0;
+        dm.s2[i] = s2 ? s2[i] : 0;
+    }
+    return 0;
+}
+
+int srgan_adam(float* param, const float* grad, float* m, float* v, const int* dims4, const long long* gstrides4,
+               void* out1, const long long* o1strides4, void* out2, const long long* o2strides4, int out_dtype,
+               float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2, void* stream) {
+    SRGAN_REQUIRE(param && grad && m && v && dims4 && gstrides4, "srgan_adam: bad arguments");
+    SRGAN_REQUIRE((out1 == nullptr) || o1strides4, "srgan_adam: out1 without strides");
+    SRGAN_REQUIRE((out2 == nullptr) || o2strides4, "srgan_adam: out2 without strides");
+    Dims4 dm;
+    SRGAN_REQUIRE(fill_dims(dm, dims4, gstrides4, o1strides4, o2strides4) == 0, "srgan_adam: non-positive dim");
+    long long total = (long long)dm.d[0] * dm.d[1] * dm.d[2] * dm.d[3];
+    cudaStream_t st = (cudaStream_t)stream;
+    float step_size = lr / bc1, isb = 1.f / sqrtf(bc2);
+    int grid = ew_grid(total, 256);
+    if (out_dtype == SRGAN_F32)
+        adam_kernel<float, true><<<grid, 256, 0, st>>>(param, grad, m, v, dm, (float*)out1, (float*)out2, step_size, beta1, beta2, eps, weight_decay, isb);
+    else
+        adam_kernel<bf16, true><<<grid, 256, 0, st>>>(param, grad, m, v, dm, (bf16*)out1, (bf16*)out2, step_size, beta1, beta2, eps, weight_decay, isb);
+    SRGAN_CHECK_LAUNCH("adam_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_repack(const float* param, const int* dims4, void* out1, const long long* o1strides4, void* out2,
+                 const long long* o2strides4, int out_dtype, void* stream) {
+    SRGAN_REQUIRE(param && dims4, "srgan_repack: bad arguments");
+    Dims4 dm;
+    SRGAN_REQUIRE(fill_dims(dm, dims4, nullptr, o1strides4, o2strides4) == 0, "srgan_repack: non-positive dim");
+    long long total = (long long)dm.d[0] * dm.d[1] * dm.d[2] * dm.d[3];
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = ew_grid(total, 256);
+    if (out_dtype == SRGAN_F32)
+        adam_kernel<float, false><<<grid, 256, 0, st>>>(const_cast<float*>(param), nullptr, nullptr, nullptr, dm, (float*)out1, (float*)out2, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
+    else
+        adam_kernel<bf16, false><<<grid, 256, 0, st>>>(const_cast<float*>(param), nullptr, nullptr, nullptr, dm, (bf16*)out1, (bf16*)out2, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
+    SRGAN_CHECK_LAUNCH("repack_kernel");
+    return SRGAN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,370 @@
+// SIMT (CUDA-core FMA, fp32 accumulate) implicit-GEMM kernels for the conv pair: down / up / wgrad.
+// They are (1) the fp32 parity mode of the SR-GAN step (1e-4 vs the reference, BASELINE.json north_star) and (2) the
+// path for shapes the tcgen05 kernels do not take (3-channel image layers, the 10-wide coefficient MLP, odd sizes).
+// Replaces cuDNN fprop/dgrad/wgrad + cuBLAS addmm behind age/models.py:44-52,68-80 and coefficient/models.py:22-72.
+#include "common.cuh"
+
+struct ConvP {
+    int n, Hs, Ws, Ca, Hl, Wl, Cb, R, S, stride, pad;
+};
+
+constexpr int BM = 128, BN = 64, BK = 16, NT = 256;
+
+// ------------------------------------------------------------------------------------------------------------
+// down / up :  out[m, c] = epilogue( sum_k A[m,k] * B[c,k] )
+//   down: m=(n,oh,ow) on the small side, c=a, k=(r,s,b):  A = L[n, oh*st-pad+r, ow*st-pad+s, b],  B = Wd[a][k]
+//   up  : per output phase (ih%st, iw%st) = blockIdx.z: m=(n,i,j), c=b, k=(tr,ts,a) over the taps that hit the
+//         phase:  A = S[n, i+qa-tr, j+qb-ts, a],  B = Wu[b][r0+st*tr][s0+st*ts][a]
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, int MODE, bool VEC>
+__global__ void __launch_bounds__(NT) conv_gemm_kernel(const T* __restrict__ src, const T* __restrict__ W,
+                                                       T* __restrict__ out, const float* __restrict__ bias, int bias_mod,
+                                                       const T* __restrict__ href, int epi, int act, float slope, ConvP p) {
+    __shared__ float As[2][BK][BM + 4];
+    __shared__ float Bs[2][BK][BN + 4];
+
+    const int tid = threadIdx.x;
+    // ---- problem view for this block
+    int M, N, K, Hm, Wm;           // Hm x Wm: the row grid (per sample)
+    int Cin;                       // channels per tap on the K axis
+    int r0 = 0, s0 = 0, qa = 0, qb = 0, Rt = p.R, St = p.S, pa = 0, pb = 0;
+    if (MODE == 0) {
+        Hm = p.Hs; Wm = p.Ws; N = p.Ca; Cin = p.Cb; K = p.R * p.S * p.Cb;
+    } else {
+        pa = blockIdx.z / p.stride; pb = blockIdx.z % p.stride;
+        Hm = (p.Hl - pa + p.stride - 1) / p.stride;
+        Wm = (p.Wl - pb + p.stride - 1) / p.stride;
+        r0 = (pa + p.pad) % p.stride; s0 = (pb + p.pad) % p.stride;
+        qa = (pa + p.pad - r0) / p.stride; qb = (pb + p.pad - s0) / p.stride;
+        Rt = r0 < p.R ? (p.R - r0 + p.stride - 1) / p.stride : 0;
+        St = s0 < p.S ? (p.S - s0 + p.stride - 1) / p.stride : 0;
+        N = p.Cb; Cin = p.Ca; K = Rt * St * p.Ca;
+    }
+    M = p.n * Hm * Wm;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    if (m0 >= M) return;
+
+    // ---- A loader: thread -> (row = tid/2, 8 consecutive k starting at (tid%2)*8)
+    const int a_row = tid >> 1, a_kq = (tid & 1) * 8;
+    const int am = m0 + a_row;
+    const bool a_ok = am < M;
+    int an = 0, ay = 0, ax = 0;
+    if (a_ok) { an = am / (Hm * Wm); int rem = am - an * Hm * Wm; ay = rem / Wm; ax = rem - ay * Wm; }
+    // ---- B loader: thread -> (col = tid/4, 4 consecutive k starting at (tid%4)*4)
+    const int b_col = tid >> 2, b_kq = (tid & 3) * 4;
+    const int bc = n0 + b_col;
+    const bool b_ok = bc < N;
+
+    auto a_addr = [&](int k, bool& valid) -> long long {      // element address of A[am, k]; k < K assumed
+        int tap = k / Cin, ch = k - tap * Cin;
+        int tr = tap / St, ts = tap - tr * St;
+        if (MODE == 0) {
+            int ih = ay * p.stride - p.pad + tr, iw = ax * p.stride - p.pad + ts;
+            valid = a_ok && ih >= 0 && ih < p.Hl && iw >= 0 && iw < p.Wl;
+            return (((long long)an * p.Hl + ih) * p.Wl + iw) * p.Cb + ch;
+        } else {
+            int oh = ay + qa - tr, ow = ax + qb - ts;
+            valid = a_ok && oh >= 0 && oh < p.Hs && ow >= 0 && ow < p.Ws;
+            return (((long long)an * p.Hs + oh) * p.Ws + ow) * p.Ca + ch;
+        }
+    };
+    auto b_addr = [&](int k) -> long long {
+        if (MODE == 0) return (long long)bc * K + k;
+        int tap = k / Cin, ch = k - tap * Cin;
+        int tr = tap / St, ts = tap - tr * St;
+        int r = r0 + p.stride * tr, s = s0 + p.stride * ts;
+        return (long long)bc * (p.R * p.S * p.Ca) + (long long)(r * p.S + s) * p.Ca + ch;
+    };
+
+    float4 ra[2], rb;
+    auto load_global = [&](int k0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int k = k0 + a_kq + h * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (VEC) {
+                if (k < K) { bool ok; long long ad = a_addr(k, ok); if (ok) v = ld4(src + ad); }
+            } else {
+                float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (k + e < K) { bool ok; long long ad = a_addr(k + e, ok); if (ok) t[e] = to_f(src[ad]); }
+                v = make_float4(t[0], t[1], t[2], t[3]);
+            }
+            ra[h] = v;
+        }
+        {
+            int k = k0 + b_kq;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b_ok) {
+                if (VEC) { if (k < K) v = ld4(W + b_addr(k)); }
+                else {
+                    float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) if (k + e < K) t[e] = to_f(W[b_addr(k + e)]);
+                    v = make_float4(t[0], t[1], t[2], t[3]);
+                }
+            }
+            rb = v;
+        }
+    };
+    auto store_smem = [&](int buf) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int kk = a_kq + h * 4;
+            As[buf][kk + 0][a_row] = ra[h].x; As[buf][kk + 1][a_row] = ra[h].y;
+            As[buf][kk + 2][a_row] = ra[h].z; As[buf][kk + 3][a_row] = ra[h].w;
+        }
+        Bs[buf][b_kq + 0][b_col] = rb.x; Bs[buf][b_kq + 1][b_col] = rb.y;
+        Bs[buf][b_kq + 2][b_col] = rb.z; Bs[buf][b_kq + 3][b_col] = rb.w;
+    };
+
+    const int tx = tid & 15, ty = tid >> 4;      // 16 x 16 threads, each 8 rows x 4 cols
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const int nk = (K + BK - 1) / BK;
+    if (nk > 0) { load_global(0); store_smem(0); }
+    __syncthreads();
+    for (int kc = 0; kc < nk; ++kc) {
+        const int cur = kc & 1;
+        if (kc + 1 < nk) load_global((kc + 1) * BK);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 8]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 8 + 4]);
+            float4 b = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
+            float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (kc + 1 < nk) store_smem(cur ^ 1);
+        __syncthreads();
+    }
+
+    // ---- epilogue
+    const int c0 = n0 + tx * 4;
+    if (c0 >= N) return;
+    const bool cvec = (N % 4 == 0);               // c0 % 4 == 0 always
+    float bv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (epi == SRGAN_EPI_BIAS_ACT && bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (c0 + j < N) bv[j] = bias[bias_mod ? (c0 + j) % bias_mod : (c0 + j)];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int m = m0 + ty * 8 + i;
+        if (m >= M) break;
+        long long o;
+        if (MODE == 0) {
+            o = (long long)m * N + c0;
+        } else {
+            int nn = m / (Hm * Wm); int rem = m - nn * Hm * Wm; int yy = rem / Wm, xx = rem - yy * Wm;
+            o = (((long long)nn * p.Hl + (yy * p.stride + pa)) * p.Wl + (xx * p.stride + pb)) * p.Cb + c0;
+        }
+        float v[4];
+        if (epi == SRGAN_EPI_BIAS_ACT) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = act_fwd(acc[i][j] + bv[j], act, slope);
+        } else {
+            if (href != nullptr && act != SRGAN_ACT_NONE) {
+                if (cvec) {
+                    float4 h = ld4(href + o);
+                    v[0] = acc[i][0] * act_bwd(h.x, act, slope); v[1] = acc[i][1] * act_bwd(h.y, act, slope);
+                    v[2] = acc[i][2] * act_bwd(h.z, act, slope); v[3] = acc[i][3] * act_bwd(h.w, act, slope);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        v[j] = (c0 + j < N) ? acc[i][j] * act_bwd(to_f(href[o + j]), act, slope) : 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = acc[i][j];
+            }
+        }
+        if (cvec) st4(out + o, make_float4(v[0], v[1], v[2], v[3]));
+        else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (c0 + j < N) out[o + j] = from_f<T>(v[j]);
+        }
+    }
+}
+
+template <typename T>
+static int launch_conv_gemm(int mode, const T* src, const T* W, T* out, int n, const srgan_geom* g, const float* bias,
+                            int bias_mod, const T* href, int epi, int act, float slope, cudaStream_t st) {
+    ConvP p{n, g->Hs, g->Ws, g->Ca, g->Hl, g->Wl, g->Cb, g->R, g->S, g->stride, g->pad};
+    int Cin = mode == 0 ? g->Cb : g->Ca;
+    bool vec = (Cin % 4 == 0);
+    dim3 grid;
+    if (mode == 0) {
+        long long M = (long long)n * g->Hs * g->Ws;
+        grid = dim3(cdiv(M, BM), cdiv(g->Ca, BN), 1);
+    } else {
+        int Hm = (g->Hl + g->stride - 1) / g->stride, Wm = (g->Wl + g->stride - 1) / g->stride;
+        long long M = (long long)n * Hm * Wm;
+        grid = dim3(cdiv(M, BM), cdiv(g->Cb, BN), g->stride * g->stride);
+    }
+    if (grid.x == 0 || grid.y == 0) return SRGAN_OK;
+    if (mode == 0) {
+        if (vec) conv_gemm_kernel<T, 0, true><<<grid, NT, 0, st>>>(src, W, out, bias, bias_mod, href, epi, act, slope, p);
+        else conv_gemm_kernel<T, 0, false><<<grid, NT, 0, st>>>(src, W, out, bias, bias_mod, href, epi, act, slope, p);
+    } else {
+        if (vec) conv_gemm_kernel<T, 1, true><<<grid, NT, 0, st>>>(src, W, out, bias, bias_mod, href, epi, act, slope, p);
+        else conv_gemm_kernel<T, 1, false><<<grid, NT, 0, st>>>(src, W, out, bias, bias_mod, href, epi, act, slope, p);
+    }
+    SRGAN_CHECK_LAUNCH("conv_gemm_kernel");
+    return SRGAN_OK;
+}
+
+int simt_conv(int mode, const void* src, const void* W, void* out, int n, const srgan_geom* g, const float* bias,
+              int bias_mod, const void* href, int epi, int act, float slope, int dtype, cudaStream_t st) {
+    if (dtype == SRGAN_F32)
+        return launch_conv_gemm<float>(mode, (const float*)src, (const float*)W, (float*)out, n, g, bias, bias_mod,
+                                       (const float*)href, epi, act, slope, st);
+    return launch_conv_gemm<bf16>(mode, (const bf16*)src, (const bf16*)W, (bf16*)out, n, g, bias, bias_mod,
+                                  (const bf16*)href, epi, act, slope, st);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// wgrad:  dW[a, (t,b)] += sum_{pixels p=(n,oh,ow)} S[p, a] * L[n, oh*st-pad+r, ow*st-pad+s, b]
+//   GEMM M = Ca, N = R*S*Cb, K = pixels; split over K across blockIdx.z, fp32 atomics into dW.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int WM = 64, WN = 64, WK = 16;
+
+template <typename T, bool VECA, bool VECB>
+__global__ void __launch_bounds__(NT) wgrad_kernel(const T* __restrict__ Ssrc, const T* __restrict__ Lsrc,
+                                                   float* __restrict__ dW, ConvP p, long long pix_per_split) {
+    __shared__ float As[2][WK][WM + 4];
+    __shared__ float Bs[2][WK][WN + 4];
+    const int tid = threadIdx.x;
+    const int M = p.Ca, N = p.R * p.S * p.Cb;
+    const long long P = (long long)p.n * p.Hs * p.Ws;
+    const int n0 = blockIdx.x * WN, m0 = blockIdx.y * WM;
+    const long long p_begin = (long long)blockIdx.z * pix_per_split;
+    long long p_end = p_begin + pix_per_split;
+    if (p_end > P) p_end = P;
+    if (p_begin >= p_end) return;
+
+    const int l_pix = tid >> 4, l_q = (tid & 15) * 4;     // thread -> (pixel within chunk, 4 consecutive a / cols)
+    // B column decode is k-invariant
+    const int col = n0 + l_q;
+    int tap = 0, cb = 0, tr = 0, ts = 0;
+    if (VECB) { if (col < N) { tap = col / p.Cb; cb = col - tap * p.Cb; tr = tap / p.S; ts = tap - tr * p.S; } }
+
+    float4 ra, rb;
+    auto load_global = [&](long long pk0) {
+        long long pp = pk0 + l_pix;
+        ra = make_float4(0.f, 0.f, 0.f, 0.f);
+        rb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pp >= p_end) return;
+        int a = m0 + l_q;
+        if (VECA) { if (a < M) ra = ld4(Ssrc + pp * p.Ca + a); }
+        else {
+            float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (a + e < M) t[e] = to_f(Ssrc[pp * p.Ca + a + e]);
+            ra = make_float4(t[0], t[1], t[2], t[3]);
+        }
+        int nn = (int)(pp / (p.Hs * p.Ws)); int rem = (int)(pp - (long long)nn * p.Hs * p.Ws);
+        int oh = rem / p.Ws, ow = rem - oh * p.Ws;
+        if (VECB) {
+            if (col < N) {
+                int ih = oh * p.stride - p.pad + tr, iw = ow * p.stride - p.pad + ts;
+                if (ih >= 0 && ih < p.Hl && iw >= 0 && iw < p.Wl)
+                    rb = ld4(Lsrc + (((long long)nn * p.Hl + ih) * p.Wl + iw) * p.Cb + cb);
+            }
+        } else {
+            float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                int c = col + e;
+                if (c < N) {
+                    int tp = c / p.Cb, b = c - tp * p.Cb, r = tp / p.S, s = tp - r * p.S;
+                    int ih = oh * p.stride - p.pad + r, iw = ow * p.stride - p.pad + s;
+                    if (ih >= 0 && ih < p.Hl && iw >= 0 && iw < p.Wl)
+                        t[e] = to_f(Lsrc[(((long long)nn * p.Hl + ih) * p.Wl + iw) * p.Cb + b]);
+                }
+            }
+            rb = make_float4(t[0], t[1], t[2], t[3]);
+        }
+    };
+    auto store_smem = [&](int buf) {
+        *reinterpret_cast<float4*>(&As[buf][l_pix][l_q]) = ra;
+        *reinterpret_cast<float4*>(&Bs[buf][l_pix][l_q]) = rb;
+    };
+
+    const int tx = tid & 15, ty = tid >> 4;       // each thread 4 (a) x 4 (cols)
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const long long nk = (p_end - p_begin + WK - 1) / WK;
+    load_global(p_begin); store_smem(0);
+    __syncthreads();
+    for (long long kc = 0; kc < nk; ++kc) {
+        const int cur = (int)(kc & 1);
+        if (kc + 1 < nk) load_global(p_begin + (kc + 1) * WK);
+#pragma unroll
+        for (int k = 0; k < WK; ++k) {
+            float4 a = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
+            float4 b = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
+            float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (kc + 1 < nk) store_smem(cur ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int a = m0 + ty * 4 + i;
+        if (a >= M) break;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int c = n0 + tx * 4 + j;
+            if (c < N) atomicAdd(dW + (long long)a * N + c, acc[i][j]);
+        }
+    }
+}
+
+template <typename T>
+static int launch_wgrad(const T* S, const T* L, float* dW, int n, const srgan_geom* g, cudaStream_t st) {
+    ConvP p{n, g->Hs, g->Ws, g->Ca, g->Hl, g->Wl, g->Cb, g->R, g->S, g->stride, g->pad};
+    const int M = g->Ca, N = g->R * g->S * g->Cb;
+    const long long P = (long long)n * g->Hs * g->Ws;
+    if (P == 0 || M == 0 || N == 0) return SRGAN_OK;
+    int tiles = cdiv(N, WN) * cdiv(M, WM);
+    long long want = (4LL * kNumSMs + tiles - 1) / tiles;          // ~4 CTAs per SM in total
+    long long max_splits = (P + 8 * WK - 1) / (8 * WK);            // at least 8 k-chunks per split
+    long long splits = want < max_splits ? want : max_splits;
+    if (splits < 1) splits = 1;
+    if (splits > 65535) splits = 65535;
+    long long pps = (P + splits - 1) / splits;
+    pps = (pps + WK - 1) / WK * WK;
+    splits = (P + pps - 1) / pps;
+    dim3 grid(cdiv(N, WN), cdiv(M, WM), (unsigned)splits);
+    bool va = (g->Ca % 4 == 0), vb = (g->Cb % 4 == 0);
+    if (va && vb) wgrad_kernel<T, true, true><<<grid, NT, 0, st>>>(S, L, dW, p, pps);
+    else if (va) wgrad_kernel<T, true, false><<<grid, NT, 0, st>>>(S, L, dW, p, pps);
+    else if (vb) wgrad_kernel<T, false, true><<<grid, NT, 0, st>>>(S, L, dW, p, pps);
+    else wgrad_kernel<T, false, false><<<grid, NT, 0, st>>>(S, L, dW, p, pps);
+    SRGAN_CHECK_LAUNCH("wgrad_kernel");
+    return SRGAN_OK;
+}
+
+int simt_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, int dtype, cudaStream_t st) {
+    if (dtype == SRGAN_F32) return launch_wgrad<float>((const float*)S, (const float*)L, dW, n, g, st);
+    return launch_wgrad<bf16>((const bf16*)S, (const bf16*)L, dW, n, g, st);
+}

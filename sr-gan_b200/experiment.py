@@ -1,0 +1,397 @@
+"""
+Host-side mirror of the reference's operator interface for the hot path.
+
+Two ways in, both with the reference's names, argument meaning and error behaviour:
+
+1. `B200StepMixin` -- mix into any reference `Experiment` subclass (coefficient / age / driving SR-GAN, coefficient
+   DG-GAN):  `class Fast(B200StepMixin, AgeExperiment): pass`.  It overrides only
+   `dnn_training_step(examples, labels, step)` (srgan.py:259-271) and
+   `gan_training_step(labeled_examples, labels, unlabeled_examples, step)` (srgan.py:273-320); `train`,
+   `training_loop`, `prepare_optimizers`, `save_models` / `load_models`, datasets and `run.py` stay the reference's.
+   The same nn.Parameter objects are updated in place and the torch.optim.Adam `state` is kept loadable.
+2. `Experiment` below -- a stand-alone mirror (this package's `Settings` + parameter containers with the reference's
+   `state_dict` keys) for machines without the reference checkout (the GPU box, bench.py, tests).
+
+Unsupported configurations raise (no silent fallback): `normalize_feature_norm=True` (srgan.py:447 bug, SURVEY
+App. E.1), distance callables not in utility.py:201-243, modules without a B200 path (nets.describe_module).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import nets
+from .engine import Engine, DIST_KINDS, SC_DNN, SC_LABELED, SC_UNLABELED, SC_FAKE, SC_GP, SC_GNORM, SC_GEN
+
+
+# ------------------------------------------------------------------------------------------------ utility.py mirror
+def abs_mean(tensor):
+    """utility.py:226-228."""
+    return tensor.abs().mean()
+
+
+def abs_mean_neg(tensor):
+    """utility.py:221-223."""
+    return tensor.abs().mean().neg()
+
+
+def abs_plus_one_sqrt_mean_neg(tensor):
+    """utility.py:216-218."""
+    return tensor.abs().add(1).sqrt().mean().neg()
+
+
+def abs_plus_one_log_mean_neg(tensor):
+    """utility.py:211-213."""
+    return tensor.abs().add(1).log().mean().neg()
+
+
+def square_mean(tensor):
+    """utility.py:241-243."""
+    return tensor.pow(2).mean()
+
+
+def norm_mean(tensor):
+    """utility.py:236-238."""
+    return tensor.pow(2).sum().pow(0.5)
+
+
+class Settings:
+    """settings.py:12-67 -- same attribute names and defaults (only the attributes the step reads plus the generic
+    ones; application/data attributes are carried verbatim when present on a reference Settings object)."""
+
+    def __init__(self):
+        self.trial_name = 'base'
+        self.steps_to_run = 200000
+        self.batch_size = 1000
+        self.summary_step_period = 2000
+        self.learning_rate = 1e-4
+        self.weight_decay = 0
+        self.labeled_loss_multiplier = 1e0
+        self.matching_loss_multiplier = 1e0
+        self.contrasting_loss_multiplier = 1e0
+        self.srgan_loss_multiplier = 1e0
+        self.dggan_loss_multiplier = 1e1
+        self.gradient_penalty_on = True
+        self.gradient_penalty_multiplier = 1e1
+        self.mean_offset = 0
+        self.labeled_loss_order = 2
+        self.generator_training_step_period = 1
+        self.normalize_fake_loss = False
+        self.normalize_feature_norm = False
+        self.contrasting_distance_function = abs_plus_one_sqrt_mean_neg
+        self.matching_distance_function = abs_mean
+        self.hidden_size = 10
+        self.map_multiplier = 1e-6
+        # new knobs (added attributes only, defaults = reference behaviour): SURVEY section 5
+        self.precision = 'fp32'          # 'fp32' (SIMT, 1e-4 parity) | 'bf16' (tcgen05 tensor cores, 2e-2 parity)
+
+
+class StepConfig:
+    """What engine.py needs from a (reference or mirror) settings object, validated."""
+
+    def __init__(self, settings, method: str):
+        if getattr(settings, 'normalize_feature_norm', False):
+            raise ValueError('normalize_feature_norm=True is not supported (reference bug at srgan.py:447)')
+        self.method = method
+        for k in ('learning_rate', 'weight_decay', 'labeled_loss_multiplier', 'matching_loss_multiplier',
+                  'contrasting_loss_multiplier', 'srgan_loss_multiplier', 'dggan_loss_multiplier',
+                  'gradient_penalty_multiplier'):
+            setattr(self, k, float(getattr(settings, k)))
+        self.labeled_loss_order = int(settings.labeled_loss_order)
+        self.generator_training_step_period = int(settings.generator_training_step_period)
+        self.mean_offset = float(getattr(settings, 'mean_offset', 0))
+        self.batch_size = int(settings.batch_size)
+        for k in ('matching_distance_function', 'contrasting_distance_function'):
+            fn = getattr(settings, k)
+            name = fn if isinstance(fn, str) else getattr(fn, '__name__', None)
+            if name not in DIST_KINDS:
+                raise ValueError(f'{k}={name!r}: only the scalar distance functions of utility.py:201-243 have a '
+                                 f'B200 path ({sorted(DIST_KINDS)})')
+            setattr(self, k, name)
+        self.betas = (0.9, 0.999)
+        self.eps = 1e-8
+
+
+# ------------------------------------------------------------------------------------------------ parameter containers
+def _seed_all(seed):
+    """utility.py:110-116 (the model constructors call seed_all(0): SURVEY App. E.6)."""
+    import random
+    import numpy as np
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+
+
+class _Container(nn.Module):
+    features = None
+
+    def forward(self, *a, **k):
+        raise NotImplementedError('parameter container: run the network through StepRunner.predict()/generate()')
+
+
+class CoefficientMLP(_Container):
+    """coefficient/models.py:31-50 (MLP) / :53-72 (DgganMLP when n_out=2): same state_dict keys."""
+
+    def __init__(self, hidden_size=10, n_out=1, n_in=50):
+        super().__init__()
+        _seed_all(0)
+        self.linear1 = nn.Linear(n_in, hidden_size)
+        self.linear2 = nn.Linear(hidden_size, hidden_size)
+        self.linear3 = nn.Linear(hidden_size, hidden_size)
+        self.linear4 = nn.Linear(hidden_size, n_out)
+
+
+class CoefficientGenerator(_Container):
+    """coefficient/models.py:12-28."""
+
+    def __init__(self, hidden_size=10, n_out=50):
+        super().__init__()
+        self.input_size = 10
+        self.linear1 = nn.Linear(self.input_size, hidden_size)
+        self.linear2 = nn.Linear(hidden_size, hidden_size)
+        self.linear3 = nn.Linear(hidden_size, hidden_size)
+        self.linear4 = nn.Linear(hidden_size, n_out)
+
+
+class DcganDiscriminator(_Container):
+    """age/models.py:55-80 == driving/models.py."""
+
+    def __init__(self, image_size=128, conv_dim=64, number_of_outputs=1):
+        super().__init__()
+        _seed_all(0)
+        c = conv_dim
+        self.layer1 = nn.Sequential(nn.Conv2d(3, c, 4, 2, 1))
+        self.layer2 = nn.Sequential(nn.Conv2d(c, c * 2, 4, 2, 1))
+        self.layer3 = nn.Sequential(nn.Conv2d(c * 2, c * 4, 4, 2, 1))
+        self.layer4 = nn.Sequential(nn.Conv2d(c * 4, c * 8, 4, 2, 1))
+        self.layer5 = nn.Sequential(nn.Conv2d(c * 8, number_of_outputs, image_size // 16, 1, 0))
+
+
+class DcganGenerator(_Container):
+    """age/models.py:32-52 (image_size=128) / crowd/models.py:127-147 DCGenerator (image_size=224)."""
+
+    def __init__(self, z_dim=256, image_size=128, conv_dim=64):
+        super().__init__()
+        _seed_all(0)
+        c = conv_dim
+        self.fc = nn.Sequential(nn.ConvTranspose2d(z_dim, c * 8, image_size // 16, 1, 0))
+        self.layer1 = nn.Sequential(nn.ConvTranspose2d(c * 8, c * 4, 4, 2, 1))
+        self.layer2 = nn.Sequential(nn.ConvTranspose2d(c * 4, c * 2, 4, 2, 1))
+        self.layer3 = nn.Sequential(nn.ConvTranspose2d(c * 2, c, 4, 2, 1))
+        self.layer4 = nn.Sequential(nn.ConvTranspose2d(c, 3, 4, 2, 1))
+        self.input_size = z_dim
+
+
+# ------------------------------------------------------------------------------------------------ the runner
+class StepRunner:
+    """Owns the Engine for one (D, G, DNN) triple and the bookkeeping that keeps torch-side objects coherent."""
+
+    def __init__(self, D: nn.Module, G: nn.Module, DNN: nn.Module, settings, method='srgan', precision=None,
+                 comm=None, device=None):
+        from .ops_cuda import CudaOps              # raises without CUDA / without the built library
+        precision = precision or getattr(settings, 'precision', 'fp32')
+        if precision not in ('fp32', 'bf16'):
+            raise ValueError(f'precision={precision!r}')
+        self.precision = precision
+        self.method = method
+        self.settings = settings
+        dev = device or next(D.parameters()).device
+        if dev.type != 'cuda':
+            raise RuntimeError('the B200 step needs the networks on a CUDA device (call gpu_mode() first)')
+        self.device = dev
+        self.modules = dict(D=D, G=G, DNN=DNN)
+        d_net, g_net = nets.describe_module(D), nets.describe_module(G)
+        if nets.describe_module(DNN) != d_net:
+            raise ValueError('DNN and D must share an architecture (srgan.py model_setup)')
+        if method == 'dggan' and d_net.head_outputs != 2:
+            raise ValueError('DG-GAN needs the two-output discriminator (coefficient/models.py:53-72)')
+
+        def pd(m):
+            return {k: p for k, p in m.named_parameters()}
+        self.engine = Engine(CudaOps(dev), d_net, g_net, pd(D), pd(G), pd(DNN),
+                             act_dtype=torch.float32 if precision == 'fp32' else torch.bfloat16, device=dev, comm=comm)
+        self.generator = torch.Generator(device=dev)
+        self.generator.manual_seed(0)
+
+    # ---- noise (srgan.py:286-289, :364, :301) drawn on the device
+    def draw_noise(self, B, cfg):
+        zdim = self.engine.g_net.input_chw[0]
+        g = self.generator
+        z = torch.randn(B, zdim, device=self.device, generator=g)
+        if cfg.mean_offset != 0:
+            sign = (torch.rand(B, zdim, device=self.device, generator=g) < 0.5).float() * 2 - 1
+            z = z + sign * cfg.mean_offset
+        alpha = torch.rand(B, device=self.device, generator=g)
+        z2 = torch.randn(B, zdim, device=self.device, generator=g)
+        return z, alpha, z2
+
+    def config(self):
+        return StepConfig(self.settings, self.method)
+
+    def dnn_step(self, examples, labels, lr=None, weight_decay=None):
+        cfg = self.config()
+        self.engine.dnn_step(examples, labels, cfg, cfg.learning_rate if lr is None else lr,
+                             cfg.weight_decay if weight_decay is None else weight_decay)
+
+    def gan_step(self, labeled_examples, labels, unlabeled_examples, step=0, noise=None):
+        cfg = self.config()
+        B = labeled_examples.shape[0]
+        z, alpha, z2 = noise if noise is not None else self.draw_noise(B, cfg)
+        self.engine.gan_step(labeled_examples, labels, unlabeled_examples, z, alpha, z2, cfg,
+                             train_generator=(step % cfg.generator_training_step_period == 0))
+
+    def scalars(self):
+        """One device->host read of the step's scalars (the .item() calls of srgan.py:268-270, 306-319)."""
+        s = self.engine.scalars
+        if self.engine.comm is not None:
+            s = s.clone()
+            self.engine.comm.all_reduce_sum_partial(s, (SC_DNN, SC_LABELED, SC_GP, SC_GNORM))
+        v = s.tolist()
+        return {'dnn_loss': v[SC_DNN], 'labeled_loss': v[SC_LABELED], 'unlabeled_loss': v[SC_UNLABELED],
+                'fake_loss': v[SC_FAKE], 'gradient_penalty': v[SC_GP], 'gradient_norm_mean': v[SC_GNORM],
+                'generator_loss': v[SC_GEN]}
+
+    # ---- forward-only helpers (D(x) / G(z) of the reference modules, on the kernels)
+    def predict(self, x, net='D'):
+        st = self.engine.D if net == 'D' else self.engine.DNN
+        pred, feats = self.engine.d_features(x, st)
+        return pred.clone(), self.features_nchw(feats, x.shape[0])
+
+    def features_nchw(self, feats_flat, B):
+        """`.features` in the reference's order: out.view(B, -1) of an NCHW tensor (age/models.py:74)."""
+        c, h, w = self.engine.d_net.feature_chw
+        out = torch.empty(B, c * h * w, device=self.device, dtype=torch.float32)
+        self.engine.ops.nhwc_to_nchw(feats_flat, out, B, c, h, w)
+        return out
+
+    def generate(self, z):
+        gnet = self.engine.g_net
+        out_l = gnet.layers[-1]
+        flat = self.engine.g_generate(z)
+        B = z.shape[0]
+        if gnet.family == 'coefficient':
+            out = torch.empty(B, out_l.out_ch, device=self.device, dtype=torch.float32)
+            self.engine.ops.nhwc_to_nchw(flat, out, B, out_l.out_ch, 1, 1)
+            return out
+        g = out_l.geom
+        out = torch.empty(B, g.Cb, g.Hl, g.Wl, device=self.device, dtype=torch.float32)
+        self.engine.ops.nhwc_to_nchw(flat, out, B, g.Cb, g.Hl, g.Wl)
+        return out
+
+    # ---- torch.optim.Adam state compatibility (checkpoints stay loadable)
+    def export_optimizer_state(self, optimizer, which: str):
+        st = {'D': self.engine.D, 'G': self.engine.G, 'DNN': self.engine.DNN}[which]
+        for name, p in self.modules[which].named_parameters():
+            if name not in st.slices:
+                continue
+            optimizer.state[p] = {'step': torch.tensor(float(st.adam_step)),
+                                  'exp_avg': st.m(name).view_as(p).clone(),
+                                  'exp_avg_sq': st.v(name).view_as(p).clone()}
+
+    def import_optimizer_state(self, optimizer, which: str):
+        st = {'D': self.engine.D, 'G': self.engine.G, 'DNN': self.engine.DNN}[which]
+        for name, p in self.modules[which].named_parameters():
+            s = optimizer.state.get(p)
+            if s and 'exp_avg' in s and name in st.slices:
+                st.m(name).copy_(s['exp_avg'].reshape(-1))
+                st.v(name).copy_(s['exp_avg_sq'].reshape(-1))
+                st.adam_step = int(float(s['step']))
+
+    def refresh_weights(self):
+        """Call after the nn.Parameters were changed from outside (load_state_dict)."""
+        for st in (self.engine.D, self.engine.G, self.engine.DNN):
+            self.engine.repack(st)
+
+
+# ------------------------------------------------------------------------------------------------ drop-in mix-in
+class B200StepMixin:
+    """Mix into a reference Experiment subclass; see module docstring."""
+    b200_precision: Optional[str] = None
+    b200_comm = None
+
+    def _b200_method(self):
+        return 'dggan' if 'Dggan' in type(self).__name__ else 'srgan'
+
+    def _b200_runner(self) -> StepRunner:
+        r = getattr(self, '_b200', None)
+        if r is None:
+            r = StepRunner(self.D, self.G, self.DNN, self.settings, self._b200_method(),
+                           precision=self.b200_precision, comm=self.b200_comm)
+            r.import_optimizer_state(self.d_optimizer, 'D')
+            r.import_optimizer_state(self.g_optimizer, 'G')
+            r.import_optimizer_state(self.dnn_optimizer, 'DNN')
+            self._b200 = r
+        return r
+
+    def dnn_training_step(self, examples, labels, step):
+        """srgan.py:259-271."""
+        r = self._b200_runner()
+        self.dnn_summary_writer.step = step
+        if isinstance(labels, (tuple, list)):
+            raise NotImplementedError('crowd (density, map) labels: KnnDenseNetCat has no B200 path yet')
+        group = self.dnn_optimizer.param_groups[0]                  # adjust_learning_rate (srgan.py:432-436) writes here
+        r.dnn_step(examples, labels, lr=group['lr'], weight_decay=group['weight_decay'])
+        if self.dnn_summary_writer.is_summary_step():
+            self.dnn_summary_writer.add_scalar('Discriminator/Labeled Loss', r.scalars()['dnn_loss'])
+
+    def gan_training_step(self, labeled_examples, labels, unlabeled_examples, step):
+        """srgan.py:273-320."""
+        r = self._b200_runner()
+        self.gan_summary_writer.step = step
+        if isinstance(labels, (tuple, list)):
+            raise NotImplementedError('crowd (density, map) labels: KnnDenseNetCat has no B200 path yet')
+        r.gan_step(labeled_examples, labels, unlabeled_examples, step, noise=getattr(self, '_b200_noise', None))
+        if self.gan_summary_writer.is_summary_step():
+            s = r.scalars()
+            w = self.gan_summary_writer
+            if step % self.settings.generator_training_step_period == 0:
+                w.add_scalar('Generator/Loss', s['generator_loss'])
+            w.add_scalar('Discriminator/Labeled Loss', s['labeled_loss'])
+            w.add_scalar('Discriminator/Unlabeled Loss', s['unlabeled_loss'])
+            w.add_scalar('Discriminator/Fake Loss', s['fake_loss'])
+            w.add_scalar('Discriminator/Gradient Penalty', s['gradient_penalty'])
+            w.add_scalar('Discriminator/Gradient Norm', s['gradient_norm_mean'])
+
+    def save_models(self, step):
+        """srgan.py:88-97 with the Adam moments exported into the torch optimizers first."""
+        r = getattr(self, '_b200', None)
+        if r is not None:
+            r.export_optimizer_state(self.d_optimizer, 'D')
+            r.export_optimizer_state(self.g_optimizer, 'G')
+            r.export_optimizer_state(self.dnn_optimizer, 'DNN')
+        super().save_models(step)
+
+
+class Experiment:
+    """Stand-alone mirror of the reference Experiment's step API (srgan.py:24-50, 259-320) for the supported model
+    families; `application` in {'coefficient', 'age', 'driving'}, `method` in {'srgan', 'dggan'}."""
+
+    def __init__(self, settings: Settings, application='age', method='srgan', device='cuda:0', comm=None, **model_kwargs):
+        self.settings = settings
+        dev = torch.device(device)
+        if application == 'coefficient':
+            n_out = 2 if method == 'dggan' else 1
+            self.D = CoefficientMLP(settings.hidden_size, n_out)
+            self.DNN = CoefficientMLP(settings.hidden_size, n_out)
+            self.G = CoefficientGenerator(settings.hidden_size)
+        elif application in ('age', 'driving'):
+            self.G = DcganGenerator(**{k: v for k, v in model_kwargs.items() if k in ('z_dim', 'image_size', 'conv_dim')})
+            dk = {k: v for k, v in model_kwargs.items() if k in ('image_size', 'conv_dim')}
+            self.D = DcganDiscriminator(**dk)
+            self.DNN = DcganDiscriminator(**dk)
+        else:
+            raise NotImplementedError(f'application {application!r}: no B200 path yet')
+        for m in (self.D, self.G, self.DNN):
+            m.to(dev)
+        self.runner = StepRunner(self.D, self.G, self.DNN, settings, method, comm=comm, device=dev)
+        self.gradient_norm = None
+
+    def dnn_training_step(self, examples, labels, step):
+        lr = self.settings.learning_rate * (0.1 ** (step // 100000))       # srgan.py:432-436
+        self.runner.dnn_step(examples, labels, lr=lr)
+
+    def gan_training_step(self, labeled_examples, labels, unlabeled_examples, step, noise=None):
+        self.runner.gan_step(labeled_examples, labels, unlabeled_examples, step, noise)

@@ -1,0 +1,228 @@
+"""
+ctypes binding of libsrgan_b200.so (include/srgan_b200.h): the ONLY ops implementation of the product.
+
+There is no CPU or PyTorch fallback: if the library is missing, cannot be loaded, or a tensor is not on a CUDA
+device, this raises.  torch is used only for device memory (data_ptr) and the current stream handle.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libsrgan_b200.so')
+
+SRGAN_F32, SRGAN_BF16 = 0, 1
+
+
+class Geom(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int) for k in ('Hs', 'Ws', 'Ca', 'Hl', 'Wl', 'Cb', 'R', 'S', 'stride', 'pad')]
+
+
+_EXPORTS = (
+    'srgan_version', 'srgan_last_error', 'srgan_launch_count', 'srgan_last_path_tensor', 'srgan_set_force_simt',
+    'srgan_conv_down', 'srgan_conv_up', 'srgan_conv_wgrad', 'srgan_colsum', 'srgan_rowdot', 'srgan_seed_rows',
+    'srgan_nchw_to_nhwc', 'srgan_nhwc_to_nchw', 'srgan_interpolate', 'srgan_labeled_loss', 'srgan_bce_logits',
+    'srgan_distance', 'srgan_feature_norm_seed', 'srgan_gradnorm_penalty', 'srgan_gp_feature_seed', 'srgan_adam',
+    'srgan_repack',
+)
+
+_lib = None
+
+
+def load_library(path: str = LIB_PATH):
+    """Loads the C-ABI library and declares the prototypes.  Raises if it is absent: build it with
+    `python sr-gan_b200/build.py` (or __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise RuntimeError(f'{path} not found: the CUDA library is required (no CPU fallback); run '
+                           '`python sr-gan_b200/build.py`')
+    lib = ctypes.CDLL(path)
+    for name in _EXPORTS:
+        if not hasattr(lib, name):
+            raise RuntimeError(f'{path} does not export {name}')
+    c_int, c_ll, c_f, vp = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p
+    gp = ctypes.POINTER(Geom)
+    lib.srgan_version.restype = c_int
+    lib.srgan_last_error.restype = ctypes.c_char_p
+    lib.srgan_launch_count.restype = c_ll
+    lib.srgan_last_path_tensor.restype = c_int
+    lib.srgan_set_force_simt.argtypes = [c_int]
+    lib.srgan_set_force_simt.restype = None
+    conv_args = [vp, vp, vp, c_int, gp, vp, c_int, vp, c_int, c_int, c_f, c_int, vp]
+    lib.srgan_conv_down.argtypes = conv_args
+    lib.srgan_conv_up.argtypes = conv_args
+    lib.srgan_conv_wgrad.argtypes = [vp, vp, vp, c_int, gp, c_int, vp]
+    lib.srgan_colsum.argtypes = [vp, c_ll, c_int, vp, c_int, vp, c_int, vp]
+    lib.srgan_rowdot.argtypes = [vp, c_int, c_int, vp, vp, c_int, vp, c_int, vp]
+    lib.srgan_seed_rows.argtypes = [vp, c_int, c_int, vp, vp, vp, vp, c_int, c_f, c_int, vp]
+    lib.srgan_nchw_to_nhwc.argtypes = [vp, vp, c_int, c_int, c_int, c_int, c_int, vp]
+    lib.srgan_nhwc_to_nchw.argtypes = [vp, vp, c_int, c_int, c_int, c_int, c_int, vp]
+    lib.srgan_interpolate.argtypes = [vp, vp, vp, vp, c_int, c_ll, c_int, vp]
+    lib.srgan_labeled_loss.argtypes = [vp, vp, c_int, c_int, c_f, vp, vp, vp]
+    lib.srgan_bce_logits.argtypes = [vp, c_int, c_f, c_f, vp, vp, vp]
+    lib.srgan_distance.argtypes = [vp, vp, c_int, c_f, c_int, c_f, vp, vp, vp, c_int, vp]
+    lib.srgan_feature_norm_seed.argtypes = [vp, c_int, c_int, vp, vp, c_int, c_f, c_int, vp]
+    lib.srgan_gradnorm_penalty.argtypes = [vp, c_int, c_ll, c_f, c_f, vp, vp, vp, vp, c_int, vp]
+    lib.srgan_gp_feature_seed.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, c_f, c_int, vp]
+    i4, l4 = ctypes.POINTER(c_int * 4), ctypes.POINTER(c_ll * 4)
+    lib.srgan_adam.argtypes = [vp, vp, vp, vp, i4, l4, vp, l4, vp, l4, c_int] + [c_f] * 7 + [vp]
+    lib.srgan_repack.argtypes = [vp, i4, vp, l4, vp, l4, c_int, vp]
+    for name in _EXPORTS[5:]:
+        getattr(lib, name).restype = c_int
+    _lib = lib
+    return lib
+
+
+def _dt(t: torch.dtype) -> int:
+    if t == torch.float32:
+        return SRGAN_F32
+    if t == torch.bfloat16:
+        return SRGAN_BF16
+    raise TypeError(f'unsupported activation dtype {t}')
+
+
+class CudaOps:
+    """The op set engine.py schedules, bound to the CUDA library.  Every tensor must live on the CUDA device."""
+
+    def __init__(self, device='cuda:0'):
+        if not torch.cuda.is_available():
+            raise RuntimeError('CudaOps needs a CUDA device; there is no CPU fallback for the SR-GAN hot path')
+        self.lib = load_library()
+        self.device = torch.device(device)
+        self._geoms = {}
+
+    # -------------------------------------------------------------- helpers
+    def _p(self, t, dtype=None):
+        if t is None:
+            return None
+        if not t.is_cuda:
+            raise RuntimeError('tensor is not on the CUDA device (no CPU fallback)')
+        if dtype is not None and t.dtype != dtype:
+            raise TypeError(f'expected {dtype}, got {t.dtype}')
+        return t.data_ptr()
+
+    def _stream(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def _geom(self, g):
+        c = self._geoms.get(g)
+        if c is None:
+            c = Geom(g.Hs, g.Ws, g.Ca, g.Hl, g.Wl, g.Cb, g.R, g.S, g.stride, g.pad)
+            self._geoms[g] = c
+        return ctypes.byref(c)
+
+    def _ck(self, rc, name):
+        if rc != 0:
+            raise RuntimeError(f'{name} failed ({rc}): {self.lib.srgan_last_error().decode()}')
+
+    @property
+    def launches(self):
+        return self.lib.srgan_launch_count()
+
+    # -------------------------------------------------------------- ops (signatures == tests/torch_ops.TorchOps)
+    def repack(self, w, dims, out1, s1, out2, s2):
+        f32 = torch.float32
+        od = out1.dtype if out1 is not None else out2.dtype
+        self._ck(self.lib.srgan_repack(self._p(w.detach(), f32), (ctypes.c_int * 4)(*dims), self._p(out1),
+                                       (ctypes.c_longlong * 4)(*s1) if s1 else None, self._p(out2),
+                                       (ctypes.c_longlong * 4)(*s2) if s2 else None, _dt(od), self._stream()),
+                 'srgan_repack')
+
+    def conv_down(self, L, Wd, S_out, n, g, bias, bias_mod, href, epi, act, slope):
+        self._ck(self.lib.srgan_conv_down(self._p(L), self._p(Wd, L.dtype), self._p(S_out, L.dtype), n, self._geom(g),
+                                          self._p(bias.detach(), torch.float32) if bias is not None else None, bias_mod,
+                                          self._p(href, L.dtype) if href is not None else None, epi, act, slope,
+                                          _dt(L.dtype), self._stream()), 'srgan_conv_down')
+
+    def conv_up(self, S, Wu, L_out, n, g, bias, bias_mod, href, epi, act, slope):
+        self._ck(self.lib.srgan_conv_up(self._p(S), self._p(Wu, S.dtype), self._p(L_out, S.dtype), n, self._geom(g),
+                                        self._p(bias.detach(), torch.float32) if bias is not None else None, bias_mod,
+                                        self._p(href, S.dtype) if href is not None else None, epi, act, slope,
+                                        _dt(S.dtype), self._stream()), 'srgan_conv_up')
+
+    def conv_wgrad(self, S, L, dW, n, g):
+        self._ck(self.lib.srgan_conv_wgrad(self._p(S), self._p(L, S.dtype), self._p(dW, torch.float32), n,
+                                           self._geom(g), _dt(S.dtype), self._stream()), 'srgan_conv_wgrad')
+
+    def colsum(self, X, rows, cols, out, mod, rowscale):
+        self._ck(self.lib.srgan_colsum(self._p(X), rows, cols, self._p(out, torch.float32), mod,
+                                       self._p(rowscale, torch.float32), _dt(X.dtype), self._stream()), 'srgan_colsum')
+
+    def rowdot(self, X, rows, cols, w, bias, bias_index, out):
+        self._ck(self.lib.srgan_rowdot(self._p(X), rows, cols, self._p(w, torch.float32),
+                                       self._p(bias.detach(), torch.float32), bias_index, self._p(out, torch.float32),
+                                       _dt(X.dtype), self._stream()), 'srgan_rowdot')
+
+    def seed_rows(self, out, rows, cols, gvec, rowscale, wrow, href, act, slope):
+        f32 = torch.float32
+        self._ck(self.lib.srgan_seed_rows(self._p(out), rows, cols, self._p(gvec, f32), self._p(rowscale, f32),
+                                          self._p(wrow, f32), self._p(href, out.dtype), act, slope, _dt(out.dtype),
+                                          self._stream()), 'srgan_seed_rows')
+
+    def nchw_to_nhwc(self, src, dst, n, c, h, w):
+        src = src.detach()
+        if src.dtype != torch.float32:
+            src = src.float()
+        self._ck(self.lib.srgan_nchw_to_nhwc(self._p(src), self._p(dst), n, c, h, w, _dt(dst.dtype), self._stream()),
+                 'srgan_nchw_to_nhwc')
+
+    def nhwc_to_nchw(self, src, dst, n, c, h, w):
+        self._ck(self.lib.srgan_nhwc_to_nchw(self._p(src), self._p(dst, torch.float32), n, c, h, w, _dt(src.dtype),
+                                             self._stream()), 'srgan_nhwc_to_nchw')
+
+    def interpolate(self, u, fake, alpha, out, n, E):
+        alpha = alpha.detach().reshape(-1)
+        self._ck(self.lib.srgan_interpolate(self._p(u), self._p(fake, u.dtype), self._p(alpha, torch.float32),
+                                            self._p(out, u.dtype), n, E, _dt(u.dtype), self._stream()),
+                 'srgan_interpolate')
+
+    def labeled_loss(self, pred, y, n, order, scale, loss_out, dpred):
+        f32 = torch.float32
+        y = y.detach()
+        if y.dtype != f32:
+            y = y.float()
+        self._ck(self.lib.srgan_labeled_loss(self._p(pred, f32), self._p(y.contiguous()), n, int(order), scale,
+                                             self._p(loss_out, f32), self._p(dpred, f32), self._stream()),
+                 'srgan_labeled_loss')
+
+    def bce_logits(self, scores, n, target, scale, loss_out, dscore):
+        f32 = torch.float32
+        self._ck(self.lib.srgan_bce_logits(self._p(scores, f32), n, target, scale, self._p(loss_out, f32),
+                                           self._p(dscore, f32), self._stream()), 'srgan_bce_logits')
+
+    def distance(self, sum_base, sum_other, F, inv_B, kind, mult, loss_out, gbase, gother, accumulate_base):
+        f32 = torch.float32
+        self._ck(self.lib.srgan_distance(self._p(sum_base, f32), self._p(sum_other, f32), F, inv_B, kind, mult,
+                                         self._p(loss_out, f32), self._p(gbase, f32), self._p(gother, f32),
+                                         int(bool(accumulate_base)), self._stream()), 'srgan_distance')
+
+    def feature_norm_seed(self, h, rows, cols, s_out, gamma_out, act, slope):
+        self._ck(self.lib.srgan_feature_norm_seed(self._p(h), rows, cols, self._p(s_out, torch.float32),
+                                                  self._p(gamma_out, h.dtype), act, slope, _dt(h.dtype),
+                                                  self._stream()), 'srgan_feature_norm_seed')
+
+    def gradnorm_penalty(self, g0, n, E, lam_over_B, inv_B, gnorm_out, pen_out, gnmean_out, u0_out):
+        f32 = torch.float32
+        self._ck(self.lib.srgan_gradnorm_penalty(self._p(g0), n, E, lam_over_B, inv_B, self._p(gnorm_out, f32),
+                                                 self._p(pen_out, f32), self._p(gnmean_out, f32),
+                                                 self._p(u0_out, g0.dtype), _dt(g0.dtype), self._stream()),
+                 'srgan_gradnorm_penalty')
+
+    def gp_feature_seed(self, uL, hL, s, out, rows, cols, act, slope):
+        self._ck(self.lib.srgan_gp_feature_seed(self._p(uL), self._p(hL, uL.dtype), self._p(s, torch.float32),
+                                                self._p(out, uL.dtype), rows, cols, act, slope, _dt(uL.dtype),
+                                                self._stream()), 'srgan_gp_feature_seed')
+
+    def adam(self, param, grad, m, v, dims, gstrides, out1, s1, out2, s2, lr, b1, b2, eps, wd, bc1, bc2):
+        f32 = torch.float32
+        od = out1.dtype if out1 is not None else (out2.dtype if out2 is not None else f32)
+        self._ck(self.lib.srgan_adam(self._p(param.detach(), f32), self._p(grad, f32), self._p(m, f32), self._p(v, f32),
+                                     (ctypes.c_int * 4)(*dims), (ctypes.c_longlong * 4)(*gstrides), self._p(out1),
+                                     (ctypes.c_longlong * 4)(*s1) if s1 else None, self._p(out2),
+                                     (ctypes.c_longlong * 4)(*s2) if s2 else None, _dt(od), lr, b1, b2, eps, wd, bc1,
+                                     bc2, self._stream()), 'srgan_adam')

@@ -1,0 +1,46 @@
+"""Helpers shared by the -m gpu tests, smoke() and bench.py: build the product StepRunner from an oracle state."""
+import torch
+
+import srgan_b200
+from oracle import srgan_oracle as O
+
+
+def settings_from_cfg(cfg: O.StepConfig, precision='fp32'):
+    s = srgan_b200.Settings()
+    for k in ('batch_size', 'learning_rate', 'weight_decay', 'labeled_loss_multiplier', 'matching_loss_multiplier',
+              'contrasting_loss_multiplier', 'srgan_loss_multiplier', 'dggan_loss_multiplier',
+              'gradient_penalty_multiplier', 'labeled_loss_order', 'generator_training_step_period'):
+        setattr(s, k, getattr(cfg, k))
+    s.matching_distance_function = getattr(srgan_b200, cfg.matching_distance_function)
+    s.contrasting_distance_function = getattr(srgan_b200, cfg.contrasting_distance_function)
+    s.precision = precision
+    return s
+
+
+def modules_from_state(st: O.OracleState, **dcgan_kwargs):
+    if st.d_spec.family == 'coefficient':
+        n_out = 2 if st.d_spec.dggan else 1
+        D, DNN, G = srgan_b200.CoefficientMLP(10, n_out), srgan_b200.CoefficientMLP(10, n_out), srgan_b200.CoefficientGenerator(10)
+    else:
+        z_dim, c8, k, _ = st.G['fc.0.weight'].shape
+        D = srgan_b200.DcganDiscriminator(k * 16, c8 // 8)
+        DNN = srgan_b200.DcganDiscriminator(k * 16, c8 // 8)
+        G = srgan_b200.DcganGenerator(z_dim, k * 16, c8 // 8)
+    D.load_state_dict({k: v.float() for k, v in st.D.items()})
+    G.load_state_dict({k: v.float() for k, v in st.G.items()})
+    DNN.load_state_dict({k: v.float() for k, v in st.DNN.items()})
+    return D.cuda(), G.cuda(), DNN.cuda()
+
+
+def runner_from_state(st: O.OracleState, cfg: O.StepConfig, precision='fp32', comm=None):
+    D, G, DNN = modules_from_state(st)
+    return srgan_b200.StepRunner(D, G, DNN, settings_from_cfg(cfg, precision), cfg.method, precision=precision, comm=comm)
+
+
+def to_cuda(*ts):
+    return tuple(t.cuda() for t in ts)
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)

@@ -1,0 +1,226 @@
+"""GPU: every C-ABI kernel against the op-level semantics in tests/torch_ops.py (plain PyTorch fp32 on CPU), fp32 and
+bf16 activations, shapes from the coefficient / DCGAN configs incl. ragged and non-vectorisable ones."""
+import pytest
+import torch
+
+from srgan_b200.nets import Geom
+from tests.torch_ops import TorchOps
+
+pytestmark = pytest.mark.gpu
+
+DT = [torch.float32, torch.bfloat16]
+
+
+def tol(dt):
+    return 2e-5 if dt == torch.float32 else 2e-2
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from srgan_b200.ops_cuda import CudaOps
+    return CudaOps()
+
+
+def rnd(gen, *shape, dt=torch.float32):
+    return (torch.rand(*shape, generator=gen) * 2 - 1).to(dt)
+
+
+def close(a, b, t, what=''):
+    a, b = a.float().cpu(), b.float().cpu()
+    err = (a - b).abs().max().item()
+    ref = b.abs().max().item() + 1e-12
+    assert err / ref < t, f'{what}: rel err {err / ref:.3e} (abs {err:.3e}, ref {ref:.3e})'
+
+
+GEOMS = [
+    Geom(1, 1, 10, 1, 1, 50, 1, 1, 1, 0),          # coefficient linear 50 -> 10
+    Geom(1, 1, 50, 1, 1, 10, 1, 1, 1, 0),          # coefficient generator 10 -> 50
+    Geom(16, 16, 8, 32, 32, 3, 4, 4, 2, 1),        # DCGAN layer1 (3 channels)
+    Geom(8, 8, 16, 16, 16, 8, 4, 4, 2, 1),         # small DCGAN layer
+    Geom(4, 4, 128, 8, 8, 64, 4, 4, 2, 1),         # tensor-core eligible channels
+    Geom(1, 1, 256, 1, 1, 64, 1, 1, 1, 0),         # fc as linear
+    Geom(5, 7, 12, 11, 15, 5, 3, 3, 2, 0),         # ragged, k3 s2 p0
+    Geom(6, 6, 8, 6, 6, 4, 3, 3, 1, 1),            # stride 1 same-pad
+]
+
+
+@pytest.mark.parametrize('dt', DT)
+@pytest.mark.parametrize('gi', range(len(GEOMS)))
+def test_conv_down_up_wgrad(ops, dt, gi):
+    g = GEOMS[gi]
+    gen = torch.Generator().manual_seed(gi)
+    n = 5
+    ref = TorchOps()
+    L = rnd(gen, n * g.Hl * g.Wl * g.Cb, dt=dt)
+    S = rnd(gen, n * g.Hs * g.Ws * g.Ca, dt=dt)
+    Wd = (rnd(gen, g.Ca * g.R * g.S * g.Cb) * 0.3).to(dt)
+    Wu = Wd.view(g.Ca, g.R, g.S, g.Cb).permute(3, 1, 2, 0).contiguous().view(-1)
+    bias_a, bias_b = rnd(gen, g.Ca), rnd(gen, g.Cb)
+    for epi, act, slope in ((0, 1, 0.05), (0, 2, 0.0), (0, 0, 0.0), (1, 1, 0.01), (1, 2, 0.0), (1, 0, 0.0)):
+        # down
+        href = rnd(gen, S.numel(), dt=dt)
+        out_ref = torch.empty_like(S)
+        ref.conv_down(L, Wd, out_ref, n, g, bias_a if epi == 0 else None, 0, href if epi == 1 else None, epi, act, slope)
+        out = torch.empty_like(S, device='cuda')
+        ops.conv_down(L.cuda(), Wd.cuda(), out, n, g, bias_a.cuda() if epi == 0 else None, 0,
+                      href.cuda() if epi == 1 else None, epi, act, slope)
+        close(out, out_ref, tol(dt), f'down epi{epi} act{act}')
+        # up
+        href = rnd(gen, L.numel(), dt=dt)
+        out_ref = torch.empty_like(L)
+        ref.conv_up(S, Wu, out_ref, n, g, bias_b if epi == 0 else None, 0, href if epi == 1 else None, epi, act, slope)
+        out = torch.empty_like(L, device='cuda')
+        ops.conv_up(S.cuda(), Wu.cuda(), out, n, g, bias_b.cuda() if epi == 0 else None, 0,
+                    href.cuda() if epi == 1 else None, epi, act, slope)
+        close(out, out_ref, tol(dt), f'up epi{epi} act{act}')
+    dW_ref = rnd(gen, Wd.numel())
+    dW = dW_ref.clone().cuda()
+    ref.conv_wgrad(S, L, dW_ref, n, g)
+    ops.conv_wgrad(S.cuda(), L.cuda(), dW, n, g)
+    close(dW, dW_ref, tol(dt) * 2, 'wgrad')
+
+
+@pytest.mark.parametrize('dt', DT)
+def test_bias_mod_epilogue(ops, dt):
+    g = Geom(1, 1, 4 * 4 * 8, 1, 1, 16, 1, 1, 1, 0)      # fc_up style: bias per channel, broadcast over 16 taps
+    gen = torch.Generator().manual_seed(3)
+    n = 6
+    L, Wd, bias = rnd(gen, n * 16, dt=dt), rnd(gen, g.Ca * 16, dt=dt), rnd(gen, 8)
+    ref_out = torch.empty(n * g.Ca, dtype=dt)
+    TorchOps().conv_down(L, Wd, ref_out, n, g, bias, 8, None, 0, 0, 0.0)
+    out = torch.empty(n * g.Ca, dtype=dt, device='cuda')
+    ops.conv_down(L.cuda(), Wd.cuda(), out, n, g, bias.cuda(), 8, None, 0, 0, 0.0)
+    close(out, ref_out, tol(dt), 'bias_mod')
+
+
+@pytest.mark.parametrize('dt', DT)
+@pytest.mark.parametrize('rows,cols,mod', [(100, 32768, 0), (64 * 64 * 7, 64, 0), (5000, 10, 0), (37, 1, 0),
+                                           (6, 128, 8), (1000, 50, 0)])
+def test_colsum_rowdot_seed(ops, dt, rows, cols, mod):
+    gen = torch.Generator().manual_seed(rows + cols)
+    ref = TorchOps()
+    X = rnd(gen, rows * cols, dt=dt)
+    rs = rnd(gen, rows)
+    for rowscale in (None, rs):
+        o_ref = rnd(gen, mod or cols)
+        o = o_ref.clone().cuda()
+        ref.colsum(X, rows, cols, o_ref, mod, rowscale)
+        ops.colsum(X.cuda(), rows, cols, o, mod, rowscale.cuda() if rowscale is not None else None)
+        close(o, o_ref, 1e-4 if dt == torch.float32 else 1e-2, 'colsum')
+    w, bias = rnd(gen, cols), rnd(gen, 2)
+    o_ref = torch.empty(rows)
+    o = torch.empty(rows, device='cuda')
+    ref.rowdot(X, rows, cols, w, bias, 1, o_ref)
+    ops.rowdot(X.cuda(), rows, cols, w.cuda(), bias.cuda(), 1, o)
+    close(o, o_ref, 1e-4 if dt == torch.float32 else 1e-2, 'rowdot')
+    gvec, wrow = rnd(gen, cols), rnd(gen, cols)
+    for gv, rsc in ((gvec, None), (None, rs), (gvec, rs)):
+        for act, slope in ((1, 0.05), (2, 0.0), (0, 0.0)):
+            o_ref = torch.empty(rows * cols, dtype=dt)
+            o = torch.empty(rows * cols, dtype=dt, device='cuda')
+            ref.seed_rows(o_ref, rows, cols, gv, rsc, wrow if rsc is not None else None, X, act, slope)
+            ops.seed_rows(o, rows, cols, gv.cuda() if gv is not None else None, rsc.cuda() if rsc is not None else None,
+                          wrow.cuda() if rsc is not None else None, X.cuda(), act, slope)
+            close(o, o_ref, tol(dt), 'seed_rows')
+
+
+@pytest.mark.parametrize('dt', DT)
+@pytest.mark.parametrize('n,c,h,w', [(4, 3, 32, 32), (7, 50, 1, 1), (3, 8, 5, 9), (2, 1, 6, 6)])
+def test_layout_and_interpolate(ops, dt, n, c, h, w):
+    gen = torch.Generator().manual_seed(n * c)
+    ref = TorchOps()
+    src = rnd(gen, n, c, h, w)
+    d_ref = torch.empty(n * c * h * w, dtype=dt)
+    d = torch.empty(n * c * h * w, dtype=dt, device='cuda')
+    ref.nchw_to_nhwc(src, d_ref, n, c, h, w)
+    ops.nchw_to_nhwc(src.cuda(), d, n, c, h, w)
+    close(d, d_ref, 1e-7, 'nchw_to_nhwc')
+    back = torch.empty(n, c, h, w, device='cuda')
+    ops.nhwc_to_nchw(d, back, n, c, h, w)
+    close(back, src.to(dt), 1e-7, 'nhwc_to_nchw')
+    E = c * h * w
+    u, f, alpha = rnd(gen, n * E, dt=dt), rnd(gen, n * E, dt=dt), torch.rand(n, generator=gen)
+    o_ref = torch.empty(n * E, dtype=dt)
+    o = torch.empty(n * E, dtype=dt, device='cuda')
+    ref.interpolate(u, f, alpha, o_ref, n, E)
+    ops.interpolate(u.cuda(), f.cuda(), alpha.cuda(), o, n, E)
+    close(o, o_ref, tol(dt), 'interpolate')
+
+
+def test_scalar_losses(ops):
+    gen = torch.Generator().manual_seed(5)
+    ref = TorchOps()
+    for n in (4, 100, 5000):
+        pred, y = rnd(gen, n) * 3, rnd(gen, n) * 3
+        for order in (1, 2, 3):
+            l_ref, d_ref = torch.zeros(1), torch.empty(n)
+            l, d = torch.zeros(1, device='cuda'), torch.empty(n, device='cuda')
+            ref.labeled_loss(pred, y, n, order, 0.37 / n, l_ref, d_ref)
+            ops.labeled_loss(pred.cuda(), y.cuda(), n, order, 0.37 / n, l, d)
+            close(l, l_ref, 1e-5, 'labeled loss'); close(d, d_ref, 1e-5, 'dpred')
+        for target in (0.0, 1.0):
+            l_ref, d_ref = torch.zeros(1), torch.empty(n)
+            l, d = torch.zeros(1, device='cuda'), torch.empty(n, device='cuda')
+            ref.bce_logits(pred * 4, n, target, 10.0 / n, l_ref, d_ref)
+            ops.bce_logits((pred * 4).cuda(), n, target, 10.0 / n, l, d)
+            close(l, l_ref, 1e-5, 'bce'); close(d, d_ref, 1e-5, 'dscore')
+    for F in (10, 80, 32768):
+        sb, so = rnd(gen, F) * 50, rnd(gen, F) * 50
+        for kind in range(6):
+            for acc in (False, True):
+                l_ref, gb_ref, go_ref = torch.zeros(1), rnd(gen, F), torch.empty(F)
+                l, gb, go = torch.zeros(1, device='cuda'), gb_ref.clone().cuda(), torch.empty(F, device='cuda')
+                ref.distance(sb, so, F, 1 / 100, kind, 7.0, l_ref, gb_ref, go_ref, acc)
+                ops.distance(sb.cuda(), so.cuda(), F, 1 / 100, kind, 7.0, l, gb, go, acc)
+                close(l, l_ref, 2e-5, f'distance {kind}'); close(gb, gb_ref, 2e-5, 'gbase'); close(go, go_ref, 2e-5, 'gother')
+
+
+@pytest.mark.parametrize('dt', DT)
+@pytest.mark.parametrize('rows,cols', [(100, 32768), (64, 10), (4, 256), (3, 150528)])
+def test_gradient_penalty_kernels(ops, dt, rows, cols):
+    gen = torch.Generator().manual_seed(cols)
+    ref = TorchOps()
+    h, u = rnd(gen, rows * cols, dt=dt), rnd(gen, rows * cols, dt=dt)
+    s_ref, gm_ref = torch.empty(rows), torch.empty(rows * cols, dtype=dt)
+    s, gm = torch.empty(rows, device='cuda'), torch.empty(rows * cols, dtype=dt, device='cuda')
+    ref.feature_norm_seed(h, rows, cols, s_ref, gm_ref, 1, 0.05)
+    ops.feature_norm_seed(h.cuda(), rows, cols, s, gm, 1, 0.05)
+    close(s, s_ref, 1e-4, 's'); close(gm, gm_ref, tol(dt), 'gamma')
+    o_ref = torch.empty(rows * cols, dtype=dt)
+    o = torch.empty(rows * cols, dtype=dt, device='cuda')
+    ref.gp_feature_seed(u, h, s_ref, o_ref, rows, cols, 1, 0.05)
+    ops.gp_feature_seed(u.cuda(), h.cuda(), s_ref.cuda(), o, rows, cols, 1, 0.05)
+    close(o, o_ref, tol(dt) * 2, 'gp_feature_seed')
+    g0 = (h.float() * (3.0 / cols ** 0.5)).to(dt)          # norms around 1.7: some rows above, none at 0
+    gn_ref, p_ref, m_ref, u0_ref = torch.empty(rows), torch.zeros(1), torch.zeros(1), torch.empty(rows * cols, dtype=dt)
+    gn, p, m, u0 = (torch.empty(rows, device='cuda'), torch.zeros(1, device='cuda'), torch.zeros(1, device='cuda'),
+                    torch.empty(rows * cols, dtype=dt, device='cuda'))
+    ref.gradnorm_penalty(g0, rows, cols, 100.0 / rows, 1.0 / rows, gn_ref, p_ref, m_ref, u0_ref)
+    ops.gradnorm_penalty(g0.cuda(), rows, cols, 100.0 / rows, 1.0 / rows, gn, p, m, u0)
+    close(gn, gn_ref, 1e-4, 'gnorm'); close(p, p_ref, 1e-3, 'penalty'); close(m, m_ref, 1e-4, 'gnorm mean')
+    close(u0, u0_ref, tol(dt) * 2, 'u0')
+
+
+def test_adam_and_repack(ops):
+    gen = torch.Generator().manual_seed(9)
+    ref = TorchOps()
+    dims = (6, 5, 4, 4)                      # master [a][b][r][s]
+    a, b, r, s = dims
+    wd_s, wu_s = (r * s * b, 1, s * b, b), (1, r * s * a, s * a, a)
+    n = a * b * r * s
+    for od in (torch.float32, torch.bfloat16):
+        p_ref = rnd(gen, *dims)
+        grad, m_ref, v_ref = rnd(gen, n), rnd(gen, n) * 0.1, rnd(gen, n).abs() * 0.01
+        o1_ref, o2_ref = torch.empty(n, dtype=od), torch.empty(n, dtype=od)
+        p, m, v = p_ref.clone().cuda(), m_ref.clone().cuda(), v_ref.clone().cuda()
+        o1, o2 = torch.empty(n, dtype=od, device='cuda'), torch.empty(n, dtype=od, device='cuda')
+        ref.repack(p_ref, dims, o1_ref, wd_s, o2_ref, wu_s)
+        ops.repack(p, dims, o1, wd_s, o2, wu_s)
+        close(o1, o1_ref, 1e-7, 'repack1'); close(o2, o2_ref, 1e-7, 'repack2')
+        for step in (1, 2):
+            bc1, bc2 = 1 - 0.9 ** step, 1 - 0.999 ** step
+            ref.adam(p_ref, grad, m_ref, v_ref, dims, wd_s, o1_ref, wd_s, o2_ref, wu_s, 1e-3, 0.9, 0.999, 1e-8, 1e-2, bc1, bc2)
+            ops.adam(p, grad.cuda(), m, v, dims, wd_s, o1, wd_s, o2, wu_s, 1e-3, 0.9, 0.999, 1e-8, 1e-2, bc1, bc2)
+            close(p, p_ref, 1e-6, 'adam p'); close(m, m_ref, 1e-6, 'adam m'); close(v, v_ref, 1e-6, 'adam v')
+            close(o1, o1_ref, 1e-6 if od == torch.float32 else 1e-2, 'adam out1')
+            close(o2, o2_ref, 1e-6 if od == torch.float32 else 1e-2, 'adam out2')
