@@ -119,7 +119,7 @@ class Engine:
         self.mdt = self.D.grad.dtype               # fp32 in the product; tests may run the schedule in fp64
         self.scalars = torch.zeros(N_SCALARS, dtype=self.mdt, device=self.device)
         self._buf = {}
-        self.launches = 0
+        self._probe = None
         for st in (self.D, self.G, self.DNN):
             if st is not None:
                 self.repack(st)
@@ -163,10 +163,34 @@ class Engine:
         act = l.act if act is None else act
         slope = l.slope if slope is None else slope
         b = st.params[l.name + '.bias'] if bias else None
+        pr = self._probe
+        timed = (pr is not None and st is self.D and l is pr['layer'] and n == pr['rows'] and epi == EPI_BIAS_ACT)
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         if l.fwd == 'down':
             self.ops.conv_down(x, st.wd_[l.name], y, n, l.geom, b, l.bias_mod, href, epi, act, slope)
         else:
             self.ops.conv_up(x, st.wu_[l.name], y, n, l.geom, b, l.bias_mod, href, epi, act, slope)
+        if timed:
+            e1.record()
+            pr['events'].append((e0, e1))
+
+    # ------------------------------------------------------------------ live kernel probe (bench.py roofline)
+    def probe_begin(self, layer_index, rows):
+        """Times, with CUDA events on the launch stream, every forward launch of D layer `layer_index` (1-based) over
+        `rows` samples until probe_end()."""
+        self._probe = {'layer': self.d_net.layers[layer_index - 1], 'rows': rows, 'events': []}
+
+    def probe_end(self):
+        pr, self._probe = self._probe, None
+        if not pr or not pr['events']:
+            return {'count': 0}
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in pr['events'])
+        l = pr['layer']
+        return {'count': len(pr['events']), 'ms': ms,
+                'kernel': f'D {l.name} forward conv ({l.geom.Cb}->{l.geom.Ca} k{l.geom.R} s{l.geom.stride}) over {pr["rows"]} samples'}
 
     def _bwd_data_layer(self, st: NetState, l: Layer, dy, dx, n, href, act, slope):
         """dx = (W_l^T dy) * act'(href)   (act = ACT_NONE: no mask)."""
