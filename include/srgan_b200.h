@@ -72,6 +72,16 @@ int srgan_conv_up(const void* S, const void* Wu, void* L_out, int n, const srgan
 /* dW (fp32, Wd layout) += wgrad(S, L) */
 int srgan_conv_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, int dtype, void* stream);
 
+/* Thin-layer lowering (image layers with <= 4 channels on the large side, age/models.py:48-51 layer4 of G and :61 layer1
+ * of D): col[p][k] = L[n, oh*stride-pad+r, ow*stride-pad+s, b], k = (r*S+s)*Cb + b, zero for k >= R*S*Cb (Kpad columns)
+ * and for the padding halo; p = (n, oh, ow) on the small side.  The contraction then runs as a [pixels x Kpad] GEMM on
+ * the tensor cores (srgan_conv_down / _up / _wgrad with a 1x1 geometry). */
+int srgan_im2col(const void* L, void* col, int n, const srgan_geom* g, int kpad, int dtype, void* stream);
+/* Inverse gather with the conv epilogue fused: L_out[n,ih,iw,b] = epilogue(sum over the taps (r,s) with
+ * ih = oh*stride-pad+r, iw = ow*stride-pad+s of col[(n,oh,ow)][(r*S+s)*Cb+b]); epilogue as in srgan_conv_up. */
+int srgan_col2im(const void* col, void* L_out, int n, const srgan_geom* g, int kpad, const float* bias, const void* href,
+                 int epi, int act, float slope, int dtype, void* stream);
+
 /* ---- reductions ---------------------------------------------------------------------------------------------
  * out[c % mod] += sum_r rowscale[r] * X[r,c]  (mod = 0: no folding; rowscale may be NULL).  Replaces
  * `features.mean(0)` (srgan.py:442-443, the division by the GLOBAL batch happens in srgan_distance) and the bias /

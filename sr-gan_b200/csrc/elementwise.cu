@@ -173,6 +173,74 @@ __global__ void __launch_bounds__(256) uncast_kernel(const T* __restrict__ src, 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// im2col / col2im for thin (<= 4 channel) image layers.  One thread per (small-side pixel, 8-element chunk of the
+// Kpad-wide row): eight 2-byte gathers (L1/L2 resident: the image is tiny next to the col buffer) and one 16-byte
+// coalesced store; col2im is one thread per large-side pixel gathering its <= ceil(R/st)*ceil(S/st) taps.
+// ------------------------------------------------------------------------------------------------------------
+struct ThinP { int n, Hs, Ws, Hl, Wl, Cb, R, S, stride, pad, kpad; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ L, T* __restrict__ col, ThinP p) {
+    const int cpr = p.kpad / 8;                                  // 8-element chunks per row
+    const long long total = (long long)p.n * p.Hs * p.Ws * cpr;
+    const int K = p.R * p.S * p.Cb;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long pix = i / cpr;
+        int j = (int)(i - pix * cpr);
+        int nn = (int)(pix / (p.Hs * p.Ws)); int rem = (int)(pix - (long long)nn * p.Hs * p.Ws);
+        int oh = rem / p.Ws, ow = rem - oh * p.Ws;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            int k = j * 8 + e;
+            float x = 0.f;
+            if (k < K) {
+                int tap = k / p.Cb, b = k - tap * p.Cb, r = tap / p.S, s = tap - r * p.S;
+                int ih = oh * p.stride - p.pad + r, iw = ow * p.stride - p.pad + s;
+                if (ih >= 0 && ih < p.Hl && iw >= 0 && iw < p.Wl)
+                    x = to_f(L[(((long long)nn * p.Hl + ih) * p.Wl + iw) * p.Cb + b]);
+            }
+            v[e] = x;
+        }
+        T* d = col + pix * p.kpad + j * 8;
+        st4(d, make_float4(v[0], v[1], v[2], v[3]));
+        st4(d + 4, make_float4(v[4], v[5], v[6], v[7]));
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) col2im_kernel(const T* __restrict__ col, T* __restrict__ out, ThinP p,
+                                                     const float* __restrict__ bias, const T* __restrict__ href, int epi,
+                                                     int act, float slope) {
+    const long long total = (long long)p.n * p.Hl * p.Wl;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int nn = (int)(i / (p.Hl * p.Wl)); int rem = (int)(i - (long long)nn * p.Hl * p.Wl);
+        int ih = rem / p.Wl, iw = rem - ih * p.Wl;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        // taps r with (ih + pad - r) % stride == 0
+        for (int r = (ih + p.pad) % p.stride; r < p.R; r += p.stride) {
+            int oh = (ih + p.pad - r) / p.stride;
+            if (oh < 0 || oh >= p.Hs) continue;
+            for (int s = (iw + p.pad) % p.stride; s < p.S; s += p.stride) {
+                int ow = (iw + p.pad - s) / p.stride;
+                if (ow < 0 || ow >= p.Ws) continue;
+                const T* c = col + (((long long)nn * p.Hs + oh) * p.Ws + ow) * p.kpad + (r * p.S + s) * p.Cb;
+                for (int b = 0; b < p.Cb; ++b) acc[b] += to_f(c[b]);
+            }
+        }
+        T* o = out + i * p.Cb;
+        for (int b = 0; b < p.Cb; ++b) {
+            float v = acc[b];
+            if (epi == SRGAN_EPI_BIAS_ACT) v = act_fwd(v + (bias ? bias[b] : 0.f), act, slope);
+            else if (href != nullptr && act != SRGAN_ACT_NONE) v *= act_bwd(to_f(href[i * p.Cb + b]), act, slope);
+            o[b] = from_f<T>(v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // interpolate: out[n,e] = alpha[n]*u[n,e] + (1-alpha[n])*fake[n,e]
 // ------------------------------------------------------------------------------------------------------------
 template <typename T, bool VEC>
@@ -469,6 +537,44 @@ int srgan_nhwc_to_nchw(const void* src, float* dst, int n, int c, int h, int w, 
         else nhwc_to_nchw_kernel<bf16><<<ew_grid(total, 256), 256, 0, st>>>((const bf16*)src, dst, n, c, hw);
     }
     SRGAN_CHECK_LAUNCH("nhwc_to_nchw_kernel");
+    return SRGAN_OK;
+}
+
+static int thin_params(ThinP& p, const char* who, int n, const srgan_geom* g, int kpad) {
+    if (!g || n < 0 || g->Cb < 1 || g->Cb > 4 || kpad % 8 != 0 || kpad < g->R * g->S * g->Cb) {
+        srgan_set_error("%s: needs 1 <= Cb <= 4 and kpad %% 8 == 0, kpad >= R*S*Cb", who);
+        return SRGAN_ERR_ARG;
+    }
+    p = ThinP{n, g->Hs, g->Ws, g->Hl, g->Wl, g->Cb, g->R, g->S, g->stride, g->pad, kpad};
+    return SRGAN_OK;
+}
+
+int srgan_im2col(const void* L, void* col, int n, const srgan_geom* g, int kpad, int dtype, void* stream) {
+    SRGAN_REQUIRE(L && col, "srgan_im2col: null pointer");
+    ThinP p;
+    int rc = thin_params(p, "srgan_im2col", n, g, kpad);
+    if (rc) return rc;
+    if (n == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    long long items = (long long)n * g->Hs * g->Ws * (kpad / 8);
+    if (dtype == SRGAN_F32) im2col_kernel<float><<<ew_grid(items, 256), 256, 0, st>>>((const float*)L, (float*)col, p);
+    else im2col_kernel<bf16><<<ew_grid(items, 256), 256, 0, st>>>((const bf16*)L, (bf16*)col, p);
+    SRGAN_CHECK_LAUNCH("im2col_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_col2im(const void* col, void* L_out, int n, const srgan_geom* g, int kpad, const float* bias, const void* href,
+                 int epi, int act, float slope, int dtype, void* stream) {
+    SRGAN_REQUIRE(col && L_out, "srgan_col2im: null pointer");
+    ThinP p;
+    int rc = thin_params(p, "srgan_col2im", n, g, kpad);
+    if (rc) return rc;
+    if (n == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    long long items = (long long)n * g->Hl * g->Wl;
+    if (dtype == SRGAN_F32) col2im_kernel<float><<<ew_grid(items, 256), 256, 0, st>>>((const float*)col, (float*)L_out, p, bias, (const float*)href, epi, act, slope);
+    else col2im_kernel<bf16><<<ew_grid(items, 256), 256, 0, st>>>((const bf16*)col, (bf16*)L_out, p, bias, (const bf16*)href, epi, act, slope);
+    SRGAN_CHECK_LAUNCH("col2im_kernel");
     return SRGAN_OK;
 }
 

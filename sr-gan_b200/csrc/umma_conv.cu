@@ -443,6 +443,7 @@ __global__ void __launch_bounds__(WG_THREADS) umma_wgrad_kernel(const __grid_con
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + k * BN + j * 32, v);
                     tmem_ld_wait();
+                    if (a >= p.Ca) continue;                  // zero-filled half tile (Ca = 64 mod 128)
                     float* dst = p.dW + (long long)a * rowN + (long long)(tap0 + k) * p.Cb + b0 + j * 32;
 #pragma unroll
                     for (int e = 0; e < 32; e += 4)
@@ -601,7 +602,7 @@ int umma_conv(int mode, const void* src, const void* W, void* out, int n, const 
 }
 
 int umma_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, cudaStream_t st) {
-    if (g->Ca % 128 != 0 || g->Cb % 64 != 0) return 0;
+    if (g->Ca % 64 != 0 || g->Cb % 64 != 0) return 0;   // Ca = 64 (mod 128): the upper half tile is TMA zero fill
     const int BN = g->Cb % 256 == 0 ? 256 : (g->Cb % 128 == 0 ? 128 : 64);
     const int taps = g->R * g->S;
     int NT = 512 / BN;
@@ -617,7 +618,7 @@ int umma_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom*
     p.tiles_w = g->Ws / p.TW; p.tiles_h = g->Hs / p.TH; p.tiles_n = (n + p.TN - 1) / p.TN;
     p.NT = NT; p.dW = dW;
     const int total_chunks = p.tiles_w * p.tiles_h * p.tiles_n;
-    const int out_tiles = (g->Ca / 128) * (taps / NT) * (g->Cb / BN);
+    const int out_tiles = ((g->Ca + 127) / 128) * (taps / NT) * (g->Cb / BN);
     int splits = (kNumSMs + out_tiles - 1) / out_tiles;
     int max_splits = (total_chunks + 3) / 4;                  // at least 4 stages of work per CTA
     if (splits > max_splits) splits = max_splits;

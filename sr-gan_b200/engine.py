@@ -52,17 +52,29 @@ def _strides_for(layer_kind: str, dims, Ca, Cb, R, S):
     return wd, wu
 
 
+KPAD = 64        # row width of the im2col buffer for thin (<= 4 channel) image layers: one 128-byte swizzle row in bf16
+
+
+def _thin_strides(Ca, Cb, R, S):
+    """Thin-layer lowering: master[a][b][r][s] -> Wd_pad[a][KPAD] (k = (r*S+s)*Cb + b) and Wu_pad[KPAD][a]."""
+    return (KPAD, 1, S * Cb, Cb), (1, Ca, S * Cb * Ca, Cb * Ca)
+
+
 class NetState:
     """Device-side state of one network: fp32 master parameters (the nn.Parameters themselves, updated in place),
     kernel-layout weight copies in the activation dtype, one flat fp32 gradient buffer, Adam moments."""
 
-    def __init__(self, net: Net, params: Dict[str, torch.Tensor], act_dtype, device):
+    def __init__(self, net: Net, params: Dict[str, torch.Tensor], act_dtype, device, tag='D', thin=False):
         self.net = net
         self.params = params
         self.act_dtype = act_dtype
         self.device = device
+        self.tag = tag                             # buffer namespace: D and DNN share 'D' (same shapes, sequential use)
+        self.thin = {l.name for l in net.layers if thin and l.thin_ok}
         n_total = 0
+        g_total = 0
         self.slices = {}
+        self.gslices = {}
         order = []
         for l in net.layers:
             order += [l.name + '.weight', l.name + '.bias']
@@ -77,23 +89,37 @@ class NetState:
             n = p.numel()
             self.slices[k] = (n_total, n)
             n_total += (n + 3) // 4 * 4            # keep every tensor 16-byte aligned inside the flat buffers
+            lname = k.rsplit('.', 1)[0]
+            gn = n
+            if k.endswith('.weight') and lname in self.thin:
+                gn = p.shape[0] * KPAD             # gradient in the padded Wd_pad layout [a][KPAD]
+            self.gslices[k] = (g_total, gn)
+            g_total += (gn + 3) // 4 * 4
         self.order = order
         mdt = params[order[0]].dtype
-        self.grad = torch.zeros(n_total, dtype=mdt, device=device)
+        self.grad = torch.zeros(g_total, dtype=mdt, device=device)
         self.exp_avg = torch.zeros(n_total, dtype=mdt, device=device)
         self.exp_avg_sq = torch.zeros(n_total, dtype=mdt, device=device)
         self.adam_step = 0
         self.wd_, self.wu_ = {}, {}
         for l in net.layers:
             n = params[l.name + '.weight'].numel()
-            self.wd_[l.name] = torch.empty(n, dtype=act_dtype, device=device)
-            self.wu_[l.name] = torch.empty(n, dtype=act_dtype, device=device)
+            if l.name in self.thin:
+                n = l.geom.Ca * KPAD               # padded copies; the pad columns / rows stay zero
+            self.wd_[l.name] = torch.zeros(n, dtype=act_dtype, device=device)
+            self.wu_[l.name] = torch.zeros(n, dtype=act_dtype, device=device)
         if net.head:
             self.whead = torch.empty(net.head_outputs * net.feature_size, dtype=mdt, device=device)
 
     def g(self, key):
-        o, n = self.slices[key]
+        o, n = self.gslices[key]
         return self.grad[o:o + n]
+
+    def strides(self, l: Layer):
+        g = l.geom
+        if l.name in self.thin:
+            return _thin_strides(g.Ca, g.Cb, g.R, g.S)
+        return _strides_for(l.master_kind, l.master_dims, g.Ca, g.Cb, g.R, g.S)
 
     def m(self, key):
         o, n = self.slices[key]
@@ -107,15 +133,18 @@ class NetState:
 class Engine:
     def __init__(self, ops, d_net: Net, g_net: Optional[Net], D: Dict[str, torch.Tensor],
                  G: Optional[Dict[str, torch.Tensor]], DNN: Optional[Dict[str, torch.Tensor]],
-                 act_dtype=torch.float32, device='cuda', comm=None):
+                 act_dtype=torch.float32, device='cuda', comm=None, thin_lowering=None):
         self.ops = ops
         self.device = torch.device(device)
         self.act_dtype = act_dtype
         self.comm = comm                           # dist.Comm or None (single rank)
         self.d_net, self.g_net = d_net, g_net
-        self.D = NetState(d_net, D, act_dtype, self.device)
-        self.G = NetState(g_net, G, act_dtype, self.device) if g_net is not None else None
-        self.DNN = NetState(d_net, DNN, act_dtype, self.device) if DNN is not None else None
+        # thin-layer lowering (3-channel image layers -> im2col/col2im + [pixels x 64] GEMM on the tensor cores):
+        # on by default in the bf16 tensor-core mode, off in the fp32 SIMT parity mode
+        self.thin = (act_dtype == torch.bfloat16) if thin_lowering is None else bool(thin_lowering)
+        self.D = NetState(d_net, D, act_dtype, self.device, 'D', self.thin)
+        self.G = NetState(g_net, G, act_dtype, self.device, 'G', self.thin) if g_net is not None else None
+        self.DNN = NetState(d_net, DNN, act_dtype, self.device, 'D', self.thin) if DNN is not None else None
         self.mdt = self.D.grad.dtype               # fp32 in the product; tests may run the schedule in fp64
         self.scalars = torch.zeros(N_SCALARS, dtype=self.mdt, device=self.device)
         self._buf = {}
@@ -141,8 +170,7 @@ class Engine:
         """Master (torch layout, fp32) -> kernel layouts.  Also done by the fused Adam after every update."""
         for l in st.net.layers:
             w = st.params[l.name + '.weight']
-            g = l.geom
-            wd_s, wu_s = _strides_for(l.master_kind, l.master_dims, g.Ca, g.Cb, g.R, g.S)
+            wd_s, wu_s = st.strides(l)
             self.ops.repack(w, l.master_dims, st.wd_[l.name], wd_s, st.wu_[l.name], wu_s)
         if st.net.head:
             self._repack_head(st)
@@ -159,7 +187,20 @@ class Engine:
         self.ops.repack(st.params[st.net.head + '.weight'], dims, st.whead, s, None, None)
 
     # ------------------------------------------------------------------ layer ops
-    def _fwd_layer(self, st: NetState, l: Layer, x, y, n, bias=True, href=None, epi=EPI_BIAS_ACT, act=None, slope=None):
+    def _lin(self, l: Layer):
+        """The [pixels x KPAD] GEMM a thin layer runs as: small side = [pix, Ca], large side = col [pix, KPAD]."""
+        from .nets import Geom
+        return Geom(1, 1, l.geom.Ca, 1, 1, KPAD, 1, 1, 1, 0)
+
+    def _col(self, st: NetState, l: Layer, lo, n):
+        P = l.geom.Hs * l.geom.Ws
+        return self._buf[('col', st.tag, l.name)][lo * P * KPAD:(lo + n) * P * KPAD]
+
+    def _coltmp(self, l: Layer, n):
+        return self.buf(('coltmp',), (n * l.geom.Hs * l.geom.Ws * KPAD,))
+
+    def _fwd_layer(self, st: NetState, l: Layer, x, y, n, bias=True, href=None, epi=EPI_BIAS_ACT, act=None, slope=None,
+                   lo=0):
         act = l.act if act is None else act
         slope = l.slope if slope is None else slope
         b = st.params[l.name + '.bias'] if bias else None
@@ -168,7 +209,17 @@ class Engine:
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        if l.fwd == 'down':
+        if l.name in st.thin:
+            P = l.geom.Hs * l.geom.Ws
+            if l.fwd == 'down':      # im2col (kept for the weight gradient) -> GEMM with the layer's epilogue
+                col = self._col(st, l, lo, n)
+                self.ops.im2col(x, col, n, l.geom, KPAD)
+                self.ops.conv_down(col, st.wd_[l.name], y, n * P, self._lin(l), b, 0, href, epi, act, slope)
+            else:                    # GEMM -> col2im with the layer's epilogue
+                ycol = self._coltmp(l, n)
+                self.ops.conv_up(x, st.wu_[l.name], ycol, n * P, self._lin(l), None, 0, None, EPI_DACT, ACT_NONE, 0.0)
+                self.ops.col2im(ycol, y, n, l.geom, KPAD, b, href, epi, act, slope)
+        elif l.fwd == 'down':
             self.ops.conv_down(x, st.wd_[l.name], y, n, l.geom, b, l.bias_mod, href, epi, act, slope)
         else:
             self.ops.conv_up(x, st.wu_[l.name], y, n, l.geom, b, l.bias_mod, href, epi, act, slope)
@@ -192,16 +243,35 @@ class Engine:
         return {'count': len(pr['events']), 'ms': ms,
                 'kernel': f'D {l.name} forward conv ({l.geom.Cb}->{l.geom.Ca} k{l.geom.R} s{l.geom.stride}) over {pr["rows"]} samples'}
 
-    def _bwd_data_layer(self, st: NetState, l: Layer, dy, dx, n, href, act, slope):
+    def _bwd_data_layer(self, st: NetState, l: Layer, dy, dx, n, href, act, slope, lo=0, col_ready=False):
         """dx = (W_l^T dy) * act'(href)   (act = ACT_NONE: no mask)."""
-        if l.fwd == 'down':
+        if l.name in st.thin:
+            P = l.geom.Hs * l.geom.Ws
+            if l.fwd == 'down':      # transpose of (im2col -> GEMM): GEMM^T -> col2im with the mask fused
+                colg = self._coltmp(l, n)
+                self.ops.conv_up(dy, st.wu_[l.name], colg, n * P, self._lin(l), None, 0, None, EPI_DACT, ACT_NONE, 0.0)
+                self.ops.col2im(colg, dx, n, l.geom, KPAD, None, href, EPI_DACT, act, slope)
+            else:                    # transpose of (GEMM -> col2im): im2col -> GEMM^T
+                col = self._col(st, l, lo, n)
+                if not col_ready:
+                    self.ops.im2col(dy, col, n, l.geom, KPAD)
+                self.ops.conv_down(col, st.wd_[l.name], dx, n * P, self._lin(l), None, 0, href, EPI_DACT, act, slope)
+        elif l.fwd == 'down':
             self.ops.conv_up(dy, st.wu_[l.name], dx, n, l.geom, None, 0, href, EPI_DACT, act, slope)
         else:
             self.ops.conv_down(dy, st.wd_[l.name], dx, n, l.geom, None, 0, href, EPI_DACT, act, slope)
 
-    def _wgrad_layer(self, st: NetState, l: Layer, x_in, dy, n):
+    def _wgrad_layer(self, st: NetState, l: Layer, x_in, dy, n, lo=0):
         dW = st.g(l.name + '.weight')
-        if l.fwd == 'down':
+        if l.name in st.thin:
+            P = l.geom.Hs * l.geom.Ws
+            col = self._col(st, l, lo, n)
+            if l.fwd == 'down':      # col = im2col(layer input), written by the forward pass
+                self.ops.conv_wgrad(dy, col, dW, n * P, self._lin(l))
+            else:                    # large side = dy: im2col it here, the data-backward reuses it (col_ready)
+                self.ops.im2col(dy, col, n, l.geom, KPAD)
+                self.ops.conv_wgrad(x_in, col, dW, n * P, self._lin(l))
+        elif l.fwd == 'down':
             self.ops.conv_wgrad(dy, x_in, dW, n, l.geom)
         else:
             self.ops.conv_wgrad(x_in, dy, dW, n, l.geom)
@@ -215,6 +285,8 @@ class Engine:
         acts = [self.buf((tag, 'a', 0), (nb_rows * net.layers[0].in_elems,))]
         for i, l in enumerate(net.layers, 1):
             acts.append(self.buf((tag, 'a', i), (nb_rows * l.out_elems,)))
+            if self.thin and l.thin_ok:
+                self.buf(('col', tag, l.name), (nb_rows * l.geom.Hs * l.geom.Ws * KPAD,))
         return acts
 
     def alloc_deltas(self, tag, net: Net, nb_rows):
@@ -232,7 +304,8 @@ class Engine:
         net = st.net
         n = hi - lo
         for i, l in enumerate(net.layers, 1):
-            self._fwd_layer(st, l, self.rows(acts[i - 1], l.in_elems, lo, hi), self.rows(acts[i], l.out_elems, lo, hi), n)
+            self._fwd_layer(st, l, self.rows(acts[i - 1], l.in_elems, lo, hi), self.rows(acts[i], l.out_elems, lo, hi), n,
+                            lo=lo)
 
     def backward(self, st: NetState, acts, deltas, lo, hi, wlo=None, whi=None, need_input_grad=False, dinput=None,
                  input_href=None, input_act=ACT_NONE, weight_grads=True):
@@ -245,16 +318,18 @@ class Engine:
             l = net.layers[i - 1]
             if weight_grads:
                 self._wgrad_layer(st, l, self.rows(acts[i - 1], l.in_elems, wlo, whi),
-                                  self.rows(deltas[i], l.out_elems, wlo, whi), whi - wlo)
+                                  self.rows(deltas[i], l.out_elems, wlo, whi), whi - wlo, lo=wlo)
                 self._bias_grad(st, l, self.rows(deltas[i], l.out_elems, lo, hi), (hi - lo) * l.out_rows)
             if i > 1:
                 lp = net.layers[i - 2]
                 self._bwd_data_layer(st, l, self.rows(deltas[i], l.out_elems, lo, hi),
                                      self.rows(deltas[i - 1], lp.out_elems, lo, hi), hi - lo,
-                                     self.rows(acts[i - 1], lp.out_elems, lo, hi), lp.act, lp.slope)
+                                     self.rows(acts[i - 1], lp.out_elems, lo, hi), lp.act, lp.slope, lo=lo,
+                                     col_ready=(weight_grads and wlo == lo and whi == hi))
             elif need_input_grad:
                 self._bwd_data_layer(st, l, self.rows(deltas[i], l.out_elems, lo, hi), dinput, hi - lo,
-                                     input_href, input_act, 0.0)
+                                     input_href, input_act, 0.0, lo=lo,
+                                     col_ready=(weight_grads and wlo == lo and whi == hi))
 
     # ------------------------------------------------------------------ Adam
     def adam(self, st: NetState, lr, weight_decay, betas=(0.9, 0.999), eps=1e-8):
@@ -267,8 +342,7 @@ class Engine:
         bc1 = 1.0 - betas[0] ** t
         bc2 = 1.0 - betas[1] ** t
         for l in st.net.layers:
-            g = l.geom
-            wd_s, wu_s = _strides_for(l.master_kind, l.master_dims, g.Ca, g.Cb, g.R, g.S)
+            wd_s, wu_s = st.strides(l)
             k = l.name + '.weight'
             self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), l.master_dims, wd_s, st.wd_[l.name], wd_s,
                           st.wu_[l.name], wu_s, lr, betas[0], betas[1], eps, weight_decay, bc1, bc2)
@@ -442,7 +516,7 @@ class Engine:
         # tangent u-chain: u_l = down(W_l, u_{l-1}) (no bias) * act'(h_l of x_hat)
         for i, l in enumerate(net.layers, 1):
             self._fwd_layer(D, l, self.rows(acts[i - 1], l.in_elems, 4 * B, 5 * B), blk(acts[i], l, 4 * B, 5 * B), B,
-                            bias=False, href=blk(acts[i], l, 3 * B, 4 * B), epi=EPI_DACT)
+                            bias=False, href=blk(acts[i], l, 3 * B, 4 * B), epi=EPI_DACT, lo=4 * B)
         if not dggan:
             ops.gp_feature_seed(fblk(4 * B, 5 * B), fblk(3 * B, 4 * B), s_norm, dblk(3 * B, 4 * B), B, F,
                                 lastl.act, lastl.slope)
@@ -459,7 +533,7 @@ class Engine:
             self.backward(D, acts, deltas, 0, 3 * B, 0, 3 * B)
             for i, l in enumerate(net.layers, 1):
                 self._wgrad_layer(D, l, self.rows(acts[i - 1], l.in_elems, 4 * B, 5 * B),
-                                  blk(deltas[i], l, 4 * B, 5 * B), B)
+                                  blk(deltas[i], l, 4 * B, 5 * B), B, lo=4 * B)
         self.adam(D, cfg.learning_rate, cfg.weight_decay, cfg.betas, cfg.eps)                     # srgan.py:297
         if not train_generator:
             return

@@ -64,6 +64,14 @@ class Layer:
     bias_mod: int = 0              # bias index = column % bias_mod  (fc_up: bias per channel, broadcast over r,s)
 
     @property
+    def thin_ok(self):
+        """Image layer with <= 4 channels on the large side whose whole receptive field fits one 64-wide im2col row:
+        eligible for the im2col/col2im + [pixels x 64] tensor-core GEMM lowering (engine.KPAD)."""
+        g = self.geom
+        return (g.Cb <= 4 and g.R * g.S * g.Cb <= 64 and g.Ca % 64 == 0 and g.Hl * g.Wl > 1
+                and self.master_kind == 'conv')
+
+    @property
     def in_elems(self):
         return self.geom.large_elems if self.fwd == 'down' else self.geom.small_elems
 

@@ -26,7 +26,7 @@ _EXPORTS = (
     'srgan_conv_down', 'srgan_conv_up', 'srgan_conv_wgrad', 'srgan_colsum', 'srgan_rowdot', 'srgan_seed_rows',
     'srgan_nchw_to_nhwc', 'srgan_nhwc_to_nchw', 'srgan_interpolate', 'srgan_labeled_loss', 'srgan_bce_logits',
     'srgan_distance', 'srgan_feature_norm_seed', 'srgan_gradnorm_penalty', 'srgan_gp_feature_seed', 'srgan_adam',
-    'srgan_repack',
+    'srgan_repack', 'srgan_im2col', 'srgan_col2im',
 )
 
 _lib = None
@@ -72,6 +72,8 @@ def load_library(path: str = LIB_PATH):
     i4, l4 = ctypes.POINTER(c_int * 4), ctypes.POINTER(c_ll * 4)
     lib.srgan_adam.argtypes = [vp, vp, vp, vp, i4, l4, vp, l4, vp, l4, c_int] + [c_f] * 7 + [vp]
     lib.srgan_repack.argtypes = [vp, i4, vp, l4, vp, l4, c_int, vp]
+    lib.srgan_im2col.argtypes = [vp, vp, c_int, gp, c_int, c_int, vp]
+    lib.srgan_col2im.argtypes = [vp, vp, c_int, gp, c_int, vp, vp, c_int, c_int, c_f, c_int, vp]
     for name in _EXPORTS[5:]:
         getattr(lib, name).restype = c_int
     _lib = lib
@@ -217,6 +219,16 @@ class CudaOps:
         self._ck(self.lib.srgan_gp_feature_seed(self._p(uL), self._p(hL, uL.dtype), self._p(s, torch.float32),
                                                 self._p(out, uL.dtype), rows, cols, act, slope, _dt(uL.dtype),
                                                 self._stream()), 'srgan_gp_feature_seed')
+
+    def im2col(self, L, col, n, g, kpad):
+        self._ck(self.lib.srgan_im2col(self._p(L), self._p(col, L.dtype), n, self._geom(g), kpad, _dt(L.dtype),
+                                       self._stream()), 'srgan_im2col')
+
+    def col2im(self, col, L_out, n, g, kpad, bias, href, epi, act, slope):
+        self._ck(self.lib.srgan_col2im(self._p(col), self._p(L_out, col.dtype), n, self._geom(g), kpad,
+                                       self._p(bias.detach(), torch.float32) if bias is not None else None,
+                                       self._p(href, col.dtype) if href is not None else None, epi, act, slope,
+                                       _dt(col.dtype), self._stream()), 'srgan_col2im')
 
     def adam(self, param, grad, m, v, dims, gstrides, out1, s1, out2, s2, lr, b1, b2, eps, wd, bc1, bc2):
         f32 = torch.float32

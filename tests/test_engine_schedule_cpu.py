@@ -69,3 +69,35 @@ def test_schedule_matches_reference_golden_fp32(name):
     for net, mine in (('D', eng.D), ('G', eng.G), ('DNN', eng.DNN)):
         for k, v in g.group(f'final/{net}').items():
             assert rel(mine.params[k], v) < 1e-4, (name, net, k)
+
+
+def test_thin_layer_lowering_matches_oracle_fp64():
+    """The im2col/col2im + [pixels x 64] GEMM lowering of the 3-channel image layers (bf16 mode default) is algebra-
+    exact: run it in fp64 through the torch emulation against the oracle (conv_dim 64 so the layers are eligible)."""
+    dt = torch.float64
+    st = O.init_dcgan(seed=4, image_size=32, conv_dim=64, z_dim=16, dtype=dt, scale=3.0)
+    cfg = O.StepConfig(batch_size=2, matching_loss_multiplier=1e2, contrasting_loss_multiplier=1e1,
+                       gradient_penalty_multiplier=1e2, weight_decay=1e-3)
+    d_net, g_net = nets.dcgan_d(32, 64), nets.dcgan_g(32, 64, 16)
+    eng = engine.Engine(TorchOps(), d_net, g_net, {k: v.clone() for k, v in st.D.items()},
+                        {k: v.clone() for k, v in st.G.items()}, {k: v.clone() for k, v in st.DNN.items()},
+                        act_dtype=dt, device='cpu', thin_lowering=True)
+    assert eng.D.thin == {'layer1.0'} and eng.G.thin == {'layer4.0'}
+    gen = torch.Generator().manual_seed(1)
+    B = 2
+    for i in range(2):
+        x = (torch.rand(B, 3, 32, 32, generator=gen, dtype=dt) * 2 - 1)
+        u = (torch.rand(B, 3, 32, 32, generator=gen, dtype=dt) * 2 - 1)
+        y = torch.rand(B, generator=gen, dtype=dt) * 85 + 10
+        z, alpha, z2 = (torch.randn(B, 16, generator=gen, dtype=dt), torch.rand(B, 1, 1, 1, generator=gen, dtype=dt),
+                        torch.randn(B, 16, generator=gen, dtype=dt))
+        out = O.training_step(st, cfg, x, y, u, z, alpha, z2, step=i)
+        eng.dnn_step(x, y, cfg, O.dnn_lr(cfg, i), cfg.weight_decay)
+        eng.gan_step(x, y, u, z, alpha, z2, cfg)
+        got = read_scalars(eng)
+        assert out['gradient_penalty'] > 0
+        for k in SCALARS:
+            assert got[k] == pytest.approx(out[k], rel=1e-9, abs=1e-12), (i, k)
+    for net, params, mine in (('D', st.D, eng.D), ('G', st.G, eng.G), ('DNN', st.DNN, eng.DNN)):
+        for k, v in params.items():
+            assert rel(mine.params[k], v) < 1e-8, (net, k, rel(mine.params[k], v))

@@ -44,9 +44,11 @@ GEOMS = [
     Geom(16, 16, 128, 32, 32, 64, 4, 4, 2, 1),     # tcgen05: DCGAN layer 2 channels
     Geom(4, 4, 512, 8, 8, 256, 4, 4, 2, 1),        # tcgen05: DCGAN layer 4 channels (wgrad BN=256)
     Geom(1, 1, 2048, 1, 1, 256, 1, 1, 1, 0),       # tcgen05: fc as linear
-    Geom(8, 8, 64, 8, 8, 64, 3, 3, 1, 1),          # tcgen05: k3 s1
+    Geom(8, 8, 64, 8, 8, 64, 3, 3, 1, 1),          # tcgen05: k3 s1; wgrad with Ca = 64 (half tile zero-filled)
+    Geom(1, 1, 64, 1, 1, 64, 1, 1, 1, 0),          # tcgen05: the [pixels x 64] GEMM of the thin-layer lowering
 ]
-TENSOR_ELIGIBLE = {4, 8, 9, 10, 11}
+TENSOR_ELIGIBLE = {4, 8, 9, 10, 11, 12}
+WGRAD_TENSOR_ELIGIBLE = {4, 8, 9, 10, 11, 12}
 
 
 @pytest.mark.parametrize('dt', DT)
@@ -54,7 +56,7 @@ TENSOR_ELIGIBLE = {4, 8, 9, 10, 11}
 def test_conv_down_up_wgrad(ops, dt, gi):
     g = GEOMS[gi]
     gen = torch.Generator().manual_seed(gi)
-    n = 130 if g.Hl == 1 else 5
+    n = (5000 if g.Ca == 64 else 130) if g.Hl == 1 else 5
     ref = TorchOps()
     L = rnd(gen, n * g.Hl * g.Wl * g.Cb, dt=dt)
     S = rnd(gen, n * g.Hs * g.Ws * g.Ca, dt=dt)
@@ -85,7 +87,7 @@ def test_conv_down_up_wgrad(ops, dt, gi):
     ref.conv_wgrad(S, L, dW_ref, n, g)
     ops.conv_wgrad(S.cuda(), L.cuda(), dW, n, g)
     close(dW, dW_ref, tol(dt) * 2, 'wgrad')
-    if dt == torch.bfloat16 and gi in TENSOR_ELIGIBLE:
+    if dt == torch.bfloat16 and gi in WGRAD_TENSOR_ELIGIBLE:
         assert ops.lib.srgan_last_path_tensor() == 1, 'expected the tcgen05 wgrad path'
 
 
@@ -233,3 +235,27 @@ def test_adam_and_repack(ops):
             close(p, p_ref, 5e-6, 'adam p'); close(m, m_ref, 5e-6, 'adam m'); close(v, v_ref, 5e-6, 'adam v')
             close(o1, o1_ref, 5e-6 if od == torch.float32 else 1e-2, 'adam out1')
             close(o2, o2_ref, 5e-6 if od == torch.float32 else 1e-2, 'adam out2')
+
+
+@pytest.mark.parametrize('dt', DT)
+@pytest.mark.parametrize('g', [Geom(16, 16, 64, 32, 32, 3, 4, 4, 2, 1), Geom(5, 7, 64, 11, 15, 4, 3, 3, 2, 0),
+                               Geom(8, 8, 128, 8, 8, 1, 3, 3, 1, 1)])
+def test_im2col_col2im(ops, dt, g):
+    gen = torch.Generator().manual_seed(g.Hl)
+    ref = TorchOps()
+    n, kpad = 3, 64
+    L = rnd(gen, n * g.Hl * g.Wl * g.Cb, dt=dt)
+    c_ref = torch.empty(n * g.Hs * g.Ws * kpad, dtype=dt)
+    c = torch.full((n * g.Hs * g.Ws * kpad,), 7.0, dtype=dt, device='cuda')
+    ref.im2col(L, c_ref, n, g, kpad)
+    ops.im2col(L.cuda(), c, n, g, kpad)
+    close(c, c_ref, 1e-7, 'im2col')
+    col = rnd(gen, n * g.Hs * g.Ws * kpad, dt=dt)
+    bias, href = rnd(gen, g.Cb), rnd(gen, L.numel(), dt=dt)
+    for epi, act, slope in ((0, 2, 0.0), (0, 1, 0.05), (1, 2, 0.0), (1, 1, 0.05), (1, 0, 0.0)):
+        o_ref = torch.empty_like(L)
+        o = torch.empty_like(L, device='cuda')
+        ref.col2im(col, o_ref, n, g, kpad, bias if epi == 0 else None, href if epi == 1 else None, epi, act, slope)
+        ops.col2im(col.cuda(), o, n, g, kpad, bias.cuda() if epi == 0 else None, href.cuda() if epi == 1 else None,
+                   epi, act, slope)
+        close(o, o_ref, tol(dt), f'col2im epi{epi} act{act}')

@@ -212,6 +212,27 @@ class TorchOps:
         df = (u - g * dot) / s.view(rows, 1)
         out.copy_((df * dact(f, act, slope)).reshape(-1).to(out.dtype))
 
+    def im2col(self, L, col, n, g, kpad):
+        self.launches += 1
+        x = L.view(n, g.Hl, g.Wl, g.Cb).permute(0, 3, 1, 2).to(torch.float64)
+        u = F.unfold(x, (g.R, g.S), padding=g.pad, stride=g.stride)            # [n, Cb*R*S, P]  (b, r, s) order
+        P = u.shape[-1]
+        assert P == g.Hs * g.Ws
+        u = u.view(n, g.Cb, g.R * g.S, P).permute(0, 3, 2, 1).reshape(n * P, g.R * g.S * g.Cb)   # (tap, b) order
+        out = torch.zeros(n * P, kpad, dtype=torch.float64)
+        out[:, :u.shape[1]] = u
+        col.copy_(out.reshape(-1).to(col.dtype))
+
+    def col2im(self, col, L_out, n, g, kpad, bias, href, epi, act, slope):
+        self.launches += 1
+        K = g.R * g.S * g.Cb
+        P = g.Hs * g.Ws
+        c = col.view(n * P, kpad)[:, :K].to(torch.float64).view(n, P, g.R * g.S, g.Cb).permute(0, 3, 2, 1)
+        c = c.reshape(n, g.Cb * g.R * g.S, P)
+        y = F.fold(c, (g.Hl, g.Wl), (g.R, g.S), padding=g.pad, stride=g.stride)       # [n, Cb, Hl, Wl]
+        cd = torch.float64 if col.dtype == torch.float64 else torch.float32
+        self._epilogue(y.permute(0, 2, 3, 1).to(cd), L_out, bias, 0, href, epi, act, slope)
+
     def adam(self, param, grad, m, v, dims, gstrides, out1, s1, out2, s2, lr, b1, b2, eps, wd, bc1, bc2):
         self.launches += 1
         p = param.detach()
