@@ -209,6 +209,55 @@ __global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ L, T*
     }
 }
 
+// The DCGAN image layers (3 channels, k4 s2 p1, kpad 64), bf16: one thread per (pixel, filter row r).  The 4 taps x 3
+// channels of a filter row are 24 contiguous bytes of the NHWC image, copied as twelve 2-byte loads (the source is only
+// 2-byte aligned) packed into three 8-byte stores; no integer division per element.  Lanes 4p..4p+3 write one 128-byte
+// col row (96 B data + 32 B zero pad), so a warp emits eight full lines.
+__global__ void __launch_bounds__(256) im2col_c3k4s2_kernel(const bf16* __restrict__ L, bf16* __restrict__ col, int n, int Hs,
+                                                            int Ws, int Hl, int Wl) {
+    const long long total = (long long)n * Hs * Ws * 4;
+    const unsigned short* Lu = reinterpret_cast<const unsigned short*>(L);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i >> 2;
+        const int r = (int)(i & 3);
+        const int ow = (int)(pix % Ws);
+        const long long t = pix / Ws;
+        const int oh = (int)(t % Hs);
+        const int nn = (int)(t / Hs);
+        const int ih = oh * 2 - 1 + r, iw0 = ow * 2 - 1;
+        unsigned short e[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) e[k] = 0;
+        if (ih >= 0 && ih < Hl) {
+            const unsigned short* src = Lu + (((long long)nn * Hl + ih) * Wl + iw0) * 3;
+            if (iw0 >= 0 && iw0 + 3 < Wl) {
+#pragma unroll
+                for (int k = 0; k < 12; ++k) e[k] = __ldg(src + k);
+            } else {
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+                    if (iw0 + s >= 0 && iw0 + s < Wl) {
+                        e[s * 3] = __ldg(src + s * 3); e[s * 3 + 1] = __ldg(src + s * 3 + 1); e[s * 3 + 2] = __ldg(src + s * 3 + 2);
+                    }
+            }
+        }
+        uint2* d = reinterpret_cast<uint2*>(col + pix * 64 + r * 12);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            uint2 w;
+            w.x = (unsigned)e[q * 4] | ((unsigned)e[q * 4 + 1] << 16);
+            w.y = (unsigned)e[q * 4 + 2] | ((unsigned)e[q * 4 + 3] << 16);
+            d[q] = w;
+        }
+        if (r == 3) {
+            uint4* z = reinterpret_cast<uint4*>(col + pix * 64 + 48);
+            z[0] = make_uint4(0u, 0u, 0u, 0u);
+            z[1] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) col2im_kernel(const T* __restrict__ col, T* __restrict__ out, ThinP p,
                                                      const float* __restrict__ bias, const T* __restrict__ href, int epi,
@@ -558,6 +607,10 @@ int srgan_im2col(const void* L, void* col, int n, const srgan_geom* g, int kpad,
     cudaStream_t st = (cudaStream_t)stream;
     long long items = (long long)n * g->Hs * g->Ws * (kpad / 8);
     if (dtype == SRGAN_F32) im2col_kernel<float><<<ew_grid(items, 256), 256, 0, st>>>((const float*)L, (float*)col, p);
+    else if (g->Cb == 3 && g->R == 4 && g->S == 4 && g->stride == 2 && g->pad == 1 && kpad == 64 && g->Hl == 2 * g->Hs &&
+             g->Wl == 2 * g->Ws)
+        im2col_c3k4s2_kernel<<<ew_grid((long long)n * g->Hs * g->Ws * 4, 256), 256, 0, st>>>((const bf16*)L, (bf16*)col, n, g->Hs,
+                                                                                           g->Ws, g->Hl, g->Wl);
     else im2col_kernel<bf16><<<ew_grid(items, 256), 256, 0, st>>>((const bf16*)L, (bf16*)col, p);
     SRGAN_CHECK_LAUNCH("im2col_kernel");
     return SRGAN_OK;

@@ -171,9 +171,23 @@ class Engine:
         for l in st.net.layers:
             w = st.params[l.name + '.weight']
             wd_s, wu_s = st.strides(l)
-            self.ops.repack(w, l.master_dims, st.wd_[l.name], wd_s, st.wu_[l.name], wu_s)
+            wd, wu = self._needed_layouts(st, l)
+            self.ops.repack(w, l.master_dims, wd, wd_s if wd is not None else None, wu, wu_s if wu is not None else None)
         if st.net.head:
             self._repack_head(st)
+
+    @staticmethod
+    def _needed_layouts(st: NetState, l: Layer):
+        """Kernel-layout copies a layer really uses: the forward op's layout always; the transposed one only if a
+        data-backward / tangent pass ever goes through the layer (never for the generator's first layer)."""
+        wd, wu = st.wd_[l.name], st.wu_[l.name]
+        first_of_g = st.net.kind == 'G' and l is st.net.layers[0]
+        if first_of_g:
+            if l.fwd == 'down':
+                wu = None
+            else:
+                wd = None
+        return wd, wu
 
     def _head_strides(self, net: Net):
         F = net.feature_size
@@ -344,8 +358,9 @@ class Engine:
         for l in st.net.layers:
             wd_s, wu_s = st.strides(l)
             k = l.name + '.weight'
-            self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), l.master_dims, wd_s, st.wd_[l.name], wd_s,
-                          st.wu_[l.name], wu_s, lr, betas[0], betas[1], eps, weight_decay, bc1, bc2)
+            wd, wu = self._needed_layouts(st, l)
+            self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), l.master_dims, wd_s, wd, wd_s if wd is not None else None,
+                          wu, wu_s if wu is not None else None, lr, betas[0], betas[1], eps, weight_decay, bc1, bc2)
             k = l.name + '.bias'
             nb = st.params[k].numel()
             self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), (nb, 1, 1, 1), (1, 0, 0, 0), None, None, None, None,
