@@ -45,10 +45,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must surface as a CUDA error, never as a hung GPU box.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
     for (uint32_t i = 0; i < (1u << 24); ++i)
         if (mbar_try_wait(bar, parity)) return;
     printf("srgan umma: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
     __trap();
+}
+// one elected lane of a converged warp (lets the compiler keep descriptors / barrier addresses in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -395,16 +406,20 @@ __global__ void __launch_bounds__(PC_THREADS, 1) umma_conv_persistent_kernel(con
     };
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            int it = 0;
+        // ================= TMA producer (one elected thread) =================
+        if (elect_one()) {
+            int s = 0;
+            uint32_t ph = 0;
+            const int mul = p.mode == 0 ? p.stride : 1;
             for (int tile = blockIdx.x; tile < pp.total_tiles; tile += gridDim.x) {
                 const Tile T = decode(tile);
-                int sw[MT], sh[MT], sn[MT];
+                int cw[MT], chh[MT], cn[MT];
 #pragma unroll
                 for (int i = 0; i < MT; ++i) {
                     int ms = T.mt * MT + i;
-                    sw[i] = ms % p.tiles_w; sh[i] = (ms / p.tiles_w) % p.tiles_h; sn[i] = ms / sub_per_n;
+                    cw[i] = (ms % p.tiles_w) * p.TW * mul;
+                    chh[i] = ((ms / p.tiles_w) % p.tiles_h) * p.TH * mul;
+                    cn[i] = (ms / sub_per_n) * p.TN;
                 }
                 for (int tr = 0; tr < T.Rt; ++tr)
                     for (int ts = 0; ts < T.St; ++ts) {
@@ -414,28 +429,27 @@ __global__ void __launch_bounds__(PC_THREADS, 1) umma_conv_persistent_kernel(con
                             dw = T.qb - ts; dh = T.qa - tr;
                             kcol = ((T.r0 + p.stride * tr) * p.S + (T.s0 + p.stride * ts)) * p.Cin;
                         }
-                        const int mul = p.mode == 0 ? p.stride : 1;
-                        for (int ch = 0; ch < nch; ++ch, ++it) {
-                            const int s = it % stages;
-                            const uint32_t ph = (it / stages) & 1;
+                        for (int ch = 0; ch < nch; ++ch) {
                             mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
                             const uint32_t fb = smem_u32(&full_bar[s]);
                             mbar_expect_tx(fb, STAGE_BYTES);
                             const uint32_t dst = tiles + s * STAGE_BYTES;
 #pragma unroll
                             for (int i = 0; i < MT; ++i)
-                                tma_load_4d(dst + i * A_STAGE_BYTES, &tmA, fb, ch * KCH, sw[i] * p.TW * mul + dw,
-                                            sh[i] * p.TH * mul + dh, sn[i] * p.TN);
+                                tma_load_4d(dst + i * A_STAGE_BYTES, &tmA, fb, ch * KCH, cw[i] + dw, chh[i] + dh, cn[i]);
                             tma_load_2d(dst + MT * A_STAGE_BYTES, &tmB, fb, kcol + ch * KCH, T.ny * BN);
+                            if (++s == stages) { s = 0; ph ^= 1; }
                         }
                     }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer (one thread) =================
-        if (lane == 0) {
+        // ================= MMA issuer (one elected thread) =================
+        if (elect_one()) {
             constexpr uint32_t idesc = make_idesc(TILE_M, BN, 0, 0);
-            int it = 0, tl = 0;
+            const uint64_t desc0 = make_desc(0, 16, 1024);      // the 14-bit address field is added per operand below
+            int s = 0, tl = 0;
+            uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < pp.total_tiles; tile += gridDim.x, ++tl) {
                 const Tile T = decode(tile);
                 const int n_iters = T.Rt * T.St * nch;
@@ -444,22 +458,21 @@ __global__ void __launch_bounds__(PC_THREADS, 1) umma_conv_persistent_kernel(con
                 mbar_wait(smem_u32(&tmem_empty_bar[buf]), bph ^ 1);     // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t acc = tmem_base + buf * ACC_COLS;
-                for (int k_it = 0; k_it < n_iters; ++k_it, ++it) {
-                    const int s = it % stages;
-                    const uint32_t ph = (it / stages) & 1;
+                for (int k_it = 0; k_it < n_iters; ++k_it) {
                     mbar_wait(smem_u32(&full_bar[s]), ph);
                     tc_fence_after();
-                    const uint32_t a_s = tiles + s * STAGE_BYTES, b_s = a_s + MT * A_STAGE_BYTES;
+                    const uint32_t a_s = tiles + s * STAGE_BYTES;
+                    const uint64_t ad0 = desc0 + (uint64_t)(a_s >> 4);
+                    const uint64_t bd0 = desc0 + (uint64_t)((a_s + MT * A_STAGE_BYTES) >> 4);
 #pragma unroll
                     for (int i = 0; i < MT; ++i) {
 #pragma unroll
-                        for (int k = 0; k < KCH / 16; ++k) {
-                            const uint64_t ad = make_desc(a_s + i * A_STAGE_BYTES + k * 32, 16, 1024);
-                            const uint64_t bd = make_desc(b_s + k * 32, 16, 1024);
-                            umma_f16(acc + i * BN, ad, bd, idesc, (k_it > 0 || k > 0) ? 1u : 0u);
-                        }
+                        for (int k = 0; k < KCH / 16; ++k)
+                            umma_f16(acc + i * BN, ad0 + (uint64_t)(i * (A_STAGE_BYTES >> 4) + k * 2), bd0 + (uint64_t)(k * 2), idesc,
+                                     (k_it > 0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(smem_u32(&empty_bar[s]));
+                    if (++s == stages) { s = 0; ph ^= 1; }
                 }
                 umma_commit(smem_u32(&tmem_full_bar[buf]));
             }
@@ -613,14 +626,14 @@ __global__ void __launch_bounds__(WG_THREADS) umma_wgrad_kernel(const __grid_con
 
     if (n_iters > 0) {
         if (warp == 0) {
-            if (lane == 0) {
+            if (elect_one()) {
+                int s = 0;
+                uint32_t ph = 0;
                 for (int it = 0; it < n_iters; ++it) {
                     int c = ch_begin + it;
                     const int tw_i = c % p.tiles_w; c /= p.tiles_w;
                     const int th_i = c % p.tiles_h; c /= p.tiles_h;
                     const int tn_i = c;
-                    const int s = it % stages;
-                    const uint32_t ph = (it / stages) & 1;
                     mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
                     const uint32_t fb = smem_u32(&full_bar[s]);
                     mbar_expect_tx(fb, STAGE_BYTES);
@@ -634,28 +647,29 @@ __global__ void __launch_bounds__(WG_THREADS) umma_wgrad_kernel(const __grid_con
                             tma_load_4d(dst + A_BYTES + k * B_TAP_BYTES + g * WG_PIX * 128, &tmL, fb, b0 + g * 64, lw, lh,
                                         tn_i * p.TN);
                     }
+                    if (++s == stages) { s = 0; ph ^= 1; }
                 }
             }
         } else if (warp == 1) {
-            if (lane == 0) {
+            if (elect_one()) {
                 constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
+                const uint64_t desc0 = make_desc(0, WG_PIX * 128, 1024);
+                int s = 0;
+                uint32_t ph = 0;
                 for (int it = 0; it < n_iters; ++it) {
-                    const int s = it % stages;
-                    const uint32_t ph = (it / stages) & 1;
                     mbar_wait(smem_u32(&full_bar[s]), ph);
                     tc_fence_after();
                     const uint32_t a_s = tiles + s * STAGE_BYTES;
+                    const uint64_t ad0 = desc0 + (uint64_t)(a_s >> 4);
                     for (int k = 0; k < NT; ++k) {
-                        const uint32_t b_s = a_s + A_BYTES + k * B_TAP_BYTES;
+                        const uint64_t bd0 = desc0 + (uint64_t)((a_s + A_BYTES + k * B_TAP_BYTES) >> 4);
 #pragma unroll
-                        for (int kk = 0; kk < WG_PIX / 16; ++kk) {
-                            // 16 K rows (pixels) = 2048 B further into every 64-wide column group
-                            const uint64_t ad = make_desc(a_s + kk * 2048, WG_PIX * 128, 1024);
-                            const uint64_t bd = make_desc(b_s + kk * 2048, WG_PIX * 128, 1024);
-                            umma_f16(tmem_base + k * BN, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
-                        }
+                        for (int kk = 0; kk < WG_PIX / 16; ++kk)      // 16 K rows (pixels) = 2048 B further into every column group
+                            umma_f16(tmem_base + k * BN, ad0 + (uint64_t)(kk * 128), bd0 + (uint64_t)(kk * 128), idesc,
+                                     (it > 0 || kk > 0) ? 1u : 0u);
                     }
                     umma_commit(smem_u32(&empty_bar[s]));
+                    if (++s == stages) { s = 0; ph ^= 1; }
                 }
                 umma_commit(smem_u32(&tmem_full_bar));
             }

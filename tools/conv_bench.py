@@ -7,10 +7,13 @@ from srgan_b200.nets import Geom
 from srgan_b200.ops_cuda import CudaOps
 
 ops = CudaOps()
-filt = [a for a in sys.argv[1:] if not a.startswith('--')]
+args = sys.argv[1:]
 iters = 10
-if '--iters' in sys.argv:
-    iters = int(sys.argv[sys.argv.index('--iters') + 1])
+if '--iters' in args:
+    k = args.index('--iters')
+    iters = int(args[k + 1])
+    del args[k:k + 2]
+filt = [a for a in args if not a.startswith('--')]
 SHAPES = [
     ('D.l2 64->128 @64->32', Geom(32, 32, 128, 64, 64, 64, 4, 4, 2, 1), 400),
     ('D.l3 128->256 @32->16', Geom(16, 16, 256, 32, 32, 128, 4, 4, 2, 1), 400),
