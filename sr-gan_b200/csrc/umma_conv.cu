@@ -8,7 +8,6 @@
 //     * the weight operand is a plain 2-D TMA tile of Wd[a][(r,s,b)] / Wu[b][(r,s,a)];
 //     * warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2-5 = epilogue
 //       (tcgen05.ld -> bias + LeakyReLU/tanh, or multiply by act'(href) for the backward / tangent passes -> bf16 NHWC);
-//     * ~97 KB of shared memory per CTA so two CTAs share an SM: one's epilogue overlaps the other's main loop.
 //   wgrad (umma_wgrad_kernel): see below.
 //
 // Replaces cuDNN fprop / dgrad behind age/models.py:44-52,68-80 and crowd/models.py:139-147.
@@ -62,7 +61,6 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
     asm volatile(
@@ -142,7 +140,6 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 constexpr int TILE_M = 128;
 constexpr int KCH = 64;                        // bf16 elements per K chunk = one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = TILE_M * KCH * 2;  // 16 KB
-constexpr int CONV_THREADS = 192;
 
 struct UmmaConvParams {
     int mode;                     // 0 down, 1 up
@@ -162,176 +159,69 @@ struct UmmaConvParams {
     int stages;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(CONV_THREADS) umma_conv_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                 const __grid_constant__ CUtensorMap tmB,
-                                                                 const UmmaConvParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[8];
-    __shared__ __align__(8) uint64_t empty_bar[8];
-    __shared__ __align__(8) uint64_t tmem_full_bar;
-    __shared__ uint32_t tmem_slot;
-
-    constexpr int B_STAGE_BYTES = BN * KCH * 2;
-    constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int stages = p.stages;
-
-    // ---- tile coordinates
-    int t = blockIdx.x;
-    const int tw_i = t % p.tiles_w; t /= p.tiles_w;
-    const int th_i = t % p.tiles_h; t /= p.tiles_h;
-    const int tn_i = t;
-    const int c0 = blockIdx.y * BN;
-    // ---- phase (up with stride > 1): which taps hit output pixels (st*i+pa, st*j+pb)
-    int pa = 0, pb = 0, r0 = 0, s0 = 0, qa = 0, qb = 0, Rt = p.R, St = p.S;
-    if (p.mode == 1) {
-        pa = blockIdx.z / p.stride; pb = blockIdx.z % p.stride;
-        r0 = (pa + p.pad) % p.stride; s0 = (pb + p.pad) % p.stride;
-        qa = (pa + p.pad - r0) / p.stride; qb = (pb + p.pad - s0) / p.stride;
-        Rt = r0 < p.R ? (p.R - r0 + p.stride - 1) / p.stride : 0;
-        St = s0 < p.S ? (p.S - s0 + p.stride - 1) / p.stride : 0;
-    }
-    const int nch = p.Cin / KCH;
-    const int n_iters = Rt * St * nch;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-        mbar_init(smem_u32(&tmem_full_bar), 1);
-        fence_barrier_init();
-        prefetch_tmap(&tmA);
-        prefetch_tmap(&tmB);
-    }
-    if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), BN);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_slot;
-
-    if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            int it = 0;
-            for (int tr = 0; tr < Rt; ++tr)
-                for (int ts = 0; ts < St; ++ts) {
-                    int aw, ah, kcol;
-                    if (p.mode == 0) {
-                        aw = tw_i * p.TW * p.stride - p.pad + ts;
-                        ah = th_i * p.TH * p.stride - p.pad + tr;
-                        kcol = (tr * p.S + ts) * p.Cin;
-                    } else {
-                        aw = tw_i * p.TW + qb - ts;
-                        ah = th_i * p.TH + qa - tr;
-                        kcol = ((r0 + p.stride * tr) * p.S + (s0 + p.stride * ts)) * p.Cin;
-                    }
-                    for (int ch = 0; ch < nch; ++ch, ++it) {
-                        const int s = it % stages;
-                        const uint32_t ph = (it / stages) & 1;
-                        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
-                        const uint32_t fb = smem_u32(&full_bar[s]);
-                        mbar_expect_tx(fb, STAGE_BYTES);
-                        const uint32_t a_dst = tiles + s * STAGE_BYTES;
-                        tma_load_4d(a_dst, &tmA, fb, ch * KCH, aw, ah, tn_i * p.TN);
-                        tma_load_2d(a_dst + A_STAGE_BYTES, &tmB, fb, kcol + ch * KCH, c0);
-                    }
-                }
-        }
-    } else if (warp == 1) {
-        // ================= MMA issuer (one thread) =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(TILE_M, BN, 0, 0);
-            for (int it = 0; it < n_iters; ++it) {
-                const int s = it % stages;
-                const uint32_t ph = (it / stages) & 1;
-                mbar_wait(smem_u32(&full_bar[s]), ph);
-                tc_fence_after();
-                const uint32_t a_s = tiles + s * STAGE_BYTES, b_s = a_s + A_STAGE_BYTES;
+// Epilogue math on one 32-column chunk of one accumulator row (all branches are warp-uniform and hoisted out of the
+// element loops; bias is read as float4 runs, href as four 16-byte loads), then 64 bytes of bf16 are stored.
+__device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], const UmmaConvParams& p, int cbase, long long oj) {
+    float f[32];
 #pragma unroll
-                for (int k = 0; k < KCH / 16; ++k) {
-                    const uint64_t ad = make_desc(a_s + k * 32, 16, 1024);
-                    const uint64_t bd = make_desc(b_s + k * 32, 16, 1024);
-                    umma_f16(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
-                }
-                umma_commit(smem_u32(&empty_bar[s]));          // frees the smem stage when these MMAs retire
+    for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+    if (p.epi == SRGAN_EPI_BIAS_ACT) {
+        if (p.bias != nullptr) {
+            const int bi = p.bias_mod ? cbase % p.bias_mod : cbase;
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + bi);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const float4 b = __ldg(bp + g);
+                f[g * 4] += b.x; f[g * 4 + 1] += b.y; f[g * 4 + 2] += b.z; f[g * 4 + 3] += b.w;
             }
-            umma_commit(smem_u32(&tmem_full_bar));             // accumulator complete
         }
-    } else {
-        // ================= epilogue: TMEM -> registers -> bf16 NHWC =================
-        const int q = warp & 3;                                // TMEM lane quarter this warp may access
-        const int row = q * 32 + lane;
-        const int tw = row % p.TW, th = (row / p.TW) % p.TH, tn = row / (p.TW * p.TH);
-        const int sample = tn_i * p.TN + tn;
-        const int oy = th_i * p.TH + th, ox = tw_i * p.TW + tw;
-        const bool valid = sample < p.n;
-        long long o;
-        if (p.mode == 0) o = (((long long)sample * p.Hm + oy) * p.Wm + ox) * p.Cout + c0;
-        else o = (((long long)sample * p.Hout + (oy * p.stride + pa)) * p.Wout + (ox * p.stride + pb)) * p.Cout + c0;
-        if (n_iters > 0) {
-            mbar_wait(smem_u32(&tmem_full_bar), 0);
-            tc_fence_after();
+        if (p.act == SRGAN_ACT_LEAKY) {
+            const float sl = p.slope;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) f[e] = f[e] > 0.f ? f[e] : f[e] * sl;
+        } else if (p.act == SRGAN_ACT_TANH) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) f[e] = tanhf(f[e]);
         }
-#pragma unroll 1
-        for (int j = 0; j < BN / 32; ++j) {
-            uint32_t v[32];
-            if (n_iters > 0) {
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + j * 32, v);
-                tmem_ld_wait();
-            } else {
+    } else if (p.href != nullptr && p.act != SRGAN_ACT_NONE) {
+        const uint4* hp = reinterpret_cast<const uint4*>(p.href + oj);
+        uint4 hv[4];
 #pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = 0u;
+        for (int g = 0; g < 4; ++g) hv[g] = __ldg(hp + g);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(hv);
+        if (p.act == SRGAN_ACT_LEAKY) {
+            const float sl = p.slope;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const float2 hf = __bfloat1622float2(h2[e]);
+                f[2 * e] *= hf.x > 0.f ? 1.f : sl;
+                f[2 * e + 1] *= hf.y > 0.f ? 1.f : sl;
             }
-            if (!valid) continue;
-            float f[32];
+        } else {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
-            const long long oj = o + j * 32;
-            if (p.epi == SRGAN_EPI_BIAS_ACT) {
-                if (p.bias != nullptr) {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        int c = c0 + j * 32 + e;
-                        f[e] += __ldg(p.bias + (p.bias_mod ? c % p.bias_mod : c));
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < 32; ++e) f[e] = act_fwd(f[e], p.act, p.slope);
-            } else if (p.href != nullptr && p.act != SRGAN_ACT_NONE) {
-                const uint4* hp = reinterpret_cast<const uint4*>(p.href + oj);
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint4 hv = __ldg(hp + g);
-                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hv);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float2 hf = __bfloat1622float2(h2[e]);
-                        f[g * 8 + e * 2] *= act_bwd(hf.x, p.act, p.slope);
-                        f[g * 8 + e * 2 + 1] *= act_bwd(hf.y, p.act, p.slope);
-                    }
-                }
-            }
-            uint4* op = reinterpret_cast<uint4*>(p.out + oj);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                uint4 w;
-                __nv_bfloat162 b0 = __floats2bfloat162_rn(f[g * 8 + 0], f[g * 8 + 1]);
-                __nv_bfloat162 b1 = __floats2bfloat162_rn(f[g * 8 + 2], f[g * 8 + 3]);
-                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g * 8 + 4], f[g * 8 + 5]);
-                __nv_bfloat162 b3 = __floats2bfloat162_rn(f[g * 8 + 6], f[g * 8 + 7]);
-                w.x = *reinterpret_cast<uint32_t*>(&b0); w.y = *reinterpret_cast<uint32_t*>(&b1);
-                w.z = *reinterpret_cast<uint32_t*>(&b2); w.w = *reinterpret_cast<uint32_t*>(&b3);
-                op[g] = w;
+            for (int e = 0; e < 16; ++e) {
+                const float2 hf = __bfloat1622float2(h2[e]);
+                f[2 * e] *= 1.f - hf.x * hf.x;
+                f[2 * e + 1] *= 1.f - hf.y * hf.y;
             }
         }
     }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, BN);
+    uint4* op = reinterpret_cast<uint4*>(p.out + oj);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint4 w;
+        __nv_bfloat162 b0 = __floats2bfloat162_rn(f[g * 8 + 0], f[g * 8 + 1]);
+        __nv_bfloat162 b1 = __floats2bfloat162_rn(f[g * 8 + 2], f[g * 8 + 3]);
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g * 8 + 4], f[g * 8 + 5]);
+        __nv_bfloat162 b3 = __floats2bfloat162_rn(f[g * 8 + 6], f[g * 8 + 7]);
+        w.x = *reinterpret_cast<uint32_t*>(&b0); w.y = *reinterpret_cast<uint32_t*>(&b1);
+        w.z = *reinterpret_cast<uint32_t*>(&b2); w.w = *reinterpret_cast<uint32_t*>(&b3);
+        op[g] = w;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Persistent variant (the default): one CTA per SM walks a static round-robin list of output tiles.
+// Persistent kernel: one CTA per SM walks a static round-robin list of output tiles.
 //   * CTA tile = MT x 128 rows (MT sub-tiles share every weight tile: halves the weight traffic per FLOP) x BN columns;
 //   * a deep TMA ring (as many 128-byte-swizzled stages as fit in ~212 KB) covers the L2/HBM latency that the
 //     3-stage version exposed (ncu: tensor pipe 22 %, nothing else above 30 %);
@@ -508,46 +398,7 @@ __global__ void __launch_bounds__(PC_THREADS, 1) umma_conv_persistent_kernel(con
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + i * BN + j * 32, v);
                     tmem_ld_wait();
                     if (!valid) continue;
-                    float f[32];
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
-                    const long long oj = o + j * 32;
-                    if (p.epi == SRGAN_EPI_BIAS_ACT) {
-                        if (p.bias != nullptr) {
-#pragma unroll
-                            for (int e = 0; e < 32; ++e) {
-                                int c = c0 + j * 32 + e;
-                                f[e] += __ldg(p.bias + (p.bias_mod ? c % p.bias_mod : c));
-                            }
-                        }
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) f[e] = act_fwd(f[e], p.act, p.slope);
-                    } else if (p.href != nullptr && p.act != SRGAN_ACT_NONE) {
-                        const uint4* hp = reinterpret_cast<const uint4*>(p.href + oj);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            uint4 hv = __ldg(hp + g);
-                            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hv);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                float2 hf = __bfloat1622float2(h2[e]);
-                                f[g * 8 + e * 2] *= act_bwd(hf.x, p.act, p.slope);
-                                f[g * 8 + e * 2 + 1] *= act_bwd(hf.y, p.act, p.slope);
-                            }
-                        }
-                    }
-                    uint4* op = reinterpret_cast<uint4*>(p.out + oj);
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        uint4 w;
-                        __nv_bfloat162 b0 = __floats2bfloat162_rn(f[g * 8 + 0], f[g * 8 + 1]);
-                        __nv_bfloat162 b1 = __floats2bfloat162_rn(f[g * 8 + 2], f[g * 8 + 3]);
-                        __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g * 8 + 4], f[g * 8 + 5]);
-                        __nv_bfloat162 b3 = __floats2bfloat162_rn(f[g * 8 + 6], f[g * 8 + 7]);
-                        w.x = *reinterpret_cast<uint32_t*>(&b0); w.y = *reinterpret_cast<uint32_t*>(&b1);
-                        w.z = *reinterpret_cast<uint32_t*>(&b2); w.w = *reinterpret_cast<uint32_t*>(&b3);
-                        op[g] = w;
-                    }
+                    epilogue_chunk(v, p, c0 + j * 32, o + j * 32);
                 }
             }
             tc_fence_before();
@@ -767,25 +618,6 @@ bool pick_patch(int W, int H, int rows, int max_w, int& TW, int& TH, int& TN) {
     return TW * TH * TN == rows && TN <= 256;
 }
 
-template <int BN>
-int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaConvParams& p, dim3 grid, cudaStream_t st) {
-    constexpr int stage_bytes = A_STAGE_BYTES + BN * KCH * 2;
-    int stages = (96 * 1024) / stage_bytes;            // <= ~97 KB per CTA: two CTAs per SM
-    if (stages > 8) stages = 8;
-    if (stages < 2) stages = 2;
-    p.stages = stages;
-    size_t smem = (size_t)stages * stage_bytes + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(umma_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        if (e != cudaSuccess) { srgan_set_error("cudaFuncSetAttribute(umma_conv_kernel): %s", cudaGetErrorString(e)); return SRGAN_ERR_CUDA; }
-        attr_set = true;
-    }
-    umma_conv_kernel<BN><<<grid, CONV_THREADS, smem, st>>>(tmA, tmB, p);
-    SRGAN_CHECK_LAUNCH("umma_conv_kernel");
-    return 1;
-}
-
 template <int MT, int BN>
 int launch_conv_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaConvParamsP& pp, cudaStream_t st) {
     constexpr int stage_bytes = MT * A_STAGE_BYTES + BN * KCH * 2;
@@ -829,9 +661,7 @@ int umma_conv(int mode, const void* src, const void* W, void* out, int n, const 
               int bias_mod, const void* href, int epi, int act, float slope, cudaStream_t st) {
     const int Cin = mode == 0 ? g->Cb : g->Ca, Cout = mode == 0 ? g->Ca : g->Cb;
     if (Cin % KCH != 0) return 0;
-    static const int kernel_variant = [] { const char* e = getenv("SRGAN_UMMA_VARIANT"); return e ? atoi(e) : 1; }();
-    const bool persistent = kernel_variant != 0;       // 0 = first-generation one-tile-per-CTA kernel (A/B checks)
-    int BN = (persistent && Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 0));
+    int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 0));
     if (BN == 0) return 0;
     int Hm, Wm, phases = 1;
     if (mode == 0) { Hm = g->Hs; Wm = g->Ws; }
@@ -845,6 +675,7 @@ int umma_conv(int mode, const void* src, const void* W, void* out, int n, const 
     if (!pick_patch(Wm, Hm, TILE_M, 16, p.TW, p.TH, p.TN)) return 0;
     if (mode == 0 && (p.TW * g->stride > 256 || p.TH * g->stride > 256)) return 0;
     if (((uintptr_t)src & 15) || ((uintptr_t)W & 15) || ((uintptr_t)out & 15) || (href && ((uintptr_t)href & 15))) return 0;
+    if (bias && (((uintptr_t)bias & 15) || (bias_mod % 32) != 0)) return 0;       // epilogue reads bias as float4 runs of 32
     p.mode = mode; p.n = n; p.Hm = Hm; p.Wm = Wm;
     p.tiles_w = Wm / p.TW; p.tiles_h = Hm / p.TH;
     const int tiles_n = (n + p.TN - 1) / p.TN;
@@ -861,7 +692,7 @@ int umma_conv(int mode, const void* src, const void* W, void* out, int n, const 
     if (rc) return rc;
     long long mtiles = (long long)p.tiles_w * p.tiles_h * tiles_n;
     if (mtiles > 0x7fffffffLL) return 0;
-    if (persistent) {
+    {
         UmmaConvParamsP pp;
         pp.c = p;
         pp.m_subtiles = (int)mtiles;
@@ -874,9 +705,6 @@ int umma_conv(int mode, const void* src, const void* W, void* out, int n, const 
         if (BN == 128) return MT == 2 ? launch_conv_persistent<2, 128>(tmA, tmB, pp, st) : launch_conv_persistent<1, 128>(tmA, tmB, pp, st);
         return MT == 2 ? launch_conv_persistent<2, 64>(tmA, tmB, pp, st) : launch_conv_persistent<1, 64>(tmA, tmB, pp, st);
     }
-    dim3 grid((unsigned)mtiles, Cout / BN, phases);
-    if (BN == 128) return launch_conv<128>(tmA, tmB, p, grid, st);
-    return launch_conv<64>(tmA, tmB, p, grid, st);
 }
 
 int umma_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, cudaStream_t st) {
