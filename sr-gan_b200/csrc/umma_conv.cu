@@ -417,7 +417,8 @@ __global__ void __launch_bounds__(PC_THREADS, 1) umma_conv_persistent_kernel(con
 //   N = BN channels b per tap (B operand MN-major), K = pixels, NT taps accumulate side by side in TMEM
 //   (NT*BN <= 512 columns) so one S tile feeds NT MMAs.  K is split across CTAs (blockIdx.z).
 // ------------------------------------------------------------------------------------------------------------
-constexpr int WG_PIX = 64;                       // pixels (K) per stage
+// pixels (K) per stage: 32 (40 KB stages, five in flight) for BN >= 128; 64 for BN = 64, where a stage is ten small TMA
+// boxes and the per-box issue cost matters more than ring depth
 constexpr int WG_THREADS = 192;
 
 struct UmmaWgradParams {
@@ -430,13 +431,13 @@ struct UmmaWgradParams {
     int stages;
 };
 
-template <int BN>
+template <int BN, int WG_PIX>
 __global__ void __launch_bounds__(WG_THREADS) umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmS,
                                                                 const __grid_constant__ CUtensorMap tmL,
                                                                 const UmmaWgradParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[4];
-    __shared__ __align__(8) uint64_t empty_bar[4];
+    __shared__ __align__(8) uint64_t full_bar[8];
+    __shared__ __align__(8) uint64_t empty_bar[8];
     __shared__ __align__(8) uint64_t tmem_full_bar;
     __shared__ uint32_t tmem_slot;
 
@@ -638,18 +639,19 @@ int launch_conv_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaC
     return 1;
 }
 
-template <int BN>
+template <int BN, int WG_PIX>
 int launch_wgrad(const CUtensorMap& tmS, const CUtensorMap& tmL, UmmaWgradParams& p, dim3 grid, cudaStream_t st) {
     const int stage_bytes = 2 * WG_PIX * 128 + p.NT * (BN / 64) * WG_PIX * 128;
-    p.stages = 2;
+    p.stages = (200 * 1024) / stage_bytes;
+    if (p.stages > 8) p.stages = 8;
     size_t smem = (size_t)p.stages * stage_bytes + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(umma_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(umma_wgrad_kernel<BN, WG_PIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024);
         if (e != cudaSuccess) { srgan_set_error("cudaFuncSetAttribute(umma_wgrad_kernel): %s", cudaGetErrorString(e)); return SRGAN_ERR_CUDA; }
         attr_set = true;
     }
-    umma_wgrad_kernel<BN><<<grid, WG_THREADS, smem, st>>>(tmS, tmL, p);
+    umma_wgrad_kernel<BN, WG_PIX><<<grid, WG_THREADS, smem, st>>>(tmS, tmL, p);
     SRGAN_CHECK_LAUNCH("umma_wgrad_kernel");
     return 1;
 }
@@ -712,11 +714,11 @@ int umma_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom*
     const int BN = g->Cb % 256 == 0 ? 256 : (g->Cb % 128 == 0 ? 128 : 64);
     const int taps = g->R * g->S;
     int NT = 512 / BN;
-    // shared memory per stage: 16 KB (S) + NT * BN * 128 B (L taps); two stages must fit in ~200 KB
-    while (NT > 1 && (taps % NT != 0 || 2 * (2 * WG_PIX * 128 + NT * (BN / 64) * WG_PIX * 128) > 198 * 1024)) NT >>= 1;
+    while (NT > 1 && taps % NT != 0) NT >>= 1;
     if (taps % NT != 0) return 0;
     if (g->stride > 8) return 0;
     UmmaWgradParams p;
+    const int WG_PIX = BN == 64 ? 64 : 32;
     if (!pick_patch(g->Ws, g->Hs, WG_PIX, 8, p.TW, p.TH, p.TN)) return 0;
     if (p.TW * g->stride > 256 || p.TH * g->stride > 256) return 0;
     if (((uintptr_t)S & 15) || ((uintptr_t)L & 15) || ((uintptr_t)dW & 15)) return 0;
@@ -725,8 +727,8 @@ int umma_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom*
     p.NT = NT; p.dW = dW;
     const int total_chunks = p.tiles_w * p.tiles_h * p.tiles_n;
     const int out_tiles = ((g->Ca + 127) / 128) * (taps / NT) * (g->Cb / BN);
-    int splits = (kNumSMs + out_tiles - 1) / out_tiles;
-    int max_splits = (total_chunks + 3) / 4;                  // at least 4 stages of work per CTA
+    int splits = kNumSMs / out_tiles;                         // one CTA per SM (512 TMEM columns each): never a second wave
+    int max_splits = (total_chunks + 7) / 8;                  // at least 8 stages of work per CTA
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     p.chunks_per_split = (total_chunks + splits - 1) / splits;
@@ -737,7 +739,7 @@ int umma_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom*
     rc = encode_act(&tmL, L, n, g->Hl, g->Wl, g->Cb, p.TW, p.TH, p.TN, g->stride);
     if (rc) return rc;
     dim3 grid(out_tiles, 1, splits);
-    if (BN == 256) return launch_wgrad<256>(tmS, tmL, p, grid, st);
-    if (BN == 128) return launch_wgrad<128>(tmS, tmL, p, grid, st);
-    return launch_wgrad<64>(tmS, tmL, p, grid, st);
+    if (BN == 256) return launch_wgrad<256, 32>(tmS, tmL, p, grid, st);
+    if (BN == 128) return launch_wgrad<128, 32>(tmS, tmL, p, grid, st);
+    return launch_wgrad<64, 64>(tmS, tmL, p, grid, st);
 }

@@ -38,6 +38,15 @@ SC_DNN, SC_LABELED, SC_UNLABELED, SC_FAKE, SC_GP, SC_GNORM, SC_GEN = range(7)
 N_SCALARS = 8
 
 
+def partial_scalar_slots(method: str):
+    """Scalar slots that hold per-rank PARTIAL sums (per-sample loss terms, already divided by the global batch) and must
+    be summed across ranks before they are read; the SR-GAN feature-distance losses are computed from all-reduced
+    feature sums and are already global on every rank.  In DG-GAN every loss is a per-sample BCE mean."""
+    if method == 'dggan':
+        return (SC_DNN, SC_LABELED, SC_UNLABELED, SC_FAKE, SC_GP, SC_GNORM, SC_GEN)
+    return (SC_DNN, SC_LABELED, SC_GP, SC_GNORM)
+
+
 def _strides_for(layer_kind: str, dims, Ca, Cb, R, S):
     """Element strides, per master dim, into the Wd[a][r][s][b] and Wu[b][r][s][a] kernel layouts (nets.py)."""
     if layer_kind == 'conv':        # master[a][b][r][s]
@@ -168,6 +177,7 @@ class Engine:
     # ------------------------------------------------------------------ weights
     def repack(self, st: NetState):
         """Master (torch layout, fp32) -> kernel layouts.  Also done by the fused Adam after every update."""
+        self.ops.begin()
         for l in st.net.layers:
             w = st.params[l.name + '.weight']
             wd_s, wu_s = st.strides(l)
@@ -402,6 +412,7 @@ class Engine:
 
     # ------------------------------------------------------------------ DNN step (srgan.py:259-271)
     def dnn_step(self, x, y, cfg, lr, weight_decay):
+        self.ops.begin()
         st, net = self.DNN, self.d_net
         B = x.shape[0]
         Bg = self._global_batch(B)
@@ -428,6 +439,7 @@ class Engine:
     # ------------------------------------------------------------------ GAN step (srgan.py:273-320)
     def gan_step(self, x, y, u, z, alpha, z2, cfg, train_generator=True):
         ops, D, G, net, gnet = self.ops, self.D, self.G, self.d_net, self.g_net
+        ops.begin()
         B = x.shape[0]
         if u.shape[0] != B or z.shape[0] != B or alpha.numel() != B:
             # srgan.py:363 draws alpha with settings.batch_size rows: the reference itself requires full batches
@@ -589,6 +601,7 @@ class Engine:
     # ------------------------------------------------------------------ inference-style helpers
     def d_features(self, x, st: Optional[NetState] = None):
         """D(x) forward only: returns (prediction [B], features rows [B, F] in NHWC order)."""
+        self.ops.begin()
         st = st or self.D
         net = st.net
         B = x.shape[0]
@@ -601,6 +614,7 @@ class Engine:
         return pred, feats
 
     def g_generate(self, z):
+        self.ops.begin()
         gnet = self.g_net
         B = z.shape[0]
         gacts = self.alloc_acts('G', gnet, B)

@@ -24,7 +24,8 @@ import torch
 from torch import nn
 
 from . import nets
-from .engine import Engine, DIST_KINDS, SC_DNN, SC_LABELED, SC_UNLABELED, SC_FAKE, SC_GP, SC_GNORM, SC_GEN
+from .engine import (Engine, DIST_KINDS, SC_DNN, SC_LABELED, SC_UNLABELED, SC_FAKE, SC_GP, SC_GNORM, SC_GEN,
+                     partial_scalar_slots)
 
 
 # ------------------------------------------------------------------------------------------------ utility.py mirror
@@ -248,7 +249,7 @@ class StepRunner:
         s = self.engine.scalars
         if self.engine.comm is not None:
             s = s.clone()
-            self.engine.comm.all_reduce_sum_partial(s, (SC_DNN, SC_LABELED, SC_GP, SC_GNORM))
+            self.engine.comm.all_reduce_sum_partial(s, partial_scalar_slots(self.method))
         v = s.tolist()
         return {'dnn_loss': v[SC_DNN], 'labeled_loss': v[SC_LABELED], 'unlabeled_loss': v[SC_UNLABELED],
                 'fake_loss': v[SC_FAKE], 'gradient_penalty': v[SC_GP], 'gradient_norm_mean': v[SC_GNORM],

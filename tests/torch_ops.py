@@ -34,6 +34,9 @@ class TorchOps:
     def __init__(self):
         self.launches = 0
 
+    def begin(self):
+        pass
+
     # ---- layouts
     @staticmethod
     def _scatter(w, dims, out, strides):
