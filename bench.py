@@ -235,7 +235,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     ms_per_step = ms / args.steps
-    value = 1e3 / ms_per_step                              # global steps/s (weak scaling: every rank steps together)
+    global_steps = 1e3 / ms_per_step                       # optimizer steps/s of the whole job
+    # whole-job throughput in units of one-GPU steps (a 100-sample dnn+gan step): every global step at N ranks does N
+    # of them (weak scaling), so value = N * global steps/s; at N=1 the two coincide
+    value = global_steps * world
 
     # ---------------- end-to-end timing: host buffers in, scalars out, every step
     for i in range(3):
@@ -251,7 +254,7 @@ def main():
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = 1e3 / (float(t.item()) / args.steps)
+    e2e_value = world * 1e3 / (float(t.item()) / args.steps)
     h2d = xh.numel() * 4 + yh.numel() * 4 + uh.numel() * 4
     d2h = eng.scalars.numel() * 4
 
@@ -274,6 +277,8 @@ def main():
                 'config': {'workload': f'age SR-GAN (BASELINE configs[1]): DCGAN G/D, 3x128x128, per-GPU batch {B}, global batch {B * world}, dnn_training_step + gan_training_step, generator period 1',
                            'precision_mode': args.precision, 'parallelism': f'dp{world}',
                            'l2': 'inputs (39 MB/step) and activations (~1 GB/step) exceed the 126 MB L2; no flush needed',
+                           'global_steps_per_s': global_steps,
+                           'value_definition': 'n_gpus x global optimizer steps/s = 100-sample step-equivalents per second over the whole job',
                            'step_algorithmic_tflops': step_tflops,
                            'step_frac_of_bf16_sustained_peak': step_tflops / (pk['bf16_tflops_sustained'] * world)},
                 'roofline': roof, 'clocks': clocks, 'gpu_launches': int(launches),
