@@ -289,6 +289,47 @@ __global__ void __launch_bounds__(256) col2im_kernel(const T* __restrict__ col, 
     }
 }
 
+// 3 channels, k4 s2 p1, kpad 64, bf16: one thread per large-side pixel, exactly 2 x 2 taps, no divisions
+__global__ void __launch_bounds__(256) col2im_c3k4s2_kernel(const bf16* __restrict__ col, bf16* __restrict__ out, int n, int Hs,
+                                                            int Ws, const float* __restrict__ bias,
+                                                            const bf16* __restrict__ href, int epi, int act, float slope) {
+    const int Hl = 2 * Hs, Wl = 2 * Ws;
+    const long long total = (long long)n * Hl * Wl;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int iw = (int)(i % Wl);
+        const long long t = i / Wl;
+        const int ih = (int)(t % Hl);
+        const int nn = (int)(t / Hl);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        const int r0 = (ih + 1) & 1, s0 = (iw + 1) & 1;
+#pragma unroll
+        for (int dr = 0; dr < 2; ++dr) {
+            const int r = r0 + 2 * dr;
+            const int oh = (ih + 1 - r) >> 1;
+            if (oh < 0 || oh >= Hs) continue;
+#pragma unroll
+            for (int ds = 0; ds < 2; ++ds) {
+                const int sx = s0 + 2 * ds;
+                const int ow = (iw + 1 - sx) >> 1;
+                if (ow < 0 || ow >= Ws) continue;
+                const bf16* c = col + (((long long)nn * Hs + oh) * Ws + ow) * 64 + (r * 4 + sx) * 3;
+                a0 += to_f(c[0]); a1 += to_f(c[1]); a2 += to_f(c[2]);
+            }
+        }
+        float v[3] = {a0, a1, a2};
+        if (epi == SRGAN_EPI_BIAS_ACT) {
+#pragma unroll
+            for (int b = 0; b < 3; ++b) v[b] = act_fwd(v[b] + (bias ? bias[b] : 0.f), act, slope);
+        } else if (href != nullptr && act != SRGAN_ACT_NONE) {
+#pragma unroll
+            for (int b = 0; b < 3; ++b) v[b] *= act_bwd(to_f(href[i * 3 + b]), act, slope);
+        }
+        bf16* o = out + i * 3;
+        o[0] = from_f<bf16>(v[0]); o[1] = from_f<bf16>(v[1]); o[2] = from_f<bf16>(v[2]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // interpolate: out[n,e] = alpha[n]*u[n,e] + (1-alpha[n])*fake[n,e]
 // ------------------------------------------------------------------------------------------------------------
@@ -385,29 +426,71 @@ __global__ void __launch_bounds__(1024) distance_kernel(const float* __restrict_
     }
 }
 
+// multi-block version for the distance functions that are a mean of an element-wise function (kinds 0..4): every block
+// reduces its slice, adds its share of the loss atomically and writes its slice of the gradients
+__global__ void __launch_bounds__(256) distance_mb_kernel(const float* __restrict__ sb, const float* __restrict__ so, int F,
+                                                          float inv_B, int kind, float mult, float* loss, float* gbase,
+                                                          float* gother, int accumulate_base) {
+    __shared__ float red[32];
+    const float invF = 1.f / (float)F;
+    const float k = mult * inv_B;
+    float acc = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < F; i += gridDim.x * blockDim.x) {
+        const float d = (sb[i] - so[i]) * inv_B;
+        const float ad = fabsf(d);
+        const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+        float g;
+        if (kind == 0) { acc += ad; g = sg * invF; }
+        else if (kind == 1) { acc -= ad; g = -sg * invF; }
+        else if (kind == 2) { const float r = sqrtf(ad + 1.f); acc -= r; g = -sg * invF * 0.5f / r; }
+        else if (kind == 3) { acc -= logf(ad + 1.f); g = -sg * invF / (ad + 1.f); }
+        else { acc += d * d; g = 2.f * d * invF; }
+        g *= k;
+        if (accumulate_base) gbase[i] += g; else gbase[i] = g;
+        gother[i] = -g;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(loss, mult * acc * invF);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // gradient-penalty kernels (one block per sample / row)
 // ------------------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) feature_norm_seed_kernel(const T* __restrict__ h, int cols, float* __restrict__ s_out,
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(512) feature_norm_seed_kernel(const T* __restrict__ h, int cols, float* __restrict__ s_out,
                                                                 T* __restrict__ gamma, int act, float slope) {
     __shared__ float red[32];
     const T* x = h + (long long)blockIdx.x * cols;
     T* g = gamma + (long long)blockIdx.x * cols;
     float acc = 0.f;
-    for (int c = threadIdx.x; c < cols; c += blockDim.x) { float v = to_f(x[c]); acc = fmaf(v, v, acc); }
+    if (VEC) {
+        for (int c = threadIdx.x * 4; c < cols; c += blockDim.x * 4) {
+            float4 v = ld4(x + c);
+            acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+    } else {
+        for (int c = threadIdx.x; c < cols; c += blockDim.x) { float v = to_f(x[c]); acc = fmaf(v, v, acc); }
+    }
     acc = block_sum(acc, red);
-    float s = sqrtf(acc);
+    const float s = sqrtf(acc);
     if (threadIdx.x == 0) s_out[blockIdx.x] = s;
-    float inv = 1.f / s;
-    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-        float v = to_f(x[c]);
-        g[c] = from_f<T>(v * inv * act_bwd(v, act, slope));
+    const float inv = 1.f / s;
+    if (VEC) {
+        for (int c = threadIdx.x * 4; c < cols; c += blockDim.x * 4) {
+            float4 v = ld4(x + c);          // second pass: the 64 KB row is L1/L2 resident
+            st4(g + c, make_float4(v.x * inv * act_bwd(v.x, act, slope), v.y * inv * act_bwd(v.y, act, slope),
+                                   v.z * inv * act_bwd(v.z, act, slope), v.w * inv * act_bwd(v.w, act, slope)));
+        }
+    } else {
+        for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+            float v = to_f(x[c]);
+            g[c] = from_f<T>(v * inv * act_bwd(v, act, slope));
+        }
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) gp_feature_seed_kernel(const T* __restrict__ uL, const T* __restrict__ hL,
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(512) gp_feature_seed_kernel(const T* __restrict__ uL, const T* __restrict__ hL,
                                                               const float* __restrict__ s, T* __restrict__ out, int cols,
                                                               int act, float slope) {
     __shared__ float red[32];
@@ -416,12 +499,31 @@ __global__ void __launch_bounds__(256) gp_feature_seed_kernel(const T* __restric
     T* o = out + (long long)blockIdx.x * cols;
     const float inv = 1.f / s[blockIdx.x];
     float acc = 0.f;
-    for (int c = threadIdx.x; c < cols; c += blockDim.x) acc = fmaf(to_f(h[c]) * inv, to_f(u[c]), acc);
+    if (VEC) {
+        for (int c = threadIdx.x * 4; c < cols; c += blockDim.x * 4) {
+            float4 hv = ld4(h + c), uv = ld4(u + c);
+            acc += (hv.x * uv.x + hv.y * uv.y + hv.z * uv.z + hv.w * uv.w) * inv;
+        }
+    } else {
+        for (int c = threadIdx.x; c < cols; c += blockDim.x) acc = fmaf(to_f(h[c]) * inv, to_f(u[c]), acc);
+    }
     const float dot = block_sum(acc, red);
-    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-        float hv = to_f(h[c]);
-        float g = hv * inv;
-        o[c] = from_f<T>((to_f(u[c]) - g * dot) * inv * act_bwd(hv, act, slope));
+    if (VEC) {
+        for (int c = threadIdx.x * 4; c < cols; c += blockDim.x * 4) {
+            float4 hv = ld4(h + c), uv = ld4(u + c);
+            float4 r;
+            r.x = (uv.x - hv.x * inv * dot) * inv * act_bwd(hv.x, act, slope);
+            r.y = (uv.y - hv.y * inv * dot) * inv * act_bwd(hv.y, act, slope);
+            r.z = (uv.z - hv.z * inv * dot) * inv * act_bwd(hv.z, act, slope);
+            r.w = (uv.w - hv.w * inv * dot) * inv * act_bwd(hv.w, act, slope);
+            st4(o + c, r);
+        }
+    } else {
+        for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+            float hv = to_f(h[c]);
+            float g = hv * inv;
+            o[c] = from_f<T>((to_f(u[c]) - g * dot) * inv * act_bwd(hv, act, slope));
+        }
     }
 }
 
@@ -626,6 +728,10 @@ int srgan_col2im(const void* col, void* L_out, int n, const srgan_geom* g, int k
     cudaStream_t st = (cudaStream_t)stream;
     long long items = (long long)n * g->Hl * g->Wl;
     if (dtype == SRGAN_F32) col2im_kernel<float><<<ew_grid(items, 256), 256, 0, st>>>((const float*)col, (float*)L_out, p, bias, (const float*)href, epi, act, slope);
+    else if (g->Cb == 3 && g->R == 4 && g->S == 4 && g->stride == 2 && g->pad == 1 && kpad == 64 && g->Hl == 2 * g->Hs &&
+             g->Wl == 2 * g->Ws)
+        col2im_c3k4s2_kernel<<<ew_grid(items, 256), 256, 0, st>>>((const bf16*)col, (bf16*)L_out, n, g->Hs, g->Ws, bias,
+                                                                 (const bf16*)href, epi, act, slope);
     else col2im_kernel<bf16><<<ew_grid(items, 256), 256, 0, st>>>((const bf16*)col, (bf16*)L_out, p, bias, (const bf16*)href, epi, act, slope);
     SRGAN_CHECK_LAUNCH("col2im_kernel");
     return SRGAN_OK;
@@ -669,8 +775,14 @@ int srgan_distance(const float* sum_base, const float* sum_other, int F, float i
                    float* loss, float* gbase, float* gother, int accumulate_base, void* stream) {
     SRGAN_REQUIRE(sum_base && sum_other && loss && gbase && gother && F > 0, "srgan_distance: bad arguments");
     SRGAN_REQUIRE(kind >= 0 && kind <= 5, "srgan_distance: unknown distance kind %d", kind);
-    distance_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(sum_base, sum_other, F, inv_B, kind, mult, loss, gbase, gother,
-                                                          accumulate_base);
+    if (kind != 5 && F >= 4096) {
+        int grid = (F + 1023) / 1024;
+        if (grid > 2 * kNumSMs) grid = 2 * kNumSMs;
+        distance_mb_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sum_base, sum_other, F, inv_B, kind, mult, loss, gbase,
+                                                                   gother, accumulate_base);
+    } else
+        distance_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(sum_base, sum_other, F, inv_B, kind, mult, loss, gbase, gother,
+                                                              accumulate_base);
     SRGAN_CHECK_LAUNCH("distance_kernel");
     return SRGAN_OK;
 }
@@ -680,8 +792,14 @@ int srgan_feature_norm_seed(const void* h, int rows, int cols, float* s_out, voi
     SRGAN_REQUIRE(h && s_out && gamma_out && rows >= 0 && cols > 0, "srgan_feature_norm_seed: bad arguments");
     if (rows == 0) return SRGAN_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == SRGAN_F32) feature_norm_seed_kernel<float><<<rows, 256, 0, st>>>((const float*)h, cols, s_out, (float*)gamma_out, act, slope);
-    else feature_norm_seed_kernel<bf16><<<rows, 256, 0, st>>>((const bf16*)h, cols, s_out, (bf16*)gamma_out, act, slope);
+    const int th = cols >= 2048 ? 512 : 128;
+    if (cols % 4 == 0) {
+        if (dtype == SRGAN_F32) feature_norm_seed_kernel<float, true><<<rows, th, 0, st>>>((const float*)h, cols, s_out, (float*)gamma_out, act, slope);
+        else feature_norm_seed_kernel<bf16, true><<<rows, th, 0, st>>>((const bf16*)h, cols, s_out, (bf16*)gamma_out, act, slope);
+    } else {
+        if (dtype == SRGAN_F32) feature_norm_seed_kernel<float, false><<<rows, th, 0, st>>>((const float*)h, cols, s_out, (float*)gamma_out, act, slope);
+        else feature_norm_seed_kernel<bf16, false><<<rows, th, 0, st>>>((const bf16*)h, cols, s_out, (bf16*)gamma_out, act, slope);
+    }
     SRGAN_CHECK_LAUNCH("feature_norm_seed_kernel");
     return SRGAN_OK;
 }
@@ -691,8 +809,14 @@ int srgan_gp_feature_seed(const void* uL, const void* hL, const float* s, void* 
     SRGAN_REQUIRE(uL && hL && s && out && rows >= 0 && cols > 0, "srgan_gp_feature_seed: bad arguments");
     if (rows == 0) return SRGAN_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == SRGAN_F32) gp_feature_seed_kernel<float><<<rows, 256, 0, st>>>((const float*)uL, (const float*)hL, s, (float*)out, cols, act, slope);
-    else gp_feature_seed_kernel<bf16><<<rows, 256, 0, st>>>((const bf16*)uL, (const bf16*)hL, s, (bf16*)out, cols, act, slope);
+    const int th = cols >= 2048 ? 512 : 128;
+    if (cols % 4 == 0) {
+        if (dtype == SRGAN_F32) gp_feature_seed_kernel<float, true><<<rows, th, 0, st>>>((const float*)uL, (const float*)hL, s, (float*)out, cols, act, slope);
+        else gp_feature_seed_kernel<bf16, true><<<rows, th, 0, st>>>((const bf16*)uL, (const bf16*)hL, s, (bf16*)out, cols, act, slope);
+    } else {
+        if (dtype == SRGAN_F32) gp_feature_seed_kernel<float, false><<<rows, th, 0, st>>>((const float*)uL, (const float*)hL, s, (float*)out, cols, act, slope);
+        else gp_feature_seed_kernel<bf16, false><<<rows, th, 0, st>>>((const bf16*)uL, (const bf16*)hL, s, (bf16*)out, cols, act, slope);
+    }
     SRGAN_CHECK_LAUNCH("gp_feature_seed_kernel");
     return SRGAN_OK;
 }
