@@ -128,13 +128,17 @@ int srgan_gp_feature_seed(const void* uL, const void* hL, const float* s, void* 
                           float slope, int dtype, void* stream);
 
 /* ---- optimizer ----------------------------------------------------------------------------------------------
- * torch.optim.Adam.step (srgan.py:136-138,266,297,305) for one tensor, fused with the rewrite of its kernel-layout
- * copies.  param/m/v: fp32, torch layout [d0,d1,d2,d3]; grad: fp32, element (i0..i3) at sum i_k*gstride[k];
+ * torch.optim.Adam.step (srgan.py:136-138,266,297,305).  The step-dependent scalars live in DEVICE memory so that a
+ * captured CUDA graph of the training step can be replayed: srgan_adam_prepare advances state[0] = t and writes
+ * state[1] = lr / (1 - beta1^t), state[2] = 1 / sqrt(1 - beta2^t) (computed in double like torch does on the host);
+ * srgan_adam then updates one tensor and rewrites its kernel-layout copies.
+ * param/m/v: fp32, torch layout [d0,d1,d2,d3]; grad: fp32, element (i0..i3) at sum i_k*gstride[k];
  * out1/out2 (may be NULL): activation-dtype (or fp32 when out_dtype == SRGAN_F32) copies at sum i_k*ostride[k].
- * bc1 = 1-beta1^t, bc2 = 1-beta2^t.  L2 (coupled) weight decay like torch. */
+ * L2 (coupled) weight decay like torch. */
+int srgan_adam_prepare(float* state3, double lr, double beta1, double beta2, void* stream);
 int srgan_adam(float* param, const float* grad, float* m, float* v, const int* dims4, const long long* gstrides4,
                void* out1, const long long* o1strides4, void* out2, const long long* o2strides4, int out_dtype,
-               float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2, void* stream);
+               const float* state3, float beta1, float beta2, float eps, float weight_decay, void* stream);
 /* layout copies only (initial weights / after load_models, srgan.py:221-251) */
 int srgan_repack(const float* param, const int* dims4, void* out1, const long long* o1strides4, void* out2,
                  const long long* o2strides4, int out_dtype, void* stream);

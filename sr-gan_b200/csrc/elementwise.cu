@@ -570,8 +570,11 @@ struct Dims4 { int d[4]; long long gs[4], s1[4], s2[4]; };
 template <typename TO, bool UPDATE>
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ param, const float* __restrict__ grad,
                                                    float* __restrict__ m, float* __restrict__ v, Dims4 dm,
-                                                   TO* __restrict__ out1, TO* __restrict__ out2, float step_size,
-                                                   float beta1, float beta2, float eps, float wd, float inv_sqrt_bc2) {
+                                                   TO* __restrict__ out1, TO* __restrict__ out2,
+                                                   const float* __restrict__ state, float beta1, float beta2, float eps,
+                                                   float wd) {
+    float step_size = 0.f, inv_sqrt_bc2 = 0.f;
+    if (UPDATE) { step_size = state[1]; inv_sqrt_bc2 = state[2]; }
     const long long total = (long long)dm.d[0] * dm.d[1] * dm.d[2] * dm.d[3];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -594,6 +597,13 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ param, co
         if (out1) out1[i0 * dm.s1[0] + i1 * dm.s1[1] + i2 * dm.s1[2] + i3 * dm.s1[3]] = from_f<TO>(p);
         if (out2) out2[i0 * dm.s2[0] + i1 * dm.s2[1] + i2 * dm.s2[2] + i3 * dm.s2[3]] = from_f<TO>(p);
     }
+}
+
+__global__ void adam_prepare_kernel(float* state, double lr, double beta1, double beta2) {
+    const double t = (double)state[0] + 1.0;
+    state[0] = (float)t;
+    state[1] = (float)(lr / (1.0 - pow(beta1, t)));
+    state[2] = (float)(1.0 / sqrt(1.0 - pow(beta2, t)));
 }
 
 static inline int ew_grid(long long work_items, int block) {
@@ -850,22 +860,28 @@ static int fill_dims(Dims4& dm, const int* dims4, const long long* gs, const lon
     return 0;
 }
 
+int srgan_adam_prepare(float* state3, double lr, double beta1, double beta2, void* stream) {
+    SRGAN_REQUIRE(state3 != nullptr, "srgan_adam_prepare: null state");
+    adam_prepare_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state3, lr, beta1, beta2);
+    SRGAN_CHECK_LAUNCH("adam_prepare_kernel");
+    return SRGAN_OK;
+}
+
 int srgan_adam(float* param, const float* grad, float* m, float* v, const int* dims4, const long long* gstrides4,
                void* out1, const long long* o1strides4, void* out2, const long long* o2strides4, int out_dtype,
-               float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2, void* stream) {
-    SRGAN_REQUIRE(param && grad && m && v && dims4 && gstrides4, "srgan_adam: bad arguments");
+               const float* state3, float beta1, float beta2, float eps, float weight_decay, void* stream) {
+    SRGAN_REQUIRE(param && grad && m && v && dims4 && gstrides4 && state3, "srgan_adam: bad arguments");
     SRGAN_REQUIRE((out1 == nullptr) || o1strides4, "srgan_adam: out1 without strides");
     SRGAN_REQUIRE((out2 == nullptr) || o2strides4, "srgan_adam: out2 without strides");
     Dims4 dm;
     SRGAN_REQUIRE(fill_dims(dm, dims4, gstrides4, o1strides4, o2strides4) == 0, "srgan_adam: non-positive dim");
     long long total = (long long)dm.d[0] * dm.d[1] * dm.d[2] * dm.d[3];
     cudaStream_t st = (cudaStream_t)stream;
-    float step_size = lr / bc1, isb = 1.f / sqrtf(bc2);
     int grid = ew_grid(total, 256);
     if (out_dtype == SRGAN_F32)
-        adam_kernel<float, true><<<grid, 256, 0, st>>>(param, grad, m, v, dm, (float*)out1, (float*)out2, step_size, beta1, beta2, eps, weight_decay, isb);
+        adam_kernel<float, true><<<grid, 256, 0, st>>>(param, grad, m, v, dm, (float*)out1, (float*)out2, state3, beta1, beta2, eps, weight_decay);
     else
-        adam_kernel<bf16, true><<<grid, 256, 0, st>>>(param, grad, m, v, dm, (bf16*)out1, (bf16*)out2, step_size, beta1, beta2, eps, weight_decay, isb);
+        adam_kernel<bf16, true><<<grid, 256, 0, st>>>(param, grad, m, v, dm, (bf16*)out1, (bf16*)out2, state3, beta1, beta2, eps, weight_decay);
     SRGAN_CHECK_LAUNCH("adam_kernel");
     return SRGAN_OK;
 }
@@ -879,9 +895,9 @@ int srgan_repack(const float* param, const int* dims4, void* out1, const long lo
     cudaStream_t st = (cudaStream_t)stream;
     int grid = ew_grid(total, 256);
     if (out_dtype == SRGAN_F32)
-        adam_kernel<float, false><<<grid, 256, 0, st>>>(const_cast<float*>(param), nullptr, nullptr, nullptr, dm, (float*)out1, (float*)out2, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
+        adam_kernel<float, false><<<grid, 256, 0, st>>>(const_cast<float*>(param), nullptr, nullptr, nullptr, dm, (float*)out1, (float*)out2, nullptr, 0.f, 0.f, 0.f, 0.f);
     else
-        adam_kernel<bf16, false><<<grid, 256, 0, st>>>(const_cast<float*>(param), nullptr, nullptr, nullptr, dm, (bf16*)out1, (bf16*)out2, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
+        adam_kernel<bf16, false><<<grid, 256, 0, st>>>(const_cast<float*>(param), nullptr, nullptr, nullptr, dm, (bf16*)out1, (bf16*)out2, nullptr, 0.f, 0.f, 0.f, 0.f);
     SRGAN_CHECK_LAUNCH("repack_kernel");
     return SRGAN_OK;
 }

@@ -109,7 +109,8 @@ class NetState:
         self.grad = torch.zeros(g_total, dtype=mdt, device=device)
         self.exp_avg = torch.zeros(n_total, dtype=mdt, device=device)
         self.exp_avg_sq = torch.zeros(n_total, dtype=mdt, device=device)
-        self.adam_step = 0
+        # [t, lr/(1-beta1^t), 1/sqrt(1-beta2^t)] in device memory (fp64 in the fp64 schedule tests): see srgan_adam_prepare
+        self.adam_state = torch.zeros(3, dtype=mdt, device=device)
         self.wd_, self.wu_ = {}, {}
         for l in net.layers:
             n = params[l.name + '.weight'].numel()
@@ -361,29 +362,26 @@ class Engine:
         layout copies.  Gradients are read from (and then zeroed in) the flat buffer."""
         if self.comm is not None:
             self.comm.all_reduce_sum(st.grad)
-        st.adam_step += 1
-        t = st.adam_step
-        bc1 = 1.0 - betas[0] ** t
-        bc2 = 1.0 - betas[1] ** t
+        self.ops.adam_prepare(st.adam_state, lr, betas[0], betas[1])
         for l in st.net.layers:
             wd_s, wu_s = st.strides(l)
             k = l.name + '.weight'
             wd, wu = self._needed_layouts(st, l)
             self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), l.master_dims, wd_s, wd, wd_s if wd is not None else None,
-                          wu, wu_s if wu is not None else None, lr, betas[0], betas[1], eps, weight_decay, bc1, bc2)
+                          wu, wu_s if wu is not None else None, st.adam_state, betas[0], betas[1], eps, weight_decay)
             k = l.name + '.bias'
             nb = st.params[k].numel()
             self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), (nb, 1, 1, 1), (1, 0, 0, 0), None, None, None, None,
-                          lr, betas[0], betas[1], eps, weight_decay, bc1, bc2)
+                          st.adam_state, betas[0], betas[1], eps, weight_decay)
         if st.net.head:
             dims, s = self._head_strides(st.net)
             k = st.net.head + '.weight'
             self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), dims, s, st.whead, s, None, None,
-                          lr, betas[0], betas[1], eps, weight_decay, bc1, bc2)
+                          st.adam_state, betas[0], betas[1], eps, weight_decay)
             k = st.net.head + '.bias'
             nb = st.params[k].numel()
             self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), (nb, 1, 1, 1), (1, 0, 0, 0), None, None, None, None,
-                          lr, betas[0], betas[1], eps, weight_decay, bc1, bc2)
+                          st.adam_state, betas[0], betas[1], eps, weight_decay)
         st.grad.zero_()
 
     # ------------------------------------------------------------------ inputs

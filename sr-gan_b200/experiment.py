@@ -216,6 +216,11 @@ class StepRunner:
                              act_dtype=torch.float32 if precision == 'fp32' else torch.bfloat16, device=dev, comm=comm)
         self.generator = torch.Generator(device=dev)
         self.generator.manual_seed(0)
+        import os
+        ug = getattr(settings, 'use_cuda_graph', True)
+        # NCCL collectives inside a captured graph are left for a later round: multi-rank steps run eagerly
+        self.use_cuda_graph = bool(ug) and os.environ.get('SRGAN_NO_GRAPH', '0') != '1' and comm is None
+        self._graphs, self._statics = {}, {}
 
     # ---- noise (srgan.py:286-289, :364, :301) drawn on the device
     def draw_noise(self, B, cfg):
@@ -232,17 +237,64 @@ class StepRunner:
     def config(self):
         return StepConfig(self.settings, self.method)
 
+    # ---- CUDA-graph replay of the two step methods -----------------------------------------------------------------
+    # The step is ~140 small-to-medium launches; replaying a captured graph removes the per-launch host cost (3.2 ms of
+    # Python per age step) and the inter-kernel gaps.  Everything step-dependent lives in device memory (inputs and
+    # noise are copied into static buffers, Adam's bias corrections come from srgan_adam_prepare), so a graph is valid
+    # until the batch size, lr / weight decay or the generator flag changes.  First call = eager (allocates the
+    # workspaces), second call = capture, later calls = replay.  SRGAN_NO_GRAPH=1 or use_cuda_graph=False -> eager.
+    def _graphed(self, key, statics, fn):
+        """statics: list of (static_buffer, source tensor) copied before replay; fn(): enqueues the step on statics."""
+        entry = self._graphs.get(key)
+        if entry is None:
+            self._graphs[key] = {'calls': 1, 'graph': None}
+            for dst, src in statics:
+                dst.copy_(src)
+            fn()
+            return
+        for dst, src in statics:
+            dst.copy_(src)
+        if entry['graph'] is None:
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            entry['graph'] = g
+        entry['graph'].replay()
+
+    def _static(self, name, like, dtype=torch.float32):
+        t = self._statics.get(name)
+        if t is None or t.shape != like.shape:
+            t = torch.empty(like.shape, dtype=dtype, device=self.device)
+            self._statics[name] = t
+        return t
+
     def dnn_step(self, examples, labels, lr=None, weight_decay=None):
         cfg = self.config()
-        self.engine.dnn_step(examples, labels, cfg, cfg.learning_rate if lr is None else lr,
-                             cfg.weight_decay if weight_decay is None else weight_decay)
+        lr = cfg.learning_rate if lr is None else lr
+        wd = cfg.weight_decay if weight_decay is None else weight_decay
+        if not self.use_cuda_graph:
+            self.engine.dnn_step(examples, labels, cfg, lr, wd)
+            return
+        xs, ys = self._static('dnn_x', examples), self._static('dnn_y', labels)
+        key = ('dnn', tuple(examples.shape), lr, wd, cfg.labeled_loss_multiplier, cfg.labeled_loss_order)
+        self._graphed(key, [(xs, examples), (ys, labels)], lambda: self.engine.dnn_step(xs, ys, cfg, lr, wd))
 
     def gan_step(self, labeled_examples, labels, unlabeled_examples, step=0, noise=None):
         cfg = self.config()
         B = labeled_examples.shape[0]
         z, alpha, z2 = noise if noise is not None else self.draw_noise(B, cfg)
-        self.engine.gan_step(labeled_examples, labels, unlabeled_examples, z, alpha, z2, cfg,
-                             train_generator=(step % cfg.generator_training_step_period == 0))
+        train_g = (step % cfg.generator_training_step_period == 0)
+        if not self.use_cuda_graph:
+            self.engine.gan_step(labeled_examples, labels, unlabeled_examples, z, alpha, z2, cfg, train_generator=train_g)
+            return
+        alpha = alpha.reshape(-1)
+        st = [(self._static('x', labeled_examples), labeled_examples), (self._static('y', labels), labels),
+              (self._static('u', unlabeled_examples), unlabeled_examples), (self._static('z', z), z),
+              (self._static('alpha', alpha), alpha), (self._static('z2', z2), z2)]
+        key = ('gan', tuple(labeled_examples.shape), train_g, repr(sorted(vars(cfg).items())))
+        xs, ys, us, zs, als, z2s = (d for d, _ in st)
+        self._graphed(key, st, lambda: self.engine.gan_step(xs, ys, us, zs, als, z2s, cfg, train_generator=train_g))
 
     def scalars(self):
         """One device->host read of the step's scalars (the .item() calls of srgan.py:268-270, 306-319)."""
@@ -288,7 +340,7 @@ class StepRunner:
         for name, p in self.modules[which].named_parameters():
             if name not in st.slices:
                 continue
-            optimizer.state[p] = {'step': torch.tensor(float(st.adam_step)),
+            optimizer.state[p] = {'step': torch.tensor(float(st.adam_state[0].item())),
                                   'exp_avg': st.m(name).view_as(p).clone(),
                                   'exp_avg_sq': st.v(name).view_as(p).clone()}
 
@@ -299,7 +351,7 @@ class StepRunner:
             if s and 'exp_avg' in s and name in st.slices:
                 st.m(name).copy_(s['exp_avg'].reshape(-1))
                 st.v(name).copy_(s['exp_avg_sq'].reshape(-1))
-                st.adam_step = int(float(s['step']))
+                st.adam_state[0] = float(s['step'])
 
     def refresh_weights(self):
         """Call after the nn.Parameters were changed from outside (load_state_dict)."""

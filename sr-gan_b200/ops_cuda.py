@@ -26,7 +26,7 @@ _EXPORTS = (
     'srgan_conv_down', 'srgan_conv_up', 'srgan_conv_wgrad', 'srgan_colsum', 'srgan_rowdot', 'srgan_seed_rows',
     'srgan_nchw_to_nhwc', 'srgan_nhwc_to_nchw', 'srgan_interpolate', 'srgan_labeled_loss', 'srgan_bce_logits',
     'srgan_distance', 'srgan_feature_norm_seed', 'srgan_gradnorm_penalty', 'srgan_gp_feature_seed', 'srgan_adam',
-    'srgan_repack', 'srgan_im2col', 'srgan_col2im',
+    'srgan_repack', 'srgan_im2col', 'srgan_col2im', 'srgan_adam_prepare',
 )
 
 _lib = None
@@ -70,7 +70,8 @@ def load_library(path: str = LIB_PATH):
     lib.srgan_gradnorm_penalty.argtypes = [vp, c_int, c_ll, c_f, c_f, vp, vp, vp, vp, c_int, vp]
     lib.srgan_gp_feature_seed.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, c_f, c_int, vp]
     i4, l4 = ctypes.POINTER(c_int * 4), ctypes.POINTER(c_ll * 4)
-    lib.srgan_adam.argtypes = [vp, vp, vp, vp, i4, l4, vp, l4, vp, l4, c_int] + [c_f] * 7 + [vp]
+    lib.srgan_adam.argtypes = [vp, vp, vp, vp, i4, l4, vp, l4, vp, l4, c_int, vp] + [c_f] * 4 + [vp]
+    lib.srgan_adam_prepare.argtypes = [vp, ctypes.c_double, ctypes.c_double, ctypes.c_double, vp]
     lib.srgan_repack.argtypes = [vp, i4, vp, l4, vp, l4, c_int, vp]
     lib.srgan_im2col.argtypes = [vp, vp, c_int, gp, c_int, c_int, vp]
     lib.srgan_col2im.argtypes = [vp, vp, c_int, gp, c_int, vp, vp, c_int, c_int, c_f, c_int, vp]
@@ -239,11 +240,15 @@ class CudaOps:
                                        self._p(href, col.dtype) if href is not None else None, epi, act, slope,
                                        _dt(col.dtype), self._stream()), 'srgan_col2im')
 
-    def adam(self, param, grad, m, v, dims, gstrides, out1, s1, out2, s2, lr, b1, b2, eps, wd, bc1, bc2):
+    def adam_prepare(self, state, lr, b1, b2):
+        self._ck(self.lib.srgan_adam_prepare(self._p(state, torch.float32), float(lr), float(b1), float(b2),
+                                             self._stream()), 'srgan_adam_prepare')
+
+    def adam(self, param, grad, m, v, dims, gstrides, out1, s1, out2, s2, state, b1, b2, eps, wd):
         f32 = torch.float32
         od = out1.dtype if out1 is not None else (out2.dtype if out2 is not None else f32)
         self._ck(self.lib.srgan_adam(self._p(param.detach(), f32), self._p(grad, f32), self._p(m, f32), self._p(v, f32),
                                      (ctypes.c_int * 4)(*dims), (ctypes.c_longlong * 4)(*gstrides), self._p(out1),
                                      (ctypes.c_longlong * 4)(*s1) if s1 else None, self._p(out2),
-                                     (ctypes.c_longlong * 4)(*s2) if s2 else None, _dt(od), lr, b1, b2, eps, wd, bc1,
-                                     bc2, self._stream()), 'srgan_adam')
+                                     (ctypes.c_longlong * 4)(*s2) if s2 else None, _dt(od), self._p(state, f32), b1, b2,
+                                     eps, wd, self._stream()), 'srgan_adam')

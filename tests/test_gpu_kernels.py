@@ -228,10 +228,14 @@ def test_adam_and_repack(ops):
         ref.repack(p_ref, dims, o1_ref, wd_s, o2_ref, wu_s)
         ops.repack(p, dims, o1, wd_s, o2, wu_s)
         close(o1, o1_ref, 1e-7, 'repack1'); close(o2, o2_ref, 1e-7, 'repack2')
+        st_ref, st = torch.zeros(3), torch.zeros(3, device='cuda')
         for step in (1, 2):
-            bc1, bc2 = 1 - 0.9 ** step, 1 - 0.999 ** step
-            ref.adam(p_ref, grad, m_ref, v_ref, dims, wd_s, o1_ref, wd_s, o2_ref, wu_s, 1e-3, 0.9, 0.999, 1e-8, 1e-2, bc1, bc2)
-            ops.adam(p, grad.cuda(), m, v, dims, wd_s, o1, wd_s, o2, wu_s, 1e-3, 0.9, 0.999, 1e-8, 1e-2, bc1, bc2)
+            ref.adam_prepare(st_ref, 1e-3, 0.9, 0.999)
+            ops.adam_prepare(st, 1e-3, 0.9, 0.999)
+            close(st, st_ref, 1e-6, 'adam state')
+            assert float(st_ref[0]) == step
+            ref.adam(p_ref, grad, m_ref, v_ref, dims, wd_s, o1_ref, wd_s, o2_ref, wu_s, st_ref, 0.9, 0.999, 1e-8, 1e-2)
+            ops.adam(p, grad.cuda(), m, v, dims, wd_s, o1, wd_s, o2, wu_s, st, 0.9, 0.999, 1e-8, 1e-2)
             close(p, p_ref, 5e-6, 'adam p'); close(m, m_ref, 5e-6, 'adam m'); close(v, v_ref, 5e-6, 'adam v')
             close(o1, o1_ref, 5e-6 if od == torch.float32 else 1e-2, 'adam out1')
             close(o2, o2_ref, 5e-6 if od == torch.float32 else 1e-2, 'adam out2')

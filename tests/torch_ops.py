@@ -236,7 +236,14 @@ class TorchOps:
         cd = torch.float64 if col.dtype == torch.float64 else torch.float32
         self._epilogue(y.permute(0, 2, 3, 1).to(cd), L_out, bias, 0, href, epi, act, slope)
 
-    def adam(self, param, grad, m, v, dims, gstrides, out1, s1, out2, s2, lr, b1, b2, eps, wd, bc1, bc2):
+    def adam_prepare(self, state, lr, b1, b2):
+        self.launches += 1
+        t = float(state[0]) + 1.0
+        state[0] = t
+        state[1] = lr / (1.0 - b1 ** t)
+        state[2] = 1.0 / (1.0 - b2 ** t) ** 0.5
+
+    def adam(self, param, grad, m, v, dims, gstrides, out1, s1, out2, s2, state, b1, b2, eps, wd):
         self.launches += 1
         p = param.detach()
         g = self._gather(grad, dims, gstrides).reshape(p.shape).to(p.dtype)
@@ -246,6 +253,6 @@ class TorchOps:
         vv = v.view(-1)[:p.numel()].view(p.shape)
         mm.mul_(b1).add_(g, alpha=1 - b1)
         vv.mul_(b2).addcmul_(g, g, value=1 - b2)
-        denom = vv.sqrt() / (bc2 ** 0.5) + eps
-        p.addcdiv_(mm, denom, value=-lr / bc1)
+        denom = vv.sqrt() * float(state[2]) + eps
+        p.addcdiv_(mm, denom, value=-float(state[1]))
         self.repack(p, dims, out1, s1, out2, s2)
