@@ -143,6 +143,28 @@ int srgan_adam(float* param, const float* grad, float* m, float* v, const int* d
 int srgan_repack(const float* param, const int* dims4, void* out1, const long long* o1strides4, void* out2,
                  const long long* o2strides4, int out_dtype, void* stream);
 
+/* ---- coefficient application: the whole step in one persistent kernel ------------------------------------------
+ * BASELINE configs[0] (run.py:46-54): coefficient/models.py:12-72 MLPs (50->10->10->10->{1,2}, generator 10->10->10->10->50,
+ * leaky 0.01) are 2.4 k parameters; the reference spends ~850 ATen launches per step on them.  One cooperative launch
+ * runs Experiment.dnn_training_step (srgan.py:259-271; phases bit 0) and/or Experiment.gan_training_step
+ * (srgan.py:273-320 incl. the DG-GAN overrides coefficient/dggan.py:22-64; phases bit 1): forwards, losses, gradient
+ * penalty with its double backward, generator step and the three torch.optim.Adam updates (moments, step counters and
+ * master parameters updated in place; the flat gradient buffers must be zero on entry and are zero again on exit).
+ * {d,g,dnn}_ptrs: 32 device pointers each = 4 layers x {W, b, gradW, gradb, mW, mb, vW, vb}, fp32, torch layouts.
+ * {d,g,dnn}_state: the srgan_adam_prepare state (only state[0] = step counter is read and advanced).
+ * x [B,50], y [B], u [B,50], z [B,10], alpha [B], z2 [B,10]; the *_mult arguments already include srgan_loss_multiplier /
+ * dggan_loss_multiplier; inv_Bg = 1 / global batch.  workspace: srgan_coefficient_step_workspace_bytes() bytes, needs no
+ * initialisation.  scalars: the 7 engine slots (dnn, labeled, unlabeled, fake, penalty, grad-norm mean, generator).
+ * Single-rank only: the feature sums are combined inside the kernel. */
+size_t srgan_coefficient_step_workspace_bytes(void);
+int srgan_coefficient_step(const float* const* d_ptrs, const float* const* g_ptrs, const float* const* dnn_ptrs,
+                           float* d_state, float* g_state, float* dnn_state, const float* x, const float* y,
+                           const float* u, const float* z, const float* alpha, const float* z2, int B, float inv_Bg,
+                           int dggan, int order, float labeled_mult, float unl_mult, float fake_mult, float gen_mult,
+                           float gp_lambda, int kind_match, int kind_contrast, float lr, float lr_dnn, float wd,
+                           float beta1, float beta2, float eps, int phases, int train_g, void* workspace,
+                           size_t workspace_bytes, float* scalars, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -221,6 +221,74 @@ class StepRunner:
         # NCCL collectives inside a captured graph are left for a later round: multi-rank steps run eagerly
         self.use_cuda_graph = bool(ug) and os.environ.get('SRGAN_NO_GRAPH', '0') != '1' and comm is None
         self._graphs, self._statics = {}, {}
+        # coefficient application: one persistent cooperative kernel per step method (csrc/coef_step.cu) instead of
+        # ~150 generic launches; single rank only (the feature sums are combined inside the kernel)
+        self.persistent = (self._persistent_shape_ok(d_net, g_net) and comm is None
+                           and bool(getattr(settings, 'use_persistent_kernel', True))
+                           and os.environ.get('SRGAN_NO_PERSISTENT', '0') != '1')
+        self._coef_tables = None
+        self._layouts_stale = False
+
+    @staticmethod
+    def _persistent_shape_ok(d_net, g_net):
+        def dims(net):
+            return [(l.geom.Cb, l.geom.Ca) for l in net.layers]
+        return (d_net.family == 'coefficient' and g_net.family == 'coefficient'
+                and dims(d_net) == [(50, 10), (10, 10), (10, 10)] and d_net.head_outputs in (1, 2)
+                and dims(g_net) == [(10, 10), (10, 10), (10, 10), (10, 50)]
+                and all(abs(l.slope - 0.01) < 1e-12 for l in d_net.layers + g_net.layers[:3]))
+
+    def _coef_step(self, phases, x, y, u=None, z=None, alpha=None, z2=None, lr_dnn=0.0, wd=None, train_g=True):
+        """srgan_coefficient_step: phases 1 = dnn_training_step, 2 = gan_training_step."""
+        eng, cfg = self.engine, self.config()
+        ops = eng.ops
+        ops.begin()
+        if self._coef_tables is None:
+            def table(st):
+                keys = [l.name for l in st.net.layers] + ([st.net.head] if st.net.head else [])
+                ts = []
+                for k in keys:
+                    w, b = k + '.weight', k + '.bias'
+                    ts += [st.params[w].detach(), st.params[b].detach(), st.g(w), st.g(b), st.m(w), st.m(b), st.v(w), st.v(b)]
+                return ops.pointer_table(ts)
+            ws = torch.empty(ops.coefficient_workspace_bytes() // 4, dtype=torch.float32, device=self.device)
+            self._coef_tables = (table(eng.D), table(eng.G), table(eng.DNN), ws)
+        td, tg, tdnn, ws = self._coef_tables
+
+        def f32(t):
+            return None if t is None else t.detach().to(torch.float32).contiguous()
+        x, y, u, z, alpha, z2 = (f32(t) for t in (x, y, u, z, alpha, z2))
+        B = x.shape[0]
+        if x.numel() != B * 50 or y.numel() != B:
+            raise ValueError('coefficient step: examples must be [B, 50] and labels [B]')
+        if phases & 2:
+            if u.shape[0] != B or z.shape[0] != B or alpha.numel() != B or z2.shape[0] != B:
+                raise ValueError('labeled, unlabeled and noise batches must have the same size (SURVEY App. E.2)')
+        dggan = cfg.method == 'dggan'
+        if dggan:
+            unl = cfg.matching_loss_multiplier * cfg.dggan_loss_multiplier
+            fake = cfg.contrasting_loss_multiplier * cfg.dggan_loss_multiplier
+            gen = 1.0
+        else:
+            unl = cfg.matching_loss_multiplier * cfg.srgan_loss_multiplier
+            fake = cfg.contrasting_loss_multiplier * cfg.srgan_loss_multiplier
+            gen = cfg.matching_loss_multiplier
+        dummy = x
+        ops.coefficient_step(td, tg, tdnn, eng.D.adam_state, eng.G.adam_state, eng.DNN.adam_state, x, y,
+                             u if u is not None else dummy, z if z is not None else dummy,
+                             alpha if alpha is not None else dummy, z2 if z2 is not None else dummy, B, 1.0 / B, dggan,
+                             cfg.labeled_loss_order, cfg.labeled_loss_multiplier, unl, fake, gen,
+                             cfg.gradient_penalty_multiplier, DIST_KINDS[cfg.matching_distance_function],
+                             DIST_KINDS[cfg.contrasting_distance_function], cfg.learning_rate, lr_dnn,
+                             cfg.weight_decay if wd is None else wd, cfg.betas[0], cfg.betas[1], cfg.eps, phases, train_g,
+                             ws, eng.scalars)
+        self._layouts_stale = True
+
+    def _fresh_layouts(self):
+        """The persistent kernel updates only the master parameters: rebuild the kernel-layout copies before the
+        generic kernels (predict / generate) read them."""
+        if self._layouts_stale:
+            self.refresh_weights()
 
     # ---- noise (srgan.py:286-289, :364, :301) drawn on the device
     def draw_noise(self, B, cfg):
@@ -273,6 +341,9 @@ class StepRunner:
         cfg = self.config()
         lr = cfg.learning_rate if lr is None else lr
         wd = cfg.weight_decay if weight_decay is None else weight_decay
+        if self.persistent:
+            self._coef_step(1, examples, labels, lr_dnn=lr, wd=wd)
+            return
         if not self.use_cuda_graph:
             self.engine.dnn_step(examples, labels, cfg, lr, wd)
             return
@@ -285,6 +356,9 @@ class StepRunner:
         B = labeled_examples.shape[0]
         z, alpha, z2 = noise if noise is not None else self.draw_noise(B, cfg)
         train_g = (step % cfg.generator_training_step_period == 0)
+        if self.persistent:
+            self._coef_step(2, labeled_examples, labels, unlabeled_examples, z, alpha.reshape(-1), z2, train_g=train_g)
+            return
         if not self.use_cuda_graph:
             self.engine.gan_step(labeled_examples, labels, unlabeled_examples, z, alpha, z2, cfg, train_generator=train_g)
             return
@@ -309,6 +383,7 @@ class StepRunner:
 
     # ---- forward-only helpers (D(x) / G(z) of the reference modules, on the kernels)
     def predict(self, x, net='D'):
+        self._fresh_layouts()
         st = self.engine.D if net == 'D' else self.engine.DNN
         pred, feats = self.engine.d_features(x, st)
         return pred.clone(), self.features_nchw(feats, x.shape[0])
@@ -321,6 +396,7 @@ class StepRunner:
         return out
 
     def generate(self, z):
+        self._fresh_layouts()
         gnet = self.engine.g_net
         out_l = gnet.layers[-1]
         flat = self.engine.g_generate(z)
@@ -357,6 +433,7 @@ class StepRunner:
         """Call after the nn.Parameters were changed from outside (load_state_dict)."""
         for st in (self.engine.D, self.engine.G, self.engine.DNN):
             self.engine.repack(st)
+        self._layouts_stale = False
 
 
 # ------------------------------------------------------------------------------------------------ drop-in mix-in

@@ -26,7 +26,8 @@ _EXPORTS = (
     'srgan_conv_down', 'srgan_conv_up', 'srgan_conv_wgrad', 'srgan_colsum', 'srgan_rowdot', 'srgan_seed_rows',
     'srgan_nchw_to_nhwc', 'srgan_nhwc_to_nchw', 'srgan_interpolate', 'srgan_labeled_loss', 'srgan_bce_logits',
     'srgan_distance', 'srgan_feature_norm_seed', 'srgan_gradnorm_penalty', 'srgan_gp_feature_seed', 'srgan_adam',
-    'srgan_repack', 'srgan_im2col', 'srgan_col2im', 'srgan_adam_prepare',
+    'srgan_repack', 'srgan_im2col', 'srgan_col2im', 'srgan_adam_prepare', 'srgan_coefficient_step',
+    'srgan_coefficient_step_workspace_bytes',
 )
 
 _lib = None
@@ -75,8 +76,12 @@ def load_library(path: str = LIB_PATH):
     lib.srgan_repack.argtypes = [vp, i4, vp, l4, vp, l4, c_int, vp]
     lib.srgan_im2col.argtypes = [vp, vp, c_int, gp, c_int, c_int, vp]
     lib.srgan_col2im.argtypes = [vp, vp, c_int, gp, c_int, vp, vp, c_int, c_int, c_f, c_int, vp]
+    pp = ctypes.POINTER(vp)
+    lib.srgan_coefficient_step.argtypes = ([pp, pp, pp, vp, vp, vp] + [vp] * 6 + [c_int, c_f, c_int, c_int] + [c_f] * 5 +
+                                           [c_int, c_int] + [c_f] * 6 + [c_int, c_int, vp, ctypes.c_size_t, vp, vp])
     for name in _EXPORTS[5:]:
         getattr(lib, name).restype = c_int
+    lib.srgan_coefficient_step_workspace_bytes.restype = ctypes.c_size_t
     _lib = lib
     return lib
 
@@ -252,3 +257,25 @@ class CudaOps:
                                      (ctypes.c_longlong * 4)(*s1) if s1 else None, self._p(out2),
                                      (ctypes.c_longlong * 4)(*s2) if s2 else None, _dt(od), self._p(state, f32), b1, b2,
                                      eps, wd, self._stream()), 'srgan_adam')
+
+    def coefficient_workspace_bytes(self):
+        return int(self.lib.srgan_coefficient_step_workspace_bytes())
+
+    def coefficient_step(self, d_ptrs, g_ptrs, dnn_ptrs, d_state, g_state, dnn_state, x, y, u, z, alpha, z2, B, inv_Bg,
+                         dggan, order, labeled_mult, unl_mult, fake_mult, gen_mult, gp_lambda, kind_match, kind_contrast,
+                         lr, lr_dnn, wd, b1, b2, eps, phases, train_g, workspace, scalars):
+        """d_ptrs / g_ptrs / dnn_ptrs: ctypes (c_void_p * 32) tables built by pointer_table()."""
+        f32 = torch.float32
+        self._ck(self.lib.srgan_coefficient_step(
+            d_ptrs, g_ptrs, dnn_ptrs, self._p(d_state, f32), self._p(g_state, f32), self._p(dnn_state, f32),
+            self._p(x, f32), self._p(y, f32), self._p(u, f32), self._p(z, f32), self._p(alpha, f32), self._p(z2, f32),
+            int(B), inv_Bg, int(dggan), int(order), labeled_mult, unl_mult, fake_mult, gen_mult, gp_lambda,
+            int(kind_match), int(kind_contrast), lr, lr_dnn, wd, b1, b2, eps, int(phases), int(train_g),
+            self._p(workspace), workspace.numel() * workspace.element_size(), self._p(scalars, f32), self._stream()),
+            'srgan_coefficient_step')
+
+    def pointer_table(self, tensors):
+        for t in tensors:
+            if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise TypeError('pointer_table: fp32 contiguous CUDA tensors only')
+        return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])

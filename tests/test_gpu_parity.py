@@ -147,3 +147,45 @@ def test_age_full_size_properties():
         outs.append(sc)
     for k in SCALARS:
         assert outs[1][k] == pytest.approx(outs[0][k], rel=2e-2, abs=2e-3), (k, outs)
+
+
+@pytest.mark.parametrize('method', ['srgan', 'dggan'])
+@pytest.mark.parametrize('B', [77, 5000, 20000])
+def test_coefficient_persistent_kernel_matches_generic_kernels(method, B):
+    """csrc/coef_step.cu (one cooperative launch per step method) against the generic per-op kernels on the same
+    inputs: ragged batch (77: one partial CTA tile), the reference batch 5000 and 20000 (> 64 x 148 samples: more than
+    one round per CTA).  Both are fp32; differences are summation order only."""
+    gen = torch.Generator().manual_seed(7)
+    st = O.init_coefficient(seed=5, dggan=(method == 'dggan'))
+    for k in ('linear1.weight', 'linear2.weight', 'linear3.weight'):
+        st.D[k] = st.D[k] * 3
+    cfg = O.StepConfig(method=method, batch_size=B, gradient_penalty_multiplier=10.0, learning_rate=1e-3)
+    ra, rb = runner_from_state(st, cfg, 'fp32'), runner_from_state(st, cfg, 'fp32')
+    assert ra.persistent
+    rb.persistent = False
+    for i in range(3):
+        x, u = torch.randn(B, 50, generator=gen), torch.randn(B, 50, generator=gen)
+        y = torch.rand(B, generator=gen) * 2 - 1
+        z, alpha, z2 = torch.randn(B, 10, generator=gen), torch.rand(B, 1, generator=gen), torch.randn(B, 10, generator=gen)
+        xc, yc, uc, zc, ac, z2c = to_cuda(x, y, u, z, alpha, z2)
+        l0 = ra.engine.ops.launches
+        for r in (ra, rb):
+            r.dnn_step(xc, yc, lr=1e-3)
+            r.gan_step(xc, yc, uc, i, noise=(zc, ac, z2c))
+        if i == 0:
+            assert rb.engine.ops.launches - l0 > 50 + 2      # ra: exactly two launches
+        check_scalars(ra.scalars(), rb.scalars(), 2e-5, (method, B, i))
+        assert rb.scalars()['gradient_penalty'] > 0
+    for net in ('D', 'G', 'DNN'):
+        sa, sb = ra.modules[net].state_dict(), rb.modules[net].state_dict()
+        init = getattr(st, net)
+        for k in sa:
+            err, cos = update_error(sa[k].cpu() - init[k], sb[k].cpu() - init[k])
+            assert err < 2e-3, (net, k, err, cos)
+        assert float(ra.engine.__dict__[net].adam_state[0]) == 3.0
+        assert ra.engine.__dict__[net].grad.abs().max().item() == 0.0
+    # forward-only helpers after persistent steps use refreshed kernel-layout copies
+    pa, fa = ra.predict(xc)
+    pb, fb = rb.predict(xc)
+    assert rel(pa, pb) < 1e-4 and rel(fa, fb) < 1e-4
+    assert rel(ra.generate(zc), rb.generate(zc)) < 1e-4
