@@ -67,9 +67,15 @@ class StepConfig:
 @dataclass
 class ModelSpec:
     """Which network family a Params dict belongs to, plus the constants its forward needs."""
-    family: str                    # 'coefficient' | 'dcgan'
+    family: str                    # 'coefficient' | 'dcgan' | 'crowd'
     dggan: bool = False            # D has a second (fake-score) output: coefficient/models.py:53-72
     leaky: float = 0.01            # coefficient: F.leaky_relu default 0.01; dcgan: 0.05 (age/models.py:46-50,70-73)
+    # crowd KnnDenseNetCat constructor arguments (crowd/models.py:1060-1062; defaults = DenseNet-201 at 224)
+    block_config: Tuple[int, ...] = (6, 12, 48, 32)
+    growth_rate: int = 32
+    num_init_features: int = 64
+    bn_size: int = 4
+    label_patch_size: int = 224
 
 
 def coefficient_d_forward(p: Params, x: torch.Tensor, dggan: bool = False):
@@ -111,8 +117,69 @@ def dcgan_g_forward(p: Params, z: torch.Tensor):
     return torch.tanh(F.conv_transpose2d(h, p['layer4.0.weight'], p['layer4.0.bias'], stride=2, padding=1))
 
 
+def _bn_eval(p: Params, prefix: str, x: torch.Tensor):
+    """nn.BatchNorm2d in eval() mode -- what disable_batch_norm_updates (srgan.py:538-542, applied :261,276) leaves on the
+    hot path: a per-channel affine of the running statistics (eps 1e-5), weight and bias still trainable."""
+    return F.batch_norm(x, p[prefix + '.running_mean'], p[prefix + '.running_var'], p[prefix + '.weight'],
+                        p[prefix + '.bias'], training=False, eps=1e-5)
+
+
+def crowd_map_module(p: Params, prefix: str, x: torch.Tensor):
+    """MapModule.forward, crowd/models.py:778-786: ConvT (k = stride = label/input) + leaky -> map; 3 x (Conv k2 s2 +
+    leaky), Conv (full extent) + leaky -> 20 features; Conv 1x1 -> count."""
+    w = p[prefix + '.map_transposed_conv_layer.weight']
+    map_ = F.leaky_relu(F.conv_transpose2d(x, w, p[prefix + '.map_transposed_conv_layer.bias'], stride=w.shape[-1]), 0.01)
+    out = map_
+    for name in ('conv1', 'conv2', 'conv3'):
+        out = F.leaky_relu(F.conv2d(out, p[f'{prefix}.{name}.weight'], p[f'{prefix}.{name}.bias'], stride=2), 0.01)
+    out = F.leaky_relu(F.conv2d(out, p[prefix + '.linear1.weight'], p[prefix + '.linear1.bias']), 0.01)
+    count = F.conv2d(out, p[prefix + '.count_layer.weight'], p[prefix + '.count_layer.bias'])
+    return map_, count, out
+
+
+def crowd_d_forward(spec: ModelSpec, p: Params, x: torch.Tensor):
+    """KnnDenseNetCat.forward, crowd/models.py:1136-1166 (+ _DenseLayer :335-353, _Transition :364-371):
+    DenseNet trunk (BN in eval mode) with taps after every transition feeding three MapModules, plus the count head.
+    Returns ((count [B], map [B,3,L,L]), features [B,80])."""
+    B = x.shape[0]
+    out = F.conv2d(x, p['conv_layer1.conv0.weight'], None, stride=2, padding=3)
+    out = F.relu(_bn_eval(p, 'conv_layer1.norm0', out))
+    out = F.max_pool2d(out, kernel_size=3, stride=2, padding=1)
+    taps = []
+    for bi, n_layers in enumerate(spec.block_config, 1):
+        for li in range(1, n_layers + 1):
+            pre = f'dense_blocks.denseblock{bi}.denselayer{li}'
+            h = F.relu(_bn_eval(p, pre + '.norm1', out))
+            h = F.conv2d(h, p[pre + '.conv1.weight'])
+            h = F.relu(_bn_eval(p, pre + '.norm2', h))
+            h = F.conv2d(h, p[pre + '.conv2.weight'], padding=1)
+            out = torch.cat([out, h], 1)
+        if bi != len(spec.block_config):
+            pre = f'transition_layers.transition{bi}'
+            h = F.relu(_bn_eval(p, pre + '.norm', out))
+            h = F.conv2d(h, p[pre + '.conv.weight'])
+            out = F.avg_pool2d(h, kernel_size=2, stride=2)
+            taps.append(out)
+    out = F.relu(_bn_eval(p, 'norm5', out))
+    final_pool = F.avg_pool2d(out, kernel_size=out.shape[-1], stride=1)        # kernel 7 at 224 (:1151)
+    fcf = F.leaky_relu(F.conv2d(final_pool, p['final_count_feature_layer.weight'], p['final_count_feature_layer.bias']), 0.01)
+    final_count = F.conv2d(fcf, p['count_layer.weight'], p['count_layer.bias'])
+    maps, counts, hs = [], [], []
+    for i, t in enumerate(taps[:3], 1):
+        m, c, h = crowd_map_module(p, f'map_module{i}', t)
+        maps.append(m), counts.append(c), hs.append(h)
+    features = torch.cat([h.reshape(B, -1) for h in hs] + [fcf.reshape(B, -1)], dim=1)
+    count = (counts[0] + counts[1] + counts[2] + final_count).reshape(B)
+    L = spec.label_patch_size
+    map_ = torch.cat(maps, dim=1).reshape(B, 3, L, L)
+    return (count, map_), features
+
+
 def d_forward(spec: ModelSpec, p: Params, x: torch.Tensor):
     """Returns (prediction, fake_score_or_None, features)."""
+    if spec.family == 'crowd':
+        out, f = crowd_d_forward(spec, p, x)
+        return out, None, f
     if spec.family == 'coefficient':
         out, f = coefficient_d_forward(p, x, spec.dggan)
         if spec.dggan:
@@ -148,6 +215,16 @@ def crowd_labeled_loss_function(predicted_count, predicted_maps, head_labels, ma
     return count_loss + map_loss * map_multiplier
 
 
+def labeled_loss(spec: ModelSpec, cfg: 'StepConfig', pred, labels):
+    """labeled_loss_function as the application overrides it: srgan.py:414-417, crowd/srgan.py:247-254
+    (crowd: pred = (count, maps), labels = (density, map): the tuple built at srgan.py:112-113)."""
+    if spec.family == 'crowd':
+        count, maps = pred
+        density, map_labels = labels
+        return crowd_labeled_loss_function(count, maps, density, map_labels, cfg.labeled_loss_order, cfg.map_multiplier)
+    return labeled_loss_function(pred, labels, cfg.labeled_loss_order)
+
+
 def feature_distance_loss(base_features, other_features, distance: str):
     """srgan.py:438-449 with normalize_feature_norm=False (the True branch is a known bug)."""
     return DISTANCES[distance](base_features.mean(0) - other_features.mean(0))
@@ -173,7 +250,7 @@ def adam_update(p: Params, grads: Dict[str, Optional[torch.Tensor]], st: AdamSta
     b1, b2 = betas
     st.step += 1
     t = st.step
-    for k in p:
+    for k in list(p):
         g = grads.get(k)
         if g is None:
             continue
@@ -209,13 +286,19 @@ class OracleState:
         return copy.deepcopy(self)
 
 
+def is_buffer_key(k: str) -> bool:
+    """state_dict entries that are module buffers, not parameters (BatchNorm statistics)."""
+    return k.endswith('running_mean') or k.endswith('running_var') or k.endswith('num_batches_tracked')
+
+
 def _leaf(p: Params) -> Params:
-    return {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+    return {k: (v.detach().clone() if is_buffer_key(k) else v.detach().clone().requires_grad_(True)) for k, v in p.items()}
 
 
 def _grads(loss, leaf: Params):
-    gs = torch.autograd.grad(loss, list(leaf.values()), allow_unused=True)
-    return dict(zip(leaf.keys(), gs))
+    keys = [k for k, v in leaf.items() if v.requires_grad]
+    gs = torch.autograd.grad(loss, [leaf[k] for k in keys], allow_unused=True)
+    return dict(zip(keys, gs))
 
 
 def dnn_lr(cfg: StepConfig, step: int) -> float:
@@ -227,7 +310,7 @@ def dnn_training_step(st: OracleState, cfg: StepConfig, x, y, step: int = 0):
     """srgan.py:259-271 + dnn_loss_calculation :322-327 (DG-GAN: coefficient/dggan.py:22-27)."""
     leaf = _leaf(st.DNN)
     pred, _, _ = d_forward(st.d_spec, leaf, x)
-    loss = labeled_loss_function(pred, y, cfg.labeled_loss_order) * cfg.labeled_loss_multiplier
+    loss = labeled_loss(st.d_spec, cfg, pred, y) * cfg.labeled_loss_multiplier
     g = _grads(loss, leaf)
     adam_update(st.DNN, g, st.dnn_adam, dnn_lr(cfg, step), cfg.weight_decay, cfg.betas, cfg.eps)
     return {'dnn_loss': float(loss.detach())}
@@ -257,7 +340,7 @@ def gan_training_step(st: OracleState, cfg: StepConfig, x, y, u, z, alpha, z2, s
     spec = st.d_spec
     # -- labeled  (:279, :329-335 | dggan.py:29-34)
     pred, _, f_x = d_forward(spec, leafD, x)
-    labeled = labeled_loss_function(pred, y, cfg.labeled_loss_order) * cfg.labeled_loss_multiplier
+    labeled = labeled_loss(spec, cfg, pred, y) * cfg.labeled_loss_multiplier
     # -- unlabeled (:283, :337-346 | dggan.py:36-43)
     _, score_u, f_u = d_forward(spec, leafD, u)
     with torch.no_grad():
@@ -356,3 +439,105 @@ def init_dcgan(seed=0, image_size=128, conv_dim=64, z_dim=256, dtype=torch.float
         g[f'layer{i}.0.weight'] = _uniform(gen, (gch[i - 1], gch[i], 4, 4), bound, dtype)
         g[f'layer{i}.0.bias'] = _uniform(gen, (gch[i],), bound, dtype)
     return OracleState(ModelSpec('dcgan', leaky=0.05), ModelSpec('dcgan', leaky=0.05), d, g, dnn)
+
+
+
+def crowd_param_shapes(spec: ModelSpec, image_size: int):
+    """Key -> shape of KnnDenseNetCat.state_dict() (crowd/models.py:1060-1134) in the module's own order, for any
+    constructor arguments; the MapModule input sizes follow the trunk (28/14/7 at image 224, hard-coded at :1129-1131)."""
+    g, bs = spec.growth_rate, spec.bn_size
+    out = {}
+
+    def bn(prefix, c):
+        out[prefix + '.weight'] = (c,); out[prefix + '.bias'] = (c,)
+        out[prefix + '.running_mean'] = (c,); out[prefix + '.running_var'] = (c,); out[prefix + '.num_batches_tracked'] = ()
+    c = spec.num_init_features
+    trans, tap_c = {}, []
+    for bi, n in enumerate(spec.block_config, 1):
+        for li in range(1, n + 1):
+            pre = f'dense_blocks.denseblock{bi}.denselayer{li}'
+            bn(pre + '.norm1', c)
+            out[pre + '.conv1.weight'] = (bs * g, c, 1, 1)
+            bn(pre + '.norm2', bs * g)
+            out[pre + '.conv2.weight'] = (g, bs * g, 3, 3)
+            c += g
+        if bi != len(spec.block_config):
+            trans[bi] = c
+            c //= 2
+            tap_c.append(c)
+    # attribute order of the module: dense_blocks, transition_layers (both created at :1069-1070), conv_layer1, norm5
+    c2 = spec.num_init_features
+    for bi, n in enumerate(spec.block_config, 1):
+        c2 += n * g
+        if bi in trans:
+            pre = f'transition_layers.transition{bi}'
+            bn(pre + '.norm', c2)
+            out[pre + '.conv.weight'] = (c2 // 2, c2, 1, 1)
+            c2 //= 2
+    out['conv_layer1.conv0.weight'] = (spec.num_init_features, 3, 7, 7)
+    bn('conv_layer1.norm0', spec.num_init_features)
+    bn('norm5', c)
+    L = spec.label_patch_size
+    for i, ci in enumerate(tap_c[:3], 1):
+        size = image_size // (8 * 2 ** (i - 1))
+        k = L // size
+        pre = f'map_module{i}'
+        out[pre + '.map_transposed_conv_layer.weight'] = (ci, 1, k, k); out[pre + '.map_transposed_conv_layer.bias'] = (1,)
+        out[pre + '.conv1.weight'] = (8, 1, 2, 2); out[pre + '.conv1.bias'] = (8,)
+        out[pre + '.conv2.weight'] = (16, 8, 2, 2); out[pre + '.conv2.bias'] = (16,)
+        out[pre + '.conv3.weight'] = (32, 16, 2, 2); out[pre + '.conv3.bias'] = (32,)
+        out[pre + '.linear1.weight'] = (20, 32, L // 8, L // 8); out[pre + '.linear1.bias'] = (20,)
+        out[pre + '.count_layer.weight'] = (1, 20, 1, 1); out[pre + '.count_layer.bias'] = (1,)
+    out['final_count_feature_layer.weight'] = (20, c, 1, 1); out['final_count_feature_layer.bias'] = (20,)
+    out['count_layer.weight'] = (1, 20, 1, 1); out['count_layer.bias'] = (1,)
+    return out
+
+
+def init_crowd_d(spec: ModelSpec, image_size: int, seed=0, dtype=torch.float32, scale=1.0) -> Params:
+    """Deterministic KnnDenseNetCat state (NOT the reference initialiser, which downloads DenseNet-201 weights,
+    crowd/models.py:1103-1127): fan-in-scaled uniform weights, BatchNorm weight/bias/running statistics drawn away from
+    their trivial values so the eval-mode affine is exercised.  Pure torch: reproducible on the GPU box."""
+    gen = torch.Generator().manual_seed(seed)
+    p = {}
+    for k, shape in crowd_param_shapes(spec, image_size).items():
+        if k.endswith('num_batches_tracked'):
+            p[k] = torch.zeros((), dtype=torch.long)
+        elif k.endswith('running_var'):
+            p[k] = (torch.rand(shape, generator=gen, dtype=torch.float64) + 0.5).to(dtype)
+        elif k.endswith('running_mean'):
+            p[k] = _uniform(gen, shape, 0.2, dtype)
+        elif '.norm' in k or k.startswith('norm5'):
+            p[k] = (torch.rand(shape, generator=gen, dtype=torch.float64) + 0.5).to(dtype) if k.endswith('weight') \
+                else _uniform(gen, shape, 0.2, dtype)
+        elif k.endswith('.bias'):
+            p[k] = _uniform(gen, shape, 0.1, dtype)
+        else:
+            fan_in = shape[1] * shape[2] * shape[3] if 'map_transposed' not in k else shape[0]
+            w = _uniform(gen, shape, math.sqrt(3.0 / fan_in), dtype)
+            p[k] = w * scale if ('conv' in k and 'map_module' not in k) else w
+    return p
+
+
+def init_crowd(seed=0, image_size=224, z_dim=256, g_conv_dim=64, dtype=torch.float32, scale=1.0, **spec_kwargs) -> OracleState:
+    """CrowdExperiment.model_setup (crowd/srgan.py:92-96): DCGenerator + two KnnDenseNetCat."""
+    spec = ModelSpec('crowd', **spec_kwargs)
+    d = init_crowd_d(spec, image_size, seed, dtype, scale)
+    dnn = init_crowd_d(spec, image_size, seed + 1, dtype, 1.0)            # KnnDenseNetCat does not reseed (App. E.6)
+    g = init_dcgan(seed + 2, image_size, g_conv_dim, z_dim, dtype).G
+    return OracleState(spec, ModelSpec('dcgan', leaky=0.05), d, g, dnn)
+
+
+def synthetic_crowd_batch(B, seed, image=224, label=224, z_dim=256, dtype=torch.float32):
+    """Synthetic crowd batch of SURVEY 8d config 3, regenerated from the seed wherever it is needed (the tensors are too
+    large to commit): images ~U(-1,1), density = Bernoulli point map (~32 heads per 224x224 patch), map = 1/(1+U(0,50));
+    plus the three noise draws.  Returns (x, (density, map), u, z, alpha, z2)."""
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, 3, image, image, generator=gen) * 2 - 1
+    u = torch.rand(B, 3, image, image, generator=gen) * 2 - 1
+    density = (torch.rand(B, label, label, generator=gen) < 6.5e-4).float()
+    map_ = 1 / (1 + torch.rand(B, label, label, generator=gen) * 50)
+    z = torch.randn(B, z_dim, generator=gen)
+    alpha = torch.rand(B, 1, 1, 1, generator=gen)
+    z2 = torch.randn(B, z_dim, generator=gen)
+    c = lambda t: t.to(dtype)
+    return c(x), (c(density), c(map_)), c(u), c(z), c(alpha), c(z2)
