@@ -79,16 +79,18 @@ class NetState:
         self.act_dtype = act_dtype
         self.device = device
         self.tag = tag                             # buffer namespace: D and DNN share 'D' (same shapes, sequential use)
-        self.thin = {l.name for l in net.layers if thin and l.thin_ok}
+        self.thin = {l.name for l in net.layers if thin and l.thin_ok and net.graph is None}
         n_total = 0
         g_total = 0
         self.slices = {}
         self.gslices = {}
         order = []
         for l in net.layers:
-            order += [l.name + '.weight', l.name + '.bias']
-        if net.head:
-            order += [net.head + '.weight', net.head + '.bias']
+            order += [l.name + '.weight'] + ([l.name + '.bias'] if l.has_bias else [])
+        for op in net.affines:                     # eval-mode BatchNorm: weight / bias are trainable, the statistics are not
+            order += [op.name + '.weight', op.name + '.bias']
+        # head parts: all weights first (contiguous in the flat buffers, in feature-column order), then the biases
+        order += [h + '.weight' for h, _ in net.parts()] + [h + '.bias' for h, _ in net.parts()]
         for k in order:
             p = params[k]
             if p.dtype != torch.float32 and p.dtype != torch.float64:
@@ -120,6 +122,7 @@ class NetState:
             self.wu_[l.name] = torch.zeros(n, dtype=act_dtype, device=device)
         if net.head:
             self.whead = torch.empty(net.head_outputs * net.feature_size, dtype=mdt, device=device)
+            self.hbias = torch.zeros(net.head_outputs, dtype=mdt, device=device)     # sum of the parts' biases
 
     def g(self, key):
         o, n = self.gslices[key]
@@ -207,9 +210,31 @@ class Engine:
         c, h, w = net.feature_chw
         return (net.head_outputs, c, h, w), (F, 1, w * c, c)
 
+    def _head_part_layouts(self, st: NetState):
+        """[(key prefix, master dims, strides into whead, whead slice)] of every head part."""
+        net = st.net
+        if net.head_parts is None:
+            dims, s = self._head_strides(net)
+            return [(net.head, dims, s, st.whead)]
+        out, c0 = [], 0
+        for h, ncol in net.head_parts:             # crowd: four Conv2d(20, 1, 1) heads over consecutive feature columns
+            out.append((h, (1, ncol, 1, 1), (ncol, 1, 0, 0), st.whead[c0:c0 + ncol]))
+            c0 += ncol
+        return out
+
     def _repack_head(self, st: NetState):
-        dims, s = self._head_strides(st.net)
-        self.ops.repack(st.params[st.net.head + '.weight'], dims, st.whead, s, None, None)
+        for h, dims, s, dst in self._head_part_layouts(st):
+            self.ops.repack(st.params[h + '.weight'], dims, dst, s, None, None)
+        if st.net.head_parts is not None:
+            self._head_bias(st)
+
+    def _head_bias(self, st: NetState):
+        """hbias[o] = sum over the head parts of bias[o] (one part for the chain nets)."""
+        st.hbias.zero_()
+        for h, _ in st.net.parts():
+            b = st.params[h + '.bias']
+            for o in range(st.net.head_outputs):
+                self.ops.colsum(b.detach()[o:o + 1], 1, 1, st.hbias[o:o + 1], 0, None)
 
     # ------------------------------------------------------------------ layer ops
     def _lin(self, l: Layer):
@@ -228,7 +253,7 @@ class Engine:
                    lo=0):
         act = l.act if act is None else act
         slope = l.slope if slope is None else slope
-        b = st.params[l.name + '.bias'] if bias else None
+        b = st.params[l.name + '.bias'] if (bias and l.has_bias) else None
         pr = self._probe
         timed = (pr is not None and st is self.D and l is pr['layer'] and n == pr['rows'] and epi == EPI_BIAS_ACT)
         if timed:
@@ -306,7 +331,10 @@ class Engine:
 
     # ------------------------------------------------------------------ passes
     def alloc_acts(self, tag, net: Net, nb_rows):
-        """acts[0] = network input, acts[l] = output of layer l; flat, nb_rows samples of NHWC rows each."""
+        """Chain nets: acts[0] = network input, acts[l] = output of layer l (a list).  Graph nets: a dict buffer name ->
+        tensor.  Flat tensors, nb_rows samples of NHWC rows each."""
+        if net.graph is not None:
+            return {name: self.buf((tag, 'a', name), (nb_rows * b.rows * b.ch,)) for name, b in net.bufs.items()}
         acts = [self.buf((tag, 'a', 0), (nb_rows * net.layers[0].in_elems,))]
         for i, l in enumerate(net.layers, 1):
             acts.append(self.buf((tag, 'a', i), (nb_rows * l.out_elems,)))
@@ -315,6 +343,9 @@ class Engine:
         return acts
 
     def alloc_deltas(self, tag, net: Net, nb_rows):
+        if net.graph is not None:
+            return {name: self.buf((tag, 'd', name), (nb_rows * b.rows * b.ch,)) for name, b in net.bufs.items()
+                    if name != net.input_buf}
         d = [None]
         for i, l in enumerate(net.layers, 1):
             d.append(self.buf((tag, 'd', i), (nb_rows * l.out_elems,)))
@@ -324,27 +355,46 @@ class Engine:
     def rows(t, elems_per_sample, lo, hi):
         return t[lo * elems_per_sample: hi * elems_per_sample]
 
+    @staticmethod
+    def _brows(t, b, lo, hi):
+        e = b.rows * b.ch
+        return t[lo * e: hi * e]
+
+    @staticmethod
+    def _in(net: Net, acts):
+        return acts[net.input_buf] if net.graph is not None else acts[0]
+
+    @staticmethod
+    def _feat(net: Net, t):
+        return t[net.feature_buf] if net.graph is not None else t[len(net.layers)]
+
     def forward(self, st: NetState, acts, lo, hi):
-        """Runs the stack on sample rows [lo, hi) of the buffers."""
+        """Runs the network on sample rows [lo, hi) of the buffers."""
         net = st.net
+        if net.graph is not None:
+            return self.graph_forward(st, acts, lo, hi)
         n = hi - lo
         for i, l in enumerate(net.layers, 1):
             self._fwd_layer(st, l, self.rows(acts[i - 1], l.in_elems, lo, hi), self.rows(acts[i], l.out_elems, lo, hi), n,
                             lo=lo)
 
     def backward(self, st: NetState, acts, deltas, lo, hi, wlo=None, whi=None, need_input_grad=False, dinput=None,
-                 input_href=None, input_act=ACT_NONE, weight_grads=True):
+                 input_href=None, input_act=ACT_NONE, weight_grads=True, hook=None):
         """Ordinary reverse pass over sample rows [lo,hi); weight gradients over rows [wlo,whi) (defaults to the
         same rows; the D step widens it to include the tangent block)."""
         net = st.net
         wlo = lo if wlo is None else wlo
         whi = hi if whi is None else whi
+        if net.graph is not None:
+            return self.graph_backward(st, acts, deltas, lo, hi, lo, wlo, whi, weight_grads,
+                                       (dinput, input_href, input_act) if need_input_grad else None, hook)
         for i in range(len(net.layers), 0, -1):
             l = net.layers[i - 1]
             if weight_grads:
                 self._wgrad_layer(st, l, self.rows(acts[i - 1], l.in_elems, wlo, whi),
                                   self.rows(deltas[i], l.out_elems, wlo, whi), whi - wlo, lo=wlo)
-                self._bias_grad(st, l, self.rows(deltas[i], l.out_elems, lo, hi), (hi - lo) * l.out_rows)
+                if l.has_bias:
+                    self._bias_grad(st, l, self.rows(deltas[i], l.out_elems, lo, hi), (hi - lo) * l.out_rows)
             if i > 1:
                 lp = net.layers[i - 2]
                 self._bwd_data_layer(st, l, self.rows(deltas[i], l.out_elems, lo, hi),
@@ -356,6 +406,118 @@ class Engine:
                                      input_href, input_act, 0.0, lo=lo,
                                      col_ready=(weight_grads and wlo == lo and whi == hi))
 
+    def gchain(self, st: NetState, acts, deltas, B, g0):
+        """Gradient-penalty g-chain on the x_hat rows: gamma_{l-1} = W_l^T gamma_l * act'(h_{l-1}),
+        delta rows [4B,5B), masks from the activations of rows [3B,4B); g0 = d s / d x_hat (no mask)."""
+        net = st.net
+        if net.graph is not None:
+            return self.graph_backward(st, acts, deltas, 4 * B, 5 * B, 3 * B, 0, 0, False, (g0, None, ACT_NONE), None)
+        L = len(net.layers)
+        for i in range(L, 1, -1):
+            l, lp = net.layers[i - 1], net.layers[i - 2]
+            self._bwd_data_layer(st, l, self.rows(deltas[i], l.out_elems, 4 * B, 5 * B),
+                                 self.rows(deltas[i - 1], lp.out_elems, 4 * B, 5 * B), B,
+                                 self.rows(acts[i - 1], lp.out_elems, 3 * B, 4 * B), lp.act, lp.slope)
+        l1 = net.layers[0]
+        self._bwd_data_layer(st, l1, self.rows(deltas[1], l1.out_elems, 4 * B, 5 * B), g0, B, None, ACT_NONE, 0.0)
+
+    def tangent(self, st: NetState, acts, B):
+        """Tangent u-chain: u_l = (W_l u_{l-1}) * act'(h_l of x_hat), no bias; rows [4B,5B), masks from rows [3B,4B)."""
+        net = st.net
+        if net.graph is not None:
+            return self.graph_forward(st, acts, 4 * B, 5 * B, tangent=True, mlo=3 * B)
+        for i, l in enumerate(net.layers, 1):
+            self._fwd_layer(st, l, self.rows(acts[i - 1], l.in_elems, 4 * B, 5 * B),
+                            self.rows(acts[i], l.out_elems, 4 * B, 5 * B), B, bias=False,
+                            href=self.rows(acts[i], l.out_elems, 3 * B, 4 * B), epi=EPI_DACT, lo=4 * B)
+
+    # ------------------------------------------------------------------ graph nets (crowd KnnDenseNetCat)
+    BN_EPS = 1e-5          # nn.BatchNorm2d default, crowd/models.py:339,343,367,1077,1092
+
+    def graph_forward(self, st: NetState, acts, lo, hi, tangent=False, mlo=None):
+        """Forward (tangent=False) or tangent pass (tangent=True: linear parts only, activation derivatives taken from the
+        stored activations of rows [mlo, mlo+n)) of a graph net over sample rows [lo,hi)."""
+        net, ops, R, P = st.net, self.ops, self._brows, st.params
+        n = hi - lo
+        for op in net.graph:
+            sb, db = net.bufs[op.src], net.bufs[op.dst]
+            x, y = R(acts[op.src], sb, lo, hi), R(acts[op.dst], db, lo, hi)
+            href = R(acts[op.dst], db, mlo, mlo + n) if tangent else None
+            if op.kind == 'conv':
+                if tangent:
+                    self._fwd_layer(st, op.layer, x, y, n, bias=False, href=href, epi=EPI_DACT, lo=lo)
+                else:
+                    self._fwd_layer(st, op.layer, x, y, n, lo=lo)
+            elif op.kind == 'affine':
+                nm = op.name
+                ops.affine(x, sb.ch, op.c0, y, n * sb.rows, op.C, P[nm + '.weight'], P[nm + '.bias'],
+                           P[nm + '.running_mean'], P[nm + '.running_var'], self.BN_EPS, href, 1 if tangent else 0,
+                           db.act, db.slope)
+            elif op.kind == 'copy':
+                ops.copy2d(x, sb.ch, 0, y, db.ch, op.c0, n * sb.rows, op.C, False)
+            elif op.kind == 'read':
+                ops.copy2d(x, sb.ch, op.c0, y, db.ch, 0, n * sb.rows, op.C, False)
+            elif op.kind == 'maxpool':
+                xref = R(acts[op.src], sb, mlo, mlo + n) if tangent else None
+                ops.maxpool(x, xref, y, db.ch, op.c0, n, op.H, op.W, op.C, op.k, op.stride, op.pad)
+            elif op.kind == 'avgpool':
+                ops.avgpool(x, y, db.ch, op.c0, n, op.H, op.W, op.C, op.k)
+            else:
+                raise ValueError(op.kind)
+
+    def graph_backward(self, st: NetState, acts, deltas, lo, hi, mlo, wlo, whi, weight_grads, input_grad, hook):
+        """Reverse pass of a graph net over delta rows [lo,hi); the activations that provide masks and weight-gradient
+        inputs are rows [mlo, mlo+n) (== [lo,hi) for an ordinary backward; the x_hat rows for the g-chain).
+        Convolution weight gradients cover rows [wlo,whi) of (acts, deltas) in one launch -- ordinary rows plus, when
+        whi > hi, the tangent block (u_{l-1}, gamma_l); the BatchNorm-scale gradient of the tangent block is a second call
+        (no mean subtraction, no bias term).  input_grad = (dinput, href, act): also d/d(network input).
+        hook(buffer name) is called before the producer of a map buffer is processed (crowd labeled map loss)."""
+        net, ops, R, P = st.net, self.ops, self._brows, st.params
+        n = hi - lo
+        for name, b in net.bufs.items():
+            if b.accumulate:
+                R(deltas[name], b, lo, hi).zero_()
+        for op in reversed(net.graph):
+            sb, db = net.bufs[op.src], net.bufs[op.dst]
+            dy = R(deltas[op.dst], db, lo, hi)
+            is_input = op.src == net.input_buf
+            dx = None if is_input else R(deltas[op.src], sb, lo, hi)
+            xa = R(acts[op.src], sb, mlo, mlo + n)
+            if op.kind == 'conv':
+                l = op.layer
+                if hook is not None and op.dst in net.map_bufs:
+                    hook(op.dst)
+                if weight_grads:
+                    self._wgrad_layer(st, l, R(acts[op.src], sb, wlo, whi), R(deltas[op.dst], db, wlo, whi), whi - wlo, lo=wlo)
+                    if l.has_bias:
+                        self._bias_grad(st, l, dy, n * l.out_rows)
+                if is_input:
+                    if input_grad is not None:
+                        dinput, ihref, iact = input_grad
+                        self._bwd_data_layer(st, l, dy, dinput, n, ihref, iact, 0.0, lo=lo)
+                else:
+                    self._bwd_data_layer(st, l, dy, dx, n, xa, sb.act, sb.slope, lo=lo)
+            elif op.kind == 'affine':
+                nm = op.name
+                mean, var = P[nm + '.running_mean'], P[nm + '.running_var']
+                if weight_grads:
+                    ops.affine_grad(dy, xa, sb.ch, op.c0, n * sb.rows, op.C, mean, var, self.BN_EPS,
+                                    st.g(nm + '.weight'), st.g(nm + '.bias'), True)
+                    if whi > hi:
+                        ops.affine_grad(R(deltas[op.dst], db, hi, whi), R(acts[op.src], sb, hi, whi), sb.ch, op.c0,
+                                        (whi - hi) * sb.rows, op.C, mean, var, self.BN_EPS, st.g(nm + '.weight'), None, False)
+                ops.affine_bwd(dy, dx, sb.ch, op.c0, n * sb.rows, op.C, P[nm + '.weight'], var, self.BN_EPS, sb.accumulate)
+            elif op.kind == 'copy':       # dst slice <- dense src: both are w.r.t. the same pre-activation
+                ops.copy2d(dy, db.ch, op.c0, dx, sb.ch, 0, n * sb.rows, op.C, False)
+            elif op.kind == 'read':       # dense dst <- src slice: add into the (accumulating) concat delta
+                ops.copy2d(dy, db.ch, 0, dx, sb.ch, op.c0, n * sb.rows, op.C, True)
+            elif op.kind == 'maxpool':
+                ops.maxpool_bwd(xa, dy, db.ch, op.c0, dx, n, op.H, op.W, op.C, op.k, op.stride, op.pad, sb.act, sb.slope)
+            elif op.kind == 'avgpool':
+                ops.avgpool_bwd(dy, db.ch, op.c0, dx, n, op.H, op.W, op.C, op.k, xa, sb.act, sb.slope)
+            else:
+                raise ValueError(op.kind)
+
     # ------------------------------------------------------------------ Adam
     def adam(self, st: NetState, lr, weight_decay, betas=(0.9, 0.999), eps=1e-8):
         """torch.optim.Adam semantics, one fused launch per tensor that also rewrites the kernel-
@@ -363,25 +525,29 @@ class Engine:
         if self.comm is not None:
             self.comm.all_reduce_sum(st.grad)
         self.ops.adam_prepare(st.adam_state, lr, betas[0], betas[1])
+        def plain(k):
+            nb = st.params[k].numel()
+            self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), (nb, 1, 1, 1), (1, 0, 0, 0), None, None, None, None,
+                          st.adam_state, betas[0], betas[1], eps, weight_decay)
         for l in st.net.layers:
             wd_s, wu_s = st.strides(l)
             k = l.name + '.weight'
             wd, wu = self._needed_layouts(st, l)
             self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), l.master_dims, wd_s, wd, wd_s if wd is not None else None,
                           wu, wu_s if wu is not None else None, st.adam_state, betas[0], betas[1], eps, weight_decay)
-            k = l.name + '.bias'
-            nb = st.params[k].numel()
-            self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), (nb, 1, 1, 1), (1, 0, 0, 0), None, None, None, None,
-                          st.adam_state, betas[0], betas[1], eps, weight_decay)
+            if l.has_bias:
+                plain(l.name + '.bias')
+        for op in st.net.affines:
+            plain(op.name + '.weight')
+            plain(op.name + '.bias')
         if st.net.head:
-            dims, s = self._head_strides(st.net)
-            k = st.net.head + '.weight'
-            self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), dims, s, st.whead, s, None, None,
-                          st.adam_state, betas[0], betas[1], eps, weight_decay)
-            k = st.net.head + '.bias'
-            nb = st.params[k].numel()
-            self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), (nb, 1, 1, 1), (1, 0, 0, 0), None, None, None, None,
-                          st.adam_state, betas[0], betas[1], eps, weight_decay)
+            for h, dims, s, dst in self._head_part_layouts(st):
+                k = h + '.weight'
+                self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), dims, s, dst, s, None, None,
+                              st.adam_state, betas[0], betas[1], eps, weight_decay)
+                plain(h + '.bias')
+            if st.net.head_parts is not None:
+                self._head_bias(st)
         st.grad.zero_()
 
     # ------------------------------------------------------------------ inputs
@@ -398,15 +564,47 @@ class Engine:
     # ------------------------------------------------------------------ head
     def _head_forward(self, st: NetState, feats, n, out_index, out):
         F = st.net.feature_size
-        self.ops.rowdot(feats, n, F, st.whead[out_index * F:(out_index + 1) * F], st.params[st.net.head + '.bias'],
-                        out_index, out)
+        bias = st.hbias if st.net.head_parts is not None else st.params[st.net.head + '.bias']
+        self.ops.rowdot(feats, n, F, st.whead[out_index * F:(out_index + 1) * F], bias, out_index, out)
 
     def _head_grads(self, st: NetState, feats, n, out_index, drow):
         F = st.net.feature_size
-        gw = st.g(st.net.head + '.weight')[out_index * F:(out_index + 1) * F]
+        parts = st.net.parts()
+        o0, _ = st.gslices[parts[0][0] + '.weight']            # the parts' weight gradients are contiguous, column order
+        gw = st.grad[o0 + out_index * F:o0 + (out_index + 1) * F]
         self.ops.colsum(feats, n, F, gw, 0, drow)
-        gb = st.g(st.net.head + '.bias')[out_index:out_index + 1]
-        self.ops.colsum(drow, n, 1, gb, 0, None)
+        for h, _ in parts:
+            self.ops.colsum(drow, n, 1, st.g(h + '.bias')[out_index:out_index + 1], 0, None)
+
+    # ------------------------------------------------------------------ labeled loss (srgan.py:414-417 | crowd/srgan.py:247-254)
+    def _labeled(self, st: NetState, acts, deltas, B, y, cfg, Bg, loss_slot, pred, dpred):
+        """Labeled loss on rows [0,B): writes the loss scalar and dLoss/dprediction; for the crowd application also
+        returns the hook that adds the map-loss gradient into the three map buffers' deltas during the backward pass."""
+        net, ops = st.net, self.ops
+        scale = cfg.labeled_loss_multiplier / Bg
+        self._head_forward(st, self._brows_feat(net, acts, 0, B), B, 0, pred)
+        if net.family != 'crowd':
+            if isinstance(y, (tuple, list)):
+                raise ValueError('tuple labels are the crowd application\'s (density, map) pair')
+            ops.labeled_loss(pred, y, B, cfg.labeled_loss_order, scale, loss_slot, dpred)
+            return None
+        density, map_label = y
+        HW = net.label_size * net.label_size
+        if density.numel() != B * HW or map_label.numel() != B * HW:
+            raise ValueError(f'crowd labels must be (density, map) of [{B}, {net.label_size}, {net.label_size}] each')
+        maps = [self._brows(acts[m], net.bufs[m], 0, B) for m in net.map_bufs]
+        dm = self.buf('dmap_scale', (B,), self.mdt)
+        ops.crowd_loss(pred, density, maps, map_label, B, HW, cfg.labeled_loss_order, scale, cfg.map_multiplier,
+                       loss_slot, dpred, dm)
+
+        def hook(name):
+            b = net.bufs[name]
+            ops.crowd_map_grad(self._brows(acts[name], b, 0, B), map_label, dm, self._brows(deltas[name], b, 0, B), B, HW,
+                               len(net.map_bufs), b.act, b.slope)
+        return hook
+
+    def _brows_feat(self, net: Net, t, lo, hi):
+        return self.rows(self._feat(net, t), net.feature_size, lo, hi)
 
     # ------------------------------------------------------------------ DNN step (srgan.py:259-271)
     def dnn_step(self, x, y, cfg, lr, weight_decay):
@@ -414,24 +612,20 @@ class Engine:
         st, net = self.DNN, self.d_net
         B = x.shape[0]
         Bg = self._global_batch(B)
-        L = len(net.layers)
         F = net.feature_size
+        fact, fslope = net.feature_act
         acts = self.alloc_acts('D', net, 5 * B)
         deltas = self.alloc_deltas('D', net, 5 * B)
-        self.load_input(net, x, self.rows(acts[0], net.layers[0].in_elems, 0, B), B)
+        self.load_input(net, x, self.rows(self._in(net, acts), net.in_elems, 0, B), B)
         self.forward(st, acts, 0, B)
-        lastl = net.layers[-1]
-        feats = self.rows(acts[L], F, 0, B)
+        feats = self._brows_feat(net, acts, 0, B)
         pred = self.buf('pred', (B,), self.mdt)
         dpred = self.buf('dpred', (B,), self.mdt)
-        self._head_forward(st, feats, B, 0, pred)
         self.scalars[SC_DNN:SC_DNN + 1].zero_()
-        self.ops.labeled_loss(pred, y, B, cfg.labeled_loss_order, cfg.labeled_loss_multiplier / Bg,
-                              self.scalars[SC_DNN:SC_DNN + 1], dpred)
-        self.ops.seed_rows(self.rows(deltas[L], F, 0, B), B, F, None, dpred,
-                           st.whead[0:F], feats, lastl.act, lastl.slope)
+        hook = self._labeled(st, acts, deltas, B, y, cfg, Bg, self.scalars[SC_DNN:SC_DNN + 1], pred, dpred)
+        self.ops.seed_rows(self._brows_feat(net, deltas, 0, B), B, F, None, dpred, st.whead[0:F], feats, fact, fslope)
         self._head_grads(st, feats, B, 0, dpred)
-        self.backward(st, acts, deltas, 0, B)
+        self.backward(st, acts, deltas, 0, B, hook=hook)
         self.adam(st, lr, weight_decay, cfg.betas, cfg.eps)
 
     # ------------------------------------------------------------------ GAN step (srgan.py:273-320)
@@ -443,43 +637,39 @@ class Engine:
             # srgan.py:363 draws alpha with settings.batch_size rows: the reference itself requires full batches
             raise ValueError('labeled, unlabeled and noise batches must have the same size (SURVEY App. E.2)')
         Bg = self._global_batch(B)
-        L = len(net.layers)
-        lastl = net.layers[-1]
         F = net.feature_size
+        fact, fslope = net.feature_act
         dggan = cfg.method == 'dggan'
+        if dggan and net.graph is not None:
+            raise NotImplementedError('DG-GAN on a graph discriminator (crowd/dggan.py KnnDenseNetCatDggan) has no B200 path')
         acts = self.alloc_acts('D', net, 5 * B)
         deltas = self.alloc_deltas('D', net, 5 * B)
-        in_rows = net.layers[0].in_rows
-        E = net.layers[0].in_elems
+        a_in = self._in(net, acts)
+        E = net.in_elems
         sc = self.scalars
         sc[SC_LABELED:SC_GEN + 1].zero_()
 
-        def blk(t, layer, lo, hi):
-            return self.rows(t, layer.out_elems, lo, hi)
-
         def fblk(lo, hi):
-            return self.rows(acts[L], F, lo, hi)
+            return self._brows_feat(net, acts, lo, hi)
 
         def dblk(lo, hi):
-            return self.rows(deltas[L], F, lo, hi)
+            return self._brows_feat(net, deltas, lo, hi)
 
         # ---- inputs: x, u, fake = G(z) (no grad, srgan.py:290/352), x_hat (srgan.py:362-366)
-        self.load_input(net, x, self.rows(acts[0], E, 0, B), B)
-        self.load_input(net, u, self.rows(acts[0], E, B, 2 * B), B)
+        self.load_input(net, x, self.rows(a_in, E, 0, B), B)
+        self.load_input(net, u, self.rows(a_in, E, B, 2 * B), B)
         gacts = self.alloc_acts('G', gnet, B)
-        gacts[-1] = self.rows(acts[0], E, 2 * B, 3 * B)
+        gacts[-1] = self.rows(a_in, E, 2 * B, 3 * B)
         self.load_input(gnet, z, gacts[0], B)
         self.forward(G, gacts, 0, B)
-        ops.interpolate(self.rows(acts[0], E, B, 2 * B), self.rows(acts[0], E, 2 * B, 3 * B), alpha,
-                        self.rows(acts[0], E, 3 * B, 4 * B), B, E)
+        ops.interpolate(self.rows(a_in, E, B, 2 * B), self.rows(a_in, E, 2 * B, 3 * B), alpha,
+                        self.rows(a_in, E, 3 * B, 4 * B), B, E)
         # ---- one D forward over [x; u; fake; x_hat]
         self.forward(D, acts, 0, 4 * B)
         # ---- labeled loss (srgan.py:329-335, :414-417)
         pred = self.buf('pred', (B,), self.mdt)
         dpred = self.buf('dpred', (B,), self.mdt)
-        self._head_forward(D, fblk(0, B), B, 0, pred)
-        ops.labeled_loss(pred, y, B, cfg.labeled_loss_order, cfg.labeled_loss_multiplier / Bg,
-                         sc[SC_LABELED:SC_LABELED + 1], dpred)
+        hook = self._labeled(D, acts, deltas, B, y, cfg, Bg, sc[SC_LABELED:SC_LABELED + 1], pred, dpred)
         gamma_L = dblk(4 * B, 5 * B)
         s_norm = self.buf('s_norm', (B,), self.mdt)
         if not dggan:
@@ -500,11 +690,11 @@ class Engine:
             ops.distance(sums[1], sums[2], F, inv, DIST_KINDS[cfg.contrasting_distance_function],
                          cfg.contrasting_loss_multiplier * cfg.srgan_loss_multiplier, sc[SC_FAKE:SC_FAKE + 1],
                          gvec[1], gvec[2], True)
-            ops.seed_rows(dblk(0, B), B, F, gvec[0], dpred, D.whead[0:F], fblk(0, B), lastl.act, lastl.slope)
-            ops.seed_rows(dblk(B, 2 * B), B, F, gvec[1], None, None, fblk(B, 2 * B), lastl.act, lastl.slope)
-            ops.seed_rows(dblk(2 * B, 3 * B), B, F, gvec[2], None, None, fblk(2 * B, 3 * B), lastl.act, lastl.slope)
+            ops.seed_rows(dblk(0, B), B, F, gvec[0], dpred, D.whead[0:F], fblk(0, B), fact, fslope)
+            ops.seed_rows(dblk(B, 2 * B), B, F, gvec[1], None, None, fblk(B, 2 * B), fact, fslope)
+            ops.seed_rows(dblk(2 * B, 3 * B), B, F, gvec[2], None, None, fblk(2 * B, 3 * B), fact, fslope)
             # ---- GP target s = ||f(x_hat)||_2 (srgan.py:377-381): gamma_L = (f/s) * act'
-            ops.feature_norm_seed(fblk(3 * B, 4 * B), B, F, s_norm, gamma_L, lastl.act, lastl.slope)
+            ops.feature_norm_seed(fblk(3 * B, 4 * B), B, F, s_norm, gamma_L, fact, fslope)
         else:
             # ---- DG-GAN (coefficient/dggan.py:36-57): BCE on the second head output; GP target = raw score
             su = self.buf('score_u', (B,), self.mdt)
@@ -518,53 +708,39 @@ class Engine:
             ops.bce_logits(sf, B, 1.0, cfg.contrasting_loss_multiplier * cfg.dggan_loss_multiplier / Bg,
                            sc[SC_FAKE:SC_FAKE + 1], dsf)
             w1 = D.whead[F:2 * F]
-            ops.seed_rows(dblk(0, B), B, F, None, dpred, D.whead[0:F], fblk(0, B), lastl.act, lastl.slope)
-            ops.seed_rows(dblk(B, 2 * B), B, F, None, dsu, w1, fblk(B, 2 * B), lastl.act, lastl.slope)
-            ops.seed_rows(dblk(2 * B, 3 * B), B, F, None, dsf, w1, fblk(2 * B, 3 * B), lastl.act, lastl.slope)
+            ops.seed_rows(dblk(0, B), B, F, None, dpred, D.whead[0:F], fblk(0, B), fact, fslope)
+            ops.seed_rows(dblk(B, 2 * B), B, F, None, dsu, w1, fblk(B, 2 * B), fact, fslope)
+            ops.seed_rows(dblk(2 * B, 3 * B), B, F, None, dsf, w1, fblk(2 * B, 3 * B), fact, fslope)
             self._head_grads(D, fblk(B, 2 * B), B, 1, dsu)
             self._head_grads(D, fblk(2 * B, 3 * B), B, 1, dsf)
-            ops.seed_rows(gamma_L, B, F, w1, None, None, fblk(3 * B, 4 * B), lastl.act, lastl.slope)
+            ops.seed_rows(gamma_L, B, F, w1, None, None, fblk(3 * B, 4 * B), fact, fslope)
         self._head_grads(D, fblk(0, B), B, 0, dpred)
         # ---- gradient penalty (srgan.py:360-375) without autograd: SURVEY App. C.3
-        # g-chain: gamma_{l-1} = up(W_l, gamma_l) * act'(h_{l-1}) on the x_hat rows; g_0 has no mask
-        for i in range(L, 1, -1):
-            l, lp = net.layers[i - 1], net.layers[i - 2]
-            self._bwd_data_layer(D, l, blk(deltas[i], l, 4 * B, 5 * B), blk(deltas[i - 1], lp, 4 * B, 5 * B), B,
-                                 blk(acts[i - 1], lp, 3 * B, 4 * B), lp.act, lp.slope)
         g0 = self.buf('g0', (B * E,))
-        l1 = net.layers[0]
-        self._bwd_data_layer(D, l1, blk(deltas[1], l1, 4 * B, 5 * B), g0, B, None, ACT_NONE, 0.0)
+        self.gchain(D, acts, deltas, B, g0)
         gnorm = self.buf('gnorm', (B,), self.mdt)
-        u0 = self.rows(acts[0], E, 4 * B, 5 * B)
+        u0 = self.rows(a_in, E, 4 * B, 5 * B)
         ops.gradnorm_penalty(g0, B, E, cfg.gradient_penalty_multiplier / Bg, 1.0 / Bg, gnorm, sc[SC_GP:SC_GP + 1],
                              sc[SC_GNORM:SC_GNORM + 1], u0)
-        # tangent u-chain: u_l = down(W_l, u_{l-1}) (no bias) * act'(h_l of x_hat)
-        for i, l in enumerate(net.layers, 1):
-            self._fwd_layer(D, l, self.rows(acts[i - 1], l.in_elems, 4 * B, 5 * B), blk(acts[i], l, 4 * B, 5 * B), B,
-                            bias=False, href=blk(acts[i], l, 3 * B, 4 * B), epi=EPI_DACT, lo=4 * B)
+        self.tangent(D, acts, B)
         if not dggan:
-            ops.gp_feature_seed(fblk(4 * B, 5 * B), fblk(3 * B, 4 * B), s_norm, dblk(3 * B, 4 * B), B, F,
-                                lastl.act, lastl.slope)
-            hi = 4 * B
+            ops.gp_feature_seed(fblk(4 * B, 5 * B), fblk(3 * B, 4 * B), s_norm, dblk(3 * B, 4 * B), B, F, fact, fslope)
+            # ---- one backward over [x; u; fake; x_hat], weight gradients also over the tangent block
+            self.backward(D, acts, deltas, 0, 4 * B, 0, 5 * B, hook=hook)
         else:
             # dP/dW_head[1,:] = sum_n u_L,n ; the Jacobian term vanishes (target is linear in the features)
             ops.colsum(fblk(4 * B, 5 * B), B, F, D.g(net.head + '.weight')[F:2 * F], 0, None)
-            hi = 3 * B
-        # ---- one backward over [x; u; fake; (x_hat)], weight gradients also over the tangent block
-        if hi == 4 * B:
-            self.backward(D, acts, deltas, 0, 4 * B, 0, 5 * B)
-        else:
             # DG-GAN: rows [3B,4B) carry no ordinary gradient; weight grads = rows [0,3B) + tangent block [4B,5B)
             self.backward(D, acts, deltas, 0, 3 * B, 0, 3 * B)
             for i, l in enumerate(net.layers, 1):
                 self._wgrad_layer(D, l, self.rows(acts[i - 1], l.in_elems, 4 * B, 5 * B),
-                                  blk(deltas[i], l, 4 * B, 5 * B), B, lo=4 * B)
+                                  self.rows(deltas[i], l.out_elems, 4 * B, 5 * B), B, lo=4 * B)
         self.adam(D, cfg.learning_rate, cfg.weight_decay, cfg.betas, cfg.eps)                     # srgan.py:297
         if not train_generator:
             return
         # ---- generator step (srgan.py:299-305, :383-391) with the UPDATED discriminator
         gacts = self.alloc_acts('G', gnet, B)
-        fake2 = self.rows(acts[0], E, 0, B)
+        fake2 = self.rows(a_in, E, 0, B)
         gacts[-1] = fake2
         self.load_input(gnet, z2, gacts[0], B)
         self.forward(G, gacts, 0, B)
@@ -579,14 +755,14 @@ class Engine:
             gvec = self.buf('gvec', (3, F), self.mdt)
             ops.distance(sums[1], sums[0], F, 1.0 / Bg, DIST_KINDS[cfg.matching_distance_function],
                          cfg.matching_loss_multiplier, sc[SC_GEN:SC_GEN + 1], gvec[1], gvec[0], False)
-            ops.seed_rows(dblk(0, B), B, F, gvec[0], None, None, fblk(0, B), lastl.act, lastl.slope)
+            ops.seed_rows(dblk(0, B), B, F, gvec[0], None, None, fblk(0, B), fact, fslope)
         else:
             self.forward(D, acts, 0, B)
             sf = self.buf('score_f', (B,), self.mdt)
             dsf = self.buf('dscore_f', (B,), self.mdt)
             self._head_forward(D, fblk(0, B), B, 1, sf)
             ops.bce_logits(sf, B, 0.0, 1.0 / Bg, sc[SC_GEN:SC_GEN + 1], dsf)                      # dggan.py:59-64
-            ops.seed_rows(dblk(0, B), B, F, None, dsf, D.whead[F:2 * F], fblk(0, B), lastl.act, lastl.slope)
+            ops.seed_rows(dblk(0, B), B, F, None, dsf, D.whead[F:2 * F], fblk(0, B), fact, fslope)
         gl = gnet.layers
         gdeltas = self.alloc_deltas('G', gnet, B)
         # D data-backward only (the reference's D weight grads here are discarded), ending in
@@ -604,9 +780,9 @@ class Engine:
         net = st.net
         B = x.shape[0]
         acts = self.alloc_acts('D', net, 5 * B)
-        self.load_input(net, x, self.rows(acts[0], net.layers[0].in_elems, 0, B), B)
+        self.load_input(net, x, self.rows(self._in(net, acts), net.in_elems, 0, B), B)
         self.forward(st, acts, 0, B)
-        feats = self.rows(acts[-1], net.feature_size, 0, B)
+        feats = self._brows_feat(net, acts, 0, B)
         pred = self.buf('pred', (B,), self.mdt)
         self._head_forward(st, feats, B, 0, pred)
         return pred, feats

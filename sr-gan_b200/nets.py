@@ -12,7 +12,8 @@ vocabulary, so one repack rule serves both.  nn.Linear [out, in] is the pair wit
 
 Reference modules covered (file:line): coefficient/models.py:12-72 (Generator, MLP, DgganMLP);
 age/models.py:32-80 == driving/models.py (Generator, Discriminator); crowd/models.py:127-147 (DCGenerator, same
-shape family as the age Generator with image_size 224).
+shape family as the age Generator with image_size 224); crowd/models.py:1049-1166 (KnnDenseNetCat: DenseNet trunk with
+eval-mode BatchNorm + three MapModules :763-786), described as a GRAPH of ops over named NHWC buffers (`Net.graph`).
 """
 from __future__ import annotations
 
@@ -62,6 +63,7 @@ class Layer:
     # a Linear with a=(r,s,c), b=b' (ConvTranspose2d on a 1x1 input, age/models.py:37,47)
     master_kind: str = 'conv'
     bias_mod: int = 0              # bias index = column % bias_mod  (fc_up: bias per channel, broadcast over r,s)
+    has_bias: bool = True          # DenseNet trunk convolutions are bias-free (crowd/models.py:341-345,1075)
 
     @property
     def thin_ok(self):
@@ -99,20 +101,87 @@ class Layer:
 
 
 @dataclass
+class Buf:
+    """A named NHWC activation buffer of a graph net: `rows` pixels per sample, `ch` channels (= row pitch).  `act` is the
+    activation its producer applied (the stored values are post-activation; deltas are w.r.t. the pre-activation, the
+    consumer's backward applies act'); `accumulate`: several consumers add into its delta (concat buffers)."""
+    name: str
+    rows: int
+    ch: int
+    act: int = ACT_NONE
+    slope: float = 0.0
+    accumulate: bool = False
+
+
+@dataclass
+class Op:
+    """One node of a graph net.  kind:
+      'conv'    layer (dense src -> dense dst, the conv-pair kernels);
+      'affine'  eval-mode BatchNorm + ReLU: dst[:, :C] = relu(gamma*(src[:, c0:c0+C]-mean)/sqrt(var+eps)+beta), `name` = BN prefix;
+      'copy'    dst[:, c0:c0+C] = src (dense C)        (concat write / feature slice write);
+      'read'    dst (dense C)   = src[:, c0:c0+C]      (tap of a concat buffer);
+      'maxpool' / 'avgpool'  src dense [H, W, C] -> dst[:, c0:c0+C] at [H', W'] (k, stride, pad)."""
+    kind: str
+    src: str
+    dst: str
+    layer: Optional[Layer] = None
+    name: str = ''
+    C: int = 0
+    c0: int = 0
+    H: int = 0
+    W: int = 0
+    k: int = 0
+    stride: int = 0
+    pad: int = 0
+
+
+@dataclass
 class Net:
     kind: str                      # 'D' | 'G'
-    family: str                    # 'coefficient' | 'dcgan'
+    family: str                    # 'coefficient' | 'dcgan' | 'crowd'
     layers: List[Layer]
     head: Optional[str] = None     # state_dict prefix of the prediction head (D only)
     head_outputs: int = 0          # 1 (srgan) or 2 (dggan)
     head_master_kind: str = 'linear'   # 'linear' [out, F] | 'conv_full' [out, C, H, W] -> NHWC feature order
     input_chw: Tuple[int, int, int] = (0, 1, 1)    # (C, H, W) of the reference-side input
     feature_chw: Tuple[int, int, int] = (0, 1, 1)  # (C, H, W) of `.features` before flattening
+    # graph nets (crowd): ops in topological order over named buffers; `layers` then lists the conv layers of the graph
+    graph: Optional[List[Op]] = None
+    bufs: Optional[Dict[str, Buf]] = None
+    input_buf: str = ''
+    feature_buf: str = ''
+    # prediction head as a list of (state_dict prefix, number of feature columns): the crowd count is the sum of four
+    # 20-column heads (crowd/models.py:1153-1162); chain nets have the single `head`
+    head_parts: Optional[List[Tuple[str, int]]] = None
+    map_bufs: Tuple[str, ...] = ()                 # crowd: the three predicted maps (label_size^2 x 1 each)
+    label_size: int = 0
 
     @property
     def feature_size(self):
         c, h, w = self.feature_chw
         return c * h * w
+
+    @property
+    def feature_act(self):
+        """(activation, slope) of the feature layer (its stored values are post-activation)."""
+        if self.graph is not None:
+            b = self.bufs[self.feature_buf]
+            return b.act, b.slope
+        return self.layers[-1].act, self.layers[-1].slope
+
+    @property
+    def in_elems(self):
+        c, h, w = self.input_chw
+        return c * h * w
+
+    @property
+    def affines(self):
+        return [op for op in (self.graph or []) if op.kind == 'affine']
+
+    def parts(self):
+        if self.head_parts is not None:
+            return self.head_parts
+        return [(self.head, self.feature_size)] if self.head else []
 
     def macs_per_sample(self):
         m = sum(l.geom.macs_per_sample for l in self.layers)
@@ -171,6 +240,111 @@ def dcgan_g(image_size=128, conv_dim=64, z_dim=256) -> Net:
     return Net('G', 'dcgan', layers, input_chw=(z_dim, 1, 1))
 
 
+def knn_densenet_cat(block_config=(6, 12, 48, 32), growth_rate=32, num_init_features=64, bn_size=4, image_size=224,
+                     label_size=224) -> Net:
+    """crowd/models.py:1049-1166 KnnDenseNetCat as a graph.  Buffers: 'x' input; 'c0','n0' stem; 'cat{i}' the in-place
+    concat buffer of dense block i (the stem pool / transition pool write its first channels, every dense layer appends
+    growth_rate channels); per dense layer 'n1','b','n2','new'; per transition 'tn','tc'; per MapModule 't','map','m1'..
+    'm3','h'; 'n5','fp','fcf'; 'features' [1 x 80].  Spatial sizes follow torch: stem conv k7 s2 p3, max-pool k3 s2 p1,
+    transitions avg-pool 2."""
+    g, bs = growth_rate, bn_size
+    bufs: Dict[str, Buf] = {}
+    ops: List[Op] = []
+    layers: List[Layer] = []
+    RELU = dict(act=ACT_LEAKY, slope=0.0)
+    LK = dict(act=ACT_LEAKY, slope=0.01)
+
+    def buf(name, rows, ch, **kw):
+        bufs[name] = Buf(name, rows, ch, **kw)
+        return name
+
+    def conv(name, src, dst, geom, fwd, master, act=ACT_NONE, slope=0.0, bias=False):
+        l = Layer(name, fwd, geom, act, slope, master, has_bias=bias)
+        layers.append(l)
+        ops.append(Op('conv', src, dst, layer=l))
+
+    H0 = image_size
+    H1 = (H0 + 2 * 3 - 7) // 2 + 1            # stem conv
+    H2 = (H1 + 2 * 1 - 3) // 2 + 1            # max-pool
+    buf('x', H0 * H0, 3)
+    buf('c0', H1 * H1, num_init_features)
+    conv('conv_layer1.conv0', 'x', 'c0', Geom(H1, H1, num_init_features, H0, H0, 3, 7, 7, 2, 3), 'down',
+         (num_init_features, 3, 7, 7))
+    buf('n0', H1 * H1, num_init_features, **RELU)
+    ops.append(Op('affine', 'c0', 'n0', name='conv_layer1.norm0', C=num_init_features))
+    c, h = num_init_features, H2
+    taps = []
+    for bi, n_layers in enumerate(block_config, 1):
+        ctot = c + n_layers * g
+        cat = buf(f'cat{bi}', h * h, ctot, accumulate=True)
+        if bi == 1:
+            ops.append(Op('maxpool', 'n0', cat, C=c, c0=0, H=H1, W=H1, k=3, stride=2, pad=1))
+        else:
+            ops.append(Op('avgpool', f'tc{bi - 1}', cat, C=c, c0=0, H=2 * h, W=2 * h, k=2, stride=2))
+            taps.append((cat, c, h))
+        for li in range(1, n_layers + 1):
+            pre = f'dense_blocks.denseblock{bi}.denselayer{li}'
+            tag = f'{bi}.{li}'
+            buf('n1.' + tag, h * h, c, **RELU)
+            ops.append(Op('affine', cat, 'n1.' + tag, name=pre + '.norm1', C=c, c0=0))
+            buf('b.' + tag, h * h, bs * g)
+            conv(pre + '.conv1', 'n1.' + tag, 'b.' + tag, Geom(h, h, bs * g, h, h, c, 1, 1, 1, 0), 'down', (bs * g, c, 1, 1))
+            buf('n2.' + tag, h * h, bs * g, **RELU)
+            ops.append(Op('affine', 'b.' + tag, 'n2.' + tag, name=pre + '.norm2', C=bs * g))
+            buf('new.' + tag, h * h, g)
+            conv(pre + '.conv2', 'n2.' + tag, 'new.' + tag, Geom(h, h, g, h, h, bs * g, 3, 3, 1, 1), 'down', (g, bs * g, 3, 3))
+            ops.append(Op('copy', 'new.' + tag, cat, C=g, c0=c))
+            c += g
+        if bi != len(block_config):
+            pre = f'transition_layers.transition{bi}'
+            buf(f'tn{bi}', h * h, c, **RELU)
+            ops.append(Op('affine', cat, f'tn{bi}', name=pre + '.norm', C=c, c0=0))
+            buf(f'tc{bi}', h * h, c // 2)
+            conv(pre + '.conv', f'tn{bi}', f'tc{bi}', Geom(h, h, c // 2, h, h, c, 1, 1, 1, 0), 'down', (c // 2, c, 1, 1))
+            c //= 2
+            if h % 2:
+                raise ValueError('transition input must have an even extent')
+            h //= 2
+    buf('n5', h * h, c, **RELU)
+    ops.append(Op('affine', f'cat{len(block_config)}', 'n5', name='norm5', C=c, c0=0))
+    buf('fp', 1, c, **RELU)                         # average of ReLU outputs; no activation of its own: see below
+    bufs['fp'].act, bufs['fp'].slope = ACT_NONE, 0.0
+    ops.append(Op('avgpool', 'n5', 'fp', C=c, c0=0, H=h, W=h, k=h, stride=h))
+    buf('fcf', 1, 20, **LK)
+    conv('final_count_feature_layer', 'fp', 'fcf', Geom(1, 1, 20, 1, 1, c, 1, 1, 1, 0), 'down', (20, c, 1, 1), bias=True, **LK)
+    F = 80
+    buf('features', 1, F, **LK)
+    L = label_size
+    maps = []
+    for i, (cat, ci, hi) in enumerate(taps[:3], 1):
+        k = L // hi
+        if k * hi != L or L % 8:
+            raise ValueError('label_size must be a multiple of the tap extents and of 8')
+        pre = f'map_module{i}'
+        buf(f't{i}', hi * hi, ci)
+        ops.append(Op('read', cat, f't{i}', C=ci, c0=0))
+        buf(f'map{i}', L * L, 1, **LK)
+        conv(pre + '.map_transposed_conv_layer', f't{i}', f'map{i}', Geom(hi, hi, ci, L, L, 1, k, k, k, 0), 'up',
+             (ci, 1, k, k), bias=True, **LK)
+        maps.append(f'map{i}')
+        src, hh, cin = f'map{i}', L, 1
+        for j, cout in enumerate((8, 16, 32), 1):
+            buf(f'm{j}.{i}', (hh // 2) ** 2, cout, **LK)
+            conv(f'{pre}.conv{j}', src, f'm{j}.{i}', Geom(hh // 2, hh // 2, cout, hh, hh, cin, 2, 2, 2, 0), 'down',
+                 (cout, cin, 2, 2), bias=True, **LK)
+            src, hh, cin = f'm{j}.{i}', hh // 2, cout
+        buf(f'h{i}', 1, 20, **LK)
+        conv(pre + '.linear1', src, f'h{i}', Geom(1, 1, 20, hh, hh, 32, hh, hh, 1, 0), 'down', (20, 32, hh, hh), bias=True, **LK)
+        ops.append(Op('copy', f'h{i}', 'features', C=20, c0=20 * (i - 1)))
+    ops.append(Op('copy', 'fcf', 'features', C=20, c0=60))
+    # the ops must be in an order where every buffer is complete before it is read: move the head ops to the end (they
+    # were appended after the trunk already) -- and the final-count ops precede the feature copy of slice 3: fine.
+    head_parts = [(f'map_module{i}.count_layer', 20) for i in (1, 2, 3)] + [('count_layer', 20)]
+    return Net('D', 'crowd', layers, head='count_layer', head_outputs=1, head_master_kind='parts',
+               input_chw=(3, image_size, image_size), feature_chw=(F, 1, 1), graph=ops, bufs=bufs, input_buf='x',
+               feature_buf='features', head_parts=head_parts, map_bufs=tuple(maps), label_size=L)
+
+
 def describe_module(module) -> Net:
     """Maps a reference nn.Module instance (or this package's mirrors) to its Net, by structure, not by import."""
     sd = {k: tuple(v.shape) for k, v in module.state_dict().items()}
@@ -182,6 +356,21 @@ def describe_module(module) -> Net:
         if n_out > 2:
             raise NotImplementedError('SganMLP (sgan.py) is outside the SR-GAN hot path (SURVEY 8f rank 3)')
         return coefficient_d(h, n_in, dggan=(n_out == 2))
+    if 'conv_layer1.conv0.weight' in sd and 'map_module3.linear1.weight' in sd and 'final_count_feature_layer.weight' in sd:
+        import re
+        blocks = {}
+        for k in sd:
+            m = re.match(r'dense_blocks\.denseblock(\d+)\.denselayer(\d+)\.conv1\.weight', k)
+            if m:
+                blocks[int(m.group(1))] = max(blocks.get(int(m.group(1)), 0), int(m.group(2)))
+        cfg = tuple(blocks[i] for i in sorted(blocks))
+        w1, w2 = sd['dense_blocks.denseblock1.denselayer1.conv1.weight'], sd['dense_blocks.denseblock1.denselayer1.conv2.weight']
+        growth, init = w2[0], sd['conv_layer1.conv0.weight'][0]
+        bn_size = w1[0] // growth
+        label = sd['map_module1.linear1.weight'][2] * 8
+        k1 = sd['map_module1.map_transposed_conv_layer.weight'][2]
+        image = (label // k1) * 8
+        return knn_densenet_cat(cfg, growth, init, bn_size, image, label)
     if 'fc.0.weight' in sd and 'layer4.0.weight' in sd:
         z_dim, c8, k, _ = sd['fc.0.weight']
         return dcgan_g(k * 16, c8 // 8, z_dim)
@@ -189,5 +378,5 @@ def describe_module(module) -> Net:
         n_out, c8, k, _ = sd['layer5.0.weight']
         return dcgan_d(k * 16, c8 // 8, n_out)
     raise NotImplementedError(
-        f'{type(module).__name__}: no B200 path for this module yet (crowd KnnDenseNetCat is SURVEY 8a16, next round); '
+        f'{type(module).__name__}: no B200 path for this module; '
         'refusing to fall back to the PyTorch path')

@@ -101,3 +101,43 @@ def test_thin_layer_lowering_matches_oracle_fp64():
     for net, params, mine in (('D', st.D, eng.D), ('G', st.G, eng.G), ('DNN', st.DNN, eng.DNN)):
         for k, v in params.items():
             assert rel(mine.params[k], v) < 1e-8, (net, k, rel(mine.params[k], v))
+
+
+def build_crowd_engine(st, dtype, spec_kwargs, image, z_dim, g_conv_dim):
+    d_net = nets.knn_densenet_cat(spec_kwargs['block_config'], spec_kwargs['growth_rate'], spec_kwargs['num_init_features'],
+                                  spec_kwargs['bn_size'], image, spec_kwargs['label_patch_size'])
+    g_net = nets.dcgan_g(image, g_conv_dim, z_dim)
+    D = {k: v.clone() for k, v in st.D.items()}
+    G = {k: v.clone() for k, v in st.G.items()}
+    DNN = {k: v.clone() for k, v in st.DNN.items()}
+    return engine.Engine(TorchOps(), d_net, g_net, D, G, DNN, act_dtype=dtype, device='cpu')
+
+
+def test_crowd_graph_schedule_matches_oracle_fp64():
+    """Crowd SR-GAN (KnnDenseNetCat graph: eval-mode BatchNorm affine with trainable weight/bias, ReLU, max/avg pools,
+    in-place concat, three MapModules, summed count heads, crowd labeled loss incl. the map term) through the explicit
+    schedule -- forward, g-chain, tangent chain, one backward with the tangent-block gradients -- against the oracle's
+    autograd double-backward, fp64, reduced DenseNet (2,2,2,2) at 64x64 (the full DenseNet-201 is pinned against the
+    reference in tests/test_oracle_golden.py)."""
+    dt = torch.float64
+    kw = dict(block_config=(2, 2, 2, 2), growth_rate=8, num_init_features=16, bn_size=2, label_patch_size=64)
+    st = O.init_crowd(seed=1, image_size=64, z_dim=16, g_conv_dim=8, dtype=dt, scale=2.0, **kw)
+    cfg = O.StepConfig(batch_size=3, matching_loss_multiplier=1e3, contrasting_loss_multiplier=1e2,
+                       gradient_penalty_multiplier=1e2, map_multiplier=1e-3, weight_decay=1e-3)
+    eng = build_crowd_engine(st, dt, kw, 64, 16, 8)
+    B = 3
+    for i in range(2):
+        x, y, u, z, alpha, z2 = O.synthetic_crowd_batch(B, 10 + i, image=64, label=64, z_dim=16, dtype=dt)
+        out = O.training_step(st, cfg, x, y, u, z, alpha, z2, step=i)
+        eng.dnn_step(x, y, cfg, O.dnn_lr(cfg, i), cfg.weight_decay)
+        eng.gan_step(x, y, u, z, alpha, z2, cfg)
+        got = read_scalars(eng)
+        assert out['gradient_penalty'] > 0
+        for k in SCALARS:
+            assert got[k] == pytest.approx(out[k], rel=1e-9, abs=1e-12), (i, k, got[k], out[k])
+    for net, params, mine in (('D', st.D, eng.D), ('G', st.G, eng.G), ('DNN', st.DNN, eng.DNN)):
+        for k, v in params.items():
+            if O.is_buffer_key(k):
+                assert torch.equal(mine.params[k], v)
+            else:
+                assert rel(mine.params[k], v) < 1e-8, (net, k, rel(mine.params[k], v))

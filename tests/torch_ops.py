@@ -256,3 +256,125 @@ class TorchOps:
         denom = vv.sqrt() * float(state[2]) + eps
         p.addcdiv_(mm, denom, value=-float(state[1]))
         self.repack(p, dims, out1, s1, out2, s2)
+
+    # ---- graph-net ops (crowd KnnDenseNetCat): eval-mode BatchNorm affine, slice copies, pools, crowd labeled loss
+    @staticmethod
+    def _cd(t):
+        return torch.float64 if t.dtype == torch.float64 else torch.float32
+
+    def affine(self, x, x_pitch, x_c0, y, rows, C, gamma, beta, mean, var, eps, href, mode, act, slope):
+        """mode 0: y = act(gamma*(x-mean)/sqrt(var+eps)+beta); mode 1 (tangent): y = gamma/sqrt(var+eps)*x * act'(href).
+        x is the channel slice [x_c0, x_c0+C) of rows with pitch x_pitch; y is dense [rows, C]."""
+        self.launches += 1
+        cd = self._cd(x)
+        xs = x.view(rows, x_pitch)[:, x_c0:x_c0 + C].to(cd)
+        s = gamma.detach().to(cd) / torch.sqrt(var.detach().to(cd) + eps)
+        if mode == 0:
+            v = apply_act((xs - mean.detach().to(cd)) * s + beta.detach().to(cd), act, slope)
+        else:
+            v = xs * s * dact(href.view(rows, C).to(cd), act, slope)
+        y.copy_(v.reshape(-1).to(y.dtype))
+
+    def affine_bwd(self, dy, dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, accumulate):
+        """dx[:, c0:c0+C] (+)= dy * gamma/sqrt(var+eps)   (dy dense [rows, C], w.r.t. the affine's pre-activation)."""
+        self.launches += 1
+        cd = self._cd(dy)
+        s = gamma.detach().to(cd) / torch.sqrt(var.detach().to(cd) + eps)
+        v = dy.view(rows, C).to(cd) * s
+        d = dx.view(rows, dx_pitch)
+        if accumulate:
+            d[:, dx_c0:dx_c0 + C] += v.to(dx.dtype)
+        else:
+            d[:, dx_c0:dx_c0 + C] = v.to(dx.dtype)
+
+    def affine_grad(self, dy, x, x_pitch, x_c0, rows, C, mean, var, eps, dgamma, dbeta, subtract_mean):
+        """dgamma[c] += sum_r dy[r,c] * (x[r,c0+c] - mean[c]*subtract_mean) / sqrt(var[c]+eps); dbeta[c] += sum_r dy[r,c]."""
+        self.launches += 1
+        cd = dgamma.dtype
+        d = dy.view(rows, C).to(cd)
+        xs = x.view(rows, x_pitch)[:, x_c0:x_c0 + C].to(cd)
+        if subtract_mean:
+            xs = xs - mean.detach().to(cd)
+        dgamma += (d * xs).sum(0) / torch.sqrt(var.detach().to(cd) + eps)
+        if dbeta is not None:
+            dbeta += d.sum(0)
+
+    def copy2d(self, src, src_pitch, src_c0, dst, dst_pitch, dst_c0, rows, C, accumulate):
+        self.launches += 1
+        s = src.view(rows, src_pitch)[:, src_c0:src_c0 + C]
+        d = dst.view(rows, dst_pitch)
+        if accumulate:
+            d[:, dst_c0:dst_c0 + C] += s.to(dst.dtype)
+        else:
+            d[:, dst_c0:dst_c0 + C] = s.to(dst.dtype)
+
+    @staticmethod
+    def _pool_out(H, k, s, p):
+        return (H + 2 * p - k) // s + 1
+
+    def _maxpool_idx(self, xref, n, H, W, C, k, s, p):
+        """argmax (flat h*W+w index, first maximum in scan order like torch) of every window: [n, C, Ho, Wo]."""
+        xr = xref.view(n, H, W, C).permute(0, 3, 1, 2).to(torch.float64)
+        _, idx = F.max_pool2d(xr, k, s, p, return_indices=True)
+        return idx
+
+    def maxpool(self, x, xref, y, y_pitch, y_c0, n, H, W, C, k, s, p):
+        """y[:, c0:c0+C] = x at the argmax of xref (xref None: of x itself) over each k x k window (stride s, pad p)."""
+        self.launches += 1
+        idx = self._maxpool_idx(x if xref is None else xref, n, H, W, C, k, s, p)
+        Ho, Wo = idx.shape[2], idx.shape[3]
+        xv = x.view(n, H * W, C).permute(0, 2, 1)                                   # [n, C, HW]
+        out = torch.gather(xv, 2, idx.reshape(n, C, Ho * Wo))                       # [n, C, HoWo]
+        y.view(n * Ho * Wo, y_pitch)[:, y_c0:y_c0 + C] = out.permute(0, 2, 1).reshape(n * Ho * Wo, C).to(y.dtype)
+
+    def maxpool_bwd(self, xref, dy, dy_pitch, dy_c0, dx, n, H, W, C, k, s, p, act, slope):
+        """dx[i] = act'(xref[i]) * sum over the windows whose argmax is i of dy[window]   (dx dense [n,H,W,C], overwritten)."""
+        self.launches += 1
+        cd = self._cd(dy)
+        idx = self._maxpool_idx(xref, n, H, W, C, k, s, p)
+        Ho, Wo = idx.shape[2], idx.shape[3]
+        d = dy.view(n * Ho * Wo, dy_pitch)[:, dy_c0:dy_c0 + C].to(cd).reshape(n, Ho * Wo, C).permute(0, 2, 1)
+        g = torch.zeros(n, C, H * W, dtype=cd)
+        g.scatter_add_(2, idx.reshape(n, C, Ho * Wo), d)
+        g = g.permute(0, 2, 1).reshape(-1) * dact(xref.to(cd), act, slope)
+        dx.copy_(g.to(dx.dtype))
+
+    def avgpool(self, x, y, y_pitch, y_c0, n, H, W, C, k):
+        """y[:, c0:c0+C] = mean over non-overlapping k x k windows of x (dense [n,H,W,C])."""
+        self.launches += 1
+        cd = self._cd(x)
+        Ho, Wo = H // k, W // k
+        v = x.view(n, Ho, k, Wo, k, C).to(cd).mean(dim=(2, 4))
+        y.view(n * Ho * Wo, y_pitch)[:, y_c0:y_c0 + C] = v.reshape(n * Ho * Wo, C).to(y.dtype)
+
+    def avgpool_bwd(self, dy, dy_pitch, dy_c0, dx, n, H, W, C, k, href, act, slope):
+        """dx[n,h,w,c] = dy[n,h/k,w/k,c0+c] / k^2 * act'(href[n,h,w,c])."""
+        self.launches += 1
+        cd = self._cd(dy)
+        Ho, Wo = H // k, W // k
+        d = dy.view(n * Ho * Wo, dy_pitch)[:, dy_c0:dy_c0 + C].to(cd).view(n, Ho, 1, Wo, 1, C) / (k * k)
+        g = d.expand(n, Ho, k, Wo, k, C).reshape(-1)
+        if href is not None and act != ACT_NONE:
+            g = g * dact(href.to(cd), act, slope)
+        dx.copy_(g.to(dx.dtype))
+
+    def crowd_loss(self, pred, density, maps, map_label, B, HW, order, scale, map_mult, loss_out, dpred, dm):
+        """crowd/srgan.py:247-254 on rows [0,B): loss += scale * sum_b (|pred_b - sum(density_b)|^o + map_mult * m_b^o),
+        m_b = sum_hw mean_c |map_c - label|; dpred_b = dLoss/dpred_b; dm_b = dLoss/dm_b."""
+        self.launches += 1
+        cd = pred.dtype
+        target = density.detach().reshape(B, HW).to(cd).sum(1)
+        lab = map_label.detach().reshape(B, HW).to(cd)
+        m = sum((mp.view(B, HW).to(cd) - lab).abs() for mp in maps).sum(1) / len(maps)
+        d = pred - target
+        loss_out += scale * (d.abs().pow(order) + map_mult * m.pow(order)).sum()
+        dpred.copy_(scale * order * d.abs().pow(order - 1) * torch.sign(d))
+        dm.copy_(scale * map_mult * order * m.pow(order - 1))
+
+    def crowd_map_grad(self, mp, map_label, dm, delta, B, HW, nmaps, act, slope):
+        """delta[b,hw] += dm_b / nmaps * sign(map - label) * act'(map)   (delta w.r.t. the map layer's pre-activation)."""
+        self.launches += 1
+        cd = dm.dtype
+        v = mp.view(B, HW).to(cd)
+        g = dm.view(B, 1) / nmaps * torch.sign(v - map_label.detach().reshape(B, HW).to(cd)) * dact(v, act, slope)
+        delta.view(B, HW).add_(g.to(delta.dtype))
