@@ -143,6 +143,47 @@ int srgan_adam(float* param, const float* grad, float* m, float* v, const int* d
 int srgan_repack(const float* param, const int* dims4, void* out1, const long long* o1strides4, void* out2,
                  const long long* o2strides4, int out_dtype, void* stream);
 
+/* ---- graph discriminator (crowd KnnDenseNetCat, crowd/models.py:1049-1166) -------------------------------------------
+ * A "slice" is the channel range [c0, c0+C) of NHWC rows with pitch `pitch` elements (the in-place concat buffers of the
+ * dense blocks, crowd/models.py:347-353 torch.cat).  Dense operands have pitch C.
+ *
+ * Eval-mode BatchNorm2d (+ReLU): disable_batch_norm_updates srgan.py:538-542 applied at :261,276 makes every
+ * _BatchNorm a per-channel affine of its running statistics; weight and bias stay trainable (crowd/models.py:339-343,
+ * 367, 1077, 1092).  mode 0: y = act(gamma*(x-mean)/sqrt(var+eps)+beta); mode 1 (tangent pass of the gradient penalty):
+ * y = gamma/sqrt(var+eps) * x * act'(href). */
+int srgan_affine(const void* x, int x_pitch, int x_c0, void* y, long long rows, int C, const float* gamma, const float* beta,
+                 const float* mean, const float* var, float eps, const void* href, int mode, int act, float slope, int dtype,
+                 void* stream);
+/* dx[:, c0:c0+C] (+)= dy * gamma/sqrt(var+eps)   (dy dense, w.r.t. the affine's pre-activation) */
+int srgan_affine_bwd(const void* dy, void* dx, int dx_pitch, int dx_c0, long long rows, int C, const float* gamma,
+                     const float* var, float eps, int accumulate, int dtype, void* stream);
+/* dgamma[c] += sum_r dy[r,c]*(x[r,c0+c] - mean[c]*subtract_mean)/sqrt(var[c]+eps); dbeta[c] += sum_r dy[r,c] (may be NULL) */
+int srgan_affine_grad(const void* dy, const void* x, int x_pitch, int x_c0, long long rows, int C, const float* mean,
+                      const float* var, float eps, float* dgamma, float* dbeta, int subtract_mean, int dtype, void* stream);
+/* dst[:, d0:d0+C] (+)= src[:, s0:s0+C] : torch.cat writes / their backward reads, MapModule taps */
+int srgan_copy2d(const void* src, int src_pitch, int src_c0, void* dst, int dst_pitch, int dst_c0, long long rows, int C,
+                 int accumulate, int dtype, void* stream);
+/* nn.MaxPool2d(k, stride, pad) (crowd/models.py:1078): y slice = x at the argmax of xref's windows (xref NULL: x itself;
+ * the tangent pass routes the tangent through the forward's argmax); first maximum in scan order like torch */
+int srgan_maxpool(const void* x, const void* xref, void* y, int y_pitch, int y_c0, int n, int H, int W, int C, int k,
+                  int stride, int pad, int dtype, void* stream);
+/* dx[i] = act'(xref[i]) * sum of dy over the windows whose argmax is i (dx dense, overwritten) */
+int srgan_maxpool_bwd(const void* xref, const void* dy, int dy_pitch, int dy_c0, void* dx, int n, int H, int W, int C, int k,
+                      int stride, int pad, int act, float slope, int dtype, void* stream);
+/* nn.AvgPool2d(k, k) (crowd/models.py:370) and avg_pool2d(kernel 7) (:1151): non-overlapping k x k means */
+int srgan_avgpool(const void* x, void* y, int y_pitch, int y_c0, int n, int H, int W, int C, int k, int dtype, void* stream);
+int srgan_avgpool_bwd(const void* dy, int dy_pitch, int dy_c0, void* dx, int n, int H, int W, int C, int k, const void* href,
+                      int act, float slope, int dtype, void* stream);
+/* CrowdExperiment.labeled_loss_function, crowd/srgan.py:247-254, on B samples:
+ * loss += scale * sum_b (|pred_b - sum(density_b)|^order + map_mult * m_b^order), m_b = sum_hw mean_c |map_c - map_label|;
+ * dpred_b = dLoss/dpred_b, dm_b = dLoss/dm_b.  maps: HOST array of nmaps (<= 4) device pointers, [B, HW] each. */
+int srgan_crowd_loss(const float* pred, const float* density, const void* const* maps, int nmaps, const float* map_label,
+                     int B, long long HW, int order, float scale, float map_mult, float* loss, float* dpred, float* dm,
+                     int dtype, void* stream);
+/* delta[b,i] += dm_b/nmaps * sign(map - map_label) * act'(map): the map-loss gradient w.r.t. one map layer's pre-activation */
+int srgan_crowd_map_grad(const void* map, const float* map_label, const float* dm, void* delta, int B, long long HW, int nmaps,
+                         int act, float slope, int dtype, void* stream);
+
 /* ---- coefficient application: the whole step in one persistent kernel ------------------------------------------
  * BASELINE configs[0] (run.py:46-54): coefficient/models.py:12-72 MLPs (50->10->10->10->{1,2}, generator 10->10->10->10->50,
  * leaky 0.01) are 2.4 k parameters; the reference spends ~850 ATen launches per step on them.  One cooperative launch

@@ -1,0 +1,459 @@
+// Bandwidth-bound kernels of the graph discriminator (crowd KnnDenseNetCat, crowd/models.py:1049-1166):
+//   eval-mode BatchNorm affine (+ReLU) forward / tangent / backward / parameter gradients (srgan.py:538-542 freezes the
+//   statistics, weight and bias stay trainable), channel-slice copies (the in-place concat of the dense blocks), max / average
+//   pooling with their transposes, and the crowd labeled loss (crowd/srgan.py:247-254).
+// All activations are NHWC rows; a "slice" is the channel range [c0, c0+C) of rows with pitch `pitch` elements.
+// Vectorised (4 elements per thread) whenever C, the pitches and the offsets are multiples of 4.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float4 ld4f(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float bn_scale(float gamma, float var, float eps) { return gamma / sqrtf(var + eps); }
+
+inline int ew_grid(long long work_items) {
+    long long b = (work_items + 255) / 256;
+    const long long cap = (long long)kNumSMs * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// affine: mode 0  y = act(gamma*(x-mean)/sqrt(var+eps) + beta) ; mode 1 (tangent)  y = gamma/sqrt(var+eps) * x * act'(href)
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) affine_kernel(const T* __restrict__ x, int x_pitch, int x_c0, T* __restrict__ y,
+                                                     long long rows, int C, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, const float* __restrict__ mean,
+                                                     const float* __restrict__ var, float eps, const T* __restrict__ href,
+                                                     int mode, int act, float slope) {
+    constexpr int V = VEC ? 4 : 1;
+    const int cv = C / V;
+    const long long total = rows * cv;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cv;
+        const int c = (int)(i - r * cv) * V;
+        const T* xp = x + r * x_pitch + x_c0 + c;
+        T* yp = y + r * C + c;
+        if (VEC) {
+            const float4 xv = ld4(xp), g = ld4f(gamma + c), vr = ld4f(var + c);
+            float4 s = make_float4(bn_scale(g.x, vr.x, eps), bn_scale(g.y, vr.y, eps), bn_scale(g.z, vr.z, eps), bn_scale(g.w, vr.w, eps));
+            float4 o;
+            if (mode == 0) {
+                const float4 m = ld4f(mean + c), b = ld4f(beta + c);
+                o.x = act_fwd((xv.x - m.x) * s.x + b.x, act, slope); o.y = act_fwd((xv.y - m.y) * s.y + b.y, act, slope);
+                o.z = act_fwd((xv.z - m.z) * s.z + b.z, act, slope); o.w = act_fwd((xv.w - m.w) * s.w + b.w, act, slope);
+            } else {
+                const float4 h = ld4(href + r * C + c);
+                o.x = xv.x * s.x * act_bwd(h.x, act, slope); o.y = xv.y * s.y * act_bwd(h.y, act, slope);
+                o.z = xv.z * s.z * act_bwd(h.z, act, slope); o.w = xv.w * s.w * act_bwd(h.w, act, slope);
+            }
+            st4(yp, o);
+        } else {
+            const float s = bn_scale(gamma[c], var[c], eps);
+            const float xv = to_f(*xp);
+            float o;
+            if (mode == 0) o = act_fwd((xv - mean[c]) * s + beta[c], act, slope);
+            else o = xv * s * act_bwd(to_f(href[r * C + c]), act, slope);
+            *yp = from_f<T>(o);
+        }
+    }
+}
+
+// dx[:, c0:c0+C] (+)= dy * gamma/sqrt(var+eps)
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) affine_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int dx_pitch, int dx_c0,
+                                                         long long rows, int C, const float* __restrict__ gamma,
+                                                         const float* __restrict__ var, float eps, int accumulate) {
+    constexpr int V = VEC ? 4 : 1;
+    const int cv = C / V;
+    const long long total = rows * cv;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cv;
+        const int c = (int)(i - r * cv) * V;
+        T* xp = dx + r * dx_pitch + dx_c0 + c;
+        if (VEC) {
+            const float4 d = ld4(dy + r * C + c), g = ld4f(gamma + c), vr = ld4f(var + c);
+            float4 o = make_float4(d.x * bn_scale(g.x, vr.x, eps), d.y * bn_scale(g.y, vr.y, eps), d.z * bn_scale(g.z, vr.z, eps),
+                                   d.w * bn_scale(g.w, vr.w, eps));
+            if (accumulate) { const float4 p = ld4(xp); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+            st4(xp, o);
+        } else {
+            float o = to_f(dy[r * C + c]) * bn_scale(gamma[c], var[c], eps);
+            if (accumulate) o += to_f(*xp);
+            *xp = from_f<T>(o);
+        }
+    }
+}
+
+// dgamma[c] += sum_r dy[r,c]*(x[r,c0+c]-mean[c]*sub)/sqrt(var[c]+eps) ; dbeta[c] += sum_r dy[r,c]
+// block = 8 warps over a 32*V-column strip; blockIdx.y = row chunk; lanes own V consecutive columns
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) affine_grad_kernel(const T* __restrict__ dy, const T* __restrict__ x, int x_pitch, int x_c0,
+                                                          long long rows, int C, const float* __restrict__ mean,
+                                                          const float* __restrict__ var, float eps, float* __restrict__ dgamma,
+                                                          float* __restrict__ dbeta, int subtract_mean, long long rows_per_block) {
+    constexpr int V = VEC ? 4 : 1;
+    __shared__ float sg[8][32 * V + 1], sb[8][32 * V + 1];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + lane) * V;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    const long long r1 = min(rows, r0 + rows_per_block);
+    float ag[V], ab[V], mu[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) { ag[v] = 0.f; ab[v] = 0.f; mu[v] = (subtract_mean && c + v < C) ? mean[c + v] : 0.f; }
+    if (c < C) {
+        for (long long r = r0 + w; r < r1; r += 8) {
+            if (VEC) {
+                const float4 d = ld4(dy + r * C + c), xv = ld4(x + r * x_pitch + x_c0 + c);
+                ag[0] = fmaf(d.x, xv.x - mu[0], ag[0]); ab[0] += d.x;
+                if (V > 1) {
+                    ag[1 % V] = fmaf(d.y, xv.y - mu[1 % V], ag[1 % V]); ab[1 % V] += d.y;
+                    ag[2 % V] = fmaf(d.z, xv.z - mu[2 % V], ag[2 % V]); ab[2 % V] += d.z;
+                    ag[3 % V] = fmaf(d.w, xv.w - mu[3 % V], ag[3 % V]); ab[3 % V] += d.w;
+                }
+            } else {
+                const float d = to_f(dy[r * C + c]);
+                ag[0] = fmaf(d, to_f(x[r * x_pitch + x_c0 + c]) - mu[0], ag[0]); ab[0] += d;
+            }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) { sg[w][lane * V + v] = ag[v]; sb[w][lane * V + v] = ab[v]; }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 32 * V; j += 256) {
+        const int cc = blockIdx.x * 32 * V + j;
+        if (cc < C) {
+            float g = 0.f, b = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { g += sg[k][j]; b += sb[k][j]; }
+            atomicAdd(dgamma + cc, g / sqrtf(var[cc] + eps));
+            if (dbeta) atomicAdd(dbeta + cc, b);
+        }
+    }
+}
+
+// dst[:, d0:d0+C] (+)= src[:, s0:s0+C]
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) copy2d_kernel(const T* __restrict__ src, int src_pitch, int src_c0, T* __restrict__ dst,
+                                                     int dst_pitch, int dst_c0, long long rows, int C, int accumulate) {
+    constexpr int V = VEC ? 4 : 1;
+    const int cv = C / V;
+    const long long total = rows * cv;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cv;
+        const int c = (int)(i - r * cv) * V;
+        const T* sp = src + r * src_pitch + src_c0 + c;
+        T* dp = dst + r * dst_pitch + dst_c0 + c;
+        if (VEC) {
+            float4 v = ld4(sp);
+            if (accumulate) { const float4 p = ld4(dp); v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w; }
+            st4(dp, v);
+        } else {
+            float v = to_f(*sp);
+            if (accumulate) v += to_f(*dp);
+            *dp = from_f<T>(v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// pooling.  Window argmax = first maximum in (h, w) scan order (torch's max_pool2d rule); NaN never occurs here.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ int window_argmax(const T* __restrict__ xr, int H, int W, int C, int ho, int wo, int k, int s, int p) {
+    // xr points at (sample, channel) of an NHWC tensor; returns h*W+w of the first maximum (-1: empty window)
+    float best = -INFINITY;
+    int arg = -1;
+    const int h0 = ho * s - p, w0 = wo * s - p;
+    for (int dh = 0; dh < k; ++dh) {
+        const int h = h0 + dh;
+        if (h < 0 || h >= H) continue;
+        for (int dw = 0; dw < k; ++dw) {
+            const int w = w0 + dw;
+            if (w < 0 || w >= W) continue;
+            const float v = to_f(xr[((long long)h * W + w) * C]);
+            if (v > best || arg < 0) { best = v; arg = h * W + w; }
+        }
+    }
+    return arg;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_kernel(const T* __restrict__ x, const T* __restrict__ xref, T* __restrict__ y,
+                                                      int y_pitch, int y_c0, int n, int H, int W, int C, int Ho, int Wo, int k,
+                                                      int s, int p) {
+    const long long total = (long long)n * Ho * Wo * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long t = i / C;
+        const int wo = (int)(t % Wo); t /= Wo;
+        const int ho = (int)(t % Ho);
+        const long long b = t / Ho;
+        const long long base = b * H * W * C + c;
+        const int arg = window_argmax(xref + base, H, W, C, ho, wo, k, s, p);
+        y[((b * Ho + ho) * Wo + wo) * y_pitch + y_c0 + c] = arg >= 0 ? x[base + (long long)arg * C] : from_f<T>(0.f);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ xref, const T* __restrict__ dy, int dy_pitch,
+                                                          int dy_c0, T* __restrict__ dx, int n, int H, int W, int C, int Ho,
+                                                          int Wo, int k, int s, int p, int act, float slope) {
+    const long long total = (long long)n * H * W * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long t = i / C;
+        const int w = (int)(t % W); t /= W;
+        const int h = (int)(t % H);
+        const long long b = t / H;
+        const long long base = b * H * W * C + c;
+        // windows (ho, wo) that contain (h, w): ho*s - p <= h <= ho*s - p + k - 1
+        int ho_lo = (h + p - k + 1 + s - 1) / s, ho_hi = (h + p) / s;
+        int wo_lo = (w + p - k + 1 + s - 1) / s, wo_hi = (w + p) / s;
+        if (h + p - k + 1 < 0) ho_lo = 0;
+        if (w + p - k + 1 < 0) wo_lo = 0;
+        ho_hi = min(ho_hi, Ho - 1); wo_hi = min(wo_hi, Wo - 1);
+        float acc = 0.f;
+        for (int ho = ho_lo; ho <= ho_hi; ++ho)
+            for (int wo = wo_lo; wo <= wo_hi; ++wo)
+                if (window_argmax(xref + base, H, W, C, ho, wo, k, s, p) == h * W + w)
+                    acc += to_f(dy[((b * Ho + ho) * Wo + wo) * dy_pitch + dy_c0 + c]);
+        dx[i] = from_f<T>(acc * act_bwd(to_f(xref[i]), act, slope));
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) avgpool_kernel(const T* __restrict__ x, T* __restrict__ y, int y_pitch, int y_c0, int n,
+                                                      int H, int W, int C, int k) {
+    const int Ho = H / k, Wo = W / k;
+    const long long total = (long long)n * Ho * Wo * C;
+    const float inv = 1.f / (float)(k * k);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long t = i / C;
+        const int wo = (int)(t % Wo); t /= Wo;
+        const int ho = (int)(t % Ho);
+        const long long b = t / Ho;
+        float acc = 0.f;
+        for (int dh = 0; dh < k; ++dh)
+            for (int dw = 0; dw < k; ++dw)
+                acc += to_f(x[((b * H + ho * k + dh) * W + wo * k + dw) * C + c]);
+        y[((b * Ho + ho) * Wo + wo) * y_pitch + y_c0 + c] = from_f<T>(acc * inv);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) avgpool_bwd_kernel(const T* __restrict__ dy, int dy_pitch, int dy_c0, T* __restrict__ dx,
+                                                          int n, int H, int W, int C, int k, const T* __restrict__ href, int act,
+                                                          float slope) {
+    const int Ho = H / k, Wo = W / k;
+    const long long total = (long long)n * H * W * C;
+    const float inv = 1.f / (float)(k * k);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long t = i / C;
+        const int w = (int)(t % W); t /= W;
+        const int h = (int)(t % H);
+        const long long b = t / H;
+        float v = to_f(dy[((b * Ho + h / k) * Wo + w / k) * dy_pitch + dy_c0 + c]) * inv;
+        if (href) v *= act_bwd(to_f(href[i]), act, slope);
+        dx[i] = from_f<T>(v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// crowd labeled loss, crowd/srgan.py:247-254.  One CTA per sample.
+// ------------------------------------------------------------------------------------------------------------
+struct MapPtrs { const void* p[4]; };
+
+template <typename T>
+__global__ void __launch_bounds__(1024) crowd_loss_kernel(const float* __restrict__ pred, const float* __restrict__ density,
+                                                          MapPtrs maps, int nmaps, const float* __restrict__ map_label,
+                                                          long long HW, int order, float scale, float map_mult,
+                                                          float* __restrict__ loss, float* __restrict__ dpred,
+                                                          float* __restrict__ dm) {
+    __shared__ float red[32];
+    const int b = blockIdx.x;
+    float cnt = 0.f, m = 0.f;
+    for (long long i = threadIdx.x; i < HW; i += blockDim.x) {
+        cnt += density[b * HW + i];
+        const float lab = map_label[b * HW + i];
+        float a = 0.f;
+        for (int j = 0; j < nmaps; ++j) a += fabsf(to_f(static_cast<const T*>(maps.p[j])[b * HW + i]) - lab);
+        m += a;
+    }
+    cnt = block_sum(cnt, red);
+    m = block_sum(m, red) / (float)nmaps;
+    if (threadIdx.x == 0) {
+        const float d = pred[b] - cnt, ad = fabsf(d), sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+        float pw, dpw, mp, dmp;
+        if (order == 2) { pw = ad * ad; dpw = 2.f * ad; mp = m * m; dmp = 2.f * m; }
+        else if (order == 1) { pw = ad; dpw = 1.f; mp = m; dmp = 1.f; }
+        else { pw = powf(ad, (float)order); dpw = order * powf(ad, (float)(order - 1)); mp = powf(m, (float)order); dmp = order * powf(m, (float)(order - 1)); }
+        atomicAdd(loss, scale * (pw + map_mult * mp));
+        dpred[b] = scale * dpw * sg;
+        dm[b] = scale * map_mult * dmp;
+    }
+}
+
+// delta[b,i] += dm[b]/nmaps * sign(map - label) * act'(map)
+template <typename T>
+__global__ void __launch_bounds__(256) crowd_map_grad_kernel(const T* __restrict__ mp, const float* __restrict__ map_label,
+                                                             const float* __restrict__ dm, T* __restrict__ delta, int B,
+                                                             long long HW, float inv_nmaps, int act, float slope) {
+    const long long total = (long long)B * HW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / HW);
+        const float v = to_f(mp[i]), d = v - map_label[i];
+        const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+        delta[i] = from_f<T>(to_f(delta[i]) + dm[b] * inv_nmaps * sg * act_bwd(v, act, slope));
+    }
+}
+
+inline bool vec_ok(int C, int p0, int o0, int p1 = 0, int o1 = 0) { return ((C | p0 | o0 | p1 | o1) & 3) == 0; }
+
+}  // namespace
+
+#define DISPATCH_T(dtype, ...)                                                          \
+    do {                                                                                \
+        if (dtype == SRGAN_F32) { typedef float T; __VA_ARGS__; }                       \
+        else if (dtype == SRGAN_BF16) { typedef bf16 T; __VA_ARGS__; }                  \
+        else { srgan_set_error("unknown dtype %d", dtype); return SRGAN_ERR_ARG; }      \
+    } while (0)
+
+extern "C" {
+
+int srgan_affine(const void* x, int x_pitch, int x_c0, void* y, long long rows, int C, const float* gamma, const float* beta,
+                 const float* mean, const float* var, float eps, const void* href, int mode, int act, float slope, int dtype,
+                 void* stream) {
+    SRGAN_REQUIRE(x && y && gamma && var && rows >= 0 && C > 0 && x_c0 >= 0 && x_c0 + C <= x_pitch, "srgan_affine: bad arguments");
+    SRGAN_REQUIRE(mode == 0 ? (beta && mean) : (mode == 1 && href), "srgan_affine: mode 0 needs beta/mean, mode 1 needs href");
+    if (rows == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = vec_ok(C, x_pitch, x_c0);
+    DISPATCH_T(dtype,
+               if (vec) affine_kernel<T, true><<<ew_grid(rows * C / 4), 256, 0, st>>>((const T*)x, x_pitch, x_c0, (T*)y, rows, C, gamma, beta, mean, var, eps, (const T*)href, mode, act, slope);
+               else affine_kernel<T, false><<<ew_grid(rows * C), 256, 0, st>>>((const T*)x, x_pitch, x_c0, (T*)y, rows, C, gamma, beta, mean, var, eps, (const T*)href, mode, act, slope));
+    SRGAN_CHECK_LAUNCH("affine_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_affine_bwd(const void* dy, void* dx, int dx_pitch, int dx_c0, long long rows, int C, const float* gamma, const float* var,
+                     float eps, int accumulate, int dtype, void* stream) {
+    SRGAN_REQUIRE(dy && dx && gamma && var && rows >= 0 && C > 0 && dx_c0 >= 0 && dx_c0 + C <= dx_pitch, "srgan_affine_bwd: bad arguments");
+    if (rows == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = vec_ok(C, dx_pitch, dx_c0);
+    DISPATCH_T(dtype,
+               if (vec) affine_bwd_kernel<T, true><<<ew_grid(rows * C / 4), 256, 0, st>>>((const T*)dy, (T*)dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, accumulate);
+               else affine_bwd_kernel<T, false><<<ew_grid(rows * C), 256, 0, st>>>((const T*)dy, (T*)dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, accumulate));
+    SRGAN_CHECK_LAUNCH("affine_bwd_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_affine_grad(const void* dy, const void* x, int x_pitch, int x_c0, long long rows, int C, const float* mean, const float* var,
+                      float eps, float* dgamma, float* dbeta, int subtract_mean, int dtype, void* stream) {
+    SRGAN_REQUIRE(dy && x && var && dgamma && rows >= 0 && C > 0 && x_c0 >= 0 && x_c0 + C <= x_pitch && (!subtract_mean || mean),
+                  "srgan_affine_grad: bad arguments");
+    if (rows == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = vec_ok(C, x_pitch, x_c0);
+    const int V = vec ? 4 : 1;
+    const int gx = (C + 32 * V - 1) / (32 * V);
+    long long want = (4LL * kNumSMs + gx - 1) / gx;                 // ~4 CTAs per SM in total
+    long long rpb = (rows + want - 1) / want;
+    if (rpb < 64) rpb = 64;
+    const long long gy = (rows + rpb - 1) / rpb;
+    dim3 grid(gx, (unsigned)gy);
+    DISPATCH_T(dtype,
+               if (vec) affine_grad_kernel<T, true><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, x_pitch, x_c0, rows, C, mean, var, eps, dgamma, dbeta, subtract_mean, rpb);
+               else affine_grad_kernel<T, false><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, x_pitch, x_c0, rows, C, mean, var, eps, dgamma, dbeta, subtract_mean, rpb));
+    SRGAN_CHECK_LAUNCH("affine_grad_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_copy2d(const void* src, int src_pitch, int src_c0, void* dst, int dst_pitch, int dst_c0, long long rows, int C,
+                 int accumulate, int dtype, void* stream) {
+    SRGAN_REQUIRE(src && dst && rows >= 0 && C > 0 && src_c0 >= 0 && dst_c0 >= 0 && src_c0 + C <= src_pitch && dst_c0 + C <= dst_pitch,
+                  "srgan_copy2d: bad arguments");
+    if (rows == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = vec_ok(C, src_pitch, src_c0, dst_pitch, dst_c0);
+    DISPATCH_T(dtype,
+               if (vec) copy2d_kernel<T, true><<<ew_grid(rows * C / 4), 256, 0, st>>>((const T*)src, src_pitch, src_c0, (T*)dst, dst_pitch, dst_c0, rows, C, accumulate);
+               else copy2d_kernel<T, false><<<ew_grid(rows * C), 256, 0, st>>>((const T*)src, src_pitch, src_c0, (T*)dst, dst_pitch, dst_c0, rows, C, accumulate));
+    SRGAN_CHECK_LAUNCH("copy2d_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_maxpool(const void* x, const void* xref, void* y, int y_pitch, int y_c0, int n, int H, int W, int C, int k, int stride,
+                  int pad, int dtype, void* stream) {
+    SRGAN_REQUIRE(x && y && n >= 0 && H > 0 && W > 0 && C > 0 && k > 0 && stride > 0 && pad >= 0 && 2 * pad <= k && y_c0 >= 0 &&
+                      y_c0 + C <= y_pitch, "srgan_maxpool: bad arguments");
+    if (n == 0) return SRGAN_OK;
+    const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_T(dtype, maxpool_kernel<T><<<ew_grid((long long)n * Ho * Wo * C), 256, 0, st>>>((const T*)x, (const T*)(xref ? xref : x), (T*)y, y_pitch, y_c0, n, H, W, C, Ho, Wo, k, stride, pad));
+    SRGAN_CHECK_LAUNCH("maxpool_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_maxpool_bwd(const void* xref, const void* dy, int dy_pitch, int dy_c0, void* dx, int n, int H, int W, int C, int k,
+                      int stride, int pad, int act, float slope, int dtype, void* stream) {
+    SRGAN_REQUIRE(xref && dy && dx && n >= 0 && H > 0 && W > 0 && C > 0 && k > 0 && stride > 0 && pad >= 0 && 2 * pad <= k && dy_c0 >= 0 &&
+                      dy_c0 + C <= dy_pitch, "srgan_maxpool_bwd: bad arguments");
+    if (n == 0) return SRGAN_OK;
+    const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_T(dtype, maxpool_bwd_kernel<T><<<ew_grid((long long)n * H * W * C), 256, 0, st>>>((const T*)xref, (const T*)dy, dy_pitch, dy_c0, (T*)dx, n, H, W, C, Ho, Wo, k, stride, pad, act, slope));
+    SRGAN_CHECK_LAUNCH("maxpool_bwd_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_avgpool(const void* x, void* y, int y_pitch, int y_c0, int n, int H, int W, int C, int k, int dtype, void* stream) {
+    SRGAN_REQUIRE(x && y && n >= 0 && H > 0 && W > 0 && C > 0 && k > 0 && H % k == 0 && W % k == 0 && y_c0 >= 0 && y_c0 + C <= y_pitch,
+                  "srgan_avgpool: bad arguments (the window must tile the input)");
+    if (n == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_T(dtype, avgpool_kernel<T><<<ew_grid((long long)n * (H / k) * (W / k) * C), 256, 0, st>>>((const T*)x, (T*)y, y_pitch, y_c0, n, H, W, C, k));
+    SRGAN_CHECK_LAUNCH("avgpool_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_avgpool_bwd(const void* dy, int dy_pitch, int dy_c0, void* dx, int n, int H, int W, int C, int k, const void* href, int act,
+                      float slope, int dtype, void* stream) {
+    SRGAN_REQUIRE(dy && dx && n >= 0 && H > 0 && W > 0 && C > 0 && k > 0 && H % k == 0 && W % k == 0 && dy_c0 >= 0 && dy_c0 + C <= dy_pitch,
+                  "srgan_avgpool_bwd: bad arguments");
+    if (n == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_T(dtype, avgpool_bwd_kernel<T><<<ew_grid((long long)n * H * W * C), 256, 0, st>>>((const T*)dy, dy_pitch, dy_c0, (T*)dx, n, H, W, C, k, (const T*)(act == SRGAN_ACT_NONE ? nullptr : href), act, slope));
+    SRGAN_CHECK_LAUNCH("avgpool_bwd_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_crowd_loss(const float* pred, const float* density, const void* const* maps, int nmaps, const float* map_label, int B,
+                     long long HW, int order, float scale, float map_mult, float* loss, float* dpred, float* dm, int dtype,
+                     void* stream) {
+    SRGAN_REQUIRE(pred && density && maps && map_label && loss && dpred && dm && B >= 0 && HW > 0 && nmaps >= 1 && nmaps <= 4 && order >= 1,
+                  "srgan_crowd_loss: bad arguments");
+    if (B == 0) return SRGAN_OK;
+    MapPtrs mp;
+    for (int j = 0; j < 4; ++j) mp.p[j] = j < nmaps ? maps[j] : nullptr;
+    for (int j = 0; j < nmaps; ++j) SRGAN_REQUIRE(mp.p[j], "srgan_crowd_loss: null map pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_T(dtype, crowd_loss_kernel<T><<<B, 1024, 0, st>>>(pred, density, mp, nmaps, map_label, HW, order, scale, map_mult, loss, dpred, dm));
+    SRGAN_CHECK_LAUNCH("crowd_loss_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_crowd_map_grad(const void* map, const float* map_label, const float* dm, void* delta, int B, long long HW, int nmaps, int act,
+                         float slope, int dtype, void* stream) {
+    SRGAN_REQUIRE(map && map_label && dm && delta && B >= 0 && HW > 0 && nmaps >= 1, "srgan_crowd_map_grad: bad arguments");
+    if (B == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_T(dtype, crowd_map_grad_kernel<T><<<ew_grid((long long)B * HW), 256, 0, st>>>((const T*)map, map_label, dm, (T*)delta, B, HW, 1.f / (float)nmaps, act, slope));
+    SRGAN_CHECK_LAUNCH("crowd_map_grad_kernel");
+    return SRGAN_OK;
+}
+
+}  // extern "C"

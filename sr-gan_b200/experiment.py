@@ -104,6 +104,7 @@ class StepConfig:
         self.labeled_loss_order = int(settings.labeled_loss_order)
         self.generator_training_step_period = int(settings.generator_training_step_period)
         self.mean_offset = float(getattr(settings, 'mean_offset', 0))
+        self.map_multiplier = float(getattr(settings, 'map_multiplier', 1e-6))
         self.batch_size = int(settings.batch_size)
         for k in ('matching_distance_function', 'contrasting_distance_function'):
             fn = getattr(settings, k)
@@ -186,6 +187,55 @@ class DcganGenerator(_Container):
         self.input_size = z_dim
 
 
+class _Named(nn.Module):
+    """A bag of named sub-modules (only their parameters / buffers matter here)."""
+
+    def __init__(self, **mods):
+        super().__init__()
+        for k, m in mods.items():
+            self.add_module(k, m)
+
+
+class KnnDenseNetCat(_Container):
+    """crowd/models.py:1049-1166: parameter container with the reference module's state_dict keys and order (dense_blocks,
+    transition_layers, conv_layer1, norm5, map_module1..3, final_count_feature_layer, count_layer).  BatchNorm layers are
+    real nn.BatchNorm2d modules so the running statistics travel in the state_dict; the step treats them as the frozen
+    per-channel affine srgan.py:538-542 makes of them.  No weights are downloaded (the reference loads DenseNet-201 from
+    the model zoo, crowd/models.py:1103-1127): load a state_dict to start from pretrained weights."""
+
+    def __init__(self, growth_rate=32, block_config=(6, 12, 48, 32), num_init_features=64, bn_size=4, label_patch_size=224,
+                 image_size=224):
+        super().__init__()
+        g, bs = growth_rate, bn_size
+        self.dense_blocks = nn.ModuleList()
+        self.transition_layers = nn.ModuleList()
+        self.conv_layer1 = _Named(conv0=nn.Conv2d(3, num_init_features, 7, 2, 3, bias=False),
+                                  norm0=nn.BatchNorm2d(num_init_features))
+        c, taps = num_init_features, []
+        for bi, n in enumerate(block_config, 1):
+            block = nn.Module()
+            for li in range(1, n + 1):
+                block.add_module(f'denselayer{li}', _Named(norm1=nn.BatchNorm2d(c), conv1=nn.Conv2d(c, bs * g, 1, bias=False),
+                                                           norm2=nn.BatchNorm2d(bs * g),
+                                                           conv2=nn.Conv2d(bs * g, g, 3, padding=1, bias=False)))
+                c += g
+            self.dense_blocks.add_module(f'denseblock{bi}', block)
+            if bi != len(block_config):
+                self.transition_layers.add_module(f'transition{bi}', _Named(norm=nn.BatchNorm2d(c),
+                                                                             conv=nn.Conv2d(c, c // 2, 1, bias=False)))
+                c //= 2
+                taps.append(c)
+        self.norm5 = nn.BatchNorm2d(c)
+        L = label_patch_size
+        for i, ci in enumerate(taps[:3], 1):
+            k = L // (image_size // (8 * 2 ** (i - 1)))
+            self.add_module(f'map_module{i}', _Named(
+                map_transposed_conv_layer=nn.ConvTranspose2d(ci, 1, k, k), conv1=nn.Conv2d(1, 8, 2, 2), conv2=nn.Conv2d(8, 16, 2, 2),
+                conv3=nn.Conv2d(16, 32, 2, 2), linear1=nn.Conv2d(32, 20, L // 8), count_layer=nn.Conv2d(20, 1, 1)))
+        self.final_count_feature_layer = nn.Conv2d(c, 20, 1)
+        self.count_layer = nn.Conv2d(20, 1, 1)
+
+
 # ------------------------------------------------------------------------------------------------ the runner
 class StepRunner:
     """Owns the Engine for one (D, G, DNN) triple and the bookkeeping that keeps torch-side objects coherent."""
@@ -211,7 +261,9 @@ class StepRunner:
             raise ValueError('DG-GAN needs the two-output discriminator (coefficient/models.py:53-72)')
 
         def pd(m):
-            return {k: p for k, p in m.named_parameters()}
+            d = {k: p for k, p in m.named_parameters()}
+            d.update({k: b for k, b in m.named_buffers() if b.is_floating_point()})      # BatchNorm running statistics
+            return d
         self.engine = Engine(CudaOps(dev), d_net, g_net, pd(D), pd(G), pd(DNN),
                              act_dtype=torch.float32 if precision == 'fp32' else torch.bfloat16, device=dev, comm=comm)
         self.generator = torch.Generator(device=dev)
@@ -337,6 +389,14 @@ class StepRunner:
             self._statics[name] = t
         return t
 
+    def _static_labels(self, name, labels):
+        """labels: a tensor, or the crowd (density, map) tuple built at srgan.py:112-113."""
+        if isinstance(labels, (tuple, list)):
+            ys = tuple(self._static(f'{name}{i}', t) for i, t in enumerate(labels))
+            return ys, list(zip(ys, labels))
+        ys = self._static(name, labels)
+        return ys, [(ys, labels)]
+
     def dnn_step(self, examples, labels, lr=None, weight_decay=None):
         cfg = self.config()
         lr = cfg.learning_rate if lr is None else lr
@@ -347,9 +407,10 @@ class StepRunner:
         if not self.use_cuda_graph:
             self.engine.dnn_step(examples, labels, cfg, lr, wd)
             return
-        xs, ys = self._static('dnn_x', examples), self._static('dnn_y', labels)
-        key = ('dnn', tuple(examples.shape), lr, wd, cfg.labeled_loss_multiplier, cfg.labeled_loss_order)
-        self._graphed(key, [(xs, examples), (ys, labels)], lambda: self.engine.dnn_step(xs, ys, cfg, lr, wd))
+        xs = self._static('dnn_x', examples)
+        ys, ypairs = self._static_labels('dnn_y', labels)
+        key = ('dnn', tuple(examples.shape), lr, wd, cfg.labeled_loss_multiplier, cfg.labeled_loss_order, cfg.map_multiplier)
+        self._graphed(key, [(xs, examples)] + ypairs, lambda: self.engine.dnn_step(xs, ys, cfg, lr, wd))
 
     def gan_step(self, labeled_examples, labels, unlabeled_examples, step=0, noise=None):
         cfg = self.config()
@@ -363,12 +424,13 @@ class StepRunner:
             self.engine.gan_step(labeled_examples, labels, unlabeled_examples, z, alpha, z2, cfg, train_generator=train_g)
             return
         alpha = alpha.reshape(-1)
-        st = [(self._static('x', labeled_examples), labeled_examples), (self._static('y', labels), labels),
+        ys, ypairs = self._static_labels('y', labels)
+        st = [(self._static('x', labeled_examples), labeled_examples),
               (self._static('u', unlabeled_examples), unlabeled_examples), (self._static('z', z), z),
               (self._static('alpha', alpha), alpha), (self._static('z2', z2), z2)]
         key = ('gan', tuple(labeled_examples.shape), train_g, repr(sorted(vars(cfg).items())))
-        xs, ys, us, zs, als, z2s = (d for d, _ in st)
-        self._graphed(key, st, lambda: self.engine.gan_step(xs, ys, us, zs, als, z2s, cfg, train_generator=train_g))
+        xs, us, zs, als, z2s = (d for d, _ in st)
+        self._graphed(key, st + ypairs, lambda: self.engine.gan_step(xs, ys, us, zs, als, z2s, cfg, train_generator=train_g))
 
     def scalars(self):
         """One device->host read of the step's scalars (the .item() calls of srgan.py:268-270, 306-319)."""
@@ -460,8 +522,6 @@ class B200StepMixin:
         """srgan.py:259-271."""
         r = self._b200_runner()
         self.dnn_summary_writer.step = step
-        if isinstance(labels, (tuple, list)):
-            raise NotImplementedError('crowd (density, map) labels: KnnDenseNetCat has no B200 path yet')
         group = self.dnn_optimizer.param_groups[0]                  # adjust_learning_rate (srgan.py:432-436) writes here
         r.dnn_step(examples, labels, lr=group['lr'], weight_decay=group['weight_decay'])
         if self.dnn_summary_writer.is_summary_step():
@@ -471,8 +531,6 @@ class B200StepMixin:
         """srgan.py:273-320."""
         r = self._b200_runner()
         self.gan_summary_writer.step = step
-        if isinstance(labels, (tuple, list)):
-            raise NotImplementedError('crowd (density, map) labels: KnnDenseNetCat has no B200 path yet')
         r.gan_step(labeled_examples, labels, unlabeled_examples, step, noise=getattr(self, '_b200_noise', None))
         if self.gan_summary_writer.is_summary_step():
             s = r.scalars()
@@ -497,7 +555,7 @@ class B200StepMixin:
 
 class Experiment:
     """Stand-alone mirror of the reference Experiment's step API (srgan.py:24-50, 259-320) for the supported model
-    families; `application` in {'coefficient', 'age', 'driving'}, `method` in {'srgan', 'dggan'}."""
+    families; `application` in {'coefficient', 'age', 'driving', 'crowd'}, `method` in {'srgan', 'dggan'}."""
 
     def __init__(self, settings: Settings, application='age', method='srgan', device='cuda:0', comm=None, **model_kwargs):
         self.settings = settings
@@ -512,6 +570,15 @@ class Experiment:
             dk = {k: v for k, v in model_kwargs.items() if k in ('image_size', 'conv_dim')}
             self.D = DcganDiscriminator(**dk)
             self.DNN = DcganDiscriminator(**dk)
+        elif application == 'crowd':                                        # crowd/srgan.py:92-96 model_setup
+            if method != 'srgan':
+                raise NotImplementedError('crowd DG-GAN (crowd/dggan.py) has no B200 path')
+            dk = {k: v for k, v in model_kwargs.items() if k in ('growth_rate', 'block_config', 'num_init_features', 'bn_size',
+                                                                 'label_patch_size', 'image_size')}
+            gk = {k: v for k, v in model_kwargs.items() if k in ('z_dim', 'conv_dim')}
+            self.G = DcganGenerator(image_size=dk.get('image_size', 224), **gk)
+            self.D = KnnDenseNetCat(**dk)
+            self.DNN = KnnDenseNetCat(**dk)
         else:
             raise NotImplementedError(f'application {application!r}: no B200 path yet')
         for m in (self.D, self.G, self.DNN):

@@ -27,7 +27,8 @@ _EXPORTS = (
     'srgan_nchw_to_nhwc', 'srgan_nhwc_to_nchw', 'srgan_interpolate', 'srgan_labeled_loss', 'srgan_bce_logits',
     'srgan_distance', 'srgan_feature_norm_seed', 'srgan_gradnorm_penalty', 'srgan_gp_feature_seed', 'srgan_adam',
     'srgan_repack', 'srgan_im2col', 'srgan_col2im', 'srgan_adam_prepare', 'srgan_coefficient_step',
-    'srgan_coefficient_step_workspace_bytes',
+    'srgan_coefficient_step_workspace_bytes', 'srgan_affine', 'srgan_affine_bwd', 'srgan_affine_grad', 'srgan_copy2d',
+    'srgan_maxpool', 'srgan_maxpool_bwd', 'srgan_avgpool', 'srgan_avgpool_bwd', 'srgan_crowd_loss', 'srgan_crowd_map_grad',
 )
 
 _lib = None
@@ -79,6 +80,16 @@ def load_library(path: str = LIB_PATH):
     pp = ctypes.POINTER(vp)
     lib.srgan_coefficient_step.argtypes = ([pp, pp, pp, vp, vp, vp] + [vp] * 6 + [c_int, c_f, c_int, c_int] + [c_f] * 5 +
                                            [c_int, c_int] + [c_f] * 6 + [c_int, c_int, vp, ctypes.c_size_t, vp, vp])
+    lib.srgan_affine.argtypes = [vp, c_int, c_int, vp, c_ll, c_int, vp, vp, vp, vp, c_f, vp, c_int, c_int, c_f, c_int, vp]
+    lib.srgan_affine_bwd.argtypes = [vp, vp, c_int, c_int, c_ll, c_int, vp, vp, c_f, c_int, c_int, vp]
+    lib.srgan_affine_grad.argtypes = [vp, vp, c_int, c_int, c_ll, c_int, vp, vp, c_f, vp, vp, c_int, c_int, vp]
+    lib.srgan_copy2d.argtypes = [vp, c_int, c_int, vp, c_int, c_int, c_ll, c_int, c_int, c_int, vp]
+    lib.srgan_maxpool.argtypes = [vp, vp, vp, c_int, c_int] + [c_int] * 7 + [c_int, vp]
+    lib.srgan_maxpool_bwd.argtypes = [vp, vp, c_int, c_int, vp] + [c_int] * 7 + [c_int, c_f, c_int, vp]
+    lib.srgan_avgpool.argtypes = [vp, vp, c_int, c_int] + [c_int] * 5 + [c_int, vp]
+    lib.srgan_avgpool_bwd.argtypes = [vp, c_int, c_int, vp] + [c_int] * 5 + [vp, c_int, c_f, c_int, vp]
+    lib.srgan_crowd_loss.argtypes = [vp, vp, pp, c_int, vp, c_int, c_ll, c_int, c_f, c_f, vp, vp, vp, c_int, vp]
+    lib.srgan_crowd_map_grad.argtypes = [vp, vp, vp, vp, c_int, c_ll, c_int, c_int, c_f, c_int, vp]
     for name in _EXPORTS[5:]:
         getattr(lib, name).restype = c_int
     lib.srgan_coefficient_step_workspace_bytes.restype = ctypes.c_size_t
@@ -279,3 +290,58 @@ class CudaOps:
             if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
                 raise TypeError('pointer_table: fp32 contiguous CUDA tensors only')
         return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+    # -------------------------------------------------------------- graph-net ops (crowd KnnDenseNetCat)
+    def _pf(self, t):
+        return self._p(t.detach() if t is not None else None, torch.float32)
+
+    def affine(self, x, x_pitch, x_c0, y, rows, C, gamma, beta, mean, var, eps, href, mode, act, slope):
+        self._ck(self.lib.srgan_affine(self._p(x), x_pitch, x_c0, self._p(y, x.dtype), rows, C, self._pf(gamma), self._pf(beta),
+                                       self._pf(mean), self._pf(var), eps, self._p(href, x.dtype) if href is not None else None,
+                                       mode, act, slope, _dt(x.dtype), self._stream()), 'srgan_affine')
+
+    def affine_bwd(self, dy, dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, accumulate):
+        self._ck(self.lib.srgan_affine_bwd(self._p(dy), self._p(dx, dy.dtype), dx_pitch, dx_c0, rows, C, self._pf(gamma),
+                                           self._pf(var), eps, int(bool(accumulate)), _dt(dy.dtype), self._stream()),
+                 'srgan_affine_bwd')
+
+    def affine_grad(self, dy, x, x_pitch, x_c0, rows, C, mean, var, eps, dgamma, dbeta, subtract_mean):
+        self._ck(self.lib.srgan_affine_grad(self._p(dy), self._p(x, dy.dtype), x_pitch, x_c0, rows, C, self._pf(mean),
+                                            self._pf(var), eps, self._pf(dgamma), self._pf(dbeta), int(bool(subtract_mean)),
+                                            _dt(dy.dtype), self._stream()), 'srgan_affine_grad')
+
+    def copy2d(self, src, src_pitch, src_c0, dst, dst_pitch, dst_c0, rows, C, accumulate):
+        self._ck(self.lib.srgan_copy2d(self._p(src), src_pitch, src_c0, self._p(dst, src.dtype), dst_pitch, dst_c0, rows, C,
+                                       int(bool(accumulate)), _dt(src.dtype), self._stream()), 'srgan_copy2d')
+
+    def maxpool(self, x, xref, y, y_pitch, y_c0, n, H, W, C, k, s, p):
+        self._ck(self.lib.srgan_maxpool(self._p(x), self._p(xref, x.dtype) if xref is not None else None, self._p(y, x.dtype),
+                                        y_pitch, y_c0, n, H, W, C, k, s, p, _dt(x.dtype), self._stream()), 'srgan_maxpool')
+
+    def maxpool_bwd(self, xref, dy, dy_pitch, dy_c0, dx, n, H, W, C, k, s, p, act, slope):
+        self._ck(self.lib.srgan_maxpool_bwd(self._p(xref), self._p(dy, xref.dtype), dy_pitch, dy_c0, self._p(dx, xref.dtype), n,
+                                            H, W, C, k, s, p, act, slope, _dt(xref.dtype), self._stream()), 'srgan_maxpool_bwd')
+
+    def avgpool(self, x, y, y_pitch, y_c0, n, H, W, C, k):
+        self._ck(self.lib.srgan_avgpool(self._p(x), self._p(y, x.dtype), y_pitch, y_c0, n, H, W, C, k, _dt(x.dtype),
+                                        self._stream()), 'srgan_avgpool')
+
+    def avgpool_bwd(self, dy, dy_pitch, dy_c0, dx, n, H, W, C, k, href, act, slope):
+        self._ck(self.lib.srgan_avgpool_bwd(self._p(dy), dy_pitch, dy_c0, self._p(dx, dy.dtype), n, H, W, C, k,
+                                            self._p(href, dy.dtype) if href is not None else None, act, slope, _dt(dy.dtype),
+                                            self._stream()), 'srgan_avgpool_bwd')
+
+    def crowd_loss(self, pred, density, maps, map_label, B, HW, order, scale, map_mult, loss_out, dpred, dm):
+        f32 = torch.float32
+        density, map_label = density.detach(), map_label.detach()
+        if density.dtype != f32 or map_label.dtype != f32 or not density.is_contiguous() or not map_label.is_contiguous():
+            raise TypeError('crowd labels (density, map) must be contiguous fp32 tensors')
+        tbl = (ctypes.c_void_p * len(maps))(*[self._p(m, maps[0].dtype) for m in maps])
+        self._ck(self.lib.srgan_crowd_loss(self._p(pred, f32), self._p(density), tbl, len(maps), self._p(map_label), B, HW,
+                                           int(order), scale, map_mult, self._p(loss_out, f32), self._p(dpred, f32),
+                                           self._p(dm, f32), _dt(maps[0].dtype), self._stream()), 'srgan_crowd_loss')
+
+    def crowd_map_grad(self, mp, map_label, dm, delta, B, HW, nmaps, act, slope):
+        self._ck(self.lib.srgan_crowd_map_grad(self._p(mp), self._p(map_label.detach(), torch.float32), self._p(dm, torch.float32),
+                                               self._p(delta, mp.dtype), B, HW, nmaps, act, slope, _dt(mp.dtype),
+                                               self._stream()), 'srgan_crowd_map_grad')

@@ -9,7 +9,7 @@ def settings_from_cfg(cfg: O.StepConfig, precision='fp32'):
     s = srgan_b200.Settings()
     for k in ('batch_size', 'learning_rate', 'weight_decay', 'labeled_loss_multiplier', 'matching_loss_multiplier',
               'contrasting_loss_multiplier', 'srgan_loss_multiplier', 'dggan_loss_multiplier',
-              'gradient_penalty_multiplier', 'labeled_loss_order', 'generator_training_step_period'):
+              'gradient_penalty_multiplier', 'labeled_loss_order', 'generator_training_step_period', 'map_multiplier'):
         setattr(s, k, getattr(cfg, k))
     s.matching_distance_function = getattr(srgan_b200, cfg.matching_distance_function)
     s.contrasting_distance_function = getattr(srgan_b200, cfg.contrasting_distance_function)
@@ -21,6 +21,13 @@ def modules_from_state(st: O.OracleState, **dcgan_kwargs):
     if st.d_spec.family == 'coefficient':
         n_out = 2 if st.d_spec.dggan else 1
         D, DNN, G = srgan_b200.CoefficientMLP(10, n_out), srgan_b200.CoefficientMLP(10, n_out), srgan_b200.CoefficientGenerator(10)
+    elif st.d_spec.family == 'crowd':
+        sp = st.d_spec
+        z_dim, c8, k, _ = st.G['fc.0.weight'].shape
+        kw = dict(growth_rate=sp.growth_rate, block_config=sp.block_config, num_init_features=sp.num_init_features,
+                  bn_size=sp.bn_size, label_patch_size=sp.label_patch_size, image_size=k * 16)
+        D, DNN = srgan_b200.KnnDenseNetCat(**kw), srgan_b200.KnnDenseNetCat(**kw)
+        G = srgan_b200.DcganGenerator(z_dim, k * 16, c8 // 8)
     else:
         z_dim, c8, k, _ = st.G['fc.0.weight'].shape
         D = srgan_b200.DcganDiscriminator(k * 16, c8 // 8)
@@ -38,7 +45,7 @@ def runner_from_state(st: O.OracleState, cfg: O.StepConfig, precision='fp32', co
 
 
 def to_cuda(*ts):
-    return tuple(t.cuda() for t in ts)
+    return tuple(tuple(e.cuda() for e in t) if isinstance(t, (tuple, list)) else t.cuda() for t in ts)
 
 
 def rel(a, b):

@@ -141,3 +141,23 @@ def test_crowd_graph_schedule_matches_oracle_fp64():
                 assert torch.equal(mine.params[k], v)
             else:
                 assert rel(mine.params[k], v) < 1e-8, (net, k, rel(mine.params[k], v))
+
+
+def test_crowd_container_matches_reference_keys_and_graph():
+    """The product's KnnDenseNetCat parameter container has the reference module's state_dict keys, order and shapes (the
+    oracle's table is pinned against the reference by oracle/make_golden.py's strict load), and describe_module maps
+    it to the same graph nets.knn_densenet_cat builds."""
+    import srgan_b200
+    for kw, image in ((dict(), 224), (dict(block_config=(2, 2, 2, 2), growth_rate=8, num_init_features=16, bn_size=2,
+                                           label_patch_size=64), 64)):
+        spec = O.ModelSpec('crowd', **kw)
+        m = srgan_b200.KnnDenseNetCat(image_size=image, **kw)
+        shapes = O.crowd_param_shapes(spec, image)
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(shapes.keys())
+        assert all(tuple(sd[k].shape) == tuple(shapes[k]) for k in shapes)
+        net = nets.describe_module(m)
+        assert net == nets.knn_densenet_cat(spec.block_config, spec.growth_rate, spec.num_init_features, spec.bn_size,
+                                            image, spec.label_patch_size)
+    full = nets.knn_densenet_cat()
+    assert abs(full.macs_per_sample() - 4.366e9) < 2e6          # SURVEY App. A.4 [probed]

@@ -263,3 +263,160 @@ def test_im2col_col2im(ops, dt, g):
         ops.col2im(col.cuda(), o, n, g, kpad, bias.cuda() if epi == 0 else None, href.cuda() if epi == 1 else None,
                    epi, act, slope)
         close(o, o_ref, tol(dt), f'col2im epi{epi} act{act}')
+
+
+# ---- crowd KnnDenseNetCat: conv shapes of the graph + the graph ops of csrc/graph_ops.cu
+CROWD_GEOMS = [
+    Geom(16, 16, 16, 32, 32, 3, 7, 7, 2, 3),        # stem conv k7 s2 p3
+    Geom(8, 8, 64, 8, 8, 40, 1, 1, 1, 0),           # dense-layer bottleneck 1x1, C not a multiple of 64
+    Geom(8, 8, 32, 8, 8, 128, 3, 3, 1, 1),          # dense-layer 3x3, growth 32
+    Geom(7, 7, 32, 7, 7, 128, 3, 3, 1, 1),          # ... at the 7x7 stage
+    Geom(4, 4, 24, 32, 32, 1, 8, 8, 8, 0),          # MapModule ConvTranspose2d k = stride = 8 (pair: small side 4x4x24)
+    Geom(16, 16, 8, 32, 32, 1, 2, 2, 2, 0),         # MapModule conv1 1 -> 8, k2 s2
+    Geom(4, 4, 32, 8, 8, 16, 2, 2, 2, 0),           # MapModule conv3
+    Geom(1, 1, 20, 4, 4, 32, 4, 4, 1, 0),           # MapModule linear1: full-extent conv
+    Geom(1, 1, 20, 1, 1, 1088, 1, 1, 1, 0),         # final_count_feature_layer
+]
+
+
+@pytest.mark.parametrize('dt', DT)
+@pytest.mark.parametrize('gi', range(len(CROWD_GEOMS)))
+def test_crowd_conv_shapes(ops, dt, gi):
+    g = CROWD_GEOMS[gi]
+    gen = torch.Generator().manual_seed(100 + gi)
+    n = 3
+    ref = TorchOps()
+    L = rnd(gen, n * g.Hl * g.Wl * g.Cb, dt=dt)
+    S = rnd(gen, n * g.Hs * g.Ws * g.Ca, dt=dt)
+    Wd = (rnd(gen, g.Ca * g.R * g.S * g.Cb) * 0.3).to(dt)
+    Wu = Wd.view(g.Ca, g.R, g.S, g.Cb).permute(3, 1, 2, 0).contiguous().view(-1)
+    bias_a, bias_b = rnd(gen, g.Ca), rnd(gen, g.Cb)
+    for epi, act, slope in ((0, 1, 0.01), (0, 0, 0.0), (1, 1, 0.0), (1, 0, 0.0)):
+        href = rnd(gen, S.numel(), dt=dt)
+        out_ref = torch.empty_like(S)
+        ref.conv_down(L, Wd, out_ref, n, g, bias_a if epi == 0 else None, 0, href if epi == 1 else None, epi, act, slope)
+        out = torch.empty_like(S, device='cuda')
+        ops.conv_down(L.cuda(), Wd.cuda(), out, n, g, bias_a.cuda() if epi == 0 else None, 0,
+                      href.cuda() if epi == 1 else None, epi, act, slope)
+        close(out, out_ref, tol(dt), f'down epi{epi} act{act}')
+        href = rnd(gen, L.numel(), dt=dt)
+        out_ref = torch.empty_like(L)
+        ref.conv_up(S, Wu, out_ref, n, g, bias_b if epi == 0 else None, 0, href if epi == 1 else None, epi, act, slope)
+        out = torch.empty_like(L, device='cuda')
+        ops.conv_up(S.cuda(), Wu.cuda(), out, n, g, bias_b.cuda() if epi == 0 else None, 0,
+                    href.cuda() if epi == 1 else None, epi, act, slope)
+        close(out, out_ref, tol(dt), f'up epi{epi} act{act}')
+    dW_ref = rnd(gen, Wd.numel())
+    dW = dW_ref.clone().cuda()
+    ref.conv_wgrad(S, L, dW_ref, n, g)
+    ops.conv_wgrad(S.cuda(), L.cuda(), dW, n, g)
+    close(dW, dW_ref, tol(dt) * 2, 'wgrad')
+
+
+@pytest.mark.parametrize('dt', DT)
+@pytest.mark.parametrize('rows,pitch,c0,C', [(3 * 56 * 56, 256, 0, 96), (1000, 40, 8, 24), (77, 13, 3, 7), (5, 1920, 0, 1920)])
+def test_affine_ops(ops, dt, rows, pitch, c0, C):
+    gen = torch.Generator().manual_seed(rows + C)
+    ref = TorchOps()
+    x = rnd(gen, rows * pitch, dt=dt)
+    gamma, beta, mean = rnd(gen, C) + 1.5, rnd(gen, C) * 0.3, rnd(gen, C) * 0.2
+    var = torch.rand(C, generator=gen) + 0.5
+    href = rnd(gen, rows * C, dt=dt)
+    cu = lambda t: t.cuda()
+    for mode, act, slope in ((0, 1, 0.0), (0, 0, 0.0), (1, 1, 0.0), (1, 1, 0.01)):
+        y_ref = torch.empty(rows * C, dtype=dt)
+        ref.affine(x, pitch, c0, y_ref, rows, C, gamma, beta, mean, var, 1e-5, href, mode, act, slope)
+        y = torch.empty(rows * C, dtype=dt, device='cuda')
+        ops.affine(cu(x), pitch, c0, y, rows, C, cu(gamma), cu(beta), cu(mean), cu(var), 1e-5, cu(href), mode, act, slope)
+        close(y, y_ref, tol(dt), f'affine mode{mode}')
+    dy = rnd(gen, rows * C, dt=dt)
+    for acc in (False, True):
+        dx_ref = rnd(gen, rows * pitch, dt=dt)
+        dx = dx_ref.clone().cuda()
+        ref.affine_bwd(dy, dx_ref, pitch, c0, rows, C, gamma, var, 1e-5, acc)
+        ops.affine_bwd(cu(dy), dx, pitch, c0, rows, C, cu(gamma), cu(var), 1e-5, acc)
+        close(dx, dx_ref, tol(dt), f'affine_bwd acc{acc}')
+    for sub in (True, False):
+        dg_ref, db_ref = rnd(gen, C), rnd(gen, C)
+        dg, db = dg_ref.clone().cuda(), db_ref.clone().cuda()
+        ref.affine_grad(dy, x, pitch, c0, rows, C, mean, var, 1e-5, dg_ref, db_ref if sub else None, sub)
+        ops.affine_grad(cu(dy), cu(x), pitch, c0, rows, C, cu(mean), cu(var), 1e-5, dg, db if sub else None, sub)
+        t = 1e-4 if dt == torch.float32 else 1e-2
+        close(dg, dg_ref, t, 'affine_grad dgamma')
+        close(db, db_ref, t, 'affine_grad dbeta')
+
+
+@pytest.mark.parametrize('dt', DT)
+def test_copy2d_and_pools(ops, dt):
+    gen = torch.Generator().manual_seed(9)
+    ref = TorchOps()
+    cu = lambda t: t.cuda()
+    for rows, sp, s0, dp, d0, C in ((500, 32, 0, 96, 64, 32), (300, 48, 8, 20, 0, 20), (41, 7, 2, 9, 3, 5)):
+        src = rnd(gen, rows * sp, dt=dt)
+        for acc in (False, True):
+            d_ref = rnd(gen, rows * dp, dt=dt)
+            d = d_ref.clone().cuda()
+            ref.copy2d(src, sp, s0, d_ref, dp, d0, rows, C, acc)
+            ops.copy2d(cu(src), sp, s0, d, dp, d0, rows, C, acc)
+            close(d, d_ref, tol(dt), 'copy2d')
+    # max-pool 3/2/1 (stem) incl. ReLU-style ties at zero, odd extent; tangent routing; backward
+    for n, H, W, C, k, s, p in ((2, 16, 16, 8, 3, 2, 1), (3, 9, 11, 5, 3, 2, 1), (2, 8, 8, 4, 2, 2, 0)):
+        x = torch.relu(rnd(gen, n * H * W * C)).to(dt)
+        Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+        pitch, c0 = C + 6, 2
+        y_ref = torch.zeros(n * Ho * Wo * pitch, dtype=dt)
+        y = y_ref.clone().cuda()
+        ref.maxpool(x, None, y_ref, pitch, c0, n, H, W, C, k, s, p)
+        ops.maxpool(cu(x), None, y, pitch, c0, n, H, W, C, k, s, p)
+        close(y, y_ref, 1e-6, 'maxpool')
+        v = rnd(gen, n * H * W * C, dt=dt)
+        ref.maxpool(v, x, y_ref, pitch, c0, n, H, W, C, k, s, p)
+        ops.maxpool(cu(v), cu(x), y, pitch, c0, n, H, W, C, k, s, p)
+        close(y, y_ref, 1e-6, 'maxpool tangent')
+        dy = rnd(gen, n * Ho * Wo * pitch, dt=dt)
+        dx_ref = torch.empty(n * H * W * C, dtype=dt)
+        dx = torch.empty(n * H * W * C, dtype=dt, device='cuda')
+        ref.maxpool_bwd(x, dy, pitch, c0, dx_ref, n, H, W, C, k, s, p, 1, 0.0)
+        ops.maxpool_bwd(cu(x), cu(dy), pitch, c0, dx, n, H, W, C, k, s, p, 1, 0.0)
+        close(dx, dx_ref, tol(dt), 'maxpool_bwd')
+    for n, H, W, C, k in ((3, 8, 8, 12, 2), (2, 7, 7, 40, 7), (1, 4, 4, 3, 2)):
+        x = rnd(gen, n * H * W * C, dt=dt)
+        Ho, Wo = H // k, W // k
+        pitch, c0 = C + 4, 4
+        y_ref = torch.zeros(n * Ho * Wo * pitch, dtype=dt)
+        y = y_ref.clone().cuda()
+        ref.avgpool(x, y_ref, pitch, c0, n, H, W, C, k)
+        ops.avgpool(cu(x), y, pitch, c0, n, H, W, C, k)
+        close(y, y_ref, tol(dt), 'avgpool')
+        dy = rnd(gen, n * Ho * Wo * pitch, dt=dt)
+        for act in (0, 1):
+            dx_ref = torch.empty(n * H * W * C, dtype=dt)
+            dx = torch.empty(n * H * W * C, dtype=dt, device='cuda')
+            ref.avgpool_bwd(dy, pitch, c0, dx_ref, n, H, W, C, k, x, act, 0.0)
+            ops.avgpool_bwd(cu(dy), pitch, c0, dx, n, H, W, C, k, cu(x), act, 0.0)
+            close(dx, dx_ref, tol(dt), 'avgpool_bwd')
+
+
+@pytest.mark.parametrize('dt', DT)
+@pytest.mark.parametrize('order', [1, 2, 3])
+def test_crowd_loss_ops(ops, dt, order):
+    gen = torch.Generator().manual_seed(order)
+    ref = TorchOps()
+    B, HW = 5, 56 * 56
+    pred = rnd(gen, B) * 30
+    density = (torch.rand(B, HW, generator=gen) < 0.01).float()
+    label = 1 / (1 + torch.rand(B, HW, generator=gen) * 50)
+    maps = [(torch.rand(B * HW, generator=gen) * 0.5 - 0.1).to(dt) for _ in range(3)]
+    l_ref, dp_ref, dm_ref = torch.tensor([0.25]), torch.empty(B), torch.empty(B)
+    ref.crowd_loss(pred, density, maps, label, B, HW, order, 0.7, 1e-3, l_ref, dp_ref, dm_ref)
+    l, dp, dm = torch.tensor([0.25]).cuda(), torch.empty(B, device='cuda'), torch.empty(B, device='cuda')
+    ops.crowd_loss(pred.cuda(), density.cuda(), [m.cuda() for m in maps], label.cuda(), B, HW, order, 0.7, 1e-3, l, dp, dm)
+    t = 1e-4 if dt == torch.float32 else 1e-2
+    close(l, l_ref, t, 'crowd loss')
+    close(dp, dp_ref, t, 'dpred')
+    close(dm, dm_ref, t, 'dm')
+    d_ref = rnd(gen, B * HW, dt=dt)
+    d = d_ref.clone().cuda()
+    ref.crowd_map_grad(maps[1], label, dm_ref, d_ref, B, HW, 3, 1, 0.01)
+    ops.crowd_map_grad(maps[1].cuda(), label.cuda(), dm_ref.cuda(), d, B, HW, 3, 1, 0.01)
+    close(d, d_ref, tol(dt), 'crowd_map_grad')

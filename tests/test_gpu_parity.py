@@ -189,3 +189,74 @@ def test_coefficient_persistent_kernel_matches_generic_kernels(method, B):
     pb, fb = rb.predict(xc)
     assert rel(pa, pb) < 1e-4 and rel(fa, fb) < 1e-4
     assert rel(ra.generate(zc), rb.generate(zc)) < 1e-4
+
+
+CROWD_SMALL = dict(block_config=(2, 2, 2, 2), growth_rate=8, num_init_features=16, bn_size=2, label_patch_size=64)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_crowd_small_seeded_vs_oracle(precision):
+    """Crowd SR-GAN on a reduced KnnDenseNetCat (2,2,2,2 / growth 8 / 64x64): CUDA graph-net path (BN-affine, pools, concat
+    slices, MapModules, crowd labeled loss incl. map term, gradient penalty through all of it) vs the oracle, two steps."""
+    st = O.init_crowd(seed=1, image_size=64, z_dim=16, g_conv_dim=8, scale=2.0, **CROWD_SMALL)
+    cfg = O.StepConfig(batch_size=3, matching_loss_multiplier=1e3, contrasting_loss_multiplier=1e2,
+                       gradient_penalty_multiplier=1e2, map_multiplier=1e-3)
+    r = runner_from_state(st, cfg, precision)
+    t = TOL[precision]['scalar']
+    st0 = st.clone()
+    for i in range(2):
+        x, y, u, z, alpha, z2 = O.synthetic_crowd_batch(3, 10 + i, image=64, label=64, z_dim=16)
+        ref = O.training_step(st, cfg, x, y, u, z, alpha, z2, step=i)
+        xc, yc, uc, zc, ac, z2c = to_cuda(x, y, u, z, alpha, z2)
+        if i == 0:
+            pred, feats = r.predict(xc)
+            (c_ref, _), _, f_ref = O.d_forward(st0.d_spec, st0.D, x)
+            assert rel(pred, c_ref) < t and rel(feats, f_ref) < t
+        r.dnn_step(xc, yc)
+        r.gan_step(xc, yc, uc, i, noise=(zc, ac, z2c))
+        check_scalars(r.scalars(), ref, t * (1 if i == 0 else 3), ('crowd-small', i))
+        assert ref['gradient_penalty'] > 0
+    for net, params in (('D', st.D), ('G', st.G), ('DNN', st.DNN)):
+        sd = r.modules[net].state_dict()
+        init = getattr(st0, net)
+        for k, v in params.items():
+            if O.is_buffer_key(k):
+                assert torch.equal(sd[k].cpu(), init[k]), k
+                continue
+            upd_ref, upd = v - init[k], sd[k].cpu() - init[k]
+            merr = (upd - upd_ref).abs().mean().item() / (upd_ref.abs().mean().item() + 1e-12)
+            # Adam's first steps are sign-like: in bf16 small gradients flip sign, so bound the direction of the update
+            _, cos = update_error(upd, upd_ref)
+            assert (merr < 2e-2) if precision == 'fp32' else (cos > 0.7 or upd_ref.numel() < 64), (net, k, merr, cos)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_crowd_full_size_matches_reference_golden(precision):
+    """BASELINE configs[2] architecture at full size (DenseNet-201 KnnDenseNetCat + DCGenerator, 224x224, B=2) against
+    the scalars the UNMODIFIED reference produced (tests/golden/crowd_srgan.npz; state and inputs regenerated from seeds)."""
+    import json
+    import os
+    import numpy as np
+    from tests.golden_io import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, 'crowd_srgan.npz'))
+    cfgj = json.loads(bytes(z['config_json']).decode())
+    cfg = O.StepConfig()
+    for k, v in cfgj.items():
+        if hasattr(cfg, k):
+            setattr(cfg, k, v)
+    st = O.init_crowd(seed=cfgj['init_seed'], scale=cfgj['d_scale'])
+    r = runner_from_state(st, cfg, precision)
+    x, y, u, zz, alpha, z2 = to_cuda(*O.synthetic_crowd_batch(2, cfgj['input_seed']))
+    r.dnn_step(x, y)
+    r.gan_step(x, y, u, 0, noise=(zz, alpha, z2))
+    ref = {k: float(z[f'step0/scalars/{k}']) for k in SCALARS}
+    # 201 layers deep: bf16 rounding compounds (the gradient norm is a product through every layer)
+    t = 1e-4 if precision == 'fp32' else 5e-2
+    check_scalars(r.scalars(), ref, t, ('crowd-full', precision))
+    if precision == 'fp32':
+        init = st
+        for net in ('D', 'G', 'DNN'):
+            keys = json.loads(bytes(z[f'update/{net}/keys']).decode())
+            sd = r.modules[net].state_dict()
+            got_abs = torch.tensor([(sd[k].cpu() - getattr(init, net)[k]).double().abs().sum().item() for k in keys])
+            assert rel(got_abs, torch.tensor(z[f'update/{net}/abs_sum'])) < 5e-3, net
