@@ -150,16 +150,19 @@ int srgan_repack(const float* param, const int* dims4, void* out1, const long lo
  * Eval-mode BatchNorm2d (+ReLU): disable_batch_norm_updates srgan.py:538-542 applied at :261,276 makes every
  * _BatchNorm a per-channel affine of its running statistics; weight and bias stay trainable (crowd/models.py:339-343,
  * 367, 1077, 1092).  mode 0: y = act(gamma*(x-mean)/sqrt(var+eps)+beta); mode 1 (tangent pass of the gradient penalty):
- * y = gamma/sqrt(var+eps) * x * act'(href). */
-int srgan_affine(const void* x, int x_pitch, int x_c0, void* y, long long rows, int C, const float* gamma, const float* beta,
-                 const float* mean, const float* var, float eps, const void* href, int mode, int act, float slope, int dtype,
-                 void* stream);
-/* dx[:, c0:c0+C] (+)= dy * gamma/sqrt(var+eps)   (dy dense, w.r.t. the affine's pre-activation) */
-int srgan_affine_bwd(const void* dy, void* dx, int dx_pitch, int dx_c0, long long rows, int C, const float* gamma,
-                     const float* var, float eps, int accumulate, int dtype, void* stream);
+ * y = gamma/sqrt(var+eps) * x * act'(href).
+ * y, href, dy: columns [0, C) of rows with pitch y_pitch / dy_pitch >= C (operand buffers padded to the tensor-core tile
+ * granularity; the pad columns are never touched). */
+int srgan_affine(const void* x, int x_pitch, int x_c0, void* y, int y_pitch, long long rows, int C, const float* gamma,
+                 const float* beta, const float* mean, const float* var, float eps, const void* href, int mode, int act,
+                 float slope, int dtype, void* stream);
+/* dx[:, c0:c0+C] (+)= dy[:, :C] * gamma/sqrt(var+eps)   (dy w.r.t. the affine's pre-activation) */
+int srgan_affine_bwd(const void* dy, int dy_pitch, void* dx, int dx_pitch, int dx_c0, long long rows, int C,
+                     const float* gamma, const float* var, float eps, int accumulate, int dtype, void* stream);
 /* dgamma[c] += sum_r dy[r,c]*(x[r,c0+c] - mean[c]*subtract_mean)/sqrt(var[c]+eps); dbeta[c] += sum_r dy[r,c] (may be NULL) */
-int srgan_affine_grad(const void* dy, const void* x, int x_pitch, int x_c0, long long rows, int C, const float* mean,
-                      const float* var, float eps, float* dgamma, float* dbeta, int subtract_mean, int dtype, void* stream);
+int srgan_affine_grad(const void* dy, int dy_pitch, const void* x, int x_pitch, int x_c0, long long rows, int C,
+                      const float* mean, const float* var, float eps, float* dgamma, float* dbeta, int subtract_mean,
+                      int dtype, void* stream);
 /* dst[:, d0:d0+C] (+)= src[:, s0:s0+C] : torch.cat writes / their backward reads, MapModule taps */
 int srgan_copy2d(const void* src, int src_pitch, int src_c0, void* dst, int dst_pitch, int dst_c0, long long rows, int C,
                  int accumulate, int dtype, void* stream);
@@ -171,9 +174,10 @@ int srgan_maxpool(const void* x, const void* xref, void* y, int y_pitch, int y_c
 int srgan_maxpool_bwd(const void* xref, const void* dy, int dy_pitch, int dy_c0, void* dx, int n, int H, int W, int C, int k,
                       int stride, int pad, int act, float slope, int dtype, void* stream);
 /* nn.AvgPool2d(k, k) (crowd/models.py:370) and avg_pool2d(kernel 7) (:1151): non-overlapping k x k means */
-int srgan_avgpool(const void* x, void* y, int y_pitch, int y_c0, int n, int H, int W, int C, int k, int dtype, void* stream);
-int srgan_avgpool_bwd(const void* dy, int dy_pitch, int dy_c0, void* dx, int n, int H, int W, int C, int k, const void* href,
-                      int act, float slope, int dtype, void* stream);
+int srgan_avgpool(const void* x, int x_pitch, void* y, int y_pitch, int y_c0, int n, int H, int W, int C, int k, int dtype,
+                  void* stream);
+int srgan_avgpool_bwd(const void* dy, int dy_pitch, int dy_c0, void* dx, int x_pitch, int n, int H, int W, int C, int k,
+                      const void* href, int act, float slope, int dtype, void* stream);
 /* CrowdExperiment.labeled_loss_function, crowd/srgan.py:247-254, on B samples:
  * loss += scale * sum_b (|pred_b - sum(density_b)|^order + map_mult * m_b^order), m_b = sum_hw mean_c |map_c - map_label|;
  * dpred_b = dLoss/dpred_b, dm_b = dLoss/dm_b.  maps: HOST array of nmaps (<= 4) device pointers, [B, HW] each. */

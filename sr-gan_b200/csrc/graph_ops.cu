@@ -22,7 +22,7 @@ inline int ew_grid(long long work_items) {
 // ------------------------------------------------------------------------------------------------------------
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) affine_kernel(const T* __restrict__ x, int x_pitch, int x_c0, T* __restrict__ y,
-                                                     long long rows, int C, const float* __restrict__ gamma,
+                                                     int y_pitch, long long rows, int C, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, const float* __restrict__ mean,
                                                      const float* __restrict__ var, float eps, const T* __restrict__ href,
                                                      int mode, int act, float slope) {
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) affine_kernel(const T* __restrict__ x, in
         const long long r = i / cv;
         const int c = (int)(i - r * cv) * V;
         const T* xp = x + r * x_pitch + x_c0 + c;
-        T* yp = y + r * C + c;
+        T* yp = y + r * y_pitch + c;
         if (VEC) {
             const float4 xv = ld4(xp), g = ld4f(gamma + c), vr = ld4f(var + c);
             float4 s = make_float4(bn_scale(g.x, vr.x, eps), bn_scale(g.y, vr.y, eps), bn_scale(g.z, vr.z, eps), bn_scale(g.w, vr.w, eps));
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) affine_kernel(const T* __restrict__ x, in
                 o.x = act_fwd((xv.x - m.x) * s.x + b.x, act, slope); o.y = act_fwd((xv.y - m.y) * s.y + b.y, act, slope);
                 o.z = act_fwd((xv.z - m.z) * s.z + b.z, act, slope); o.w = act_fwd((xv.w - m.w) * s.w + b.w, act, slope);
             } else {
-                const float4 h = ld4(href + r * C + c);
+                const float4 h = ld4(href + r * y_pitch + c);
                 o.x = xv.x * s.x * act_bwd(h.x, act, slope); o.y = xv.y * s.y * act_bwd(h.y, act, slope);
                 o.z = xv.z * s.z * act_bwd(h.z, act, slope); o.w = xv.w * s.w * act_bwd(h.w, act, slope);
             }
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) affine_kernel(const T* __restrict__ x, in
             const float xv = to_f(*xp);
             float o;
             if (mode == 0) o = act_fwd((xv - mean[c]) * s + beta[c], act, slope);
-            else o = xv * s * act_bwd(to_f(href[r * C + c]), act, slope);
+            else o = xv * s * act_bwd(to_f(href[r * y_pitch + c]), act, slope);
             *yp = from_f<T>(o);
         }
     }
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) affine_kernel(const T* __restrict__ x, in
 
 // dx[:, c0:c0+C] (+)= dy * gamma/sqrt(var+eps)
 template <typename T, bool VEC>
-__global__ void __launch_bounds__(256) affine_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int dx_pitch, int dx_c0,
+__global__ void __launch_bounds__(256) affine_bwd_kernel(const T* __restrict__ dy, int dy_pitch, T* __restrict__ dx, int dx_pitch, int dx_c0,
                                                          long long rows, int C, const float* __restrict__ gamma,
                                                          const float* __restrict__ var, float eps, int accumulate) {
     constexpr int V = VEC ? 4 : 1;
@@ -72,13 +72,13 @@ __global__ void __launch_bounds__(256) affine_bwd_kernel(const T* __restrict__ d
         const int c = (int)(i - r * cv) * V;
         T* xp = dx + r * dx_pitch + dx_c0 + c;
         if (VEC) {
-            const float4 d = ld4(dy + r * C + c), g = ld4f(gamma + c), vr = ld4f(var + c);
+            const float4 d = ld4(dy + r * dy_pitch + c), g = ld4f(gamma + c), vr = ld4f(var + c);
             float4 o = make_float4(d.x * bn_scale(g.x, vr.x, eps), d.y * bn_scale(g.y, vr.y, eps), d.z * bn_scale(g.z, vr.z, eps),
                                    d.w * bn_scale(g.w, vr.w, eps));
             if (accumulate) { const float4 p = ld4(xp); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
             st4(xp, o);
         } else {
-            float o = to_f(dy[r * C + c]) * bn_scale(gamma[c], var[c], eps);
+            float o = to_f(dy[r * dy_pitch + c]) * bn_scale(gamma[c], var[c], eps);
             if (accumulate) o += to_f(*xp);
             *xp = from_f<T>(o);
         }
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) affine_bwd_kernel(const T* __restrict__ d
 // dgamma[c] += sum_r dy[r,c]*(x[r,c0+c]-mean[c]*sub)/sqrt(var[c]+eps) ; dbeta[c] += sum_r dy[r,c]
 // block = 8 warps over a 32*V-column strip; blockIdx.y = row chunk; lanes own V consecutive columns
 template <typename T, bool VEC>
-__global__ void __launch_bounds__(256) affine_grad_kernel(const T* __restrict__ dy, const T* __restrict__ x, int x_pitch, int x_c0,
+__global__ void __launch_bounds__(256) affine_grad_kernel(const T* __restrict__ dy, int dy_pitch, const T* __restrict__ x, int x_pitch, int x_c0,
                                                           long long rows, int C, const float* __restrict__ mean,
                                                           const float* __restrict__ var, float eps, float* __restrict__ dgamma,
                                                           float* __restrict__ dbeta, int subtract_mean, long long rows_per_block) {
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) affine_grad_kernel(const T* __restrict__ 
     if (c < C) {
         for (long long r = r0 + w; r < r1; r += 8) {
             if (VEC) {
-                const float4 d = ld4(dy + r * C + c), xv = ld4(x + r * x_pitch + x_c0 + c);
+                const float4 d = ld4(dy + r * dy_pitch + c), xv = ld4(x + r * x_pitch + x_c0 + c);
                 ag[0] = fmaf(d.x, xv.x - mu[0], ag[0]); ab[0] += d.x;
                 if (V > 1) {
                     ag[1 % V] = fmaf(d.y, xv.y - mu[1 % V], ag[1 % V]); ab[1 % V] += d.y;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) affine_grad_kernel(const T* __restrict__ 
                     ag[3 % V] = fmaf(d.w, xv.w - mu[3 % V], ag[3 % V]); ab[3 % V] += d.w;
                 }
             } else {
-                const float d = to_f(dy[r * C + c]);
+                const float d = to_f(dy[r * dy_pitch + c]);
                 ag[0] = fmaf(d, to_f(x[r * x_pitch + x_c0 + c]) - mu[0], ag[0]); ab[0] += d;
             }
         }
@@ -223,8 +223,8 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) avgpool_kernel(const T* __restrict__ x, T* __restrict__ y, int y_pitch, int y_c0, int n,
-                                                      int H, int W, int C, int k) {
+__global__ void __launch_bounds__(256) avgpool_kernel(const T* __restrict__ x, int x_pitch, T* __restrict__ y, int y_pitch, int y_c0,
+                                                      int n, int H, int W, int C, int k) {
     const int Ho = H / k, Wo = W / k;
     const long long total = (long long)n * Ho * Wo * C;
     const float inv = 1.f / (float)(k * k);
@@ -237,15 +237,15 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const T* __restrict__ x, T
         float acc = 0.f;
         for (int dh = 0; dh < k; ++dh)
             for (int dw = 0; dw < k; ++dw)
-                acc += to_f(x[((b * H + ho * k + dh) * W + wo * k + dw) * C + c]);
+                acc += to_f(x[((b * H + ho * k + dh) * W + wo * k + dw) * x_pitch + c]);
         y[((b * Ho + ho) * Wo + wo) * y_pitch + y_c0 + c] = from_f<T>(acc * inv);
     }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const T* __restrict__ dy, int dy_pitch, int dy_c0, T* __restrict__ dx,
-                                                          int n, int H, int W, int C, int k, const T* __restrict__ href, int act,
-                                                          float slope) {
+                                                          int x_pitch, int n, int H, int W, int C, int k,
+                                                          const T* __restrict__ href, int act, float slope) {
     const int Ho = H / k, Wo = W / k;
     const long long total = (long long)n * H * W * C;
     const float inv = 1.f / (float)(k * k);
@@ -256,8 +256,9 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const T* __restrict__ 
         const int h = (int)(t % H);
         const long long b = t / H;
         float v = to_f(dy[((b * Ho + h / k) * Wo + w / k) * dy_pitch + dy_c0 + c]) * inv;
-        if (href) v *= act_bwd(to_f(href[i]), act, slope);
-        dx[i] = from_f<T>(v);
+        const long long xi = ((b * H + h) * W + w) * x_pitch + c;
+        if (href) v *= act_bwd(to_f(href[xi]), act, slope);
+        dx[xi] = from_f<T>(v);
     }
 }
 
@@ -323,41 +324,43 @@ inline bool vec_ok(int C, int p0, int o0, int p1 = 0, int o1 = 0) { return ((C |
 
 extern "C" {
 
-int srgan_affine(const void* x, int x_pitch, int x_c0, void* y, long long rows, int C, const float* gamma, const float* beta,
-                 const float* mean, const float* var, float eps, const void* href, int mode, int act, float slope, int dtype,
-                 void* stream) {
-    SRGAN_REQUIRE(x && y && gamma && var && rows >= 0 && C > 0 && x_c0 >= 0 && x_c0 + C <= x_pitch, "srgan_affine: bad arguments");
+int srgan_affine(const void* x, int x_pitch, int x_c0, void* y, int y_pitch, long long rows, int C, const float* gamma,
+                 const float* beta, const float* mean, const float* var, float eps, const void* href, int mode, int act,
+                 float slope, int dtype, void* stream) {
+    SRGAN_REQUIRE(x && y && gamma && var && rows >= 0 && C > 0 && x_c0 >= 0 && x_c0 + C <= x_pitch && C <= y_pitch,
+                  "srgan_affine: bad arguments");
     SRGAN_REQUIRE(mode == 0 ? (beta && mean) : (mode == 1 && href), "srgan_affine: mode 0 needs beta/mean, mode 1 needs href");
     if (rows == 0) return SRGAN_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool vec = vec_ok(C, x_pitch, x_c0);
+    const bool vec = vec_ok(C, x_pitch, x_c0, y_pitch);
     DISPATCH_T(dtype,
-               if (vec) affine_kernel<T, true><<<ew_grid(rows * C / 4), 256, 0, st>>>((const T*)x, x_pitch, x_c0, (T*)y, rows, C, gamma, beta, mean, var, eps, (const T*)href, mode, act, slope);
-               else affine_kernel<T, false><<<ew_grid(rows * C), 256, 0, st>>>((const T*)x, x_pitch, x_c0, (T*)y, rows, C, gamma, beta, mean, var, eps, (const T*)href, mode, act, slope));
+               if (vec) affine_kernel<T, true><<<ew_grid(rows * C / 4), 256, 0, st>>>((const T*)x, x_pitch, x_c0, (T*)y, y_pitch, rows, C, gamma, beta, mean, var, eps, (const T*)href, mode, act, slope);
+               else affine_kernel<T, false><<<ew_grid(rows * C), 256, 0, st>>>((const T*)x, x_pitch, x_c0, (T*)y, y_pitch, rows, C, gamma, beta, mean, var, eps, (const T*)href, mode, act, slope));
     SRGAN_CHECK_LAUNCH("affine_kernel");
     return SRGAN_OK;
 }
 
-int srgan_affine_bwd(const void* dy, void* dx, int dx_pitch, int dx_c0, long long rows, int C, const float* gamma, const float* var,
-                     float eps, int accumulate, int dtype, void* stream) {
-    SRGAN_REQUIRE(dy && dx && gamma && var && rows >= 0 && C > 0 && dx_c0 >= 0 && dx_c0 + C <= dx_pitch, "srgan_affine_bwd: bad arguments");
+int srgan_affine_bwd(const void* dy, int dy_pitch, void* dx, int dx_pitch, int dx_c0, long long rows, int C, const float* gamma,
+                     const float* var, float eps, int accumulate, int dtype, void* stream) {
+    SRGAN_REQUIRE(dy && dx && gamma && var && rows >= 0 && C > 0 && dx_c0 >= 0 && dx_c0 + C <= dx_pitch && C <= dy_pitch,
+                  "srgan_affine_bwd: bad arguments");
     if (rows == 0) return SRGAN_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool vec = vec_ok(C, dx_pitch, dx_c0);
+    const bool vec = vec_ok(C, dx_pitch, dx_c0, dy_pitch);
     DISPATCH_T(dtype,
-               if (vec) affine_bwd_kernel<T, true><<<ew_grid(rows * C / 4), 256, 0, st>>>((const T*)dy, (T*)dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, accumulate);
-               else affine_bwd_kernel<T, false><<<ew_grid(rows * C), 256, 0, st>>>((const T*)dy, (T*)dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, accumulate));
+               if (vec) affine_bwd_kernel<T, true><<<ew_grid(rows * C / 4), 256, 0, st>>>((const T*)dy, dy_pitch, (T*)dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, accumulate);
+               else affine_bwd_kernel<T, false><<<ew_grid(rows * C), 256, 0, st>>>((const T*)dy, dy_pitch, (T*)dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, accumulate));
     SRGAN_CHECK_LAUNCH("affine_bwd_kernel");
     return SRGAN_OK;
 }
 
-int srgan_affine_grad(const void* dy, const void* x, int x_pitch, int x_c0, long long rows, int C, const float* mean, const float* var,
-                      float eps, float* dgamma, float* dbeta, int subtract_mean, int dtype, void* stream) {
-    SRGAN_REQUIRE(dy && x && var && dgamma && rows >= 0 && C > 0 && x_c0 >= 0 && x_c0 + C <= x_pitch && (!subtract_mean || mean),
+int srgan_affine_grad(const void* dy, int dy_pitch, const void* x, int x_pitch, int x_c0, long long rows, int C, const float* mean,
+                      const float* var, float eps, float* dgamma, float* dbeta, int subtract_mean, int dtype, void* stream) {
+    SRGAN_REQUIRE(dy && x && var && dgamma && rows >= 0 && C > 0 && x_c0 >= 0 && x_c0 + C <= x_pitch && C <= dy_pitch && (!subtract_mean || mean),
                   "srgan_affine_grad: bad arguments");
     if (rows == 0) return SRGAN_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool vec = vec_ok(C, x_pitch, x_c0);
+    const bool vec = vec_ok(C, x_pitch, x_c0, dy_pitch);
     const int V = vec ? 4 : 1;
     const int gx = (C + 32 * V - 1) / (32 * V);
     long long want = (4LL * kNumSMs + gx - 1) / gx;                 // ~4 CTAs per SM in total
@@ -366,8 +369,8 @@ int srgan_affine_grad(const void* dy, const void* x, int x_pitch, int x_c0, long
     const long long gy = (rows + rpb - 1) / rpb;
     dim3 grid(gx, (unsigned)gy);
     DISPATCH_T(dtype,
-               if (vec) affine_grad_kernel<T, true><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, x_pitch, x_c0, rows, C, mean, var, eps, dgamma, dbeta, subtract_mean, rpb);
-               else affine_grad_kernel<T, false><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, x_pitch, x_c0, rows, C, mean, var, eps, dgamma, dbeta, subtract_mean, rpb));
+               if (vec) affine_grad_kernel<T, true><<<grid, 256, 0, st>>>((const T*)dy, dy_pitch, (const T*)x, x_pitch, x_c0, rows, C, mean, var, eps, dgamma, dbeta, subtract_mean, rpb);
+               else affine_grad_kernel<T, false><<<grid, 256, 0, st>>>((const T*)dy, dy_pitch, (const T*)x, x_pitch, x_c0, rows, C, mean, var, eps, dgamma, dbeta, subtract_mean, rpb));
     SRGAN_CHECK_LAUNCH("affine_grad_kernel");
     return SRGAN_OK;
 }
@@ -410,23 +413,26 @@ int srgan_maxpool_bwd(const void* xref, const void* dy, int dy_pitch, int dy_c0,
     return SRGAN_OK;
 }
 
-int srgan_avgpool(const void* x, void* y, int y_pitch, int y_c0, int n, int H, int W, int C, int k, int dtype, void* stream) {
-    SRGAN_REQUIRE(x && y && n >= 0 && H > 0 && W > 0 && C > 0 && k > 0 && H % k == 0 && W % k == 0 && y_c0 >= 0 && y_c0 + C <= y_pitch,
+int srgan_avgpool(const void* x, int x_pitch, void* y, int y_pitch, int y_c0, int n, int H, int W, int C, int k, int dtype,
+                  void* stream) {
+    SRGAN_REQUIRE(x && y && n >= 0 && H > 0 && W > 0 && C > 0 && k > 0 && H % k == 0 && W % k == 0 && y_c0 >= 0 && y_c0 + C <= y_pitch &&
+                      C <= x_pitch,
                   "srgan_avgpool: bad arguments (the window must tile the input)");
     if (n == 0) return SRGAN_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    DISPATCH_T(dtype, avgpool_kernel<T><<<ew_grid((long long)n * (H / k) * (W / k) * C), 256, 0, st>>>((const T*)x, (T*)y, y_pitch, y_c0, n, H, W, C, k));
+    DISPATCH_T(dtype, avgpool_kernel<T><<<ew_grid((long long)n * (H / k) * (W / k) * C), 256, 0, st>>>((const T*)x, x_pitch, (T*)y, y_pitch, y_c0, n, H, W, C, k));
     SRGAN_CHECK_LAUNCH("avgpool_kernel");
     return SRGAN_OK;
 }
 
-int srgan_avgpool_bwd(const void* dy, int dy_pitch, int dy_c0, void* dx, int n, int H, int W, int C, int k, const void* href, int act,
-                      float slope, int dtype, void* stream) {
-    SRGAN_REQUIRE(dy && dx && n >= 0 && H > 0 && W > 0 && C > 0 && k > 0 && H % k == 0 && W % k == 0 && dy_c0 >= 0 && dy_c0 + C <= dy_pitch,
+int srgan_avgpool_bwd(const void* dy, int dy_pitch, int dy_c0, void* dx, int x_pitch, int n, int H, int W, int C, int k,
+                      const void* href, int act, float slope, int dtype, void* stream) {
+    SRGAN_REQUIRE(dy && dx && n >= 0 && H > 0 && W > 0 && C > 0 && k > 0 && H % k == 0 && W % k == 0 && dy_c0 >= 0 && dy_c0 + C <= dy_pitch &&
+                      C <= x_pitch,
                   "srgan_avgpool_bwd: bad arguments");
     if (n == 0) return SRGAN_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    DISPATCH_T(dtype, avgpool_bwd_kernel<T><<<ew_grid((long long)n * H * W * C), 256, 0, st>>>((const T*)dy, dy_pitch, dy_c0, (T*)dx, n, H, W, C, k, (const T*)(act == SRGAN_ACT_NONE ? nullptr : href), act, slope));
+    DISPATCH_T(dtype, avgpool_bwd_kernel<T><<<ew_grid((long long)n * H * W * C), 256, 0, st>>>((const T*)dy, dy_pitch, dy_c0, (T*)dx, x_pitch, n, H, W, C, k, (const T*)(act == SRGAN_ACT_NONE ? nullptr : href), act, slope));
     SRGAN_CHECK_LAUNCH("avgpool_bwd_kernel");
     return SRGAN_OK;
 }

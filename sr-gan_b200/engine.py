@@ -85,6 +85,8 @@ class NetState:
         self.slices = {}
         self.gslices = {}
         order = []
+        # elements of a layer's kernel-layout weight copies: geom.Ca / geom.Cb may be padded beyond the master dims
+        kl = {l.name: l.geom.Ca * l.geom.R * l.geom.S * l.geom.Cb for l in net.layers}
         for l in net.layers:
             order += [l.name + '.weight'] + ([l.name + '.bias'] if l.has_bias else [])
         for op in net.affines:                     # eval-mode BatchNorm: weight / bias are trainable, the statistics are not
@@ -104,6 +106,8 @@ class NetState:
             gn = n
             if k.endswith('.weight') and lname in self.thin:
                 gn = p.shape[0] * KPAD             # gradient in the padded Wd_pad layout [a][KPAD]
+            elif k.endswith('.weight') and lname in kl:
+                gn = kl[lname]                     # gradient in the (possibly channel-padded) Wd layout
             self.gslices[k] = (g_total, gn)
             g_total += (gn + 3) // 4 * 4
         self.order = order
@@ -115,7 +119,7 @@ class NetState:
         self.adam_state = torch.zeros(3, dtype=mdt, device=device)
         self.wd_, self.wu_ = {}, {}
         for l in net.layers:
-            n = params[l.name + '.weight'].numel()
+            n = kl[l.name]
             if l.name in self.thin:
                 n = l.geom.Ca * KPAD               # padded copies; the pad columns / rows stay zero
             self.wd_[l.name] = torch.zeros(n, dtype=act_dtype, device=device)
@@ -167,14 +171,14 @@ class Engine:
                 self.repack(st)
 
     # ------------------------------------------------------------------ buffers
-    def buf(self, key, shape, dtype=None):
+    def buf(self, key, shape, dtype=None, zero=False):
         dtype = dtype or self.act_dtype
         t = self._buf.get(key)
         n = 1
         for s in shape:
             n *= s
         if t is None or t.numel() < n or t.dtype != dtype:
-            t = torch.empty(n, dtype=dtype, device=self.device)
+            t = (torch.zeros if zero else torch.empty)(n, dtype=dtype, device=self.device)
             self._buf[key] = t
         return t[:n].view(*shape)
 
@@ -334,7 +338,8 @@ class Engine:
         """Chain nets: acts[0] = network input, acts[l] = output of layer l (a list).  Graph nets: a dict buffer name ->
         tensor.  Flat tensors, nb_rows samples of NHWC rows each."""
         if net.graph is not None:
-            return {name: self.buf((tag, 'a', name), (nb_rows * b.rows * b.ch,)) for name, b in net.bufs.items()}
+            # zero-filled on (re)allocation: the pad channels of the padded operand buffers are never written
+            return {name: self.buf((tag, 'a', name), (nb_rows * b.rows * b.ch,), zero=True) for name, b in net.bufs.items()}
         acts = [self.buf((tag, 'a', 0), (nb_rows * net.layers[0].in_elems,))]
         for i, l in enumerate(net.layers, 1):
             acts.append(self.buf((tag, 'a', i), (nb_rows * l.out_elems,)))
@@ -344,7 +349,7 @@ class Engine:
 
     def alloc_deltas(self, tag, net: Net, nb_rows):
         if net.graph is not None:
-            return {name: self.buf((tag, 'd', name), (nb_rows * b.rows * b.ch,)) for name, b in net.bufs.items()
+            return {name: self.buf((tag, 'd', name), (nb_rows * b.rows * b.ch,), zero=True) for name, b in net.bufs.items()
                     if name != net.input_buf}
         d = [None]
         for i, l in enumerate(net.layers, 1):
@@ -444,13 +449,14 @@ class Engine:
             x, y = R(acts[op.src], sb, lo, hi), R(acts[op.dst], db, lo, hi)
             href = R(acts[op.dst], db, mlo, mlo + n) if tangent else None
             if op.kind == 'conv':
+                ng = n * op.layer.gemm_rows
                 if tangent:
-                    self._fwd_layer(st, op.layer, x, y, n, bias=False, href=href, epi=EPI_DACT, lo=lo)
+                    self._fwd_layer(st, op.layer, x, y, ng, bias=False, href=href, epi=EPI_DACT, lo=lo)
                 else:
-                    self._fwd_layer(st, op.layer, x, y, n, lo=lo)
+                    self._fwd_layer(st, op.layer, x, y, ng, lo=lo)
             elif op.kind == 'affine':
                 nm = op.name
-                ops.affine(x, sb.ch, op.c0, y, n * sb.rows, op.C, P[nm + '.weight'], P[nm + '.bias'],
+                ops.affine(x, sb.ch, op.c0, y, db.ch, n * sb.rows, op.C, P[nm + '.weight'], P[nm + '.bias'],
                            P[nm + '.running_mean'], P[nm + '.running_var'], self.BN_EPS, href, 1 if tangent else 0,
                            db.act, db.slope)
             elif op.kind == 'copy':
@@ -461,7 +467,7 @@ class Engine:
                 xref = R(acts[op.src], sb, mlo, mlo + n) if tangent else None
                 ops.maxpool(x, xref, y, db.ch, op.c0, n, op.H, op.W, op.C, op.k, op.stride, op.pad)
             elif op.kind == 'avgpool':
-                ops.avgpool(x, y, db.ch, op.c0, n, op.H, op.W, op.C, op.k)
+                ops.avgpool(x, sb.ch, y, db.ch, op.c0, n, op.H, op.W, op.C, op.k)
             else:
                 raise ValueError(op.kind)
 
@@ -488,25 +494,27 @@ class Engine:
                 if hook is not None and op.dst in net.map_bufs:
                     hook(op.dst)
                 if weight_grads:
-                    self._wgrad_layer(st, l, R(acts[op.src], sb, wlo, whi), R(deltas[op.dst], db, wlo, whi), whi - wlo, lo=wlo)
+                    self._wgrad_layer(st, l, R(acts[op.src], sb, wlo, whi), R(deltas[op.dst], db, wlo, whi),
+                                      (whi - wlo) * l.gemm_rows, lo=wlo)
                     if l.has_bias:
-                        self._bias_grad(st, l, dy, n * l.out_rows)
+                        self._bias_grad(st, l, dy, n * db.rows)
                 if is_input:
                     if input_grad is not None:
                         dinput, ihref, iact = input_grad
-                        self._bwd_data_layer(st, l, dy, dinput, n, ihref, iact, 0.0, lo=lo)
+                        self._bwd_data_layer(st, l, dy, dinput, n * l.gemm_rows, ihref, iact, 0.0, lo=lo)
                 else:
-                    self._bwd_data_layer(st, l, dy, dx, n, xa, sb.act, sb.slope, lo=lo)
+                    self._bwd_data_layer(st, l, dy, dx, n * l.gemm_rows, xa, sb.act, sb.slope, lo=lo)
             elif op.kind == 'affine':
                 nm = op.name
                 mean, var = P[nm + '.running_mean'], P[nm + '.running_var']
                 if weight_grads:
-                    ops.affine_grad(dy, xa, sb.ch, op.c0, n * sb.rows, op.C, mean, var, self.BN_EPS,
+                    ops.affine_grad(dy, db.ch, xa, sb.ch, op.c0, n * sb.rows, op.C, mean, var, self.BN_EPS,
                                     st.g(nm + '.weight'), st.g(nm + '.bias'), True)
                     if whi > hi:
-                        ops.affine_grad(R(deltas[op.dst], db, hi, whi), R(acts[op.src], sb, hi, whi), sb.ch, op.c0,
+                        ops.affine_grad(R(deltas[op.dst], db, hi, whi), db.ch, R(acts[op.src], sb, hi, whi), sb.ch, op.c0,
                                         (whi - hi) * sb.rows, op.C, mean, var, self.BN_EPS, st.g(nm + '.weight'), None, False)
-                ops.affine_bwd(dy, dx, sb.ch, op.c0, n * sb.rows, op.C, P[nm + '.weight'], var, self.BN_EPS, sb.accumulate)
+                ops.affine_bwd(dy, db.ch, dx, sb.ch, op.c0, n * sb.rows, op.C, P[nm + '.weight'], var, self.BN_EPS,
+                               sb.accumulate)
             elif op.kind == 'copy':       # dst slice <- dense src: both are w.r.t. the same pre-activation
                 ops.copy2d(dy, db.ch, op.c0, dx, sb.ch, 0, n * sb.rows, op.C, False)
             elif op.kind == 'read':       # dense dst <- src slice: add into the (accumulating) concat delta
@@ -514,7 +522,7 @@ class Engine:
             elif op.kind == 'maxpool':
                 ops.maxpool_bwd(xa, dy, db.ch, op.c0, dx, n, op.H, op.W, op.C, op.k, op.stride, op.pad, sb.act, sb.slope)
             elif op.kind == 'avgpool':
-                ops.avgpool_bwd(dy, db.ch, op.c0, dx, n, op.H, op.W, op.C, op.k, xa, sb.act, sb.slope)
+                ops.avgpool_bwd(dy, db.ch, op.c0, dx, sb.ch, n, op.H, op.W, op.C, op.k, xa, sb.act, sb.slope)
             else:
                 raise ValueError(op.kind)
 

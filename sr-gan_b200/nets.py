@@ -64,6 +64,18 @@ class Layer:
     master_kind: str = 'conv'
     bias_mod: int = 0              # bias index = column % bias_mod  (fc_up: bias per channel, broadcast over r,s)
     has_bias: bool = True          # DenseNet trunk convolutions are bias-free (crowd/models.py:341-345,1075)
+    # 1x1 convolutions of graph nets run as a plain [pixels x Cb] GEMM: geom is then the Linear pair and the kernels see
+    # gemm_rows x (number of samples) rows.  geom.Ca / geom.Cb may exceed the master dims (channel padding to the
+    # tensor-core tile granularity; the pad rows / columns of the kernel-layout weights and of the buffers stay zero).
+    gemm_rows: int = 1
+
+    @property
+    def macs_per_sample(self):
+        """Algorithmic MACs (master dims; channel padding of the kernel operands is not counted)."""
+        d0, d1, d2, d3 = self.master_dims
+        if self.master_kind == 'conv':
+            return d0 * d1 * d2 * d3 * self.geom.Hs * self.geom.Ws * self.gemm_rows
+        return d0 * d1 * d2 * d3
 
     @property
     def thin_ok(self):
@@ -184,7 +196,7 @@ class Net:
         return [(self.head, self.feature_size)] if self.head else []
 
     def macs_per_sample(self):
-        m = sum(l.geom.macs_per_sample for l in self.layers)
+        m = sum(l.macs_per_sample for l in self.layers)
         if self.head:
             m += self.feature_size * self.head_outputs
         return m
@@ -241,13 +253,18 @@ def dcgan_g(image_size=128, conv_dim=64, z_dim=256) -> Net:
 
 
 def knn_densenet_cat(block_config=(6, 12, 48, 32), growth_rate=32, num_init_features=64, bn_size=4, image_size=224,
-                     label_size=224) -> Net:
+                     label_size=224, pad_to=64) -> Net:
     """crowd/models.py:1049-1166 KnnDenseNetCat as a graph.  Buffers: 'x' input; 'c0','n0' stem; 'cat{i}' the in-place
     concat buffer of dense block i (the stem pool / transition pool write its first channels, every dense layer appends
     growth_rate channels); per dense layer 'n1','b','n2','new'; per transition 'tn','tc'; per MapModule 't','map','m1'..
     'm3','h'; 'n5','fp','fcf'; 'features' [1 x 80].  Spatial sizes follow torch: stem conv k7 s2 p3, max-pool k3 s2 p1,
-    transitions avg-pool 2."""
+    transitions avg-pool 2.  The operand buffers of the trunk convolutions ('n1', 'new', ...) are padded to multiples of
+    `pad_to` channels so that every trunk contraction is tcgen05-eligible (K and N multiples of 64); 1x1 convolutions are
+    declared as [pixels x C] GEMMs (Layer.gemm_rows)."""
     g, bs = growth_rate, bn_size
+
+    def pad(c):
+        return (c + pad_to - 1) // pad_to * pad_to
     bufs: Dict[str, Buf] = {}
     ops: List[Op] = []
     layers: List[Layer] = []
@@ -258,8 +275,8 @@ def knn_densenet_cat(block_config=(6, 12, 48, 32), growth_rate=32, num_init_feat
         bufs[name] = Buf(name, rows, ch, **kw)
         return name
 
-    def conv(name, src, dst, geom, fwd, master, act=ACT_NONE, slope=0.0, bias=False):
-        l = Layer(name, fwd, geom, act, slope, master, has_bias=bias)
+    def conv(name, src, dst, geom, fwd, master, act=ACT_NONE, slope=0.0, bias=False, gemm_rows=1):
+        l = Layer(name, fwd, geom, act, slope, master, has_bias=bias, gemm_rows=gemm_rows)
         layers.append(l)
         ops.append(Op('conv', src, dst, layer=l))
 
@@ -285,22 +302,23 @@ def knn_densenet_cat(block_config=(6, 12, 48, 32), growth_rate=32, num_init_feat
         for li in range(1, n_layers + 1):
             pre = f'dense_blocks.denseblock{bi}.denselayer{li}'
             tag = f'{bi}.{li}'
-            buf('n1.' + tag, h * h, c, **RELU)
+            cb = pad(bs * g)
+            buf('n1.' + tag, h * h, pad(c), **RELU)
             ops.append(Op('affine', cat, 'n1.' + tag, name=pre + '.norm1', C=c, c0=0))
-            buf('b.' + tag, h * h, bs * g)
-            conv(pre + '.conv1', 'n1.' + tag, 'b.' + tag, Geom(h, h, bs * g, h, h, c, 1, 1, 1, 0), 'down', (bs * g, c, 1, 1))
-            buf('n2.' + tag, h * h, bs * g, **RELU)
+            buf('b.' + tag, h * h, cb)
+            conv(pre + '.conv1', 'n1.' + tag, 'b.' + tag, linear_geom(cb, pad(c)), 'down', (bs * g, c, 1, 1), gemm_rows=h * h)
+            buf('n2.' + tag, h * h, cb, **RELU)
             ops.append(Op('affine', 'b.' + tag, 'n2.' + tag, name=pre + '.norm2', C=bs * g))
-            buf('new.' + tag, h * h, g)
-            conv(pre + '.conv2', 'n2.' + tag, 'new.' + tag, Geom(h, h, g, h, h, bs * g, 3, 3, 1, 1), 'down', (g, bs * g, 3, 3))
+            buf('new.' + tag, h * h, pad(g))
+            conv(pre + '.conv2', 'n2.' + tag, 'new.' + tag, Geom(h, h, pad(g), h, h, cb, 3, 3, 1, 1), 'down', (g, bs * g, 3, 3))
             ops.append(Op('copy', 'new.' + tag, cat, C=g, c0=c))
             c += g
         if bi != len(block_config):
             pre = f'transition_layers.transition{bi}'
-            buf(f'tn{bi}', h * h, c, **RELU)
+            buf(f'tn{bi}', h * h, pad(c), **RELU)
             ops.append(Op('affine', cat, f'tn{bi}', name=pre + '.norm', C=c, c0=0))
-            buf(f'tc{bi}', h * h, c // 2)
-            conv(pre + '.conv', f'tn{bi}', f'tc{bi}', Geom(h, h, c // 2, h, h, c, 1, 1, 1, 0), 'down', (c // 2, c, 1, 1))
+            buf(f'tc{bi}', h * h, pad(c // 2))
+            conv(pre + '.conv', f'tn{bi}', f'tc{bi}', linear_geom(pad(c // 2), pad(c)), 'down', (c // 2, c, 1, 1), gemm_rows=h * h)
             c //= 2
             if h % 2:
                 raise ValueError('transition input must have an even extent')

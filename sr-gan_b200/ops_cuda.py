@@ -80,14 +80,14 @@ def load_library(path: str = LIB_PATH):
     pp = ctypes.POINTER(vp)
     lib.srgan_coefficient_step.argtypes = ([pp, pp, pp, vp, vp, vp] + [vp] * 6 + [c_int, c_f, c_int, c_int] + [c_f] * 5 +
                                            [c_int, c_int] + [c_f] * 6 + [c_int, c_int, vp, ctypes.c_size_t, vp, vp])
-    lib.srgan_affine.argtypes = [vp, c_int, c_int, vp, c_ll, c_int, vp, vp, vp, vp, c_f, vp, c_int, c_int, c_f, c_int, vp]
-    lib.srgan_affine_bwd.argtypes = [vp, vp, c_int, c_int, c_ll, c_int, vp, vp, c_f, c_int, c_int, vp]
-    lib.srgan_affine_grad.argtypes = [vp, vp, c_int, c_int, c_ll, c_int, vp, vp, c_f, vp, vp, c_int, c_int, vp]
+    lib.srgan_affine.argtypes = [vp, c_int, c_int, vp, c_int, c_ll, c_int, vp, vp, vp, vp, c_f, vp, c_int, c_int, c_f, c_int, vp]
+    lib.srgan_affine_bwd.argtypes = [vp, c_int, vp, c_int, c_int, c_ll, c_int, vp, vp, c_f, c_int, c_int, vp]
+    lib.srgan_affine_grad.argtypes = [vp, c_int, vp, c_int, c_int, c_ll, c_int, vp, vp, c_f, vp, vp, c_int, c_int, vp]
     lib.srgan_copy2d.argtypes = [vp, c_int, c_int, vp, c_int, c_int, c_ll, c_int, c_int, c_int, vp]
     lib.srgan_maxpool.argtypes = [vp, vp, vp, c_int, c_int] + [c_int] * 7 + [c_int, vp]
     lib.srgan_maxpool_bwd.argtypes = [vp, vp, c_int, c_int, vp] + [c_int] * 7 + [c_int, c_f, c_int, vp]
-    lib.srgan_avgpool.argtypes = [vp, vp, c_int, c_int] + [c_int] * 5 + [c_int, vp]
-    lib.srgan_avgpool_bwd.argtypes = [vp, c_int, c_int, vp] + [c_int] * 5 + [vp, c_int, c_f, c_int, vp]
+    lib.srgan_avgpool.argtypes = [vp, c_int, vp, c_int, c_int] + [c_int] * 5 + [c_int, vp]
+    lib.srgan_avgpool_bwd.argtypes = [vp, c_int, c_int, vp, c_int] + [c_int] * 5 + [vp, c_int, c_f, c_int, vp]
     lib.srgan_crowd_loss.argtypes = [vp, vp, pp, c_int, vp, c_int, c_ll, c_int, c_f, c_f, vp, vp, vp, c_int, vp]
     lib.srgan_crowd_map_grad.argtypes = [vp, vp, vp, vp, c_int, c_ll, c_int, c_int, c_f, c_int, vp]
     for name in _EXPORTS[5:]:
@@ -295,18 +295,18 @@ class CudaOps:
     def _pf(self, t):
         return self._p(t.detach() if t is not None else None, torch.float32)
 
-    def affine(self, x, x_pitch, x_c0, y, rows, C, gamma, beta, mean, var, eps, href, mode, act, slope):
-        self._ck(self.lib.srgan_affine(self._p(x), x_pitch, x_c0, self._p(y, x.dtype), rows, C, self._pf(gamma), self._pf(beta),
+    def affine(self, x, x_pitch, x_c0, y, y_pitch, rows, C, gamma, beta, mean, var, eps, href, mode, act, slope):
+        self._ck(self.lib.srgan_affine(self._p(x), x_pitch, x_c0, self._p(y, x.dtype), y_pitch, rows, C, self._pf(gamma), self._pf(beta),
                                        self._pf(mean), self._pf(var), eps, self._p(href, x.dtype) if href is not None else None,
                                        mode, act, slope, _dt(x.dtype), self._stream()), 'srgan_affine')
 
-    def affine_bwd(self, dy, dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, accumulate):
-        self._ck(self.lib.srgan_affine_bwd(self._p(dy), self._p(dx, dy.dtype), dx_pitch, dx_c0, rows, C, self._pf(gamma),
+    def affine_bwd(self, dy, dy_pitch, dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, accumulate):
+        self._ck(self.lib.srgan_affine_bwd(self._p(dy), dy_pitch, self._p(dx, dy.dtype), dx_pitch, dx_c0, rows, C, self._pf(gamma),
                                            self._pf(var), eps, int(bool(accumulate)), _dt(dy.dtype), self._stream()),
                  'srgan_affine_bwd')
 
-    def affine_grad(self, dy, x, x_pitch, x_c0, rows, C, mean, var, eps, dgamma, dbeta, subtract_mean):
-        self._ck(self.lib.srgan_affine_grad(self._p(dy), self._p(x, dy.dtype), x_pitch, x_c0, rows, C, self._pf(mean),
+    def affine_grad(self, dy, dy_pitch, x, x_pitch, x_c0, rows, C, mean, var, eps, dgamma, dbeta, subtract_mean):
+        self._ck(self.lib.srgan_affine_grad(self._p(dy), dy_pitch, self._p(x, dy.dtype), x_pitch, x_c0, rows, C, self._pf(mean),
                                             self._pf(var), eps, self._pf(dgamma), self._pf(dbeta), int(bool(subtract_mean)),
                                             _dt(dy.dtype), self._stream()), 'srgan_affine_grad')
 
@@ -322,12 +322,12 @@ class CudaOps:
         self._ck(self.lib.srgan_maxpool_bwd(self._p(xref), self._p(dy, xref.dtype), dy_pitch, dy_c0, self._p(dx, xref.dtype), n,
                                             H, W, C, k, s, p, act, slope, _dt(xref.dtype), self._stream()), 'srgan_maxpool_bwd')
 
-    def avgpool(self, x, y, y_pitch, y_c0, n, H, W, C, k):
-        self._ck(self.lib.srgan_avgpool(self._p(x), self._p(y, x.dtype), y_pitch, y_c0, n, H, W, C, k, _dt(x.dtype),
+    def avgpool(self, x, x_pitch, y, y_pitch, y_c0, n, H, W, C, k):
+        self._ck(self.lib.srgan_avgpool(self._p(x), x_pitch, self._p(y, x.dtype), y_pitch, y_c0, n, H, W, C, k, _dt(x.dtype),
                                         self._stream()), 'srgan_avgpool')
 
-    def avgpool_bwd(self, dy, dy_pitch, dy_c0, dx, n, H, W, C, k, href, act, slope):
-        self._ck(self.lib.srgan_avgpool_bwd(self._p(dy), dy_pitch, dy_c0, self._p(dx, dy.dtype), n, H, W, C, k,
+    def avgpool_bwd(self, dy, dy_pitch, dy_c0, dx, x_pitch, n, H, W, C, k, href, act, slope):
+        self._ck(self.lib.srgan_avgpool_bwd(self._p(dy), dy_pitch, dy_c0, self._p(dx, dy.dtype), x_pitch, n, H, W, C, k,
                                             self._p(href, dy.dtype) if href is not None else None, act, slope, _dt(dy.dtype),
                                             self._stream()), 'srgan_avgpool_bwd')
 

@@ -314,33 +314,34 @@ def test_crowd_conv_shapes(ops, dt, gi):
 
 
 @pytest.mark.parametrize('dt', DT)
-@pytest.mark.parametrize('rows,pitch,c0,C', [(3 * 56 * 56, 256, 0, 96), (1000, 40, 8, 24), (77, 13, 3, 7), (5, 1920, 0, 1920)])
-def test_affine_ops(ops, dt, rows, pitch, c0, C):
+@pytest.mark.parametrize('rows,pitch,c0,C,yp', [(3 * 56 * 56, 256, 0, 96, 128), (1000, 40, 8, 24, 24), (77, 13, 3, 7, 9),
+                                                 (5, 1920, 0, 1920, 1920)])
+def test_affine_ops(ops, dt, rows, pitch, c0, C, yp):
     gen = torch.Generator().manual_seed(rows + C)
     ref = TorchOps()
     x = rnd(gen, rows * pitch, dt=dt)
     gamma, beta, mean = rnd(gen, C) + 1.5, rnd(gen, C) * 0.3, rnd(gen, C) * 0.2
     var = torch.rand(C, generator=gen) + 0.5
-    href = rnd(gen, rows * C, dt=dt)
+    href = rnd(gen, rows * yp, dt=dt)
     cu = lambda t: t.cuda()
     for mode, act, slope in ((0, 1, 0.0), (0, 0, 0.0), (1, 1, 0.0), (1, 1, 0.01)):
-        y_ref = torch.empty(rows * C, dtype=dt)
-        ref.affine(x, pitch, c0, y_ref, rows, C, gamma, beta, mean, var, 1e-5, href, mode, act, slope)
-        y = torch.empty(rows * C, dtype=dt, device='cuda')
-        ops.affine(cu(x), pitch, c0, y, rows, C, cu(gamma), cu(beta), cu(mean), cu(var), 1e-5, cu(href), mode, act, slope)
+        y_ref = rnd(gen, rows * yp, dt=dt)                  # pad columns must survive
+        y = y_ref.clone().cuda()
+        ref.affine(x, pitch, c0, y_ref, yp, rows, C, gamma, beta, mean, var, 1e-5, href, mode, act, slope)
+        ops.affine(cu(x), pitch, c0, y, yp, rows, C, cu(gamma), cu(beta), cu(mean), cu(var), 1e-5, cu(href), mode, act, slope)
         close(y, y_ref, tol(dt), f'affine mode{mode}')
-    dy = rnd(gen, rows * C, dt=dt)
+    dy = rnd(gen, rows * yp, dt=dt)
     for acc in (False, True):
         dx_ref = rnd(gen, rows * pitch, dt=dt)
         dx = dx_ref.clone().cuda()
-        ref.affine_bwd(dy, dx_ref, pitch, c0, rows, C, gamma, var, 1e-5, acc)
-        ops.affine_bwd(cu(dy), dx, pitch, c0, rows, C, cu(gamma), cu(var), 1e-5, acc)
+        ref.affine_bwd(dy, yp, dx_ref, pitch, c0, rows, C, gamma, var, 1e-5, acc)
+        ops.affine_bwd(cu(dy), yp, dx, pitch, c0, rows, C, cu(gamma), cu(var), 1e-5, acc)
         close(dx, dx_ref, tol(dt), f'affine_bwd acc{acc}')
     for sub in (True, False):
         dg_ref, db_ref = rnd(gen, C), rnd(gen, C)
         dg, db = dg_ref.clone().cuda(), db_ref.clone().cuda()
-        ref.affine_grad(dy, x, pitch, c0, rows, C, mean, var, 1e-5, dg_ref, db_ref if sub else None, sub)
-        ops.affine_grad(cu(dy), cu(x), pitch, c0, rows, C, cu(mean), cu(var), 1e-5, dg, db if sub else None, sub)
+        ref.affine_grad(dy, yp, x, pitch, c0, rows, C, mean, var, 1e-5, dg_ref, db_ref if sub else None, sub)
+        ops.affine_grad(cu(dy), yp, cu(x), pitch, c0, rows, C, cu(mean), cu(var), 1e-5, dg, db if sub else None, sub)
         t = 1e-4 if dt == torch.float32 else 1e-2
         close(dg, dg_ref, t, 'affine_grad dgamma')
         close(db, db_ref, t, 'affine_grad dbeta')
@@ -379,21 +380,21 @@ def test_copy2d_and_pools(ops, dt):
         ref.maxpool_bwd(x, dy, pitch, c0, dx_ref, n, H, W, C, k, s, p, 1, 0.0)
         ops.maxpool_bwd(cu(x), cu(dy), pitch, c0, dx, n, H, W, C, k, s, p, 1, 0.0)
         close(dx, dx_ref, tol(dt), 'maxpool_bwd')
-    for n, H, W, C, k in ((3, 8, 8, 12, 2), (2, 7, 7, 40, 7), (1, 4, 4, 3, 2)):
-        x = rnd(gen, n * H * W * C, dt=dt)
+    for n, H, W, C, k, xp in ((3, 8, 8, 12, 2, 12), (2, 7, 7, 40, 7, 64), (1, 4, 4, 3, 2, 5)):
+        x = rnd(gen, n * H * W * xp, dt=dt)
         Ho, Wo = H // k, W // k
         pitch, c0 = C + 4, 4
         y_ref = torch.zeros(n * Ho * Wo * pitch, dtype=dt)
         y = y_ref.clone().cuda()
-        ref.avgpool(x, y_ref, pitch, c0, n, H, W, C, k)
-        ops.avgpool(cu(x), y, pitch, c0, n, H, W, C, k)
+        ref.avgpool(x, xp, y_ref, pitch, c0, n, H, W, C, k)
+        ops.avgpool(cu(x), xp, y, pitch, c0, n, H, W, C, k)
         close(y, y_ref, tol(dt), 'avgpool')
         dy = rnd(gen, n * Ho * Wo * pitch, dt=dt)
         for act in (0, 1):
-            dx_ref = torch.empty(n * H * W * C, dtype=dt)
-            dx = torch.empty(n * H * W * C, dtype=dt, device='cuda')
-            ref.avgpool_bwd(dy, pitch, c0, dx_ref, n, H, W, C, k, x, act, 0.0)
-            ops.avgpool_bwd(cu(dy), pitch, c0, dx, n, H, W, C, k, cu(x), act, 0.0)
+            dx_ref = rnd(gen, n * H * W * xp, dt=dt)
+            dx = dx_ref.clone().cuda()
+            ref.avgpool_bwd(dy, pitch, c0, dx_ref, xp, n, H, W, C, k, x, act, 0.0)
+            ops.avgpool_bwd(cu(dy), pitch, c0, dx, xp, n, H, W, C, k, cu(x), act, 0.0)
             close(dx, dx_ref, tol(dt), 'avgpool_bwd')
 
 

@@ -262,9 +262,10 @@ class TorchOps:
     def _cd(t):
         return torch.float64 if t.dtype == torch.float64 else torch.float32
 
-    def affine(self, x, x_pitch, x_c0, y, rows, C, gamma, beta, mean, var, eps, href, mode, act, slope):
+    def affine(self, x, x_pitch, x_c0, y, y_pitch, rows, C, gamma, beta, mean, var, eps, href, mode, act, slope):
         """mode 0: y = act(gamma*(x-mean)/sqrt(var+eps)+beta); mode 1 (tangent): y = gamma/sqrt(var+eps)*x * act'(href).
-        x is the channel slice [x_c0, x_c0+C) of rows with pitch x_pitch; y is dense [rows, C]."""
+        x is the channel slice [x_c0, x_c0+C) of rows with pitch x_pitch; y / href are columns [0, C) of rows with pitch
+        y_pitch (columns >= C are left untouched)."""
         self.launches += 1
         cd = self._cd(x)
         xs = x.view(rows, x_pitch)[:, x_c0:x_c0 + C].to(cd)
@@ -272,26 +273,26 @@ class TorchOps:
         if mode == 0:
             v = apply_act((xs - mean.detach().to(cd)) * s + beta.detach().to(cd), act, slope)
         else:
-            v = xs * s * dact(href.view(rows, C).to(cd), act, slope)
-        y.copy_(v.reshape(-1).to(y.dtype))
+            v = xs * s * dact(href.view(rows, y_pitch)[:, :C].to(cd), act, slope)
+        y.view(rows, y_pitch)[:, :C] = v.to(y.dtype)
 
-    def affine_bwd(self, dy, dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, accumulate):
-        """dx[:, c0:c0+C] (+)= dy * gamma/sqrt(var+eps)   (dy dense [rows, C], w.r.t. the affine's pre-activation)."""
+    def affine_bwd(self, dy, dy_pitch, dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, accumulate):
+        """dx[:, c0:c0+C] (+)= dy[:, :C] * gamma/sqrt(var+eps)   (dy w.r.t. the affine's pre-activation, pitch dy_pitch)."""
         self.launches += 1
         cd = self._cd(dy)
         s = gamma.detach().to(cd) / torch.sqrt(var.detach().to(cd) + eps)
-        v = dy.view(rows, C).to(cd) * s
+        v = dy.view(rows, dy_pitch)[:, :C].to(cd) * s
         d = dx.view(rows, dx_pitch)
         if accumulate:
             d[:, dx_c0:dx_c0 + C] += v.to(dx.dtype)
         else:
             d[:, dx_c0:dx_c0 + C] = v.to(dx.dtype)
 
-    def affine_grad(self, dy, x, x_pitch, x_c0, rows, C, mean, var, eps, dgamma, dbeta, subtract_mean):
+    def affine_grad(self, dy, dy_pitch, x, x_pitch, x_c0, rows, C, mean, var, eps, dgamma, dbeta, subtract_mean):
         """dgamma[c] += sum_r dy[r,c] * (x[r,c0+c] - mean[c]*subtract_mean) / sqrt(var[c]+eps); dbeta[c] += sum_r dy[r,c]."""
         self.launches += 1
         cd = dgamma.dtype
-        d = dy.view(rows, C).to(cd)
+        d = dy.view(rows, dy_pitch)[:, :C].to(cd)
         xs = x.view(rows, x_pitch)[:, x_c0:x_c0 + C].to(cd)
         if subtract_mean:
             xs = xs - mean.detach().to(cd)
@@ -339,24 +340,24 @@ class TorchOps:
         g = g.permute(0, 2, 1).reshape(-1) * dact(xref.to(cd), act, slope)
         dx.copy_(g.to(dx.dtype))
 
-    def avgpool(self, x, y, y_pitch, y_c0, n, H, W, C, k):
-        """y[:, c0:c0+C] = mean over non-overlapping k x k windows of x (dense [n,H,W,C])."""
+    def avgpool(self, x, x_pitch, y, y_pitch, y_c0, n, H, W, C, k):
+        """y[:, c0:c0+C] = mean over non-overlapping k x k windows of x[..., :C] (x: [n,H,W,x_pitch])."""
         self.launches += 1
         cd = self._cd(x)
         Ho, Wo = H // k, W // k
-        v = x.view(n, Ho, k, Wo, k, C).to(cd).mean(dim=(2, 4))
+        v = x.view(n, Ho, k, Wo, k, x_pitch)[..., :C].to(cd).mean(dim=(2, 4))
         y.view(n * Ho * Wo, y_pitch)[:, y_c0:y_c0 + C] = v.reshape(n * Ho * Wo, C).to(y.dtype)
 
-    def avgpool_bwd(self, dy, dy_pitch, dy_c0, dx, n, H, W, C, k, href, act, slope):
-        """dx[n,h,w,c] = dy[n,h/k,w/k,c0+c] / k^2 * act'(href[n,h,w,c])."""
+    def avgpool_bwd(self, dy, dy_pitch, dy_c0, dx, x_pitch, n, H, W, C, k, href, act, slope):
+        """dx[n,h,w,c] = dy[n,h/k,w/k,c0+c] / k^2 * act'(href[n,h,w,c]) for c < C (dx, href: [n,H,W,x_pitch])."""
         self.launches += 1
         cd = self._cd(dy)
         Ho, Wo = H // k, W // k
         d = dy.view(n * Ho * Wo, dy_pitch)[:, dy_c0:dy_c0 + C].to(cd).view(n, Ho, 1, Wo, 1, C) / (k * k)
-        g = d.expand(n, Ho, k, Wo, k, C).reshape(-1)
+        g = d.expand(n, Ho, k, Wo, k, C).reshape(n * H * W, C)
         if href is not None and act != ACT_NONE:
-            g = g * dact(href.to(cd), act, slope)
-        dx.copy_(g.to(dx.dtype))
+            g = g * dact(href.view(n * H * W, x_pitch)[:, :C].to(cd), act, slope)
+        dx.view(n * H * W, x_pitch)[:, :C] = g.to(dx.dtype)
 
     def crowd_loss(self, pred, density, maps, map_label, B, HW, order, scale, map_mult, loss_out, dpred, dm):
         """crowd/srgan.py:247-254 on rows [0,B): loss += scale * sum_b (|pred_b - sum(density_b)|^o + map_mult * m_b^o),
