@@ -178,6 +178,10 @@ int srgan_avgpool(const void* x, int x_pitch, void* y, int y_pitch, int y_c0, in
                   void* stream);
 int srgan_avgpool_bwd(const void* dy, int dy_pitch, int dy_c0, void* dx, int x_pitch, int n, int H, int W, int C, int k,
                       const void* href, int act, float slope, int dtype, void* stream);
+/* MapModule.map_transposed_conv_layer (crowd/models.py:768-769,780): a ConvTranspose2d whose kernel equals its stride and
+ * whose output has one channel is a [pixels x C] x [C x k*k] GEMM (srgan_conv_down with a 1x1 geometry) followed by this
+ * rearrangement: img[n, i*k+r, j*k+s] = blk[n, i, j, r*k+s]  (inverse != 0: the other direction, for the backward pass). */
+int srgan_depth_to_space(const void* src, void* dst, int n, int Hs, int Ws, int k, int inverse, int dtype, void* stream);
 /* CrowdExperiment.labeled_loss_function, crowd/srgan.py:247-254, on B samples:
  * loss += scale * sum_b (|pred_b - sum(density_b)|^order + map_mult * m_b^order), m_b = sum_hw mean_c |map_c - map_label|;
  * dpred_b = dLoss/dpred_b, dm_b = dLoss/dm_b.  maps: HOST array of nmaps (<= 4) device pointers, [B, HW] each. */

@@ -24,6 +24,12 @@ int umma_conv(int mode, const void* src, const void* W, void* out, int n, const 
               int bias_mod, const void* href, int epi, int act, float slope, cudaStream_t st);
 int umma_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, cudaStream_t st);
 
+// skinny.cu : few outputs over a long full-extent reduction axis (MapModule.linear1, the count feature layer)
+bool skinny_eligible(const srgan_geom* g);
+int skinny_conv(int mode, const void* src, const void* W, void* out, int n, const srgan_geom* g, const float* bias, int bias_mod,
+                const void* href, int epi, int act, float slope, int dtype, cudaStream_t st);
+int skinny_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, int dtype, cudaStream_t st);
+
 static int check_geom(const char* who, const srgan_geom* g, int n) {
     if (!g || n < 0 || g->Hs <= 0 || g->Ws <= 0 || g->Ca <= 0 || g->Hl <= 0 || g->Wl <= 0 || g->Cb <= 0 || g->R <= 0 ||
         g->S <= 0 || g->stride <= 0 || g->pad < 0) {
@@ -61,6 +67,8 @@ static int conv_common(int mode, const char* who, const void* src, const void* W
     if (n == 0) return SRGAN_OK;
     cudaStream_t st = (cudaStream_t)stream;
     t_last_tensor = 0;
+    if (skinny_eligible(g) && !g_force_simt.load())
+        return skinny_conv(mode, src, W, out, n, g, bias, bias_mod, href, epi, act, slope, dtype, st);
     if (dtype == SRGAN_BF16 && !g_force_simt.load()) {
         int took = umma_conv(mode, src, W, out, n, g, bias, bias_mod, href, epi, act, slope, st);
         if (took < 0) return took;
@@ -87,6 +95,7 @@ int srgan_conv_wgrad(const void* S, const void* L, float* dW, int n, const srgan
     if (n == 0) return SRGAN_OK;
     cudaStream_t st = (cudaStream_t)stream;
     t_last_tensor = 0;
+    if (skinny_eligible(g) && !g_force_simt.load()) return skinny_wgrad(S, L, dW, n, g, dtype, st);
     if (dtype == SRGAN_BF16 && !g_force_simt.load()) {
         int took = umma_wgrad(S, L, dW, n, g, st);
         if (took < 0) return took;

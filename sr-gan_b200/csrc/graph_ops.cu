@@ -311,6 +311,23 @@ __global__ void __launch_bounds__(256) crowd_map_grad_kernel(const T* __restrict
     }
 }
 
+// depth-to-space of a one-channel map: img[n, i*k+r, j*k+s] <-> blk[n, i, j, r*k+s]   (one thread per image pixel)
+template <typename T>
+__global__ void __launch_bounds__(256) depth_to_space_kernel(const T* __restrict__ src, T* __restrict__ dst, int n, int Hs, int Ws,
+                                                             int k, int inverse) {
+    const int Wl = Ws * k, Hl = Hs * k;
+    const long long total = (long long)n * Hl * Wl;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % Wl);
+        long long t = i / Wl;
+        const int y = (int)(t % Hl);
+        const long long b = t / Hl;
+        const long long blk = ((b * Hs + y / k) * Ws + x / k) * (k * k) + (y % k) * k + (x % k);
+        if (inverse) dst[blk] = src[i];
+        else dst[i] = src[blk];
+    }
+}
+
 inline bool vec_ok(int C, int p0, int o0, int p1 = 0, int o1 = 0) { return ((C | p0 | o0 | p1 | o1) & 3) == 0; }
 
 }  // namespace
@@ -434,6 +451,15 @@ int srgan_avgpool_bwd(const void* dy, int dy_pitch, int dy_c0, void* dx, int x_p
     cudaStream_t st = (cudaStream_t)stream;
     DISPATCH_T(dtype, avgpool_bwd_kernel<T><<<ew_grid((long long)n * H * W * C), 256, 0, st>>>((const T*)dy, dy_pitch, dy_c0, (T*)dx, x_pitch, n, H, W, C, k, (const T*)(act == SRGAN_ACT_NONE ? nullptr : href), act, slope));
     SRGAN_CHECK_LAUNCH("avgpool_bwd_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_depth_to_space(const void* src, void* dst, int n, int Hs, int Ws, int k, int inverse, int dtype, void* stream) {
+    SRGAN_REQUIRE(src && dst && n >= 0 && Hs > 0 && Ws > 0 && k > 0, "srgan_depth_to_space: bad arguments");
+    if (n == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_T(dtype, depth_to_space_kernel<T><<<ew_grid((long long)n * Hs * Ws * k * k), 256, 0, st>>>((const T*)src, (T*)dst, n, Hs, Ws, k, inverse));
+    SRGAN_CHECK_LAUNCH("depth_to_space_kernel");
     return SRGAN_OK;
 }
 

@@ -167,12 +167,18 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], const UmmaConv
     for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
     if (p.epi == SRGAN_EPI_BIAS_ACT) {
         if (p.bias != nullptr) {
-            const int bi = p.bias_mod ? cbase % p.bias_mod : cbase;
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + bi);
+            if (p.bias_mod == 1) {                // one scalar bias for every column (ConvTranspose2d with out_channels = 1)
+                const float b = __ldg(p.bias);
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                const float4 b = __ldg(bp + g);
-                f[g * 4] += b.x; f[g * 4 + 1] += b.y; f[g * 4 + 2] += b.z; f[g * 4 + 3] += b.w;
+                for (int e = 0; e < 32; ++e) f[e] += b;
+            } else {
+                const int bi = p.bias_mod ? cbase % p.bias_mod : cbase;
+                const float4* bp = reinterpret_cast<const float4*>(p.bias + bi);
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const float4 b = __ldg(bp + g);
+                    f[g * 4] += b.x; f[g * 4 + 1] += b.y; f[g * 4 + 2] += b.z; f[g * 4 + 3] += b.w;
+                }
             }
         }
         if (p.act == SRGAN_ACT_LEAKY) {
@@ -677,7 +683,7 @@ int umma_conv(int mode, const void* src, const void* W, void* out, int n, const 
     if (!pick_patch(Wm, Hm, TILE_M, 16, p.TW, p.TH, p.TN)) return 0;
     if (mode == 0 && (p.TW * g->stride > 256 || p.TH * g->stride > 256)) return 0;
     if (((uintptr_t)src & 15) || ((uintptr_t)W & 15) || ((uintptr_t)out & 15) || (href && ((uintptr_t)href & 15))) return 0;
-    if (bias && (((uintptr_t)bias & 15) || (bias_mod % 32) != 0)) return 0;       // epilogue reads bias as float4 runs of 32
+    if (bias && bias_mod != 1 && (((uintptr_t)bias & 15) || (bias_mod % 32) != 0)) return 0;   // epilogue reads bias as float4 runs of 32
     p.mode = mode; p.n = n; p.Hm = Hm; p.Wm = Wm;
     p.tiles_w = Wm / p.TW; p.tiles_h = Hm / p.TH;
     const int tiles_n = (n + p.TN - 1) / p.TN;

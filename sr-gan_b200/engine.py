@@ -56,6 +56,10 @@ def _strides_for(layer_kind: str, dims, Ca, Cb, R, S):
         zb, c, k, _ = dims
         wd = (1, zb, k * c * zb, c * zb)
         wu = (Ca, 1, k * c, c)
+    elif layer_kind == 'ct_gemm':   # master[c][1][r][s] (ConvTranspose2d, kernel = stride, one output channel) as a Linear
+        _, _, k, _ = dims           # with a = (r, s), b = c:  Wd[a][b], Wu[b][a]
+        wd = (1, 0, k * Cb, Cb)
+        wu = (Ca, 0, k, 1)
     else:
         raise ValueError(layer_kind)
     return wd, wu
@@ -468,6 +472,8 @@ class Engine:
                 ops.maxpool(x, xref, y, db.ch, op.c0, n, op.H, op.W, op.C, op.k, op.stride, op.pad)
             elif op.kind == 'avgpool':
                 ops.avgpool(x, sb.ch, y, db.ch, op.c0, n, op.H, op.W, op.C, op.k)
+            elif op.kind == 'shuffle':
+                ops.depth_to_space(x, y, n, op.H, op.W, op.k, False)
             else:
                 raise ValueError(op.kind)
 
@@ -489,10 +495,10 @@ class Engine:
             is_input = op.src == net.input_buf
             dx = None if is_input else R(deltas[op.src], sb, lo, hi)
             xa = R(acts[op.src], sb, mlo, mlo + n)
+            if hook is not None and op.dst in net.map_bufs:
+                hook(op.dst)
             if op.kind == 'conv':
                 l = op.layer
-                if hook is not None and op.dst in net.map_bufs:
-                    hook(op.dst)
                 if weight_grads:
                     self._wgrad_layer(st, l, R(acts[op.src], sb, wlo, whi), R(deltas[op.dst], db, wlo, whi),
                                       (whi - wlo) * l.gemm_rows, lo=wlo)
@@ -523,6 +529,8 @@ class Engine:
                 ops.maxpool_bwd(xa, dy, db.ch, op.c0, dx, n, op.H, op.W, op.C, op.k, op.stride, op.pad, sb.act, sb.slope)
             elif op.kind == 'avgpool':
                 ops.avgpool_bwd(dy, db.ch, op.c0, dx, sb.ch, n, op.H, op.W, op.C, op.k, xa, sb.act, sb.slope)
+            elif op.kind == 'shuffle':    # a permutation: both sides are w.r.t. the same pre-activation
+                ops.depth_to_space(dy, dx, n, op.H, op.W, op.k, True)
             else:
                 raise ValueError(op.kind)
 

@@ -73,7 +73,7 @@ class Layer:
     def macs_per_sample(self):
         """Algorithmic MACs (master dims; channel padding of the kernel operands is not counted)."""
         d0, d1, d2, d3 = self.master_dims
-        if self.master_kind == 'conv':
+        if self.master_kind in ('conv', 'ct_gemm'):
             return d0 * d1 * d2 * d3 * self.geom.Hs * self.geom.Ws * self.gemm_rows
         return d0 * d1 * d2 * d3
 
@@ -132,7 +132,8 @@ class Op:
       'affine'  eval-mode BatchNorm + ReLU: dst[:, :C] = relu(gamma*(src[:, c0:c0+C]-mean)/sqrt(var+eps)+beta), `name` = BN prefix;
       'copy'    dst[:, c0:c0+C] = src (dense C)        (concat write / feature slice write);
       'read'    dst (dense C)   = src[:, c0:c0+C]      (tap of a concat buffer);
-      'maxpool' / 'avgpool'  src dense [H, W, C] -> dst[:, c0:c0+C] at [H', W'] (k, stride, pad)."""
+      'maxpool' / 'avgpool'  src dense [H, W, C] -> dst[:, c0:c0+C] at [H', W'] (k, stride, pad);
+      'shuffle' depth-to-space of a one-channel map: dst[(i*k+r), (j*k+s)] = src[(i, j), r*k+s] (H x W blocks of k x k)."""
     kind: str
     src: str
     dst: str
@@ -341,9 +342,14 @@ def knn_densenet_cat(block_config=(6, 12, 48, 32), growth_rate=32, num_init_feat
         pre = f'map_module{i}'
         buf(f't{i}', hi * hi, ci)
         ops.append(Op('read', cat, f't{i}', C=ci, c0=0))
+        # ConvTranspose2d(ci, 1, k, stride k): a [pixels x ci] x [ci x k*k] GEMM (one scalar bias) + depth-to-space
+        buf(f'mapb{i}', hi * hi, k * k, **LK)
+        l = Layer(pre + '.map_transposed_conv_layer', 'down', linear_geom(k * k, ci), ACT_LEAKY, 0.01, (ci, 1, k, k),
+                  master_kind='ct_gemm', bias_mod=1, has_bias=True, gemm_rows=hi * hi)
+        layers.append(l)
+        ops.append(Op('conv', f't{i}', f'mapb{i}', layer=l))
         buf(f'map{i}', L * L, 1, **LK)
-        conv(pre + '.map_transposed_conv_layer', f't{i}', f'map{i}', Geom(hi, hi, ci, L, L, 1, k, k, k, 0), 'up',
-             (ci, 1, k, k), bias=True, **LK)
+        ops.append(Op('shuffle', f'mapb{i}', f'map{i}', H=hi, W=hi, k=k))
         maps.append(f'map{i}')
         src, hh, cin = f'map{i}', L, 1
         for j, cout in enumerate((8, 16, 32), 1):

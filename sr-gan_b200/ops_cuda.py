@@ -28,7 +28,7 @@ _EXPORTS = (
     'srgan_distance', 'srgan_feature_norm_seed', 'srgan_gradnorm_penalty', 'srgan_gp_feature_seed', 'srgan_adam',
     'srgan_repack', 'srgan_im2col', 'srgan_col2im', 'srgan_adam_prepare', 'srgan_coefficient_step',
     'srgan_coefficient_step_workspace_bytes', 'srgan_affine', 'srgan_affine_bwd', 'srgan_affine_grad', 'srgan_copy2d',
-    'srgan_maxpool', 'srgan_maxpool_bwd', 'srgan_avgpool', 'srgan_avgpool_bwd', 'srgan_crowd_loss', 'srgan_crowd_map_grad',
+    'srgan_maxpool', 'srgan_maxpool_bwd', 'srgan_avgpool', 'srgan_avgpool_bwd', 'srgan_crowd_loss', 'srgan_crowd_map_grad', 'srgan_depth_to_space',
 )
 
 _lib = None
@@ -89,6 +89,7 @@ def load_library(path: str = LIB_PATH):
     lib.srgan_avgpool.argtypes = [vp, c_int, vp, c_int, c_int] + [c_int] * 5 + [c_int, vp]
     lib.srgan_avgpool_bwd.argtypes = [vp, c_int, c_int, vp, c_int] + [c_int] * 5 + [vp, c_int, c_f, c_int, vp]
     lib.srgan_crowd_loss.argtypes = [vp, vp, pp, c_int, vp, c_int, c_ll, c_int, c_f, c_f, vp, vp, vp, c_int, vp]
+    lib.srgan_depth_to_space.argtypes = [vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, vp]
     lib.srgan_crowd_map_grad.argtypes = [vp, vp, vp, vp, c_int, c_ll, c_int, c_int, c_f, c_int, vp]
     for name in _EXPORTS[5:]:
         getattr(lib, name).restype = c_int
@@ -345,3 +346,7 @@ class CudaOps:
         self._ck(self.lib.srgan_crowd_map_grad(self._p(mp), self._p(map_label.detach(), torch.float32), self._p(dm, torch.float32),
                                                self._p(delta, mp.dtype), B, HW, nmaps, act, slope, _dt(mp.dtype),
                                                self._stream()), 'srgan_crowd_map_grad')
+
+    def depth_to_space(self, src, dst, n, Hs, Ws, k, inverse):
+        self._ck(self.lib.srgan_depth_to_space(self._p(src), self._p(dst, src.dtype), n, Hs, Ws, k, int(bool(inverse)),
+                                               _dt(src.dtype), self._stream()), 'srgan_depth_to_space')

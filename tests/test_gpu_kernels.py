@@ -421,3 +421,50 @@ def test_crowd_loss_ops(ops, dt, order):
     ref.crowd_map_grad(maps[1], label, dm_ref, d_ref, B, HW, 3, 1, 0.01)
     ops.crowd_map_grad(maps[1].cuda(), label.cuda(), dm_ref.cuda(), d, B, HW, 3, 1, 0.01)
     close(d, d_ref, tol(dt), 'crowd_map_grad')
+
+
+@pytest.mark.parametrize('dt', DT)
+def test_depth_to_space_and_scalar_bias_gemm(ops, dt):
+    """MapModule ConvTranspose2d (kernel = stride, one output channel) = GEMM with ONE scalar bias (bias_mod 1, tcgen05 path
+    in bf16) + depth-to-space; and the skinny full-extent pair (K = 25088 -> 20 outputs) at an odd row count."""
+    gen = torch.Generator().manual_seed(4)
+    ref = TorchOps()
+    n, Hs, Ws, k = 3, 7, 5, 4
+    blk = rnd(gen, n * Hs * Ws * k * k, dt=dt)
+    img_ref, img = torch.empty_like(blk), torch.empty_like(blk, device='cuda')
+    ref.depth_to_space(blk, img_ref, n, Hs, Ws, k, False)
+    ops.depth_to_space(blk.cuda(), img, n, Hs, Ws, k, False)
+    close(img, img_ref, 1e-7, 'depth_to_space')
+    back = torch.empty_like(blk, device='cuda')
+    ops.depth_to_space(img, back, n, Hs, Ws, k, True)
+    close(back, blk, 1e-7, 'space_to_depth')
+    g = Geom(1, 1, 64, 1, 1, 128, 1, 1, 1, 0)
+    rows = 3 * 28 * 28
+    L, Wd, bias = rnd(gen, rows * 128, dt=dt), (rnd(gen, 64 * 128) * 0.2).to(dt), rnd(gen, 1)
+    o_ref, o = torch.empty(rows * 64, dtype=dt), torch.empty(rows * 64, dtype=dt, device='cuda')
+    ref.conv_down(L, Wd, o_ref, rows, g, bias, 1, None, 0, 1, 0.01)
+    ops.conv_down(L.cuda(), Wd.cuda(), o, rows, g, bias.cuda(), 1, None, 0, 1, 0.01)
+    close(o, o_ref, tol(dt), 'scalar-bias gemm')
+    if dt == torch.bfloat16:
+        assert ops.lib.srgan_last_path_tensor() == 1
+    g = Geom(1, 1, 20, 28, 28, 32, 28, 28, 1, 0)
+    n = 5
+    K = 28 * 28 * 32
+    L, S = rnd(gen, n * K, dt=dt), rnd(gen, n * 20, dt=dt)
+    Wd = (rnd(gen, 20 * K) * 0.05).to(dt)
+    Wu = Wd.view(20, K).t().contiguous().view(-1)
+    b = rnd(gen, 20)
+    o_ref, o = torch.empty(n * 20, dtype=dt), torch.empty(n * 20, dtype=dt, device='cuda')
+    ref.conv_down(L, Wd, o_ref, n, g, b, 0, None, 0, 1, 0.01)
+    ops.conv_down(L.cuda(), Wd.cuda(), o, n, g, b.cuda(), 0, None, 0, 1, 0.01)
+    close(o, o_ref, tol(dt), 'skinny down')
+    href = rnd(gen, n * K, dt=dt)
+    o_ref, o = torch.empty(n * K, dtype=dt), torch.empty(n * K, dtype=dt, device='cuda')
+    ref.conv_up(S, Wu, o_ref, n, g, None, 0, href, 1, 1, 0.01)
+    ops.conv_up(S.cuda(), Wu.cuda(), o, n, g, None, 0, href.cuda(), 1, 1, 0.01)
+    close(o, o_ref, tol(dt), 'skinny up')
+    dW_ref = rnd(gen, 20 * K)
+    dW = dW_ref.clone().cuda()
+    ref.conv_wgrad(S, L, dW_ref, n, g)
+    ops.conv_wgrad(S.cuda(), L.cuda(), dW, n, g)
+    close(dW, dW_ref, tol(dt) * 2, 'skinny wgrad')

@@ -174,7 +174,7 @@ def test_coefficient_persistent_kernel_matches_generic_kernels(method, B):
             r.gan_step(xc, yc, uc, i, noise=(zc, ac, z2c))
         if i == 0:
             assert rb.engine.ops.launches - l0 > 50 + 2      # ra: exactly two launches
-        check_scalars(ra.scalars(), rb.scalars(), 1e-4, (method, B, i))
+        check_scalars(ra.scalars(), rb.scalars(), 1e-4 if i == 0 else 1e-3, (method, B, i))
         assert rb.scalars()['gradient_penalty'] > 0
     for net in ('D', 'G', 'DNN'):
         sa, sb = ra.modules[net].state_dict(), rb.modules[net].state_dict()

@@ -379,3 +379,12 @@ class TorchOps:
         v = mp.view(B, HW).to(cd)
         g = dm.view(B, 1) / nmaps * torch.sign(v - map_label.detach().reshape(B, HW).to(cd)) * dact(v, act, slope)
         delta.view(B, HW).add_(g.to(delta.dtype))
+
+    def depth_to_space(self, src, dst, n, Hs, Ws, k, inverse):
+        """img[n, i*k+r, j*k+s] = blk[n, i, j, r*k+s]; inverse: blk from img."""
+        self.launches += 1
+        if not inverse:
+            v = src.view(n, Hs, Ws, k, k).permute(0, 1, 3, 2, 4).reshape(-1)
+        else:
+            v = src.view(n, Hs, k, Ws, k).permute(0, 1, 3, 2, 4).reshape(-1)
+        dst.copy_(v)

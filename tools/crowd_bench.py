@@ -23,6 +23,42 @@ torch.cuda.synchronize()
 print(f'warm-up (3 steps incl. graph capture): {time.perf_counter() - t0:.2f} s', flush=True)
 l0 = exp.runner.engine.ops.launches
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+if os.environ.get('SRGAN_OPTIME', '0') == '1':
+    # per-op device time (CUDA events around every C-ABI call of one eager step), grouped by op and shape
+    import collections
+    ops = exp.runner.engine.ops
+    exp.runner.use_cuda_graph = False
+    recs = []
+    names = ['conv_down', 'conv_up', 'conv_wgrad', 'affine', 'affine_bwd', 'affine_grad', 'copy2d', 'maxpool', 'maxpool_bwd',
+             'avgpool', 'avgpool_bwd', 'colsum', 'adam', 'seed_rows', 'rowdot', 'crowd_loss', 'crowd_map_grad', 'im2col', 'col2im',
+             'nchw_to_nhwc', 'interpolate', 'gradnorm_penalty', 'feature_norm_seed', 'gp_feature_seed', 'distance', 'repack']
+    def wrap(name, fn):
+        def w(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r = fn(*a, **k); e1.record()
+            key = name
+            if name.startswith('conv_'):
+                g, n = a[4], a[3]
+                key = f'{name} n={n} {g.Hs}x{g.Ws}x{g.Ca}<-{g.Hl}x{g.Wl}x{g.Cb} k{g.R}s{g.stride} tensor={ops.lib.srgan_last_path_tensor()}'
+            recs.append((key, name, e0, e1))
+            return r
+        return w
+    for nme in names:
+        setattr(ops, nme, wrap(nme, getattr(ops, nme)))
+    exp.dnn_training_step(x, y, 9); exp.gan_training_step(x, y, u, 9)
+    torch.cuda.synchronize()
+    by_key, by_name = collections.defaultdict(lambda: [0, 0.0]), collections.defaultdict(lambda: [0, 0.0])
+    for key, name, e0, e1 in recs:
+        t = e0.elapsed_time(e1)
+        by_key[key][0] += 1; by_key[key][1] += t; by_name[name][0] += 1; by_name[name][1] += t
+    tot = sum(v[1] for v in by_name.values())
+    print(f'op-timed eager step: {tot:.1f} ms in {len(recs)} calls')
+    for k, (c, t) in sorted(by_name.items(), key=lambda kv: -kv[1][1]):
+        print(f'  {t:9.2f} ms {100 * t / tot:5.1f}% {c:5d}  {k}')
+    print('top shapes:')
+    for k, (c, t) in sorted(by_key.items(), key=lambda kv: -kv[1][1])[:40]:
+        print(f'  {t:9.2f} ms {100 * t / tot:5.1f}% {c:5d}  {k}')
+    sys.exit(0)
 prof = os.environ.get('SRGAN_PROFILE', '0') == '1'       # ncu --profile-from-start off: only the timed steps are captured
 if prof:
     torch.cuda.profiler.start()
