@@ -139,6 +139,11 @@ int srgan_adam_prepare(float* state3, double lr, double beta1, double beta2, voi
 int srgan_adam(float* param, const float* grad, float* m, float* v, const int* dims4, const long long* gstrides4,
                void* out1, const long long* o1strides4, void* out2, const long long* o2strides4, int out_dtype,
                const float* state3, float beta1, float beta2, float eps, float weight_decay, void* stream);
+/* the same update for many small tensors that have no kernel-layout copies (biases, BatchNorm weight / bias) in one launch.
+ * table: DEVICE array [n_tensors][4] of int64 = {param pointer, offset into grad, offset into m and v, element count};
+ * one CTA per tensor.  Moments and gradients are slices of the flat buffers grad / m / v. */
+int srgan_adam_multi(const long long* table, int n_tensors, const float* grad, float* m, float* v, const float* state3,
+                     float beta1, float beta2, float eps, float weight_decay, void* stream);
 /* layout copies only (initial weights / after load_models, srgan.py:221-251) */
 int srgan_repack(const float* param, const int* dims4, void* out1, const long long* o1strides4, void* out2,
                  const long long* o2strides4, int out_dtype, void* stream);

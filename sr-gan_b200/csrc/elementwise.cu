@@ -617,6 +617,31 @@ static inline int ew_grid(long long work_items, int block) {
 // ============================================================================================================
 // C ABI
 // ============================================================================================================
+// ------------------------------------------------------------------------------------------------------------
+// adam_multi: torch.optim.Adam on many small tensors without kernel-layout copies (biases, BatchNorm weight / bias) in ONE
+// launch: block = tensor (table row: {param pointer, gradient offset, moment offset, element count})
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) adam_multi_kernel(const long long* __restrict__ table, const float* __restrict__ grad,
+                                                         float* __restrict__ m, float* __restrict__ v,
+                                                         const float* __restrict__ state, float b1, float b2, float eps, float wd) {
+    const long long* row = table + 4LL * blockIdx.x;
+    float* p = reinterpret_cast<float*>(row[0]);
+    const float* g = grad + row[1];
+    float* mm = m + row[2];
+    float* vv = v + row[2];
+    const int n = (int)row[3];
+    const float step_size = state[1], isb = state[2];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float gr = g[i];
+        const float pv = p[i];
+        if (wd != 0.f) gr = fmaf(wd, pv, gr);
+        const float m1 = b1 * mm[i] + (1.f - b1) * gr;
+        const float v1 = b2 * vv[i] + (1.f - b2) * gr * gr;
+        mm[i] = m1; vv[i] = v1;
+        p[i] = pv - step_size * (m1 / (sqrtf(v1) * isb + eps));
+    }
+}
+
 extern "C" {
 
 int srgan_colsum(const void* X, long long rows, int cols, float* out, int mod, const float* rowscale, int dtype,
@@ -899,6 +924,16 @@ int srgan_repack(const float* param, const int* dims4, void* out1, const long lo
     else
         adam_kernel<bf16, false><<<grid, 256, 0, st>>>(const_cast<float*>(param), nullptr, nullptr, nullptr, dm, (bf16*)out1, (bf16*)out2, nullptr, 0.f, 0.f, 0.f, 0.f);
     SRGAN_CHECK_LAUNCH("repack_kernel");
+    return SRGAN_OK;
+}
+
+
+int srgan_adam_multi(const long long* table, int n_tensors, const float* grad, float* m, float* v, const float* state3,
+                     float beta1, float beta2, float eps, float weight_decay, void* stream) {
+    SRGAN_REQUIRE(table && grad && m && v && state3 && n_tensors >= 0, "srgan_adam_multi: bad arguments");
+    if (n_tensors == 0) return SRGAN_OK;
+    adam_multi_kernel<<<n_tensors, 128, 0, (cudaStream_t)stream>>>(table, grad, m, v, state3, beta1, beta2, eps, weight_decay);
+    SRGAN_CHECK_LAUNCH("adam_multi_kernel");
     return SRGAN_OK;
 }
 

@@ -224,8 +224,95 @@ static int launch_conv_gemm(int mode, const T* src, const T* W, T* out, int n, c
     return SRGAN_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// direct `up` for image-side layers (Cb <= 4 output channels, e.g. the data-gradient of the crowd stem Conv2d(3, 64, k7 s2 p3),
+// crowd/models.py:1075): as a GEMM the N axis would be 3 wide.  One thread per large-side pixel, all Cb channels in
+// registers, weights staged in shared memory, S rows read as 4-wide vectors.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, int CB>
+__global__ void __launch_bounds__(256) direct_up_kernel(const T* __restrict__ S, const T* __restrict__ Wu, T* __restrict__ out,
+                                                        const float* __restrict__ bias, int bias_mod, const T* __restrict__ href,
+                                                        int epi, int act, float slope, ConvP p) {
+    extern __shared__ float wsm[];                 // [CB][R][S][Ca]
+    const int wn = CB * p.R * p.S * p.Ca;
+    for (int i = threadIdx.x; i < wn; i += 256) wsm[i] = to_f(Wu[i]);
+    __syncthreads();
+    const long long total = (long long)p.n * p.Hl * p.Wl;
+    const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (pix >= total) return;
+    const int iw = (int)(pix % p.Wl);
+    const long long t = pix / p.Wl;
+    const int ih = (int)(t % p.Hl);
+    const long long b = t / p.Hl;
+    float acc[CB];
+#pragma unroll
+    for (int c = 0; c < CB; ++c) acc[c] = 0.f;
+    const int tap = p.R * p.S * p.Ca;              // stride between output channels in wsm
+    for (int r = (ih + p.pad) % p.stride; r < p.R; r += p.stride) {
+        const int oh = (ih + p.pad - r) / p.stride;
+        if (ih + p.pad - r < 0) break;
+        if (oh >= p.Hs) continue;
+        for (int s = (iw + p.pad) % p.stride; s < p.S; s += p.stride) {
+            const int ow = (iw + p.pad - s) / p.stride;
+            if (iw + p.pad - s < 0) break;
+            if (ow >= p.Ws) continue;
+            const T* sp = S + ((b * p.Hs + oh) * p.Ws + ow) * p.Ca;
+            const float* wp = wsm + (r * p.S + s) * p.Ca;
+            for (int a = 0; a < p.Ca; a += 4) {
+                const float4 v = ld4(sp + a);
+#pragma unroll
+                for (int c = 0; c < CB; ++c) {
+                    const float4 w = *reinterpret_cast<const float4*>(wp + c * tap + a);
+                    acc[c] += v.x * w.x + v.y * w.y + v.z * w.z + v.w * w.w;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+        const long long o = pix * CB + c;
+        float v = acc[c];
+        if (epi == SRGAN_EPI_BIAS_ACT) {
+            if (bias) v += bias[bias_mod ? c % bias_mod : c];
+            v = act_fwd(v, act, slope);
+        } else if (href && act != SRGAN_ACT_NONE) {
+            v *= act_bwd(to_f(href[o]), act, slope);
+        }
+        out[o] = from_f<T>(v);
+    }
+}
+
+template <typename T>
+static int launch_direct_up(const T* S, const T* Wu, T* out, int n, const srgan_geom* g, const float* bias, int bias_mod,
+                            const T* href, int epi, int act, float slope, cudaStream_t st) {
+    ConvP p{n, g->Hs, g->Ws, g->Ca, g->Hl, g->Wl, g->Cb, g->R, g->S, g->stride, g->pad};
+    const size_t smem = (size_t)g->Cb * g->R * g->S * g->Ca * sizeof(float);
+    const long long total = (long long)n * g->Hl * g->Wl;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    switch (g->Cb) {
+        case 1: direct_up_kernel<T, 1><<<grid, 256, smem, st>>>(S, Wu, out, bias, bias_mod, href, epi, act, slope, p); break;
+        case 2: direct_up_kernel<T, 2><<<grid, 256, smem, st>>>(S, Wu, out, bias, bias_mod, href, epi, act, slope, p); break;
+        case 3: direct_up_kernel<T, 3><<<grid, 256, smem, st>>>(S, Wu, out, bias, bias_mod, href, epi, act, slope, p); break;
+        default: direct_up_kernel<T, 4><<<grid, 256, smem, st>>>(S, Wu, out, bias, bias_mod, href, epi, act, slope, p); break;
+    }
+    SRGAN_CHECK_LAUNCH("direct_up_kernel");
+    return SRGAN_OK;
+}
+
+static bool direct_up_eligible(int mode, const srgan_geom* g, int n) {
+    return mode == 1 && g->Cb <= 4 && g->Ca % 4 == 0 && (size_t)g->Cb * g->R * g->S * g->Ca * sizeof(float) <= 48 * 1024 &&
+           (long long)n * g->Hl * g->Wl >= 1024;
+}
+
 int simt_conv(int mode, const void* src, const void* W, void* out, int n, const srgan_geom* g, const float* bias,
               int bias_mod, const void* href, int epi, int act, float slope, int dtype, cudaStream_t st) {
+    if (direct_up_eligible(mode, g, n)) {
+        if (dtype == SRGAN_F32)
+            return launch_direct_up<float>((const float*)src, (const float*)W, (float*)out, n, g, bias, bias_mod, (const float*)href,
+                                           epi, act, slope, st);
+        return launch_direct_up<bf16>((const bf16*)src, (const bf16*)W, (bf16*)out, n, g, bias, bias_mod, (const bf16*)href, epi,
+                                      act, slope, st);
+    }
     if (dtype == SRGAN_F32)
         return launch_conv_gemm<float>(mode, (const float*)src, (const float*)W, (float*)out, n, g, bias, bias_mod,
                                        (const float*)href, epi, act, slope, st);

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) skinny_down_kernel(const T* __restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(256) skinny_up_kernel(const T* __restrict__ S, const T* __restrict__ Wu, T* __restrict__ out,
                                                         const float* __restrict__ bias, int bias_mod, const T* __restrict__ href,
-                                                        int epi, int act, float slope, int Ca, long long K) {
+                                                        int epi, int act, float slope, int Ca, int Cb, long long K) {
     __shared__ float s[CA_MAX];
     const int row = blockIdx.y;
     if (threadIdx.x < Ca) s[threadIdx.x] = to_f(S[(long long)row * Ca + threadIdx.x]);
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) skinny_up_kernel(const T* __restrict__ S,
     }
     const long long o = (long long)row * K + k;
     if (epi == SRGAN_EPI_BIAS_ACT) {
-        if (bias) v += bias[bias_mod ? (int)(k % bias_mod) : (int)k];
+        if (bias) { const int b = (int)(k % Cb); v += bias[bias_mod ? b % bias_mod : b]; }     // bias per large-side channel
         v = act_fwd(v, act, slope);
     } else if (href && act != SRGAN_ACT_NONE) {
         v *= act_bwd(to_f(href[o]), act, slope);
@@ -160,7 +160,7 @@ static int skinny_conv_t(int mode, const void* src, const void* W, void* out, in
         SRGAN_CHECK_LAUNCH("skinny_down_kernel");
     } else {
         dim3 grid((unsigned)((K + 255) / 256), n);
-        skinny_up_kernel<T><<<grid, 256, 0, st>>>((const T*)src, (const T*)W, (T*)out, bias, bias_mod, (const T*)href, epi, act, slope, g->Ca, K);
+        skinny_up_kernel<T><<<grid, 256, 0, st>>>((const T*)src, (const T*)W, (T*)out, bias, bias_mod, (const T*)href, epi, act, slope, g->Ca, g->Cb, K);
         SRGAN_CHECK_LAUNCH("skinny_up_kernel");
     }
     return SRGAN_OK;

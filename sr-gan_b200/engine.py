@@ -121,6 +121,7 @@ class NetState:
         self.exp_avg_sq = torch.zeros(n_total, dtype=mdt, device=device)
         # [t, lr/(1-beta1^t), 1/sqrt(1-beta2^t)] in device memory (fp64 in the fp64 schedule tests): see srgan_adam_prepare
         self.adam_state = torch.zeros(3, dtype=mdt, device=device)
+        self.plain_entries = None                  # adam_multi table rows, built on the first update
         self.wd_, self.wu_ = {}, {}
         for l in net.layers:
             n = kl[l.name]
@@ -541,10 +542,10 @@ class Engine:
         if self.comm is not None:
             self.comm.all_reduce_sum(st.grad)
         self.ops.adam_prepare(st.adam_state, lr, betas[0], betas[1])
+        plain_keys = []
+
         def plain(k):
-            nb = st.params[k].numel()
-            self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), (nb, 1, 1, 1), (1, 0, 0, 0), None, None, None, None,
-                          st.adam_state, betas[0], betas[1], eps, weight_decay)
+            plain_keys.append(k)
         for l in st.net.layers:
             wd_s, wu_s = st.strides(l)
             k = l.name + '.weight'
@@ -562,8 +563,14 @@ class Engine:
                 self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), dims, s, dst, s, None, None,
                               st.adam_state, betas[0], betas[1], eps, weight_decay)
                 plain(h + '.bias')
-            if st.net.head_parts is not None:
-                self._head_bias(st)
+        # every tensor without kernel-layout copies (biases, BatchNorm weight / bias) in one launch
+        if st.plain_entries is None:
+            st.plain_entries = [(st.params[k].detach(), st.gslices[k][0], st.slices[k][0], st.params[k].numel())
+                                for k in plain_keys]
+        self.ops.adam_multi(st.plain_entries, st.grad, st.exp_avg, st.exp_avg_sq, st.adam_state, betas[0], betas[1], eps,
+                            weight_decay)
+        if st.net.head and st.net.head_parts is not None:
+            self._head_bias(st)
         st.grad.zero_()
 
     # ------------------------------------------------------------------ inputs

@@ -28,7 +28,7 @@ _EXPORTS = (
     'srgan_distance', 'srgan_feature_norm_seed', 'srgan_gradnorm_penalty', 'srgan_gp_feature_seed', 'srgan_adam',
     'srgan_repack', 'srgan_im2col', 'srgan_col2im', 'srgan_adam_prepare', 'srgan_coefficient_step',
     'srgan_coefficient_step_workspace_bytes', 'srgan_affine', 'srgan_affine_bwd', 'srgan_affine_grad', 'srgan_copy2d',
-    'srgan_maxpool', 'srgan_maxpool_bwd', 'srgan_avgpool', 'srgan_avgpool_bwd', 'srgan_crowd_loss', 'srgan_crowd_map_grad', 'srgan_depth_to_space',
+    'srgan_maxpool', 'srgan_maxpool_bwd', 'srgan_avgpool', 'srgan_avgpool_bwd', 'srgan_crowd_loss', 'srgan_crowd_map_grad', 'srgan_depth_to_space', 'srgan_adam_multi',
 )
 
 _lib = None
@@ -89,6 +89,7 @@ def load_library(path: str = LIB_PATH):
     lib.srgan_avgpool.argtypes = [vp, c_int, vp, c_int, c_int] + [c_int] * 5 + [c_int, vp]
     lib.srgan_avgpool_bwd.argtypes = [vp, c_int, c_int, vp, c_int] + [c_int] * 5 + [vp, c_int, c_f, c_int, vp]
     lib.srgan_crowd_loss.argtypes = [vp, vp, pp, c_int, vp, c_int, c_ll, c_int, c_f, c_f, vp, vp, vp, c_int, vp]
+    lib.srgan_adam_multi.argtypes = [vp, c_int, vp, vp, vp, vp, c_f, c_f, c_f, c_f, vp]
     lib.srgan_depth_to_space.argtypes = [vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, vp]
     lib.srgan_crowd_map_grad.argtypes = [vp, vp, vp, vp, c_int, c_ll, c_int, c_int, c_f, c_int, vp]
     for name in _EXPORTS[5:]:
@@ -350,3 +351,21 @@ class CudaOps:
     def depth_to_space(self, src, dst, n, Hs, Ws, k, inverse):
         self._ck(self.lib.srgan_depth_to_space(self._p(src), self._p(dst, src.dtype), n, Hs, Ws, k, int(bool(inverse)),
                                                _dt(src.dtype), self._stream()), 'srgan_depth_to_space')
+
+    def adam_multi(self, entries, grad, m, v, state, b1, b2, eps, wd):
+        """entries: list of (param, grad offset, moment offset, numel); the device table is built once per list."""
+        key = id(entries)
+        tbl = self._tables.get(key) if hasattr(self, '_tables') else None
+        if tbl is None:
+            if not hasattr(self, '_tables'):
+                self._tables = {}
+            rows = []
+            for p, go, mo, n in entries:
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise TypeError('adam_multi: fp32 contiguous CUDA parameters only')
+                rows.append([p.data_ptr(), go, mo, n])
+            tbl = (torch.tensor(rows, dtype=torch.int64).to(self.device), entries)      # keep `entries` alive with its id
+            self._tables[key] = tbl
+        f32 = torch.float32
+        self._ck(self.lib.srgan_adam_multi(self._p(tbl[0]), len(entries), self._p(grad, f32), self._p(m, f32), self._p(v, f32),
+                                           self._p(state, f32), b1, b2, eps, wd, self._stream()), 'srgan_adam_multi')

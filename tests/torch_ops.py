@@ -388,3 +388,10 @@ class TorchOps:
         else:
             v = src.view(n, Hs, k, Ws, k).permute(0, 1, 3, 2, 4).reshape(-1)
         dst.copy_(v)
+
+    def adam_multi(self, entries, grad, m, v, state, b1, b2, eps, wd):
+        self.launches += 1
+        for p, go, mo, n in entries:
+            self.adam(p, grad[go:go + n], m[mo:mo + n], v[mo:mo + n], (n, 1, 1, 1), (1, 0, 0, 0), None, None, None, None,
+                      state, b1, b2, eps, wd)
+            self.launches -= 1
