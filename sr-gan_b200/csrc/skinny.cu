@@ -3,7 +3,7 @@
 // final_count_feature_layer = Conv2d(1920, 20, 1) (:1132).  As GEMMs these are M = batch rows, N = 20: a 128x64-tiled kernel runs
 // them on ONE CTA.  They are bandwidth problems: each kernel below streams the long operand once, coalesced.
 //   down : S[n,a]  = epilogue(sum_k L[n,k] * Wd[a,k])          one CTA per ROWS rows, threads stride over k
-//   up   : L[n,k]  = epilogue(sum_a S[n,a] * Wu[k,a])          one thread per (n, k)
+//   up   : L[n,k]  = epilogue(sum_a S[n,a] * Wu[b(k)][tap(k)][a])  one thread per (n, k)
 //   wgrad: dW[a,k] += sum_n S[n,a] * L[n,k]                    one thread per k, all a in registers
 #include "common.cuh"
 
@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(256) skinny_up_kernel(const T* __restrict__ S,
     __syncthreads();
     const long long k = (long long)blockIdx.x * 256 + threadIdx.x;
     if (k >= K) return;
-    const T* w = Wu + k * Ca;
+    // Wu is [b][r][s][a] while k runs over (r, s, b) like the large side's memory order
+    const T* w = Wu + ((k % Cb) * (K / Cb) + k / Cb) * Ca;
     float v = 0.f;
     if ((Ca & 3) == 0) {
         for (int a = 0; a < Ca; a += 4) {
