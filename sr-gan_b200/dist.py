@@ -18,9 +18,18 @@ class Comm:
         self.world_size = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.calls = 0
+        # set by StepRunner while it captures a step piecewise: called instead of the collective (which it then issues
+        # itself between two graph segments)
+        self.capture_hook = None
 
     def all_reduce_sum(self, t: torch.Tensor):
         self.calls += 1
+        if self.capture_hook is not None:
+            self.capture_hook(t)
+            return
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def all_reduce_sum_now(self, t: torch.Tensor):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
     def all_reduce_sum_partial(self, t: torch.Tensor, slots):

@@ -270,8 +270,9 @@ class StepRunner:
         self.generator.manual_seed(0)
         import os
         ug = getattr(settings, 'use_cuda_graph', True)
-        # NCCL collectives inside a captured graph are left for a later round: multi-rank steps run eagerly
-        self.use_cuda_graph = bool(ug) and os.environ.get('SRGAN_NO_GRAPH', '0') != '1' and comm is None
+        # multi-rank steps are captured PIECEWISE: one graph segment between every two collectives, the NCCL all-reduces
+        # (feature sums, gradients) are issued eagerly between the segments on the same stream (_capture_segments)
+        self.use_cuda_graph = bool(ug) and os.environ.get('SRGAN_NO_GRAPH', '0') != '1' 
         self._graphs, self._statics = {}, {}
         # coefficient application: one persistent cooperative kernel per step method (csrc/coef_step.cu) instead of
         # ~150 generic launches; single rank only (the feature sums are combined inside the kernel)
@@ -376,11 +377,46 @@ class StepRunner:
             dst.copy_(src)
         if entry['graph'] is None:
             torch.cuda.synchronize(self.device)
+            entry['graph'] = self._capture_segments(fn)
+        for seg in entry['graph']:
+            seg()
+
+    def _capture_segments(self, fn):
+        """Captures fn() as a list of callables: CUDA-graph replays, separated (multi-rank only) by the collectives the
+        step issues through Comm.all_reduce_sum, which are not captured but re-issued eagerly at the same places."""
+        comm = self.engine.comm
+        segs, state = [], {'g': None}
+        pool = torch.cuda.graph_pool_handle()
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+
+        def begin():
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            g.capture_begin(pool=pool, capture_error_mode='thread_local')
+            state['g'] = g
+
+        def end():
+            g, state['g'] = state['g'], None
+            g.capture_end()
+            segs.append(g.replay)
+
+        def on_collective(t):
+            end()
+            segs.append(lambda t=t: comm.all_reduce_sum(t))
+            comm.all_reduce_sum_now(t)             # keeps the ranks' NCCL call sequences aligned during capture as well
+            begin()
+        with torch.cuda.stream(side):
+            if comm is not None:
+                comm.capture_hook = on_collective
+            try:
+                begin()
                 fn()
-            entry['graph'] = g
-        entry['graph'].replay()
+                end()
+            finally:
+                if comm is not None:
+                    comm.capture_hook = None
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        return segs
 
     def _static(self, name, like, dtype=torch.float32):
         t = self._statics.get(name)
