@@ -287,10 +287,11 @@ class Engine:
             pr['events'].append((e0, e1))
 
     # ------------------------------------------------------------------ live kernel probe (bench.py roofline)
-    def probe_begin(self, layer_index, rows):
-        """Times, with CUDA events on the launch stream, every forward launch of D layer `layer_index` (1-based) over
-        `rows` samples until probe_end()."""
-        self._probe = {'layer': self.d_net.layers[layer_index - 1], 'rows': rows, 'events': []}
+    def probe_begin(self, layer_name, rows):
+        """Times, with CUDA events on the launch stream, every forward launch of the D layer `layer_name` over `rows`
+        samples until probe_end()."""
+        layer = next(l for l in self.d_net.layers if l.name == layer_name)
+        self._probe = {'layer': layer, 'rows': rows * layer.gemm_rows, 'samples': rows, 'events': []}
 
     def probe_end(self):
         pr, self._probe = self._probe, None
@@ -299,8 +300,9 @@ class Engine:
         torch.cuda.synchronize()
         ms = sum(a.elapsed_time(b) for a, b in pr['events'])
         l = pr['layer']
-        return {'count': len(pr['events']), 'ms': ms,
-                'kernel': f'D {l.name} forward conv ({l.geom.Cb}->{l.geom.Ca} k{l.geom.R} s{l.geom.stride}) over {pr["rows"]} samples'}
+        d = l.master_dims
+        return {'count': len(pr['events']), 'ms': ms, 'macs_per_sample': l.macs_per_sample,
+                'kernel': f'D {l.name} forward conv ({d[1]}->{d[0]} k{l.geom.R} s{l.geom.stride}) over {pr["samples"]} samples'}
 
     def _bwd_data_layer(self, st: NetState, l: Layer, dy, dx, n, href, act, slope, lo=0, col_ready=False):
         """dx = (W_l^T dy) * act'(href)   (act = ACT_NONE: no mask)."""
