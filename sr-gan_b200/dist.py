@@ -25,9 +25,19 @@ class Comm:
     def all_reduce_sum(self, t: torch.Tensor):
         self.calls += 1
         if self.capture_hook is not None:
-            self.capture_hook(t)
+            self.capture_hook('all_reduce', t)
             return
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def begin_deferred(self, tag):
+        """Everything up to end_deferred() (a gradient all-reduce and the optimizer update that consumes it) may run on
+        a side stream, overlapped with whatever the caller enqueues next; only honoured under piecewise graph capture."""
+        if self.capture_hook is not None:
+            self.capture_hook('defer_begin', tag)
+
+    def end_deferred(self):
+        if self.capture_hook is not None:
+            self.capture_hook('defer_end', None)
 
     def all_reduce_sum_now(self, t: torch.Tensor):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)

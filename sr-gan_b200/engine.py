@@ -538,10 +538,14 @@ class Engine:
                 raise ValueError(op.kind)
 
     # ------------------------------------------------------------------ Adam
-    def adam(self, st: NetState, lr, weight_decay, betas=(0.9, 0.999), eps=1e-8):
+    def adam(self, st: NetState, lr, weight_decay, betas=(0.9, 0.999), eps=1e-8, deferrable=None):
         """torch.optim.Adam semantics, one fused launch per tensor that also rewrites the kernel-
-        layout copies.  Gradients are read from (and then zeroed in) the flat buffer."""
+        layout copies.  Gradients are read from (and then zeroed in) the flat buffer.  deferrable = a tag: this update is
+        the LAST thing its step method enqueues, so (multi-rank) its gradient all-reduce and the update may overlap with
+        the next step method; StepRunner waits for the tag before the network or its gradient buffer is touched again."""
         if self.comm is not None:
+            if deferrable:
+                self.comm.begin_deferred(deferrable)
             self.comm.all_reduce_sum(st.grad)
         self.ops.adam_prepare(st.adam_state, lr, betas[0], betas[1])
         plain_keys = []
@@ -574,6 +578,8 @@ class Engine:
         if st.net.head and st.net.head_parts is not None:
             self._head_bias(st)
         st.grad.zero_()
+        if self.comm is not None and deferrable:
+            self.comm.end_deferred()
 
     # ------------------------------------------------------------------ inputs
     def load_input(self, net: Net, src: torch.Tensor, dst, n):
@@ -651,7 +657,7 @@ class Engine:
         self.ops.seed_rows(self._brows_feat(net, deltas, 0, B), B, F, None, dpred, st.whead[0:F], feats, fact, fslope)
         self._head_grads(st, feats, B, 0, dpred)
         self.backward(st, acts, deltas, 0, B, hook=hook)
-        self.adam(st, lr, weight_decay, cfg.betas, cfg.eps)
+        self.adam(st, lr, weight_decay, cfg.betas, cfg.eps, deferrable='DNN')
 
     # ------------------------------------------------------------------ GAN step (srgan.py:273-320)
     def gan_step(self, x, y, u, z, alpha, z2, cfg, train_generator=True):
@@ -795,7 +801,7 @@ class Engine:
         self.backward(D, acts, deltas, 0, B, need_input_grad=True, dinput=gdeltas[len(gl)], input_href=gacts[-1],
                       input_act=gl[-1].act, weight_grads=False)
         self.backward(G, gacts, gdeltas, 0, B)
-        self.adam(G, cfg.learning_rate, 0.0, cfg.betas, cfg.eps)                                  # srgan.py:137, :305
+        self.adam(G, cfg.learning_rate, 0.0, cfg.betas, cfg.eps, deferrable='G')                  # srgan.py:137, :305
 
     # ------------------------------------------------------------------ inference-style helpers
     def d_features(self, x, st: Optional[NetState] = None):

@@ -274,6 +274,7 @@ class StepRunner:
         # (feature sums, gradients) are issued eagerly between the segments on the same stream (_capture_segments)
         self.use_cuda_graph = bool(ug) and os.environ.get('SRGAN_NO_GRAPH', '0') != '1' 
         self._graphs, self._statics = {}, {}
+        self._side, self._pending = None, {}       # deferred (overlapped) gradient all-reduce + Adam groups: _run_deferred
         # coefficient application: one persistent cooperative kernel per step method (csrc/coef_step.cu) instead of
         # ~150 generic launches; single rank only (the feature sums are combined inside the kernel)
         self.persistent = (self._persistent_shape_ok(d_net, g_net) and comm is None
@@ -379,7 +380,37 @@ class StepRunner:
             torch.cuda.synchronize(self.device)
             entry['graph'] = self._capture_segments(fn)
         for seg in entry['graph']:
-            seg()
+            if isinstance(seg, tuple):
+                self._run_deferred(*seg)
+            else:
+                seg()
+
+    def _run_deferred(self, tag, items):
+        """A deferred group (gradient all-reduce + the Adam graph of one network) on the side stream, after everything
+        enqueued so far; whoever touches that network next waits for it (_wait_pending)."""
+        main = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._side.wait_event(ev)
+        with torch.cuda.stream(self._side):
+            for it in items:
+                it()
+            done = torch.cuda.Event()
+            done.record(self._side)
+        self._pending[tag] = done
+
+    def _wait_pending(self, tags=None):
+        """Makes the current stream wait for the deferred updates of the given networks (None: all).  dnn_step touches
+        only DNN (parameters, gradient buffer, moments; the activation scratch it shares with D is not used by an
+        update), gan_step only D and G: so DNN's all-reduce + Adam overlap the whole GAN step, G's the next DNN step."""
+        if self._pending:
+            main = torch.cuda.current_stream(self.device)
+            for tag in list(self._pending) if tags is None else tags:
+                ev = self._pending.pop(tag, None)
+                if ev is not None:
+                    main.wait_event(ev)
 
     def _capture_segments(self, fn):
         """Captures fn() as a list of callables: CUDA-graph replays, separated (multi-rank only) by the collectives the
@@ -398,20 +429,33 @@ class StepRunner:
         def end():
             g, state['g'] = state['g'], None
             g.capture_end()
-            segs.append(g.replay)
+            cur['list'].append(g.replay)
 
-        def on_collective(t):
+        cur = {'list': segs, 'closed': False}
+
+        def on_collective(kind, arg):
+            if cur['closed']:
+                raise RuntimeError('a deferrable update must be the last thing its step method enqueues')
             end()
-            segs.append(lambda t=t: comm.all_reduce_sum(t))
-            comm.all_reduce_sum_now(t)             # keeps the ranks' NCCL call sequences aligned during capture as well
-            begin()
+            if kind == 'all_reduce':
+                cur['list'].append(lambda t=arg: comm.all_reduce_sum(t))
+                comm.all_reduce_sum_now(arg)       # keeps the ranks' NCCL call sequences aligned during capture as well
+                begin()
+            elif kind == 'defer_begin':
+                items = []
+                segs.append((arg, items))          # (tag, items): replayed by _run_deferred on the side stream
+                cur['list'] = items
+                begin()
+            else:                                  # defer_end: nothing may follow
+                cur['closed'] = True
         with torch.cuda.stream(side):
             if comm is not None:
                 comm.capture_hook = on_collective
             try:
                 begin()
                 fn()
-                end()
+                if not cur['closed']:
+                    end()
             finally:
                 if comm is not None:
                     comm.capture_hook = None
@@ -437,6 +481,7 @@ class StepRunner:
         cfg = self.config()
         lr = cfg.learning_rate if lr is None else lr
         wd = cfg.weight_decay if weight_decay is None else weight_decay
+        self._wait_pending(('DNN',))
         if self.persistent:
             self._coef_step(1, examples, labels, lr_dnn=lr, wd=wd)
             return
@@ -453,6 +498,7 @@ class StepRunner:
         B = labeled_examples.shape[0]
         z, alpha, z2 = noise if noise is not None else self.draw_noise(B, cfg)
         train_g = (step % cfg.generator_training_step_period == 0)
+        self._wait_pending(('G',))
         if self.persistent:
             self._coef_step(2, labeled_examples, labels, unlabeled_examples, z, alpha.reshape(-1), z2, train_g=train_g)
             return
@@ -470,6 +516,7 @@ class StepRunner:
 
     def scalars(self):
         """One device->host read of the step's scalars (the .item() calls of srgan.py:268-270, 306-319)."""
+        self._wait_pending()
         s = self.engine.scalars
         if self.engine.comm is not None:
             s = s.clone()
@@ -481,6 +528,7 @@ class StepRunner:
 
     # ---- forward-only helpers (D(x) / G(z) of the reference modules, on the kernels)
     def predict(self, x, net='D'):
+        self._wait_pending()
         self._fresh_layouts()
         st = self.engine.D if net == 'D' else self.engine.DNN
         pred, feats = self.engine.d_features(x, st)
@@ -494,6 +542,7 @@ class StepRunner:
         return out
 
     def generate(self, z):
+        self._wait_pending()
         self._fresh_layouts()
         gnet = self.engine.g_net
         out_l = gnet.layers[-1]
@@ -510,6 +559,7 @@ class StepRunner:
 
     # ---- torch.optim.Adam state compatibility (checkpoints stay loadable)
     def export_optimizer_state(self, optimizer, which: str):
+        self._wait_pending()
         st = {'D': self.engine.D, 'G': self.engine.G, 'DNN': self.engine.DNN}[which]
         for name, p in self.modules[which].named_parameters():
             if name not in st.slices:
