@@ -260,3 +260,47 @@ def test_crowd_full_size_matches_reference_golden(precision):
             sd = r.modules[net].state_dict()
             got_abs = torch.tensor([(sd[k].cpu() - getattr(init, net)[k]).double().abs().sum().item() for k in keys])
             assert rel(got_abs, torch.tensor(z[f'update/{net}/abs_sum'])) < 5e-3, net
+
+
+def test_coefficient_1k_step_loss_curve_band():
+    """BASELINE north_star: the bf16 mode's 1k-step loss curves stay inside a stated band around the fp32 reference path.
+    Coefficient SR-GAN, B=5000 (run.py:50), lr 1e-4, identical data order and noise for: the oracle (CPU fp32 autograd), the
+    persistent fp32 kernel, and the generic kernels in bf16 mode.  Band (derived from the chaos floor of the
+    GAN dynamics): +-5 % on labeled / unlabeled / fake / generator losses and the gradient norm, +-15 % or 1e-3 absolute on the
+    gradient penalty, evaluated on the mean of the last 50 steps."""
+    B, steps, win = 5000, 1000, 50
+    gen = torch.Generator().manual_seed(31)
+    st = O.init_coefficient(seed=11)
+    for k in ('linear1.weight', 'linear2.weight', 'linear3.weight'):
+        st.D[k] = st.D[k] * 2.5                       # gradient norms around 1: the penalty hinge switches on and off
+    cfg = O.StepConfig(batch_size=B, gradient_penalty_multiplier=10.0, learning_rate=1e-4)
+    pool = 8                                           # a small pool of batches cycled in a fixed order
+    data = [(torch.randn(B, 50, generator=gen), torch.rand(B, generator=gen) * 2 - 1, torch.randn(B, 50, generator=gen),
+             torch.randn(B, 10, generator=gen), torch.rand(B, 1, generator=gen), torch.randn(B, 10, generator=gen)) for _ in range(pool)]
+    r_fp32 = runner_from_state(st, cfg, 'fp32')
+    r_bf16 = runner_from_state(st, cfg, 'bf16')
+    r_bf16.persistent = False                          # the generic kernels really run in bf16 (the persistent kernel is fp32)
+    assert r_fp32.persistent
+    cuda_data = [to_cuda(*d) for d in data]
+    torch.set_num_threads(max(1, (torch.get_num_threads())))
+    curves = {'oracle': [], 'fp32': [], 'bf16': []}
+    for i in range(steps):
+        x, y, u, z, alpha, z2 = data[i % pool]
+        out = O.training_step(st, cfg, x, y, u, z, alpha, z2, step=i)
+        if i >= steps - win:
+            curves['oracle'].append([out[k] for k in SCALARS])
+        xc, yc, uc, zc, ac, z2c = cuda_data[i % pool]
+        for name, r in (('fp32', r_fp32), ('bf16', r_bf16)):
+            r.dnn_step(xc, yc)
+            r.gan_step(xc, yc, uc, i, noise=(zc, ac, z2c))
+            if i >= steps - win:
+                s = r.scalars()
+                curves[name].append([s[k] for k in SCALARS])
+    mean = {k: torch.tensor(v, dtype=torch.float64).mean(0) for k, v in curves.items()}
+    for name in ('fp32', 'bf16'):
+        for j, k in enumerate(SCALARS):
+            ref, got = mean['oracle'][j].item(), mean[name][j].item()
+            if k == 'gradient_penalty':
+                assert abs(got - ref) <= max(0.15 * abs(ref), 1e-3), (name, k, got, ref)
+            else:
+                assert abs(got - ref) <= 0.05 * abs(ref) + 1e-6, (name, k, got, ref)
