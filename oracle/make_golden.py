@@ -118,26 +118,29 @@ def coefficient_batches(batch, steps, seed):
     return out
 
 
-def crowd_case():
-    """CrowdExperiment (crowd/srgan.py) with the UNMODIFIED KnnDenseNetCat (DenseNet-201 trunk, crowd/models.py:1049-1166)
+def crowd_case(method='srgan', d_scale=1.56):
+    """CrowdExperiment (crowd/srgan.py; method 'dggan': CrowdDgganExperiment, crowd/dggan.py, with KnnDenseNetCatDggan) with the UNMODIFIED KnnDenseNetCat (DenseNet-201 trunk, crowd/models.py:1049-1166)
     and DCGenerator at 224x224, B=2, one step.  The 20.6 M-parameter initial state is not stored: both sides build it
     with oracle.init_crowd(seed) (pure torch, deterministic) and the reference modules load it with strict=True, which
     also pins the oracle's key/shape table against the reference state_dict.  Stored: scalars, per-sample gradient
     norms, labeled features, and per-tensor checksums of the parameter updates of D, G and DNN."""
     from oracle import srgan_oracle as O
     from crowd.srgan import CrowdExperiment
-    from crowd.models import KnnDenseNetCat, DCGenerator
+    from crowd.dggan import CrowdDgganExperiment
+    from crowd.models import KnnDenseNetCat, KnnDenseNetCatDggan, DCGenerator
+    dggan = method == 'dggan'
     torch.set_num_threads(os.cpu_count())
-    cfg = dict(method='srgan', family='crowd', batch_size=2, learning_rate=1e-4, weight_decay=0.0,
+    cfg = dict(method=method, family='crowd', batch_size=2, learning_rate=1e-4, weight_decay=0.0,
                matching_loss_multiplier=1e3, contrasting_loss_multiplier=1e2, gradient_penalty_multiplier=1e2,
-               map_multiplier=1e-3, init_seed=5, input_seed=6, d_scale=1.56)
-    st = O.init_crowd(seed=cfg['init_seed'], scale=cfg['d_scale'])
-    D, DNN, G = KnnDenseNetCat(pretrained=False), KnnDenseNetCat(pretrained=False), DCGenerator()
+               map_multiplier=1e-3, init_seed=5, input_seed=6, d_scale=d_scale)
+    st = O.init_crowd(seed=cfg['init_seed'], scale=cfg['d_scale'], dggan=dggan)
+    cls = KnnDenseNetCatDggan if dggan else KnnDenseNetCat
+    D, DNN, G = cls(pretrained=False), cls(pretrained=False), DCGenerator()
     D.load_state_dict(st.D, strict=True)
     DNN.load_state_dict(st.DNN, strict=True)
     G.load_state_dict(st.G, strict=True)
     assert list(D.state_dict().keys()) == list(st.D.keys()), 'oracle key order differs from the reference state_dict'
-    exp = ref_harness.make_experiment(CrowdExperiment, settings_for(cfg), D=D, G=G, DNN=DNN)
+    exp = ref_harness.make_experiment(CrowdDgganExperiment if dggan else CrowdExperiment, settings_for(cfg), D=D, G=G, DNN=DNN)
     x, y, u, z, alpha, z2 = O.synthetic_crowd_batch(2, cfg['input_seed'])
     exp.dnn_training_step(x, y, 0)
     with ref_harness.injected_noise(z, alpha, z2):
@@ -147,7 +150,8 @@ def crowd_case():
     for tag, key in SCALAR_TAGS.items():
         data[f'step0/scalars/{key}'] = np.float64(sc[tag])
     data['step0/gradient_norm'] = exp.gradient_norm.detach().numpy().copy()
-    data['step0/labeled_features'] = exp.labeled_features.detach().reshape(2, -1).numpy().copy()
+    if not dggan:                                  # KnnDenseNetCatDggan does not publish .features
+        data['step0/labeled_features'] = exp.labeled_features.detach().reshape(2, -1).numpy().copy()
     for net, mod, init in (('D', exp.D, st.D), ('G', exp.G, st.G), ('DNN', exp.DNN, st.DNN)):
         keys, sums, abss = [], [], []
         for k, v in mod.state_dict().items():
@@ -161,9 +165,9 @@ def crowd_case():
         data[f'update/{net}/abs_sum'] = np.array(abss)
     cfg_json = dict(cfg, steps=1, torch=torch.__version__)
     data['config_json'] = np.frombuffer(json.dumps(cfg_json).encode(), dtype=np.uint8)
-    path = os.path.join(OUT, 'crowd_srgan.npz')
+    path = os.path.join(OUT, f'crowd_{method}.npz')
     np.savez_compressed(path, **data)
-    print('crowd_srgan', {k: float(v) for k, v in data.items() if '/scalars/' in k}, os.path.getsize(path), 'bytes')
+    print(f'crowd_{method}', {k: float(v) for k, v in data.items() if '/scalars/' in k}, os.path.getsize(path), 'bytes')
 
 
 def main():
@@ -171,6 +175,9 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     if 'crowd' in sys.argv[1:]:
         crowd_case()
+        return
+    if 'crowd_dggan' in sys.argv[1:]:
+        crowd_case('dggan', d_scale=float(os.environ.get('D_SCALE', '1.6')))
         return
     torch.set_num_threads(1)                     # deterministic reduction order for the fixtures
     from coefficient.srgan import CoefficientExperiment
@@ -230,6 +237,7 @@ def main():
         batches.append((x, y, u, z, alpha, z2))
     run_case('dcgan_mini', exp, cfg, batches, steps=3)
     crowd_case()
+    crowd_case('dggan', d_scale=1.6)
 
 
 if __name__ == '__main__':

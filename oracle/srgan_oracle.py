@@ -169,17 +169,21 @@ def crowd_d_forward(spec: ModelSpec, p: Params, x: torch.Tensor):
         m, c, h = crowd_map_module(p, f'map_module{i}', t)
         maps.append(m), counts.append(c), hs.append(h)
     features = torch.cat([h.reshape(B, -1) for h in hs] + [fcf.reshape(B, -1)], dim=1)
-    count = (counts[0] + counts[1] + counts[2] + final_count).reshape(B)
+    count = counts[0] + counts[1] + counts[2] + final_count
     L = spec.label_patch_size
     map_ = torch.cat(maps, dim=1).reshape(B, 3, L, L)
-    return (count, map_), features
+    if spec.dggan:
+        # KnnDenseNetCatDggan.forward, crowd/models.py:1024-1046: every count layer has two outputs, the second is
+        # `real_label` (the DG-GAN score); that module does not publish `.features` (the DG-GAN losses do not use them)
+        count = count.reshape(B, 2)
+        return (count[:, 0], map_), count[:, 1], features
+    return (count.reshape(B), map_), None, features
 
 
 def d_forward(spec: ModelSpec, p: Params, x: torch.Tensor):
     """Returns (prediction, fake_score_or_None, features)."""
     if spec.family == 'crowd':
-        out, f = crowd_d_forward(spec, p, x)
-        return out, None, f
+        return crowd_d_forward(spec, p, x)
     if spec.family == 'coefficient':
         out, f = coefficient_d_forward(p, x, spec.dggan)
         if spec.dggan:
@@ -446,6 +450,7 @@ def crowd_param_shapes(spec: ModelSpec, image_size: int):
     """Key -> shape of KnnDenseNetCat.state_dict() (crowd/models.py:1060-1134) in the module's own order, for any
     constructor arguments; the MapModule input sizes follow the trunk (28/14/7 at image 224, hard-coded at :1129-1131)."""
     g, bs = spec.growth_rate, spec.bn_size
+    n_out = 2 if spec.dggan else 1               # KnnDenseNetCatDggan / MapModuleDggan: crowd/models.py:915,1020
     out = {}
 
     def bn(prefix, c):
@@ -487,9 +492,9 @@ def crowd_param_shapes(spec: ModelSpec, image_size: int):
         out[pre + '.conv2.weight'] = (16, 8, 2, 2); out[pre + '.conv2.bias'] = (16,)
         out[pre + '.conv3.weight'] = (32, 16, 2, 2); out[pre + '.conv3.bias'] = (32,)
         out[pre + '.linear1.weight'] = (20, 32, L // 8, L // 8); out[pre + '.linear1.bias'] = (20,)
-        out[pre + '.count_layer.weight'] = (1, 20, 1, 1); out[pre + '.count_layer.bias'] = (1,)
+        out[pre + '.count_layer.weight'] = (n_out, 20, 1, 1); out[pre + '.count_layer.bias'] = (n_out,)
     out['final_count_feature_layer.weight'] = (20, c, 1, 1); out['final_count_feature_layer.bias'] = (20,)
-    out['count_layer.weight'] = (1, 20, 1, 1); out['count_layer.bias'] = (1,)
+    out['count_layer.weight'] = (n_out, 20, 1, 1); out['count_layer.bias'] = (n_out,)
     return out
 
 

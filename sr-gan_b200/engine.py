@@ -91,6 +91,10 @@ class NetState:
         order = []
         # elements of a layer's kernel-layout weight copies: geom.Ca / geom.Cb may be padded beyond the master dims
         kl = {l.name: l.geom.Ca * l.geom.R * l.geom.S * l.geom.Cb for l in net.layers}
+        part_c0, c0 = {}, 0
+        for h, ncol in (net.head_parts or []):
+            part_c0[h] = c0
+            c0 += ncol
         for l in net.layers:
             order += [l.name + '.weight'] + ([l.name + '.bias'] if l.has_bias else [])
         for op in net.affines:                     # eval-mode BatchNorm: weight / bias are trainable, the statistics are not
@@ -112,8 +116,17 @@ class NetState:
                 gn = p.shape[0] * KPAD             # gradient in the padded Wd_pad layout [a][KPAD]
             elif k.endswith('.weight') and lname in kl:
                 gn = kl[lname]                     # gradient in the (possibly channel-padded) Wd layout
+            if k.endswith('.weight') and lname in part_c0:
+                continue                           # multi-part head: gradients live in the shared [outputs][F] region below
             self.gslices[k] = (g_total, gn)
             g_total += (gn + 3) // 4 * 4
+        if net.head_parts is not None:
+            # row o of the region = d/d(head output o) over all feature columns; part p owns columns [c0_p, c0_p + ncol_p)
+            F = net.feature_size
+            self.head_gbase = g_total
+            for h, ncol in net.head_parts:
+                self.gslices[h + '.weight'] = (g_total + part_c0[h], (net.head_outputs - 1) * F + ncol)
+            g_total += (net.head_outputs * F + 3) // 4 * 4
         self.order = order
         mdt = params[order[0]].dtype
         self.grad = torch.zeros(g_total, dtype=mdt, device=device)
@@ -225,9 +238,9 @@ class Engine:
         if net.head_parts is None:
             dims, s = self._head_strides(net)
             return [(net.head, dims, s, st.whead)]
-        out, c0 = [], 0
-        for h, ncol in net.head_parts:             # crowd: four Conv2d(20, 1, 1) heads over consecutive feature columns
-            out.append((h, (1, ncol, 1, 1), (ncol, 1, 0, 0), st.whead[c0:c0 + ncol]))
+        out, c0, F = [], 0, net.feature_size
+        for h, ncol in net.head_parts:             # crowd: four Conv2d(20, n_out, 1) heads over consecutive feature columns
+            out.append((h, (net.head_outputs, ncol, 1, 1), (F, 1, 0, 0), st.whead[c0:]))
             c0 += ncol
         return out
 
@@ -443,6 +456,27 @@ class Engine:
                             self.rows(acts[i], l.out_elems, 4 * B, 5 * B), B, bias=False,
                             href=self.rows(acts[i], l.out_elems, 3 * B, 4 * B), epi=EPI_DACT, lo=4 * B)
 
+    def tangent_block_grads(self, st: NetState, acts, deltas, tlo, thi):
+        """Parameter gradients of the tangent block alone (wgrad(u_{l-1}, gamma_l); no bias terms): used
+        when the block is not contiguous with the ordinary rows of the backward pass (DG-GAN)."""
+        net, R = st.net, self._brows
+        n = thi - tlo
+        if net.graph is None:
+            for i, l in enumerate(net.layers, 1):
+                self._wgrad_layer(st, l, self.rows(acts[i - 1], l.in_elems, tlo, thi),
+                                  self.rows(deltas[i], l.out_elems, tlo, thi), n, lo=tlo)
+            return
+        for op in net.graph:
+            sb, db = net.bufs[op.src], net.bufs[op.dst]
+            if op.kind == 'conv':
+                self._wgrad_layer(st, op.layer, R(acts[op.src], sb, tlo, thi), R(deltas[op.dst], db, tlo, thi),
+                                  n * op.layer.gemm_rows, lo=tlo)
+            elif op.kind == 'affine':
+                P, nm = st.params, op.name
+                self.ops.affine_grad(R(deltas[op.dst], db, tlo, thi), db.ch, R(acts[op.src], sb, tlo, thi), sb.ch, op.c0,
+                                     n * sb.rows, op.C, P[nm + '.running_mean'], P[nm + '.running_var'], self.BN_EPS,
+                                     st.g(nm + '.weight'), None, False)
+
     # ------------------------------------------------------------------ graph nets (crowd KnnDenseNetCat)
     BN_EPS = 1e-5          # nn.BatchNorm2d default, crowd/models.py:339,343,367,1077,1092
 
@@ -565,7 +599,7 @@ class Engine:
             plain(op.name + '.bias')
         if st.net.head:
             for h, dims, s, dst in self._head_part_layouts(st):
-                k = h + '.weight'
+                k = h + '.weight'                  # multi-part heads: st.g(k) starts at the part's first column of row 0
                 self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), dims, s, dst, s, None, None,
                               st.adam_state, betas[0], betas[1], eps, weight_decay)
                 plain(h + '.bias')
@@ -598,12 +632,17 @@ class Engine:
         bias = st.hbias if st.net.head_parts is not None else st.params[st.net.head + '.bias']
         self.ops.rowdot(feats, n, F, st.whead[out_index * F:(out_index + 1) * F], bias, out_index, out)
 
+    def _head_grad_row(self, st: NetState, out_index):
+        """Gradient slice of row `out_index` of the [outputs][F] head weight (one tensor, or the region the parts share)."""
+        F = st.net.feature_size
+        if st.net.head_parts is not None:
+            return st.grad[st.head_gbase + out_index * F:st.head_gbase + (out_index + 1) * F]
+        return st.g(st.net.head + '.weight')[out_index * F:(out_index + 1) * F]
+
     def _head_grads(self, st: NetState, feats, n, out_index, drow):
         F = st.net.feature_size
         parts = st.net.parts()
-        o0, _ = st.gslices[parts[0][0] + '.weight']            # the parts' weight gradients are contiguous, column order
-        gw = st.grad[o0 + out_index * F:o0 + (out_index + 1) * F]
-        self.ops.colsum(feats, n, F, gw, 0, drow)
+        self.ops.colsum(feats, n, F, self._head_grad_row(st, out_index), 0, drow)
         for h, _ in parts:
             self.ops.colsum(drow, n, 1, st.g(h + '.bias')[out_index:out_index + 1], 0, None)
 
@@ -671,8 +710,6 @@ class Engine:
         F = net.feature_size
         fact, fslope = net.feature_act
         dggan = cfg.method == 'dggan'
-        if dggan and net.graph is not None:
-            raise NotImplementedError('DG-GAN on a graph discriminator (crowd/dggan.py KnnDenseNetCatDggan) has no B200 path')
         acts = self.alloc_acts('D', net, 5 * B)
         deltas = self.alloc_deltas('D', net, 5 * B)
         a_in = self._in(net, acts)
@@ -760,12 +797,10 @@ class Engine:
             self.backward(D, acts, deltas, 0, 4 * B, 0, 5 * B, hook=hook)
         else:
             # dP/dW_head[1,:] = sum_n u_L,n ; the Jacobian term vanishes (target is linear in the features)
-            ops.colsum(fblk(4 * B, 5 * B), B, F, D.g(net.head + '.weight')[F:2 * F], 0, None)
+            ops.colsum(fblk(4 * B, 5 * B), B, F, self._head_grad_row(D, 1), 0, None)
             # DG-GAN: rows [3B,4B) carry no ordinary gradient; weight grads = rows [0,3B) + tangent block [4B,5B)
-            self.backward(D, acts, deltas, 0, 3 * B, 0, 3 * B)
-            for i, l in enumerate(net.layers, 1):
-                self._wgrad_layer(D, l, self.rows(acts[i - 1], l.in_elems, 4 * B, 5 * B),
-                                  self.rows(deltas[i], l.out_elems, 4 * B, 5 * B), B, lo=4 * B)
+            self.backward(D, acts, deltas, 0, 3 * B, 0, 3 * B, hook=hook)
+            self.tangent_block_grads(D, acts, deltas, 4 * B, 5 * B)
         self.adam(D, cfg.learning_rate, cfg.weight_decay, cfg.betas, cfg.eps)                     # srgan.py:297
         if not train_generator:
             return

@@ -204,7 +204,7 @@ class KnnDenseNetCat(_Container):
     the model zoo, crowd/models.py:1103-1127): load a state_dict to start from pretrained weights."""
 
     def __init__(self, growth_rate=32, block_config=(6, 12, 48, 32), num_init_features=64, bn_size=4, label_patch_size=224,
-                 image_size=224):
+                 image_size=224, number_of_outputs=1):
         super().__init__()
         g, bs = growth_rate, bn_size
         self.dense_blocks = nn.ModuleList()
@@ -231,9 +231,10 @@ class KnnDenseNetCat(_Container):
             k = L // (image_size // (8 * 2 ** (i - 1)))
             self.add_module(f'map_module{i}', _Named(
                 map_transposed_conv_layer=nn.ConvTranspose2d(ci, 1, k, k), conv1=nn.Conv2d(1, 8, 2, 2), conv2=nn.Conv2d(8, 16, 2, 2),
-                conv3=nn.Conv2d(16, 32, 2, 2), linear1=nn.Conv2d(32, 20, L // 8), count_layer=nn.Conv2d(20, 1, 1)))
+                conv3=nn.Conv2d(16, 32, 2, 2), linear1=nn.Conv2d(32, 20, L // 8),
+                count_layer=nn.Conv2d(20, number_of_outputs, 1)))
         self.final_count_feature_layer = nn.Conv2d(c, 20, 1)
-        self.count_layer = nn.Conv2d(20, 1, 1)
+        self.count_layer = nn.Conv2d(20, number_of_outputs, 1)     # 2: KnnDenseNetCatDggan (crowd/models.py:929-1046)
 
 
 # ------------------------------------------------------------------------------------------------ the runner
@@ -657,14 +658,13 @@ class Experiment:
             self.D = DcganDiscriminator(**dk)
             self.DNN = DcganDiscriminator(**dk)
         elif application == 'crowd':                                        # crowd/srgan.py:92-96 model_setup
-            if method != 'srgan':
-                raise NotImplementedError('crowd DG-GAN (crowd/dggan.py) has no B200 path')
             dk = {k: v for k, v in model_kwargs.items() if k in ('growth_rate', 'block_config', 'num_init_features', 'bn_size',
                                                                  'label_patch_size', 'image_size')}
             gk = {k: v for k, v in model_kwargs.items() if k in ('z_dim', 'conv_dim')}
             self.G = DcganGenerator(image_size=dk.get('image_size', 224), **gk)
-            self.D = KnnDenseNetCat(**dk)
-            self.DNN = KnnDenseNetCat(**dk)
+            n_out = 2 if method == 'dggan' else 1                          # crowd/dggan.py:11-15
+            self.D = KnnDenseNetCat(number_of_outputs=n_out, **dk)
+            self.DNN = KnnDenseNetCat(number_of_outputs=n_out, **dk)
         else:
             raise NotImplementedError(f'application {application!r}: no B200 path yet')
         for m in (self.D, self.G, self.DNN):

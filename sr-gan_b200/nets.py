@@ -254,7 +254,7 @@ def dcgan_g(image_size=128, conv_dim=64, z_dim=256) -> Net:
 
 
 def knn_densenet_cat(block_config=(6, 12, 48, 32), growth_rate=32, num_init_features=64, bn_size=4, image_size=224,
-                     label_size=224, pad_to=64) -> Net:
+                     label_size=224, pad_to=64, n_out=1) -> Net:
     """crowd/models.py:1049-1166 KnnDenseNetCat as a graph.  Buffers: 'x' input; 'c0','n0' stem; 'cat{i}' the in-place
     concat buffer of dense block i (the stem pool / transition pool write its first channels, every dense layer appends
     growth_rate channels); per dense layer 'n1','b','n2','new'; per transition 'tn','tc'; per MapModule 't','map','m1'..
@@ -364,7 +364,8 @@ def knn_densenet_cat(block_config=(6, 12, 48, 32), growth_rate=32, num_init_feat
     # the ops must be in an order where every buffer is complete before it is read: move the head ops to the end (they
     # were appended after the trunk already) -- and the final-count ops precede the feature copy of slice 3: fine.
     head_parts = [(f'map_module{i}.count_layer', 20) for i in (1, 2, 3)] + [('count_layer', 20)]
-    return Net('D', 'crowd', layers, head='count_layer', head_outputs=1, head_master_kind='parts',
+    # n_out = 2: KnnDenseNetCatDggan (crowd/models.py:929-1046), every count layer has a second (DG-GAN score) output
+    return Net('D', 'crowd', layers, head='count_layer', head_outputs=n_out, head_master_kind='parts',
                input_chw=(3, image_size, image_size), feature_chw=(F, 1, 1), graph=ops, bufs=bufs, input_buf='x',
                feature_buf='features', head_parts=head_parts, map_bufs=tuple(maps), label_size=L)
 
@@ -394,7 +395,7 @@ def describe_module(module) -> Net:
         label = sd['map_module1.linear1.weight'][2] * 8
         k1 = sd['map_module1.map_transposed_conv_layer.weight'][2]
         image = (label // k1) * 8
-        return knn_densenet_cat(cfg, growth, init, bn_size, image, label)
+        return knn_densenet_cat(cfg, growth, init, bn_size, image, label, n_out=sd['count_layer.weight'][0])
     if 'fc.0.weight' in sd and 'layer4.0.weight' in sd:
         z_dim, c8, k, _ = sd['fc.0.weight']
         return dcgan_g(k * 16, c8 // 8, z_dim)

@@ -26,6 +26,7 @@ def modules_from_state(st: O.OracleState, **dcgan_kwargs):
         z_dim, c8, k, _ = st.G['fc.0.weight'].shape
         kw = dict(growth_rate=sp.growth_rate, block_config=sp.block_config, num_init_features=sp.num_init_features,
                   bn_size=sp.bn_size, label_patch_size=sp.label_patch_size, image_size=k * 16)
+        kw['number_of_outputs'] = 2 if sp.dggan else 1
         D, DNN = srgan_b200.KnnDenseNetCat(**kw), srgan_b200.KnnDenseNetCat(**kw)
         G = srgan_b200.DcganGenerator(z_dim, k * 16, c8 // 8)
     else:

@@ -194,12 +194,13 @@ def test_coefficient_persistent_kernel_matches_generic_kernels(method, B):
 CROWD_SMALL = dict(block_config=(2, 2, 2, 2), growth_rate=8, num_init_features=16, bn_size=2, label_patch_size=64)
 
 
+@pytest.mark.parametrize('method', ['srgan', 'dggan'])
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
-def test_crowd_small_seeded_vs_oracle(precision):
+def test_crowd_small_seeded_vs_oracle(precision, method):
     """Crowd SR-GAN on a reduced KnnDenseNetCat (2,2,2,2 / growth 8 / 64x64): CUDA graph-net path (BN-affine, pools, concat
     slices, MapModules, crowd labeled loss incl. map term, gradient penalty through all of it) vs the oracle, two steps."""
-    st = O.init_crowd(seed=1, image_size=64, z_dim=16, g_conv_dim=8, scale=2.0, **CROWD_SMALL)
-    cfg = O.StepConfig(batch_size=3, matching_loss_multiplier=1e3, contrasting_loss_multiplier=1e2,
+    st = O.init_crowd(seed=1, image_size=64, z_dim=16, g_conv_dim=8, scale=2.0, dggan=(method == 'dggan'), **CROWD_SMALL)
+    cfg = O.StepConfig(method=method, batch_size=3, matching_loss_multiplier=1e3, contrasting_loss_multiplier=1e2,
                        gradient_penalty_multiplier=1e2, map_multiplier=1e-3)
     r = runner_from_state(st, cfg, precision)
     t = TOL[precision]['scalar']
@@ -210,7 +211,7 @@ def test_crowd_small_seeded_vs_oracle(precision):
         xc, yc, uc, zc, ac, z2c = to_cuda(x, y, u, z, alpha, z2)
         if i == 0:
             pred, feats = r.predict(xc)
-            (c_ref, _), _, f_ref = O.d_forward(st0.d_spec, st0.D, x)
+            (c_ref, _), _s, f_ref = O.d_forward(st0.d_spec, st0.D, x)
             assert rel(pred, c_ref) < t and rel(feats, f_ref) < t
         r.dnn_step(xc, yc)
         r.gan_step(xc, yc, uc, i, noise=(zc, ac, z2c))
@@ -230,21 +231,22 @@ def test_crowd_small_seeded_vs_oracle(precision):
             assert (merr < 2e-2) if precision == 'fp32' else (cos > 0.7 or upd_ref.numel() < 64), (net, k, merr, cos)
 
 
+@pytest.mark.parametrize('method', ['srgan', 'dggan'])
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
-def test_crowd_full_size_matches_reference_golden(precision):
+def test_crowd_full_size_matches_reference_golden(precision, method):
     """BASELINE configs[2] architecture at full size (DenseNet-201 KnnDenseNetCat + DCGenerator, 224x224, B=2) against
     the scalars the UNMODIFIED reference produced (tests/golden/crowd_srgan.npz; state and inputs regenerated from seeds)."""
     import json
     import os
     import numpy as np
     from tests.golden_io import GOLDEN_DIR
-    z = np.load(os.path.join(GOLDEN_DIR, 'crowd_srgan.npz'))
+    z = np.load(os.path.join(GOLDEN_DIR, f'crowd_{method}.npz'))
     cfgj = json.loads(bytes(z['config_json']).decode())
     cfg = O.StepConfig()
     for k, v in cfgj.items():
         if hasattr(cfg, k):
             setattr(cfg, k, v)
-    st = O.init_crowd(seed=cfgj['init_seed'], scale=cfgj['d_scale'])
+    st = O.init_crowd(seed=cfgj['init_seed'], scale=cfgj['d_scale'], dggan=(method == 'dggan'))
     r = runner_from_state(st, cfg, precision)
     x, y, u, zz, alpha, z2 = to_cuda(*O.synthetic_crowd_batch(2, cfgj['input_seed']))
     r.dnn_step(x, y)
