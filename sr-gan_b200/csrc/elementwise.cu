@@ -5,43 +5,93 @@
 
 // ------------------------------------------------------------------------------------------------------------
 // colsum: out[c % mod] += sum_r rowscale[r] * X[r, c]
-// block = 32 column-lanes (4 columns each when VEC) x 8 row-lanes; grid.y splits the rows.
+// VEC (cols % 4 == 0): a lane owns 4 consecutive columns; a warp covers cvp = min(32, pow2 >= cols/4) column groups and
+// 32/cvp rows per sweep (narrow matrices fold rows into the spare lanes), 8 warps per block, 4 independent row sweeps in
+// flight per thread; grid.y splits the rows.  Narrow (cols <= 8, any alignment): one thread per row, the row's elements in
+// registers (consecutive threads read consecutive rows: coalesced).  Otherwise: one column per lane.
 // ------------------------------------------------------------------------------------------------------------
-template <typename T, bool VEC>
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ X, long long rows, int cols,
+                                                         float* __restrict__ out, int mod,
+                                                         const float* __restrict__ rowscale, int lg) {
+    __shared__ float red[8][32][4];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int cvp = 1 << lg, rpw = 32 >> lg;                       // column groups per warp, rows per warp sweep
+    const int c = (blockIdx.x * 32 + (lane & (cvp - 1))) * 4;
+    const int rsub = lane >> lg;
+    const long long rstep = (long long)gridDim.y * 8 * rpw;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    if (c < cols) {
+        long long r = ((long long)blockIdx.y * 8 + w) * rpw + rsub;
+        for (; r + 3 * rstep < rows; r += 4 * rstep) {
+            const float4 v0 = ld4(X + r * cols + c), v1 = ld4(X + (r + rstep) * cols + c);
+            const float4 v2 = ld4(X + (r + 2 * rstep) * cols + c), v3 = ld4(X + (r + 3 * rstep) * cols + c);
+            float s0 = 1.f, s1 = 1.f, s2 = 1.f, s3 = 1.f;
+            if (rowscale) { s0 = rowscale[r]; s1 = rowscale[r + rstep]; s2 = rowscale[r + 2 * rstep]; s3 = rowscale[r + 3 * rstep]; }
+            a0.x = fmaf(s0, v0.x, a0.x); a0.y = fmaf(s0, v0.y, a0.y); a0.z = fmaf(s0, v0.z, a0.z); a0.w = fmaf(s0, v0.w, a0.w);
+            a1.x = fmaf(s1, v1.x, a1.x); a1.y = fmaf(s1, v1.y, a1.y); a1.z = fmaf(s1, v1.z, a1.z); a1.w = fmaf(s1, v1.w, a1.w);
+            a2.x = fmaf(s2, v2.x, a2.x); a2.y = fmaf(s2, v2.y, a2.y); a2.z = fmaf(s2, v2.z, a2.z); a2.w = fmaf(s2, v2.w, a2.w);
+            a3.x = fmaf(s3, v3.x, a3.x); a3.y = fmaf(s3, v3.y, a3.y); a3.z = fmaf(s3, v3.z, a3.z); a3.w = fmaf(s3, v3.w, a3.w);
+        }
+        for (; r < rows; r += rstep) {
+            const float4 v = ld4(X + r * cols + c);
+            const float sc = rowscale ? rowscale[r] : 1.f;
+            a0.x = fmaf(sc, v.x, a0.x); a0.y = fmaf(sc, v.y, a0.y); a0.z = fmaf(sc, v.z, a0.z); a0.w = fmaf(sc, v.w, a0.w);
+        }
+    }
+    red[w][lane][0] = a0.x + a1.x + a2.x + a3.x; red[w][lane][1] = a0.y + a1.y + a2.y + a3.y;
+    red[w][lane][2] = a0.z + a1.z + a2.z + a3.z; red[w][lane][3] = a0.w + a1.w + a2.w + a3.w;
+    __syncthreads();
+    // threads 0 .. cvp*4-1: column (group g, element j) summed over the 8 warps and the rpw row-lanes
+    if ((int)threadIdx.x < cvp * 4) {
+        const int g = threadIdx.x >> 2, j = threadIdx.x & 3;
+        const int cc = (blockIdx.x * 32 + g) * 4 + j;
+        if (cc < cols) {
+            float sum = 0.f;
+            for (int y = 0; y < 8; ++y)
+                for (int q = 0; q < rpw; ++q) sum += red[y][g + q * cvp][j];
+            atomicAdd(out + (mod ? cc % mod : cc), sum);
+        }
+    }
+}
+
+template <typename T, int COLS>
+__global__ void __launch_bounds__(256) colsum_narrow_kernel(const T* __restrict__ X, long long rows, float* __restrict__ out,
+                                                            int mod, const float* __restrict__ rowscale) {
+    __shared__ float red[32];
+    float acc[COLS];
+#pragma unroll
+    for (int j = 0; j < COLS; ++j) acc[j] = 0.f;
+    for (long long r = (long long)blockIdx.x * 256 + threadIdx.x; r < rows; r += 256LL * gridDim.x) {
+        const float sc = rowscale ? rowscale[r] : 1.f;
+#pragma unroll
+        for (int j = 0; j < COLS; ++j) acc[j] = fmaf(sc, to_f(X[r * COLS + j]), acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < COLS; ++j) {
+        const float v = block_sum(acc[j], red);
+        if (threadIdx.x == 0) atomicAdd(out + (mod ? j % mod : j), v);
+    }
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, long long rows, int cols,
                                                      float* __restrict__ out, int mod,
                                                      const float* __restrict__ rowscale) {
-    constexpr int CPT = VEC ? 4 : 1;
-    __shared__ float red[8][32 * CPT + 1];
+    __shared__ float red[8][33];
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-    const int c = (blockIdx.x * 32 + lx) * CPT;
-    float acc[CPT];
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) acc[j] = 0.f;
-    if (c < cols) {
-        for (long long r = (long long)blockIdx.y * 8 + ly; r < rows; r += 8LL * gridDim.y) {
-            float s = rowscale ? rowscale[r] : 1.f;
-            if (VEC) {
-                float4 v = ld4(X + r * cols + c);
-                acc[0] = fmaf(s, v.x, acc[0]); acc[1 % CPT] = fmaf(s, v.y, acc[1 % CPT]);
-                acc[2 % CPT] = fmaf(s, v.z, acc[2 % CPT]); acc[3 % CPT] = fmaf(s, v.w, acc[3 % CPT]);
-            } else {
-                acc[0] = fmaf(s, to_f(X[r * cols + c]), acc[0]);
-            }
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) red[ly][lx * CPT + j] = acc[j];
+    const int c = blockIdx.x * 32 + lx;
+    float acc = 0.f;
+    if (c < cols)
+        for (long long r = (long long)blockIdx.y * 8 + ly; r < rows; r += 8LL * gridDim.y)
+            acc = fmaf(rowscale ? rowscale[r] : 1.f, to_f(X[r * cols + c]), acc);
+    red[ly][lx] = acc;
     __syncthreads();
     if (ly == 0 && c < cols) {
+        float sum = 0.f;
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) {
-            float s = 0.f;
-#pragma unroll
-            for (int y = 0; y < 8; ++y) s += red[y][lx * CPT + j];
-            int oc = mod ? (c + j) % mod : (c + j);
-            atomicAdd(out + oc, s);
-        }
+        for (int y = 0; y < 8; ++y) sum += red[y][lx];
+        atomicAdd(out + (mod ? c % mod : c), sum);
     }
 }
 
@@ -49,17 +99,42 @@ template <typename T>
 static int launch_colsum(const T* X, long long rows, int cols, float* out, int mod, const float* rowscale,
                          cudaStream_t st) {
     if (rows <= 0 || cols <= 0) return SRGAN_OK;
-    bool vec = (cols % 4 == 0);
-    int cpb = vec ? 128 : 32;
-    int gx = cdiv(cols, cpb);
+    const bool vec = (cols % 4 == 0);
+    if (!vec && cols <= 8 && rows >= 4096) {
+        long long b = (rows + 256 * 8 - 1) / (256 * 8);
+        const int grid = (int)(b > 8LL * kNumSMs ? 8LL * kNumSMs : b);
+        switch (cols) {
+            case 1: colsum_narrow_kernel<T, 1><<<grid, 256, 0, st>>>(X, rows, out, mod, rowscale); break;
+            case 2: colsum_narrow_kernel<T, 2><<<grid, 256, 0, st>>>(X, rows, out, mod, rowscale); break;
+            case 3: colsum_narrow_kernel<T, 3><<<grid, 256, 0, st>>>(X, rows, out, mod, rowscale); break;
+            case 5: colsum_narrow_kernel<T, 5><<<grid, 256, 0, st>>>(X, rows, out, mod, rowscale); break;
+            case 6: colsum_narrow_kernel<T, 6><<<grid, 256, 0, st>>>(X, rows, out, mod, rowscale); break;
+            default: colsum_narrow_kernel<T, 7><<<grid, 256, 0, st>>>(X, rows, out, mod, rowscale); break;
+        }
+        SRGAN_CHECK_LAUNCH("colsum_narrow_kernel");
+        return SRGAN_OK;
+    }
+    if (vec) {
+        int lg = 0;
+        while (lg < 5 && (1 << lg) < cols / 4) ++lg;
+        const int rows_per_sweep = 8 * (32 >> lg);
+        const int gx = cdiv(cols, 128);
+        long long want = (8LL * kNumSMs + gx - 1) / gx;
+        long long maxy = (rows + 4LL * rows_per_sweep - 1) / (4LL * rows_per_sweep);      // >= 4 sweeps per block
+        long long gy = want < maxy ? want : maxy;
+        if (gy < 1) gy = 1;
+        if (gy > 65535) gy = 65535;
+        colsum_vec_kernel<T><<<dim3(gx, (unsigned)gy), 256, 0, st>>>(X, rows, cols, out, mod, rowscale, lg);
+        SRGAN_CHECK_LAUNCH("colsum_vec_kernel");
+        return SRGAN_OK;
+    }
+    const int gx = cdiv(cols, 32);
     long long want = (4LL * kNumSMs + gx - 1) / gx;
     long long maxy = (rows + 31) / 32;                 // >= 4 rows per row-lane
     long long gy = want < maxy ? want : maxy;
     if (gy < 1) gy = 1;
     if (gy > 65535) gy = 65535;
-    dim3 grid(gx, (unsigned)gy);
-    if (vec) colsum_kernel<T, true><<<grid, 256, 0, st>>>(X, rows, cols, out, mod, rowscale);
-    else colsum_kernel<T, false><<<grid, 256, 0, st>>>(X, rows, cols, out, mod, rowscale);
+    colsum_kernel<T><<<dim3(gx, (unsigned)gy), 256, 0, st>>>(X, rows, cols, out, mod, rowscale);
     SRGAN_CHECK_LAUNCH("colsum_kernel");
     return SRGAN_OK;
 }

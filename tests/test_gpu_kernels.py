@@ -106,7 +106,8 @@ def test_bias_mod_epilogue(ops, dt):
 
 @pytest.mark.parametrize('dt', DT)
 @pytest.mark.parametrize('rows,cols,mod', [(100, 32768, 0), (64 * 64 * 7, 64, 0), (5000, 10, 0), (37, 1, 0),
-                                           (6, 128, 8), (1000, 50, 0)])
+                                           (6, 128, 8), (1000, 50, 0), (20001, 3, 0), (8192, 64, 0), (301, 20, 0),
+                                           (5000, 1, 0), (9000, 8, 4), (4097, 6, 3)])
 def test_colsum_rowdot_seed(ops, dt, rows, cols, mod):
     gen = torch.Generator().manual_seed(rows + cols)
     ref = TorchOps()
@@ -212,19 +213,29 @@ def test_gradient_penalty_kernels(ops, dt, rows, cols):
     close(u0, u0_ref, tol(dt) * 2, 'u0')
 
 
-def test_adam_and_repack(ops):
+@pytest.mark.parametrize('dims,kind', [((6, 5, 4, 4), 'conv'), ((72, 40, 4, 4), 'conv'), ((33, 50, 3, 3), 'conv'),
+                                       ((128, 96, 1, 1), 'conv'), ((20, 9, 7, 7), 'conv'), ((24, 40, 8, 8), 'fc_up'),
+                                       ((64, 3, 4, 4), 'thin')])
+def test_adam_and_repack(ops, dims, kind):
+    """dims[0]*dims[1]*... >= 4096 with both leading dims >= 8 takes the shared-memory tiled kernel (transposed layouts),
+    the rest the element-wise one; fc_up / thin are the other stride patterns engine.py produces."""
     gen = torch.Generator().manual_seed(9)
     ref = TorchOps()
-    dims = (6, 5, 4, 4)                      # master [a][b][r][s]
-    a, b, r, s = dims
-    wd_s, wu_s = (r * s * b, 1, s * b, b), (1, r * s * a, s * a, a)
-    n = a * b * r * s
+    a, b, r, s = dims                        # master [a][b][r][s]
+    if kind == 'conv':
+        wd_s, wu_s = (r * s * b, 1, s * b, b), (1, r * s * a, s * a, a)
+    elif kind == 'fc_up':                    # master[zb][c][k][k] as a Linear (engine._strides_for)
+        zb, c, k = a, b, r
+        wd_s, wu_s = (1, zb, k * c * zb, c * zb), (k * k * c, 1, k * c, c)
+    else:                                    # thin-layer lowering (engine._thin_strides), KPAD = 64
+        wd_s, wu_s = (64, 1, s * b, b), (1, a, s * b * a, b * a)
+    n = a * b * r * s if kind != 'thin' else a * 64
     for od in (torch.float32, torch.bfloat16):
         p_ref = rnd(gen, *dims)
         grad, m_ref, v_ref = rnd(gen, n), rnd(gen, n) * 0.1, rnd(gen, n).abs() * 0.01
-        o1_ref, o2_ref = torch.empty(n, dtype=od), torch.empty(n, dtype=od)
+        o1_ref, o2_ref = torch.zeros(n, dtype=od), torch.zeros(n, dtype=od)
         p, m, v = p_ref.clone().cuda(), m_ref.clone().cuda(), v_ref.clone().cuda()
-        o1, o2 = torch.empty(n, dtype=od, device='cuda'), torch.empty(n, dtype=od, device='cuda')
+        o1, o2 = torch.zeros(n, dtype=od, device='cuda'), torch.zeros(n, dtype=od, device='cuda')
         ref.repack(p_ref, dims, o1_ref, wd_s, o2_ref, wu_s)
         ops.repack(p, dims, o1, wd_s, o2, wu_s)
         close(o1, o1_ref, 1e-7, 'repack1'); close(o2, o2_ref, 1e-7, 'repack2')
