@@ -222,6 +222,91 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ 
     }
 }
 
+// 4-channel-per-thread versions (C % 4 == 0 and 4-aligned pitches): the window scan is done once for four channels
+template <typename T>
+__device__ __forceinline__ void window_argmax4(const T* __restrict__ xr, int H, int W, int C, int ho, int wo, int k, int s, int p,
+                                               int (&arg)[4]) {
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    arg[0] = arg[1] = arg[2] = arg[3] = -1;
+    const int h0 = ho * s - p, w0 = wo * s - p;
+    for (int dh = 0; dh < k; ++dh) {
+        const int h = h0 + dh;
+        if (h < 0 || h >= H) continue;
+        for (int dw = 0; dw < k; ++dw) {
+            const int w = w0 + dw;
+            if (w < 0 || w >= W) continue;
+            const float4 v = ld4(xr + ((long long)h * W + w) * C);
+            const int pos = h * W + w;
+            if (v.x > best[0] || arg[0] < 0) { best[0] = v.x; arg[0] = pos; }
+            if (v.y > best[1] || arg[1] < 0) { best[1] = v.y; arg[1] = pos; }
+            if (v.z > best[2] || arg[2] < 0) { best[2] = v.z; arg[2] = pos; }
+            if (v.w > best[3] || arg[3] < 0) { best[3] = v.w; arg[3] = pos; }
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool4_kernel(const T* __restrict__ x, const T* __restrict__ xref, T* __restrict__ y,
+                                                       int y_pitch, int y_c0, int n, int H, int W, int C, int Ho, int Wo, int k,
+                                                       int s, int p) {
+    const int C4 = C / 4;
+    const long long total = (long long)n * Ho * Wo * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4) * 4;
+        long long t = i / C4;
+        const int wo = (int)(t % Wo); t /= Wo;
+        const int ho = (int)(t % Ho);
+        const long long b = t / Ho;
+        const long long base = b * H * W * C + c;
+        int arg[4];
+        window_argmax4(xref + base, H, W, C, ho, wo, k, s, p, arg);
+        float4 o;
+        o.x = arg[0] >= 0 ? to_f(x[base + (long long)arg[0] * C]) : 0.f;
+        o.y = arg[1] >= 0 ? to_f(x[base + (long long)arg[1] * C + 1]) : 0.f;
+        o.z = arg[2] >= 0 ? to_f(x[base + (long long)arg[2] * C + 2]) : 0.f;
+        o.w = arg[3] >= 0 ? to_f(x[base + (long long)arg[3] * C + 3]) : 0.f;
+        st4(y + ((b * Ho + ho) * Wo + wo) * y_pitch + y_c0 + c, o);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_bwd4_kernel(const T* __restrict__ xref, const T* __restrict__ dy, int dy_pitch,
+                                                           int dy_c0, T* __restrict__ dx, int n, int H, int W, int C, int Ho,
+                                                           int Wo, int k, int s, int p, int act, float slope) {
+    const int C4 = C / 4;
+    const long long total = (long long)n * H * W * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4) * 4;
+        long long t = i / C4;
+        const int w = (int)(t % W); t /= W;
+        const int h = (int)(t % H);
+        const long long b = t / H;
+        const long long base = b * H * W * C + c;
+        int ho_lo = (h + p - k + 1 + s - 1) / s, ho_hi = (h + p) / s;
+        int wo_lo = (w + p - k + 1 + s - 1) / s, wo_hi = (w + p) / s;
+        if (h + p - k + 1 < 0) ho_lo = 0;
+        if (w + p - k + 1 < 0) wo_lo = 0;
+        ho_hi = min(ho_hi, Ho - 1); wo_hi = min(wo_hi, Wo - 1);
+        const int me = h * W + w;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ho = ho_lo; ho <= ho_hi; ++ho)
+            for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+                int arg[4];
+                window_argmax4(xref + base, H, W, C, ho, wo, k, s, p, arg);
+                const float4 d = ld4(dy + ((b * Ho + ho) * Wo + wo) * dy_pitch + dy_c0 + c);
+                if (arg[0] == me) acc.x += d.x;
+                if (arg[1] == me) acc.y += d.y;
+                if (arg[2] == me) acc.z += d.z;
+                if (arg[3] == me) acc.w += d.w;
+            }
+        const long long xi = base + (long long)me * C;
+        const float4 hx = ld4(xref + xi);
+        acc.x *= act_bwd(hx.x, act, slope); acc.y *= act_bwd(hx.y, act, slope);
+        acc.z *= act_bwd(hx.z, act, slope); acc.w *= act_bwd(hx.w, act, slope);
+        st4(dx + xi, acc);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) avgpool_kernel(const T* __restrict__ x, int x_pitch, T* __restrict__ y, int y_pitch, int y_c0,
                                                       int n, int H, int W, int C, int k) {
@@ -512,7 +597,10 @@ int srgan_maxpool(const void* x, const void* xref, void* y, int y_pitch, int y_c
     if (n == 0) return SRGAN_OK;
     const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
     cudaStream_t st = (cudaStream_t)stream;
-    DISPATCH_T(dtype, maxpool_kernel<T><<<ew_grid((long long)n * Ho * Wo * C), 256, 0, st>>>((const T*)x, (const T*)(xref ? xref : x), (T*)y, y_pitch, y_c0, n, H, W, C, Ho, Wo, k, stride, pad));
+    const bool vec = vec_ok(C, y_pitch, y_c0);
+    DISPATCH_T(dtype,
+               if (vec) maxpool4_kernel<T><<<ew_grid((long long)n * Ho * Wo * C / 4), 256, 0, st>>>((const T*)x, (const T*)(xref ? xref : x), (T*)y, y_pitch, y_c0, n, H, W, C, Ho, Wo, k, stride, pad);
+               else maxpool_kernel<T><<<ew_grid((long long)n * Ho * Wo * C), 256, 0, st>>>((const T*)x, (const T*)(xref ? xref : x), (T*)y, y_pitch, y_c0, n, H, W, C, Ho, Wo, k, stride, pad));
     SRGAN_CHECK_LAUNCH("maxpool_kernel");
     return SRGAN_OK;
 }
@@ -524,7 +612,10 @@ int srgan_maxpool_bwd(const void* xref, const void* dy, int dy_pitch, int dy_c0,
     if (n == 0) return SRGAN_OK;
     const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
     cudaStream_t st = (cudaStream_t)stream;
-    DISPATCH_T(dtype, maxpool_bwd_kernel<T><<<ew_grid((long long)n * H * W * C), 256, 0, st>>>((const T*)xref, (const T*)dy, dy_pitch, dy_c0, (T*)dx, n, H, W, C, Ho, Wo, k, stride, pad, act, slope));
+    const bool vec = vec_ok(C, dy_pitch, dy_c0);
+    DISPATCH_T(dtype,
+               if (vec) maxpool_bwd4_kernel<T><<<ew_grid((long long)n * H * W * C / 4), 256, 0, st>>>((const T*)xref, (const T*)dy, dy_pitch, dy_c0, (T*)dx, n, H, W, C, Ho, Wo, k, stride, pad, act, slope);
+               else maxpool_bwd_kernel<T><<<ew_grid((long long)n * H * W * C), 256, 0, st>>>((const T*)xref, (const T*)dy, dy_pitch, dy_c0, (T*)dx, n, H, W, C, Ho, Wo, k, stride, pad, act, slope));
     SRGAN_CHECK_LAUNCH("maxpool_bwd_kernel");
     return SRGAN_OK;
 }

@@ -372,10 +372,11 @@ def test_copy2d_and_pools(ops, dt):
             ops.copy2d(cu(src), sp, s0, d, dp, d0, rows, C, acc)
             close(d, d_ref, tol(dt), 'copy2d')
     # max-pool 3/2/1 (stem) incl. ReLU-style ties at zero, odd extent; tangent routing; backward
-    for n, H, W, C, k, s, p in ((2, 16, 16, 8, 3, 2, 1), (3, 9, 11, 5, 3, 2, 1), (2, 8, 8, 4, 2, 2, 0)):
+    for n, H, W, C, k, s, p in ((2, 16, 16, 8, 3, 2, 1), (3, 9, 11, 5, 3, 2, 1), (2, 8, 8, 4, 2, 2, 0), (2, 14, 14, 64, 3, 2, 1),
+                                (1, 6, 6, 2, 3, 2, 1)):
         x = torch.relu(rnd(gen, n * H * W * C)).to(dt)
         Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
-        pitch, c0 = C + 6, 2
+        pitch, c0 = (C + 8, 4) if C % 4 == 0 else (C + 6, 2)        # 4-aligned slices take the 4-channel kernels
         y_ref = torch.zeros(n * Ho * Wo * pitch, dtype=dt)
         y = y_ref.clone().cuda()
         ref.maxpool(x, None, y_ref, pitch, c0, n, H, W, C, k, s, p)
