@@ -5,7 +5,8 @@
 //   generic kernels, ONE launch per step method here (`phases`: 1 = dnn_training_step, 2 = gan_training_step, 3 = both).
 // Layout of the work: the three networks (2.4 k parameters) live in shared memory; every thread owns one sample per
 // round and keeps only 10-wide vectors in registers; 50-wide vectors (inputs, fake, x_hat, dLoss/dinput) are streamed
-// through the thread's own row of a shared staging tile.  Batch-wide sums (feature sums, losses) are per-CTA partials in
+// through the thread's own column of a shared staging tile ([slot][sample]: conflict-free, and 4 samples per LDS.128 in the
+// outer-product sums); weight matrices sit in shared memory with rows padded to 12 floats (three LDS.128 per row).  Batch-wide sums (feature sums, losses) are per-CTA partials in
 // a caller workspace, combined after a grid-wide sync in a fixed order (bit-reproducible); weight gradients are
 // CTA-level outer-product sums over the staging tile (one table-driven loop for every tensor of a net), flushed with
 // fp32 atomics into the engine's flat gradient buffers, which the in-kernel Adam reads and re-zeroes.
@@ -26,8 +27,9 @@ constexpr int CT = 64;         // threads (= samples per round) per CTA
 constexpr float SLOPE = 0.01f;
 constexpr int MAXG = kNumSMs;  // grid size bound (one CTA per SM)
 
-// staging tile: one row per sample of the CTA.  [0,50) = a 50-wide vector, then seven 10-wide slots, then 3 scalars.
-constexpr int PITCH = 123;     // odd: conflict-free row writes and column reads
+// staging tile [slot][sample]: per sample, slots [0,50) = a 50-wide vector, then seven 10-wide groups, then 3 scalars.
+constexpr int NSLOT = 123;
+constexpr int HP = 12;         // padded row length of the shared-memory weight matrices (10 -> 12: three float4)
 constexpr int O_IN = 0;
 __host__ __device__ constexpr int O_S(int k) { return NIN + H * k; }
 constexpr int O_HV0 = 120, O_HV1 = 121, O_ONE = 122;
@@ -66,15 +68,32 @@ struct CoefParams {
 __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : v * SLOPE; }
 __device__ __forceinline__ float dleaky(float h) { return h > 0.f ? 1.f : SLOPE; }
 
-struct SW { const float *W1, *b1, *W2, *b2, *W3, *b3, *W4, *b4; };     // shared-memory copy of one 4-layer MLP
+// shared-memory copy of one 4-layer MLP.  Matrices are row-padded to HP floats; for discriminator-shaped nets W1 is stored
+// TRANSPOSED ([input j][output o]): one padded row serves both W1 x and W1^T y at input j.
+struct SW { const float *W1, *b1, *W2, *b2, *W3, *b3, *W4, *b4; };
 
-// y[o] = sum_i W[o][i] x[i] (+ b[o]);  W row-major [H][H] in shared memory
+// this thread's column of the staging tile: row[slot]
+struct Row {
+    float* p;
+    __device__ __forceinline__ float& operator[](int i) const { return p[i * CT]; }
+    __device__ __forceinline__ Row operator+(int off) const { return Row{p + off * CT}; }
+};
+__device__ __forceinline__ void ldrow(const float* __restrict__ w, float (&r)[HP]) {
+    const float4 a = *reinterpret_cast<const float4*>(w), b = *reinterpret_cast<const float4*>(w + 4),
+                 c = *reinterpret_cast<const float4*>(w + 8);
+    r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+    r[8] = c.x; r[9] = c.y; r[10] = c.z; r[11] = c.w;
+}
+
+// y[o] = sum_i W[o][i] x[i] (+ b[o]);  W row-major [H][HP] in shared memory
 __device__ __forceinline__ void mv(const float* __restrict__ W, const float* __restrict__ b, const float* x, float* y) {
 #pragma unroll
     for (int o = 0; o < H; ++o) {
+        float r[HP];
+        ldrow(W + o * HP, r);
         float a = b ? b[o] : 0.f;
 #pragma unroll
-        for (int i = 0; i < H; ++i) a = fmaf(W[o * H + i], x[i], a);
+        for (int i = 0; i < H; ++i) a = fmaf(r[i], x[i], a);
         y[o] = a;
     }
 }
@@ -84,9 +103,11 @@ __device__ __forceinline__ void mvt(const float* __restrict__ W, const float* y,
     for (int i = 0; i < H; ++i) x[i] = 0.f;
 #pragma unroll
     for (int o = 0; o < H; ++o) {
+        float r[HP];
+        ldrow(W + o * HP, r);
         const float v = y[o];
 #pragma unroll
-        for (int i = 0; i < H; ++i) x[i] = fmaf(W[o * H + i], v, x[i]);
+        for (int i = 0; i < H; ++i) x[i] = fmaf(r[i], v, x[i]);
     }
 }
 __device__ __forceinline__ void leaky10(float* h) {
@@ -102,14 +123,16 @@ __device__ __forceinline__ void d_tail(const SW& w, float* h1, float* h2, float*
     leaky10(h3);
 }
 // forward of a discriminator-shaped net on the 50-vector in `row` (shared memory)
-__device__ __forceinline__ void d_fwd_row(const SW& w, const float* row, float* h1, float* h2, float* h3) {
+__device__ __forceinline__ void d_fwd_row(const SW& w, const Row row, float* h1, float* h2, float* h3) {
 #pragma unroll
     for (int o = 0; o < H; ++o) h1[o] = w.b1[o];
 #pragma unroll 2
     for (int j = 0; j < NIN; ++j) {
         const float v = row[j];
+        float r[HP];
+        ldrow(w.W1 + j * HP, r);
 #pragma unroll
-        for (int o = 0; o < H; ++o) h1[o] = fmaf(w.W1[o * NIN + j], v, h1[o]);
+        for (int o = 0; o < H; ++o) h1[o] = fmaf(r[o], v, h1[o]);
     }
     d_tail(w, h1, h2, h3);
 }
@@ -124,14 +147,15 @@ __device__ __forceinline__ void g_hidden(const SW& w, const float* zin, float* g
 }
 // one element of the generator output (no activation on the last layer, coefficient/models.py:26)
 __device__ __forceinline__ float g_out(const SW& w, const float* g3, int j) {
-    float a = w.b4[j];
+    float a = w.b4[j], r[HP];
+    ldrow(w.W4 + j * HP, r);
 #pragma unroll
-    for (int i = 0; i < H; ++i) a = fmaf(w.W4[j * H + i], g3[i], a);
+    for (int i = 0; i < H; ++i) a = fmaf(r[i], g3[i], a);
     return a;
 }
 // D(G(z)) with the fake sample streamed: optionally stored into `row`
 template <bool STORE>
-__device__ __forceinline__ void d_fwd_fake(const SW& wd, const SW& wg, const float* g3, float* row, float* h1, float* h2,
+__device__ __forceinline__ void d_fwd_fake(const SW& wd, const SW& wg, const float* g3, const Row row, float* h1, float* h2,
                                            float* h3) {
 #pragma unroll
     for (int o = 0; o < H; ++o) h1[o] = wd.b1[o];
@@ -139,8 +163,10 @@ __device__ __forceinline__ void d_fwd_fake(const SW& wd, const SW& wg, const flo
     for (int j = 0; j < NIN; ++j) {
         const float v = g_out(wg, g3, j);
         if (STORE) row[j] = v;
+        float r[HP];
+        ldrow(wd.W1 + j * HP, r);
 #pragma unroll
-        for (int o = 0; o < H; ++o) h1[o] = fmaf(wd.W1[o * NIN + j], v, h1[o]);
+        for (int o = 0; o < H; ++o) h1[o] = fmaf(r[o], v, h1[o]);
     }
     d_tail(wd, h1, h2, h3);
 }
@@ -155,7 +181,7 @@ __device__ __forceinline__ void d_bwd_hidden(const SW& w, const float* h1, const
 #pragma unroll
     for (int i = 0; i < H; ++i) da1[i] = t[i] * dleaky(h1[i]);
 }
-__device__ __forceinline__ void put10(float* dst, const float* v, float k = 1.f) {
+__device__ __forceinline__ void put10(const Row dst, const float* v, float k = 1.f) {
 #pragma unroll
     for (int i = 0; i < H; ++i) dst[i] = k * v[i];
 }
@@ -254,13 +280,14 @@ __device__ __forceinline__ void accumulate(const float* stage, const int (&pk)[K
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         if ((int)threadIdx.x + k * CT < nelem) {
-            const float* pa = stage + (pk[k] & 0xff);
-            const float* pb = stage + (pk[k] >> 8);
+            const float4* pa = reinterpret_cast<const float4*>(stage + (pk[k] & 0xff) * CT);
+            const float4* pb = reinterpret_cast<const float4*>(stage + (pk[k] >> 8) * CT);
             float a0 = 0.f, a1 = 0.f;
 #pragma unroll 4
-            for (int s = 0; s < CT; s += 2) {
-                a0 = fmaf(pa[s * PITCH], pb[s * PITCH], a0);
-                a1 = fmaf(pa[(s + 1) * PITCH], pb[(s + 1) * PITCH], a1);
+            for (int s = 0; s < CT / 4; s += 2) {
+                const float4 x0 = pa[s], y0 = pb[s], x1 = pa[s + 1], y1 = pb[s + 1];
+                a0 += x0.x * y0.x + x0.y * y0.y + x0.z * y0.z + x0.w * y0.w;
+                a1 += x1.x * y1.x + x1.y * y1.y + x1.z * y1.z + x1.w * y1.w;
             }
             acc[k] += a0 + a1;
         }
@@ -268,36 +295,48 @@ __device__ __forceinline__ void accumulate(const float* stage, const int (&pk)[K
     __syncthreads();
 }
 
-// the CTA's CT consecutive samples of a [B][n] global tensor -> the IN slot of the tile rows (coalesced)
-__device__ __forceinline__ void tile_load(float* stage, const float* __restrict__ src, int first, int B, int n) {
-    const int rows = max(0, min(CT, B - first));       // rows past the batch end are zero-filled (their threads are masked)
-    for (int i = threadIdx.x; i < CT * n; i += CT)
-        stage[(i / n) * PITCH + O_IN + i % n] = i < rows * n ? src[(long long)first * n + i] : 0.f;
-}
-
-__device__ __forceinline__ void load_net(float* dst, const NetP& n, int l1_in, int l4_out) {
-    const int sz[8] = {H * l1_in, H, H * H, H, H * H, H, l4_out * H, l4_out};
-    const float* src[8] = {n.l[0].W, n.l[0].b, n.l[1].W, n.l[1].b, n.l[2].W, n.l[2].b, n.l[3].W, n.l[3].b};
-    int off = 0;
-    for (int k = 0; k < 8; ++k) {
-        for (int i = threadIdx.x; i < sz[k]; i += CT) dst[off + i] = __ldcg(src[k] + i);    // L2: other CTAs update them
-        off += sz[k];
+// this thread's sample of a [B][NIN] global tensor -> the IN slots of its staging column (rows are 200 bytes: float2 loads);
+// threads past the batch end get zeros (they are masked everywhere)
+__device__ __forceinline__ void row_load(const Row row, const float* __restrict__ src, long long sample, bool active) {
+    const float2* p = reinterpret_cast<const float2*>(src + sample * NIN);
+#pragma unroll 5
+    for (int q = 0; q < NIN / 2; ++q) {
+        const float2 v = active ? __ldg(p + q) : make_float2(0.f, 0.f);
+        row[O_IN + 2 * q] = v.x;
+        row[O_IN + 2 * q + 1] = v.y;
     }
 }
-__device__ __forceinline__ SW carve(const float* base, int l1_in, int l4_out) {
+
+// shared-memory layout of a net (floats): W1 | b1 | W2 | b2 | W3 | b3 | W4 | b4, matrices row-padded to HP, vectors to 4
+__host__ __device__ constexpr int pad4(int n) { return (n + 3) / 4 * 4; }
+__host__ __device__ constexpr int net_floats(int l1_in, int l4_out, bool w1_transposed) {
+    return (w1_transposed ? l1_in : H) * HP + pad4(H) + 2 * (H * HP + pad4(H)) + l4_out * HP + pad4(l4_out);
+}
+// dst[r * HP + c] = src[r][c] (or src[c][r] when `transposed`), the pad columns are zero
+__device__ __forceinline__ void load_mat(float* dst, const float* src, int rows, int cols, bool transposed) {
+    for (int i = threadIdx.x; i < rows * HP; i += CT) {
+        const int r = i / HP, c = i % HP;
+        dst[i] = c < cols ? __ldcg(transposed ? src + c * rows + r : src + r * cols + c) : 0.f;   // L2: other CTAs update them
+    }
+}
+__device__ __forceinline__ void load_vec(float* dst, const float* src, int n) {
+    for (int i = threadIdx.x; i < pad4(n); i += CT) dst[i] = i < n ? __ldcg(src + i) : 0.f;
+}
+__device__ __forceinline__ SW load_net(float* base, const NetP& n, int l1_in, int l4_out, bool w1_transposed) {
+    float* q = base;
     SW w;
-    int off = 0;
-    w.W1 = base + off; off += H * l1_in;
-    w.b1 = base + off; off += H;
-    w.W2 = base + off; off += H * H;
-    w.b2 = base + off; off += H;
-    w.W3 = base + off; off += H * H;
-    w.b3 = base + off; off += H;
-    w.W4 = base + off; off += l4_out * H;
-    w.b4 = base + off;
+    w.W1 = q;
+    if (w1_transposed) { load_mat(q, n.l[0].W, l1_in, H, true); q += l1_in * HP; }     // [input][output]
+    else { load_mat(q, n.l[0].W, H, l1_in, false); q += H * HP; }
+    w.b1 = q; load_vec(q, n.l[0].b, H); q += pad4(H);
+    w.W2 = q; load_mat(q, n.l[1].W, H, H, false); q += H * HP;
+    w.b2 = q; load_vec(q, n.l[1].b, H); q += pad4(H);
+    w.W3 = q; load_mat(q, n.l[2].W, H, H, false); q += H * HP;
+    w.b3 = q; load_vec(q, n.l[2].b, H); q += pad4(H);
+    w.W4 = q; load_mat(q, n.l[3].W, l4_out, H, false); q += l4_out * HP;
+    w.b4 = q; load_vec(q, n.l[3].b, l4_out);
     return w;
 }
-__host__ __device__ constexpr int net_floats(int l1_in, int l4_out) { return H * l1_in + H + 2 * (H * H + H) + l4_out * H + l4_out; }
 
 // Adam for one flat tensor (torch.optim.Adam semantics); the whole GRID strides over it; grad re-zeroed
 __device__ __forceinline__ void adam_tensor(float* p, float* g, float* m, float* v, int n, float step_size, float isb,
@@ -346,7 +385,7 @@ __device__ __forceinline__ void combine_scalars(const float* ws, float* scalars,
 
 __global__ void __launch_bounds__(CT) coef_step_kernel(const CoefParams P) {
     cg::grid_group grid = cg::this_grid();
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     __shared__ float red[32];
     __shared__ float fsum[30];
     __shared__ float bc[2];
@@ -359,17 +398,17 @@ __global__ void __launch_bounds__(CT) coef_step_kernel(const CoefParams P) {
 
     // shared-memory carve-up: DNN | D | G weights, then the staging tile
     float* wDNN = smem;
-    float* wD = wDNN + net_floats(NIN, 2);
-    float* wG = wD + net_floats(NIN, 2);
-    float* stage = wG + net_floats(NZ, NIN);
-    float* row = stage + tid * PITCH;
-    if (do_dnn) load_net(wDNN, P.DNN, NIN, HO);
-    if (do_gan) { load_net(wD, P.D, NIN, HO); load_net(wG, P.G, NZ, NIN); }
+    float* wD = wDNN + net_floats(NIN, 2, true);
+    float* wG = wD + net_floats(NIN, 2, true);
+    float* stage = wG + net_floats(NZ, NIN, false);
+    const Row row{stage + tid};
+    SW sDNN = {}, sD = {}, sG = {};
+    if (do_dnn) sDNN = load_net(wDNN, P.DNN, NIN, HO, true);
+    if (do_gan) { sD = load_net(wD, P.D, NIN, HO, true); sG = load_net(wG, P.G, NZ, NIN, false); }
     // step numbers of the updates this launch performs (read before anybody advances them)
     const float tD = P.D.state[0] + 1.f, tG = P.G.state[0] + 1.f, tDNN = P.DNN.state[0] + 1.f;
     __syncthreads();
-    const SW sDNN = carve(wDNN, NIN, HO), sD = carve(wD, NIN, HO), sG = carve(wG, NZ, NIN);
-    const float* W4r1 = sD.W4 + H;                 // DG-GAN fake-score head row
+    const float* W4r1 = sD.W4 + HP;                // DG-GAN fake-score head row
 
     int pkD[KD];
 #pragma unroll
@@ -392,8 +431,7 @@ __global__ void __launch_bounds__(CT) coef_step_kernel(const CoefParams P) {
             const int sc = act ? first + tid : 0;
             const float k = act ? 1.f : 0.f;
             float h1[H], h2[H], h3[H];
-            tile_load(stage, P.x, first, P.B, NIN);
-            __syncthreads();
+            row_load(row, P.x, sc, act);
             if (do_dnn) {
                 d_fwd_row(sDNN, row, h1, h2, h3);
                 float pred = sDNN.b4[0];
@@ -416,9 +454,7 @@ __global__ void __launch_bounds__(CT) coef_step_kernel(const CoefParams P) {
                 d_fwd_row(sD, row, h1, h2, h3);
 #pragma unroll
                 for (int i = 0; i < H; ++i) fs0[i] += k * h3[i];
-                __syncthreads();
-                tile_load(stage, P.u, first, P.B, NIN);
-                __syncthreads();
+                row_load(row, P.u, sc, act);
                 d_fwd_row(sD, row, h1, h2, h3);
 #pragma unroll
                 for (int i = 0; i < H; ++i) fs1[i] += k * h3[i];
@@ -426,11 +462,10 @@ __global__ void __launch_bounds__(CT) coef_step_kernel(const CoefParams P) {
 #pragma unroll
                 for (int i = 0; i < NZ; ++i) zz[i] = P.z[(long long)sc * NZ + i];
                 g_hidden(sG, zz, g1, g2, g3);
-                d_fwd_fake<false>(sD, sG, g3, nullptr, h1, h2, h3);
+                d_fwd_fake<false>(sD, sG, g3, row, h1, h2, h3);
 #pragma unroll
                 for (int i = 0; i < H; ++i) fs2[i] += k * h3[i];
             }
-            __syncthreads();
         }
         if (do_dnn) {
 #pragma unroll
@@ -445,7 +480,7 @@ __global__ void __launch_bounds__(CT) coef_step_kernel(const CoefParams P) {
             __syncthreads();
             if (tid < 30) {
                 float a = 0.f;
-                for (int s = 0; s < CT; ++s) a += stage[s * PITCH + O_S(0) + tid];
+                for (int s = 0; s < CT; ++s) a += stage[(O_S(0) + tid) * CT + s];
                 P.ws[WS_FA + blockIdx.x * 30 + tid] = a;
             }
         }
@@ -494,8 +529,7 @@ __global__ void __launch_bounds__(CT) coef_step_kernel(const CoefParams P) {
             const float k = act ? 1.f : 0.f;
             float h1[H], h2[H], h3[H], da3[H], da2[H], da1[H];
             // ---- x: labeled loss + matching seed
-            tile_load(stage, P.x, first, P.B, NIN);
-            __syncthreads();
+            row_load(row, P.x, sc, act);
             d_fwd_row(sD, row, h1, h2, h3);
             {
                 float pred = sD.b4[0];
@@ -513,8 +547,7 @@ __global__ void __launch_bounds__(CT) coef_step_kernel(const CoefParams P) {
             put10(row + O_D3, da3); put10(row + O_H3, h3);
             accumulate<KD>(stage, pkD, acc, ND);
             // ---- u
-            tile_load(stage, P.u, first, P.B, NIN);
-            __syncthreads();
+            row_load(row, P.u, sc, act);
             d_fwd_row(sD, row, h1, h2, h3);
             {
                 float dsu = 0.f;
@@ -574,8 +607,10 @@ __global__ void __launch_bounds__(CT) coef_step_kernel(const CoefParams P) {
                 for (int j = 0; j < NIN; ++j) {
                     const float v = a * P.u[(long long)sc * NIN + j] + (1.f - a) * row[O_IN + j];
                     row[O_IN + j] = v;
+                    float r[HP];
+                    ldrow(sD.W1 + j * HP, r);
 #pragma unroll
-                    for (int o = 0; o < H; ++o) h1[o] = fmaf(sD.W1[o * NIN + j], v, h1[o]);
+                    for (int o = 0; o < H; ++o) h1[o] = fmaf(r[o], v, h1[o]);
                 }
                 d_tail(sD, h1, h2, h3);
                 float g3v[H], gm3[H], gm2[H], gm1[H], t[H];
@@ -601,12 +636,13 @@ __global__ void __launch_bounds__(CT) coef_step_kernel(const CoefParams P) {
                 for (int o = 0; o < H; ++o) t[o] = 0.f;
 #pragma unroll 2
                 for (int j = 0; j < NIN; ++j) {
-                    float g0 = 0.f;
+                    float g0 = 0.f, r[HP];
+                    ldrow(sD.W1 + j * HP, r);
 #pragma unroll
-                    for (int o = 0; o < H; ++o) g0 = fmaf(sD.W1[o * NIN + j], gm1[o], g0);
+                    for (int o = 0; o < H; ++o) g0 = fmaf(r[o], gm1[o], g0);
                     rr = fmaf(g0, g0, rr);
 #pragma unroll
-                    for (int o = 0; o < H; ++o) t[o] = fmaf(sD.W1[o * NIN + j], g0, t[o]);
+                    for (int o = 0; o < H; ++o) t[o] = fmaf(r[o], g0, t[o]);
                 }
                 rr = sqrtf(rr);
                 const float ex = fmaxf(rr - 1.f, 0.f);
@@ -640,9 +676,10 @@ __global__ void __launch_bounds__(CT) coef_step_kernel(const CoefParams P) {
                 // gets sum_n u_L,n (the target is linear in the features: the Jacobian term vanishes)
 #pragma unroll 2
                 for (int j = 0; j < NIN; ++j) {
-                    float g0 = 0.f;
+                    float g0 = 0.f, r[HP];
+                    ldrow(sD.W1 + j * HP, r);
 #pragma unroll
-                    for (int o = 0; o < H; ++o) g0 = fmaf(sD.W1[o * NIN + j], gm1[o], g0);
+                    for (int o = 0; o < H; ++o) g0 = fmaf(r[o], gm1[o], g0);
                     row[O_IN + j] = g0;
                 }
                 put10(row + O_D1, gm1, coef); put10(row + O_H1, u1); put10(row + O_D2, gm2, k); put10(row + O_H2, u2);
@@ -674,7 +711,7 @@ __global__ void __launch_bounds__(CT) coef_step_kernel(const CoefParams P) {
     grid.sync();
 
     // =========================================================================================== phase C: G step, sums
-    load_net(wD, P.D, NIN, HO);                    // the UPDATED discriminator
+    sD = load_net(wD, P.D, NIN, HO, true);         // the UPDATED discriminator
     __syncthreads();
     if (!dggan) {
         float fs0[H], fs1[H];
@@ -689,21 +726,19 @@ __global__ void __launch_bounds__(CT) coef_step_kernel(const CoefParams P) {
 #pragma unroll
             for (int i = 0; i < NZ; ++i) zz[i] = P.z2[(long long)sc * NZ + i];
             g_hidden(sG, zz, g1, g2, g3);
-            d_fwd_fake<false>(sD, sG, g3, nullptr, h1, h2, h3);
+            d_fwd_fake<false>(sD, sG, g3, row, h1, h2, h3);
 #pragma unroll
             for (int i = 0; i < H; ++i) fs0[i] += k * h3[i];
-            tile_load(stage, P.u, first, P.B, NIN);
-            __syncthreads();
+            row_load(row, P.u, sc, act);
             d_fwd_row(sD, row, h1, h2, h3);
 #pragma unroll
             for (int i = 0; i < H; ++i) fs1[i] += k * h3[i];
-            __syncthreads();
         }
         put10(row + O_S(0), fs0); put10(row + O_S(1), fs1);
         __syncthreads();
         if (tid < 20) {
             float a = 0.f;
-            for (int s = 0; s < CT; ++s) a += stage[s * PITCH + O_S(0) + tid];
+            for (int s = 0; s < CT; ++s) a += stage[(O_S(0) + tid) * CT + s];
             P.ws[WS_FC + blockIdx.x * 20 + tid] = a;
         }
         __threadfence();
@@ -744,7 +779,7 @@ __global__ void __launch_bounds__(CT) coef_step_kernel(const CoefParams P) {
 #pragma unroll
             for (int i = 0; i < NZ; ++i) zz[i] = P.z2[(long long)sc * NZ + i];
             g_hidden(sG, zz, g1, g2, g3);
-            d_fwd_fake<false>(sD, sG, g3, nullptr, h1, h2, h3);
+            d_fwd_fake<false>(sD, sG, g3, row, h1, h2, h3);
             if (dggan) {
                 float s1 = sD.b4[1], lt, ds;
 #pragma unroll
@@ -764,12 +799,14 @@ __global__ void __launch_bounds__(CT) coef_step_kernel(const CoefParams P) {
             for (int i = 0; i < H; ++i) t[i] = 0.f;
 #pragma unroll 2
             for (int j = 0; j < NIN; ++j) {
-                float dj = 0.f;
+                float dj = 0.f, r[HP], q[HP];
+                ldrow(sD.W1 + j * HP, r);
 #pragma unroll
-                for (int o = 0; o < H; ++o) dj = fmaf(sD.W1[o * NIN + j], da1[o], dj);
+                for (int o = 0; o < H; ++o) dj = fmaf(r[o], da1[o], dj);
                 row[O_IN + j] = dj;
+                ldrow(sG.W4 + j * HP, q);
 #pragma unroll
-                for (int i = 0; i < H; ++i) t[i] = fmaf(sG.W4[j * H + i], dj, t[i]);
+                for (int i = 0; i < H; ++i) t[i] = fmaf(q[i], dj, t[i]);
             }
 #pragma unroll
             for (int i = 0; i < H; ++i) e3[i] = t[i] * dleaky(g3[i]);
@@ -839,7 +876,7 @@ extern "C" int srgan_coefficient_step(const float* const* d_ptrs, const float* c
     P.lr = lr; P.lr_dnn = lr_dnn; P.wd = wd; P.beta1 = beta1; P.beta2 = beta2; P.eps = eps;
     P.phases = phases; P.train_g = train_g;
     P.ws = static_cast<float*>(workspace); P.scalars = scalars;
-    const size_t smem = (size_t)(2 * net_floats(NIN, 2) + net_floats(NZ, NIN) + CT * PITCH) * sizeof(float);
+    const size_t smem = (size_t)(2 * net_floats(NIN, 2, true) + net_floats(NZ, NIN, false) + NSLOT * CT) * sizeof(float);
     int grid = (B + CT - 1) / CT;
     if (grid > MAXG) grid = MAXG;
     void* args[] = {(void*)&P};
