@@ -8,7 +8,7 @@ bench.py -- SR-GAN training steps/sec on B200 (BASELINE.json metric), one JSON l
 Default workload (config.workload): BASELINE configs[1] "age SR-GAN": DCGAN G/D (age/models.py:32-80), synthetic
 3x128x128 inputs ~U(-1,1), labels ~U(10,95), per-GPU batch 100, multipliers of run.py:30-35; one step =
 dnn_training_step + gan_training_step with generator_training_step_period=1.  `--workload crowd` runs
-BASELINE configs[2] (DCGenerator + KnnDenseNetCat/DenseNet-201 at 224x224, per-GPU batch 32, run.py:57-68 multipliers),
+BASELINE configs[2] (DCGenerator + KnnDenseNetCat/DenseNet-201 at 224x224, per-GPU batch 64, run.py:57-68 multipliers),
 `--workload coefficient` BASELINE configs[0] (MLPs, batch 5000).  N>1 is weak scaling: every rank holds a per-GPU-batch
 shard of the global batch, feature sums and gradients are all-reduced (NCCL) so the loss is the global-batch loss.
 
@@ -43,12 +43,17 @@ WORKLOADS = {
     'age': dict(batch=100, ref_batch=10, flops_per_sample=21 * 0.8305e9 + 4 * 0.8472e9, mult=(1e2, 1e1, 1e2),
                 desc='age SR-GAN (BASELINE configs[1]): DCGAN G/D, 3x128x128'),
     # BASELINE configs[2]: DCGenerator + KnnDenseNetCat (DenseNet-201) at 224x224, run.py:57-68 multipliers
-    'crowd': dict(batch=32, ref_batch=2, flops_per_sample=21 * 8.732e9 + 4 * 2.595e9, mult=(1e3, 1e2, 1e2),
+    'crowd': dict(batch=64, ref_batch=2, flops_per_sample=21 * 8.732e9 + 4 * 2.595e9, mult=(1e3, 1e2, 1e2),
                   desc='crowd SR-GAN (BASELINE configs[2]): DCGenerator + KnnDenseNetCat (DenseNet-201), 3x224x224'),
     # BASELINE configs[0]: coefficient MLPs, B = 5000 (run.py:50), one persistent kernel per step method
     'coefficient': dict(batch=5000, ref_batch=5000, flops_per_sample=21 * 1420.0 + 4 * 1600.0, mult=(1.0, 1.0, 10.0),
                         desc='coefficient SR-GAN (BASELINE configs[0]): MLP G/D, 50 observations'),
 }
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of the probed kernel per launch, from one `ncu --set full` capture of exactly that
+# launch (profiles/r1_ncu_full_summary.txt: D layer-2 fprop over 400 samples; algorithmic bytes 315 MB = input 210 + output 105)
+NCU_TRAFFIC_BYTES = {('age', 100): 279.16e6}
 
 
 def workload_string(name, B, world):
@@ -368,6 +373,9 @@ def main():
                 'traffic': None, 'kernel': probe.get('kernel', 'conv_down layer2 over 4B rows'), 'peak_source': f'{pk_kind} (sustained: kernel timed inside a long step)',
                 'launches_timed': probe.get('count', 0),
                 'timing': 'CUDA events around each launch during K eager steps run right after the timed region (the timed region replays CUDA graphs)' if graphed else 'CUDA events around each launch inside the timed region'}
+        roof['traffic'] = NCU_TRAFFIC_BYTES.get((name, B))
+        if roof['traffic'] is not None:
+            roof['traffic_source'] = 'profiles/r1_ncu_full_summary.txt (one ncu --set full capture of this launch)'
         if probe.get('count'):
             avg_ms = probe['ms'] / probe['count']
             roof['achieved'] = flops_launch / (avg_ms * 1e-3) / 1e12

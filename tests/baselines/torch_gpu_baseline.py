@@ -1,8 +1,8 @@
 """The "existing Blackwell kernels" bar: the oracle's PyTorch step (autograd + double backward, cuDNN / cuBLAS)
 run ON the B200 for the bench workloads -- fp32 with TF32 off, fp32 with TF32 on, and bf16 autocast -- next to this
-repository's step.  Test/bench infrastructure only (imports oracle/).  usage: python tools/torch_gpu_baseline.py [age|crowd] [B]"""
+repository's step.  Test infrastructure (it executes oracle/, so it lives under tests/).  usage: python tests/baselines/torch_gpu_baseline.py [age|crowd] [B]"""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import bench
 

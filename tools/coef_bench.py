@@ -1,10 +1,9 @@
-"""Coefficient config (BASELINE configs[0], B=5000, run.py:46-54): ms/step of the B200 path (graph replay and eager) and the
-oracle port on the host CPU."""
+"""Coefficient config (BASELINE configs[0], B=5000, run.py:46-54): us/step of the B200 path with and without CUDA graphs
+(the CPU figure next to it comes from `bench.py --workload coefficient`, cpu_baseline)."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import srgan_b200
-from oracle import srgan_oracle as O
 
 B = 5000
 method = sys.argv[1] if len(sys.argv) > 1 else 'srgan'
@@ -30,13 +29,3 @@ for precision in ('fp32', 'bf16'):
         torch.cuda.synchronize()
         print(f'coefficient {method} B={B} {precision} graph={graph}: {e0.elapsed_time(e1) / N * 1e3:.1f} us/step device, '
               f'{(time.perf_counter() - t0) / N * 1e6:.1f} us/step wall, scalars {exp.runner.scalars()}', flush=True)
-st = O.init_coefficient(seed=0, dggan=(method == 'dggan'))
-cfg = O.StepConfig(method=method, batch_size=B, gradient_penalty_multiplier=10.0)
-z, alpha, z2 = torch.randn(B, 10, generator=gen), torch.rand(B, 1, generator=gen), torch.randn(B, 10, generator=gen)
-torch.set_num_threads(os.cpu_count())
-for _ in range(3):
-    O.training_step(st, cfg, x, y, u, z, alpha, z2)
-t0 = time.perf_counter()
-for _ in range(20):
-    O.training_step(st, cfg, x, y, u, z, alpha, z2)
-print(f'oracle port on {os.cpu_count()} host cores: {(time.perf_counter() - t0) / 20 * 1e3:.2f} ms/step')

@@ -4,7 +4,7 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import srgan_b200
-from oracle import srgan_oracle as O
+import bench
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 precision = sys.argv[2] if len(sys.argv) > 2 else 'bf16'
@@ -14,7 +14,7 @@ s.batch_size, s.precision = B, precision
 s.matching_loss_multiplier, s.contrasting_loss_multiplier, s.gradient_penalty_multiplier, s.map_multiplier = 1e3, 1e2, 1e2, 1e-3
 s.use_cuda_graph = os.environ.get('SRGAN_NO_GRAPH', '0') != '1'
 exp = srgan_b200.Experiment(s, 'crowd')
-x, y, u, z, alpha, z2 = O.synthetic_crowd_batch(B, 3)
+x, y, u = bench.make_batches('crowd', B, 3)
 x, u, y = x.cuda(), u.cuda(), tuple(t.cuda() for t in y)
 t0 = time.perf_counter()
 for i in range(3):
