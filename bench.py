@@ -390,7 +390,7 @@ def main():
                            'l2': ('inputs and activations of one step (age: 39 MB + ~1 GB, crowd: ~0.7 GB per sample) exceed the 126 MB L2; no flush needed'
                                   if name != 'coefficient' else 'working set (2 MB) is L2-resident by design: the step is launch/latency-bound, not bandwidth-bound'),
                            'global_steps_per_s': global_steps,
-                           'value_definition': 'n_gpus x global optimizer steps/s = 100-sample step-equivalents per second over the whole job',
+                           'value_definition': 'n_gpus x global optimizer steps/s = per-GPU-batch step-equivalents per second over the whole job',
                            'step_algorithmic_tflops': step_tflops,
                            'step_frac_of_bf16_sustained_peak': step_tflops / (pk['bf16_tflops_sustained'] * world)},
                 'roofline': roof_coef if name == 'coefficient' else roof, 'clocks': clocks, 'gpu_launches': int(launches),

@@ -168,6 +168,11 @@ int srgan_affine_bwd(const void* dy, int dy_pitch, void* dx, int dx_pitch, int d
 int srgan_affine_grad(const void* dy, int dy_pitch, const void* x, int x_pitch, int x_c0, long long rows, int C,
                       const float* mean, const float* var, float eps, float* dgamma, float* dbeta, int subtract_mean,
                       int dtype, void* stream);
+/* srgan_affine_grad (subtract_mean = 1) and srgan_affine_bwd fused: one pass over dy; x and dx are the same slice of the
+ * activation / delta buffers */
+int srgan_affine_bwd_grad(const void* dy, int dy_pitch, const void* x, void* dx, int x_pitch, int x_c0, long long rows, int C,
+                          const float* gamma, const float* mean, const float* var, float eps, float* dgamma, float* dbeta,
+                          int accumulate, int dtype, void* stream);
 /* dst[:, d0:d0+C] (+)= src[:, s0:s0+C] : torch.cat writes / their backward reads, MapModule taps */
 int srgan_copy2d(const void* src, int src_pitch, int src_c0, void* dst, int dst_pitch, int dst_c0, long long rows, int C,
                  int accumulate, int dtype, void* stream);

@@ -132,6 +132,50 @@ __global__ void __launch_bounds__(256) affine_grad_kernel(const T* __restrict__ 
     }
 }
 
+// fused backward of one eval-BatchNorm(+ReLU) node: the parameter gradients AND the data gradient from ONE pass over dy
+//   dgamma[c] += sum_r dy[r,c]*(x[r,c0+c]-mean[c])/sqrt(var[c]+eps) ; dbeta[c] += sum_r dy[r,c] ; dx[r,c0+c] (+)= dy[r,c]*gamma[c]/sqrt(..)
+// same thread mapping as affine_grad_kernel (x and dx are the same slice of the activation / delta buffers)
+template <typename T>
+__global__ void __launch_bounds__(256) affine_bwd_grad_kernel(const T* __restrict__ dy, int dy_pitch, const T* __restrict__ x,
+                                                              T* __restrict__ dx, int x_pitch, int x_c0, long long rows, int C,
+                                                              const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                              const float* __restrict__ var, float eps, float* __restrict__ dgamma,
+                                                              float* __restrict__ dbeta, int accumulate, long long rows_per_block) {
+    __shared__ float sg[8][129], sb[8][129];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + lane) * 4;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    const long long r1 = min(rows, r0 + rows_per_block);
+    float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
+    if (c < C) {
+        const float4 mu = ld4f(mean + c), g = ld4f(gamma + c), vr = ld4f(var + c);
+        const float4 s = make_float4(bn_scale(g.x, vr.x, eps), bn_scale(g.y, vr.y, eps), bn_scale(g.z, vr.z, eps), bn_scale(g.w, vr.w, eps));
+        for (long long r = r0 + w; r < r1; r += 8) {
+            const float4 d = ld4(dy + r * dy_pitch + c), xv = ld4(x + r * x_pitch + x_c0 + c);
+            ag.x = fmaf(d.x, xv.x - mu.x, ag.x); ag.y = fmaf(d.y, xv.y - mu.y, ag.y);
+            ag.z = fmaf(d.z, xv.z - mu.z, ag.z); ag.w = fmaf(d.w, xv.w - mu.w, ag.w);
+            ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
+            T* xp = dx + r * x_pitch + x_c0 + c;
+            float4 o = make_float4(d.x * s.x, d.y * s.y, d.z * s.z, d.w * s.w);
+            if (accumulate) { const float4 p = ld4(xp); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+            st4(xp, o);
+        }
+    }
+    sg[w][lane * 4] = ag.x; sg[w][lane * 4 + 1] = ag.y; sg[w][lane * 4 + 2] = ag.z; sg[w][lane * 4 + 3] = ag.w;
+    sb[w][lane * 4] = ab.x; sb[w][lane * 4 + 1] = ab.y; sb[w][lane * 4 + 2] = ab.z; sb[w][lane * 4 + 3] = ab.w;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int cc = blockIdx.x * 128 + threadIdx.x;
+        if (cc < C) {
+            float gsum = 0.f, bsum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { gsum += sg[k][threadIdx.x]; bsum += sb[k][threadIdx.x]; }
+            atomicAdd(dgamma + cc, gsum / sqrtf(var[cc] + eps));
+            atomicAdd(dbeta + cc, bsum);
+        }
+    }
+}
+
 // dst[:, d0:d0+C] (+)= src[:, s0:s0+C]
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) copy2d_kernel(const T* __restrict__ src, int src_pitch, int src_c0, T* __restrict__ dst,
@@ -572,6 +616,28 @@ int srgan_affine_grad(const void* dy, int dy_pitch, const void* x, int x_pitch, 
                if (vec) affine_grad_kernel<T, true><<<grid, 256, 0, st>>>((const T*)dy, dy_pitch, (const T*)x, x_pitch, x_c0, rows, C, mean, var, eps, dgamma, dbeta, subtract_mean, rpb);
                else affine_grad_kernel<T, false><<<grid, 256, 0, st>>>((const T*)dy, dy_pitch, (const T*)x, x_pitch, x_c0, rows, C, mean, var, eps, dgamma, dbeta, subtract_mean, rpb));
     SRGAN_CHECK_LAUNCH("affine_grad_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_affine_bwd_grad(const void* dy, int dy_pitch, const void* x, void* dx, int x_pitch, int x_c0, long long rows, int C,
+                          const float* gamma, const float* mean, const float* var, float eps, float* dgamma, float* dbeta,
+                          int accumulate, int dtype, void* stream) {
+    SRGAN_REQUIRE(dy && x && dx && gamma && mean && var && dgamma && dbeta && rows >= 0 && C > 0 && x_c0 >= 0 && x_c0 + C <= x_pitch &&
+                      C <= dy_pitch, "srgan_affine_bwd_grad: bad arguments");
+    if (rows == 0) return SRGAN_OK;
+    if (!vec_ok(C, x_pitch, x_c0, dy_pitch)) {            // unaligned slices: the two separate kernels
+        int rc = srgan_affine_grad(dy, dy_pitch, x, x_pitch, x_c0, rows, C, mean, var, eps, dgamma, dbeta, 1, dtype, stream);
+        if (rc) return rc;
+        return srgan_affine_bwd(dy, dy_pitch, dx, x_pitch, x_c0, rows, C, gamma, var, eps, accumulate, dtype, stream);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int gx = (C + 127) / 128;
+    long long want = (8LL * kNumSMs + gx - 1) / gx;
+    long long rpb = (rows + want - 1) / want;
+    if (rpb < 64) rpb = 64;
+    dim3 grid(gx, (unsigned)((rows + rpb - 1) / rpb));
+    DISPATCH_T(dtype, affine_bwd_grad_kernel<T><<<grid, 256, 0, st>>>((const T*)dy, dy_pitch, (const T*)x, (T*)dx, x_pitch, x_c0, rows, C, gamma, mean, var, eps, dgamma, dbeta, accumulate, rpb));
+    SRGAN_CHECK_LAUNCH("affine_bwd_grad_kernel");
     return SRGAN_OK;
 }
 

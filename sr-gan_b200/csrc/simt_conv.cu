@@ -451,7 +451,59 @@ static int launch_wgrad(const T* S, const T* L, float* dW, int n, const srgan_ge
     return SRGAN_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// direct wgrad for tiny filters (Ca * R * S * Cb <= 64 weights, e.g. MapModule.conv1 = Conv2d(1, 8, k2 s2), crowd/models.py:770):
+// as a GEMM the output is 8 x 4 and the tiled kernel wastes 99 % of its work.  One thread per small-side pixel (grid-stride),
+// all weights' partial sums in registers, one warp-shuffle reduction and 32 atomics per warp at the end.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, int CA, int R, int S, int CB>
+__global__ void __launch_bounds__(256) direct_wgrad_small_kernel(const T* __restrict__ Ssrc, const T* __restrict__ Lsrc,
+                                                                 float* __restrict__ dW, ConvP p) {
+    constexpr int TT = R * S * CB, NW = CA * TT;
+    float acc[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) acc[i] = 0.f;
+    const long long total = (long long)p.n * p.Hs * p.Ws;
+    for (long long pix = (long long)blockIdx.x * 256 + threadIdx.x; pix < total; pix += 256LL * gridDim.x) {
+        const int ow = (int)(pix % p.Ws);
+        const long long t = pix / p.Ws;
+        const int oh = (int)(t % p.Hs);
+        const long long b = t / p.Hs;
+        float sv[CA], lv[TT];
+#pragma unroll
+        for (int a = 0; a < CA; ++a) sv[a] = to_f(Ssrc[pix * CA + a]);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int q = 0; q < S; ++q) {
+                const int ih = oh * p.stride - p.pad + r, iw = ow * p.stride - p.pad + q;
+                const bool ok = ih >= 0 && ih < p.Hl && iw >= 0 && iw < p.Wl;
+#pragma unroll
+                for (int c = 0; c < CB; ++c)
+                    lv[(r * S + q) * CB + c] = ok ? to_f(Lsrc[((b * p.Hl + ih) * p.Wl + iw) * CB + c]) : 0.f;
+            }
+#pragma unroll
+        for (int a = 0; a < CA; ++a)
+#pragma unroll
+            for (int k = 0; k < TT; ++k) acc[a * TT + k] = fmaf(sv[a], lv[k], acc[a * TT + k]);
+    }
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        const float v = warp_sum(acc[i]);
+        if (lane == (i & 31)) atomicAdd(dW + i, v);          // dW is [a][r][s][b] = [a][k]
+    }
+}
+
 int simt_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, int dtype, cudaStream_t st) {
+    if (g->Ca == 8 && g->R == 2 && g->S == 2 && g->Cb == 1 && (long long)n * g->Hs * g->Ws >= 512) {
+        ConvP p{n, g->Hs, g->Ws, g->Ca, g->Hl, g->Wl, g->Cb, g->R, g->S, g->stride, g->pad};
+        const int grid = 4 * kNumSMs;
+        if (dtype == SRGAN_F32) direct_wgrad_small_kernel<float, 8, 2, 2, 1><<<grid, 256, 0, st>>>((const float*)S, (const float*)L, dW, p);
+        else direct_wgrad_small_kernel<bf16, 8, 2, 2, 1><<<grid, 256, 0, st>>>((const bf16*)S, (const bf16*)L, dW, p);
+        SRGAN_CHECK_LAUNCH("direct_wgrad_small_kernel");
+        return SRGAN_OK;
+    }
     if (dtype == SRGAN_F32) return launch_wgrad<float>((const float*)S, (const float*)L, dW, n, g, st);
     return launch_wgrad<bf16>((const bf16*)S, (const bf16*)L, dW, n, g, st);
 }

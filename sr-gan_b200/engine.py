@@ -550,14 +550,15 @@ class Engine:
             elif op.kind == 'affine':
                 nm = op.name
                 mean, var = P[nm + '.running_mean'], P[nm + '.running_var']
-                if weight_grads:
-                    ops.affine_grad(dy, db.ch, xa, sb.ch, op.c0, n * sb.rows, op.C, mean, var, self.BN_EPS,
-                                    st.g(nm + '.weight'), st.g(nm + '.bias'), True)
+                if weight_grads:          # parameter gradients and data gradient from one pass over dy
+                    ops.affine_bwd_grad(dy, db.ch, xa, dx, sb.ch, op.c0, n * sb.rows, op.C, P[nm + '.weight'], mean, var,
+                                        self.BN_EPS, st.g(nm + '.weight'), st.g(nm + '.bias'), sb.accumulate)
                     if whi > hi:
                         ops.affine_grad(R(deltas[op.dst], db, hi, whi), db.ch, R(acts[op.src], sb, hi, whi), sb.ch, op.c0,
                                         (whi - hi) * sb.rows, op.C, mean, var, self.BN_EPS, st.g(nm + '.weight'), None, False)
-                ops.affine_bwd(dy, db.ch, dx, sb.ch, op.c0, n * sb.rows, op.C, P[nm + '.weight'], var, self.BN_EPS,
-                               sb.accumulate)
+                else:
+                    ops.affine_bwd(dy, db.ch, dx, sb.ch, op.c0, n * sb.rows, op.C, P[nm + '.weight'], var, self.BN_EPS,
+                                   sb.accumulate)
             elif op.kind == 'copy':       # dst slice <- dense src: both are w.r.t. the same pre-activation
                 ops.copy2d(dy, db.ch, op.c0, dx, sb.ch, 0, n * sb.rows, op.C, False)
             elif op.kind == 'read':       # dense dst <- src slice: add into the (accumulating) concat delta

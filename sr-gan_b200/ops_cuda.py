@@ -28,7 +28,7 @@ _EXPORTS = (
     'srgan_distance', 'srgan_feature_norm_seed', 'srgan_gradnorm_penalty', 'srgan_gp_feature_seed', 'srgan_adam',
     'srgan_repack', 'srgan_im2col', 'srgan_col2im', 'srgan_adam_prepare', 'srgan_coefficient_step',
     'srgan_coefficient_step_workspace_bytes', 'srgan_affine', 'srgan_affine_bwd', 'srgan_affine_grad', 'srgan_copy2d',
-    'srgan_maxpool', 'srgan_maxpool_bwd', 'srgan_avgpool', 'srgan_avgpool_bwd', 'srgan_crowd_loss', 'srgan_crowd_map_grad', 'srgan_depth_to_space', 'srgan_adam_multi',
+    'srgan_maxpool', 'srgan_maxpool_bwd', 'srgan_avgpool', 'srgan_avgpool_bwd', 'srgan_crowd_loss', 'srgan_crowd_map_grad', 'srgan_depth_to_space', 'srgan_adam_multi', 'srgan_affine_bwd_grad',
 )
 
 _lib = None
@@ -83,6 +83,7 @@ def load_library(path: str = LIB_PATH):
     lib.srgan_affine.argtypes = [vp, c_int, c_int, vp, c_int, c_ll, c_int, vp, vp, vp, vp, c_f, vp, c_int, c_int, c_f, c_int, vp]
     lib.srgan_affine_bwd.argtypes = [vp, c_int, vp, c_int, c_int, c_ll, c_int, vp, vp, c_f, c_int, c_int, vp]
     lib.srgan_affine_grad.argtypes = [vp, c_int, vp, c_int, c_int, c_ll, c_int, vp, vp, c_f, vp, vp, c_int, c_int, vp]
+    lib.srgan_affine_bwd_grad.argtypes = [vp, c_int, vp, vp, c_int, c_int, c_ll, c_int, vp, vp, vp, c_f, vp, vp, c_int, c_int, vp]
     lib.srgan_copy2d.argtypes = [vp, c_int, c_int, vp, c_int, c_int, c_ll, c_int, c_int, c_int, vp]
     lib.srgan_maxpool.argtypes = [vp, vp, vp, c_int, c_int] + [c_int] * 7 + [c_int, vp]
     lib.srgan_maxpool_bwd.argtypes = [vp, vp, c_int, c_int, vp] + [c_int] * 7 + [c_int, c_f, c_int, vp]
@@ -369,3 +370,9 @@ class CudaOps:
         f32 = torch.float32
         self._ck(self.lib.srgan_adam_multi(self._p(tbl[0]), len(entries), self._p(grad, f32), self._p(m, f32), self._p(v, f32),
                                            self._p(state, f32), b1, b2, eps, wd, self._stream()), 'srgan_adam_multi')
+
+    def affine_bwd_grad(self, dy, dy_pitch, x, dx, x_pitch, x_c0, rows, C, gamma, mean, var, eps, dgamma, dbeta, accumulate):
+        self._ck(self.lib.srgan_affine_bwd_grad(self._p(dy), dy_pitch, self._p(x, dy.dtype), self._p(dx, dy.dtype), x_pitch, x_c0,
+                                                rows, C, self._pf(gamma), self._pf(mean), self._pf(var), eps, self._pf(dgamma),
+                                                self._pf(dbeta), int(bool(accumulate)), _dt(dy.dtype), self._stream()),
+                 'srgan_affine_bwd_grad')

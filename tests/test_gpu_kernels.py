@@ -356,6 +356,17 @@ def test_affine_ops(ops, dt, rows, pitch, c0, C, yp):
         t = 1e-4 if dt == torch.float32 else 1e-2
         close(dg, dg_ref, t, 'affine_grad dgamma')
         close(db, db_ref, t, 'affine_grad dbeta')
+    for acc in (False, True):                            # the fused backward: parameter gradients + data gradient in one pass
+        dx_ref = rnd(gen, rows * pitch, dt=dt)
+        dx = dx_ref.clone().cuda()
+        dg_ref, db_ref = rnd(gen, C), rnd(gen, C)
+        dg, db = dg_ref.clone().cuda(), db_ref.clone().cuda()
+        ref.affine_bwd_grad(dy, yp, x, dx_ref, pitch, c0, rows, C, gamma, mean, var, 1e-5, dg_ref, db_ref, acc)
+        ops.affine_bwd_grad(cu(dy), yp, cu(x), dx, pitch, c0, rows, C, cu(gamma), cu(mean), cu(var), 1e-5, dg, db, acc)
+        t = 1e-4 if dt == torch.float32 else 1e-2
+        close(dx, dx_ref, tol(dt), f'affine_bwd_grad dx acc{acc}')
+        close(dg, dg_ref, t, 'affine_bwd_grad dgamma')
+        close(db, db_ref, t, 'affine_bwd_grad dbeta')
 
 
 @pytest.mark.parametrize('dt', DT)

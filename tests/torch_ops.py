@@ -395,3 +395,8 @@ class TorchOps:
             self.adam(p, grad[go:go + n], m[mo:mo + n], v[mo:mo + n], (n, 1, 1, 1), (1, 0, 0, 0), None, None, None, None,
                       state, b1, b2, eps, wd)
             self.launches -= 1
+
+    def affine_bwd_grad(self, dy, dy_pitch, x, dx, x_pitch, x_c0, rows, C, gamma, mean, var, eps, dgamma, dbeta, accumulate):
+        self.affine_grad(dy, dy_pitch, x, x_pitch, x_c0, rows, C, mean, var, eps, dgamma, dbeta, True)
+        self.affine_bwd(dy, dy_pitch, dx, x_pitch, x_c0, rows, C, gamma, var, eps, accumulate)
+        self.launches -= 1
