@@ -65,12 +65,10 @@ def _strides_for(layer_kind: str, dims, Ca, Cb, R, S):
     return wd, wu
 
 
-KPAD = 64        # row width of the im2col buffer for thin (<= 4 channel) image layers: one 128-byte swizzle row in bf16
-
-
-def _thin_strides(Ca, Cb, R, S):
-    """Thin-layer lowering: master[a][b][r][s] -> Wd_pad[a][KPAD] (k = (r*S+s)*Cb + b) and Wu_pad[KPAD][a]."""
-    return (KPAD, 1, S * Cb, Cb), (1, Ca, S * Cb * Ca, Cb * Ca)
+def _thin_strides(Ca, Cb, R, S, kpad):
+    """Thin-layer lowering: master[a][b][r][s] -> Wd_pad[a][kpad] (k = (r*S+s)*Cb + b) and Wu_pad[kpad][a]; kpad = the
+    row width of the im2col buffer (Layer.kpad: a multiple of the 64-element = 128-byte swizzle row in bf16)."""
+    return (kpad, 1, S * Cb, Cb), (1, Ca, S * Cb * Ca, Cb * Ca)
 
 
 class NetState:
@@ -83,7 +81,8 @@ class NetState:
         self.act_dtype = act_dtype
         self.device = device
         self.tag = tag                             # buffer namespace: D and DNN share 'D' (same shapes, sequential use)
-        self.thin = {l.name for l in net.layers if thin and l.thin_ok and net.graph is None}
+        # graph nets: only forward-'down' layers fed by the network input (the crowd stem) are lowered
+        self.thin = {l.name for l in net.layers if thin and l.thin_ok and (net.graph is None or l.fwd == 'down')}
         n_total = 0
         g_total = 0
         self.slices = {}
@@ -91,6 +90,7 @@ class NetState:
         order = []
         # elements of a layer's kernel-layout weight copies: geom.Ca / geom.Cb may be padded beyond the master dims
         kl = {l.name: l.geom.Ca * l.geom.R * l.geom.S * l.geom.Cb for l in net.layers}
+        thin_l = {l.name: l for l in net.layers}
         part_c0, c0 = {}, 0
         for h, ncol in (net.head_parts or []):
             part_c0[h] = c0
@@ -113,7 +113,7 @@ class NetState:
             lname = k.rsplit('.', 1)[0]
             gn = n
             if k.endswith('.weight') and lname in self.thin:
-                gn = p.shape[0] * KPAD             # gradient in the padded Wd_pad layout [a][KPAD]
+                gn = p.shape[0] * thin_l[lname].kpad    # gradient in the padded Wd_pad layout [a][kpad]
             elif k.endswith('.weight') and lname in kl:
                 gn = kl[lname]                     # gradient in the (possibly channel-padded) Wd layout
             if k.endswith('.weight') and lname in part_c0:
@@ -139,7 +139,7 @@ class NetState:
         for l in net.layers:
             n = kl[l.name]
             if l.name in self.thin:
-                n = l.geom.Ca * KPAD               # padded copies; the pad columns / rows stay zero
+                n = l.geom.Ca * l.kpad             # padded copies; the pad columns / rows stay zero
             self.wd_[l.name] = torch.zeros(n, dtype=act_dtype, device=device)
             self.wu_[l.name] = torch.zeros(n, dtype=act_dtype, device=device)
         if net.head:
@@ -153,7 +153,7 @@ class NetState:
     def strides(self, l: Layer):
         g = l.geom
         if l.name in self.thin:
-            return _thin_strides(g.Ca, g.Cb, g.R, g.S)
+            return _thin_strides(g.Ca, g.Cb, g.R, g.S, l.kpad)
         return _strides_for(l.master_kind, l.master_dims, g.Ca, g.Cb, g.R, g.S)
 
     def m(self, key):
@@ -260,16 +260,16 @@ class Engine:
 
     # ------------------------------------------------------------------ layer ops
     def _lin(self, l: Layer):
-        """The [pixels x KPAD] GEMM a thin layer runs as: small side = [pix, Ca], large side = col [pix, KPAD]."""
+        """The [pixels x kpad] GEMM a thin layer runs as: small side = [pix, Ca], large side = col [pix, kpad]."""
         from .nets import Geom
-        return Geom(1, 1, l.geom.Ca, 1, 1, KPAD, 1, 1, 1, 0)
+        return Geom(1, 1, l.geom.Ca, 1, 1, l.kpad, 1, 1, 1, 0)
 
     def _col(self, st: NetState, l: Layer, lo, n):
         P = l.geom.Hs * l.geom.Ws
-        return self._buf[('col', st.tag, l.name)][lo * P * KPAD:(lo + n) * P * KPAD]
+        return self._buf[('col', st.tag, l.name)][lo * P * l.kpad:(lo + n) * P * l.kpad]
 
     def _coltmp(self, l: Layer, n):
-        return self.buf(('coltmp',), (n * l.geom.Hs * l.geom.Ws * KPAD,))
+        return self.buf(('coltmp',), (n * l.geom.Hs * l.geom.Ws * l.kpad,))
 
     def _fwd_layer(self, st: NetState, l: Layer, x, y, n, bias=True, href=None, epi=EPI_BIAS_ACT, act=None, slope=None,
                    lo=0):
@@ -285,12 +285,12 @@ class Engine:
             P = l.geom.Hs * l.geom.Ws
             if l.fwd == 'down':      # im2col (kept for the weight gradient) -> GEMM with the layer's epilogue
                 col = self._col(st, l, lo, n)
-                self.ops.im2col(x, col, n, l.geom, KPAD)
+                self.ops.im2col(x, col, n, l.geom, l.kpad)
                 self.ops.conv_down(col, st.wd_[l.name], y, n * P, self._lin(l), b, 0, href, epi, act, slope)
             else:                    # GEMM -> col2im with the layer's epilogue
                 ycol = self._coltmp(l, n)
                 self.ops.conv_up(x, st.wu_[l.name], ycol, n * P, self._lin(l), None, 0, None, EPI_DACT, ACT_NONE, 0.0)
-                self.ops.col2im(ycol, y, n, l.geom, KPAD, b, href, epi, act, slope)
+                self.ops.col2im(ycol, y, n, l.geom, l.kpad, b, href, epi, act, slope)
         elif l.fwd == 'down':
             self.ops.conv_down(x, st.wd_[l.name], y, n, l.geom, b, l.bias_mod, href, epi, act, slope)
         else:
@@ -324,11 +324,11 @@ class Engine:
             if l.fwd == 'down':      # transpose of (im2col -> GEMM): GEMM^T -> col2im with the mask fused
                 colg = self._coltmp(l, n)
                 self.ops.conv_up(dy, st.wu_[l.name], colg, n * P, self._lin(l), None, 0, None, EPI_DACT, ACT_NONE, 0.0)
-                self.ops.col2im(colg, dx, n, l.geom, KPAD, None, href, EPI_DACT, act, slope)
+                self.ops.col2im(colg, dx, n, l.geom, l.kpad, None, href, EPI_DACT, act, slope)
             else:                    # transpose of (GEMM -> col2im): im2col -> GEMM^T
                 col = self._col(st, l, lo, n)
                 if not col_ready:
-                    self.ops.im2col(dy, col, n, l.geom, KPAD)
+                    self.ops.im2col(dy, col, n, l.geom, l.kpad)
                 self.ops.conv_down(col, st.wd_[l.name], dx, n * P, self._lin(l), None, 0, href, EPI_DACT, act, slope)
         elif l.fwd == 'down':
             self.ops.conv_up(dy, st.wu_[l.name], dx, n, l.geom, None, 0, href, EPI_DACT, act, slope)
@@ -343,7 +343,7 @@ class Engine:
             if l.fwd == 'down':      # col = im2col(layer input), written by the forward pass
                 self.ops.conv_wgrad(dy, col, dW, n * P, self._lin(l))
             else:                    # large side = dy: im2col it here, the data-backward reuses it (col_ready)
-                self.ops.im2col(dy, col, n, l.geom, KPAD)
+                self.ops.im2col(dy, col, n, l.geom, l.kpad)
                 self.ops.conv_wgrad(x_in, col, dW, n * P, self._lin(l))
         elif l.fwd == 'down':
             self.ops.conv_wgrad(dy, x_in, dW, n, l.geom)
@@ -359,12 +359,16 @@ class Engine:
         tensor.  Flat tensors, nb_rows samples of NHWC rows each."""
         if net.graph is not None:
             # zero-filled on (re)allocation: the pad channels of the padded operand buffers are never written
+            if self.thin:
+                for l in net.layers:
+                    if l.thin_ok and l.fwd == 'down':
+                        self.buf(('col', tag, l.name), (nb_rows * l.geom.Hs * l.geom.Ws * l.kpad,))
             return {name: self.buf((tag, 'a', name), (nb_rows * b.rows * b.ch,), zero=True) for name, b in net.bufs.items()}
         acts = [self.buf((tag, 'a', 0), (nb_rows * net.layers[0].in_elems,))]
         for i, l in enumerate(net.layers, 1):
             acts.append(self.buf((tag, 'a', i), (nb_rows * l.out_elems,)))
             if self.thin and l.thin_ok:
-                self.buf(('col', tag, l.name), (nb_rows * l.geom.Hs * l.geom.Ws * KPAD,))
+                self.buf(('col', tag, l.name), (nb_rows * l.geom.Hs * l.geom.Ws * l.kpad,))
         return acts
 
     def alloc_deltas(self, tag, net: Net, nb_rows):

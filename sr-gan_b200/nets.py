@@ -79,11 +79,17 @@ class Layer:
 
     @property
     def thin_ok(self):
-        """Image layer with <= 4 channels on the large side whose whole receptive field fits one 64-wide im2col row:
-        eligible for the im2col/col2im + [pixels x 64] tensor-core GEMM lowering (engine.KPAD)."""
+        """Image layer with <= 4 channels on the large side whose whole receptive field fits an im2col row of at most
+        256 elements: eligible for the im2col/col2im + [pixels x kpad] tensor-core GEMM lowering (kpad = the receptive
+        field rounded up to 64: 64 for the DCGAN k4 layers, 192 for the crowd stem k7)."""
         g = self.geom
-        return (g.Cb <= 4 and g.R * g.S * g.Cb <= 64 and g.Ca % 64 == 0 and g.Hl * g.Wl > 1
-                and self.master_kind == 'conv')
+        return (g.Cb <= 4 and g.R * g.S * g.Cb <= 256 and g.Ca % 64 == 0 and g.Hl * g.Wl > 1
+                and self.master_kind == 'conv' and self.gemm_rows == 1)
+
+    @property
+    def kpad(self):
+        g = self.geom
+        return (g.R * g.S * g.Cb + 63) // 64 * 64
 
     @property
     def in_elems(self):

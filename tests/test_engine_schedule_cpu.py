@@ -163,3 +163,30 @@ def test_crowd_container_matches_reference_keys_and_graph():
                                             image, spec.label_patch_size)
     full = nets.knn_densenet_cat()
     assert abs(full.macs_per_sample() - 4.366e9) < 2e6          # SURVEY App. A.4 [probed]
+
+
+def test_crowd_stem_thin_lowering_matches_oracle_fp64():
+    """The crowd stem (Conv2d(3, 64, k7 s2 p3): receptive field 147 -> im2col rows of 192) through the thin-layer lowering
+    (im2col + [pixels x 192] GEMM, GEMM^T + col2im for the data gradient, linear wgrad on the saved col buffer), fp64."""
+    dt = torch.float64
+    kw = dict(block_config=(1, 1, 1, 1), growth_rate=8, num_init_features=64, bn_size=2, label_patch_size=64)
+    st = O.init_crowd(seed=3, image_size=64, z_dim=16, g_conv_dim=8, dtype=dt, scale=2.0, **kw)
+    cfg = O.StepConfig(batch_size=2, matching_loss_multiplier=1e3, contrasting_loss_multiplier=1e2,
+                       gradient_penalty_multiplier=1e2, map_multiplier=1e-3)
+    d_net = nets.knn_densenet_cat(kw['block_config'], kw['growth_rate'], kw['num_init_features'], kw['bn_size'], 64, 64)
+    g_net = nets.dcgan_g(64, 8, 16)
+    eng = engine.Engine(TorchOps(), d_net, g_net, {k: v.clone() for k, v in st.D.items()},
+                        {k: v.clone() for k, v in st.G.items()}, {k: v.clone() for k, v in st.DNN.items()},
+                        act_dtype=dt, device='cpu', thin_lowering=True)
+    assert eng.D.thin == {'conv_layer1.conv0'} and d_net.layers[0].kpad == 192
+    x, y, u, z, alpha, z2 = O.synthetic_crowd_batch(2, 17, image=64, label=64, z_dim=16, dtype=dt)
+    out = O.training_step(st, cfg, x, y, u, z, alpha, z2, step=0)
+    eng.dnn_step(x, y, cfg, O.dnn_lr(cfg, 0), cfg.weight_decay)
+    eng.gan_step(x, y, u, z, alpha, z2, cfg)
+    got = read_scalars(eng)
+    for k in SCALARS:
+        assert got[k] == pytest.approx(out[k], rel=1e-9, abs=1e-12), (k, got[k], out[k])
+    for net, params, mine in (('D', st.D, eng.D), ('G', st.G, eng.G), ('DNN', st.DNN, eng.DNN)):
+        for k, v in params.items():
+            if not O.is_buffer_key(k):
+                assert rel(mine.params[k], v) < 1e-8, (net, k, rel(mine.params[k], v))
