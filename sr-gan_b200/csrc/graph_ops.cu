@@ -440,101 +440,153 @@ __global__ void __launch_bounds__(256) crowd_map_grad_kernel(const T* __restrict
     }
 }
 
-// ---- 2-D mapped, 4-wide vector versions of the streaming kernels: a thread owns ONE group of 4 channels (its BatchNorm
-// scale / shift are computed once) and walks down the rows; a warp covers 32 consecutive channel groups of a row
-// (256 contiguous bytes in bf16).  grid.x = channel-group tiles, grid.y = row tiles.
+// ---- 2-D mapped vector versions of the streaming kernels: a thread owns ONE group of W = 4 or 8 channels (its BatchNorm
+// scale / shift are computed once) and walks down the rows; a warp covers 32 consecutive channel groups of a row (512
+// contiguous bytes in bf16 with W = 8: one 16-byte access per thread).  grid.x = channel-group tiles, grid.y = row tiles.
 // When a row has fewer than 32 groups the spare lanes take further rows: thread t -> (group t & (cvp-1), row t >> lg).
 constexpr int EW_RI = 8;                      // row sweeps per block
-struct Ew2d { int lg; };                      // log2(cvp), cvp = min(32, next power of two >= C/4)
+struct Ew2d { int lg; };                      // log2(cvp), cvp = min(32, next power of two >= C/W)
+template <int W>
 __device__ __forceinline__ void ew2d_map(const Ew2d e, int& c, long long& r0, int& rstep) {
     const int t = threadIdx.x;
-    c = (blockIdx.x * 32 + (t & ((1 << e.lg) - 1))) * 4;
+    c = (blockIdx.x * 32 + (t & ((1 << e.lg) - 1))) * W;
     rstep = 256 >> e.lg;
     r0 = (long long)blockIdx.y * (rstep * EW_RI) + (t >> e.lg);
 }
+// W consecutive elements <-> W floats (16-byte accesses for 8 x bf16 and 4 x fp32)
+template <int W> __device__ __forceinline__ void ldw(const float* p, float (&v)[W]) {
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) { const float4 a = *reinterpret_cast<const float4*>(p + 4 * q); v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w; }
+}
+template <int W> __device__ __forceinline__ void ldw(const bf16* p, float (&v)[W]) {
+    if (W == 8) {
+        const uint4 r = *reinterpret_cast<const uint4*>(p);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h[q]); v[2 * q] = f.x; v[(2 * q + 1) % W] = f.y; }
+    } else {
+        const float4 a = ld4(p);
+        v[0] = a.x; v[1 % W] = a.y; v[2 % W] = a.z; v[3 % W] = a.w;
+    }
+}
+template <int W> __device__ __forceinline__ void stw(float* p, const float (&v)[W]) {
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) *reinterpret_cast<float4*>(p + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+template <int W> __device__ __forceinline__ void stw(bf16* p, const float (&v)[W]) {
+    if (W == 8) {
+        uint4 r;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(v[2 * q], v[(2 * q + 1) % W]);
+        *reinterpret_cast<uint4*>(p) = r;
+    } else {
+        st4(p, make_float4(v[0], v[1 % W], v[2 % W], v[3 % W]));
+    }
+}
 
-template <typename T>
+template <typename T, int W>
 __global__ void __launch_bounds__(256) affine2d_kernel(const T* __restrict__ x, int x_pitch, int x_c0, T* __restrict__ y, int y_pitch,
                                                        long long rows, int C, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, const float* __restrict__ mean,
                                                        const float* __restrict__ var, float eps, const T* __restrict__ href,
                                                        int mode, int act, float slope, Ew2d e) {
     int c, rstep; long long r0;
-    ew2d_map(e, c, r0, rstep);
+    ew2d_map<W>(e, c, r0, rstep);
     if (c >= C) return;
-    const float4 g = ld4f(gamma + c), vr = ld4f(var + c);
-    const float4 s = make_float4(bn_scale(g.x, vr.x, eps), bn_scale(g.y, vr.y, eps), bn_scale(g.z, vr.z, eps), bn_scale(g.w, vr.w, eps));
-    float4 m = make_float4(0.f, 0.f, 0.f, 0.f), b = m;
-    if (mode == 0) { m = ld4f(mean + c); b = ld4f(beta + c); }
+    float s[W], m[W], b[W];
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+        s[q] = bn_scale(gamma[c + q], var[c + q], eps);
+        m[q] = mode == 0 ? mean[c + q] : 0.f;
+        b[q] = mode == 0 ? beta[c + q] : 0.f;
+    }
 #pragma unroll 4
     for (int j = 0; j < EW_RI; ++j) {
         const long long r = r0 + (long long)j * rstep;
         if (r >= rows) break;
-        const float4 xv = ld4(x + r * x_pitch + x_c0 + c);
-        float4 o;
+        float xv[W], o[W];
+        ldw<W>(x + r * x_pitch + x_c0 + c, xv);
         if (mode == 0) {
-            o.x = act_fwd((xv.x - m.x) * s.x + b.x, act, slope); o.y = act_fwd((xv.y - m.y) * s.y + b.y, act, slope);
-            o.z = act_fwd((xv.z - m.z) * s.z + b.z, act, slope); o.w = act_fwd((xv.w - m.w) * s.w + b.w, act, slope);
+#pragma unroll
+            for (int q = 0; q < W; ++q) o[q] = act_fwd((xv[q] - m[q]) * s[q] + b[q], act, slope);
         } else {
-            const float4 h = ld4(href + r * y_pitch + c);
-            o.x = xv.x * s.x * act_bwd(h.x, act, slope); o.y = xv.y * s.y * act_bwd(h.y, act, slope);
-            o.z = xv.z * s.z * act_bwd(h.z, act, slope); o.w = xv.w * s.w * act_bwd(h.w, act, slope);
+            float h[W];
+            ldw<W>(href + r * y_pitch + c, h);
+#pragma unroll
+            for (int q = 0; q < W; ++q) o[q] = xv[q] * s[q] * act_bwd(h[q], act, slope);
         }
-        st4(y + r * y_pitch + c, o);
+        stw<W>(y + r * y_pitch + c, o);
     }
 }
 
-template <typename T>
+template <typename T, int W>
 __global__ void __launch_bounds__(256) affine_bwd2d_kernel(const T* __restrict__ dy, int dy_pitch, T* __restrict__ dx, int dx_pitch,
                                                            int dx_c0, long long rows, int C, const float* __restrict__ gamma,
                                                            const float* __restrict__ var, float eps, int accumulate, Ew2d e) {
     int c, rstep; long long r0;
-    ew2d_map(e, c, r0, rstep);
+    ew2d_map<W>(e, c, r0, rstep);
     if (c >= C) return;
-    const float4 g = ld4f(gamma + c), vr = ld4f(var + c);
-    const float4 s = make_float4(bn_scale(g.x, vr.x, eps), bn_scale(g.y, vr.y, eps), bn_scale(g.z, vr.z, eps), bn_scale(g.w, vr.w, eps));
+    float s[W];
+#pragma unroll
+    for (int q = 0; q < W; ++q) s[q] = bn_scale(gamma[c + q], var[c + q], eps);
 #pragma unroll 4
     for (int j = 0; j < EW_RI; ++j) {
         const long long r = r0 + (long long)j * rstep;
         if (r >= rows) break;
-        const float4 d = ld4(dy + r * dy_pitch + c);
+        float d[W], o[W];
+        ldw<W>(dy + r * dy_pitch + c, d);
         T* xp = dx + r * dx_pitch + dx_c0 + c;
-        float4 o = make_float4(d.x * s.x, d.y * s.y, d.z * s.z, d.w * s.w);
-        if (accumulate) { const float4 p = ld4(xp); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
-        st4(xp, o);
+#pragma unroll
+        for (int q = 0; q < W; ++q) o[q] = d[q] * s[q];
+        if (accumulate) {
+            float pv[W];
+            ldw<W>(xp, pv);
+#pragma unroll
+            for (int q = 0; q < W; ++q) o[q] += pv[q];
+        }
+        stw<W>(xp, o);
     }
 }
 
-template <typename T>
+template <typename T, int W>
 __global__ void __launch_bounds__(256) copy2d2d_kernel(const T* __restrict__ src, int src_pitch, int src_c0, T* __restrict__ dst,
                                                        int dst_pitch, int dst_c0, long long rows, int C, int accumulate, Ew2d e) {
     int c, rstep; long long r0;
-    ew2d_map(e, c, r0, rstep);
+    ew2d_map<W>(e, c, r0, rstep);
     if (c >= C) return;
 #pragma unroll 4
     for (int j = 0; j < EW_RI; ++j) {
         const long long r = r0 + (long long)j * rstep;
         if (r >= rows) break;
-        float4 v = ld4(src + r * src_pitch + src_c0 + c);
+        float v[W];
+        ldw<W>(src + r * src_pitch + src_c0 + c, v);
         T* dp = dst + r * dst_pitch + dst_c0 + c;
-        if (accumulate) { const float4 p = ld4(dp); v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w; }
-        st4(dp, v);
+        if (accumulate) {
+            float pv[W];
+            ldw<W>(dp, pv);
+#pragma unroll
+            for (int q = 0; q < W; ++q) v[q] += pv[q];
+        }
+        stw<W>(dp, v);
     }
 }
 
-inline Ew2d ew2d_map_for(int C) {
+inline Ew2d ew2d_map_for(int C, int W) {
     int lg = 0;
-    while (lg < 5 && (1 << lg) < C / 4) ++lg;
+    while (lg < 5 && (1 << lg) < C / W) ++lg;
     return Ew2d{lg};
 }
-inline dim3 ew2d_grid(long long rows, int C) {
-    const long long rpb = (long long)(256 >> ew2d_map_for(C).lg) * EW_RI;
-    return dim3((unsigned)((C / 4 + 31) / 32), (unsigned)((rows + rpb - 1) / rpb));
+inline dim3 ew2d_grid(long long rows, int C, int W) {
+    const long long rpb = (long long)(256 >> ew2d_map_for(C, W).lg) * EW_RI;
+    return dim3((unsigned)((C / W + 31) / 32), (unsigned)((rows + rpb - 1) / rpb));
 }
-inline bool ew2d_ok(long long rows, int C) {
-    const long long rpb = (long long)(256 >> ew2d_map_for(C).lg) * EW_RI;
+inline bool ew2d_ok(long long rows, int C, int W) {
+    const long long rpb = (long long)(256 >> ew2d_map_for(C, W).lg) * EW_RI;
     return (rows + rpb - 1) / rpb <= 65535;
 }
+// 8 elements per thread need 16-byte alignment in bf16 (and 32-byte runs in fp32): everything a multiple of 8
+inline bool vec8_ok(int C, int p0, int o0, int p1 = 0, int o1 = 0) { return ((C | p0 | o0 | p1 | o1) & 7) == 0; }
 
 // depth-to-space of a one-channel map: img[n, i*k+r, j*k+s] <-> blk[n, i, j, r*k+s]   (one thread per image pixel)
 template <typename T>
@@ -576,7 +628,8 @@ int srgan_affine(const void* x, int x_pitch, int x_c0, void* y, int y_pitch, lon
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = vec_ok(C, x_pitch, x_c0, y_pitch);
     DISPATCH_T(dtype,
-               if (vec && ew2d_ok(rows, C)) affine2d_kernel<T><<<ew2d_grid(rows, C), 256, 0, st>>>((const T*)x, x_pitch, x_c0, (T*)y, y_pitch, rows, C, gamma, beta, mean, var, eps, (const T*)href, mode, act, slope, ew2d_map_for(C));
+               if (vec8_ok(C, x_pitch, x_c0, y_pitch) && ew2d_ok(rows, C, 8)) affine2d_kernel<T, 8><<<ew2d_grid(rows, C, 8), 256, 0, st>>>((const T*)x, x_pitch, x_c0, (T*)y, y_pitch, rows, C, gamma, beta, mean, var, eps, (const T*)href, mode, act, slope, ew2d_map_for(C, 8));
+               else if (vec && ew2d_ok(rows, C, 4)) affine2d_kernel<T, 4><<<ew2d_grid(rows, C, 4), 256, 0, st>>>((const T*)x, x_pitch, x_c0, (T*)y, y_pitch, rows, C, gamma, beta, mean, var, eps, (const T*)href, mode, act, slope, ew2d_map_for(C, 4));
                else if (vec) affine_kernel<T, true><<<ew_grid(rows * C / 4), 256, 0, st>>>((const T*)x, x_pitch, x_c0, (T*)y, y_pitch, rows, C, gamma, beta, mean, var, eps, (const T*)href, mode, act, slope);
                else affine_kernel<T, false><<<ew_grid(rows * C), 256, 0, st>>>((const T*)x, x_pitch, x_c0, (T*)y, y_pitch, rows, C, gamma, beta, mean, var, eps, (const T*)href, mode, act, slope));
     SRGAN_CHECK_LAUNCH("affine_kernel");
@@ -591,7 +644,8 @@ int srgan_affine_bwd(const void* dy, int dy_pitch, void* dx, int dx_pitch, int d
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = vec_ok(C, dx_pitch, dx_c0, dy_pitch);
     DISPATCH_T(dtype,
-               if (vec && ew2d_ok(rows, C)) affine_bwd2d_kernel<T><<<ew2d_grid(rows, C), 256, 0, st>>>((const T*)dy, dy_pitch, (T*)dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, accumulate, ew2d_map_for(C));
+               if (vec8_ok(C, dx_pitch, dx_c0, dy_pitch) && ew2d_ok(rows, C, 8)) affine_bwd2d_kernel<T, 8><<<ew2d_grid(rows, C, 8), 256, 0, st>>>((const T*)dy, dy_pitch, (T*)dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, accumulate, ew2d_map_for(C, 8));
+               else if (vec && ew2d_ok(rows, C, 4)) affine_bwd2d_kernel<T, 4><<<ew2d_grid(rows, C, 4), 256, 0, st>>>((const T*)dy, dy_pitch, (T*)dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, accumulate, ew2d_map_for(C, 4));
                else if (vec) affine_bwd_kernel<T, true><<<ew_grid(rows * C / 4), 256, 0, st>>>((const T*)dy, dy_pitch, (T*)dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, accumulate);
                else affine_bwd_kernel<T, false><<<ew_grid(rows * C), 256, 0, st>>>((const T*)dy, dy_pitch, (T*)dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, accumulate));
     SRGAN_CHECK_LAUNCH("affine_bwd_kernel");
@@ -649,7 +703,8 @@ int srgan_copy2d(const void* src, int src_pitch, int src_c0, void* dst, int dst_
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = vec_ok(C, src_pitch, src_c0, dst_pitch, dst_c0);
     DISPATCH_T(dtype,
-               if (vec && ew2d_ok(rows, C)) copy2d2d_kernel<T><<<ew2d_grid(rows, C), 256, 0, st>>>((const T*)src, src_pitch, src_c0, (T*)dst, dst_pitch, dst_c0, rows, C, accumulate, ew2d_map_for(C));
+               if (vec8_ok(C, src_pitch, src_c0, dst_pitch, dst_c0) && ew2d_ok(rows, C, 8)) copy2d2d_kernel<T, 8><<<ew2d_grid(rows, C, 8), 256, 0, st>>>((const T*)src, src_pitch, src_c0, (T*)dst, dst_pitch, dst_c0, rows, C, accumulate, ew2d_map_for(C, 8));
+               else if (vec && ew2d_ok(rows, C, 4)) copy2d2d_kernel<T, 4><<<ew2d_grid(rows, C, 4), 256, 0, st>>>((const T*)src, src_pitch, src_c0, (T*)dst, dst_pitch, dst_c0, rows, C, accumulate, ew2d_map_for(C, 4));
                else if (vec) copy2d_kernel<T, true><<<ew_grid(rows * C / 4), 256, 0, st>>>((const T*)src, src_pitch, src_c0, (T*)dst, dst_pitch, dst_c0, rows, C, accumulate);
                else copy2d_kernel<T, false><<<ew_grid(rows * C), 256, 0, st>>>((const T*)src, src_pitch, src_c0, (T*)dst, dst_pitch, dst_c0, rows, C, accumulate));
     SRGAN_CHECK_LAUNCH("copy2d_kernel");
