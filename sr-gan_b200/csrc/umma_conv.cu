@@ -719,8 +719,8 @@ int umma_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom*
     if (g->Ca % 64 != 0 || g->Cb % 64 != 0) return 0;   // Ca = 64 (mod 128): the upper half tile is TMA zero fill
     const int BN = g->Cb % 256 == 0 ? 256 : (g->Cb % 128 == 0 ? 128 : 64);
     const int taps = g->R * g->S;
-    int NT = 512 / BN;
-    while (NT > 1 && taps % NT != 0) NT >>= 1;
+    int NT = 512 / BN;                                         // largest divisor of the tap count that fits TMEM (3 for 3x3)
+    while (NT > 1 && taps % NT != 0) --NT;
     if (taps % NT != 0) return 0;
     if (g->stride > 8) return 0;
     UmmaWgradParams p;
