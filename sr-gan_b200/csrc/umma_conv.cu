@@ -705,7 +705,14 @@ int umma_conv(int mode, const void* src, const void* W, void* out, int n, const 
         pp.c = p;
         pp.m_subtiles = (int)mtiles;
         pp.n_tiles = Cout / BN;
-        const int MT = (BN <= 128 && mtiles % 2 == 0) ? 2 : 1;
+        // 256-row CTA tiles (two M sub-tiles share every weight tile) unless the wave quantisation on 148 persistent CTAs
+        // makes 128-row tiles finish sooner: time ~ rounds x rows per tile
+        int MT = (BN <= 128 && mtiles % 2 == 0) ? 2 : 1;
+        if (MT == 2) {
+            const long long t1 = (long long)phases * pp.n_tiles * mtiles, t2 = t1 / 2;
+            const long long r1 = (t1 + kNumSMs - 1) / kNumSMs, r2 = (t2 + kNumSMs - 1) / kNumSMs;
+            if (r1 < 2 * r2) MT = 1;
+        }
         long long total = (long long)phases * pp.n_tiles * (mtiles / MT);
         if (total > 0x7fffffffLL) return 0;
         pp.total_tiles = (int)total;
