@@ -88,6 +88,8 @@ class Settings:
         self.map_multiplier = 1e-6
         # new knobs (added attributes only, defaults = reference behaviour): SURVEY section 5
         self.precision = 'fp32'          # 'fp32' (SIMT, 1e-4 parity) | 'bf16' (tcgen05 tensor cores, 2e-2 parity)
+        self.use_cuda_graph = True       # replay the step methods from CUDA graphs (piecewise around collectives)
+        self.use_persistent_kernel = True    # coefficient application, single rank: one cooperative kernel per step method
 
 
 class StepConfig:

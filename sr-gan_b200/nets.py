@@ -332,8 +332,7 @@ def knn_densenet_cat(block_config=(6, 12, 48, 32), growth_rate=32, num_init_feat
             h //= 2
     buf('n5', h * h, c, **RELU)
     ops.append(Op('affine', f'cat{len(block_config)}', 'n5', name='norm5', C=c, c0=0))
-    buf('fp', 1, c, **RELU)                         # average of ReLU outputs; no activation of its own: see below
-    bufs['fp'].act, bufs['fp'].slope = ACT_NONE, 0.0
+    buf('fp', 1, c)                                 # global average of the ReLU outputs: a linear op, no activation of its own
     ops.append(Op('avgpool', 'n5', 'fp', C=c, c0=0, H=h, W=h, k=h, stride=h))
     buf('fcf', 1, 20, **LK)
     conv('final_count_feature_layer', 'fp', 'fcf', Geom(1, 1, 20, 1, 1, c, 1, 1, 1, 0), 'down', (20, c, 1, 1), bias=True, **LK)
@@ -367,8 +366,7 @@ def knn_densenet_cat(block_config=(6, 12, 48, 32), growth_rate=32, num_init_feat
         conv(pre + '.linear1', src, f'h{i}', Geom(1, 1, 20, hh, hh, 32, hh, hh, 1, 0), 'down', (20, 32, hh, hh), bias=True, **LK)
         ops.append(Op('copy', f'h{i}', 'features', C=20, c0=20 * (i - 1)))
     ops.append(Op('copy', 'fcf', 'features', C=20, c0=60))
-    # the ops must be in an order where every buffer is complete before it is read: move the head ops to the end (they
-    # were appended after the trunk already) -- and the final-count ops precede the feature copy of slice 3: fine.
+    # (ops are in topological order: the trunk, then the count head, then the three MapModules, then the feature copies)
     head_parts = [(f'map_module{i}.count_layer', 20) for i in (1, 2, 3)] + [('count_layer', 20)]
     # n_out = 2: KnnDenseNetCatDggan (crowd/models.py:929-1046), every count layer has a second (DG-GAN score) output
     return Net('D', 'crowd', layers, head='count_layer', head_outputs=n_out, head_master_kind='parts',

@@ -118,6 +118,7 @@ class CudaOps:
         self.device = torch.device(device)
         self._geoms = {}
         self._stream_handle = None
+        self._tables = {}                          # adam_multi device tables, one per NetState
 
     # -------------------------------------------------------------- helpers
     def _p(self, t, dtype=None):
@@ -356,10 +357,8 @@ class CudaOps:
     def adam_multi(self, entries, grad, m, v, state, b1, b2, eps, wd):
         """entries: list of (param, grad offset, moment offset, numel); the device table is built once per list."""
         key = id(entries)
-        tbl = self._tables.get(key) if hasattr(self, '_tables') else None
+        tbl = self._tables.get(key)
         if tbl is None:
-            if not hasattr(self, '_tables'):
-                self._tables = {}
             rows = []
             for p, go, mo, n in entries:
                 if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
