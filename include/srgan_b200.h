@@ -177,12 +177,15 @@ int srgan_affine_bwd_grad(const void* dy, int dy_pitch, const void* x, void* dx,
 int srgan_copy2d(const void* src, int src_pitch, int src_c0, void* dst, int dst_pitch, int dst_c0, long long rows, int C,
                  int accumulate, int dtype, void* stream);
 /* nn.MaxPool2d(k, stride, pad) (crowd/models.py:1078): y slice = x at the argmax of xref's windows (xref NULL: x itself;
- * the tangent pass routes the tangent through the forward's argmax); first maximum in scan order like torch */
-int srgan_maxpool(const void* x, const void* xref, void* y, int y_pitch, int y_c0, int n, int H, int W, int C, int k,
-                  int stride, int pad, int dtype, void* stream);
-/* dx[i] = act'(xref[i]) * sum of dy over the windows whose argmax is i (dx dense, overwritten) */
-int srgan_maxpool_bwd(const void* xref, const void* dy, int dy_pitch, int dy_c0, void* dx, int n, int H, int W, int C, int k,
-                      int stride, int pad, int act, float slope, int dtype, void* stream);
+ * the tangent pass routes the tangent through the forward's argmax); first maximum in scan order like torch.
+ * Index map (idx: one byte per pooled element [n, Ho, Wo, C], the winning window position dh*k+dw): idx_mode 0 = none,
+ * 1 = the forward pass WRITES it, 2 = y = x at the recorded positions (tangent pass; xref is ignored). */
+int srgan_maxpool(const void* x, const void* xref, void* y, int y_pitch, int y_c0, unsigned char* idx, int idx_mode, int n,
+                  int H, int W, int C, int k, int stride, int pad, int dtype, void* stream);
+/* dx[i] = act'(xref[i]) * sum of dy over the windows whose argmax is i (dx dense, overwritten); with idx (may be NULL) the
+ * argmax is read from the forward's index map instead of being recomputed from xref */
+int srgan_maxpool_bwd(const void* xref, const unsigned char* idx, const void* dy, int dy_pitch, int dy_c0, void* dx, int n,
+                      int H, int W, int C, int k, int stride, int pad, int act, float slope, int dtype, void* stream);
 /* nn.AvgPool2d(k, k) (crowd/models.py:370) and avg_pool2d(kernel 7) (:1151): non-overlapping k x k means */
 int srgan_avgpool(const void* x, int x_pitch, void* y, int y_pitch, int y_c0, int n, int H, int W, int C, int k, int dtype,
                   void* stream);

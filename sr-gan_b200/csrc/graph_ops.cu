@@ -351,6 +351,105 @@ __global__ void __launch_bounds__(256) maxpool_bwd4_kernel(const T* __restrict__
     }
 }
 
+// ---- index-map variants: the forward pass records, per pooled element, which window position won (one byte, dh*k+dw); the
+// tangent pass and the backward pass then read one byte per window instead of re-scanning k*k inputs of the forward tensor
+template <typename T, int V>
+__global__ void __launch_bounds__(256) maxpool_idx_kernel(const T* __restrict__ x, T* __restrict__ y, int y_pitch, int y_c0,
+                                                          unsigned char* __restrict__ idx, int write_idx, int n, int H, int W, int C,
+                                                          int Ho, int Wo, int k, int s, int p) {
+    const int CV = C / V;
+    const long long total = (long long)n * Ho * Wo * CV;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % CV) * V;
+        long long t = i / CV;
+        const int wo = (int)(t % Wo); t /= Wo;
+        const int ho = (int)(t % Ho);
+        const long long b = t / Ho;
+        const long long base = b * H * W * C + c;
+        const long long oi = ((b * Ho + ho) * Wo + wo);
+        const int h0 = ho * s - p, w0 = wo * s - p;
+        float out[V];
+        unsigned char win[V];
+        if (write_idx) {
+            float best[V];
+#pragma unroll
+            for (int q = 0; q < V; ++q) { best[q] = -INFINITY; win[q] = 255; out[q] = 0.f; }
+            for (int dh = 0; dh < k; ++dh) {
+                const int h = h0 + dh;
+                if (h < 0 || h >= H) continue;
+                for (int dw = 0; dw < k; ++dw) {
+                    const int w = w0 + dw;
+                    if (w < 0 || w >= W) continue;
+                    float v[V];
+                    if (V == 4) { const float4 a = ld4(x + base + ((long long)h * W + w) * C); v[0] = a.x; v[1 % V] = a.y; v[2 % V] = a.z; v[3 % V] = a.w; }
+                    else v[0] = to_f(x[base + ((long long)h * W + w) * C]);
+#pragma unroll
+                    for (int q = 0; q < V; ++q)
+                        if (v[q] > best[q] || win[q] == 255) { best[q] = v[q]; win[q] = (unsigned char)(dh * k + dw); out[q] = v[q]; }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < V; ++q) idx[oi * C + c + q] = win[q];
+        } else {
+#pragma unroll
+            for (int q = 0; q < V; ++q) {
+                const int wq = idx[oi * C + c + q];
+                out[q] = wq == 255 ? 0.f : to_f(x[base + q + ((long long)(h0 + wq / k) * W + (w0 + wq % k)) * C]);
+            }
+        }
+        T* yp = y + oi * y_pitch + y_c0 + c;
+        if (V == 4) st4(yp, make_float4(out[0], out[1 % V], out[2 % V], out[3 % V]));
+        else *yp = from_f<T>(out[0]);
+    }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) maxpool_bwd_idx_kernel(const T* __restrict__ xref, const unsigned char* __restrict__ idx,
+                                                              const T* __restrict__ dy, int dy_pitch, int dy_c0, T* __restrict__ dx,
+                                                              int n, int H, int W, int C, int Ho, int Wo, int k, int s, int p, int act,
+                                                              float slope) {
+    const int CV = C / V;
+    const long long total = (long long)n * H * W * CV;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % CV) * V;
+        long long t = i / CV;
+        const int w = (int)(t % W); t /= W;
+        const int h = (int)(t % H);
+        const long long b = t / H;
+        int ho_lo = (h + p - k + 1 + s - 1) / s, ho_hi = (h + p) / s;
+        int wo_lo = (w + p - k + 1 + s - 1) / s, wo_hi = (w + p) / s;
+        if (h + p - k + 1 < 0) ho_lo = 0;
+        if (w + p - k + 1 < 0) wo_lo = 0;
+        ho_hi = min(ho_hi, Ho - 1); wo_hi = min(wo_hi, Wo - 1);
+        float acc[V];
+#pragma unroll
+        for (int q = 0; q < V; ++q) acc[q] = 0.f;
+        for (int ho = ho_lo; ho <= ho_hi; ++ho)
+            for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+                const int me = (h - (ho * s - p)) * k + (w - (wo * s - p));       // this input's position inside that window
+                const long long oi = ((b * Ho + ho) * Wo + wo);
+                float d[V];
+                if (V == 4) { const float4 a = ld4(dy + oi * dy_pitch + dy_c0 + c); d[0] = a.x; d[1 % V] = a.y; d[2 % V] = a.z; d[3 % V] = a.w; }
+                else d[0] = to_f(dy[oi * dy_pitch + dy_c0 + c]);
+                if (V == 4) {
+                    const uchar4 wv = *reinterpret_cast<const uchar4*>(idx + oi * C + c);
+                    if (wv.x == me) acc[0] += d[0];
+                    if (wv.y == me) acc[1 % V] += d[1 % V];
+                    if (wv.z == me) acc[2 % V] += d[2 % V];
+                    if (wv.w == me) acc[3 % V] += d[3 % V];
+                } else if (idx[oi * C + c] == me) acc[0] += d[0];
+            }
+        const long long xi = ((b * H + h) * W + w) * C + c;
+        if (V == 4) {
+            const float4 hx = ld4(xref + xi);
+            st4(dx + xi, make_float4(acc[0] * act_bwd(hx.x, act, slope), acc[1 % V] * act_bwd(hx.y, act, slope),
+                                     acc[2 % V] * act_bwd(hx.z, act, slope), acc[3 % V] * act_bwd(hx.w, act, slope)));
+        } else {
+            dx[xi] = from_f<T>(acc[0] * act_bwd(to_f(xref[xi]), act, slope));
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) avgpool_kernel(const T* __restrict__ x, int x_pitch, T* __restrict__ y, int y_pitch, int y_c0,
                                                       int n, int H, int W, int C, int k) {
@@ -711,14 +810,22 @@ int srgan_copy2d(const void* src, int src_pitch, int src_c0, void* dst, int dst_
     return SRGAN_OK;
 }
 
-int srgan_maxpool(const void* x, const void* xref, void* y, int y_pitch, int y_c0, int n, int H, int W, int C, int k, int stride,
-                  int pad, int dtype, void* stream) {
+int srgan_maxpool(const void* x, const void* xref, void* y, int y_pitch, int y_c0, unsigned char* idx, int idx_mode, int n, int H,
+                  int W, int C, int k, int stride, int pad, int dtype, void* stream) {
     SRGAN_REQUIRE(x && y && n >= 0 && H > 0 && W > 0 && C > 0 && k > 0 && stride > 0 && pad >= 0 && 2 * pad <= k && y_c0 >= 0 &&
                       y_c0 + C <= y_pitch, "srgan_maxpool: bad arguments");
     if (n == 0) return SRGAN_OK;
     const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = vec_ok(C, y_pitch, y_c0);
+    SRGAN_REQUIRE(idx_mode >= 0 && idx_mode <= 2 && (idx_mode == 0 || idx) && k * k < 255, "srgan_maxpool: bad index-map arguments");
+    if (idx_mode != 0) {
+        DISPATCH_T(dtype,
+                   if (vec) maxpool_idx_kernel<T, 4><<<ew_grid((long long)n * Ho * Wo * C / 4), 256, 0, st>>>((const T*)x, (T*)y, y_pitch, y_c0, idx, idx_mode == 1, n, H, W, C, Ho, Wo, k, stride, pad);
+                   else maxpool_idx_kernel<T, 1><<<ew_grid((long long)n * Ho * Wo * C), 256, 0, st>>>((const T*)x, (T*)y, y_pitch, y_c0, idx, idx_mode == 1, n, H, W, C, Ho, Wo, k, stride, pad));
+        SRGAN_CHECK_LAUNCH("maxpool_idx_kernel");
+        return SRGAN_OK;
+    }
     DISPATCH_T(dtype,
                if (vec) maxpool4_kernel<T><<<ew_grid((long long)n * Ho * Wo * C / 4), 256, 0, st>>>((const T*)x, (const T*)(xref ? xref : x), (T*)y, y_pitch, y_c0, n, H, W, C, Ho, Wo, k, stride, pad);
                else maxpool_kernel<T><<<ew_grid((long long)n * Ho * Wo * C), 256, 0, st>>>((const T*)x, (const T*)(xref ? xref : x), (T*)y, y_pitch, y_c0, n, H, W, C, Ho, Wo, k, stride, pad));
@@ -726,14 +833,21 @@ int srgan_maxpool(const void* x, const void* xref, void* y, int y_pitch, int y_c
     return SRGAN_OK;
 }
 
-int srgan_maxpool_bwd(const void* xref, const void* dy, int dy_pitch, int dy_c0, void* dx, int n, int H, int W, int C, int k,
-                      int stride, int pad, int act, float slope, int dtype, void* stream) {
+int srgan_maxpool_bwd(const void* xref, const unsigned char* idx, const void* dy, int dy_pitch, int dy_c0, void* dx, int n, int H, int W,
+                      int C, int k, int stride, int pad, int act, float slope, int dtype, void* stream) {
     SRGAN_REQUIRE(xref && dy && dx && n >= 0 && H > 0 && W > 0 && C > 0 && k > 0 && stride > 0 && pad >= 0 && 2 * pad <= k && dy_c0 >= 0 &&
                       dy_c0 + C <= dy_pitch, "srgan_maxpool_bwd: bad arguments");
     if (n == 0) return SRGAN_OK;
     const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = vec_ok(C, dy_pitch, dy_c0);
+    if (idx) {
+        DISPATCH_T(dtype,
+                   if (vec) maxpool_bwd_idx_kernel<T, 4><<<ew_grid((long long)n * H * W * C / 4), 256, 0, st>>>((const T*)xref, idx, (const T*)dy, dy_pitch, dy_c0, (T*)dx, n, H, W, C, Ho, Wo, k, stride, pad, act, slope);
+                   else maxpool_bwd_idx_kernel<T, 1><<<ew_grid((long long)n * H * W * C), 256, 0, st>>>((const T*)xref, idx, (const T*)dy, dy_pitch, dy_c0, (T*)dx, n, H, W, C, Ho, Wo, k, stride, pad, act, slope));
+        SRGAN_CHECK_LAUNCH("maxpool_bwd_idx_kernel");
+        return SRGAN_OK;
+    }
     DISPATCH_T(dtype,
                if (vec) maxpool_bwd4_kernel<T><<<ew_grid((long long)n * H * W * C / 4), 256, 0, st>>>((const T*)xref, (const T*)dy, dy_pitch, dy_c0, (T*)dx, n, H, W, C, Ho, Wo, k, stride, pad, act, slope);
                else maxpool_bwd_kernel<T><<<ew_grid((long long)n * H * W * C), 256, 0, st>>>((const T*)xref, (const T*)dy, dy_pitch, dy_c0, (T*)dx, n, H, W, C, Ho, Wo, k, stride, pad, act, slope));

@@ -183,6 +183,7 @@ class Engine:
         self.mdt = self.D.grad.dtype               # fp32 in the product; tests may run the schedule in fp64
         self.scalars = torch.zeros(N_SCALARS, dtype=self.mdt, device=self.device)
         self._buf = {}
+        self._idx_rows = {}
         self._probe = None
         for st in (self.D, self.G, self.DNN):
             if st is not None:
@@ -363,7 +364,13 @@ class Engine:
                 for l in net.layers:
                     if l.thin_ok and l.fwd == 'down':
                         self.buf(('col', tag, l.name), (nb_rows * l.geom.Hs * l.geom.Ws * l.kpad,))
-            return {name: self.buf((tag, 'a', name), (nb_rows * b.rows * b.ch,), zero=True) for name, b in net.bufs.items()}
+            acts = {name: self.buf((tag, 'a', name), (nb_rows * b.rows * b.ch,), zero=True) for name, b in net.bufs.items()}
+            for op in net.graph:
+                if op.kind == 'maxpool':               # one byte per pooled element: the max-pool index map
+                    acts['idx:' + op.dst] = self.buf((tag, 'idx', op.dst), (nb_rows * net.bufs[op.dst].rows * op.C,),
+                                                     dtype=torch.uint8)
+                    self._idx_rows[op.dst] = nb_rows
+            return acts
         acts = [self.buf((tag, 'a', 0), (nb_rows * net.layers[0].in_elems,))]
         for i, l in enumerate(net.layers, 1):
             acts.append(self.buf((tag, 'a', i), (nb_rows * l.out_elems,)))
@@ -509,8 +516,16 @@ class Engine:
             elif op.kind == 'read':
                 ops.copy2d(x, sb.ch, op.c0, y, db.ch, 0, n * sb.rows, op.C, False)
             elif op.kind == 'maxpool':
-                xref = R(acts[op.src], sb, mlo, mlo + n) if tangent else None
-                ops.maxpool(x, xref, y, db.ch, op.c0, n, op.H, op.W, op.C, op.k, op.stride, op.pad)
+                # the forward records the winning window position per pooled element; the tangent pass routes by the map of
+                # the x_hat rows, the backward pass reads the map of its own rows
+                im = acts['idx:' + op.dst]
+                e = (im.numel() // self._idx_rows[op.dst])
+                if tangent:
+                    ops.maxpool(x, None, y, db.ch, op.c0, n, op.H, op.W, op.C, op.k, op.stride, op.pad,
+                                idx=im[mlo * e:(mlo + n) * e], idx_mode=2)
+                else:
+                    ops.maxpool(x, None, y, db.ch, op.c0, n, op.H, op.W, op.C, op.k, op.stride, op.pad,
+                                idx=im[lo * e:hi * e], idx_mode=1)
             elif op.kind == 'avgpool':
                 ops.avgpool(x, sb.ch, y, db.ch, op.c0, n, op.H, op.W, op.C, op.k)
             elif op.kind == 'shuffle':
@@ -568,7 +583,10 @@ class Engine:
             elif op.kind == 'read':       # dense dst <- src slice: add into the (accumulating) concat delta
                 ops.copy2d(dy, db.ch, 0, dx, sb.ch, op.c0, n * sb.rows, op.C, True)
             elif op.kind == 'maxpool':
-                ops.maxpool_bwd(xa, dy, db.ch, op.c0, dx, n, op.H, op.W, op.C, op.k, op.stride, op.pad, sb.act, sb.slope)
+                im = acts['idx:' + op.dst]
+                e = (im.numel() // self._idx_rows[op.dst])
+                ops.maxpool_bwd(xa, dy, db.ch, op.c0, dx, n, op.H, op.W, op.C, op.k, op.stride, op.pad, sb.act, sb.slope,
+                                idx=im[mlo * e:(mlo + n) * e])
             elif op.kind == 'avgpool':
                 ops.avgpool_bwd(dy, db.ch, op.c0, dx, sb.ch, n, op.H, op.W, op.C, op.k, xa, sb.act, sb.slope)
             elif op.kind == 'shuffle':    # a permutation: both sides are w.r.t. the same pre-activation

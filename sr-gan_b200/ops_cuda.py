@@ -85,8 +85,8 @@ def load_library(path: str = LIB_PATH):
     lib.srgan_affine_grad.argtypes = [vp, c_int, vp, c_int, c_int, c_ll, c_int, vp, vp, c_f, vp, vp, c_int, c_int, vp]
     lib.srgan_affine_bwd_grad.argtypes = [vp, c_int, vp, vp, c_int, c_int, c_ll, c_int, vp, vp, vp, c_f, vp, vp, c_int, c_int, vp]
     lib.srgan_copy2d.argtypes = [vp, c_int, c_int, vp, c_int, c_int, c_ll, c_int, c_int, c_int, vp]
-    lib.srgan_maxpool.argtypes = [vp, vp, vp, c_int, c_int] + [c_int] * 7 + [c_int, vp]
-    lib.srgan_maxpool_bwd.argtypes = [vp, vp, c_int, c_int, vp] + [c_int] * 7 + [c_int, c_f, c_int, vp]
+    lib.srgan_maxpool.argtypes = [vp, vp, vp, c_int, c_int, vp, c_int] + [c_int] * 7 + [c_int, vp]
+    lib.srgan_maxpool_bwd.argtypes = [vp, vp, vp, c_int, c_int, vp] + [c_int] * 7 + [c_int, c_f, c_int, vp]
     lib.srgan_avgpool.argtypes = [vp, c_int, vp, c_int, c_int] + [c_int] * 5 + [c_int, vp]
     lib.srgan_avgpool_bwd.argtypes = [vp, c_int, c_int, vp, c_int] + [c_int] * 5 + [vp, c_int, c_f, c_int, vp]
     lib.srgan_crowd_loss.argtypes = [vp, vp, pp, c_int, vp, c_int, c_ll, c_int, c_f, c_f, vp, vp, vp, c_int, vp]
@@ -318,13 +318,16 @@ class CudaOps:
         self._ck(self.lib.srgan_copy2d(self._p(src), src_pitch, src_c0, self._p(dst, src.dtype), dst_pitch, dst_c0, rows, C,
                                        int(bool(accumulate)), _dt(src.dtype), self._stream()), 'srgan_copy2d')
 
-    def maxpool(self, x, xref, y, y_pitch, y_c0, n, H, W, C, k, s, p):
+    def maxpool(self, x, xref, y, y_pitch, y_c0, n, H, W, C, k, s, p, idx=None, idx_mode=0):
+        """idx (uint8 [n, Ho, Wo, C]): idx_mode 1 = written by this (forward) call, 2 = read (tangent routing)."""
         self._ck(self.lib.srgan_maxpool(self._p(x), self._p(xref, x.dtype) if xref is not None else None, self._p(y, x.dtype),
-                                        y_pitch, y_c0, n, H, W, C, k, s, p, _dt(x.dtype), self._stream()), 'srgan_maxpool')
+                                        y_pitch, y_c0, self._p(idx, torch.uint8) if idx is not None else None, idx_mode, n, H, W,
+                                        C, k, s, p, _dt(x.dtype), self._stream()), 'srgan_maxpool')
 
-    def maxpool_bwd(self, xref, dy, dy_pitch, dy_c0, dx, n, H, W, C, k, s, p, act, slope):
-        self._ck(self.lib.srgan_maxpool_bwd(self._p(xref), self._p(dy, xref.dtype), dy_pitch, dy_c0, self._p(dx, xref.dtype), n,
-                                            H, W, C, k, s, p, act, slope, _dt(xref.dtype), self._stream()), 'srgan_maxpool_bwd')
+    def maxpool_bwd(self, xref, dy, dy_pitch, dy_c0, dx, n, H, W, C, k, s, p, act, slope, idx=None):
+        self._ck(self.lib.srgan_maxpool_bwd(self._p(xref), self._p(idx, torch.uint8) if idx is not None else None,
+                                            self._p(dy, xref.dtype), dy_pitch, dy_c0, self._p(dx, xref.dtype), n, H, W, C, k, s, p,
+                                            act, slope, _dt(xref.dtype), self._stream()), 'srgan_maxpool_bwd')
 
     def avgpool(self, x, x_pitch, y, y_pitch, y_c0, n, H, W, C, k):
         self._ck(self.lib.srgan_avgpool(self._p(x), x_pitch, self._p(y, x.dtype), y_pitch, y_c0, n, H, W, C, k, _dt(x.dtype),

@@ -403,6 +403,19 @@ def test_copy2d_and_pools(ops, dt):
         ref.maxpool_bwd(x, dy, pitch, c0, dx_ref, n, H, W, C, k, s, p, 1, 0.0)
         ops.maxpool_bwd(cu(x), cu(dy), pitch, c0, dx, n, H, W, C, k, s, p, 1, 0.0)
         close(dx, dx_ref, tol(dt), 'maxpool_bwd')
+        # index-map variants: the forward writes one byte per pooled element, tangent routing and backward read it
+        idx_ref = torch.zeros(n * Ho * Wo * C, dtype=torch.uint8)
+        idx = idx_ref.clone().cuda()
+        ref.maxpool(x, None, y_ref, pitch, c0, n, H, W, C, k, s, p, idx=idx_ref, idx_mode=1)
+        ops.maxpool(cu(x), None, y, pitch, c0, n, H, W, C, k, s, p, idx=idx, idx_mode=1)
+        close(y, y_ref, 1e-6, 'maxpool idx fwd')
+        assert torch.equal(idx.cpu(), idx_ref), 'index maps differ (first-maximum rule)'
+        ref.maxpool(v, None, y_ref, pitch, c0, n, H, W, C, k, s, p, idx=idx_ref, idx_mode=2)
+        ops.maxpool(cu(v), None, y, pitch, c0, n, H, W, C, k, s, p, idx=idx, idx_mode=2)
+        close(y, y_ref, 1e-6, 'maxpool idx route')
+        ref.maxpool_bwd(x, dy, pitch, c0, dx_ref, n, H, W, C, k, s, p, 1, 0.0, idx=idx_ref)
+        ops.maxpool_bwd(cu(x), cu(dy), pitch, c0, dx, n, H, W, C, k, s, p, 1, 0.0, idx=idx)
+        close(dx, dx_ref, tol(dt), 'maxpool_bwd idx')
     for n, H, W, C, k, xp in ((3, 8, 8, 12, 2, 12), (2, 7, 7, 40, 7, 64), (1, 4, 4, 3, 2, 5)):
         x = rnd(gen, n * H * W * xp, dt=dt)
         Ho, Wo = H // k, W // k

@@ -319,24 +319,48 @@ class TorchOps:
         _, idx = F.max_pool2d(xr, k, s, p, return_indices=True)
         return idx
 
-    def maxpool(self, x, xref, y, y_pitch, y_c0, n, H, W, C, k, s, p):
-        """y[:, c0:c0+C] = x at the argmax of xref (xref None: of x itself) over each k x k window (stride s, pad p)."""
+    @staticmethod
+    def _window_origin(Ho, Wo, s, p):
+        h0 = (torch.arange(Ho) * s - p).view(1, 1, Ho, 1)
+        w0 = (torch.arange(Wo) * s - p).view(1, 1, 1, Wo)
+        return h0, w0
+
+    def _idx_encode(self, flat, W, k, s, p):
+        """torch's flat argmax (h*W+w) [n,C,Ho,Wo] -> the CUDA op's byte map [n,Ho,Wo,C] of window positions dh*k+dw."""
+        h0, w0 = self._window_origin(flat.shape[2], flat.shape[3], s, p)
+        code = (flat // W - h0) * k + (flat % W - w0)
+        return code.permute(0, 2, 3, 1).contiguous().to(torch.uint8)
+
+    def _idx_decode(self, idx, n, Ho, Wo, C, W, k, s, p):
+        code = idx.view(n, Ho, Wo, C).permute(0, 3, 1, 2).to(torch.int64)
+        h0, w0 = self._window_origin(Ho, Wo, s, p)
+        return (h0 + code // k) * W + (w0 + code % k)
+
+    def maxpool(self, x, xref, y, y_pitch, y_c0, n, H, W, C, k, s, p, idx=None, idx_mode=0):
+        """y[:, c0:c0+C] = x at the argmax of xref (xref None: of x itself) over each k x k window (stride s, pad p).
+        idx (uint8 [n,Ho,Wo,C], window position dh*k+dw of the winner): idx_mode 1 = written here, 2 = routed by it."""
         self.launches += 1
-        idx = self._maxpool_idx(x if xref is None else xref, n, H, W, C, k, s, p)
-        Ho, Wo = idx.shape[2], idx.shape[3]
+        Ho, Wo = self._pool_out(H, k, s, p), self._pool_out(W, k, s, p)
+        if idx_mode == 2:
+            flat = self._idx_decode(idx, n, Ho, Wo, C, W, k, s, p)
+        else:
+            flat = self._maxpool_idx(x if xref is None else xref, n, H, W, C, k, s, p)
+            if idx_mode == 1:
+                idx.view(n, Ho, Wo, C).copy_(self._idx_encode(flat, W, k, s, p))
         xv = x.view(n, H * W, C).permute(0, 2, 1)                                   # [n, C, HW]
-        out = torch.gather(xv, 2, idx.reshape(n, C, Ho * Wo))                       # [n, C, HoWo]
+        out = torch.gather(xv, 2, flat.reshape(n, C, Ho * Wo))                      # [n, C, HoWo]
         y.view(n * Ho * Wo, y_pitch)[:, y_c0:y_c0 + C] = out.permute(0, 2, 1).reshape(n * Ho * Wo, C).to(y.dtype)
 
-    def maxpool_bwd(self, xref, dy, dy_pitch, dy_c0, dx, n, H, W, C, k, s, p, act, slope):
-        """dx[i] = act'(xref[i]) * sum over the windows whose argmax is i of dy[window]   (dx dense [n,H,W,C], overwritten)."""
+    def maxpool_bwd(self, xref, dy, dy_pitch, dy_c0, dx, n, H, W, C, k, s, p, act, slope, idx=None):
+        """dx[i] = act'(xref[i]) * sum over the windows whose argmax is i of dy[window]   (dx dense [n,H,W,C], overwritten);
+        with idx the argmax comes from the forward's index map."""
         self.launches += 1
         cd = self._cd(dy)
-        idx = self._maxpool_idx(xref, n, H, W, C, k, s, p)
-        Ho, Wo = idx.shape[2], idx.shape[3]
+        Ho, Wo = self._pool_out(H, k, s, p), self._pool_out(W, k, s, p)
+        flat = self._idx_decode(idx, n, Ho, Wo, C, W, k, s, p) if idx is not None else self._maxpool_idx(xref, n, H, W, C, k, s, p)
         d = dy.view(n * Ho * Wo, dy_pitch)[:, dy_c0:dy_c0 + C].to(cd).reshape(n, Ho * Wo, C).permute(0, 2, 1)
         g = torch.zeros(n, C, H * W, dtype=cd)
-        g.scatter_add_(2, idx.reshape(n, C, Ho * Wo), d)
+        g.scatter_add_(2, flat.reshape(n, C, Ho * Wo), d)
         g = g.permute(0, 2, 1).reshape(-1) * dact(xref.to(cd), act, slope)
         dx.copy_(g.to(dx.dtype))
 
