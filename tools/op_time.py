@@ -57,6 +57,16 @@ tot = sum(v[1] for v in by_name.values())
 print(f'{name} B={B} {s.precision}: op-timed eager step {tot:.2f} ms in {len(recs)} calls (wall of the eager step on the device: {e0.elapsed_time(e1):.2f} ms)')
 for k, (c, t) in sorted(by_name.items(), key=lambda kv: -kv[1][1]):
     print(f'  {t:9.3f} ms {100 * t / tot:5.1f}% {c:5d}  {k}')
+cat = collections.defaultdict(lambda: [0, 0.0])
+for key, nm, a, b in recs:
+    m = __import__('re').match(r'(conv_\w+) n=(\d+) (\d+)x(\d+)x(\d+)<-(\d+)x(\d+)x(\d+) k(\d+)s(\d+) tensor=(\d)', key)
+    if m:
+        op, n, hs, ws, ca, hl, wl, cb, k, st, tc = m.groups()
+        c = f'{op} k{k}s{st} ' + ('gemm(1x1)' if hl == '1' and k == '1' else f'{hs}x{ws}') + f' tensor={tc}'
+        cat[c][0] += 1; cat[c][1] += a.elapsed_time(b)
+print('contractions by class:')
+for k, (c, t) in sorted(cat.items(), key=lambda kv: -kv[1][1])[:24]:
+    print(f'  {t:9.3f} ms {100 * t / tot:5.1f}% {c:5d}  {k}')
 print('top shapes:')
 for k, (c, t) in sorted(by_key.items(), key=lambda kv: -kv[1][1])[:45]:
     print(f'  {t:9.3f} ms {100 * t / tot:5.1f}% {c:5d}  {k}')
