@@ -213,6 +213,7 @@ def main():
     ap.add_argument('--workload', default='age', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=0, help='per-GPU batch (default: the workload\'s)')
     ap.add_argument('--ref-batch', type=int, default=0)
+    ap.add_argument('--micro-batch', type=int, default=0, help='run every step in micro-batches of this many samples (exact)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.warmup < 3:
@@ -244,6 +245,7 @@ def main():
     s.matching_loss_multiplier, s.contrasting_loss_multiplier, s.gradient_penalty_multiplier = wl['mult']
     s.map_multiplier = 1e-3
     s.precision = args.precision
+    s.micro_batch = args.micro_batch
     if name == 'age':
         exp = srgan_b200.Experiment(s, 'age', device=dev, comm=comm, image_size=AGE['image'], conv_dim=AGE['conv_dim'], z_dim=AGE['z_dim'])
     else:
@@ -386,7 +388,7 @@ def main():
                 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
                 'config': {'workload': workload_string(name, B, world),
-                           'precision_mode': args.precision, 'parallelism': f'dp{world}', 'cuda_graph': bool(graphed),
+                           'precision_mode': args.precision, 'parallelism': f'dp{world}', 'cuda_graph': bool(graphed), 'micro_batch': args.micro_batch,
                            'l2': ('inputs and activations of one step (age: 39 MB + ~1 GB, crowd: ~0.7 GB per sample) exceed the 126 MB L2; no flush needed'
                                   if name != 'coefficient' else 'working set (2 MB) is L2-resident by design: the step is launch/latency-bound, not bandwidth-bound'),
                            'global_steps_per_s': global_steps,

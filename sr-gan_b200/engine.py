@@ -861,6 +861,157 @@ class Engine:
         self.backward(G, gacts, gdeltas, 0, B)
         self.adam(G, cfg.learning_rate, 0.0, cfg.betas, cfg.eps, deferrable='G')                  # srgan.py:137, :305
 
+    # ------------------------------------------------------------------ micro-batched steps
+    # Activation memory is 5 row blocks per buffer: the crowd discriminator needs ~0.7 GB per sample of the local batch, so a
+    # per-GPU batch of 512 (global 4096 on 8 GPUs, BASELINE configs[4]) cannot be held at once.  Micro-batching is EXACT
+    # for SR-GAN because the feature losses see the activations only through the batch mean (hard parts):
+    # pass 1 runs the forwards micro-batch by micro-batch and accumulates the feature sums; the sums are all-reduced and
+    # the distance losses give d(loss)/d(mean); pass 2 re-runs each micro-batch (forward, gradient penalty, backward) with
+    # that known seed and accumulates the parameter gradients; one Adam update at the end.  Cost: one extra forward.
+    @staticmethod
+    def _ysl(y, r0, r1):
+        return tuple(t[r0:r1] for t in y) if isinstance(y, (tuple, list)) else y[r0:r1]
+
+    def dnn_step_micro(self, x, y, cfg, lr, weight_decay, mb):
+        self.ops.begin()
+        st, net = self.DNN, self.d_net
+        B = x.shape[0]
+        if B % mb:
+            raise ValueError(f'local batch {B} is not a multiple of the micro-batch {mb}')
+        Bg = self._global_batch(B)
+        F = net.feature_size
+        fact, fslope = net.feature_act
+        acts = self.alloc_acts('D', net, 5 * mb)
+        deltas = self.alloc_deltas('D', net, 5 * mb)
+        pred = self.buf('pred', (mb,), self.mdt)
+        dpred = self.buf('dpred', (mb,), self.mdt)
+        self.scalars[SC_DNN:SC_DNN + 1].zero_()
+        for m in range(B // mb):
+            r0, r1 = m * mb, (m + 1) * mb
+            self.load_input(net, x[r0:r1], self.rows(self._in(net, acts), net.in_elems, 0, mb), mb)
+            self.forward(st, acts, 0, mb)
+            feats = self._brows_feat(net, acts, 0, mb)
+            hook = self._labeled(st, acts, deltas, mb, self._ysl(y, r0, r1), cfg, Bg, self.scalars[SC_DNN:SC_DNN + 1], pred, dpred)
+            self.ops.seed_rows(self._brows_feat(net, deltas, 0, mb), mb, F, None, dpred, st.whead[0:F], feats, fact, fslope)
+            self._head_grads(st, feats, mb, 0, dpred)
+            self.backward(st, acts, deltas, 0, mb, hook=hook)
+        self.adam(st, lr, weight_decay, cfg.betas, cfg.eps, deferrable='DNN')
+
+    def gan_step_micro(self, x, y, u, z, alpha, z2, cfg, train_generator, mb):
+        ops, D, G, net, gnet = self.ops, self.D, self.G, self.d_net, self.g_net
+        ops.begin()
+        B = x.shape[0]
+        if u.shape[0] != B or z.shape[0] != B or alpha.numel() != B:
+            raise ValueError('labeled, unlabeled and noise batches must have the same size (SURVEY App. E.2)')
+        if B % mb:
+            raise ValueError(f'local batch {B} is not a multiple of the micro-batch {mb}')
+        if cfg.method == 'dggan':
+            raise NotImplementedError('micro-batching is implemented for the SR-GAN feature losses only')
+        b, nm = mb, B // mb
+        Bg = self._global_batch(B)
+        F = net.feature_size
+        fact, fslope = net.feature_act
+        acts = self.alloc_acts('D', net, 5 * b)
+        deltas = self.alloc_deltas('D', net, 5 * b)
+        a_in = self._in(net, acts)
+        E = net.in_elems
+        alpha = alpha.reshape(-1)
+        sc = self.scalars
+        sc[SC_LABELED:SC_GEN + 1].zero_()
+
+        def fblk(lo, hi):
+            return self._brows_feat(net, acts, lo, hi)
+
+        def dblk(lo, hi):
+            return self._brows_feat(net, deltas, lo, hi)
+
+        def d_inputs(m, with_hat):
+            """rows [0,b) = x_m, [b,2b) = u_m, [2b,3b) = G(z_m), [3b,4b) = x_hat_m"""
+            r0, r1 = m * b, (m + 1) * b
+            self.load_input(net, x[r0:r1], self.rows(a_in, E, 0, b), b)
+            self.load_input(net, u[r0:r1], self.rows(a_in, E, b, 2 * b), b)
+            gacts = self.alloc_acts('G', gnet, b)
+            gacts[-1] = self.rows(a_in, E, 2 * b, 3 * b)
+            self.load_input(gnet, z[r0:r1], gacts[0], b)
+            self.forward(G, gacts, 0, b)
+            if with_hat:
+                ops.interpolate(self.rows(a_in, E, b, 2 * b), self.rows(a_in, E, 2 * b, 3 * b), alpha[r0:r1],
+                                self.rows(a_in, E, 3 * b, 4 * b), b, E)
+        # ---- D step, pass 1: feature sums of x, u, fake over all micro-batches
+        sums = self.buf('fsums', (3, F), self.mdt)
+        sums.zero_()
+        for m in range(nm):
+            d_inputs(m, False)
+            self.forward(D, acts, 0, 3 * b)
+            for j in range(3):
+                ops.colsum(fblk(j * b, (j + 1) * b), b, F, sums[j], 0, None)
+        if self.comm is not None:
+            self.comm.all_reduce_sum(sums)
+        gvec = self.buf('gvec', (3, F), self.mdt)
+        inv = 1.0 / Bg
+        ops.distance(sums[1], sums[0], F, inv, DIST_KINDS[cfg.matching_distance_function],
+                     cfg.matching_loss_multiplier * cfg.srgan_loss_multiplier, sc[SC_UNLABELED:SC_UNLABELED + 1],
+                     gvec[1], gvec[0], False)
+        ops.distance(sums[1], sums[2], F, inv, DIST_KINDS[cfg.contrasting_distance_function],
+                     cfg.contrasting_loss_multiplier * cfg.srgan_loss_multiplier, sc[SC_FAKE:SC_FAKE + 1],
+                     gvec[1], gvec[2], True)
+        # ---- D step, pass 2: per micro-batch forward over [x; u; fake; x_hat], gradient penalty, one backward
+        pred = self.buf('pred', (b,), self.mdt)
+        dpred = self.buf('dpred', (b,), self.mdt)
+        s_norm = self.buf('s_norm', (b,), self.mdt)
+        g0 = self.buf('g0', (b * E,))
+        gnorm = self.buf('gnorm', (b,), self.mdt)
+        for m in range(nm):
+            r0, r1 = m * b, (m + 1) * b
+            d_inputs(m, True)
+            self.forward(D, acts, 0, 4 * b)
+            hook = self._labeled(D, acts, deltas, b, self._ysl(y, r0, r1), cfg, Bg, sc[SC_LABELED:SC_LABELED + 1], pred, dpred)
+            ops.seed_rows(dblk(0, b), b, F, gvec[0], dpred, D.whead[0:F], fblk(0, b), fact, fslope)
+            ops.seed_rows(dblk(b, 2 * b), b, F, gvec[1], None, None, fblk(b, 2 * b), fact, fslope)
+            ops.seed_rows(dblk(2 * b, 3 * b), b, F, gvec[2], None, None, fblk(2 * b, 3 * b), fact, fslope)
+            ops.feature_norm_seed(fblk(3 * b, 4 * b), b, F, s_norm, dblk(4 * b, 5 * b), fact, fslope)
+            self._head_grads(D, fblk(0, b), b, 0, dpred)
+            self.gchain(D, acts, deltas, b, g0)
+            ops.gradnorm_penalty(g0, b, E, cfg.gradient_penalty_multiplier / Bg, 1.0 / Bg, gnorm, sc[SC_GP:SC_GP + 1],
+                                 sc[SC_GNORM:SC_GNORM + 1], self.rows(a_in, E, 4 * b, 5 * b))
+            self.tangent(D, acts, b)
+            ops.gp_feature_seed(fblk(4 * b, 5 * b), fblk(3 * b, 4 * b), s_norm, dblk(3 * b, 4 * b), b, F, fact, fslope)
+            self.backward(D, acts, deltas, 0, 4 * b, 0, 5 * b, hook=hook)
+        self.adam(D, cfg.learning_rate, cfg.weight_decay, cfg.betas, cfg.eps)
+        if not train_generator:
+            return
+        # ---- G step with the updated D, pass 1: feature sums of G(z2) and u
+        gl = gnet.layers
+
+        def g_inputs(m):
+            r0, r1 = m * b, (m + 1) * b
+            gacts = self.alloc_acts('G', gnet, b)
+            gacts[-1] = self.rows(a_in, E, 0, b)
+            self.load_input(gnet, z2[r0:r1], gacts[0], b)
+            self.forward(G, gacts, 0, b)
+            return gacts
+        sums.zero_()
+        for m in range(nm):
+            g_inputs(m)
+            self.load_input(net, u[m * b:(m + 1) * b], self.rows(a_in, E, b, 2 * b), b)
+            self.forward(D, acts, 0, 2 * b)
+            ops.colsum(fblk(0, b), b, F, sums[0], 0, None)
+            ops.colsum(fblk(b, 2 * b), b, F, sums[1], 0, None)
+        if self.comm is not None:
+            self.comm.all_reduce_sum(sums)
+        ops.distance(sums[1], sums[0], F, 1.0 / Bg, DIST_KINDS[cfg.matching_distance_function],
+                     cfg.matching_loss_multiplier, sc[SC_GEN:SC_GEN + 1], gvec[1], gvec[0], False)
+        # ---- G step, pass 2: per micro-batch G forward, D forward on the fake rows, D data-backward, G backward
+        gdeltas = self.alloc_deltas('G', gnet, b)
+        for m in range(nm):
+            gacts = g_inputs(m)
+            self.forward(D, acts, 0, b)
+            ops.seed_rows(dblk(0, b), b, F, gvec[0], None, None, fblk(0, b), fact, fslope)
+            self.backward(D, acts, deltas, 0, b, need_input_grad=True, dinput=gdeltas[len(gl)], input_href=gacts[-1],
+                          input_act=gl[-1].act, weight_grads=False)
+            self.backward(G, gacts, gdeltas, 0, b)
+        self.adam(G, cfg.learning_rate, 0.0, cfg.betas, cfg.eps, deferrable='G')
+
     # ------------------------------------------------------------------ inference-style helpers
     def d_features(self, x, st: Optional[NetState] = None):
         """D(x) forward only: returns (prediction [B], features rows [B, F] in NHWC order)."""

@@ -90,6 +90,7 @@ class Settings:
         self.precision = 'fp32'          # 'fp32' (SIMT, 1e-4 parity) | 'bf16' (tcgen05 tensor cores, 2e-2 parity)
         self.use_cuda_graph = True       # replay the step methods from CUDA graphs (piecewise around collectives)
         self.use_persistent_kernel = True    # coefficient application, single rank: one cooperative kernel per step method
+        self.micro_batch = 0             # > 0: run the step in micro-batches of this many samples (exact; bounds activation memory)
 
 
 class StepConfig:
@@ -107,6 +108,7 @@ class StepConfig:
         self.generator_training_step_period = int(settings.generator_training_step_period)
         self.mean_offset = float(getattr(settings, 'mean_offset', 0))
         self.map_multiplier = float(getattr(settings, 'map_multiplier', 1e-6))
+        self.micro_batch = int(getattr(settings, 'micro_batch', 0) or 0)
         self.batch_size = int(settings.batch_size)
         for k in ('matching_distance_function', 'contrasting_distance_function'):
             fn = getattr(settings, k)
@@ -488,13 +490,20 @@ class StepRunner:
         if self.persistent:
             self._coef_step(1, examples, labels, lr_dnn=lr, wd=wd)
             return
+        mb = cfg.micro_batch if 0 < cfg.micro_batch < examples.shape[0] else 0
+
+        def run(xx, yy):
+            if mb:
+                self.engine.dnn_step_micro(xx, yy, cfg, lr, wd, mb)
+            else:
+                self.engine.dnn_step(xx, yy, cfg, lr, wd)
         if not self.use_cuda_graph:
-            self.engine.dnn_step(examples, labels, cfg, lr, wd)
+            run(examples, labels)
             return
         xs = self._static('dnn_x', examples)
         ys, ypairs = self._static_labels('dnn_y', labels)
-        key = ('dnn', tuple(examples.shape), lr, wd, cfg.labeled_loss_multiplier, cfg.labeled_loss_order, cfg.map_multiplier)
-        self._graphed(key, [(xs, examples)] + ypairs, lambda: self.engine.dnn_step(xs, ys, cfg, lr, wd))
+        key = ('dnn', tuple(examples.shape), lr, wd, cfg.labeled_loss_multiplier, cfg.labeled_loss_order, cfg.map_multiplier, mb)
+        self._graphed(key, [(xs, examples)] + ypairs, lambda: run(xs, ys))
 
     def gan_step(self, labeled_examples, labels, unlabeled_examples, step=0, noise=None):
         cfg = self.config()
@@ -505,8 +514,15 @@ class StepRunner:
         if self.persistent:
             self._coef_step(2, labeled_examples, labels, unlabeled_examples, z, alpha.reshape(-1), z2, train_g=train_g)
             return
+        mb = cfg.micro_batch if 0 < cfg.micro_batch < B else 0
+
+        def run(xx, yy, uu, zz, aa, zz2):
+            if mb:
+                self.engine.gan_step_micro(xx, yy, uu, zz, aa, zz2, cfg, train_g, mb)
+            else:
+                self.engine.gan_step(xx, yy, uu, zz, aa, zz2, cfg, train_generator=train_g)
         if not self.use_cuda_graph:
-            self.engine.gan_step(labeled_examples, labels, unlabeled_examples, z, alpha, z2, cfg, train_generator=train_g)
+            run(labeled_examples, labels, unlabeled_examples, z, alpha, z2)
             return
         alpha = alpha.reshape(-1)
         ys, ypairs = self._static_labels('y', labels)
@@ -515,7 +531,7 @@ class StepRunner:
               (self._static('alpha', alpha), alpha), (self._static('z2', z2), z2)]
         key = ('gan', tuple(labeled_examples.shape), train_g, repr(sorted(vars(cfg).items())))
         xs, us, zs, als, z2s = (d for d, _ in st)
-        self._graphed(key, st + ypairs, lambda: self.engine.gan_step(xs, ys, us, zs, als, z2s, cfg, train_generator=train_g))
+        self._graphed(key, st + ypairs, lambda: run(xs, ys, us, zs, als, z2s))
 
     def scalars(self):
         """One device->host read of the step's scalars (the .item() calls of srgan.py:268-270, 306-319)."""

@@ -40,9 +40,11 @@ def modules_from_state(st: O.OracleState, **dcgan_kwargs):
     return D.cuda(), G.cuda(), DNN.cuda()
 
 
-def runner_from_state(st: O.OracleState, cfg: O.StepConfig, precision='fp32', comm=None):
+def runner_from_state(st: O.OracleState, cfg: O.StepConfig, precision='fp32', comm=None, micro_batch=0):
     D, G, DNN = modules_from_state(st)
-    return srgan_b200.StepRunner(D, G, DNN, settings_from_cfg(cfg, precision), cfg.method, precision=precision, comm=comm)
+    s = settings_from_cfg(cfg, precision)
+    s.micro_batch = micro_batch
+    return srgan_b200.StepRunner(D, G, DNN, s, cfg.method, precision=precision, comm=comm)
 
 
 def to_cuda(*ts):

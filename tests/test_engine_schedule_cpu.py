@@ -190,3 +190,46 @@ def test_crowd_stem_thin_lowering_matches_oracle_fp64():
         for k, v in params.items():
             if not O.is_buffer_key(k):
                 assert rel(mine.params[k], v) < 1e-8, (net, k, rel(mine.params[k], v))
+
+
+@pytest.mark.parametrize('family', ['dcgan', 'crowd'])
+def test_micro_batched_step_is_exact_fp64(family):
+    """Micro-batching (BASELINE configs[4]: per-GPU batches too large for the activation buffers) must reproduce the
+    full-batch oracle step: feature sums are accumulated over the micro-batches before the distance losses, the
+    per-sample terms are normalised by the full batch, gradients accumulate across micro-batches."""
+    dt = torch.float64
+    B, mb = 4, 2
+    if family == 'dcgan':
+        st = O.init_dcgan(seed=4, image_size=32, conv_dim=8, z_dim=16, dtype=dt, scale=3.0)
+        cfg = O.StepConfig(batch_size=B, matching_loss_multiplier=1e2, contrasting_loss_multiplier=1e1,
+                           gradient_penalty_multiplier=1e2)
+        eng = build_engine(st, dt, 32, 8, 16)
+        gen = torch.Generator().manual_seed(3)
+
+        def batch():
+            return ((torch.rand(B, 3, 32, 32, generator=gen, dtype=dt) * 2 - 1), torch.rand(B, generator=gen, dtype=dt) * 85 + 10,
+                    (torch.rand(B, 3, 32, 32, generator=gen, dtype=dt) * 2 - 1), torch.randn(B, 16, generator=gen, dtype=dt),
+                    torch.rand(B, 1, 1, 1, generator=gen, dtype=dt), torch.randn(B, 16, generator=gen, dtype=dt))
+    else:
+        kw = dict(block_config=(2, 2, 2, 2), growth_rate=8, num_init_features=16, bn_size=2, label_patch_size=64)
+        st = O.init_crowd(seed=1, image_size=64, z_dim=16, g_conv_dim=8, dtype=dt, scale=2.0, **kw)
+        cfg = O.StepConfig(batch_size=B, matching_loss_multiplier=1e3, contrasting_loss_multiplier=1e2,
+                           gradient_penalty_multiplier=1e2, map_multiplier=1e-3)
+        eng = build_crowd_engine(st, dt, kw, 64, 16, 8)
+        seeds = iter(range(50, 60))
+
+        def batch():
+            return O.synthetic_crowd_batch(B, next(seeds), image=64, label=64, z_dim=16, dtype=dt)
+    for i in range(2):
+        x, y, u, z, alpha, z2 = batch()
+        out = O.training_step(st, cfg, x, y, u, z, alpha, z2, step=i)
+        eng.dnn_step_micro(x, y, cfg, O.dnn_lr(cfg, i), cfg.weight_decay, mb)
+        eng.gan_step_micro(x, y, u, z, alpha, z2, cfg, True, mb)
+        got = read_scalars(eng)
+        assert out['gradient_penalty'] > 0
+        for k in SCALARS:
+            assert got[k] == pytest.approx(out[k], rel=1e-9, abs=1e-12), (family, i, k, got[k], out[k])
+    for net, params, mine in (('D', st.D, eng.D), ('G', st.G, eng.G), ('DNN', st.DNN, eng.DNN)):
+        for k, v in params.items():
+            if not O.is_buffer_key(k):
+                assert rel(mine.params[k], v) < 1e-8, (family, net, k, rel(mine.params[k], v))

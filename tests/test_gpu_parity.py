@@ -306,3 +306,22 @@ def test_coefficient_1k_step_loss_curve_band():
                 assert abs(got - ref) <= max(0.15 * abs(ref), 1e-3), (name, k, got, ref)
             else:
                 assert abs(got - ref) <= 0.05 * abs(ref) + 1e-6, (name, k, got, ref)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_crowd_micro_batched_step_vs_oracle(precision):
+    """Exact micro-batching (BASELINE configs[4]): the crowd step with local batch 4 in micro-batches of 2 (eager, capture,
+    replay) against the full-batch oracle step."""
+    st = O.init_crowd(seed=1, image_size=64, z_dim=16, g_conv_dim=8, scale=2.0, **CROWD_SMALL)
+    cfg = O.StepConfig(batch_size=4, matching_loss_multiplier=1e3, contrasting_loss_multiplier=1e2,
+                       gradient_penalty_multiplier=1e2, map_multiplier=1e-3)
+    r = runner_from_state(st, cfg, precision, micro_batch=2)
+    t = TOL[precision]['scalar']
+    for i in range(3):
+        x, y, u, z, alpha, z2 = O.synthetic_crowd_batch(4, 70 + i, image=64, label=64, z_dim=16)
+        ref = O.training_step(st, cfg, x, y, u, z, alpha, z2, step=i)
+        xc, yc, uc, zc, ac, z2c = to_cuda(x, y, u, z, alpha, z2)
+        r.dnn_step(xc, yc)
+        r.gan_step(xc, yc, uc, i, noise=(zc, ac, z2c))
+        check_scalars(r.scalars(), ref, t * (1 if i == 0 else 3), ('crowd-micro', i))
+        assert ref['gradient_penalty'] > 0
