@@ -9,7 +9,14 @@
 namespace {
 
 __device__ __forceinline__ float4 ld4f(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ float bn_scale(float gamma, float var, float eps) { return gamma / sqrtf(var + eps); }
+// gamma / sqrt(var + eps), branch-free (MUFU.RSQ + one Newton step, ~1 ulp): sqrtf / division compile to slow-path branches
+// that serialise the per-thread parameter loads of the streaming kernels
+__device__ __forceinline__ float bn_scale(float gamma, float var, float eps) {
+    const float v = var + eps;
+    float y = rsqrtf(v);
+    y = y * (1.5f - 0.5f * v * y * y);
+    return gamma * y;
+}
 
 inline int ew_grid(long long work_items) {
     long long b = (work_items + 255) / 256;
@@ -128,50 +135,6 @@ __global__ void __launch_bounds__(256) affine_grad_kernel(const T* __restrict__ 
             for (int k = 0; k < 8; ++k) { g += sg[k][j]; b += sb[k][j]; }
             atomicAdd(dgamma + cc, g / sqrtf(var[cc] + eps));
             if (dbeta) atomicAdd(dbeta + cc, b);
-        }
-    }
-}
-
-// fused backward of one eval-BatchNorm(+ReLU) node: the parameter gradients AND the data gradient from ONE pass over dy
-//   dgamma[c] += sum_r dy[r,c]*(x[r,c0+c]-mean[c])/sqrt(var[c]+eps) ; dbeta[c] += sum_r dy[r,c] ; dx[r,c0+c] (+)= dy[r,c]*gamma[c]/sqrt(..)
-// same thread mapping as affine_grad_kernel (x and dx are the same slice of the activation / delta buffers)
-template <typename T>
-__global__ void __launch_bounds__(256) affine_bwd_grad_kernel(const T* __restrict__ dy, int dy_pitch, const T* __restrict__ x,
-                                                              T* __restrict__ dx, int x_pitch, int x_c0, long long rows, int C,
-                                                              const float* __restrict__ gamma, const float* __restrict__ mean,
-                                                              const float* __restrict__ var, float eps, float* __restrict__ dgamma,
-                                                              float* __restrict__ dbeta, int accumulate, long long rows_per_block) {
-    __shared__ float sg[8][129], sb[8][129];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int c = (blockIdx.x * 32 + lane) * 4;
-    const long long r0 = (long long)blockIdx.y * rows_per_block;
-    const long long r1 = min(rows, r0 + rows_per_block);
-    float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
-    if (c < C) {
-        const float4 mu = ld4f(mean + c), g = ld4f(gamma + c), vr = ld4f(var + c);
-        const float4 s = make_float4(bn_scale(g.x, vr.x, eps), bn_scale(g.y, vr.y, eps), bn_scale(g.z, vr.z, eps), bn_scale(g.w, vr.w, eps));
-        for (long long r = r0 + w; r < r1; r += 8) {
-            const float4 d = ld4(dy + r * dy_pitch + c), xv = ld4(x + r * x_pitch + x_c0 + c);
-            ag.x = fmaf(d.x, xv.x - mu.x, ag.x); ag.y = fmaf(d.y, xv.y - mu.y, ag.y);
-            ag.z = fmaf(d.z, xv.z - mu.z, ag.z); ag.w = fmaf(d.w, xv.w - mu.w, ag.w);
-            ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
-            T* xp = dx + r * x_pitch + x_c0 + c;
-            float4 o = make_float4(d.x * s.x, d.y * s.y, d.z * s.z, d.w * s.w);
-            if (accumulate) { const float4 p = ld4(xp); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
-            st4(xp, o);
-        }
-    }
-    sg[w][lane * 4] = ag.x; sg[w][lane * 4 + 1] = ag.y; sg[w][lane * 4 + 2] = ag.z; sg[w][lane * 4 + 3] = ag.w;
-    sb[w][lane * 4] = ab.x; sb[w][lane * 4 + 1] = ab.y; sb[w][lane * 4 + 2] = ab.z; sb[w][lane * 4 + 3] = ab.w;
-    __syncthreads();
-    if (threadIdx.x < 128) {
-        const int cc = blockIdx.x * 128 + threadIdx.x;
-        if (cc < C) {
-            float gsum = 0.f, bsum = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { gsum += sg[k][threadIdx.x]; bsum += sb[k][threadIdx.x]; }
-            atomicAdd(dgamma + cc, gsum / sqrtf(var[cc] + eps));
-            atomicAdd(dbeta + cc, bsum);
         }
     }
 }
@@ -540,152 +503,364 @@ __global__ void __launch_bounds__(256) crowd_map_grad_kernel(const T* __restrict
 }
 
 // ---- 2-D mapped vector versions of the streaming kernels: a thread owns ONE group of W = 4 or 8 channels (its BatchNorm
-// scale / shift are computed once) and walks down the rows; a warp covers 32 consecutive channel groups of a row (512
-// contiguous bytes in bf16 with W = 8: one 16-byte access per thread).  grid.x = channel-group tiles, grid.y = row tiles.
-// When a row has fewer than 32 groups the spare lanes take further rows: thread t -> (group t & (cvp-1), row t >> lg).
-constexpr int EW_RI = 8;                      // row sweeps per block
-struct Ew2d { int lg; };                      // log2(cvp), cvp = min(32, next power of two >= C/W)
+// scale / shift are loaded with vector loads and computed once, branch-free) and walks down the rows of its block's row
+// range; a warp covers 32 consecutive channel groups of a row (512 contiguous bytes in bf16 with W = 8: one 16-byte access
+// per thread).  grid.x = channel-group tiles, grid.y = row ranges sized so that the grid is ~EW_WAVES waves of resident
+// blocks.  When a row has fewer than 32 groups the spare lanes take further rows: thread t -> (group t & (cvp-1), row
+// t >> lg).  Every row loop is batched: the loads of EW_U rows are issued back to back before the first use, so a thread
+// keeps EW_U x 16 bytes (x the number of input streams) in flight instead of one dependent load -> use -> store chain
+// per row (the first version reached 2.4 TB/s = 0.37 of the measured HBM peak; ncu: profiles/r1_ncu_crowd_streaming.txt).
+constexpr int EW_U = 4;                       // rows in flight per thread
+constexpr int EW_WAVES = 2;
+struct Ew2d { int lg; long long rpb; };       // log2(cvp), cvp = min(32, next power of two >= C/W); rows per block
 template <int W>
-__device__ __forceinline__ void ew2d_map(const Ew2d e, int& c, long long& r0, int& rstep) {
+__device__ __forceinline__ void ew2d_map(const Ew2d e, long long rows, int& c, long long& r0, long long& r1, int& rstep) {
     const int t = threadIdx.x;
     c = (blockIdx.x * 32 + (t & ((1 << e.lg) - 1))) * W;
     rstep = 256 >> e.lg;
-    r0 = (long long)blockIdx.y * (rstep * EW_RI) + (t >> e.lg);
+    r0 = (long long)blockIdx.y * e.rpb + (t >> e.lg);
+    r1 = min(rows, (long long)(blockIdx.y + 1) * e.rpb);
 }
-// W consecutive elements <-> W floats (16-byte accesses for 8 x bf16 and 4 x fp32)
-template <int W> __device__ __forceinline__ void ldw(const float* p, float (&v)[W]) {
-#pragma unroll
-    for (int q = 0; q < W / 4; ++q) { const float4 a = *reinterpret_cast<const float4*>(p + 4 * q); v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w; }
+// W consecutive elements kept packed while in flight (16 bytes for 8 x bf16 and 4 x fp32)
+template <typename T, int W> struct Raw;
+template <> struct Raw<bf16, 8> { uint4 d; };
+template <> struct Raw<bf16, 4> { uint2 d; };
+template <> struct Raw<float, 4> { float4 d; };
+template <> struct Raw<float, 8> { float4 d[2]; };
+__device__ __forceinline__ Raw<bf16, 8> ld_raw8(const bf16* p) { Raw<bf16, 8> r; r.d = *reinterpret_cast<const uint4*>(p); return r; }
+__device__ __forceinline__ Raw<bf16, 4> ld_raw4(const bf16* p) { Raw<bf16, 4> r; r.d = *reinterpret_cast<const uint2*>(p); return r; }
+__device__ __forceinline__ Raw<float, 4> ld_raw4(const float* p) { Raw<float, 4> r; r.d = *reinterpret_cast<const float4*>(p); return r; }
+__device__ __forceinline__ Raw<float, 8> ld_raw8(const float* p) {
+    Raw<float, 8> r; r.d[0] = *reinterpret_cast<const float4*>(p); r.d[1] = *reinterpret_cast<const float4*>(p + 4); return r;
 }
-template <int W> __device__ __forceinline__ void ldw(const bf16* p, float (&v)[W]) {
-    if (W == 8) {
-        const uint4 r = *reinterpret_cast<const uint4*>(p);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+template <typename T, int W> __device__ __forceinline__ Raw<T, W> ld_raw(const T* p) {
+    if constexpr (W == 8) return ld_raw8(p); else return ld_raw4(p);
+}
+__device__ __forceinline__ void unpack(const Raw<bf16, 8>& r, float (&v)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.d);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h[q]); v[2 * q] = f.x; v[(2 * q + 1) % W] = f.y; }
-    } else {
-        const float4 a = ld4(p);
-        v[0] = a.x; v[1 % W] = a.y; v[2 % W] = a.z; v[3 % W] = a.w;
-    }
+    for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
+}
+__device__ __forceinline__ void unpack(const Raw<bf16, 4>& r, float (&v)[4]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.d);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) { const float2 f = __bfloat1622float2(h[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
+}
+__device__ __forceinline__ void unpack(const Raw<float, 4>& r, float (&v)[4]) { v[0] = r.d.x; v[1] = r.d.y; v[2] = r.d.z; v[3] = r.d.w; }
+__device__ __forceinline__ void unpack(const Raw<float, 8>& r, float (&v)[8]) {
+    v[0] = r.d[0].x; v[1] = r.d[0].y; v[2] = r.d[0].z; v[3] = r.d[0].w; v[4] = r.d[1].x; v[5] = r.d[1].y; v[6] = r.d[1].z; v[7] = r.d[1].w;
 }
 template <int W> __device__ __forceinline__ void stw(float* p, const float (&v)[W]) {
 #pragma unroll
     for (int q = 0; q < W / 4; ++q) *reinterpret_cast<float4*>(p + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 template <int W> __device__ __forceinline__ void stw(bf16* p, const float (&v)[W]) {
-    if (W == 8) {
+    if constexpr (W == 8) {
         uint4 r;
         __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(v[2 * q], v[(2 * q + 1) % W]);
+        for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
         *reinterpret_cast<uint4*>(p) = r;
     } else {
-        st4(p, make_float4(v[0], v[1 % W], v[2 % W], v[3 % W]));
+        st4(p, make_float4(v[0], v[1], v[2], v[3]));
+    }
+}
+// W per-channel parameters starting at channel c (a multiple of W): float4 loads when the table is 16-byte aligned
+template <int W> __device__ __forceinline__ void ldp(const float* __restrict__ p, int c, float (&v)[W]) {
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+        for (int q = 0; q < W / 4; ++q) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p + c) + q);
+            v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < W; ++q) v[q] = __ldg(p + c + q);
     }
 }
 
-template <typename T, int W>
-__global__ void __launch_bounds__(256) affine2d_kernel(const T* __restrict__ x, int x_pitch, int x_c0, T* __restrict__ y, int y_pitch,
-                                                       long long rows, int C, const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, const float* __restrict__ mean,
-                                                       const float* __restrict__ var, float eps, const T* __restrict__ href,
-                                                       int mode, int act, float slope, Ew2d e) {
-    int c, rstep; long long r0;
-    ew2d_map<W>(e, c, r0, rstep);
+// Software-pipelined row loop of the streaming kernels: the loads of batch k+1 (U rows per thread) are issued before batch
+// k is processed, so every thread keeps U..2U rows in flight all the time (two register batches, ping-pong).
+template <typename Batch, int U, typename LoadF, typename ProcF, typename TailF>
+__device__ __forceinline__ void ew_rows(long long r, const long long r1, const int rstep, LoadF load, ProcF proc, TailF tail) {
+    const long long span = (long long)U * rstep;
+    Batch a, b;
+    bool have = r + span - rstep < r1;
+    if (have) load(a, r);
+    while (have) {
+        long long rn = r + span;
+        bool have_n = rn + span - rstep < r1;
+        if (have_n) load(b, rn);
+        proc(a, r);
+        r = rn; have = have_n;
+        if (!have) break;
+        rn = r + span; have_n = rn + span - rstep < r1;
+        if (have_n) load(a, rn);
+        proc(b, r);
+        r = rn; have = have_n;
+    }
+    for (; r < r1; r += rstep) tail(r);
+}
+template <typename T, int W, int U> struct Batch1 { Raw<T, W> a[U]; };
+template <typename T, int W, int U> struct Batch2 { Raw<T, W> a[U], b[U]; };
+template <typename T, int W, int U> struct Batch3 { Raw<T, W> a[U], b[U], c[U]; };
+
+// MODE 0: y = act(gamma*(x-mean)/sqrt(var+eps)+beta); MODE 1 (tangent): y = gamma/sqrt(var+eps) * x * act'(href)
+template <typename T, int W, int MODE>
+__global__ void __launch_bounds__(256, 2) affine2d_kernel(const T* __restrict__ x, int x_pitch, int x_c0, T* __restrict__ y, int y_pitch,
+                                                          long long rows, int C, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, const float* __restrict__ mean,
+                                                          const float* __restrict__ var, float eps, const T* __restrict__ href,
+                                                          int act, float slope, Ew2d e) {
+    int c, rstep; long long r0, r1;
+    ew2d_map<W>(e, rows, c, r0, r1, rstep);
     if (c >= C) return;
     float s[W], m[W], b[W];
+    ldp<W>(gamma, c, s);
+    ldp<W>(var, c, m);
 #pragma unroll
-    for (int q = 0; q < W; ++q) {
-        s[q] = bn_scale(gamma[c + q], var[c + q], eps);
-        m[q] = mode == 0 ? mean[c + q] : 0.f;
-        b[q] = mode == 0 ? beta[c + q] : 0.f;
-    }
-#pragma unroll 4
-    for (int j = 0; j < EW_RI; ++j) {
-        const long long r = r0 + (long long)j * rstep;
-        if (r >= rows) break;
+    for (int q = 0; q < W; ++q) s[q] = bn_scale(s[q], m[q], eps);
+    if (MODE == 0) { ldp<W>(mean, c, m); ldp<W>(beta, c, b); }
+    const T* xp = x + x_c0 + c;
+    const T* hp = href + c;
+    T* yp = y + c;
+    auto one = [&](const Raw<T, W>& xr, const Raw<T, W>& hr, long long r) {
         float xv[W], o[W];
-        ldw<W>(x + r * x_pitch + x_c0 + c, xv);
-        if (mode == 0) {
+        unpack(xr, xv);
+        if (MODE == 0) {
 #pragma unroll
             for (int q = 0; q < W; ++q) o[q] = act_fwd((xv[q] - m[q]) * s[q] + b[q], act, slope);
         } else {
             float h[W];
-            ldw<W>(href + r * y_pitch + c, h);
+            unpack(hr, h);
 #pragma unroll
             for (int q = 0; q < W; ++q) o[q] = xv[q] * s[q] * act_bwd(h[q], act, slope);
         }
-        stw<W>(y + r * y_pitch + c, o);
-    }
+        stw<W>(yp + r * y_pitch, o);
+    };
+    typedef Batch2<T, W, EW_U> B;
+    ew_rows<B, EW_U>(r0, r1, rstep,
+        [&](B& t, long long r) {
+#pragma unroll
+            for (int u = 0; u < EW_U; ++u) t.a[u] = ld_raw<T, W>(xp + (r + (long long)u * rstep) * x_pitch);
+            if (MODE == 1) {
+#pragma unroll
+                for (int u = 0; u < EW_U; ++u) t.b[u] = ld_raw<T, W>(hp + (r + (long long)u * rstep) * y_pitch);
+            }
+        },
+        [&](const B& t, long long r) {
+#pragma unroll
+            for (int u = 0; u < EW_U; ++u) one(t.a[u], MODE == 1 ? t.b[u] : t.a[u], r + (long long)u * rstep);
+        },
+        [&](long long r) {
+            Raw<T, W> xr = ld_raw<T, W>(xp + r * x_pitch), hr = xr;
+            if (MODE == 1) hr = ld_raw<T, W>(hp + r * y_pitch);
+            one(xr, hr, r);
+        });
 }
 
-template <typename T, int W>
-__global__ void __launch_bounds__(256) affine_bwd2d_kernel(const T* __restrict__ dy, int dy_pitch, T* __restrict__ dx, int dx_pitch,
-                                                           int dx_c0, long long rows, int C, const float* __restrict__ gamma,
-                                                           const float* __restrict__ var, float eps, int accumulate, Ew2d e) {
-    int c, rstep; long long r0;
-    ew2d_map<W>(e, c, r0, rstep);
+// dx[:, c0:c0+C] (+)= dy * gamma/sqrt(var+eps)
+template <typename T, int W, bool ACC>
+__global__ void __launch_bounds__(256, 2) affine_bwd2d_kernel(const T* __restrict__ dy, int dy_pitch, T* __restrict__ dx, int dx_pitch,
+                                                              int dx_c0, long long rows, int C, const float* __restrict__ gamma,
+                                                              const float* __restrict__ var, float eps, Ew2d e) {
+    int c, rstep; long long r0, r1;
+    ew2d_map<W>(e, rows, c, r0, r1, rstep);
     if (c >= C) return;
-    float s[W];
+    float s[W], vr[W];
+    ldp<W>(gamma, c, s);
+    ldp<W>(var, c, vr);
 #pragma unroll
-    for (int q = 0; q < W; ++q) s[q] = bn_scale(gamma[c + q], var[c + q], eps);
-#pragma unroll 4
-    for (int j = 0; j < EW_RI; ++j) {
-        const long long r = r0 + (long long)j * rstep;
-        if (r >= rows) break;
+    for (int q = 0; q < W; ++q) s[q] = bn_scale(s[q], vr[q], eps);
+    const T* dp = dy + c;
+    T* xp = dx + dx_c0 + c;
+    auto one = [&](const Raw<T, W>& dr, const Raw<T, W>& pr, long long r) {
         float d[W], o[W];
-        ldw<W>(dy + r * dy_pitch + c, d);
-        T* xp = dx + r * dx_pitch + dx_c0 + c;
+        unpack(dr, d);
 #pragma unroll
         for (int q = 0; q < W; ++q) o[q] = d[q] * s[q];
-        if (accumulate) {
+        if (ACC) {
             float pv[W];
-            ldw<W>(xp, pv);
+            unpack(pr, pv);
 #pragma unroll
             for (int q = 0; q < W; ++q) o[q] += pv[q];
         }
-        stw<W>(xp, o);
-    }
+        stw<W>(xp + r * dx_pitch, o);
+    };
+    typedef Batch2<T, W, EW_U> B;
+    ew_rows<B, EW_U>(r0, r1, rstep,
+        [&](B& t, long long r) {
+#pragma unroll
+            for (int u = 0; u < EW_U; ++u) t.a[u] = ld_raw<T, W>(dp + (r + (long long)u * rstep) * dy_pitch);
+            if (ACC) {
+#pragma unroll
+                for (int u = 0; u < EW_U; ++u) t.b[u] = ld_raw<T, W>(xp + (r + (long long)u * rstep) * dx_pitch);
+            }
+        },
+        [&](const B& t, long long r) {
+#pragma unroll
+            for (int u = 0; u < EW_U; ++u) one(t.a[u], ACC ? t.b[u] : t.a[u], r + (long long)u * rstep);
+        },
+        [&](long long r) {
+            Raw<T, W> dr = ld_raw<T, W>(dp + r * dy_pitch), pr = dr;
+            if (ACC) pr = ld_raw<T, W>(xp + r * dx_pitch);
+            one(dr, pr, r);
+        });
 }
 
-template <typename T, int W>
-__global__ void __launch_bounds__(256) copy2d2d_kernel(const T* __restrict__ src, int src_pitch, int src_c0, T* __restrict__ dst,
-                                                       int dst_pitch, int dst_c0, long long rows, int C, int accumulate, Ew2d e) {
-    int c, rstep; long long r0;
-    ew2d_map<W>(e, c, r0, rstep);
+template <typename T, int W, bool ACC>
+__global__ void __launch_bounds__(256, 2) copy2d2d_kernel(const T* __restrict__ src, int src_pitch, int src_c0, T* __restrict__ dst,
+                                                          int dst_pitch, int dst_c0, long long rows, int C, Ew2d e) {
+    int c, rstep; long long r0, r1;
+    ew2d_map<W>(e, rows, c, r0, r1, rstep);
     if (c >= C) return;
-#pragma unroll 4
-    for (int j = 0; j < EW_RI; ++j) {
-        const long long r = r0 + (long long)j * rstep;
-        if (r >= rows) break;
-        float v[W];
-        ldw<W>(src + r * src_pitch + src_c0 + c, v);
-        T* dp = dst + r * dst_pitch + dst_c0 + c;
-        if (accumulate) {
-            float pv[W];
-            ldw<W>(dp, pv);
+    const T* sp = src + src_c0 + c;
+    T* dp = dst + dst_c0 + c;
+    auto one = [&](const Raw<T, W>& sr, const Raw<T, W>& pr, long long r) {
+        if (ACC) {
+            float v[W], pv[W];
+            unpack(sr, v);
+            unpack(pr, pv);
 #pragma unroll
             for (int q = 0; q < W; ++q) v[q] += pv[q];
+            stw<W>(dp + r * dst_pitch, v);
+        } else {
+            *reinterpret_cast<Raw<T, W>*>(dp + r * dst_pitch) = sr;
         }
-        stw<W>(dp, v);
+    };
+    typedef Batch2<T, W, EW_U> B;
+    ew_rows<B, EW_U>(r0, r1, rstep,
+        [&](B& t, long long r) {
+#pragma unroll
+            for (int u = 0; u < EW_U; ++u) t.a[u] = ld_raw<T, W>(sp + (r + (long long)u * rstep) * src_pitch);
+            if (ACC) {
+#pragma unroll
+                for (int u = 0; u < EW_U; ++u) t.b[u] = ld_raw<T, W>(dp + (r + (long long)u * rstep) * dst_pitch);
+            }
+        },
+        [&](const B& t, long long r) {
+#pragma unroll
+            for (int u = 0; u < EW_U; ++u) one(t.a[u], ACC ? t.b[u] : t.a[u], r + (long long)u * rstep);
+        },
+        [&](long long r) {
+            Raw<T, W> sr = ld_raw<T, W>(sp + r * src_pitch), pr = sr;
+            if (ACC) pr = ld_raw<T, W>(dp + r * dst_pitch);
+            one(sr, pr, r);
+        });
+}
+
+// BatchNorm parameter gradients, optionally fused with the data gradient (DX), from ONE pass over dy:
+//   dgamma[c] += sum_r dy[r,c]*(x[r,c0+c]-mean[c]*sub)/sqrt(var[c]+eps) ; dbeta[c] += sum_r dy[r,c] ;
+//   DX: dx[r,c0+c] (+)= dy[r,c]*gamma[c]/sqrt(var[c]+eps)     (x and dx are the same slice of the activation / delta buffers)
+// Same thread mapping as the kernels above; the row lanes of a block are combined in shared memory, one atomicAdd per
+// channel and block.
+template <typename T, int W, bool DX>
+__global__ void __launch_bounds__(256, 2) affine_grad2d_kernel(const T* __restrict__ dy, int dy_pitch, const T* __restrict__ x,
+                                                               T* __restrict__ dx, int x_pitch, int x_c0, long long rows, int C,
+                                                               const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                               const float* __restrict__ var, float eps, float* __restrict__ dgamma,
+                                                               float* __restrict__ dbeta, int subtract_mean, int accumulate, Ew2d e) {
+    constexpr int U = 2;
+    __shared__ float sg[256 * W], sb[256 * W];
+    int c, rstep; long long r0, r1;
+    ew2d_map<W>(e, rows, c, r0, r1, rstep);
+    float ag[W], ab[W];
+#pragma unroll
+    for (int q = 0; q < W; ++q) { ag[q] = 0.f; ab[q] = 0.f; }
+    if (c < C) {
+        float s[W], mu[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) { s[q] = 0.f; mu[q] = 0.f; }
+        if (subtract_mean) ldp<W>(mean, c, mu);
+        if (DX) {
+            float vr[W];
+            ldp<W>(gamma, c, s);
+            ldp<W>(var, c, vr);
+#pragma unroll
+            for (int q = 0; q < W; ++q) s[q] = bn_scale(s[q], vr[q], eps);
+        }
+        const T* dp = dy + c;
+        const T* xp = x + x_c0 + c;
+        T* gp = DX ? dx + x_c0 + c : nullptr;
+        auto one = [&](const Raw<T, W>& dr, const Raw<T, W>& xr, const Raw<T, W>& pr, long long r) {
+            float d[W], xv[W];
+            unpack(dr, d);
+            unpack(xr, xv);
+#pragma unroll
+            for (int q = 0; q < W; ++q) { ag[q] = fmaf(d[q], xv[q] - mu[q], ag[q]); ab[q] += d[q]; }
+            if (DX) {
+                float o[W];
+#pragma unroll
+                for (int q = 0; q < W; ++q) o[q] = d[q] * s[q];
+                if (accumulate) {
+                    float pv[W];
+                    unpack(pr, pv);
+#pragma unroll
+                    for (int q = 0; q < W; ++q) o[q] += pv[q];
+                }
+                stw<W>(gp + r * x_pitch, o);
+            }
+        };
+        typedef Batch3<T, W, U> B;
+        ew_rows<B, U>(r0, r1, rstep,
+            [&](B& t, long long r) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    t.a[u] = ld_raw<T, W>(dp + (r + (long long)u * rstep) * dy_pitch);
+                    t.b[u] = ld_raw<T, W>(xp + (r + (long long)u * rstep) * x_pitch);
+                }
+                if (DX && accumulate) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) t.c[u] = ld_raw<T, W>(gp + (r + (long long)u * rstep) * x_pitch);
+                }
+            },
+            [&](const B& t, long long r) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) one(t.a[u], t.b[u], t.c[u], r + (long long)u * rstep);     // t.c is read only when accumulating
+            },
+            [&](long long r) {
+                Raw<T, W> dr = ld_raw<T, W>(dp + r * dy_pitch), xr = ld_raw<T, W>(xp + r * x_pitch), pr = dr;
+                if (DX && accumulate) pr = ld_raw<T, W>(gp + r * x_pitch);
+                one(dr, xr, pr, r);
+            });
+    }
+    // combine the row lanes: thread t holds columns (t & (cvp-1))*W.. of row lane t >> lg
+    const int cvp = 1 << e.lg, ncol = cvp * W, nrl = 256 >> e.lg;
+    {
+        const int base = (threadIdx.x >> e.lg) * ncol + (threadIdx.x & (cvp - 1)) * W;
+#pragma unroll
+        for (int q = 0; q < W; ++q) { sg[base + q] = ag[q]; sb[base + q] = ab[q]; }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < ncol; j += 256) {
+        const int cc = blockIdx.x * 32 * W + j;
+        if (cc < C) {
+            float g = 0.f, b = 0.f;
+            for (int k = 0; k < nrl; ++k) { g += sg[k * ncol + j]; b += sb[k * ncol + j]; }
+            atomicAdd(dgamma + cc, g / sqrtf(var[cc] + eps));
+            if (dbeta) atomicAdd(dbeta + cc, b);
+        }
     }
 }
 
-inline Ew2d ew2d_map_for(int C, int W) {
+inline Ew2d ew2d_plan(long long rows, int C, int W, dim3& grid, int unroll = EW_U, int blocks_per_sm = 2) {
     int lg = 0;
     while (lg < 5 && (1 << lg) < C / W) ++lg;
-    return Ew2d{lg};
+    const int rstep = 256 >> lg;
+    const int gx = (C / W + 31) / 32;
+    const long long unit = (long long)rstep * unroll;              // one batch of rows per row lane
+    long long want = (long long)kNumSMs * blocks_per_sm * EW_WAVES / gx;
+    if (want < 1) want = 1;
+    long long rpb = (rows + want - 1) / want;
+    rpb = (rpb + unit - 1) / unit * unit;
+    if (rpb < 2 * unit) rpb = 2 * unit;
+    grid = dim3((unsigned)gx, (unsigned)((rows + rpb - 1) / rpb));
+    return Ew2d{lg, rpb};
 }
-inline dim3 ew2d_grid(long long rows, int C, int W) {
-    const long long rpb = (long long)(256 >> ew2d_map_for(C, W).lg) * EW_RI;
-    return dim3((unsigned)((C / W + 31) / 32), (unsigned)((rows + rpb - 1) / rpb));
+// 8 elements per thread need 16-byte alignment in bf16: everything a multiple of 8 (fp32 keeps 4 = 16 bytes per access)
+inline bool vec8_ok(int dtype, int C, int p0, int o0, int p1 = 0, int o1 = 0) {
+    return dtype == SRGAN_BF16 && ((C | p0 | o0 | p1 | o1) & 7) == 0;
 }
-inline bool ew2d_ok(long long rows, int C, int W) {
-    const long long rpb = (long long)(256 >> ew2d_map_for(C, W).lg) * EW_RI;
-    return (rows + rpb - 1) / rpb <= 65535;
-}
-// 8 elements per thread need 16-byte alignment in bf16 (and 32-byte runs in fp32): everything a multiple of 8
-inline bool vec8_ok(int C, int p0, int o0, int p1 = 0, int o1 = 0) { return ((C | p0 | o0 | p1 | o1) & 7) == 0; }
 
 // depth-to-space of a one-channel map: img[n, i*k+r, j*k+s] <-> blk[n, i, j, r*k+s]   (one thread per image pixel)
 template <typename T>
@@ -726,11 +901,18 @@ int srgan_affine(const void* x, int x_pitch, int x_c0, void* y, int y_pitch, lon
     if (rows == 0) return SRGAN_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = vec_ok(C, x_pitch, x_c0, y_pitch);
+    dim3 grid;
+#define AFFINE2D(W_)                                                                                                       \
+    do {                                                                                                                   \
+        const Ew2d e = ew2d_plan(rows, C, W_, grid);                                                                       \
+        if (mode == 0) affine2d_kernel<T, W_, 0><<<grid, 256, 0, st>>>((const T*)x, x_pitch, x_c0, (T*)y, y_pitch, rows, C, gamma, beta, mean, var, eps, (const T*)href, act, slope, e); \
+        else affine2d_kernel<T, W_, 1><<<grid, 256, 0, st>>>((const T*)x, x_pitch, x_c0, (T*)y, y_pitch, rows, C, gamma, beta, mean, var, eps, (const T*)href, act, slope, e); \
+    } while (0)
     DISPATCH_T(dtype,
-               if (vec8_ok(C, x_pitch, x_c0, y_pitch) && ew2d_ok(rows, C, 8)) affine2d_kernel<T, 8><<<ew2d_grid(rows, C, 8), 256, 0, st>>>((const T*)x, x_pitch, x_c0, (T*)y, y_pitch, rows, C, gamma, beta, mean, var, eps, (const T*)href, mode, act, slope, ew2d_map_for(C, 8));
-               else if (vec && ew2d_ok(rows, C, 4)) affine2d_kernel<T, 4><<<ew2d_grid(rows, C, 4), 256, 0, st>>>((const T*)x, x_pitch, x_c0, (T*)y, y_pitch, rows, C, gamma, beta, mean, var, eps, (const T*)href, mode, act, slope, ew2d_map_for(C, 4));
-               else if (vec) affine_kernel<T, true><<<ew_grid(rows * C / 4), 256, 0, st>>>((const T*)x, x_pitch, x_c0, (T*)y, y_pitch, rows, C, gamma, beta, mean, var, eps, (const T*)href, mode, act, slope);
+               if (vec8_ok(dtype, C, x_pitch, x_c0, y_pitch)) AFFINE2D(8);
+               else if (vec) AFFINE2D(4);
                else affine_kernel<T, false><<<ew_grid(rows * C), 256, 0, st>>>((const T*)x, x_pitch, x_c0, (T*)y, y_pitch, rows, C, gamma, beta, mean, var, eps, (const T*)href, mode, act, slope));
+#undef AFFINE2D
     SRGAN_CHECK_LAUNCH("affine_kernel");
     return SRGAN_OK;
 }
@@ -742,11 +924,18 @@ int srgan_affine_bwd(const void* dy, int dy_pitch, void* dx, int dx_pitch, int d
     if (rows == 0) return SRGAN_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = vec_ok(C, dx_pitch, dx_c0, dy_pitch);
+    dim3 grid;
+#define AFFINE_BWD2D(W_)                                                                                                   \
+    do {                                                                                                                   \
+        const Ew2d e = ew2d_plan(rows, C, W_, grid);                                                                       \
+        if (accumulate) affine_bwd2d_kernel<T, W_, true><<<grid, 256, 0, st>>>((const T*)dy, dy_pitch, (T*)dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, e); \
+        else affine_bwd2d_kernel<T, W_, false><<<grid, 256, 0, st>>>((const T*)dy, dy_pitch, (T*)dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, e); \
+    } while (0)
     DISPATCH_T(dtype,
-               if (vec8_ok(C, dx_pitch, dx_c0, dy_pitch) && ew2d_ok(rows, C, 8)) affine_bwd2d_kernel<T, 8><<<ew2d_grid(rows, C, 8), 256, 0, st>>>((const T*)dy, dy_pitch, (T*)dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, accumulate, ew2d_map_for(C, 8));
-               else if (vec && ew2d_ok(rows, C, 4)) affine_bwd2d_kernel<T, 4><<<ew2d_grid(rows, C, 4), 256, 0, st>>>((const T*)dy, dy_pitch, (T*)dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, accumulate, ew2d_map_for(C, 4));
-               else if (vec) affine_bwd_kernel<T, true><<<ew_grid(rows * C / 4), 256, 0, st>>>((const T*)dy, dy_pitch, (T*)dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, accumulate);
+               if (vec8_ok(dtype, C, dx_pitch, dx_c0, dy_pitch)) AFFINE_BWD2D(8);
+               else if (vec) AFFINE_BWD2D(4);
                else affine_bwd_kernel<T, false><<<ew_grid(rows * C), 256, 0, st>>>((const T*)dy, dy_pitch, (T*)dx, dx_pitch, dx_c0, rows, C, gamma, var, eps, accumulate));
+#undef AFFINE_BWD2D
     SRGAN_CHECK_LAUNCH("affine_bwd_kernel");
     return SRGAN_OK;
 }
@@ -758,16 +947,19 @@ int srgan_affine_grad(const void* dy, int dy_pitch, const void* x, int x_pitch, 
     if (rows == 0) return SRGAN_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = vec_ok(C, x_pitch, x_c0, dy_pitch);
-    const int V = vec ? 4 : 1;
-    const int gx = (C + 32 * V - 1) / (32 * V);
-    long long want = (4LL * kNumSMs + gx - 1) / gx;                 // ~4 CTAs per SM in total
-    long long rpb = (rows + want - 1) / want;
-    if (rpb < 64) rpb = 64;
-    const long long gy = (rows + rpb - 1) / rpb;
-    dim3 grid(gx, (unsigned)gy);
-    DISPATCH_T(dtype,
-               if (vec) affine_grad_kernel<T, true><<<grid, 256, 0, st>>>((const T*)dy, dy_pitch, (const T*)x, x_pitch, x_c0, rows, C, mean, var, eps, dgamma, dbeta, subtract_mean, rpb);
-               else affine_grad_kernel<T, false><<<grid, 256, 0, st>>>((const T*)dy, dy_pitch, (const T*)x, x_pitch, x_c0, rows, C, mean, var, eps, dgamma, dbeta, subtract_mean, rpb));
+    dim3 grid;
+    if (vec) {
+        DISPATCH_T(dtype,
+                   if (vec8_ok(dtype, C, x_pitch, x_c0, dy_pitch)) { const Ew2d e = ew2d_plan(rows, C, 8, grid, 2); affine_grad2d_kernel<T, 8, false><<<grid, 256, 0, st>>>((const T*)dy, dy_pitch, (const T*)x, nullptr, x_pitch, x_c0, rows, C, nullptr, mean, var, eps, dgamma, dbeta, subtract_mean, 0, e); }
+                   else { const Ew2d e = ew2d_plan(rows, C, 4, grid, 2); affine_grad2d_kernel<T, 4, false><<<grid, 256, 0, st>>>((const T*)dy, dy_pitch, (const T*)x, nullptr, x_pitch, x_c0, rows, C, nullptr, mean, var, eps, dgamma, dbeta, subtract_mean, 0, e); });
+    } else {
+        const int gx = (C + 31) / 32;
+        long long want = (4LL * kNumSMs + gx - 1) / gx;                 // ~4 CTAs per SM in total
+        long long rpb = (rows + want - 1) / want;
+        if (rpb < 64) rpb = 64;
+        grid = dim3(gx, (unsigned)((rows + rpb - 1) / rpb));
+        DISPATCH_T(dtype, affine_grad_kernel<T, false><<<grid, 256, 0, st>>>((const T*)dy, dy_pitch, (const T*)x, x_pitch, x_c0, rows, C, mean, var, eps, dgamma, dbeta, subtract_mean, rpb));
+    }
     SRGAN_CHECK_LAUNCH("affine_grad_kernel");
     return SRGAN_OK;
 }
@@ -784,12 +976,10 @@ int srgan_affine_bwd_grad(const void* dy, int dy_pitch, const void* x, void* dx,
         return srgan_affine_bwd(dy, dy_pitch, dx, x_pitch, x_c0, rows, C, gamma, var, eps, accumulate, dtype, stream);
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const int gx = (C + 127) / 128;
-    long long want = (8LL * kNumSMs + gx - 1) / gx;
-    long long rpb = (rows + want - 1) / want;
-    if (rpb < 64) rpb = 64;
-    dim3 grid(gx, (unsigned)((rows + rpb - 1) / rpb));
-    DISPATCH_T(dtype, affine_bwd_grad_kernel<T><<<grid, 256, 0, st>>>((const T*)dy, dy_pitch, (const T*)x, (T*)dx, x_pitch, x_c0, rows, C, gamma, mean, var, eps, dgamma, dbeta, accumulate, rpb));
+    dim3 grid;
+    DISPATCH_T(dtype,
+               if (vec8_ok(dtype, C, x_pitch, x_c0, dy_pitch)) { const Ew2d e = ew2d_plan(rows, C, 8, grid, 2); affine_grad2d_kernel<T, 8, true><<<grid, 256, 0, st>>>((const T*)dy, dy_pitch, (const T*)x, (T*)dx, x_pitch, x_c0, rows, C, gamma, mean, var, eps, dgamma, dbeta, 1, accumulate, e); }
+               else { const Ew2d e = ew2d_plan(rows, C, 4, grid, 2); affine_grad2d_kernel<T, 4, true><<<grid, 256, 0, st>>>((const T*)dy, dy_pitch, (const T*)x, (T*)dx, x_pitch, x_c0, rows, C, gamma, mean, var, eps, dgamma, dbeta, 1, accumulate, e); });
     SRGAN_CHECK_LAUNCH("affine_bwd_grad_kernel");
     return SRGAN_OK;
 }
@@ -801,11 +991,18 @@ int srgan_copy2d(const void* src, int src_pitch, int src_c0, void* dst, int dst_
     if (rows == 0) return SRGAN_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = vec_ok(C, src_pitch, src_c0, dst_pitch, dst_c0);
+    dim3 grid;
+#define COPY2D2D(W_)                                                                                                       \
+    do {                                                                                                                   \
+        const Ew2d e = ew2d_plan(rows, C, W_, grid);                                                                       \
+        if (accumulate) copy2d2d_kernel<T, W_, true><<<grid, 256, 0, st>>>((const T*)src, src_pitch, src_c0, (T*)dst, dst_pitch, dst_c0, rows, C, e); \
+        else copy2d2d_kernel<T, W_, false><<<grid, 256, 0, st>>>((const T*)src, src_pitch, src_c0, (T*)dst, dst_pitch, dst_c0, rows, C, e); \
+    } while (0)
     DISPATCH_T(dtype,
-               if (vec8_ok(C, src_pitch, src_c0, dst_pitch, dst_c0) && ew2d_ok(rows, C, 8)) copy2d2d_kernel<T, 8><<<ew2d_grid(rows, C, 8), 256, 0, st>>>((const T*)src, src_pitch, src_c0, (T*)dst, dst_pitch, dst_c0, rows, C, accumulate, ew2d_map_for(C, 8));
-               else if (vec && ew2d_ok(rows, C, 4)) copy2d2d_kernel<T, 4><<<ew2d_grid(rows, C, 4), 256, 0, st>>>((const T*)src, src_pitch, src_c0, (T*)dst, dst_pitch, dst_c0, rows, C, accumulate, ew2d_map_for(C, 4));
-               else if (vec) copy2d_kernel<T, true><<<ew_grid(rows * C / 4), 256, 0, st>>>((const T*)src, src_pitch, src_c0, (T*)dst, dst_pitch, dst_c0, rows, C, accumulate);
+               if (vec8_ok(dtype, C, src_pitch, src_c0, dst_pitch, dst_c0)) COPY2D2D(8);
+               else if (vec) COPY2D2D(4);
                else copy2d_kernel<T, false><<<ew_grid(rows * C), 256, 0, st>>>((const T*)src, src_pitch, src_c0, (T*)dst, dst_pitch, dst_c0, rows, C, accumulate));
+#undef COPY2D2D
     SRGAN_CHECK_LAUNCH("copy2d_kernel");
     return SRGAN_OK;
 }

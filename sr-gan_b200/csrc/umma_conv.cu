@@ -160,8 +160,9 @@ struct UmmaConvParams {
 };
 
 // Epilogue math on one 32-column chunk of one accumulator row (all branches are warp-uniform and hoisted out of the
-// element loops; bias is read as float4 runs, href as four 16-byte loads), then 64 bytes of bf16 are stored.
-__device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], const UmmaConvParams& p, int cbase, long long oj) {
+// element loops; bias is read as float4 runs, href arrives as the row's four 16-byte pieces), packed to 64 bytes of bf16.
+__device__ __forceinline__ void epilogue_math(const uint32_t (&v)[32], const UmmaConvParams& p, int cbase, const uint4 (&hv)[4],
+                                              uint4 (&w)[4]) {
     float f[32];
 #pragma unroll
     for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
@@ -190,10 +191,6 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], const UmmaConv
             for (int e = 0; e < 32; ++e) f[e] = tanhf(f[e]);
         }
     } else if (p.href != nullptr && p.act != SRGAN_ACT_NONE) {
-        const uint4* hp = reinterpret_cast<const uint4*>(p.href + oj);
-        uint4 hv[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) hv[g] = __ldg(hp + g);
         const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(hv);
         if (p.act == SRGAN_ACT_LEAKY) {
             const float sl = p.slope;
@@ -212,18 +209,34 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], const UmmaConv
             }
         }
     }
-    uint4* op = reinterpret_cast<uint4*>(p.out + oj);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-        uint4 w;
         __nv_bfloat162 b0 = __floats2bfloat162_rn(f[g * 8 + 0], f[g * 8 + 1]);
         __nv_bfloat162 b1 = __floats2bfloat162_rn(f[g * 8 + 2], f[g * 8 + 3]);
         __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g * 8 + 4], f[g * 8 + 5]);
         __nv_bfloat162 b3 = __floats2bfloat162_rn(f[g * 8 + 6], f[g * 8 + 7]);
-        w.x = *reinterpret_cast<uint32_t*>(&b0); w.y = *reinterpret_cast<uint32_t*>(&b1);
-        w.z = *reinterpret_cast<uint32_t*>(&b2); w.w = *reinterpret_cast<uint32_t*>(&b3);
-        op[g] = w;
+        w[g].x = *reinterpret_cast<uint32_t*>(&b0); w[g].y = *reinterpret_cast<uint32_t*>(&b1);
+        w[g].z = *reinterpret_cast<uint32_t*>(&b2); w[g].w = *reinterpret_cast<uint32_t*>(&b3);
     }
+}
+
+// Per-warp transposition buffer of the epilogue: 32 rows x 64 bytes (one 32-column bf16 chunk of 32 accumulator rows).
+// A thread owns accumulator row `lane`, but a warp-wide 16-byte access with one ROW per lane touches 32 different
+// 128-byte lines (32 LSU wavefronts per instruction: the k1s1 data-gradient GEMMs were bound by exactly that).  Through
+// this buffer the global accesses are issued "transposed": lane l moves 16-byte unit (l & 3) of rows 8*it + (l >> 2),
+// so one instruction covers 8 rows x 64 contiguous bytes.  Units are XOR-swizzled by (row >> 1) & 3: both access
+// patterns are bank-conflict free.
+constexpr int EPI_STG_BYTES = 32 * 64;
+__device__ __forceinline__ uint32_t stg_addr(uint32_t base, int row, int unit) {
+    return base + (uint32_t)(row * 64 + ((unit ^ ((row >> 1) & 3)) << 4));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -374,37 +387,87 @@ __global__ void __launch_bounds__(PC_THREADS, 1) umma_conv_persistent_kernel(con
             }
         }
     } else {
-        // ================= epilogue (8 warps): TMEM -> registers -> bf16 NHWC =================
+        // ================= epilogue (8 warps): TMEM -> registers -> smem transposition -> bf16 NHWC =================
         const int ew = warp - 2;
         const int q = warp & 3;                  // TMEM lane quarter this warp may access
         const int half = ew >> 2;                // which half of the 32-column chunks
         const int row = q * 32 + lane;
         const int tw = row % p.TW, th = (row / p.TW) % p.TH, tn = row / (p.TW * p.TH);
+        const uint32_t stg = tiles + (uint32_t)stages * STAGE_BYTES + (uint32_t)ew * EPI_STG_BYTES;
+        const int t_unit = lane & 3, t_row = lane >> 2;       // transposed role: unit t_unit of rows 8*it + t_row
+        const bool use_href = p.epi != SRGAN_EPI_BIAS_ACT && p.href != nullptr && p.act != SRGAN_ACT_NONE;
+        constexpr int NCH = (BN / 32 + 1) / 2;   // chunks per sub-tile handled by this warp (BN = 64: one)
         int tl = 0;
         for (int tile = blockIdx.x; tile < pp.total_tiles; tile += gridDim.x, ++tl) {
             const Tile T = decode(tile);
             const int buf = tl & 1;
             const uint32_t bph = (tl >> 1) & 1;
             const int c0 = T.ny * BN;
-            mbar_wait(smem_u32(&tmem_full_bar[buf]), bph);
-            tc_fence_after();
-#pragma unroll 1
+            // element offsets of the rows this lane moves in the transposed accesses (-1: row beyond the last sample)
+            long long o_t[MT][4];
+#pragma unroll
             for (int i = 0; i < MT; ++i) {
                 const int ms = T.mt * MT + i;
                 const int tw_i = ms % p.tiles_w, th_i = (ms / p.tiles_w) % p.tiles_h, tn_i = ms / sub_per_n;
                 const int sample = tn_i * p.TN + tn;
                 const int oy = th_i * p.TH + th, ox = tw_i * p.TW + tw;
-                const bool valid = sample < p.n;
                 long long o;
                 if (p.mode == 0) o = (((long long)sample * p.Hm + oy) * p.Wm + ox) * p.Cout + c0;
                 else o = (((long long)sample * p.Hout + (oy * p.stride + T.pa)) * p.Wout + (ox * p.stride + T.pb)) * p.Cout + c0;
-#pragma unroll 1
-                for (int j = half; j < BN / 32; j += 2) {
+                if (sample >= p.n) o = -1;
+#pragma unroll
+                for (int it = 0; it < 4; ++it) o_t[i][it] = __shfl_sync(0xffffffffu, o, 8 * it + t_row);
+            }
+            // the tile's href pieces are requested before the accumulator is waited for: their latency hides behind the MMAs
+            uint4 hreg[MT][NCH][4];
+            if (use_href) {
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < NCH; ++jj) {
+                        const int j = half + 2 * jj;
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) {
+                            hreg[i][jj][it] = make_uint4(0u, 0u, 0u, 0u);
+                            if (j < BN / 32 && o_t[i][it] >= 0)
+                                hreg[i][jj][it] = __ldg(reinterpret_cast<const uint4*>(p.href + o_t[i][it] + j * 32 + t_unit * 8));
+                        }
+                    }
+            }
+            mbar_wait(smem_u32(&tmem_full_bar[buf]), bph);
+            tc_fence_after();
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+#pragma unroll
+                for (int jj = 0; jj < NCH; ++jj) {
+                    const int j = half + 2 * jj;
+                    if (j >= BN / 32) continue;               // warp-uniform
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + i * BN + j * 32, v);
+                    uint4 hv[4];
+                    if (use_href) {                           // transposed pieces -> this thread's own row
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) sts128(stg_addr(stg, 8 * it + t_row, t_unit), hreg[i][jj][it]);
+                        __syncwarp();
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) hv[k] = lds128(stg_addr(stg, lane, k));
+                        __syncwarp();
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) hv[k] = make_uint4(0u, 0u, 0u, 0u);
+                    }
                     tmem_ld_wait();
-                    if (!valid) continue;
-                    epilogue_chunk(v, p, c0 + j * 32, o + j * 32);
+                    uint4 w[4];
+                    epilogue_math(v, p, c0 + j * 32, hv, w);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) sts128(stg_addr(stg, lane, k), w[k]);
+                    __syncwarp();
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const uint4 x = lds128(stg_addr(stg, 8 * it + t_row, t_unit));
+                        if (o_t[i][it] >= 0) *reinterpret_cast<uint4*>(p.out + o_t[i][it] + j * 32 + t_unit * 8) = x;
+                    }
+                    __syncwarp();
                 }
             }
             tc_fence_before();
@@ -631,11 +694,11 @@ int launch_conv_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaC
     int stages = (212 * 1024) / stage_bytes;
     if (stages > 12) stages = 12;
     pp.c.stages = stages;
-    size_t smem = (size_t)stages * stage_bytes + 1024;
+    size_t smem = (size_t)stages * stage_bytes + 8 * EPI_STG_BYTES + 1024;   // ring + epilogue transposition buffers + alignment
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(umma_conv_persistent_kernel<MT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             214 * 1024);
+                                             226 * 1024);
         if (e != cudaSuccess) { srgan_set_error("cudaFuncSetAttribute(umma_conv_persistent_kernel): %s", cudaGetErrorString(e)); return SRGAN_ERR_CUDA; }
         attr_set = true;
     }

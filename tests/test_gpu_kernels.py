@@ -326,7 +326,8 @@ def test_crowd_conv_shapes(ops, dt, gi):
 
 @pytest.mark.parametrize('dt', DT)
 @pytest.mark.parametrize('rows,pitch,c0,C,yp', [(3 * 56 * 56, 256, 0, 96, 128), (1000, 40, 8, 24, 24), (77, 13, 3, 7, 9),
-                                                 (5, 1920, 0, 1920, 1920)])
+                                                 (5, 1920, 0, 1920, 1920), (20011, 200, 4, 100, 100),
+                                                 (4 * 196 * 16 + 3, 1024, 64, 640, 640)])
 def test_affine_ops(ops, dt, rows, pitch, c0, C, yp):
     gen = torch.Generator().manual_seed(rows + C)
     ref = TorchOps()
@@ -374,7 +375,8 @@ def test_copy2d_and_pools(ops, dt):
     gen = torch.Generator().manual_seed(9)
     ref = TorchOps()
     cu = lambda t: t.cuda()
-    for rows, sp, s0, dp, d0, C in ((500, 32, 0, 96, 64, 32), (300, 48, 8, 20, 0, 20), (41, 7, 2, 9, 3, 5)):
+    for rows, sp, s0, dp, d0, C in ((500, 32, 0, 96, 64, 32), (300, 48, 8, 20, 0, 20), (41, 7, 2, 9, 3, 5),
+                                    (30001, 64, 0, 1792, 256, 32), (9000, 512, 128, 384, 0, 380)):
         src = rnd(gen, rows * sp, dt=dt)
         for acc in (False, True):
             d_ref = rnd(gen, rows * dp, dt=dt)
