@@ -293,6 +293,7 @@ def main():
     # replays CUDA graphs (no host launches, so no event records inside it); the same kernel on the same buffers is
     # therefore timed during K eager steps run right after it, still inside this process and clock state.
     exp.runner.use_cuda_graph = False
+    overlap, exp.runner.overlap_dnn = exp.runner.overlap_dnn, False      # the probed kernel is timed alone on its stream
     launches_eager0 = eng.ops.launches
     # the probed kernel: age = D layer-2 conv (64->128 k4 s2) over the 4B-row batch; crowd = the transition-1 1x1 conv
     # (256->128 at 56x56, a [4B*3136 x 256] x [256 x 128] GEMM); coefficient = no dense kernel to probe (one persistent kernel)
@@ -305,6 +306,7 @@ def main():
     probe = eng.probe_end() if probe_layer is not None else {'count': 0}
     launches_per_step = (eng.ops.launches - launches_eager0) / probe_steps
     exp.runner.use_cuda_graph = graphed
+    exp.runner.overlap_dnn = overlap
     if graphed:
         launches = int(round(launches_per_step * args.steps))     # kernels executed by the replayed graphs
     t = torch.tensor([ms], device=dev)
@@ -388,7 +390,7 @@ def main():
                 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
                 'config': {'workload': workload_string(name, B, world),
-                           'precision_mode': args.precision, 'parallelism': f'dp{world}', 'cuda_graph': bool(graphed), 'micro_batch': args.micro_batch,
+                           'precision_mode': args.precision, 'parallelism': f'dp{world}', 'cuda_graph': bool(graphed), 'dnn_gan_overlap': bool(exp.runner.overlap_dnn), 'micro_batch': args.micro_batch,
                            'l2': ('inputs and activations of one step (age: 39 MB + ~1 GB, crowd: ~0.7 GB per sample) exceed the 126 MB L2; no flush needed'
                                   if name != 'coefficient' else 'working set (2 MB) is L2-resident by design: the step is launch/latency-bound, not bandwidth-bound'),
                            'global_steps_per_s': global_steps,

@@ -183,7 +183,9 @@ class Engine:
         self.mdt = self.D.grad.dtype               # fp32 in the product; tests may run the schedule in fp64
         self.scalars = torch.zeros(N_SCALARS, dtype=self.mdt, device=self.device)
         self._buf = {}
-        self._idx_rows = {}
+        # scratch-buffer scope: the DNN step ('dnn') and the GAN step ('gan') never share a workspace buffer, so the two
+        # step methods may be in flight at the same time on different streams (StepRunner overlaps them)
+        self._scope = 'gan'
         self._probe = None
         for st in (self.D, self.G, self.DNN):
             if st is not None:
@@ -192,6 +194,7 @@ class Engine:
     # ------------------------------------------------------------------ buffers
     def buf(self, key, shape, dtype=None, zero=False):
         dtype = dtype or self.act_dtype
+        key = (self._scope, key)
         t = self._buf.get(key)
         n = 1
         for s in shape:
@@ -267,7 +270,7 @@ class Engine:
 
     def _col(self, st: NetState, l: Layer, lo, n):
         P = l.geom.Hs * l.geom.Ws
-        return self._buf[('col', st.tag, l.name)][lo * P * l.kpad:(lo + n) * P * l.kpad]
+        return self._buf[(self._scope, ('col', st.tag, l.name))][lo * P * l.kpad:(lo + n) * P * l.kpad]
 
     def _coltmp(self, l: Layer, n):
         return self.buf(('coltmp',), (n * l.geom.Hs * l.geom.Ws * l.kpad,))
@@ -369,7 +372,6 @@ class Engine:
                 if op.kind == 'maxpool':               # one byte per pooled element: the max-pool index map
                     acts['idx:' + op.dst] = self.buf((tag, 'idx', op.dst), (nb_rows * net.bufs[op.dst].rows * op.C,),
                                                      dtype=torch.uint8)
-                    self._idx_rows[op.dst] = nb_rows
             return acts
         acts = [self.buf((tag, 'a', 0), (nb_rows * net.layers[0].in_elems,))]
         for i, l in enumerate(net.layers, 1):
@@ -519,7 +521,7 @@ class Engine:
                 # the forward records the winning window position per pooled element; the tangent pass routes by the map of
                 # the x_hat rows, the backward pass reads the map of its own rows
                 im = acts['idx:' + op.dst]
-                e = (im.numel() // self._idx_rows[op.dst])
+                e = db.rows * op.C                  # index bytes per sample
                 if tangent:
                     ops.maxpool(x, None, y, db.ch, op.c0, n, op.H, op.W, op.C, op.k, op.stride, op.pad,
                                 idx=im[mlo * e:(mlo + n) * e], idx_mode=2)
@@ -584,7 +586,7 @@ class Engine:
                 ops.copy2d(dy, db.ch, 0, dx, sb.ch, op.c0, n * sb.rows, op.C, True)
             elif op.kind == 'maxpool':
                 im = acts['idx:' + op.dst]
-                e = (im.numel() // self._idx_rows[op.dst])
+                e = db.rows * op.C
                 ops.maxpool_bwd(xa, dy, db.ch, op.c0, dx, n, op.H, op.W, op.C, op.k, op.stride, op.pad, sb.act, sb.slope,
                                 idx=im[mlo * e:(mlo + n) * e])
             elif op.kind == 'avgpool':
@@ -702,13 +704,14 @@ class Engine:
     # ------------------------------------------------------------------ DNN step (srgan.py:259-271)
     def dnn_step(self, x, y, cfg, lr, weight_decay):
         self.ops.begin()
+        self._scope = 'dnn'
         st, net = self.DNN, self.d_net
         B = x.shape[0]
         Bg = self._global_batch(B)
         F = net.feature_size
         fact, fslope = net.feature_act
-        acts = self.alloc_acts('D', net, 5 * B)
-        deltas = self.alloc_deltas('D', net, 5 * B)
+        acts = self.alloc_acts('D', net, B)
+        deltas = self.alloc_deltas('D', net, B)
         self.load_input(net, x, self.rows(self._in(net, acts), net.in_elems, 0, B), B)
         self.forward(st, acts, 0, B)
         feats = self._brows_feat(net, acts, 0, B)
@@ -725,6 +728,7 @@ class Engine:
     def gan_step(self, x, y, u, z, alpha, z2, cfg, train_generator=True):
         ops, D, G, net, gnet = self.ops, self.D, self.G, self.d_net, self.g_net
         ops.begin()
+        self._scope = 'gan'
         B = x.shape[0]
         if u.shape[0] != B or z.shape[0] != B or alpha.numel() != B:
             # srgan.py:363 draws alpha with settings.batch_size rows: the reference itself requires full batches
@@ -874,6 +878,7 @@ class Engine:
 
     def dnn_step_micro(self, x, y, cfg, lr, weight_decay, mb):
         self.ops.begin()
+        self._scope = 'dnn'
         st, net = self.DNN, self.d_net
         B = x.shape[0]
         if B % mb:
@@ -881,8 +886,8 @@ class Engine:
         Bg = self._global_batch(B)
         F = net.feature_size
         fact, fslope = net.feature_act
-        acts = self.alloc_acts('D', net, 5 * mb)
-        deltas = self.alloc_deltas('D', net, 5 * mb)
+        acts = self.alloc_acts('D', net, mb)
+        deltas = self.alloc_deltas('D', net, mb)
         pred = self.buf('pred', (mb,), self.mdt)
         dpred = self.buf('dpred', (mb,), self.mdt)
         self.scalars[SC_DNN:SC_DNN + 1].zero_()
@@ -900,6 +905,7 @@ class Engine:
     def gan_step_micro(self, x, y, u, z, alpha, z2, cfg, train_generator, mb):
         ops, D, G, net, gnet = self.ops, self.D, self.G, self.d_net, self.g_net
         ops.begin()
+        self._scope = 'gan'
         B = x.shape[0]
         if u.shape[0] != B or z.shape[0] != B or alpha.numel() != B:
             raise ValueError('labeled, unlabeled and noise batches must have the same size (SURVEY App. E.2)')
@@ -1017,9 +1023,10 @@ class Engine:
         """D(x) forward only: returns (prediction [B], features rows [B, F] in NHWC order)."""
         self.ops.begin()
         st = st or self.D
+        self._scope = 'dnn' if st is self.DNN else 'gan'       # the forward shares the scratch of its network's step
         net = st.net
         B = x.shape[0]
-        acts = self.alloc_acts('D', net, 5 * B)
+        acts = self.alloc_acts('D', net, B if st is self.DNN else 5 * B)
         self.load_input(net, x, self.rows(self._in(net, acts), net.in_elems, 0, B), B)
         self.forward(st, acts, 0, B)
         feats = self._brows_feat(net, acts, 0, B)
@@ -1029,6 +1036,7 @@ class Engine:
 
     def g_generate(self, z):
         self.ops.begin()
+        self._scope = 'gan'
         gnet = self.g_net
         B = z.shape[0]
         gacts = self.alloc_acts('G', gnet, B)

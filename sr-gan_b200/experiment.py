@@ -90,6 +90,7 @@ class Settings:
         self.precision = 'fp32'          # 'fp32' (SIMT, 1e-4 parity) | 'bf16' (tcgen05 tensor cores, 2e-2 parity)
         self.use_cuda_graph = True       # replay the step methods from CUDA graphs (piecewise around collectives)
         self.use_persistent_kernel = True    # coefficient application, single rank: one cooperative kernel per step method
+        self.overlap_dnn_step = True     # single rank: the DNN step runs on its own stream, overlapped with the GAN step
         self.micro_batch = 0             # > 0: run the step in micro-batches of this many samples (exact; bounds activation memory)
 
 
@@ -280,6 +281,13 @@ class StepRunner:
         self.use_cuda_graph = bool(ug) and os.environ.get('SRGAN_NO_GRAPH', '0') != '1' 
         self._graphs, self._statics = {}, {}
         self._side, self._pending = None, {}       # deferred (overlapped) gradient all-reduce + Adam groups: _run_deferred
+        # single rank: the DNN step (its own network, gradients, moments and -- Engine._scope -- scratch buffers) is
+        # enqueued on its own stream and overlaps the GAN step that follows it; gan_step joins the two streams at its end,
+        # so everything is ordered on the caller's stream again when a step pair returns.  The crowd step is thousands of
+        # launches that under-fill the GPU (7x7 / 14x14 stages): two independent chains in flight fill the gaps.
+        self.overlap_dnn = (comm is None and bool(getattr(settings, 'overlap_dnn_step', True))
+                            and os.environ.get('SRGAN_NO_OVERLAP', '0') != '1')
+        self._dnn_stream, self._dnn_done = None, None
         # coefficient application: one persistent cooperative kernel per step method (csrc/coef_step.cu) instead of
         # ~150 generic launches; single rank only (the feature sums are combined inside the kernel)
         self.persistent = (self._persistent_shape_ok(d_net, g_net) and comm is None
@@ -370,25 +378,51 @@ class StepRunner:
     # noise are copied into static buffers, Adam's bias corrections come from srgan_adam_prepare), so a graph is valid
     # until the batch size, lr / weight decay or the generator flag changes.  First call = eager (allocates the
     # workspaces), second call = capture, later calls = replay.  SRGAN_NO_GRAPH=1 or use_cuda_graph=False -> eager.
-    def _graphed(self, key, statics, fn):
-        """statics: list of (static_buffer, source tensor) copied before replay; fn(): enqueues the step on statics."""
+    def _graphed(self, key, statics, fn, launch=None):
+        """statics: list of (static_buffer, source tensor) copied (on the caller's stream) before replay; fn(): enqueues
+        the step on statics; launch(f): runs the enqueueing callable f (default: in place; the DNN step passes
+        _on_dnn_stream)."""
+        launch = launch or (lambda f: f())
         entry = self._graphs.get(key)
         if entry is None:
             self._graphs[key] = {'calls': 1, 'graph': None}
             for dst, src in statics:
                 dst.copy_(src)
-            fn()
+            launch(fn)
             return
         for dst, src in statics:
             dst.copy_(src)
         if entry['graph'] is None:
             torch.cuda.synchronize(self.device)
             entry['graph'] = self._capture_segments(fn)
-        for seg in entry['graph']:
-            if isinstance(seg, tuple):
-                self._run_deferred(*seg)
-            else:
-                seg()
+
+        def replay():
+            for seg in entry['graph']:
+                if isinstance(seg, tuple):
+                    self._run_deferred(*seg)
+                else:
+                    seg()
+        launch(replay)
+
+    def _on_dnn_stream(self, f):
+        """Runs f() on the DNN stream, after everything enqueued on the caller's stream so far."""
+        main = torch.cuda.current_stream(self.device)
+        if self._dnn_stream is None:
+            self._dnn_stream = torch.cuda.Stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._dnn_stream.wait_event(ev)
+        with torch.cuda.stream(self._dnn_stream):
+            f()
+            done = torch.cuda.Event()
+            done.record(self._dnn_stream)
+        self._dnn_done = done
+
+    def _join_dnn(self):
+        """The caller's stream waits for the DNN step in flight (if any)."""
+        if self._dnn_done is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._dnn_done)
+            self._dnn_done = None
 
     def _run_deferred(self, tag, items):
         """A deferred group (gradient all-reduce + the Adam graph of one network) on the side stream, after everything
@@ -410,6 +444,8 @@ class StepRunner:
         """Makes the current stream wait for the deferred updates of the given networks (None: all).  dnn_step touches
         only DNN (parameters, gradient buffer, moments; the activation scratch it shares with D is not used by an
         update), gan_step only D and G: so DNN's all-reduce + Adam overlap the whole GAN step, G's the next DNN step."""
+        if tags is None or 'DNN' in tags:
+            self._join_dnn()
         if self._pending:
             main = torch.cuda.current_stream(self.device)
             for tag in list(self._pending) if tags is None else tags:
@@ -497,13 +533,19 @@ class StepRunner:
                 self.engine.dnn_step_micro(xx, yy, cfg, lr, wd, mb)
             else:
                 self.engine.dnn_step(xx, yy, cfg, lr, wd)
+        launch = self._on_dnn_stream if self.overlap_dnn else None
         if not self.use_cuda_graph:
-            run(examples, labels)
+            if launch is None:
+                run(examples, labels)
+            else:                                   # eager: the inputs themselves are read on the DNN stream
+                launch(lambda: run(examples, labels))
+                for t in (examples,) + (tuple(labels) if isinstance(labels, (tuple, list)) else (labels,)):
+                    t.record_stream(self._dnn_stream)
             return
         xs = self._static('dnn_x', examples)
         ys, ypairs = self._static_labels('dnn_y', labels)
         key = ('dnn', tuple(examples.shape), lr, wd, cfg.labeled_loss_multiplier, cfg.labeled_loss_order, cfg.map_multiplier, mb)
-        self._graphed(key, [(xs, examples)] + ypairs, lambda: run(xs, ys))
+        self._graphed(key, [(xs, examples)] + ypairs, lambda: run(xs, ys), launch)
 
     def gan_step(self, labeled_examples, labels, unlabeled_examples, step=0, noise=None):
         cfg = self.config()
@@ -523,6 +565,7 @@ class StepRunner:
                 self.engine.gan_step(xx, yy, uu, zz, aa, zz2, cfg, train_generator=train_g)
         if not self.use_cuda_graph:
             run(labeled_examples, labels, unlabeled_examples, z, alpha, z2)
+            self._join_dnn()
             return
         alpha = alpha.reshape(-1)
         ys, ypairs = self._static_labels('y', labels)
@@ -532,6 +575,7 @@ class StepRunner:
         key = ('gan', tuple(labeled_examples.shape), train_g, repr(sorted(vars(cfg).items())))
         xs, us, zs, als, z2s = (d for d, _ in st)
         self._graphed(key, st + ypairs, lambda: run(xs, ys, us, zs, als, z2s))
+        self._join_dnn()
 
     def scalars(self):
         """One device->host read of the step's scalars (the .item() calls of srgan.py:268-270, 306-319)."""

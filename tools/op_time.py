@@ -14,6 +14,7 @@ s.batch_size, s.precision, s.map_multiplier = B, (sys.argv[3] if len(sys.argv) >
 s.matching_loss_multiplier, s.contrasting_loss_multiplier, s.gradient_penalty_multiplier = wl['mult']
 s.use_cuda_graph = False
 s.use_persistent_kernel = False
+s.overlap_dnn_step = False           # per-op events need one stream
 kw = dict(image_size=128, conv_dim=64, z_dim=256) if name == 'age' else {}
 exp = srgan_b200.Experiment(s, name, **kw)
 x, y, u = bench.make_batches(name, B, 1)
