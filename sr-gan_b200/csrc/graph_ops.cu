@@ -862,6 +862,78 @@ inline bool vec8_ok(int dtype, int C, int p0, int o0, int p1 = 0, int o1 = 0) {
     return dtype == SRGAN_BF16 && ((C | p0 | o0 | p1 | o1) & 7) == 0;
 }
 
+// vector average pooling: a thread owns W consecutive channels of one output (forward) / input (backward) pixel
+template <typename T, int W>
+__global__ void __launch_bounds__(256) avgpool_vec_kernel(const T* __restrict__ x, int x_pitch, T* __restrict__ y, int y_pitch, int y_c0,
+                                                          int n, int H, int Wd, int C, int k) {
+    const int Ho = H / k, Wo = Wd / k, cg = C / W;
+    const long long total = (long long)n * Ho * Wo * cg;
+    const float inv = 1.f / (float)(k * k);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cg) * W;
+        long long t = i / cg;
+        const int wo = (int)(t % Wo); t /= Wo;
+        const int ho = (int)(t % Ho);
+        const long long b = t / Ho;
+        float acc[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) acc[q] = 0.f;
+        const T* xb = x + ((b * H + (long long)ho * k) * Wd + (long long)wo * k) * x_pitch + c;
+        if (k == 2) {                                         // the DenseNet transitions: four independent loads
+            Raw<T, W> r[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) r[d] = ld_raw<T, W>(xb + ((long long)(d >> 1) * Wd + (d & 1)) * x_pitch);
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                float v[W];
+                unpack(r[d], v);
+#pragma unroll
+                for (int q = 0; q < W; ++q) acc[q] += v[q];
+            }
+        } else {
+            for (int dh = 0; dh < k; ++dh)
+                for (int dw = 0; dw < k; ++dw) {
+                    float v[W];
+                    unpack(ld_raw<T, W>(xb + ((long long)dh * Wd + dw) * x_pitch), v);
+#pragma unroll
+                    for (int q = 0; q < W; ++q) acc[q] += v[q];
+                }
+        }
+#pragma unroll
+        for (int q = 0; q < W; ++q) acc[q] *= inv;
+        stw<W>(y + ((b * Ho + ho) * Wo + wo) * y_pitch + y_c0 + c, acc);
+    }
+}
+template <typename T, int W>
+__global__ void __launch_bounds__(256) avgpool_bwd_vec_kernel(const T* __restrict__ dy, int dy_pitch, int dy_c0, T* __restrict__ dx,
+                                                              int x_pitch, int n, int H, int Wd, int C, int k,
+                                                              const T* __restrict__ href, int act, float slope) {
+    const int Ho = H / k, Wo = Wd / k, cg = C / W;
+    const long long total = (long long)n * H * Wd * cg;
+    const float inv = 1.f / (float)(k * k);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cg) * W;
+        long long t = i / cg;
+        const int w = (int)(t % Wd); t /= Wd;
+        const int h = (int)(t % H);
+        const long long b = t / H;
+        const long long xi = ((b * H + h) * Wd + w) * x_pitch + c;
+        const Raw<T, W> dr = ld_raw<T, W>(dy + ((b * Ho + h / k) * Wo + w / k) * dy_pitch + dy_c0 + c);
+        float v[W];
+        unpack(dr, v);
+        if (href) {
+            float hv[W];
+            unpack(ld_raw<T, W>(href + xi), hv);
+#pragma unroll
+            for (int q = 0; q < W; ++q) v[q] *= inv * act_bwd(hv[q], act, slope);
+        } else {
+#pragma unroll
+            for (int q = 0; q < W; ++q) v[q] *= inv;
+        }
+        stw<W>(dx + xi, v);
+    }
+}
+
 // depth-to-space of a one-channel map: img[n, i*k+r, j*k+s] <-> blk[n, i, j, r*k+s]   (one thread per image pixel)
 template <typename T>
 __global__ void __launch_bounds__(256) depth_to_space_kernel(const T* __restrict__ src, T* __restrict__ dst, int n, int Hs, int Ws,
@@ -1059,7 +1131,10 @@ int srgan_avgpool(const void* x, int x_pitch, void* y, int y_pitch, int y_c0, in
                   "srgan_avgpool: bad arguments (the window must tile the input)");
     if (n == 0) return SRGAN_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    DISPATCH_T(dtype, avgpool_kernel<T><<<ew_grid((long long)n * (H / k) * (W / k) * C), 256, 0, st>>>((const T*)x, x_pitch, (T*)y, y_pitch, y_c0, n, H, W, C, k));
+    DISPATCH_T(dtype,
+               if (vec8_ok(dtype, C, x_pitch, y_pitch, y_c0)) avgpool_vec_kernel<T, 8><<<ew_grid((long long)n * (H / k) * (W / k) * C / 8), 256, 0, st>>>((const T*)x, x_pitch, (T*)y, y_pitch, y_c0, n, H, W, C, k);
+               else if (vec_ok(C, x_pitch, y_pitch, y_c0)) avgpool_vec_kernel<T, 4><<<ew_grid((long long)n * (H / k) * (W / k) * C / 4), 256, 0, st>>>((const T*)x, x_pitch, (T*)y, y_pitch, y_c0, n, H, W, C, k);
+               else avgpool_kernel<T><<<ew_grid((long long)n * (H / k) * (W / k) * C), 256, 0, st>>>((const T*)x, x_pitch, (T*)y, y_pitch, y_c0, n, H, W, C, k));
     SRGAN_CHECK_LAUNCH("avgpool_kernel");
     return SRGAN_OK;
 }
@@ -1071,7 +1146,11 @@ int srgan_avgpool_bwd(const void* dy, int dy_pitch, int dy_c0, void* dx, int x_p
                   "srgan_avgpool_bwd: bad arguments");
     if (n == 0) return SRGAN_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    DISPATCH_T(dtype, avgpool_bwd_kernel<T><<<ew_grid((long long)n * H * W * C), 256, 0, st>>>((const T*)dy, dy_pitch, dy_c0, (T*)dx, x_pitch, n, H, W, C, k, (const T*)(act == SRGAN_ACT_NONE ? nullptr : href), act, slope));
+    const void* hr = act == SRGAN_ACT_NONE ? nullptr : href;
+    DISPATCH_T(dtype,
+               if (vec8_ok(dtype, C, x_pitch, dy_pitch, dy_c0)) avgpool_bwd_vec_kernel<T, 8><<<ew_grid((long long)n * H * W * C / 8), 256, 0, st>>>((const T*)dy, dy_pitch, dy_c0, (T*)dx, x_pitch, n, H, W, C, k, (const T*)hr, act, slope);
+               else if (vec_ok(C, x_pitch, dy_pitch, dy_c0)) avgpool_bwd_vec_kernel<T, 4><<<ew_grid((long long)n * H * W * C / 4), 256, 0, st>>>((const T*)dy, dy_pitch, dy_c0, (T*)dx, x_pitch, n, H, W, C, k, (const T*)hr, act, slope);
+               else avgpool_bwd_kernel<T><<<ew_grid((long long)n * H * W * C), 256, 0, st>>>((const T*)dy, dy_pitch, dy_c0, (T*)dx, x_pitch, n, H, W, C, k, (const T*)hr, act, slope));
     SRGAN_CHECK_LAUNCH("avgpool_bwd_kernel");
     return SRGAN_OK;
 }

@@ -495,6 +495,7 @@ struct UmmaWgradParams {
     int TW, TH, TN;               // pixel patch per stage: TW*TH*TN == 64
     int tiles_w, tiles_h, tiles_n;
     int NT;                       // taps per CTA
+    int NB;                       // b tiles (BN channels each) per CTA: NT*NB accumulators share every S tile
     int chunks_per_split;
     float* dW;
     int stages;
@@ -512,25 +513,25 @@ __global__ void __launch_bounds__(WG_THREADS) umma_wgrad_kernel(const __grid_con
 
     constexpr int A_BYTES = 2 * WG_PIX * 128;            // two 64-channel column groups of [64 pixels x 128 B]
     constexpr int B_TAP_BYTES = (BN / 64) * WG_PIX * 128;
-    const int NT = p.NT;
-    const int STAGE_BYTES = A_BYTES + NT * B_TAP_BYTES;
+    const int NT = p.NT, NB = p.NB, NS = NT * NB;            // NS sub-problems (tap, b tile) per CTA
+    const int STAGE_BYTES = A_BYTES + NS * B_TAP_BYTES;
     const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stages = p.stages;
 
     // blockIdx.x -> (a tile, tap group, b tile); blockIdx.z -> K split
-    const int b_tiles = p.Cb / BN, tap_groups = (p.R * p.S) / NT;
+    const int b_tiles = (p.Cb + NB * BN - 1) / (NB * BN), tap_groups = (p.R * p.S) / NT;
     int t = blockIdx.x;
     const int bt = t % b_tiles; t /= b_tiles;
     const int tg = t % tap_groups; t /= tap_groups;
     const int at = t;
-    const int a0 = at * 128, b0 = bt * BN, tap0 = tg * NT;
+    const int a0 = at * 128, b0 = bt * NB * BN, tap0 = tg * NT;     // channels >= Cb of the last group: TMA zero fill
     const int total_chunks = p.tiles_w * p.tiles_h * p.tiles_n;
     const int ch_begin = blockIdx.z * p.chunks_per_split;
     int ch_end = ch_begin + p.chunks_per_split;
     if (ch_end > total_chunks) ch_end = total_chunks;
     const int n_iters = ch_end - ch_begin;
-    const uint32_t ncols = NT * BN <= 32 ? 32 : (NT * BN <= 64 ? 64 : (NT * BN <= 128 ? 128 : (NT * BN <= 256 ? 256 : 512)));
+    const uint32_t ncols = NS * BN <= 32 ? 32 : (NS * BN <= 64 ? 64 : (NS * BN <= 128 ? 128 : (NS * BN <= 256 ? 256 : 512)));
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
@@ -561,11 +562,11 @@ __global__ void __launch_bounds__(WG_THREADS) umma_wgrad_kernel(const __grid_con
                     const uint32_t dst = tiles + s * STAGE_BYTES;
                     tma_load_4d(dst, &tmS, fb, a0, tw_i * p.TW, th_i * p.TH, tn_i * p.TN);
                     tma_load_4d(dst + WG_PIX * 128, &tmS, fb, a0 + 64, tw_i * p.TW, th_i * p.TH, tn_i * p.TN);
-                    for (int k = 0; k < NT; ++k) {
-                        const int tap = tap0 + k, r = tap / p.S, sx = tap % p.S;
+                    for (int k = 0; k < NS; ++k) {
+                        const int tap = tap0 + k / NB, r = tap / p.S, sx = tap % p.S, bk = b0 + (k % NB) * BN;
                         const int lw = tw_i * p.TW * p.stride - p.pad + sx, lh = th_i * p.TH * p.stride - p.pad + r;
                         for (int g = 0; g < BN / 64; ++g)
-                            tma_load_4d(dst + A_BYTES + k * B_TAP_BYTES + g * WG_PIX * 128, &tmL, fb, b0 + g * 64, lw, lh,
+                            tma_load_4d(dst + A_BYTES + k * B_TAP_BYTES + g * WG_PIX * 128, &tmL, fb, bk + g * 64, lw, lh,
                                         tn_i * p.TN);
                     }
                     if (++s == stages) { s = 0; ph ^= 1; }
@@ -582,7 +583,7 @@ __global__ void __launch_bounds__(WG_THREADS) umma_wgrad_kernel(const __grid_con
                     tc_fence_after();
                     const uint32_t a_s = tiles + s * STAGE_BYTES;
                     const uint64_t ad0 = desc0 + (uint64_t)(a_s >> 4);
-                    for (int k = 0; k < NT; ++k) {
+                    for (int k = 0; k < NS; ++k) {
                         const uint64_t bd0 = desc0 + (uint64_t)((a_s + A_BYTES + k * B_TAP_BYTES) >> 4);
 #pragma unroll
                         for (int kk = 0; kk < WG_PIX / 16; ++kk)      // 16 K rows (pixels) = 2048 B further into every column group
@@ -601,14 +602,16 @@ __global__ void __launch_bounds__(WG_THREADS) umma_wgrad_kernel(const __grid_con
             tc_fence_after();
             const long long rowN = (long long)p.R * p.S * p.Cb;
 #pragma unroll 1
-            for (int k = 0; k < NT; ++k) {
+            for (int k = 0; k < NS; ++k) {
 #pragma unroll 1
                 for (int j = 0; j < BN / 32; ++j) {
+                    const int bcol = b0 + (k % NB) * BN + j * 32;
+                    if (bcol >= p.Cb) continue;               // warp-uniform: zero-filled tail of the last b group
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + k * BN + j * 32, v);
                     tmem_ld_wait();
                     if (a >= p.Ca) continue;                  // zero-filled half tile (Ca = 64 mod 128)
-                    float* dst = p.dW + (long long)a * rowN + (long long)(tap0 + k) * p.Cb + b0 + j * 32;
+                    float* dst = p.dW + (long long)a * rowN + (long long)(tap0 + k / NB) * p.Cb + bcol;
 #pragma unroll
                     for (int e = 0; e < 32; e += 4)
                         red_add_v4(dst + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
@@ -710,7 +713,7 @@ int launch_conv_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaC
 
 template <int BN, int WG_PIX>
 int launch_wgrad(const CUtensorMap& tmS, const CUtensorMap& tmL, UmmaWgradParams& p, dim3 grid, cudaStream_t st) {
-    const int stage_bytes = 2 * WG_PIX * 128 + p.NT * (BN / 64) * WG_PIX * 128;
+    const int stage_bytes = 2 * WG_PIX * 128 + p.NT * p.NB * (BN / 64) * WG_PIX * 128;
     p.stages = (200 * 1024) / stage_bytes;
     if (p.stages > 8) p.stages = 8;
     size_t smem = (size_t)p.stages * stage_bytes + 1024;
@@ -787,11 +790,38 @@ int umma_conv(int mode, const void* src, const void* W, void* out, int n, const 
 
 int umma_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, cudaStream_t st) {
     if (g->Ca % 64 != 0 || g->Cb % 64 != 0) return 0;   // Ca = 64 (mod 128): the upper half tile is TMA zero fill
-    const int BN = g->Cb % 256 == 0 ? 256 : (g->Cb % 128 == 0 ? 128 : 64);
+    int BN = g->Cb % 256 == 0 ? 256 : (g->Cb % 128 == 0 ? 128 : 64);
     const int taps = g->R * g->S;
     int NT = 512 / BN;                                         // largest divisor of the tap count that fits TMEM (3 for 3x3)
     while (NT > 1 && taps % NT != 0) --NT;
     if (taps % NT != 0) return 0;
+    // 1x1 (the DenseNet trunk: S = the 128-channel delta, L = up to 1920 input channels): TMEM columns that the taps do
+    // not use can hold further b tiles (NB), so one S tile feeds all of them, and tiles may be wider than Cb's
+    // factorisation allows (the tail beyond Cb is TMA zero fill, skipped in the epilogue).  Fewer output tiles t mean S
+    // is re-read t times instead of Cb/64 times, but the K split over one wave of CTAs then adds 148/t partial sums into
+    // dW with fp32 reductions: pick (BN, NB) by that traffic model (a reduced byte weighted 4x a read byte).
+    int NB = 1;
+    if (taps == 1) {
+        const double rows = (double)n * g->Hs * g->Ws;
+        const double s_bytes = rows * g->Ca * 2.0, dw_bytes = 4.0 * g->Ca * g->Cb;
+        const int a_tiles = (g->Ca + 127) / 128;
+        double best = -1.0;
+        int best_bn = BN, best_nb = 1;
+        for (int bn = 64; bn <= 256; bn *= 2)
+            for (int nb = 1; nb * bn <= 512; ++nb) {
+                if (nb > 1 && (nb - 1) * bn >= g->Cb) break;          // an entirely empty b tile
+                if (bn == BN && nb == 1) {}                              // the exact-fit default is always a candidate
+                else if (bn < BN) continue;                              // narrower than the exact fit never helps
+                const int t = a_tiles * ((g->Cb + nb * bn - 1) / (nb * bn));
+                const double chunks = rows / (bn == 64 ? 64 : 32);
+                double splits = kNumSMs / t < 1 ? 1 : kNumSMs / t;
+                if (splits > (chunks + 7) / 8) splits = (chunks + 7) / 8;
+                if (splits < 1) splits = 1;
+                const double cost = s_bytes * t + 4.0 * dw_bytes * splits;
+                if (best < 0 || cost < best) { best = cost; best_bn = bn; best_nb = nb; }
+            }
+        BN = best_bn; NB = best_nb;
+    }
     if (g->stride > 8) return 0;
     UmmaWgradParams p;
     const int WG_PIX = BN == 64 ? 64 : 32;
@@ -800,9 +830,9 @@ int umma_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom*
     if (((uintptr_t)S & 15) || ((uintptr_t)L & 15) || ((uintptr_t)dW & 15)) return 0;
     p.n = n; p.Hs = g->Hs; p.Ws = g->Ws; p.Ca = g->Ca; p.Cb = g->Cb; p.R = g->R; p.S = g->S; p.stride = g->stride; p.pad = g->pad;
     p.tiles_w = g->Ws / p.TW; p.tiles_h = g->Hs / p.TH; p.tiles_n = (n + p.TN - 1) / p.TN;
-    p.NT = NT; p.dW = dW;
+    p.NT = NT; p.NB = NB; p.dW = dW;
     const int total_chunks = p.tiles_w * p.tiles_h * p.tiles_n;
-    const int out_tiles = ((g->Ca + 127) / 128) * (taps / NT) * (g->Cb / BN);
+    const int out_tiles = ((g->Ca + 127) / 128) * (taps / NT) * ((g->Cb + NB * BN - 1) / (NB * BN));
     int splits = kNumSMs / out_tiles;                         // one CTA per SM (512 TMEM columns each): never a second wave
     int max_splits = (total_chunks + 7) / 8;                  // at least 8 stages of work per CTA
     if (splits > max_splits) splits = max_splits;

@@ -46,9 +46,14 @@ GEOMS = [
     Geom(1, 1, 2048, 1, 1, 256, 1, 1, 1, 0),       # tcgen05: fc as linear
     Geom(8, 8, 64, 8, 8, 64, 3, 3, 1, 1),          # tcgen05: k3 s1; wgrad with Ca = 64 (half tile zero-filled)
     Geom(1, 1, 64, 1, 1, 64, 1, 1, 1, 0),          # tcgen05: the [pixels x 64] GEMM of the thin-layer lowering
+    # DenseNet trunk 1x1 GEMMs (Ca = 128 bottleneck channels, Cb = padded concat width): wgrad b-tile groups / partial tiles
+    Geom(1, 1, 128, 1, 1, 192, 1, 1, 1, 0),        # Cb = 3 x 64
+    Geom(1, 1, 128, 1, 1, 1088, 1, 1, 1, 0),       # Cb = 17 x 64: 256-wide tiles, the last one mostly TMA zero fill
+    Geom(1, 1, 128, 1, 1, 320, 1, 1, 1, 0),        # Cb = 5 x 64
 ]
-TENSOR_ELIGIBLE = {4, 8, 9, 10, 11, 12}
-WGRAD_TENSOR_ELIGIBLE = {4, 8, 9, 10, 11, 12}
+TENSOR_ELIGIBLE = {4, 8, 9, 10, 11, 12, 13, 14, 15}
+WGRAD_TENSOR_ELIGIBLE = {4, 8, 9, 10, 11, 12, 13, 14, 15}
+TRUNK_GEMM_ROWS = {13: 64 * 196 + 5, 14: 3001, 15: 20 * 3136}       # small / large row counts flip the (BN, NB) choice
 
 
 @pytest.mark.parametrize('dt', DT)
@@ -57,6 +62,7 @@ def test_conv_down_up_wgrad(ops, dt, gi):
     g = GEOMS[gi]
     gen = torch.Generator().manual_seed(gi)
     n = (5000 if g.Ca == 64 else 130) if g.Hl == 1 else 5
+    n = TRUNK_GEMM_ROWS.get(gi, n)
     ref = TorchOps()
     L = rnd(gen, n * g.Hl * g.Wl * g.Cb, dt=dt)
     S = rnd(gen, n * g.Hs * g.Ws * g.Ca, dt=dt)
@@ -418,10 +424,13 @@ def test_copy2d_and_pools(ops, dt):
         ref.maxpool_bwd(x, dy, pitch, c0, dx_ref, n, H, W, C, k, s, p, 1, 0.0, idx=idx_ref)
         ops.maxpool_bwd(cu(x), cu(dy), pitch, c0, dx, n, H, W, C, k, s, p, 1, 0.0, idx=idx)
         close(dx, dx_ref, tol(dt), 'maxpool_bwd idx')
-    for n, H, W, C, k, xp in ((3, 8, 8, 12, 2, 12), (2, 7, 7, 40, 7, 64), (1, 4, 4, 3, 2, 5)):
+    # (.., pad): destination slice at channel offset `pad` of rows C + pad wide; pad = 8 with C % 8 == 0 takes the
+    # 8-channel vector kernels in bf16, pad = 4 the 4-channel ones
+    for n, H, W, C, k, xp, pad in ((3, 8, 8, 12, 2, 12, 4), (2, 7, 7, 40, 7, 64, 4), (1, 4, 4, 3, 2, 5, 4), (3, 14, 14, 64, 2, 64, 8),
+                                   (2, 7, 7, 40, 7, 64, 8), (5, 28, 28, 256, 2, 256, 0)):
         x = rnd(gen, n * H * W * xp, dt=dt)
         Ho, Wo = H // k, W // k
-        pitch, c0 = C + 4, 4
+        pitch, c0 = C + pad, pad
         y_ref = torch.zeros(n * Ho * Wo * pitch, dtype=dt)
         y = y_ref.clone().cuda()
         ref.avgpool(x, xp, y_ref, pitch, c0, n, H, W, C, k)
