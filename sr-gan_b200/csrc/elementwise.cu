@@ -254,29 +254,61 @@ __global__ void __launch_bounds__(256) uncast_kernel(const T* __restrict__ src, 
 // ------------------------------------------------------------------------------------------------------------
 struct ThinP { int n, Hs, Ws, Hl, Wl, Cb, R, S, stride, pad, kpad; };
 
+// The column index k -> (filter row r, filter column s, channel b) split costs three integer divisions; it is the same for
+// every pixel, so each block tabulates it once in shared memory (Kpad <= 256: the crowd stem k7 s2, 3 channels, has 147 of
+// 192 columns) and the element loop is one table read, two adds and the 2-byte gather (interior pixels skip the bounds
+// checks).
+constexpr int IM2COL_TAB = 256;
 template <typename T>
 __global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ L, T* __restrict__ col, ThinP p) {
+    __shared__ int tab[IM2COL_TAB];                              // (r << 20) | (s << 10) | b, or -1 for the pad columns
+    const int K = p.R * p.S * p.Cb;
+    const bool tabbed = p.kpad <= IM2COL_TAB;
+    if (tabbed) {
+        for (int k = threadIdx.x; k < p.kpad; k += blockDim.x) {
+            int v = -1;
+            if (k < K) { const int tap = k / p.Cb, b = k - tap * p.Cb, r = tap / p.S, sx = tap - r * p.S; v = (r << 20) | (sx << 10) | b; }
+            tab[k] = v;
+        }
+        __syncthreads();
+    }
     const int cpr = p.kpad / 8;                                  // 8-element chunks per row
     const long long total = (long long)p.n * p.Hs * p.Ws * cpr;
-    const int K = p.R * p.S * p.Cb;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         long long pix = i / cpr;
         int j = (int)(i - pix * cpr);
         int nn = (int)(pix / (p.Hs * p.Ws)); int rem = (int)(pix - (long long)nn * p.Hs * p.Ws);
         int oh = rem / p.Ws, ow = rem - oh * p.Ws;
+        const int ih0 = oh * p.stride - p.pad, iw0 = ow * p.stride - p.pad;
         float v[8];
+        if (tabbed) {
+            const long long base = (((long long)nn * p.Hl + ih0) * p.Wl + iw0) * p.Cb;   // may be negative: only in-bounds offsets are read
+            const bool interior = ih0 >= 0 && iw0 >= 0 && ih0 + p.R <= p.Hl && iw0 + p.S <= p.Wl;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            int k = j * 8 + e;
-            float x = 0.f;
-            if (k < K) {
-                int tap = k / p.Cb, b = k - tap * p.Cb, r = tap / p.S, s = tap - r * p.S;
-                int ih = oh * p.stride - p.pad + r, iw = ow * p.stride - p.pad + s;
-                if (ih >= 0 && ih < p.Hl && iw >= 0 && iw < p.Wl)
-                    x = to_f(L[(((long long)nn * p.Hl + ih) * p.Wl + iw) * p.Cb + b]);
+            for (int e = 0; e < 8; ++e) {
+                const int t = tab[j * 8 + e];
+                float x = 0.f;
+                if (t >= 0) {
+                    const int r = t >> 20, sx = (t >> 10) & 1023, b = t & 1023;
+                    if (interior || (ih0 + r >= 0 && ih0 + r < p.Hl && iw0 + sx >= 0 && iw0 + sx < p.Wl))
+                        x = to_f(L[base + (r * p.Wl + sx) * p.Cb + b]);
+                }
+                v[e] = x;
             }
-            v[e] = x;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                int k = j * 8 + e;
+                float x = 0.f;
+                if (k < K) {
+                    int tap = k / p.Cb, b = k - tap * p.Cb, r = tap / p.S, sx = tap - r * p.S;
+                    int ih = ih0 + r, iw = iw0 + sx;
+                    if (ih >= 0 && ih < p.Hl && iw >= 0 && iw < p.Wl)
+                        x = to_f(L[(((long long)nn * p.Hl + ih) * p.Wl + iw) * p.Cb + b]);
+                }
+                v[e] = x;
+            }
         }
         T* d = col + pix * p.kpad + j * 8;
         st4(d, make_float4(v[0], v[1], v[2], v[3]));

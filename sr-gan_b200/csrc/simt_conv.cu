@@ -304,8 +304,191 @@ static bool direct_up_eligible(int mode, const srgan_geom* g, int n) {
            (long long)n * g->Hl * g->Wl >= 1024;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// patch convolutions: kernel = stride = 2, no padding, a handful of channels (the crowd MapModule convs 1->8->16->32,
+// crowd/models.py:770-776, and their data gradients).  Every output pixel reads its own 2x2 input patch and nothing else,
+// the whole filter is <= 2048 weights: one thread per small-side pixel, the patch / the Ca deltas in registers, weights
+// broadcast from shared memory as float4, contiguous runs moved with the widest aligned vector access.  As tiled GEMMs
+// these ran at 0.2-0.5 TB/s (N = 8..32 columns of a 64-wide tile); they are pure streaming problems.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, int N> struct RunVec {
+    static constexpr int BYTES = N * (int)sizeof(T);
+    static constexpr int VB = BYTES % 16 == 0 ? 16 : (BYTES % 8 == 0 ? 8 : (BYTES % 4 == 0 ? 4 : (int)sizeof(T)));
+};
+template <typename T, int N>
+__device__ __forceinline__ void ld_run(const T* __restrict__ p, float (&v)[N]) {
+    constexpr int VB = RunVec<T, N>::VB, E = VB / (int)sizeof(T);
+    T tmp[N];
+#pragma unroll
+    for (int i = 0; i < N / E; ++i) {
+        if (VB == 16) *reinterpret_cast<uint4*>(tmp + i * E) = *reinterpret_cast<const uint4*>(p + i * E);
+        else if (VB == 8) *reinterpret_cast<uint2*>(tmp + i * E) = *reinterpret_cast<const uint2*>(p + i * E);
+        else if (VB == 4) *reinterpret_cast<uint32_t*>(tmp + i * E) = *reinterpret_cast<const uint32_t*>(p + i * E);
+        else tmp[i] = p[i];
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = to_f(tmp[i]);
+}
+template <typename T, int N>
+__device__ __forceinline__ void st_run(T* __restrict__ p, const float (&v)[N]) {
+    constexpr int VB = RunVec<T, N>::VB, E = VB / (int)sizeof(T);
+    T tmp[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) tmp[i] = from_f<T>(v[i]);
+#pragma unroll
+    for (int i = 0; i < N / E; ++i) {
+        if (VB == 16) *reinterpret_cast<uint4*>(p + i * E) = *reinterpret_cast<const uint4*>(tmp + i * E);
+        else if (VB == 8) *reinterpret_cast<uint2*>(p + i * E) = *reinterpret_cast<const uint2*>(tmp + i * E);
+        else if (VB == 4) *reinterpret_cast<uint32_t*>(p + i * E) = *reinterpret_cast<const uint32_t*>(tmp + i * E);
+        else p[i] = tmp[i];
+    }
+}
+
+// down: S[pix, a] = epi(sum_{r,s,b} L[2oh+r, 2ow+s, b] * Wd[a][r][s][b])
+template <typename T, int CA, int CB>
+__global__ void __launch_bounds__(128) patch_down_kernel(const T* __restrict__ L, const T* __restrict__ Wd, T* __restrict__ out,
+                                                         const float* __restrict__ bias, int bias_mod, const T* __restrict__ href,
+                                                         int epi, int act, float slope, ConvP p) {
+    constexpr int KK = 4 * CB;                     // patch elements; (r, s, b) order = two runs of 2*CB contiguous elements
+    __shared__ __align__(16) float wsm[CA * KK];
+    for (int i = threadIdx.x; i < CA * KK; i += blockDim.x) wsm[i] = to_f(Wd[i]);
+    __syncthreads();
+    const long long total = (long long)p.n * p.Hs * p.Ws;
+    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
+        const int ow = (int)(pix % p.Ws);
+        const long long t = pix / p.Ws;
+        const int oh = (int)(t % p.Hs);
+        const long long b = t / p.Hs;
+        float in[KK];
+        {
+            float r0[2 * CB], r1[2 * CB];
+            const T* lp = L + ((b * p.Hl + 2 * oh) * p.Wl + 2 * ow) * CB;
+            ld_run<T, 2 * CB>(lp, r0);
+            ld_run<T, 2 * CB>(lp + (long long)p.Wl * CB, r1);
+#pragma unroll
+            for (int i = 0; i < 2 * CB; ++i) { in[i] = r0[i]; in[2 * CB + i] = r1[i]; }
+        }
+        // outputs in groups of 8 channels (one 16-byte store in bf16): bounded register use, the group loop stays rolled
+        constexpr int G = CA < 8 ? CA : 8;
+#pragma unroll 1
+        for (int a0 = 0; a0 < CA; a0 += G) {
+            float o[G];
+#pragma unroll
+            for (int a = 0; a < G; ++a) {
+                float acc = 0.f;
+#pragma unroll
+                for (int k = 0; k < KK; k += 4) {
+                    const float4 w = *reinterpret_cast<const float4*>(wsm + (a0 + a) * KK + k);
+                    acc += in[k] * w.x + in[k + 1] * w.y + in[k + 2] * w.z + in[k + 3] * w.w;
+                }
+                o[a] = acc;
+            }
+            if (epi == SRGAN_EPI_BIAS_ACT) {
+#pragma unroll
+                for (int a = 0; a < G; ++a) {
+                    float v = o[a];
+                    if (bias) v += bias[bias_mod ? (a0 + a) % bias_mod : (a0 + a)];
+                    o[a] = act_fwd(v, act, slope);
+                }
+            } else if (href && act != SRGAN_ACT_NONE) {
+                float h[G];
+                ld_run<T, G>(href + pix * CA + a0, h);
+#pragma unroll
+                for (int a = 0; a < G; ++a) o[a] *= act_bwd(h[a], act, slope);
+            }
+            st_run<T, G>(out + pix * CA + a0, o);
+        }
+    }
+}
+
+// up: L[2oh+r, 2ow+s, b] = epi(sum_a S[pix, a] * Wu[b][r][s][a])
+template <typename T, int CA, int CB>
+__global__ void __launch_bounds__(128) patch_up_kernel(const T* __restrict__ S, const T* __restrict__ Wu, T* __restrict__ out,
+                                                       const float* __restrict__ bias, int bias_mod, const T* __restrict__ href,
+                                                       int epi, int act, float slope, ConvP p) {
+    __shared__ __align__(16) float wsm[4 * CB * CA];              // [(r, s, b)][a]
+    for (int i = threadIdx.x; i < 4 * CB * CA; i += blockDim.x) {
+        const int a = i % CA, q = i / CA, b = q % CB, rs = q / CB;        // q = (r*2+s)*CB + b
+        wsm[i] = to_f(Wu[(b * 4 + rs) * CA + a]);
+    }
+    __syncthreads();
+    const long long total = (long long)p.n * p.Hs * p.Ws;
+    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
+        const int ow = (int)(pix % p.Ws);
+        const long long t = pix / p.Ws;
+        const int oh = (int)(t % p.Hs);
+        const long long b = t / p.Hs;
+        float sv[CA];
+        ld_run<T, CA>(S + pix * CA, sv);
+        constexpr int G = 2 * CB < 8 ? 2 * CB : 8;               // outputs per group: 8 of the 2*CB-long (s, b) run
+#pragma unroll 1
+        for (int rq = 0; rq < 4 * CB; rq += G) {                  // rq = r * 2*CB + q0
+            const int r = rq / (2 * CB), q0 = rq - r * 2 * CB;
+            const long long o0 = ((b * p.Hl + 2 * oh + r) * p.Wl + 2 * ow) * CB + q0;
+            float o[G];
+#pragma unroll
+            for (int q = 0; q < G; ++q) {
+                float acc = 0.f;
+#pragma unroll
+                for (int a = 0; a < CA; a += 4) {
+                    const float4 w = *reinterpret_cast<const float4*>(wsm + (rq + q) * CA + a);
+                    acc += sv[a] * w.x + sv[a + 1] * w.y + sv[a + 2] * w.z + sv[a + 3] * w.w;
+                }
+                o[q] = acc;
+            }
+            if (epi == SRGAN_EPI_BIAS_ACT) {
+#pragma unroll
+                for (int q = 0; q < G; ++q) {
+                    float v = o[q];
+                    const int bc = (q0 + q) % CB;
+                    if (bias) v += bias[bias_mod ? bc % bias_mod : bc];
+                    o[q] = act_fwd(v, act, slope);
+                }
+            } else if (href && act != SRGAN_ACT_NONE) {
+                float h[G];
+                ld_run<T, G>(href + o0, h);
+#pragma unroll
+                for (int q = 0; q < G; ++q) o[q] *= act_bwd(h[q], act, slope);
+            }
+            st_run<T, G>(out + o0, o);
+        }
+    }
+}
+
+static bool patch_eligible(const srgan_geom* g, int n) {
+    return g->R == 2 && g->S == 2 && g->stride == 2 && g->pad == 0 && g->Hl == 2 * g->Hs && g->Wl == 2 * g->Ws &&
+           (long long)n * g->Hs * g->Ws >= 4096 &&
+           ((g->Ca == 8 && g->Cb == 1) || (g->Ca == 16 && g->Cb == 8) || (g->Ca == 32 && g->Cb == 16));
+}
+
+template <typename T>
+static int launch_patch(int mode, const T* src, const T* W, T* out, int n, const srgan_geom* g, const float* bias, int bias_mod,
+                        const T* href, int epi, int act, float slope, cudaStream_t st) {
+    ConvP p{n, g->Hs, g->Ws, g->Ca, g->Hl, g->Wl, g->Cb, g->R, g->S, g->stride, g->pad};
+    const long long total = (long long)n * g->Hs * g->Ws;
+    long long blocks = (total + 127) / 128;
+    if (blocks > 16LL * kNumSMs) blocks = 16LL * kNumSMs;
+    const unsigned grid = (unsigned)blocks;
+#define PATCH_CASE(CA_, CB_)                                                                                               \
+    if (g->Ca == CA_ && g->Cb == CB_) {                                                                                    \
+        if (mode == 0) patch_down_kernel<T, CA_, CB_><<<grid, 128, 0, st>>>(src, W, out, bias, bias_mod, href, epi, act, slope, p); \
+        else patch_up_kernel<T, CA_, CB_><<<grid, 128, 0, st>>>(src, W, out, bias, bias_mod, href, epi, act, slope, p);    \
+    }
+    PATCH_CASE(8, 1) else PATCH_CASE(16, 8) else PATCH_CASE(32, 16)
+#undef PATCH_CASE
+    SRGAN_CHECK_LAUNCH("patch_conv_kernel");
+    return SRGAN_OK;
+}
+
 int simt_conv(int mode, const void* src, const void* W, void* out, int n, const srgan_geom* g, const float* bias,
               int bias_mod, const void* href, int epi, int act, float slope, int dtype, cudaStream_t st) {
+    if (patch_eligible(g, n) && !(mode == 1 && g->Cb == 1)) {       // (8, 1) up: the few-channel direct kernel below
+        if (dtype == SRGAN_F32)
+            return launch_patch<float>(mode, (const float*)src, (const float*)W, (float*)out, n, g, bias, bias_mod,
+                                       (const float*)href, epi, act, slope, st);
+        return launch_patch<bf16>(mode, (const bf16*)src, (const bf16*)W, (bf16*)out, n, g, bias, bias_mod, (const bf16*)href,
+                                  epi, act, slope, st);
+    }
     if (direct_up_eligible(mode, g, n)) {
         if (dtype == SRGAN_F32)
             return launch_direct_up<float>((const float*)src, (const float*)W, (float*)out, n, g, bias, bias_mod, (const float*)href,

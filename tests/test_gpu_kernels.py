@@ -98,6 +98,37 @@ def test_conv_down_up_wgrad(ops, dt, gi):
 
 
 @pytest.mark.parametrize('dt', DT)
+@pytest.mark.parametrize('ca,cb', [(8, 1), (16, 8), (32, 16)])
+def test_patch_convs(ops, dt, ca, cb):
+    """The crowd MapModule convs (kernel = stride = 2, crowd/models.py:770-776) and their data gradients at a pixel count that
+    takes the one-thread-per-pixel patch kernels (simt_conv.cu), every epilogue."""
+    g = Geom(24, 20, ca, 48, 40, cb, 2, 2, 2, 0)
+    gen = torch.Generator().manual_seed(ca)
+    n = 9
+    ref = TorchOps()
+    L = rnd(gen, n * g.Hl * g.Wl * g.Cb, dt=dt)
+    S = rnd(gen, n * g.Hs * g.Ws * g.Ca, dt=dt)
+    Wd = (rnd(gen, g.Ca * g.R * g.S * g.Cb) * 0.3).to(dt)
+    Wu = Wd.view(g.Ca, g.R, g.S, g.Cb).permute(3, 1, 2, 0).contiguous().view(-1)
+    bias_a, bias_b = rnd(gen, g.Ca), rnd(gen, g.Cb)
+    for epi, act, slope in ((0, 1, 0.01), (0, 0, 0.0), (0, 2, 0.0), (1, 1, 0.01), (1, 2, 0.0), (1, 0, 0.0)):
+        href = rnd(gen, S.numel(), dt=dt)
+        out_ref = torch.empty_like(S)
+        ref.conv_down(L, Wd, out_ref, n, g, bias_a if epi == 0 else None, 0, href if epi == 1 else None, epi, act, slope)
+        out = torch.empty_like(S, device='cuda')
+        ops.conv_down(L.cuda(), Wd.cuda(), out, n, g, bias_a.cuda() if epi == 0 else None, 0,
+                      href.cuda() if epi == 1 else None, epi, act, slope)
+        close(out, out_ref, tol(dt), f'patch down epi{epi} act{act}')
+        href = rnd(gen, L.numel(), dt=dt)
+        out_ref = torch.empty_like(L)
+        ref.conv_up(S, Wu, out_ref, n, g, bias_b if epi == 0 else None, 0, href if epi == 1 else None, epi, act, slope)
+        out = torch.empty_like(L, device='cuda')
+        ops.conv_up(S.cuda(), Wu.cuda(), out, n, g, bias_b.cuda() if epi == 0 else None, 0,
+                    href.cuda() if epi == 1 else None, epi, act, slope)
+        close(out, out_ref, tol(dt), f'patch up epi{epi} act{act}')
+
+
+@pytest.mark.parametrize('dt', DT)
 def test_bias_mod_epilogue(ops, dt):
     g = Geom(1, 1, 4 * 4 * 8, 1, 1, 16, 1, 1, 1, 0)      # fc_up style: bias per channel, broadcast over 16 taps
     gen = torch.Generator().manual_seed(3)
