@@ -852,8 +852,10 @@ inline Ew2d ew2d_plan(long long rows, int C, int W, dim3& grid, int unroll = EW_
     long long want = (long long)kNumSMs * blocks_per_sm * EW_WAVES / gx;
     if (want < 1) want = 1;
     long long rpb = (rows + want - 1) / want;
-    rpb = (rpb + unit - 1) / unit * unit;
-    if (rpb < 2 * unit) rpb = 2 * unit;
+    // whole batches per row lane when the launch is big enough to fill the GPU that way; small launches (narrow concat
+    // slices, the 7x7 stage) keep all their parallelism instead: down to one row per thread
+    if (rpb >= unit) rpb = (rpb + unit - 1) / unit * unit;
+    else rpb = (rpb + rstep - 1) / rstep * rstep;
     grid = dim3((unsigned)gx, (unsigned)((rows + rpb - 1) / rpb));
     return Ew2d{lg, rpb};
 }

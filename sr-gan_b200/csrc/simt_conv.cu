@@ -678,6 +678,98 @@ __global__ void __launch_bounds__(256) direct_wgrad_small_kernel(const T* __rest
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// wgrad of the patch convolutions (kernel = stride = 2, pad 0; MapModule conv2 / conv3):
+//   dW[a][(r,s,b)] += sum_pix S[pix, a] * L[patch(pix), (r,s,b)]          CA x 4*CB outputs (512 / 2048), K = pixels.
+// A CTA walks its pixel range in chunks of 64 staged in shared memory as fp32 (the next chunk's global loads are in
+// flight while the current one is multiplied); thread (aq, kq) owns a TA x TK block of outputs; fp32 atomics at the end.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, int CA, int CB>
+__global__ void __launch_bounds__(256) patch_wgrad_kernel(const T* __restrict__ Ssrc, const T* __restrict__ Lsrc,
+                                                          float* __restrict__ dW, ConvP p, long long pix_per_block) {
+    constexpr int KK = 4 * CB, PC = 64;
+    constexpr int TK = KK / 16, TA = CA / 16;                     // 16 x 16 threads over (a, k)
+    static_assert(TK >= 1 && TA >= 1 && TK * 16 == KK && TA * 16 == CA, "patch_wgrad tile");
+    __shared__ __align__(16) float Ss[PC][CA];
+    __shared__ __align__(16) float Ls[PC][KK];
+    const long long total = (long long)p.n * p.Hs * p.Ws;
+    const long long p0 = (long long)blockIdx.x * pix_per_block;
+    const long long p1 = p0 + pix_per_block < total ? p0 + pix_per_block : total;
+    const int t = threadIdx.x;
+    const int kq = t & 15, aq = t >> 4;
+    float acc[TA][TK];
+#pragma unroll
+    for (int i = 0; i < TA; ++i)
+#pragma unroll
+        for (int j = 0; j < TK; ++j) acc[i][j] = 0.f;
+    // loader roles: threads 0..127 = one (pixel, patch row r) run of 2*CB elements of L; threads 128..191 = one S row
+    float lrun[2 * CB], srow[CA];
+    auto fetch = [&](long long base) {
+        if (t < 2 * PC) {
+            const long long pix = base + (t >> 1);
+#pragma unroll
+            for (int i = 0; i < 2 * CB; ++i) lrun[i] = 0.f;
+            if (pix < p1) {
+                const int ow = (int)(pix % p.Ws);
+                const long long q = pix / p.Ws;
+                const int oh = (int)(q % p.Hs);
+                const long long b = q / p.Hs;
+                ld_run<T, 2 * CB>(Lsrc + ((b * p.Hl + 2 * oh + (t & 1)) * p.Wl + 2 * ow) * CB, lrun);
+            }
+        } else if (t < 3 * PC) {
+            const long long pix = base + (t - 2 * PC);
+#pragma unroll
+            for (int i = 0; i < CA; ++i) srow[i] = 0.f;
+            if (pix < p1) ld_run<T, CA>(Ssrc + pix * CA, srow);
+        }
+    };
+    if (p0 < p1) fetch(p0);
+    for (long long base = p0; base < p1; base += PC) {
+        if (t < 2 * PC) {
+#pragma unroll
+            for (int i = 0; i < 2 * CB; i += 4)
+                *reinterpret_cast<float4*>(&Ls[t >> 1][(t & 1) * 2 * CB + i]) = make_float4(lrun[i], lrun[(i + 1) % (2 * CB)], lrun[(i + 2) % (2 * CB)], lrun[(i + 3) % (2 * CB)]);
+        } else if (t < 3 * PC) {
+#pragma unroll
+            for (int i = 0; i < CA; i += 4)
+                *reinterpret_cast<float4*>(&Ss[t - 2 * PC][i]) = make_float4(srow[i], srow[i + 1], srow[i + 2], srow[i + 3]);
+        }
+        __syncthreads();
+        if (base + PC < p1) fetch(base + PC);
+#pragma unroll 8
+        for (int pp = 0; pp < PC; ++pp) {
+            float sv[TA], lv[TK];
+#pragma unroll
+            for (int i = 0; i < TA; ++i) sv[i] = Ss[pp][aq * TA + i];
+#pragma unroll
+            for (int j = 0; j < TK; ++j) lv[j] = Ls[pp][kq * TK + j];
+#pragma unroll
+            for (int i = 0; i < TA; ++i)
+#pragma unroll
+                for (int j = 0; j < TK; ++j) acc[i][j] = fmaf(sv[i], lv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < TA; ++i)
+#pragma unroll
+        for (int j = 0; j < TK; ++j) atomicAdd(dW + (aq * TA + i) * KK + kq * TK + j, acc[i][j]);
+}
+
+template <typename T>
+static int launch_patch_wgrad(const T* S, const T* L, float* dW, int n, const srgan_geom* g, cudaStream_t st) {
+    ConvP p{n, g->Hs, g->Ws, g->Ca, g->Hl, g->Wl, g->Cb, g->R, g->S, g->stride, g->pad};
+    const long long total = (long long)n * g->Hs * g->Ws;
+    long long blocks = 4LL * kNumSMs;
+    long long ppb = (total + blocks - 1) / blocks;
+    ppb = (ppb + 63) / 64 * 64;
+    blocks = (total + ppb - 1) / ppb;
+    if (g->Ca == 16 && g->Cb == 8) patch_wgrad_kernel<T, 16, 8><<<(unsigned)blocks, 256, 0, st>>>(S, L, dW, p, ppb);
+    else patch_wgrad_kernel<T, 32, 16><<<(unsigned)blocks, 256, 0, st>>>(S, L, dW, p, ppb);
+    SRGAN_CHECK_LAUNCH("patch_wgrad_kernel");
+    return SRGAN_OK;
+}
+
 int simt_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, int dtype, cudaStream_t st) {
     if (g->Ca == 8 && g->R == 2 && g->S == 2 && g->Cb == 1 && (long long)n * g->Hs * g->Ws >= 512) {
         ConvP p{n, g->Hs, g->Ws, g->Ca, g->Hl, g->Wl, g->Cb, g->R, g->S, g->stride, g->pad};
@@ -686,6 +778,10 @@ int simt_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom*
         else direct_wgrad_small_kernel<bf16, 8, 2, 2, 1><<<grid, 256, 0, st>>>((const bf16*)S, (const bf16*)L, dW, p);
         SRGAN_CHECK_LAUNCH("direct_wgrad_small_kernel");
         return SRGAN_OK;
+    }
+    if (patch_eligible(g, n) && g->Cb >= 8) {
+        if (dtype == SRGAN_F32) return launch_patch_wgrad<float>((const float*)S, (const float*)L, dW, n, g, st);
+        return launch_patch_wgrad<bf16>((const bf16*)S, (const bf16*)L, dW, n, g, st);
     }
     if (dtype == SRGAN_F32) return launch_wgrad<float>((const float*)S, (const float*)L, dW, n, g, st);
     return launch_wgrad<bf16>((const bf16*)S, (const bf16*)L, dW, n, g, st);

@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(PC_THREADS, 1) umma_conv_persistent_kernel(con
 #pragma unroll
                         for (int it = 0; it < 4; ++it) {
                             hreg[i][jj][it] = make_uint4(0u, 0u, 0u, 0u);
-                            if (j < BN / 32 && o_t[i][it] >= 0)
+                            if (j < BN / 32 && c0 + j * 32 < p.Cout && o_t[i][it] >= 0)
                                 hreg[i][jj][it] = __ldg(reinterpret_cast<const uint4*>(p.href + o_t[i][it] + j * 32 + t_unit * 8));
                         }
                     }
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(PC_THREADS, 1) umma_conv_persistent_kernel(con
 #pragma unroll
                 for (int jj = 0; jj < NCH; ++jj) {
                     const int j = half + 2 * jj;
-                    if (j >= BN / 32) continue;               // warp-uniform
+                    if (j >= BN / 32 || c0 + j * 32 >= p.Cout) continue;      // warp-uniform; partial last N tile
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + i * BN + j * 32, v);
                     uint4 hv[4];
@@ -737,6 +737,10 @@ int umma_conv(int mode, const void* src, const void* W, void* out, int n, const 
     if (Cin % KCH != 0) return 0;
     int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 0));
     if (BN == 0) return 0;
+    // Cout = 64 (mod 128) with three or more 64-wide tiles (the DenseNet trunk's 1x1 data gradients: every second concat
+    // width): 256-wide tiles with a partial last one instead -- the weight rows beyond Cout are TMA zero fill and the
+    // epilogue skips their 32-column chunks -- so the A operand is re-read from L2 Cout/256 instead of Cout/64 times
+    if (BN == 64 && Cout >= 192) BN = 256;
     int Hm, Wm, phases = 1;
     if (mode == 0) { Hm = g->Hs; Wm = g->Ws; }
     else {
@@ -770,7 +774,7 @@ int umma_conv(int mode, const void* src, const void* W, void* out, int n, const 
         UmmaConvParamsP pp;
         pp.c = p;
         pp.m_subtiles = (int)mtiles;
-        pp.n_tiles = Cout / BN;
+        pp.n_tiles = (Cout + BN - 1) / BN;
         // 256-row CTA tiles (two M sub-tiles share every weight tile) unless the wave quantisation on 148 persistent CTAs
         // makes 128-row tiles finish sooner: time ~ rounds x rows per tile
         int MT = (BN <= 128 && mtiles % 2 == 0) ? 2 : 1;

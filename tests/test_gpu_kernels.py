@@ -126,6 +126,11 @@ def test_patch_convs(ops, dt, ca, cb):
         ops.conv_up(S.cuda(), Wu.cuda(), out, n, g, bias_b.cuda() if epi == 0 else None, 0,
                     href.cuda() if epi == 1 else None, epi, act, slope)
         close(out, out_ref, tol(dt), f'patch up epi{epi} act{act}')
+    dW_ref = rnd(gen, Wd.numel())
+    dW = dW_ref.clone().cuda()
+    ref.conv_wgrad(S, L, dW_ref, n, g)
+    ops.conv_wgrad(S.cuda(), L.cuda(), dW, n, g)
+    close(dW, dW_ref, tol(dt) * 2, 'patch wgrad')
 
 
 @pytest.mark.parametrize('dt', DT)
