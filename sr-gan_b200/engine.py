@@ -186,6 +186,13 @@ class Engine:
         # scratch-buffer scope: the DNN step ('dnn') and the GAN step ('gan') never share a workspace buffer, so the two
         # step methods may be in flight at the same time on different streams (StepRunner overlaps them)
         self._scope = 'gan'
+        # graph nets: the weight-gradient kernels of a backward pass (conv wgrad, bias sums, the tangent block's BatchNorm
+        # scale gradients) are off the critical path -- nothing reads the flat gradient buffer before the optimizer -- so
+        # they are enqueued on a side stream (one per scratch scope), forked after the op that produced their delta and
+        # joined at the end of the pass.  The crowd data path is a chain of small kernels that under-fill the GPU.
+        import os
+        self.wgrad_side_stream = self.device.type == 'cuda' and os.environ.get('SRGAN_NO_WGRAD_STREAM', '0') != '1'
+        self._wg_streams = {}
         self._probe = None
         for st in (self.D, self.G, self.DNN):
             if st is not None:
@@ -547,6 +554,25 @@ class Engine:
         for name, b in net.bufs.items():
             if b.accumulate:
                 R(deltas[name], b, lo, hi).zero_()
+        side = None
+        if weight_grads and self.wgrad_side_stream and hasattr(ops, 'use_stream'):
+            side = self._wg_streams.get(self._scope)
+            if side is None:
+                side = self._wg_streams[self._scope] = torch.cuda.Stream(self.device)
+
+        def off_path(fn):
+            """fn() enqueues weight-gradient kernels: on the side stream, after everything enqueued so far."""
+            if side is None:
+                fn()
+                return
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            side.wait_event(ev)
+            prev = ops.use_stream(side)
+            try:
+                fn()
+            finally:
+                ops.restore_stream(prev)
         for op in reversed(net.graph):
             sb, db = net.bufs[op.src], net.bufs[op.dst]
             dy = R(deltas[op.dst], db, lo, hi)
@@ -558,10 +584,15 @@ class Engine:
             if op.kind == 'conv':
                 l = op.layer
                 if weight_grads:
-                    self._wgrad_layer(st, l, R(acts[op.src], sb, wlo, whi), R(deltas[op.dst], db, wlo, whi),
-                                      (whi - wlo) * l.gemm_rows, lo=wlo)
-                    if l.has_bias:
-                        self._bias_grad(st, l, dy, n * db.rows)
+                    def wg(l=l, op=op, sb=sb, db=db, dy=dy):
+                        self._wgrad_layer(st, l, R(acts[op.src], sb, wlo, whi), R(deltas[op.dst], db, wlo, whi),
+                                          (whi - wlo) * l.gemm_rows, lo=wlo)
+                        if l.has_bias:
+                            self._bias_grad(st, l, dy, n * db.rows)
+                    if l.name in st.thin and l.fwd != 'down':      # its im2col output is reused by the data gradient below
+                        wg()
+                    else:
+                        off_path(wg)
                 if is_input:
                     if input_grad is not None:
                         dinput, ihref, iact = input_grad
@@ -575,8 +606,9 @@ class Engine:
                     ops.affine_bwd_grad(dy, db.ch, xa, dx, sb.ch, op.c0, n * sb.rows, op.C, P[nm + '.weight'], mean, var,
                                         self.BN_EPS, st.g(nm + '.weight'), st.g(nm + '.bias'), sb.accumulate)
                     if whi > hi:
-                        ops.affine_grad(R(deltas[op.dst], db, hi, whi), db.ch, R(acts[op.src], sb, hi, whi), sb.ch, op.c0,
-                                        (whi - hi) * sb.rows, op.C, mean, var, self.BN_EPS, st.g(nm + '.weight'), None, False)
+                        off_path(lambda op=op, sb=sb, db=db, nm=nm, mean=mean, var=var: ops.affine_grad(
+                            R(deltas[op.dst], db, hi, whi), db.ch, R(acts[op.src], sb, hi, whi), sb.ch, op.c0,
+                            (whi - hi) * sb.rows, op.C, mean, var, self.BN_EPS, st.g(nm + '.weight'), None, False))
                 else:
                     ops.affine_bwd(dy, db.ch, dx, sb.ch, op.c0, n * sb.rows, op.C, P[nm + '.weight'], var, self.BN_EPS,
                                    sb.accumulate)
@@ -595,6 +627,10 @@ class Engine:
                 ops.depth_to_space(dy, dx, n, op.H, op.W, op.k, True)
             else:
                 raise ValueError(op.kind)
+        if side is not None:                  # join: the optimizer (or the gradient all-reduce) follows
+            ev = torch.cuda.Event()
+            ev.record(side)
+            torch.cuda.current_stream(self.device).wait_event(ev)
 
     # ------------------------------------------------------------------ Adam
     def adam(self, st: NetState, lr, weight_decay, betas=(0.9, 0.999), eps=1e-8, deferrable=None):

@@ -135,6 +135,14 @@ class CudaOps:
         ~10 us, once per kernel launch it was 40 % of the host time of a step)."""
         self._stream_handle = torch.cuda.current_stream(self.device).cuda_stream
 
+    def use_stream(self, stream):
+        """Directs the following launches to `stream` (a torch.cuda.Stream); returns the previous handle for restore_stream."""
+        prev, self._stream_handle = self._stream_handle, stream.cuda_stream
+        return prev
+
+    def restore_stream(self, handle):
+        self._stream_handle = handle
+
     def _stream(self):
         h = self._stream_handle
         if h is None:
