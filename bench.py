@@ -52,8 +52,9 @@ WORKLOADS = {
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the probed kernel per launch, from one `ncu --set full` capture of exactly that
-# launch (profiles/r1_ncu_full_summary.txt: D layer-2 fprop over 400 samples; algorithmic bytes 315 MB = input 210 + output 105)
-NCU_TRAFFIC_BYTES = {('age', 100): 279.16e6}
+# launch (profiles/r1_final_ncu_full_summary.txt: D layer-2 fprop over 400 samples, read 210.1 + write 75.5 MB; algorithmic bytes
+# 315 MB = input 210 + output 105: part of the output is still in L2 when the kernel ends)
+NCU_TRAFFIC_BYTES = {('age', 100): 285.57e6}
 
 
 def workload_string(name, B, world):
@@ -379,12 +380,24 @@ def main():
                 'timing': 'CUDA events around each launch during K eager steps run right after the timed region (the timed region replays CUDA graphs)' if graphed else 'CUDA events around each launch inside the timed region'}
         roof['traffic'] = NCU_TRAFFIC_BYTES.get((name, B))
         if roof['traffic'] is not None:
-            roof['traffic_source'] = 'profiles/r1_ncu_full_summary.txt (one ncu --set full capture of this launch)'
+            roof['traffic_source'] = 'profiles/r1_final_ncu_full_summary.txt (one ncu --set full capture of this launch)'
         if probe.get('count'):
             avg_ms = probe['ms'] / probe['count']
             roof['achieved'] = flops_launch / (avg_ms * 1e-3) / 1e12
             roof['frac'] = roof['achieved'] / roof['peak']
             roof['avg_launch_ms'] = avg_ms
+            # which roofline binds this launch: arithmetic intensity (algorithmic FLOP / algorithmic byte: input, output
+            # and weights moved once) against the ridge of the two measured peaks.  The age layer-2 conv (AI ~ 680) is
+            # tensor-bound; the crowd trunk's 1x1 GEMMs (N = 128: AI ~ 170 and less) are HBM-bound.
+            by = probe.get('bytes_per_launch', 0)
+            if by and args.precision == 'bf16':
+                ai, ridge = flops_launch / by, pk['bf16_tflops_sustained'] * 1e12 / (pk['hbm_gbs'] * 1e9)
+                roof['arithmetic_intensity'], roof['ridge'] = ai, ridge
+                roof['tensor_tflops'] = roof['achieved']
+                if ai < ridge:
+                    gbs = by / (avg_ms * 1e-3) / 1e9
+                    roof.update({'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / pk['hbm_gbs'],
+                                 'peak_source': f'{pk_kind} (HBM copy bandwidth)', 'algorithmic_bytes_per_launch': by})
         step_tflops = wl['flops_per_sample'] * B * world / (ms_per_step * 1e-3) / 1e12
         line = {'metric': METRIC, 'value': value, 'unit': 'steps/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',

@@ -325,7 +325,10 @@ class Engine:
         ms = sum(a.elapsed_time(b) for a, b in pr['events'])
         l = pr['layer']
         d = l.master_dims
+        g = l.geom
+        elems = pr['rows'] * (g.Hl * g.Wl * g.Cb + g.Hs * g.Ws * g.Ca) + g.Ca * g.R * g.S * g.Cb      # in + out + weights, once each
         return {'count': len(pr['events']), 'ms': ms, 'macs_per_sample': l.macs_per_sample,
+                'bytes_per_launch': elems * (2 if self.act_dtype == torch.bfloat16 else 4),
                 'kernel': f'D {l.name} forward conv ({d[1]}->{d[0]} k{l.geom.R} s{l.geom.stride}) over {pr["samples"]} samples'}
 
     def _bwd_data_layer(self, st: NetState, l: Layer, dy, dx, n, href, act, slope, lo=0, col_ready=False):
