@@ -26,6 +26,8 @@ from __future__ import annotations
 import math
 from typing import Dict, List, Optional
 
+import itertools
+
 import torch
 
 from .nets import Net, Layer, ACT_NONE, ACT_LEAKY, ACT_TANH
@@ -193,6 +195,12 @@ class Engine:
         import os
         self.wgrad_side_stream = self.device.type == 'cuda' and os.environ.get('SRGAN_NO_WGRAD_STREAM', '0') != '1'
         self._wg_streams = {}
+        # graph nets: side branches (the three crowd MapModules: ~10 launches each, hanging off cat2..cat4 and ending in
+        # `features`) run on their own streams, concurrently with the trunk: forward = forked when their tap is written,
+        # joined at the end of the pass; backward = forked at the start, joined before the trunk first adds into the
+        # tapped concat delta
+        self.branch_streams = self.device.type == 'cuda' and os.environ.get('SRGAN_NO_BRANCH_STREAMS', '0') != '1'
+        self._br_streams = {}
         self._probe = None
         for st in (self.D, self.G, self.DNN):
             if st is not None:
@@ -508,7 +516,52 @@ class Engine:
         stored activations of rows [mlo, mlo+n)) of a graph net over sample rows [lo,hi)."""
         net, ops, R, P = st.net, self.ops, self._brows, st.params
         n = hi - lo
+        streams = self._branch_streams_for(net)
+        main = torch.cuda.current_stream(self.device) if streams else None
+        tap_ev, done = {}, []
+        taps = net.branch_taps() if streams else ()
+        for branch, run in itertools.groupby(net.graph, key=lambda o: o.branch):
+            run = list(run)
+            if not streams or branch == 0:
+                for op in run:
+                    self._graph_forward_op(st, acts, op, lo, hi, n, tangent, mlo)
+                    if streams and op.dst in taps and op.dst not in tap_ev:      # first writer of a tapped buffer (the pool)
+                        ev = torch.cuda.Event()
+                        ev.record(main)
+                        tap_ev[op.dst] = ev
+                continue
+            s = streams[branch]
+            for name in {op.src for op in run} & set(taps):
+                if name in tap_ev:
+                    s.wait_event(tap_ev[name])
+                else:
+                    s.wait_stream(main)
+            with torch.cuda.stream(s):
+                prev = ops.use_stream(s)
+                try:
+                    for op in run:
+                        self._graph_forward_op(st, acts, op, lo, hi, n, tangent, mlo)
+                finally:
+                    ops.restore_stream(prev)
+                ev = torch.cuda.Event()
+                ev.record(s)
+                done.append(ev)
+        for ev in done:
+            main.wait_event(ev)
+
+    def _branch_streams_for(self, net: Net):
+        """{branch id: stream} of the current scratch scope, or None when side branches run inline."""
+        if not (self.branch_streams and hasattr(self.ops, 'use_stream')) or not any(op.branch for op in net.graph):
+            return None
+        d = self._br_streams.setdefault(self._scope, {})
         for op in net.graph:
+            if op.branch and op.branch not in d:
+                d[op.branch] = torch.cuda.Stream(self.device)
+        return d
+
+    def _graph_forward_op(self, st: NetState, acts, op, lo, hi, n, tangent, mlo):
+        net, ops, R, P = st.net, self.ops, self._brows, st.params
+        if True:
             sb, db = net.bufs[op.src], net.bufs[op.dst]
             x, y = R(acts[op.src], sb, lo, hi), R(acts[op.dst], db, lo, hi)
             href = R(acts[op.dst], db, mlo, mlo + n) if tangent else None
@@ -576,7 +629,7 @@ class Engine:
                 fn()
             finally:
                 ops.restore_stream(prev)
-        for op in reversed(net.graph):
+        def one(op):
             sb, db = net.bufs[op.src], net.bufs[op.dst]
             dy = R(deltas[op.dst], db, lo, hi)
             is_input = op.src == net.input_buf
@@ -630,6 +683,34 @@ class Engine:
                 ops.depth_to_space(dy, dx, n, op.H, op.W, op.k, True)
             else:
                 raise ValueError(op.kind)
+
+        streams = self._branch_streams_for(net)
+        main = torch.cuda.current_stream(self.device) if streams else None
+        taps = net.branch_taps() if streams else ()
+        pending = {}                          # tapped concat buffer -> event: a branch still adds into its delta
+        for branch, run in itertools.groupby(reversed(net.graph), key=lambda o: o.branch):
+            run = list(run)
+            if not streams or branch == 0:
+                for op in run:
+                    if pending and op.src in pending:          # the trunk's first read-modify-write of that concat delta
+                        main.wait_event(pending.pop(op.src))
+                    one(op)
+                continue
+            s = streams[branch]
+            s.wait_stream(main)                                # the feature deltas / seeds enqueued so far
+            with torch.cuda.stream(s):
+                prev = ops.use_stream(s)
+                try:
+                    for op in run:
+                        one(op)
+                finally:
+                    ops.restore_stream(prev)
+                ev = torch.cuda.Event()
+                ev.record(s)
+            for name in {op.src for op in run} & set(taps):
+                pending[name] = ev
+        for ev in pending.values():
+            main.wait_event(ev)
         if side is not None:                  # join: the optimizer (or the gradient all-reduce) follows
             ev = torch.cuda.Event()
             ev.record(side)

@@ -152,6 +152,7 @@ class Op:
     k: int = 0
     stride: int = 0
     pad: int = 0
+    branch: int = 0                # 0 = trunk; i > 0 = side branch i (crowd MapModule i): reads a trunk buffer, ends in `features`
 
 
 @dataclass
@@ -196,6 +197,11 @@ class Net:
     @property
     def affines(self):
         return [op for op in (self.graph or []) if op.kind == 'affine']
+
+    def branch_taps(self):
+        """Trunk buffers read by side-branch ops (crowd: cat2..cat4, tapped by the MapModules)."""
+        trunk_made = {op.dst for op in self.graph if not op.branch} | {self.input_buf}
+        return {op.src for op in self.graph if op.branch and op.src in trunk_made}
 
     def parts(self):
         if self.head_parts is not None:
@@ -345,6 +351,7 @@ def knn_densenet_cat(block_config=(6, 12, 48, 32), growth_rate=32, num_init_feat
         if k * hi != L or L % 8:
             raise ValueError('label_size must be a multiple of the tap extents and of 8')
         pre = f'map_module{i}'
+        first_op = len(ops)
         buf(f't{i}', hi * hi, ci)
         ops.append(Op('read', cat, f't{i}', C=ci, c0=0))
         # ConvTranspose2d(ci, 1, k, stride k): a [pixels x ci] x [ci x k*k] GEMM (one scalar bias) + depth-to-space
@@ -365,6 +372,8 @@ def knn_densenet_cat(block_config=(6, 12, 48, 32), growth_rate=32, num_init_feat
         buf(f'h{i}', 1, 20, **LK)
         conv(pre + '.linear1', src, f'h{i}', Geom(1, 1, 20, hh, hh, 32, hh, hh, 1, 0), 'down', (20, 32, hh, hh), bias=True, **LK)
         ops.append(Op('copy', f'h{i}', 'features', C=20, c0=20 * (i - 1)))
+        for o in ops[first_op:]:          # an independent chain hanging off cat{i+1}: the engine may run it on its own stream
+            o.branch = i
     ops.append(Op('copy', 'fcf', 'features', C=20, c0=60))
     # (ops are in topological order: the trunk, then the count head, then the three MapModules, then the feature copies)
     head_parts = [(f'map_module{i}.count_layer', 20) for i in (1, 2, 3)] + [('count_layer', 20)]
