@@ -257,10 +257,11 @@ def test_gradient_penalty_kernels(ops, dt, rows, cols):
 
 @pytest.mark.parametrize('dims,kind', [((6, 5, 4, 4), 'conv'), ((72, 40, 4, 4), 'conv'), ((33, 50, 3, 3), 'conv'),
                                        ((128, 96, 1, 1), 'conv'), ((20, 9, 7, 7), 'conv'), ((24, 40, 8, 8), 'fc_up'),
-                                       ((64, 3, 4, 4), 'thin')])
+                                       ((64, 3, 4, 4), 'thin'), ((64, 64, 4, 4), 'conv'), ((96, 96, 3, 3), 'conv'),
+                                       ((128, 544, 1, 1), 'conv'), ((64, 32, 8, 8), 'fc_up')])
 def test_adam_and_repack(ops, dims, kind):
-    """dims[0]*dims[1]*... >= 4096 with both leading dims >= 8 takes the shared-memory tiled kernel (transposed layouts),
-    the rest the element-wise one; fc_up / thin are the other stride patterns engine.py produces."""
+    """Fused Adam + kernel-layout rewrite over the stride patterns engine.py produces (conv, fc_up, thin, the crowd trunk's
+    padded 1x1 layouts), small and large tensors."""
     gen = torch.Generator().manual_seed(9)
     ref = TorchOps()
     a, b, r, s = dims                        # master [a][b][r][s]
