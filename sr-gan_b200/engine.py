@@ -560,43 +560,43 @@ class Engine:
         return d
 
     def _graph_forward_op(self, st: NetState, acts, op, lo, hi, n, tangent, mlo):
+        """One op of graph_forward over sample rows [lo,hi) (n = hi - lo), on the current stream."""
         net, ops, R, P = st.net, self.ops, self._brows, st.params
-        if True:
-            sb, db = net.bufs[op.src], net.bufs[op.dst]
-            x, y = R(acts[op.src], sb, lo, hi), R(acts[op.dst], db, lo, hi)
-            href = R(acts[op.dst], db, mlo, mlo + n) if tangent else None
-            if op.kind == 'conv':
-                ng = n * op.layer.gemm_rows
-                if tangent:
-                    self._fwd_layer(st, op.layer, x, y, ng, bias=False, href=href, epi=EPI_DACT, lo=lo)
-                else:
-                    self._fwd_layer(st, op.layer, x, y, ng, lo=lo)
-            elif op.kind == 'affine':
-                nm = op.name
-                ops.affine(x, sb.ch, op.c0, y, db.ch, n * sb.rows, op.C, P[nm + '.weight'], P[nm + '.bias'],
-                           P[nm + '.running_mean'], P[nm + '.running_var'], self.BN_EPS, href, 1 if tangent else 0,
-                           db.act, db.slope)
-            elif op.kind == 'copy':
-                ops.copy2d(x, sb.ch, 0, y, db.ch, op.c0, n * sb.rows, op.C, False)
-            elif op.kind == 'read':
-                ops.copy2d(x, sb.ch, op.c0, y, db.ch, 0, n * sb.rows, op.C, False)
-            elif op.kind == 'maxpool':
-                # the forward records the winning window position per pooled element; the tangent pass routes by the map of
-                # the x_hat rows, the backward pass reads the map of its own rows
-                im = acts['idx:' + op.dst]
-                e = db.rows * op.C                  # index bytes per sample
-                if tangent:
-                    ops.maxpool(x, None, y, db.ch, op.c0, n, op.H, op.W, op.C, op.k, op.stride, op.pad,
-                                idx=im[mlo * e:(mlo + n) * e], idx_mode=2)
-                else:
-                    ops.maxpool(x, None, y, db.ch, op.c0, n, op.H, op.W, op.C, op.k, op.stride, op.pad,
-                                idx=im[lo * e:hi * e], idx_mode=1)
-            elif op.kind == 'avgpool':
-                ops.avgpool(x, sb.ch, y, db.ch, op.c0, n, op.H, op.W, op.C, op.k)
-            elif op.kind == 'shuffle':
-                ops.depth_to_space(x, y, n, op.H, op.W, op.k, False)
+        sb, db = net.bufs[op.src], net.bufs[op.dst]
+        x, y = R(acts[op.src], sb, lo, hi), R(acts[op.dst], db, lo, hi)
+        href = R(acts[op.dst], db, mlo, mlo + n) if tangent else None
+        if op.kind == 'conv':
+            ng = n * op.layer.gemm_rows
+            if tangent:
+                self._fwd_layer(st, op.layer, x, y, ng, bias=False, href=href, epi=EPI_DACT, lo=lo)
             else:
-                raise ValueError(op.kind)
+                self._fwd_layer(st, op.layer, x, y, ng, lo=lo)
+        elif op.kind == 'affine':
+            nm = op.name
+            ops.affine(x, sb.ch, op.c0, y, db.ch, n * sb.rows, op.C, P[nm + '.weight'], P[nm + '.bias'],
+                       P[nm + '.running_mean'], P[nm + '.running_var'], self.BN_EPS, href, 1 if tangent else 0,
+                       db.act, db.slope)
+        elif op.kind == 'copy':
+            ops.copy2d(x, sb.ch, 0, y, db.ch, op.c0, n * sb.rows, op.C, False)
+        elif op.kind == 'read':
+            ops.copy2d(x, sb.ch, op.c0, y, db.ch, 0, n * sb.rows, op.C, False)
+        elif op.kind == 'maxpool':
+            # the forward records the winning window position per pooled element; the tangent pass routes by the map of
+            # the x_hat rows, the backward pass reads the map of its own rows
+            im = acts['idx:' + op.dst]
+            e = db.rows * op.C                  # index bytes per sample
+            if tangent:
+                ops.maxpool(x, None, y, db.ch, op.c0, n, op.H, op.W, op.C, op.k, op.stride, op.pad,
+                            idx=im[mlo * e:(mlo + n) * e], idx_mode=2)
+            else:
+                ops.maxpool(x, None, y, db.ch, op.c0, n, op.H, op.W, op.C, op.k, op.stride, op.pad,
+                            idx=im[lo * e:hi * e], idx_mode=1)
+        elif op.kind == 'avgpool':
+            ops.avgpool(x, sb.ch, y, db.ch, op.c0, n, op.H, op.W, op.C, op.k)
+        elif op.kind == 'shuffle':
+            ops.depth_to_space(x, y, n, op.H, op.W, op.k, False)
+        else:
+            raise ValueError(op.kind)
 
     def graph_backward(self, st: NetState, acts, deltas, lo, hi, mlo, wlo, whi, weight_grads, input_grad, hook):
         """Reverse pass of a graph net over delta rows [lo,hi); the activations that provide masks and weight-gradient

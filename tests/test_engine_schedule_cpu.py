@@ -233,3 +233,51 @@ def test_micro_batched_step_is_exact_fp64(family):
         for k, v in params.items():
             if not O.is_buffer_key(k):
                 assert rel(mine.params[k], v) < 1e-8, (family, net, k, rel(mine.params[k], v))
+
+
+def test_dnn_and_gan_steps_use_disjoint_scratch_scopes():
+    """The DNN step may be in flight on its own stream while the GAN step runs (StepRunner._on_dnn_stream): the two step
+    methods must not share a single workspace buffer, and the DNN step allocates B rows, not the 5B-row D workspace."""
+    g = Golden('dcgan_mini')
+    dt = torch.float64
+    st, cfg = g.oracle_state(dt), g.step_config()
+    eng = build_engine(st, dt, g.cfg.get('image_size'), g.cfg.get('conv_dim'), g.cfg.get('z_dim'))
+    x, y, u, z, alpha, z2 = g.step_inputs(0, dt)
+    eng.dnn_step(x, y, cfg, O.dnn_lr(cfg, 0), cfg.weight_decay)
+    dnn_keys = set(eng._buf)
+    assert dnn_keys and all(k[0] == 'dnn' for k in dnn_keys)
+    eng.gan_step(x, y, u, z, alpha, z2, cfg)
+    gan_keys = set(eng._buf) - dnn_keys
+    assert gan_keys and all(k[0] == 'gan' for k in gan_keys)
+    ptrs = {}
+    for k, t in eng._buf.items():
+        ptrs.setdefault(t.untyped_storage().data_ptr(), []).append(k)
+    assert all(len(v) == 1 for v in ptrs.values()), 'two scratch keys share storage'
+    B = x.shape[0]
+    a_dnn, a_gan = eng._buf[('dnn', ('D', 'a', 1))], eng._buf[('gan', ('D', 'a', 1))]
+    assert a_gan.numel() == 5 * a_dnn.numel() and a_dnn.numel() == B * eng.d_net.layers[0].out_elems
+
+
+def test_crowd_graph_side_branches():
+    """nets.knn_densenet_cat marks the three MapModules as side branches: each is one contiguous run of ops that reads a
+    trunk concat buffer first and writes `features` last, and touches no buffer of another branch (Engine runs them on
+    their own streams, forked at the tap and joined before the trunk adds into the tapped concat delta)."""
+    net = nets.knn_densenet_cat(block_config=(2, 2, 2, 2), growth_rate=8, num_init_features=16, bn_size=2, image_size=64,
+                                label_size=64)
+    assert net.branch_taps() == {'cat2', 'cat3', 'cat4'}
+    runs = [(b, [op for op in net.graph if op.branch == b]) for b in (1, 2, 3)]
+    idx = {id(op): i for i, op in enumerate(net.graph)}
+    owned = {}
+    for b, ops_ in runs:
+        pos = [idx[id(op)] for op in ops_]
+        assert pos == list(range(pos[0], pos[0] + len(pos))), 'a branch is one contiguous run'
+        assert ops_[0].kind == 'read' and ops_[0].src == f'cat{b + 1}' and ops_[0].c0 == 0
+        assert ops_[-1].kind == 'copy' and ops_[-1].dst == 'features'
+        for op in ops_[1:]:
+            assert op.src not in net.branch_taps()
+        for op in ops_[:-1]:
+            assert owned.setdefault(op.dst, b) == b, 'a buffer written by two branches'
+    trunk_dsts = {op.dst for op in net.graph if not op.branch}
+    assert not (set(owned) & trunk_dsts), 'a branch writes a trunk buffer'
+    # the trunk never reads a branch buffer: the only meeting points are the tap (read) and `features`
+    assert not ({op.src for op in net.graph if not op.branch} & set(owned))
