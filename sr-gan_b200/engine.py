@@ -23,10 +23,10 @@ batch B:  acts[l] rows [0,B)=x  [B,2B)=u  [2B,3B)=fake  [3B,4B)=x_hat  [4B,5B)=t
 """
 from __future__ import annotations
 
-import math
-from typing import Dict, List, Optional
-
 import itertools
+import math
+import os
+from typing import Dict, List, Optional
 
 import torch
 
@@ -192,7 +192,6 @@ class Engine:
         # scale gradients) are off the critical path -- nothing reads the flat gradient buffer before the optimizer -- so
         # they are enqueued on a side stream (one per scratch scope), forked after the op that produced their delta and
         # joined at the end of the pass.  The crowd data path is a chain of small kernels that under-fill the GPU.
-        import os
         self.wgrad_side_stream = self.device.type == 'cuda' and os.environ.get('SRGAN_NO_WGRAD_STREAM', '0') != '1'
         self._wg_streams = {}
         # graph nets: side branches (the three crowd MapModules: ~10 launches each, hanging off cat2..cat4 and ending in
