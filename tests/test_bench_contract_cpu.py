@@ -1,0 +1,25 @@
+"""CPU: the reference arm of bench.py (`--impl reference`: the oracle port timed on the host cores) prints ONE JSON line with
+the keys the driver reads, on the metric / unit / config of the product arm.  The product arm itself needs a GPU."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_json_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--workload', 'coefficient',
+                          '--steps', '2', '--warmup', '3'], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['metric'] == 'SR-GAN train steps/sec' and d['unit'] == 'steps/s'
+    assert d['higher_is_better'] is True and d['n_gpus'] == 1 and d['steps'] == 2 and d['vs_baseline'] is None
+    assert d['value'] > 0 and abs(d['value'] - 1e3 / d['ms_per_step']) / d['value'] < 1e-6
+    assert 'coefficient SR-GAN' in d['config']['workload'] and 'model' not in d['config']
+    cb = d['cpu_baseline']
+    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and cb['sample']
+    e = d['e2e']
+    assert e['value'] == d['value'] and e['unit'] == d['unit'] and e['h2d_bytes_per_step'] == 0 and e['d2h_bytes_per_step'] == 0
