@@ -42,6 +42,10 @@ WORKLOADS = {
     # BASELINE configs[1] -- the N=1 workload of the default run (the metric's single-GPU configuration)
     'age': dict(batch=100, ref_batch=10, flops_per_sample=21 * 0.8305e9 + 4 * 0.8472e9, mult=(1e2, 1e1, 1e2),
                 desc='age SR-GAN (BASELINE configs[1]): DCGAN G/D, 3x128x128'),
+    # BASELINE configs[3]: the same DCGAN G/D (driving/models.py == age/models.py), steering-angle labels ~ N(0, 30 deg),
+    # run.py:36-44 multipliers, gradient penalty on (B = 100)
+    'driving': dict(batch=100, ref_batch=10, flops_per_sample=21 * 0.8305e9 + 4 * 0.8472e9, mult=(1e2, 1e1, 1e2),
+                    desc='driving SR-GAN (BASELINE configs[3]): DCGAN G/D, 3x128x128, steering-angle labels'),
     # BASELINE configs[2]: DCGenerator + KnnDenseNetCat (DenseNet-201) at 224x224, run.py:57-68 multipliers
     'crowd': dict(batch=64, ref_batch=2, flops_per_sample=21 * 8.732e9 + 4 * 2.595e9, mult=(1e3, 1e2, 1e2),
                   desc='crowd SR-GAN (BASELINE configs[2]): DCGenerator + KnnDenseNetCat (DenseNet-201), 3x224x224'),
@@ -54,7 +58,7 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum of the probed kernel per launch, from one `ncu --set full` capture of exactly that
 # launch (profiles/r1_final_ncu_full_summary.txt: D layer-2 fprop over 400 samples, read 210.1 + write 75.5 MB; algorithmic bytes
 # 315 MB = input 210 + output 105: part of the output is still in L2 when the kernel ends)
-NCU_TRAFFIC_BYTES = {('age', 100): 285.57e6}
+NCU_TRAFFIC_BYTES = {('age', 100): 285.57e6, ('driving', 100): 285.57e6}
 
 
 def workload_string(name, B, world):
@@ -119,9 +123,11 @@ def make_batches(name, B, seed):
     """(x, y, u) host tensors of one per-GPU batch of the workload; y is the crowd (density, map) pair for crowd."""
     import torch
     gen = torch.Generator().manual_seed(seed)
-    if name == 'age':
+    if name in ('age', 'driving'):
         x = torch.rand(B, 3, 128, 128, generator=gen) * 2 - 1
         u = torch.rand(B, 3, 128, 128, generator=gen) * 2 - 1
+        if name == 'driving':                 # steering angle in degrees
+            return x, torch.randn(B, generator=gen) * 30, u
         return x, torch.rand(B, generator=gen) * 85 + 10, u
     if name == 'crowd':                       # SURVEY 8d config 3
         x = torch.rand(B, 3, 224, 224, generator=gen) * 2 - 1
@@ -140,7 +146,7 @@ def oracle_setup(name, Bs):
     cfg = O.StepConfig(batch_size=Bs, matching_loss_multiplier=m, contrasting_loss_multiplier=c, gradient_penalty_multiplier=gp,
                        map_multiplier=1e-3)
     gen = torch.Generator().manual_seed(2)
-    if name == 'age':
+    if name in ('age', 'driving'):
         st = O.init_dcgan(seed=0, image_size=AGE['image'], conv_dim=AGE['conv_dim'], z_dim=AGE['z_dim'])
         zd, ashape = 256, (Bs, 1, 1, 1)
     elif name == 'crowd':
@@ -189,7 +195,7 @@ def cpu_baseline(name, full, budget_s=20.0):
     import torch
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    Bs = {'age': 20, 'crowd': 2, 'coefficient': 5000}[name]
+    Bs = {'age': 20, 'driving': 20, 'crowd': 2, 'coefficient': 5000}[name]
     O, st, cfg, inputs = oracle_setup(name, Bs)
     O.training_step(st, cfg, *inputs)                    # warm-up (thread pools, allocator)
     n, t0 = 0, time.perf_counter()
@@ -247,8 +253,8 @@ def main():
     s.map_multiplier = 1e-3
     s.precision = args.precision
     s.micro_batch = args.micro_batch
-    if name == 'age':
-        exp = srgan_b200.Experiment(s, 'age', device=dev, comm=comm, image_size=AGE['image'], conv_dim=AGE['conv_dim'], z_dim=AGE['z_dim'])
+    if name in ('age', 'driving'):
+        exp = srgan_b200.Experiment(s, name, device=dev, comm=comm, image_size=AGE['image'], conv_dim=AGE['conv_dim'], z_dim=AGE['z_dim'])
     else:
         exp = srgan_b200.Experiment(s, name, device=dev, comm=comm)
     eng = exp.runner.engine
@@ -298,7 +304,7 @@ def main():
     launches_eager0 = eng.ops.launches
     # the probed kernel: age = D layer-2 conv (64->128 k4 s2) over the 4B-row batch; crowd = the transition-1 1x1 conv
     # (256->128 at 56x56, a [4B*3136 x 256] x [256 x 128] GEMM); coefficient = no dense kernel to probe (one persistent kernel)
-    probe_layer = {'age': 'layer2.0', 'crowd': 'transition_layers.transition1.conv'}.get(name)
+    probe_layer = {'age': 'layer2.0', 'driving': 'layer2.0', 'crowd': 'transition_layers.transition1.conv'}.get(name)
     probe_steps = min(args.steps, 20)
     if probe_layer is not None:
         eng.probe_begin(layer_name=probe_layer, rows=4 * B)

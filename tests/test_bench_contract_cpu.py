@@ -23,3 +23,24 @@ def test_reference_arm_json_line():
     assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and cb['sample']
     e = d['e2e']
     assert e['value'] == d['value'] and e['unit'] == d['unit'] and e['h2d_bytes_per_step'] == 0 and e['d2h_bytes_per_step'] == 0
+
+
+def test_synthetic_batches_of_every_workload():
+    """bench.make_batches: shapes / label kinds of SURVEY 8(d) configs 1-4 (the bench never reads a dataset)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    import torch
+    for name in sorted(bench.WORKLOADS):
+        x, y, u = bench.make_batches(name, 4, 7)
+        assert x.shape == u.shape and x.shape[0] == 4 and x.dtype == torch.float32
+        if name == 'crowd':
+            density, label_map = y
+            assert x.shape[1:] == (3, 224, 224) and density.shape == label_map.shape == (4, 224, 224)
+            assert set(density.unique().tolist()) <= {0.0, 1.0} and 0 < label_map.min() and label_map.max() <= 1
+        elif name in ('age', 'driving'):
+            assert x.shape[1:] == (3, 128, 128) and y.shape == (4,) and x.abs().max() <= 1
+        else:
+            assert x.shape[1:] == (50,) and y.shape == (4,)
+    ya = bench.make_batches('age', 256, 1)[1]
+    yd = bench.make_batches('driving', 256, 1)[1]
+    assert ya.min() >= 10 and ya.max() <= 95 and yd.min() < 0 < yd.max()

@@ -15,7 +15,7 @@ s.matching_loss_multiplier, s.contrasting_loss_multiplier, s.gradient_penalty_mu
 s.use_cuda_graph = False
 s.use_persistent_kernel = False
 s.overlap_dnn_step = False           # per-op events need one stream
-kw = dict(image_size=128, conv_dim=64, z_dim=256) if name == 'age' else {}
+kw = dict(image_size=128, conv_dim=64, z_dim=256) if name in ('age', 'driving') else {}
 exp = srgan_b200.Experiment(s, name, **kw)
 x, y, u = bench.make_batches(name, B, 1)
 cu = lambda t: tuple(e.cuda() for e in t) if isinstance(t, tuple) else t.cuda()
