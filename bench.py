@@ -1,30 +1,37 @@
 """
 bench.py -- SR-GAN training steps/sec on B200 (BASELINE.json metric), one JSON line on rank 0.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload age|crowd|coefficient] [--precision bf16|fp32] [--batch B]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload crowd|age|driving|coefficient] [--precision bf16|fp32] [--batch B]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-  python bench.py --impl reference ...     (the oracle port of the reference step on the host CPU cores)
+  python bench.py --impl reference ...     (the UNMODIFIED reference step on the host CPU cores)
 
-Default workload (config.workload): BASELINE configs[1] "age SR-GAN": DCGAN G/D (age/models.py:32-80), synthetic
-3x128x128 inputs ~U(-1,1), labels ~U(10,95), per-GPU batch 100, multipliers of run.py:30-35; one step =
-dnn_training_step + gan_training_step with generator_training_step_period=1.  `--workload crowd` runs
-BASELINE configs[2] (DCGenerator + KnnDenseNetCat/DenseNet-201 at 224x224, per-GPU batch 64, run.py:57-68 multipliers),
-`--workload coefficient` BASELINE configs[0] (MLPs, batch 5000).  N>1 is weak scaling: every rank holds a per-GPU-batch
-shard of the global batch, feature sums and gradients are all-reduced (NCCL) so the loss is the global-batch loss.
+Default workload (config.workload) = the configuration BASELINE.json's metric is quoted on: configs[2] "crowd SR-GAN":
+DCGenerator + KnnDenseNetCat (DenseNet-201) at 224x224 (crowd/srgan.py:92-96, crowd/models.py:127-147, 1049-1166), synthetic
+inputs of SURVEY 8d config 3, run.py:57-68 multipliers, per-GPU batch 64; one step = dnn_training_step +
+gan_training_step with generator_training_step_period = 1.  The same line carries `secondary`: the age SR-GAN workload
+(configs[1], DCGAN G/D at 128x128, batch 100) measured the same way in the same process.  `--workload age|driving|
+coefficient` make one of the other configs the primary.  N>1 is weak scaling: every rank holds a per-GPU-batch shard of
+the global batch, feature sums and gradients are all-reduced (NCCL) so the loss is the global-batch loss.
 
 `value`   : steps/s with the step's inputs already resident in HBM (CUDA events, max over ranks), times N.
 `e2e`     : steps/s through the public API (srgan_b200.Experiment.*_training_step) with HOST (pinned) input buffers:
             H2D copy of x, y, u for every step (prefetched one step ahead on a copy stream) and a D2H read of the step's
             scalars inside the timed region.
-`roofline`: dominant dense kernel (age: the layer-2 discriminator conv over the 4B-row batch) timed live with CUDA events;
-            algorithmic FLOPs / duration against MEASURED_PEAKS.json.
-`cpu_baseline`: the oracle port (PyTorch fp32 autograd on the host cores) on a bounded sample, rank 0, N=1 only.
+`roofline`: the dominant kernel class of the step timed live with CUDA events around each of its launches (crowd: the
+            DenseNet trunk's 1x1 data-gradient GEMMs, HBM-bound; age: the layer-2 discriminator conv, tensor-bound);
+            algorithmic bytes or FLOPs per launch / average launch duration against MEASURED_PEAKS.json.
+`cpu_baseline`: the reference's own step on the box's host cores on a bounded sample, rank 0, N=1 only ("reference" = the
+            unmodified reference staged under baseline/_ref by oracle/stage_reference.py; "port" = the oracle restatement
+            when the staged tree is absent).
+`gpu_baseline`: the same reference step as stock PyTorch (cuDNN / cuBLAS) ON cuda:0, TF32 off and on -- the "existing
+            Blackwell kernels" bar of SURVEY section 0 / 8d.  N=1 only, after the product arm has released its memory.
 Inputs and activations of one step are far larger than L2 (126 MB), so no L2 flush is needed between iterations
-(stated in config.l2).
+(stated in details.l2).
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -39,26 +46,28 @@ METRIC = 'SR-GAN train steps/sec'
 AGE = dict(image=128, conv_dim=64, z_dim=256, batch=100, matching=1e2, contrasting=1e1, gp=1e2)
 # algorithmic FLOPs per sample per step = 21 F_D + 4 F_G
 WORKLOADS = {
-    # BASELINE configs[1] -- the N=1 workload of the default run (the metric's single-GPU configuration)
-    'age': dict(batch=100, ref_batch=10, flops_per_sample=21 * 0.8305e9 + 4 * 0.8472e9, mult=(1e2, 1e1, 1e2),
+    # BASELINE configs[2]: DCGenerator + KnnDenseNetCat (DenseNet-201) at 224x224, run.py:57-68 multipliers -- the
+    # configuration the metric ("at 1/2/4/8 B200") and the target sentence are quoted on
+    'crowd': dict(batch=64, ref_batch=2, gpu_ref_batch=32, flops_per_sample=21 * 8.732e9 + 4 * 2.595e9, mult=(1e3, 1e2, 1e2),
+                  desc='crowd SR-GAN (BASELINE configs[2]): DCGenerator + KnnDenseNetCat (DenseNet-201), 3x224x224'),
+    # BASELINE configs[1]
+    'age': dict(batch=100, ref_batch=10, gpu_ref_batch=100, flops_per_sample=21 * 0.8305e9 + 4 * 0.8472e9, mult=(1e2, 1e1, 1e2),
                 desc='age SR-GAN (BASELINE configs[1]): DCGAN G/D, 3x128x128'),
     # BASELINE configs[3]: the same DCGAN G/D (driving/models.py == age/models.py), steering-angle labels ~ N(0, 30 deg),
     # run.py:36-44 multipliers, gradient penalty on (B = 100)
-    'driving': dict(batch=100, ref_batch=10, flops_per_sample=21 * 0.8305e9 + 4 * 0.8472e9, mult=(1e2, 1e1, 1e2),
+    'driving': dict(batch=100, ref_batch=10, gpu_ref_batch=100, flops_per_sample=21 * 0.8305e9 + 4 * 0.8472e9, mult=(1e2, 1e1, 1e2),
                     desc='driving SR-GAN (BASELINE configs[3]): DCGAN G/D, 3x128x128, steering-angle labels'),
-    # BASELINE configs[2]: DCGenerator + KnnDenseNetCat (DenseNet-201) at 224x224, run.py:57-68 multipliers
-    'crowd': dict(batch=64, ref_batch=2, flops_per_sample=21 * 8.732e9 + 4 * 2.595e9, mult=(1e3, 1e2, 1e2),
-                  desc='crowd SR-GAN (BASELINE configs[2]): DCGenerator + KnnDenseNetCat (DenseNet-201), 3x224x224'),
     # BASELINE configs[0]: coefficient MLPs, B = 5000 (run.py:50), one persistent kernel per step method
-    'coefficient': dict(batch=5000, ref_batch=5000, flops_per_sample=21 * 1420.0 + 4 * 1600.0, mult=(1.0, 1.0, 10.0),
+    'coefficient': dict(batch=5000, ref_batch=5000, gpu_ref_batch=5000, flops_per_sample=21 * 1420.0 + 4 * 1600.0, mult=(1.0, 1.0, 10.0),
                         desc='coefficient SR-GAN (BASELINE configs[0]): MLP G/D, 50 observations'),
 }
 
-
-# dram__bytes_read.sum + dram__bytes_write.sum of the probed kernel per launch, from one `ncu --set full` capture of exactly that
-# launch (profiles/r1_final_ncu_full_summary.txt: D layer-2 fprop over 400 samples, read 210.1 + write 75.5 MB; algorithmic bytes
-# 315 MB = input 210 + output 105: part of the output is still in L2 when the kernel ends)
-NCU_TRAFFIC_BYTES = {('age', 100): 285.57e6, ('driving', 100): 285.57e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the probed kernel class, from `ncu --set full` captures of
+# exactly those launches (profiles/): filled in per round by the builder, None = not captured for this shape
+NCU_TRAFFIC = {
+    ('age', 100): (285.57e6, 'profiles/r1_final_ncu_full_summary.txt (D layer-2 fprop over 400 samples: read 210.1 + write 75.5 MB)'),
+    ('driving', 100): (285.57e6, 'profiles/r1_final_ncu_full_summary.txt (D layer-2 fprop over 400 samples)'),
+}
 
 
 def workload_string(name, B, world):
@@ -69,8 +78,7 @@ def workload_string(name, B, world):
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
-        d = json.load(open(p))
-        return d, 'measured'
+        return json.load(open(p)), 'measured'
     return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
 
 
@@ -139,7 +147,7 @@ def make_batches(name, B, seed):
 
 
 def oracle_setup(name, Bs):
-    """Oracle state, config, inputs and noise of a Bs-sample step of the workload (reference arm / cpu_baseline)."""
+    """Oracle state, config, inputs and noise of a Bs-sample step of the workload (the "port" CPU arm)."""
     import torch
     from oracle import srgan_oracle as O
     m, c, gp = WORKLOADS[name]['mult']
@@ -160,8 +168,61 @@ def oracle_setup(name, Bs):
     return O, st, cfg, (x, y, u, z, alpha, z2)
 
 
+# ------------------------------------------------------------------------------------------------ the reference's own step
+class ReferenceStep:
+    """One dnn_training_step + gan_training_step of the reference on `device` at batch Bs: the UNMODIFIED reference
+    (srgan.py:259-320 through its own Experiment subclass and nn.Modules, its own noise draws and torch.optim.Adam) when
+    the staged tree is present, else the oracle restatement ("port")."""
+
+    def __init__(self, name, Bs, device='cpu'):
+        import torch
+        from oracle import ref_harness
+        self.name, self.Bs, self.device = name, Bs, torch.device(device)
+        self.kind = 'reference' if ref_harness.reference_available() else 'port'
+        self.i = 0
+
+        def put(t):
+            return tuple(e.to(self.device) for e in t) if isinstance(t, tuple) else t.to(self.device)
+        if self.kind == 'reference':
+            m, c, gp = WORKLOADS[name]['mult']
+            kw = dict(batch_size=Bs, matching_loss_multiplier=m, contrasting_loss_multiplier=c, gradient_penalty_multiplier=gp,
+                      map_multiplier=1e-3, summary_step_period=1000000)
+            self.exp = ref_harness.workload_experiment(name, kw, device=self.device)
+            x, y, u = make_batches(name, Bs, 1)
+            self.inputs = (put(x), put(y), put(u))
+        else:
+            self.O, st, self.cfg, inputs = oracle_setup(name, Bs)
+            for net in ('D', 'G', 'DNN'):
+                setattr(st, net, {k: v.to(self.device) for k, v in getattr(st, net).items()})
+            self.st = st
+            self.inputs = tuple(put(t) for t in inputs)
+
+    def step(self):
+        if self.kind == 'reference':
+            x, y, u = self.inputs
+            self.exp.dnn_training_step(x, y, self.i + 1)          # step 0 would be a summary step (extra .item() syncs)
+            self.exp.gan_training_step(x, y, u, self.i + 1)
+        else:
+            self.O.training_step(self.st, self.cfg, *self.inputs)
+        self.i += 1
+
+    def describe(self):
+        if self.kind == 'reference':
+            return 'the unmodified reference step (baseline/_ref: srgan.py dnn_training_step + gan_training_step, torch autograd)'
+        return 'oracle port of the reference step (PyTorch fp32 autograd); the staged reference tree baseline/_ref is absent'
+
+
+def _timed_cpu(ref, n):
+    t0 = time.perf_counter()
+    for _ in range(n):
+        ref.step()
+    return time.perf_counter() - t0
+
+
 def run_reference(args):
-    """The reference's algorithm on the host CPU (oracle port; the reference checkout does not travel to the GPU box)."""
+    """The reference's own CPU implementation of the step on the box's host cores, all threads.  Every timed step is the
+    full step on a bounded sample of the per-GPU batch: the sample size is chosen from a probe step so that the
+    K + W steps end within ~4 minutes (the full batch when that fits: age B=100 on a 16-core host does)."""
     import torch
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -171,82 +232,114 @@ def run_reference(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    Bs = args.ref_batch or WORKLOADS[name]['ref_batch']
-    O, st, cfg, inputs = oracle_setup(name, Bs)
+    Bs = args.ref_batch
+    if not Bs:
+        b0 = min(full, WORKLOADS[name]['ref_batch'])
+        probe = ReferenceStep(name, b0)
+        probe.step()                                     # thread pools, allocator
+        t1 = _timed_cpu(probe, 1)
+        del probe
+        gc.collect()
+        per_step_budget = args.ref_budget_s / (args.steps + args.warmup)
+        Bs = int(max(b0, min(full, b0 * per_step_budget / max(t1, 1e-6))))
+    ref = ReferenceStep(name, Bs)
     for _ in range(args.warmup):
-        O.training_step(st, cfg, *inputs)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        O.training_step(st, cfg, *inputs)
-    dt = time.perf_counter() - t0
+        ref.step()
+    dt = _timed_cpu(ref, args.steps)
+    ms_sample_step = dt / args.steps * 1e3
     value = (args.steps * Bs / full) / dt                # full-step equivalents per second (per-sample scaling)
-    sample = f'{args.steps} oracle steps on {Bs}-sample batches in {dt:.1f} s (full step = {full} samples; steps/s scaled by {Bs}/{full})'
+    exact = Bs == full
+    sample = (f'{args.steps} steps of {ref.describe()} on {Bs}-sample batches in {dt:.1f} s'
+              + ('' if exact else f' (full step = {full} samples; steps/s scaled by {Bs}/{full}, the CPU cost is linear in the batch)'))
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'steps/s', 'n_gpus': args.gpus,
-            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 / value, 'higher_is_better': True,
+            'steps': args.steps, 'warmup': args.warmup,
+            # wall time of one timed step as executed (a Bs-sample step); ms of a full-batch step = 1e3 / value
+            'ms_per_step': ms_sample_step, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': workload_string(name, full, world),
-                       'reference_arm': 'oracle port of the reference step (PyTorch fp32 autograd) on the host CPU cores; the reference is a script tree without packaging metadata and does not travel to the GPU box'},
-            'cpu_baseline': {'value': value, 'unit': 'steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'config': {'workload': workload_string(name, full, world)},
+            'details': {'reference_arm': ref.describe(), 'sample_batch': Bs, 'full_batch': full, 'full_batch_run': exact,
+                        'ms_per_full_step': 1e3 / value},
+            'cpu_baseline': {'value': value, 'unit': 'steps/s', 'cores': cores, 'kind': ref.kind, 'sample': sample},
             'e2e': {'value': value, 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(name, full, budget_s=20.0):
+def cpu_baseline(name, full, budget_s=25.0):
     import torch
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    Bs = {'age': 20, 'driving': 20, 'crowd': 2, 'coefficient': 5000}[name]
-    O, st, cfg, inputs = oracle_setup(name, Bs)
-    O.training_step(st, cfg, *inputs)                    # warm-up (thread pools, allocator)
+    Bs = {'age': 100, 'driving': 100, 'crowd': 4, 'coefficient': 5000}[name]
+    Bs = min(Bs, full)
+    ref = ReferenceStep(name, Bs)
+    ref.step()                                           # warm-up (thread pools, allocator)
     n, t0 = 0, time.perf_counter()
     while True:
-        O.training_step(st, cfg, *inputs)
+        ref.step()
         n += 1
         dt = time.perf_counter() - t0
         if dt > budget_s or n >= (200 if name == 'coefficient' else 10):
             break
     value = (n * Bs / full) / dt
-    return {'value': value, 'unit': 'steps/s', 'cores': cores, 'kind': 'port',
-            'sample': f'{n} oracle steps on {Bs}-sample batches in {dt:.1f} s (full step = {full} samples; steps/s scaled by {Bs}/{full})'}
+    return {'value': value, 'unit': 'steps/s', 'cores': cores, 'kind': ref.kind,
+            'sample': f'{n} steps of {ref.describe()} on {Bs}-sample batches in {dt:.1f} s'
+                      + ('' if Bs == full else f' (full step = {full} samples; steps/s scaled by {Bs}/{full})')}
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
-    ap.add_argument('--warmup', type=int, default=10)
-    ap.add_argument('--impl', default='b200')
-    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
-    ap.add_argument('--workload', default='age', choices=sorted(WORKLOADS))
-    ap.add_argument('--batch', type=int, default=0, help='per-GPU batch (default: the workload\'s)')
-    ap.add_argument('--ref-batch', type=int, default=0)
-    ap.add_argument('--micro-batch', type=int, default=0, help='run every step in micro-batches of this many samples (exact)')
-    ap.add_argument('--no-cpu-baseline', action='store_true')
-    args = ap.parse_args()
-    if args.warmup < 3:
-        args.warmup = 3
-    if args.impl == 'reference':
-        run_reference(args)
-        return
+def gpu_baseline(name, full, dev, budget_s=15.0):
+    """Stock PyTorch on the same B200: the reference step with its modules on cuda:0 (cuDNN / cuBLAS), TF32 off and on."""
+    import torch
+    Bs = min(full, WORKLOADS[name]['gpu_ref_batch'])
+    out = {'unit': 'steps/s', 'sample_batch': Bs, 'full_batch': full}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        for mode, tf32 in (('fp32_tf32_off', False), ('fp32_tf32_on', True)):
+            try:
+                torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = tf32
+                torch.backends.cudnn.benchmark = True            # run.py:21
+                ref = ReferenceStep(name, Bs, dev)
+                out['kind'] = ref.kind
+                for _ in range(3):
+                    ref.step()
+                torch.cuda.synchronize(dev)
+                n, t0 = 0, time.perf_counter()
+                while n < 20 and time.perf_counter() - t0 < budget_s / 2:
+                    ref.step()
+                    n += 1
+                torch.cuda.synchronize(dev)
+                dt = (time.perf_counter() - t0) / n
+                out[mode] = {'value': (Bs / full) / dt, 'ms_per_sample_step': dt * 1e3, 'steps_timed': n}
+                del ref
+            except Exception as e:                               # e.g. out of memory at this batch: reported, not hidden
+                out[mode] = {'error': f'{type(e).__name__}: {str(e)[:160]}'}
+            gc.collect()
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = old
+    out['note'] = ('the reference step as stock PyTorch on cuda:0, wall clock around synchronised steps'
+                   + ('' if Bs == full else f'; steps/s scaled by {Bs}/{full}'))
+    return out
 
+
+# ------------------------------------------------------------------------------------------------ the product arm
+def probe_selector(name, eng, B):
+    """(select, label, bound) of the dominant kernel class of the workload."""
+    if name in ('age', 'driving'):
+        return (lambda role, st, l, n: role == 'forward' and st is eng.D and l.name == 'layer2.0' and n == 4 * B,
+                f'D layer2.0 forward conv (64->128 k4 s2) over {4 * B} samples (umma_conv_persistent_kernel)')
+    if name == 'crowd':
+        return (lambda role, st, l, n: role == 'dgrad' and l.name.endswith('.conv1'),
+                'DenseNet trunk 1x1 data-gradient GEMMs (every dense layer conv1, all passes; umma_conv_persistent_kernel): '
+                '[pixels x 128] x [128 x C] with the BatchNorm/ReLU mask epilogue')
+    return None, None
+
+
+def run_workload(name, args, dev, comm, world, rank, local_rank, steps, warmup, with_cpu_baseline, with_gpu_baseline):
     import torch
     import torch.distributed as dist
     import srgan_b200
-    from srgan_b200.dist import Comm
 
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local_rank)
-    comm = None
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-        comm = Comm()
-    dev = torch.device('cuda', local_rank)
-    name = args.workload
     wl = WORKLOADS[name]
-    B = args.batch or wl['batch']
-
+    B = (args.batch if name == args.workload else 0) or wl['batch']
     s = srgan_b200.Settings()
     s.batch_size = B
     s.matching_loss_multiplier, s.contrasting_loss_multiplier, s.gradient_penalty_multiplier = wl['mult']
@@ -267,7 +360,7 @@ def main():
         return tuple(e.to(dev, non_blocking=True) for e in t) if isinstance(t, tuple) else t.to(dev, non_blocking=True)
 
     def nbytes(t):
-        return sum(e.numel() * 4 for e in t) if isinstance(t, tuple) else t.numel() * 4
+        return sum(e.numel() * e.element_size() for e in t) if isinstance(t, tuple) else t.numel() * t.element_size()
     xh, yh, uh = pin(xh), pin(yh), pin(uh)
     x, y, u = dev_copy(xh), dev_copy(yh), dev_copy(uh)
 
@@ -281,48 +374,48 @@ def main():
         exp.gan_training_step(xx, yy, uu, i)
 
     # ---------------- resident-input timing
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(i, x, y, u)
     barrier()
-    launches0 = eng.ops.launches
     sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        step(args.warmup + i, x, y, u)
+    for i in range(steps):
+        step(warmup + i, x, y, u)
     e1.record()
     barrier()
     clocks = sampler.stop() if sampler else None
     graphed = exp.runner.use_cuda_graph
-    launches = eng.ops.launches - launches0
     ms = e0.elapsed_time(e1)
-    # dominant-kernel timing: CUDA events around every launch of the D layer-2 forward conv.  The timed region above
-    # replays CUDA graphs (no host launches, so no event records inside it); the same kernel on the same buffers is
-    # therefore timed during K eager steps run right after it, still inside this process and clock state.
+    scalars_resident = exp.runner.scalars()
+    # dominant-kernel timing: CUDA events around every launch of the probed kernel class.  The timed region above
+    # replays CUDA graphs (no host launches, so no event records inside it); the same kernels on the same buffers are
+    # therefore timed during eager steps run right after it, still inside this process and clock state, with the side
+    # streams off so that each probed kernel runs alone on the device.
     exp.runner.use_cuda_graph = False
-    overlap, exp.runner.overlap_dnn = exp.runner.overlap_dnn, False      # the probed kernel is timed alone on its stream
+    overlap, exp.runner.overlap_dnn = exp.runner.overlap_dnn, False
+    side = (eng.wgrad_side_stream, eng.branch_streams)
+    eng.wgrad_side_stream = eng.branch_streams = False
     launches_eager0 = eng.ops.launches
-    # the probed kernel: age = D layer-2 conv (64->128 k4 s2) over the 4B-row batch; crowd = the transition-1 1x1 conv
-    # (256->128 at 56x56, a [4B*3136 x 256] x [256 x 128] GEMM); coefficient = no dense kernel to probe (one persistent kernel)
-    probe_layer = {'age': 'layer2.0', 'driving': 'layer2.0', 'crowd': 'transition_layers.transition1.conv'}.get(name)
-    probe_steps = min(args.steps, 20)
-    if probe_layer is not None:
-        eng.probe_begin(layer_name=probe_layer, rows=4 * B)
+    select, label = probe_selector(name, eng, B)
+    probe_steps = min(steps, 20 if name != 'crowd' else 3)
+    if select is not None:
+        eng.probe_begin(select, label)
     for i in range(probe_steps):
-        step(args.warmup + args.steps + i, x, y, u)
-    probe = eng.probe_end() if probe_layer is not None else {'count': 0}
+        step(warmup + steps + i, x, y, u)
+    probe = eng.probe_end() if select is not None else {'count': 0}
     launches_per_step = (eng.ops.launches - launches_eager0) / probe_steps
     exp.runner.use_cuda_graph = graphed
     exp.runner.overlap_dnn = overlap
-    if graphed:
-        launches = int(round(launches_per_step * args.steps))     # kernels executed by the replayed graphs
+    eng.wgrad_side_stream, eng.branch_streams = side
+    launches = int(round(launches_per_step * steps))         # kernels executed inside the timed region (graph replays)
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    ms_per_step = ms / args.steps
+    ms_per_step = ms / steps
     global_steps = 1e3 / ms_per_step                       # optimizer steps/s of the whole job
-    # whole-job throughput in units of one-GPU steps (a 100-sample dnn+gan step): every global step at N ranks does N
+    # whole-job throughput in units of one-GPU steps (a per-GPU-batch dnn+gan step): every global step at N ranks does N
     # of them (weak scaling), so value = N * global steps/s; at N=1 the two coincide
     value = global_steps * world
 
@@ -346,6 +439,7 @@ def main():
         for k in range(2):
             consumed[k].record(main)
         prefetch(0)
+        sc_ = None
         for i in range(n):
             k = i % 2
             if i + 1 < n:
@@ -359,68 +453,129 @@ def main():
     e2e_loop(3)
     barrier()
     e0.record()
-    sc = e2e_loop(args.steps)
+    sc = e2e_loop(steps)
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * 1e3 / (float(t.item()) / args.steps)
+    e2e_value = world * 1e3 / (float(t.item()) / steps)
     h2d = nbytes(xh) + nbytes(yh) + nbytes(uh)
     d2h = eng.scalars.numel() * 4
+    overlap_flag = bool(exp.runner.overlap_dnn)
 
-    if rank == 0:
-        pk, pk_kind = peaks()
-        flops_launch = 2.0 * probe.get('macs_per_sample', 0) * 4 * B
-        if name == 'coefficient':
-            # one persistent kernel per step method: latency-bound by design; reported against HBM with its algorithmic bytes
-            by = B * (50 + 50 + 50 + 10 + 10 + 1 + 1 + 1) * 4.0 + 3 * 2 * 2400 * 4 * 4.0
-            ach = by / (ms_per_step * 1e-3) / 1e9
-            roof_coef = {'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / pk['hbm_gbs'],
-                         'traffic': None, 'kernel': 'coef_step_kernel (two cooperative launches per step: dnn, gan)',
-                         'peak_source': pk_kind, 'launches_timed': 2 * args.steps,
-                         'note': 'launch/latency-bound tiny MLPs: the figure of merit is us/step, not bandwidth'}
+    # release the engine's buffers before the baselines / the secondary workload allocate theirs
+    del exp, eng, x, y, u, slots
+    gc.collect()
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    pk, pk_kind = peaks()
+    if name == 'coefficient':
+        # one persistent kernel per step method: latency-bound by design; reported against HBM with its algorithmic bytes
+        by = B * (50 + 50 + 50 + 10 + 10 + 1 + 1 + 1) * 4.0 + 3 * 2 * 2400 * 4 * 4.0
+        ach = by / (ms_per_step * 1e-3) / 1e9
+        roof = {'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / pk['hbm_gbs'],
+                'traffic': None, 'kernel': 'coef_step_kernel (two cooperative launches per step: dnn, gan)',
+                'peak_source': pk_kind, 'launches_timed': 2 * steps,
+                'note': 'launch/latency-bound tiny MLPs: the figure of merit is us/step, not bandwidth'}
+    else:
         roof = {'bound': 'tensor', 'achieved': None, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s', 'frac': None,
-                'traffic': None, 'kernel': probe.get('kernel', 'conv_down layer2 over 4B rows'), 'peak_source': f'{pk_kind} (sustained: kernel timed inside a long step)',
+                'traffic': None, 'kernel': probe.get('kernel', label), 'peak_source': f'{pk_kind} (sustained: kernel timed inside a long step)',
                 'launches_timed': probe.get('count', 0),
-                'timing': 'CUDA events around each launch during K eager steps run right after the timed region (the timed region replays CUDA graphs)' if graphed else 'CUDA events around each launch inside the timed region'}
-        roof['traffic'] = NCU_TRAFFIC_BYTES.get((name, B))
-        if roof['traffic'] is not None:
-            roof['traffic_source'] = 'profiles/r1_final_ncu_full_summary.txt (one ncu --set full capture of this launch)'
+                'timing': 'CUDA events around each launch during eager steps run right after the timed region (the timed region replays CUDA graphs)'}
+        tr = NCU_TRAFFIC.get((name, B))
+        if tr is not None:
+            roof['traffic'], roof['traffic_source'] = tr
         if probe.get('count'):
             avg_ms = probe['ms'] / probe['count']
-            roof['achieved'] = flops_launch / (avg_ms * 1e-3) / 1e12
+            fl, by = probe['flops_per_launch'], probe['bytes_per_launch']
+            roof['achieved'] = fl / (avg_ms * 1e-3) / 1e12
             roof['frac'] = roof['achieved'] / roof['peak']
             roof['avg_launch_ms'] = avg_ms
-            # which roofline binds this launch: arithmetic intensity (algorithmic FLOP / algorithmic byte: input, output
-            # and weights moved once) against the ridge of the two measured peaks.  The age layer-2 conv (AI ~ 680) is
-            # tensor-bound; the crowd trunk's 1x1 GEMMs (N = 128: AI ~ 170 and less) are HBM-bound.
-            by = probe.get('bytes_per_launch', 0)
+            # which roofline binds this kernel class: arithmetic intensity (algorithmic FLOP / algorithmic byte: operands
+            # and result moved once) against the ridge of the two measured peaks.  The age layer-2 conv (AI ~ 340) is
+            # tensor-bound; the crowd trunk's 1x1 GEMMs (K or N = 128: AI < 130) are HBM-bound.
             if by and args.precision == 'bf16':
-                ai, ridge = flops_launch / by, pk['bf16_tflops_sustained'] * 1e12 / (pk['hbm_gbs'] * 1e9)
+                ai, ridge = fl / by, pk['bf16_tflops_sustained'] * 1e12 / (pk['hbm_gbs'] * 1e9)
                 roof['arithmetic_intensity'], roof['ridge'] = ai, ridge
                 roof['tensor_tflops'] = roof['achieved']
                 if ai < ridge:
                     gbs = by / (avg_ms * 1e-3) / 1e9
                     roof.update({'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / pk['hbm_gbs'],
                                  'peak_source': f'{pk_kind} (HBM copy bandwidth)', 'algorithmic_bytes_per_launch': by})
-        step_tflops = wl['flops_per_sample'] * B * world / (ms_per_step * 1e-3) / 1e12
-        line = {'metric': METRIC, 'value': value, 'unit': 'steps/s', 'n_gpus': world, 'steps': args.steps,
-                'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
-                'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
-                'config': {'workload': workload_string(name, B, world),
-                           'precision_mode': args.precision, 'parallelism': f'dp{world}', 'cuda_graph': bool(graphed), 'dnn_gan_overlap': bool(exp.runner.overlap_dnn), 'micro_batch': args.micro_batch,
-                           'l2': ('inputs and activations of one step (age: 39 MB + ~1 GB, crowd: ~0.7 GB per sample) exceed the 126 MB L2; no flush needed'
-                                  if name != 'coefficient' else 'working set (2 MB) is L2-resident by design: the step is launch/latency-bound, not bandwidth-bound'),
-                           'global_steps_per_s': global_steps,
-                           'value_definition': 'n_gpus x global optimizer steps/s = per-GPU-batch step-equivalents per second over the whole job',
-                           'step_algorithmic_tflops': step_tflops,
-                           'step_frac_of_bf16_sustained_peak': step_tflops / (pk['bf16_tflops_sustained'] * world)},
-                'roofline': roof_coef if name == 'coefficient' else roof, 'clocks': clocks, 'gpu_launches': int(launches),
-                'e2e': {'value': e2e_value, 'unit': 'steps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
-                'last_scalars': sc}
-        if world == 1 and not args.no_cpu_baseline:
-            line['cpu_baseline'] = cpu_baseline(name, B)
+    step_tflops = wl['flops_per_sample'] * B * world / (ms_per_step * 1e-3) / 1e12
+    line = {'metric': METRIC, 'value': value, 'unit': 'steps/s', 'n_gpus': world, 'steps': steps,
+            'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
+            'config': {'workload': workload_string(name, B, world)},
+            'details': {'precision_mode': args.precision, 'parallelism': f'dp{world}', 'cuda_graph': bool(graphed),
+                        'dnn_gan_overlap': overlap_flag, 'micro_batch': args.micro_batch,
+                        'l2': ('inputs and activations of one step (age: 39 MB + ~1 GB, crowd: ~0.7 GB per sample) exceed the 126 MB L2; no flush needed'
+                               if name != 'coefficient' else 'working set (2 MB) is L2-resident by design: the step is launch/latency-bound, not bandwidth-bound'),
+                        'global_steps_per_s': global_steps,
+                        'value_definition': 'n_gpus x global optimizer steps/s = per-GPU-batch step-equivalents per second over the whole job',
+                        'samples_per_s': global_steps * B * world,
+                        'step_algorithmic_tflops': step_tflops,
+                        'step_frac_of_bf16_sustained_peak': step_tflops / (pk['bf16_tflops_sustained'] * world)},
+            'roofline': roof, 'clocks': clocks, 'gpu_launches': int(launches),
+            'e2e': {'value': e2e_value, 'unit': 'steps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
+            # the losses of the last timed step (global-batch values: equal across N at equal global batch, tests/test_gpu_dist.py)
+            'last_scalars': sc, 'last_scalars_resident': scalars_resident}
+    if world == 1 and with_gpu_baseline:
+        line['gpu_baseline'] = gpu_baseline(name, B, dev)
+    if world == 1 and with_cpu_baseline:
+        line['cpu_baseline'] = cpu_baseline(name, B)
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--workload', default='crowd', choices=sorted(WORKLOADS))
+    ap.add_argument('--secondary', default=None, help='second workload reported under `secondary` (default: age when the primary is crowd; "none" = off)')
+    ap.add_argument('--batch', type=int, default=0, help='per-GPU batch (default: the workload\'s)')
+    ap.add_argument('--ref-batch', type=int, default=0, help='reference arm: samples per timed step (default: from the time budget)')
+    ap.add_argument('--ref-budget-s', type=float, default=240.0, help='reference arm: wall-clock budget of the K + W steps')
+    ap.add_argument('--micro-batch', type=int, default=0, help='run every step in micro-batches of this many samples (exact)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-gpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from srgan_b200.dist import Comm
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    comm = None
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        comm = Comm()
+    dev = torch.device('cuda', local_rank)
+    line = run_workload(args.workload, args, dev, comm, world, rank, local_rank, args.steps, args.warmup,
+                        not args.no_cpu_baseline, not args.no_gpu_baseline)
+    sec = args.secondary if args.secondary is not None else ('age' if args.workload == 'crowd' else 'none')
+    if sec != 'none' and sec != args.workload:
+        # the secondary workload is small next to the primary (age: 4 ms steps): more steps for a stable number
+        s2 = run_workload(sec, args, dev, comm, world, rank, local_rank, max(args.steps, 100), max(args.warmup, 10),
+                          not args.no_cpu_baseline, not args.no_gpu_baseline)
+        if rank == 0:
+            line['secondary'] = {k: s2[k] for k in ('value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'scaling', 'dtype',
+                                                    'config', 'details', 'roofline', 'gpu_launches', 'e2e', 'last_scalars',
+                                                    'cpu_baseline', 'gpu_baseline') if k in s2}
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

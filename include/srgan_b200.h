@@ -58,6 +58,11 @@ const char* srgan_last_error(void);
 long long srgan_launch_count(void);
 /* 1 if the last conv call on this thread ran on the tcgen05 path, 0 if SIMT */
 int srgan_last_path_tensor(void);
+/* number of contraction calls that ran on the tcgen05 kernels / that were bf16 calls of tensor-core size (both channel
+ * counts >= 64) but not eligible and went to the fp32-FMA kernels instead (each distinct such shape is also reported once
+ * on stderr unless SRGAN_QUIET_FALLBACK=1: a 30x slower path must not be silent) */
+long long srgan_tensor_launch_count(void);
+long long srgan_simt_fallback_count(void);
 /* force the SIMT path even for bf16 (debug / A-B checks): 0 = auto, 1 = SIMT only */
 void srgan_set_force_simt(int on);
 
@@ -217,6 +222,9 @@ int srgan_crowd_map_grad(const void* map, const float* map_label, const float* d
  * x [B,50], y [B], u [B,50], z [B,10], alpha [B], z2 [B,10]; the *_mult arguments already include srgan_loss_multiplier /
  * dggan_loss_multiplier; inv_Bg = 1 / global batch.  workspace: srgan_coefficient_step_workspace_bytes() bytes, needs no
  * initialisation.  scalars: the 7 engine slots (dnn, labeled, unlabeled, fake, penalty, grad-norm mean, generator).
+ * publish (may be NULL): [4][B][10] fp32 features of x | u | fake | x_hat as the D step saw them (the fake block is replaced
+ * by the generator step's) followed by [B] gradient norms -- the tensors srgan.py:332-386 leaves in
+ * Experiment.{labeled,unlabeled,fake,interpolates}_features and Experiment.gradient_norm.
  * Single-rank only: the feature sums are combined inside the kernel. */
 size_t srgan_coefficient_step_workspace_bytes(void);
 int srgan_coefficient_step(const float* const* d_ptrs, const float* const* g_ptrs, const float* const* dnn_ptrs,
@@ -225,7 +233,7 @@ int srgan_coefficient_step(const float* const* d_ptrs, const float* const* g_ptr
                            int dggan, int order, float labeled_mult, float unl_mult, float fake_mult, float gen_mult,
                            float gp_lambda, int kind_match, int kind_contrast, float lr, float lr_dnn, float wd,
                            float beta1, float beta2, float eps, int phases, int train_g, void* workspace,
-                           size_t workspace_bytes, float* scalars, void* stream);
+                           size_t workspace_bytes, float* scalars, float* publish, void* stream);
 
 #ifdef __cplusplus
 }

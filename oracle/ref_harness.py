@@ -1,9 +1,10 @@
 """
-Harness that imports the UNMODIFIED reference from /root/reference  --  TEST INFRASTRUCTURE, build container only.
+Harness that imports the UNMODIFIED reference  --  TEST / BENCH INFRASTRUCTURE, never product code.
 
-/root/reference does not exist on the GPU box, so nothing under tests/ (-m gpu), smoke() or bench.py imports this
-module; only oracle/make_golden.py (run here, output committed under tests/golden/) and the optional
-tests/test_oracle_vs_reference.py (skipped when the reference is absent) do.
+The reference tree is read from /root/reference when it is mounted (build container) and otherwise from the copy
+oracle/stage_reference.py staged under baseline/_ref/ (git-ignored, travels to the GPU box like the built .so).  Users:
+oracle/make_golden.py (fixtures under tests/golden/), bench.py's reference arm / cpu_baseline / gpu_baseline legs (the
+reference's own step, timed), tests/test_gpu_mixin_reference.py (B200StepMixin composed with the reference classes).
 
 The reference needs eight non-numeric third-party modules that are not installed; they are
 replaced by empty stand-ins in sys.modules so that no reference file has to be edited.
@@ -18,11 +19,32 @@ import types
 import numpy as np
 import torch
 
-REFERENCE_ROOT = os.environ.get('SRGAN_REFERENCE_ROOT', '/root/reference')
+def _find_root():
+    env = os.environ.get('SRGAN_REFERENCE_ROOT')
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in ([env] if env else []) + ['/root/reference', os.path.join(here, 'baseline', '_ref')]:
+        if os.path.isfile(os.path.join(p, 'srgan.py')):
+            return p
+    return env or '/root/reference'
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, 'srgan.py'))
+
+
+def set_reference_device(device):
+    """The reference binds `gpu = cuda:0 if available else cpu` at import (utility.py:18) and copies the name into every
+    module that uses it; the CPU arm on a GPU box re-points those module globals (no file is edited)."""
+    dev = torch.device(device)
+    import utility
+    utility.gpu = dev
+    for name in ('srgan', 'dnn', 'coefficient.srgan', 'coefficient.dggan', 'age.srgan', 'driving.srgan', 'crowd.srgan'):
+        m = sys.modules.get(name)
+        if m is not None and hasattr(m, 'gpu'):
+            m.gpu = dev
 
 
 class _RecordingWriter:
@@ -117,3 +139,54 @@ def last_scalars(exp):
         for tag, vals in w.scalars.items():
             out[f'{prefix}/{tag}'] = vals[-1][1]
     return out
+
+
+def workload_experiment(name, settings_kwargs, device='cpu', state=None, method='srgan', base=None):
+    """A reference Experiment of a bench workload ('coefficient' | 'age' | 'driving' | 'crowd') on `device`, built the way
+    Experiment.train does, with the reference's own modules.  state = an oracle OracleState whose parameter dicts are
+    loaded (strict) into the reference modules: the crowd trunk cannot download its pretrained weights here
+    (crowd/models.py:1103-1127), and tests want identical initial parameters on both sides.  base = extra base classes
+    placed in front of the reference Experiment subclass (tests: B200StepMixin)."""
+    install_shims()
+    import utility                                   # noqa: F401  (first import decides utility.gpu)
+    from settings import Settings
+    s = Settings()
+    for k, v in settings_kwargs.items():
+        setattr(s, k, v)
+    if name == 'coefficient':
+        from coefficient.srgan import CoefficientExperiment
+        from coefficient.dggan import CoefficientDgganExperiment
+        from coefficient.models import Generator, MLP, DgganMLP
+        cls = CoefficientDgganExperiment if method == 'dggan' else CoefficientExperiment
+        mk = DgganMLP if method == 'dggan' else MLP
+        D, DNN, G = mk(), mk(), Generator()
+    elif name in ('age', 'driving'):
+        if name == 'age':
+            from age.srgan import AgeExperiment as cls
+            from age.models import Generator, Discriminator
+        else:
+            from driving.srgan import DrivingExperiment as cls
+            from driving.models import Generator, Discriminator
+        if state is not None:
+            z_dim, c8, k, _ = state.G['fc.0.weight'].shape
+            D, DNN = Discriminator(image_size=k * 16, conv_dim=c8 // 8), Discriminator(image_size=k * 16, conv_dim=c8 // 8)
+            G = Generator(z_dim=z_dim, image_size=k * 16, conv_dim=c8 // 8)
+        else:
+            D, DNN, G = Discriminator(), Discriminator(), Generator()
+    elif name == 'crowd':
+        from crowd.srgan import CrowdExperiment
+        from crowd.dggan import CrowdDgganExperiment
+        from crowd.models import KnnDenseNetCat, KnnDenseNetCatDggan, DCGenerator
+        cls = CrowdDgganExperiment if method == 'dggan' else CrowdExperiment
+        mk = KnnDenseNetCatDggan if method == 'dggan' else KnnDenseNetCat
+        D, DNN, G = mk(pretrained=False), mk(pretrained=False), DCGenerator()
+    else:
+        raise ValueError(name)
+    if state is not None:
+        D.load_state_dict(state.D, strict=True)
+        DNN.load_state_dict(state.DNN, strict=True)
+        G.load_state_dict(state.G, strict=True)
+    set_reference_device(device)
+    if base:
+        cls = type('B200' + cls.__name__, tuple(base) + (cls,), {})
+    return make_experiment(cls, s, D=D, G=G, DNN=DNN)

@@ -1,5 +1,6 @@
 // C ABI: library plumbing + dispatch of the dense contractions between the tcgen05 path and the SIMT path.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -7,6 +8,28 @@ std::atomic<long long> g_launches{0};
 static thread_local char t_err[512] = "";
 static thread_local int t_last_tensor = 0;
 static std::atomic<int> g_force_simt{0};
+static std::atomic<long long> g_tensor_calls{0}, g_simt_fallbacks{0};
+
+// A bf16 contraction of tensor-core size that is not eligible for the tcgen05 kernels runs ~30x slower on the fp32-FMA
+// kernels: count it and say so once per distinct shape (up to a few lines), never silently.
+static void note_simt_fallback(const char* who, const srgan_geom* g, int n) {
+    if (g->Ca < 64 || g->Cb < 64) return;            // narrow layers (MLPs, map heads, image stems) are SIMT by design
+    g_simt_fallbacks.fetch_add(1, std::memory_order_relaxed);
+    static std::atomic<int> lines{0};
+    static std::atomic<unsigned long long> seen[8];
+    const unsigned long long key = ((unsigned long long)g->Ca << 44) ^ ((unsigned long long)g->Cb << 28) ^
+                                   ((unsigned long long)g->Hs << 16) ^ ((unsigned long long)g->R << 8) ^ (unsigned)g->stride ^
+                                   ((unsigned long long)(who[11] == 'w') << 60);
+    for (auto& s : seen)
+        if (s.load() == key) return;
+    const int i = lines.fetch_add(1);
+    if (i >= 8) return;
+    seen[i].store(key);
+    const char* q = getenv("SRGAN_QUIET_FALLBACK");
+    if (q && q[0] == '1') return;
+    fprintf(stderr, "srgan_b200: %s n=%d %dx%dx%d <- %dx%dx%d k%d s%d p%d (bf16) is not tcgen05-eligible: running on the fp32-FMA "
+            "kernel\n", who, n, g->Hs, g->Ws, g->Ca, g->Hl, g->Wl, g->Cb, g->R, g->stride, g->pad);
+}
 
 void srgan_set_error(const char* fmt, ...) {
     va_list ap;
@@ -51,6 +74,8 @@ int srgan_version(void) { return 100; }
 const char* srgan_last_error(void) { return t_err; }
 long long srgan_launch_count(void) { return g_launches.load(); }
 int srgan_last_path_tensor(void) { return t_last_tensor; }
+long long srgan_tensor_launch_count(void) { return g_tensor_calls.load(); }
+long long srgan_simt_fallback_count(void) { return g_simt_fallbacks.load(); }
 void srgan_set_force_simt(int on) { g_force_simt.store(on); }
 
 static int conv_common(int mode, const char* who, const void* src, const void* W, void* out, int n, const srgan_geom* g,
@@ -72,7 +97,8 @@ static int conv_common(int mode, const char* who, const void* src, const void* W
     if (dtype == SRGAN_BF16 && !g_force_simt.load()) {
         int took = umma_conv(mode, src, W, out, n, g, bias, bias_mod, href, epi, act, slope, st);
         if (took < 0) return took;
-        if (took == 1) { t_last_tensor = 1; return SRGAN_OK; }
+        if (took == 1) { t_last_tensor = 1; g_tensor_calls.fetch_add(1, std::memory_order_relaxed); return SRGAN_OK; }
+        note_simt_fallback(who, g, n);
     }
     return simt_conv(mode, src, W, out, n, g, bias, bias_mod, href, epi, act, slope, dtype, st);
 }
@@ -99,7 +125,8 @@ int srgan_conv_wgrad(const void* S, const void* L, float* dW, int n, const srgan
     if (dtype == SRGAN_BF16 && !g_force_simt.load()) {
         int took = umma_wgrad(S, L, dW, n, g, st);
         if (took < 0) return took;
-        if (took == 1) { t_last_tensor = 1; return SRGAN_OK; }
+        if (took == 1) { t_last_tensor = 1; g_tensor_calls.fetch_add(1, std::memory_order_relaxed); return SRGAN_OK; }
+        note_simt_fallback("srgan_conv_wgrad", g, n);
     }
     return simt_wgrad(S, L, dW, n, g, dtype, st);
 }

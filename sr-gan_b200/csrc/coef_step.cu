@@ -63,7 +63,19 @@ struct CoefParams {
     int phases, train_g;
     float* ws;                  // WS_FLOATS floats, no initialisation required
     float* scalars;             // engine scalar slots
+    // optional (may be null): [4][B][10] features of x | u | fake | x_hat as the D step saw them (the fake block is
+    // replaced by the generator step's G(z2) under the updated discriminator), then [B] gradient norms: the tensors
+    // srgan.py:332-386 leaves in self.*_features / self.gradient_norm
+    float* publish;
 };
+
+__device__ __forceinline__ void publish10(float* pub, int block, int B, int sample, bool act, const float* h) {
+    if (pub != nullptr && act) {
+        float* d = pub + ((long long)block * B + sample) * H;
+#pragma unroll
+        for (int i = 0; i < H; ++i) d[i] = h[i];
+    }
+}
 
 __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : v * SLOPE; }
 __device__ __forceinline__ float dleaky(float h) { return h > 0.f ? 1.f : SLOPE; }
@@ -531,6 +543,7 @@ __global__ void __launch_bounds__(CT) coef_step_kernel(const CoefParams P) {
             // ---- x: labeled loss + matching seed
             row_load(row, P.x, sc, act);
             d_fwd_row(sD, row, h1, h2, h3);
+            publish10(P.publish, 0, P.B, sc, act, h3);
             {
                 float pred = sD.b4[0];
 #pragma unroll
@@ -549,6 +562,7 @@ __global__ void __launch_bounds__(CT) coef_step_kernel(const CoefParams P) {
             // ---- u
             row_load(row, P.u, sc, act);
             d_fwd_row(sD, row, h1, h2, h3);
+            publish10(P.publish, 1, P.B, sc, act, h3);
             {
                 float dsu = 0.f;
                 if (dggan) {
@@ -578,6 +592,7 @@ __global__ void __launch_bounds__(CT) coef_step_kernel(const CoefParams P) {
                 for (int i = 0; i < NZ; ++i) zz[i] = P.z[(long long)sc * NZ + i];
                 g_hidden(sG, zz, g1, g2, g3);
                 d_fwd_fake<true>(sD, sG, g3, row + O_IN, h1, h2, h3);
+                publish10(P.publish, 2, P.B, sc, act, h3);
                 float dsf = 0.f;
                 if (dggan) {
                     float s1 = sD.b4[1], lt;
@@ -613,6 +628,7 @@ __global__ void __launch_bounds__(CT) coef_step_kernel(const CoefParams P) {
                     for (int o = 0; o < H; ++o) h1[o] = fmaf(r[o], v, h1[o]);
                 }
                 d_tail(sD, h1, h2, h3);
+                publish10(P.publish, 3, P.B, sc, act, h3);
                 float g3v[H], gm3[H], gm2[H], gm1[H], t[H];
                 float snorm = 1.f, inv_s = 1.f;
                 if (dggan) {
@@ -645,6 +661,7 @@ __global__ void __launch_bounds__(CT) coef_step_kernel(const CoefParams P) {
                     for (int o = 0; o < H; ++o) t[o] = fmaf(r[o], g0, t[o]);
                 }
                 rr = sqrtf(rr);
+                if (P.publish != nullptr && act) P.publish[(long long)4 * P.B * H + sc] = rr;
                 const float ex = fmaxf(rr - 1.f, 0.f);
                 l_pen += k * lam * ex * ex;
                 l_gn += k * P.inv_Bg * rr;
@@ -780,6 +797,7 @@ __global__ void __launch_bounds__(CT) coef_step_kernel(const CoefParams P) {
             for (int i = 0; i < NZ; ++i) zz[i] = P.z2[(long long)sc * NZ + i];
             g_hidden(sG, zz, g1, g2, g3);
             d_fwd_fake<false>(sD, sG, g3, row, h1, h2, h3);
+            publish10(P.publish, 2, P.B, sc, act, h3);                                  // srgan.py:386
             if (dggan) {
                 float s1 = sD.b4[1], lt, ds;
 #pragma unroll
@@ -845,7 +863,8 @@ extern "C" int srgan_coefficient_step(const float* const* d_ptrs, const float* c
                                       float inv_Bg, int dggan, int order, float labeled_mult, float unl_mult,
                                       float fake_mult, float gen_mult, float gp_lambda, int kind_match, int kind_contrast,
                                       float lr, float lr_dnn, float wd, float beta1, float beta2, float eps, int phases,
-                                      int train_g, void* workspace, size_t workspace_bytes, float* scalars, void* stream) {
+                                      int train_g, void* workspace, size_t workspace_bytes, float* scalars, float* publish,
+                                      void* stream) {
     SRGAN_REQUIRE(d_ptrs && g_ptrs && dnn_ptrs && d_state && g_state && dnn_state && x && y && scalars && B > 0,
                   "srgan_coefficient_step: bad arguments");
     SRGAN_REQUIRE(phases >= 1 && phases <= 3, "srgan_coefficient_step: phases must be 1 (dnn), 2 (gan) or 3 (both)");
@@ -875,7 +894,7 @@ extern "C" int srgan_coefficient_step(const float* const* d_ptrs, const float* c
     P.kind_match = kind_match; P.kind_contrast = kind_contrast;
     P.lr = lr; P.lr_dnn = lr_dnn; P.wd = wd; P.beta1 = beta1; P.beta2 = beta2; P.eps = eps;
     P.phases = phases; P.train_g = train_g;
-    P.ws = static_cast<float*>(workspace); P.scalars = scalars;
+    P.ws = static_cast<float*>(workspace); P.scalars = scalars; P.publish = publish;
     const size_t smem = (size_t)(2 * net_floats(NIN, 2, true) + net_floats(NZ, NIN, false) + NSLOT * CT) * sizeof(float);
     int grid = (B + CT - 1) / CT;
     if (grid > MAXG) grid = MAXG;

@@ -185,6 +185,7 @@ class Engine:
         self.mdt = self.D.grad.dtype               # fp32 in the product; tests may run the schedule in fp64
         self.scalars = torch.zeros(N_SCALARS, dtype=self.mdt, device=self.device)
         self._buf = {}
+        self.buf_generation = 0                    # bumped when an existing scratch buffer is replaced (StepRunner drops its CUDA graphs)
         # scratch-buffer scope: the DNN step ('dnn') and the GAN step ('gan') never share a workspace buffer, so the two
         # step methods may be in flight at the same time on different streams (StepRunner overlaps them)
         self._scope = 'gan'
@@ -201,6 +202,10 @@ class Engine:
         self.branch_streams = self.device.type == 'cuda' and os.environ.get('SRGAN_NO_BRANCH_STREAMS', '0') != '1'
         self._br_streams = {}
         self._probe = None
+        # srgan.py:332-386 side effects: keep a copy of the feature rows the reference would leave in
+        # self.{labeled,unlabeled,fake,interpolates}_features (rows x | u | fake | x_hat of the D step; the fake block is
+        # replaced by the generator step's, srgan.py:386).  Off by default: the mirror Experiment has no reader.
+        self.publish_features = False
         for st in (self.D, self.G, self.DNN):
             if st is not None:
                 self.repack(st)
@@ -214,6 +219,8 @@ class Engine:
         for s in shape:
             n *= s
         if t is None or t.numel() < n or t.dtype != dtype:
+            if t is not None:
+                self.buf_generation += 1           # the old storage is freed: addresses captured in CUDA graphs dangle
             t = (torch.zeros if zero else torch.empty)(n, dtype=dtype, device=self.device)
             self._buf[key] = t
         return t[:n].view(*shape)
@@ -294,11 +301,7 @@ class Engine:
         act = l.act if act is None else act
         slope = l.slope if slope is None else slope
         b = st.params[l.name + '.bias'] if (bias and l.has_bias) else None
-        pr = self._probe
-        timed = (pr is not None and st is self.D and l is pr['layer'] and n == pr['rows'] and epi == EPI_BIAS_ACT)
-        if timed:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+        timed = self._probe_open('tangent' if epi == EPI_DACT else 'forward', st, l, n)
         if l.name in st.thin:
             P = l.geom.Hs * l.geom.Ws
             if l.fwd == 'down':      # im2col (kept for the weight gradient) -> GEMM with the layer's epilogue
@@ -313,16 +316,42 @@ class Engine:
             self.ops.conv_down(x, st.wd_[l.name], y, n, l.geom, b, l.bias_mod, href, epi, act, slope)
         else:
             self.ops.conv_up(x, st.wu_[l.name], y, n, l.geom, b, l.bias_mod, href, epi, act, slope)
-        if timed:
-            e1.record()
-            pr['events'].append((e0, e1))
+        self._probe_close(timed)
 
     # ------------------------------------------------------------------ live kernel probe (bench.py roofline)
-    def probe_begin(self, layer_name, rows):
-        """Times, with CUDA events on the launch stream, every forward launch of the D layer `layer_name` over `rows`
-        samples until probe_end()."""
-        layer = next(l for l in self.d_net.layers if l.name == layer_name)
-        self._probe = {'layer': layer, 'rows': rows * layer.gemm_rows, 'samples': rows, 'events': []}
+    def probe_begin(self, select, label):
+        """Times, with CUDA events on the launch stream, every contraction launch for which
+        select(role, net_state, layer, rows) is true until probe_end(); role in {'forward', 'tangent', 'dgrad', 'wgrad'},
+        rows = samples (x gemm_rows for the [pixels x C] GEMM layers).  Thin-lowered layers are timed with their
+        im2col / col2im companions."""
+        self._probe = {'select': select, 'label': label, 'events': [], 'flops': 0.0, 'elems': 0.0}
+
+    def _probe_open(self, role, st, l, n):
+        pr = self._probe
+        if pr is None or not pr['select'](role, st, l, n):
+            return None
+        g = l.geom
+        if l.gemm_rows > 1:                        # [pixels x C] GEMM: algorithmic sizes from the master dims
+            d0, d1 = l.master_dims[0], l.master_dims[1] * l.master_dims[2] * l.master_dims[3]
+            small, large, wts, macs = n * d0, n * d1, d0 * d1, n * d0 * d1
+        else:
+            d = l.master_dims
+            ca, cb = (d[0], d[1]) if l.master_kind == 'conv' else (g.Ca, g.Cb)
+            small, large, wts = n * g.Hs * g.Ws * ca, n * g.Hl * g.Wl * cb, ca * g.R * g.S * cb
+            macs = n * g.Hs * g.Ws * ca * g.R * g.S * cb
+        out_side = (small if l.fwd == 'down' else large) if role in ('forward', 'tangent') else (large if l.fwd == 'down' else small)
+        # operands once each; the tangent / data-gradient epilogues also read the stored activation of the output side;
+        # the weight gradient reads both activations and writes fp32 weights (counted as 2 elements each)
+        pr['elems'] += small + large + (2 * wts if role == 'wgrad' else wts) + (out_side if role in ('tangent', 'dgrad') else 0)
+        pr['flops'] += 2.0 * macs
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(self.device))
+        return e0, e1
+
+    def _probe_close(self, timed):
+        if timed is not None:
+            timed[1].record(torch.cuda.current_stream(self.device))
+            self._probe['events'].append(timed)
 
     def probe_end(self):
         pr, self._probe = self._probe, None
@@ -330,16 +359,17 @@ class Engine:
             return {'count': 0}
         torch.cuda.synchronize()
         ms = sum(a.elapsed_time(b) for a, b in pr['events'])
-        l = pr['layer']
-        d = l.master_dims
-        g = l.geom
-        elems = pr['rows'] * (g.Hl * g.Wl * g.Cb + g.Hs * g.Ws * g.Ca) + g.Ca * g.R * g.S * g.Cb      # in + out + weights, once each
-        return {'count': len(pr['events']), 'ms': ms, 'macs_per_sample': l.macs_per_sample,
-                'bytes_per_launch': elems * (2 if self.act_dtype == torch.bfloat16 else 4),
-                'kernel': f'D {l.name} forward conv ({d[1]}->{d[0]} k{l.geom.R} s{l.geom.stride}) over {pr["samples"]} samples'}
+        n = len(pr['events'])
+        return {'count': n, 'ms': ms, 'flops_per_launch': pr['flops'] / n,
+                'bytes_per_launch': pr['elems'] / n * (2 if self.act_dtype == torch.bfloat16 else 4), 'kernel': pr['label']}
 
     def _bwd_data_layer(self, st: NetState, l: Layer, dy, dx, n, href, act, slope, lo=0, col_ready=False):
         """dx = (W_l^T dy) * act'(href)   (act = ACT_NONE: no mask)."""
+        timed = self._probe_open('dgrad', st, l, n)
+        self._bwd_data_layer_(st, l, dy, dx, n, href, act, slope, lo, col_ready)
+        self._probe_close(timed)
+
+    def _bwd_data_layer_(self, st: NetState, l: Layer, dy, dx, n, href, act, slope, lo, col_ready):
         if l.name in st.thin:
             P = l.geom.Hs * l.geom.Ws
             if l.fwd == 'down':      # transpose of (im2col -> GEMM): GEMM^T -> col2im with the mask fused
@@ -357,6 +387,11 @@ class Engine:
             self.ops.conv_down(dy, st.wd_[l.name], dx, n, l.geom, None, 0, href, EPI_DACT, act, slope)
 
     def _wgrad_layer(self, st: NetState, l: Layer, x_in, dy, n, lo=0):
+        timed = self._probe_open('wgrad', st, l, n)
+        self._wgrad_layer_(st, l, x_in, dy, n, lo)
+        self._probe_close(timed)
+
+    def _wgrad_layer_(self, st: NetState, l: Layer, x_in, dy, n, lo):
         dW = st.g(l.name + '.weight')
         if l.name in st.thin:
             P = l.geom.Hs * l.geom.Ws
@@ -880,6 +915,9 @@ class Engine:
                         self.rows(a_in, E, 3 * B, 4 * B), B, E)
         # ---- one D forward over [x; u; fake; x_hat]
         self.forward(D, acts, 0, 4 * B)
+        self.last_gan_batch = B
+        if self.publish_features and not dggan:
+            self.buf('feat_snap', (4 * B * F,)).copy_(fblk(0, 4 * B))
         # ---- labeled loss (srgan.py:329-335, :414-417)
         pred = self.buf('pred', (B,), self.mdt)
         dpred = self.buf('dpred', (B,), self.mdt)
@@ -958,6 +996,8 @@ class Engine:
         self.forward(G, gacts, 0, B)
         if not dggan:
             self.forward(D, acts, 0, 2 * B)                     # rows [B,2B) still hold u
+            if self.publish_features:
+                self.buf('feat_snap', (4 * B * F,))[2 * B * F:3 * B * F].copy_(fblk(0, B))      # srgan.py:386
             sums = self.buf('fsums', (3, F), self.mdt)
             sums.zero_()
             ops.colsum(fblk(0, B), B, F, sums[0], 0, None)

@@ -263,8 +263,13 @@ class StepRunner:
         d_net, g_net = nets.describe_module(D), nets.describe_module(G)
         if nets.describe_module(DNN) != d_net:
             raise ValueError('DNN and D must share an architecture (srgan.py model_setup)')
+        if method not in ('srgan', 'dggan'):
+            raise ValueError(f'method={method!r}: the B200 path covers srgan and dggan (sgan: SURVEY 8f rank 3)')
         if method == 'dggan' and d_net.head_outputs != 2:
-            raise ValueError('DG-GAN needs the two-output discriminator (coefficient/models.py:53-72)')
+            raise ValueError('DG-GAN needs the two-output discriminator (coefficient/models.py:53-72, crowd/models.py:929-1046)')
+        if method == 'srgan' and d_net.head_outputs != 1:
+            raise ValueError('SR-GAN feature matching expects a one-output discriminator; a two-output (DG-GAN) module was '
+                             'given: use method=\'dggan\' (coefficient/dggan.py, crowd/dggan.py)')
 
         def pd(m):
             d = {k: p for k, p in m.named_parameters()}
@@ -272,8 +277,9 @@ class StepRunner:
             return d
         self.engine = Engine(CudaOps(dev), d_net, g_net, pd(D), pd(G), pd(DNN),
                              act_dtype=torch.float32 if precision == 'fp32' else torch.bfloat16, device=dev, comm=comm)
+        # device noise stream (draw_noise): every rank draws its OWN shard of the global batch's z / alpha / z2
         self.generator = torch.Generator(device=dev)
-        self.generator.manual_seed(0)
+        self.generator.manual_seed(int(getattr(settings, 'noise_seed', 0)) + (comm.rank if comm is not None else 0))
         import os
         ug = getattr(settings, 'use_cuda_graph', True)
         # multi-rank steps are captured PIECEWISE: one graph segment between every two collectives, the NCCL all-reduces
@@ -348,8 +354,15 @@ class StepRunner:
                              cfg.gradient_penalty_multiplier, DIST_KINDS[cfg.matching_distance_function],
                              DIST_KINDS[cfg.contrasting_distance_function], cfg.learning_rate, lr_dnn,
                              cfg.weight_decay if wd is None else wd, cfg.betas[0], cfg.betas[1], cfg.eps, phases, train_g,
-                             ws, eng.scalars)
+                             ws, eng.scalars, self._coef_publish(B) if (phases & 2) and eng.publish_features else None)
         self._layouts_stale = True
+
+    def _coef_publish(self, B):
+        """[4][B][10] features + [B] gradient norms written by the persistent kernel (srgan.py:332-386 side effects)."""
+        t = getattr(self, '_coef_pub', None)
+        if t is None or t.numel() != 41 * B:
+            t = self._coef_pub = torch.zeros(41 * B, dtype=torch.float32, device=self.device)
+        return t
 
     def _fresh_layouts(self):
         """The persistent kernel updates only the master parameters: rebuild the kernel-layout copies before the
@@ -384,17 +397,25 @@ class StepRunner:
         _on_dnn_stream)."""
         launch = launch or (lambda f: f())
         entry = self._graphs.get(key)
+        gen = self.engine.buf_generation
+        if entry is not None and entry['gen'] != gen:
+            # an engine scratch buffer was reallocated since this graph was captured (a larger batch shape, predict() /
+            # generate() on a bigger batch): the addresses baked into the graph may dangle -- capture again
+            entry = None
         if entry is None:
-            self._graphs[key] = {'calls': 1, 'graph': None}
             for dst, src in statics:
                 dst.copy_(src)
             launch(fn)
+            # the static input buffers stay referenced by the entry for as long as its graph may replay
+            self._graphs[key] = {'calls': 1, 'graph': None, 'gen': self.engine.buf_generation, 'statics': [d for d, _ in statics]}
             return
         for dst, src in statics:
             dst.copy_(src)
         if entry['graph'] is None:
             torch.cuda.synchronize(self.device)
             entry['graph'] = self._capture_segments(fn)
+            if self.engine.buf_generation != entry['gen']:
+                raise RuntimeError('engine buffers were reallocated during graph capture')
 
         def replay():
             for seg in entry['graph']:
@@ -504,10 +525,13 @@ class StepRunner:
         return segs
 
     def _static(self, name, like, dtype=torch.float32):
-        t = self._statics.get(name)
-        if t is None or t.shape != like.shape:
+        """Static graph input, one per (name, shape): a graph captured for one batch shape keeps ITS buffers when another
+        shape comes by (shapes A, B, A replay graph A on the buffers it was captured with)."""
+        key = (name, tuple(like.shape))
+        t = self._statics.get(key)
+        if t is None:
             t = torch.empty(like.shape, dtype=dtype, device=self.device)
-            self._statics[name] = t
+            self._statics[key] = t
         return t
 
     def _static_labels(self, name, labels):
@@ -589,6 +613,61 @@ class StepRunner:
                 'fake_loss': v[SC_FAKE], 'gradient_penalty': v[SC_GP], 'gradient_norm_mean': v[SC_GNORM],
                 'generator_loss': v[SC_GEN]}
 
+    # ---- srgan.py side effects of the last GAN step (device tensors in the reference's layout)
+    FEATURE_BLOCKS = {'labeled': 0, 'unlabeled': 1, 'fake': 2, 'interpolates': 3}
+
+    def step_features(self, which):
+        """`.features` of the last gan_step in the reference's order and shape ([B, C*H*W] for the DCGAN discriminator,
+        age/models.py:74; [B, 80, 1, 1] for KnnDenseNetCat, crowd/models.py:1163; [B, 10] for the coefficient MLP):
+        'labeled' / 'unlabeled' / 'interpolates' with the discriminator of the D step, 'fake' = the generator step's
+        G(z2) under the updated discriminator when the generator was trained (srgan.py:332-386).  Needs
+        engine.publish_features (set before the step); a per-rank shard under data parallelism."""
+        eng = self.engine
+        if not eng.publish_features or self.method == 'dggan':
+            return None
+        self._wait_pending()
+        F = eng.d_net.feature_size
+        if self.persistent:
+            pub = getattr(self, '_coef_pub', None)
+            if pub is None:
+                return None
+            B = pub.numel() // 41
+            j = self.FEATURE_BLOCKS[which]
+            return pub[j * B * F:(j + 1) * B * F].view(B, F).clone()
+        snap = eng._buf.get(('gan', 'feat_snap'))
+        if snap is None:
+            return None
+        B = eng.last_gan_batch
+        j = self.FEATURE_BLOCKS[which]
+        eng.ops.begin()
+        out = self.features_nchw(snap[j * B * F:(j + 1) * B * F], B)
+        return out.view(B, F, 1, 1) if eng.d_net.family == 'crowd' else out
+
+    def dnn_step_features(self, examples):
+        """`DNN.features` of the dnn_step just run on `examples` (srgan.py:270-271), in the reference's shape.  The
+        persistent coefficient kernel keeps DNN's activations on chip: there the features are recomputed with the
+        updated network (one Adam update later)."""
+        eng, net = self.engine, self.engine.d_net
+        if self.persistent:
+            return self.predict(examples, net='DNN')[1]
+        self._wait_pending(('DNN',))
+        t = eng._buf[('dnn', ('D', 'a', net.feature_buf if net.graph is not None else len(net.layers)))]
+        B, F = examples.shape[0], net.feature_size
+        eng.ops.begin()
+        out = self.features_nchw(t[:B * F], B)
+        return out.view(B, F, 1, 1) if net.family == 'crowd' else out
+
+    def gradient_norm(self):
+        """Per-sample ||d s / d x_hat||_2 of the last gan_step (srgan.py:371-372), [B] fp32."""
+        self._wait_pending()
+        if self.persistent:
+            pub = getattr(self, '_coef_pub', None)
+            if pub is not None:
+                return pub[40 * (pub.numel() // 41):].clone()
+            raise RuntimeError('gradient_norm(): set engine.publish_features before the step (persistent coefficient kernel)')
+        g = self.engine._buf.get(('gan', 'gnorm'))
+        return None if g is None else g.clone()
+
     # ---- forward-only helpers (D(x) / G(z) of the reference modules, on the kernels)
     def predict(self, x, net='D'):
         self._wait_pending()
@@ -652,9 +731,20 @@ class B200StepMixin:
     """Mix into a reference Experiment subclass; see module docstring."""
     b200_precision: Optional[str] = None
     b200_comm = None
+    # srgan.py:332-386 leave the step's feature tensors and gradient norms on the Experiment; keep doing so (a 4B x F copy
+    # inside the step + one layout kernel per attribute).  Set False to skip the materialisation when nothing reads them.
+    b200_publish_features = True
 
     def _b200_method(self):
-        return 'dggan' if 'Dggan' in type(self).__name__ else 'srgan'
+        """DG-GAN = the experiment overrides the loss hooks the way coefficient/dggan.py:22-64 / crowd/dggan.py:17-49 do;
+        recognised by the discriminator's second head output (DgganMLP, KnnDenseNetCatDggan), cross-checked against the
+        class hierarchy so that a mismatched pair raises instead of training the wrong loss."""
+        by_module = nets.describe_module(self.D).head_outputs == 2
+        by_class = any('dggan' in c.__name__.lower() for c in type(self).__mro__)
+        if by_module != by_class:
+            raise ValueError(f'{type(self).__name__}: discriminator has {2 if by_module else 1} head output(s) but the '
+                             f'experiment class is {"" if by_class else "not "}a DG-GAN experiment')
+        return 'dggan' if by_module else 'srgan'
 
     def _b200_runner(self) -> StepRunner:
         r = getattr(self, '_b200', None)
@@ -664,6 +754,7 @@ class B200StepMixin:
             r.import_optimizer_state(self.d_optimizer, 'D')
             r.import_optimizer_state(self.g_optimizer, 'G')
             r.import_optimizer_state(self.dnn_optimizer, 'DNN')
+            r.engine.publish_features = bool(self.b200_publish_features)
             self._b200 = r
         return r
 
@@ -675,12 +766,29 @@ class B200StepMixin:
         r.dnn_step(examples, labels, lr=group['lr'], weight_decay=group['weight_decay'])
         if self.dnn_summary_writer.is_summary_step():
             self.dnn_summary_writer.add_scalar('Discriminator/Labeled Loss', r.scalars()['dnn_loss'])
+            if r.method != 'dggan' or r.engine.d_net.family == 'coefficient':     # srgan.py:270-271 (KnnDenseNetCatDggan publishes no .features)
+                f = r.dnn_step_features(examples)
+                self.DNN.features = f
+                self.dnn_summary_writer.add_scalar('Feature Norm/Labeled', f.norm(dim=1).mean().item())
 
     def gan_training_step(self, labeled_examples, labels, unlabeled_examples, step):
         """srgan.py:273-320."""
         r = self._b200_runner()
         self.gan_summary_writer.step = step
         r.gan_step(labeled_examples, labels, unlabeled_examples, step, noise=getattr(self, '_b200_noise', None))
+        group = self.d_optimizer.param_groups[0]
+        if (group['lr'], group['weight_decay']) != (self.settings.learning_rate, self.settings.weight_decay):
+            raise ValueError('the B200 step reads the D / G learning rate and weight decay from settings (srgan.py:131-138); '
+                             'd_optimizer.param_groups was changed away from them')
+        # side effects of srgan.py:332-386 (device tensors; per-rank shards under data parallelism)
+        self.gradient_norm = r.gradient_norm()
+        if r.engine.publish_features and r.method != 'dggan':
+            self.labeled_features = r.step_features('labeled')
+            self.unlabeled_features = r.step_features('unlabeled')
+            self.fake_features = r.step_features('fake')
+            self.interpolates_features = r.step_features('interpolates')
+        # validation_summaries / save_models of the reference read the nn.Parameters on the caller's stream
+        r._wait_pending()
         if self.gan_summary_writer.is_summary_step():
             s = r.scalars()
             w = self.gan_summary_writer
@@ -691,6 +799,9 @@ class B200StepMixin:
             w.add_scalar('Discriminator/Fake Loss', s['fake_loss'])
             w.add_scalar('Discriminator/Gradient Penalty', s['gradient_penalty'])
             w.add_scalar('Discriminator/Gradient Norm', s['gradient_norm_mean'])
+            if self.labeled_features is not None and self.unlabeled_features is not None:        # srgan.py:315-319
+                w.add_scalar('Feature Norm/Labeled', self.labeled_features.mean(0).norm().item())
+                w.add_scalar('Feature Norm/Unlabeled', self.unlabeled_features.mean(0).norm().item())
 
     def save_models(self, step):
         """srgan.py:88-97 with the Adam moments exported into the torch optimizers first."""

@@ -23,6 +23,7 @@ class Geom(ctypes.Structure):
 
 _EXPORTS = (
     'srgan_version', 'srgan_last_error', 'srgan_launch_count', 'srgan_last_path_tensor', 'srgan_set_force_simt',
+    'srgan_tensor_launch_count', 'srgan_simt_fallback_count',
     'srgan_conv_down', 'srgan_conv_up', 'srgan_conv_wgrad', 'srgan_colsum', 'srgan_rowdot', 'srgan_seed_rows',
     'srgan_nchw_to_nhwc', 'srgan_nhwc_to_nchw', 'srgan_interpolate', 'srgan_labeled_loss', 'srgan_bce_logits',
     'srgan_distance', 'srgan_feature_norm_seed', 'srgan_gradnorm_penalty', 'srgan_gp_feature_seed', 'srgan_adam',
@@ -79,7 +80,7 @@ def load_library(path: str = LIB_PATH):
     lib.srgan_col2im.argtypes = [vp, vp, c_int, gp, c_int, vp, vp, c_int, c_int, c_f, c_int, vp]
     pp = ctypes.POINTER(vp)
     lib.srgan_coefficient_step.argtypes = ([pp, pp, pp, vp, vp, vp] + [vp] * 6 + [c_int, c_f, c_int, c_int] + [c_f] * 5 +
-                                           [c_int, c_int] + [c_f] * 6 + [c_int, c_int, vp, ctypes.c_size_t, vp, vp])
+                                           [c_int, c_int] + [c_f] * 6 + [c_int, c_int, vp, ctypes.c_size_t, vp, vp, vp])
     lib.srgan_affine.argtypes = [vp, c_int, c_int, vp, c_int, c_ll, c_int, vp, vp, vp, vp, c_f, vp, c_int, c_int, c_f, c_int, vp]
     lib.srgan_affine_bwd.argtypes = [vp, c_int, vp, c_int, c_int, c_ll, c_int, vp, vp, c_f, c_int, c_int, vp]
     lib.srgan_affine_grad.argtypes = [vp, c_int, vp, c_int, c_int, c_ll, c_int, vp, vp, c_f, vp, vp, c_int, c_int, vp]
@@ -93,7 +94,9 @@ def load_library(path: str = LIB_PATH):
     lib.srgan_adam_multi.argtypes = [vp, c_int, vp, vp, vp, vp, c_f, c_f, c_f, c_f, vp]
     lib.srgan_depth_to_space.argtypes = [vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, vp]
     lib.srgan_crowd_map_grad.argtypes = [vp, vp, vp, vp, c_int, c_ll, c_int, c_int, c_f, c_int, vp]
-    for name in _EXPORTS[5:]:
+    lib.srgan_tensor_launch_count.restype = c_ll
+    lib.srgan_simt_fallback_count.restype = c_ll
+    for name in _EXPORTS[7:]:
         getattr(lib, name).restype = c_int
     lib.srgan_coefficient_step_workspace_bytes.restype = ctypes.c_size_t
     _lib = lib
@@ -163,6 +166,16 @@ class CudaOps:
     @property
     def launches(self):
         return self.lib.srgan_launch_count()
+
+    @property
+    def tensor_launches(self):
+        """Contraction calls that ran on the tcgen05 kernels."""
+        return self.lib.srgan_tensor_launch_count()
+
+    @property
+    def simt_fallbacks(self):
+        """bf16 contraction calls of tensor-core size that were not tcgen05-eligible (also reported once on stderr)."""
+        return self.lib.srgan_simt_fallback_count()
 
     # -------------------------------------------------------------- ops (signatures == tests/torch_ops.TorchOps)
     def repack(self, w, dims, out1, s1, out2, s2):
@@ -286,7 +299,7 @@ class CudaOps:
 
     def coefficient_step(self, d_ptrs, g_ptrs, dnn_ptrs, d_state, g_state, dnn_state, x, y, u, z, alpha, z2, B, inv_Bg,
                          dggan, order, labeled_mult, unl_mult, fake_mult, gen_mult, gp_lambda, kind_match, kind_contrast,
-                         lr, lr_dnn, wd, b1, b2, eps, phases, train_g, workspace, scalars):
+                         lr, lr_dnn, wd, b1, b2, eps, phases, train_g, workspace, scalars, publish=None):
         """d_ptrs / g_ptrs / dnn_ptrs: ctypes (c_void_p * 32) tables built by pointer_table()."""
         f32 = torch.float32
         self._ck(self.lib.srgan_coefficient_step(
@@ -294,7 +307,8 @@ class CudaOps:
             self._p(x, f32), self._p(y, f32), self._p(u, f32), self._p(z, f32), self._p(alpha, f32), self._p(z2, f32),
             int(B), inv_Bg, int(dggan), int(order), labeled_mult, unl_mult, fake_mult, gen_mult, gp_lambda,
             int(kind_match), int(kind_contrast), lr, lr_dnn, wd, b1, b2, eps, int(phases), int(train_g),
-            self._p(workspace), workspace.numel() * workspace.element_size(), self._p(scalars, f32), self._stream()),
+            self._p(workspace), workspace.numel() * workspace.element_size(), self._p(scalars, f32),
+            self._p(publish, f32) if publish is not None else None, self._stream()),
             'srgan_coefficient_step')
 
     def pointer_table(self, tensors):

@@ -1,4 +1,4 @@
-"""CPU: the reference arm of bench.py (`--impl reference`: the oracle port timed on the host cores) prints ONE JSON line with
+"""CPU: the reference arm of bench.py (`--impl reference`: the staged reference, else the oracle port, timed on the host cores) prints ONE JSON line with
 the keys the driver reads, on the metric / unit / config of the product arm.  The product arm itself needs a GPU."""
 import json
 import os
@@ -20,7 +20,8 @@ def test_reference_arm_json_line():
     assert d['value'] > 0 and abs(d['value'] - 1e3 / d['ms_per_step']) / d['value'] < 1e-6
     assert 'coefficient SR-GAN' in d['config']['workload'] and 'model' not in d['config']
     cb = d['cpu_baseline']
-    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and cb['sample']
+    assert cb['kind'] in ('reference', 'port') and cb['cores'] >= 1 and cb['value'] == d['value'] and cb['sample']
+    assert d['details']['full_batch_run'] is True and d['details']['sample_batch'] == 5000      # coefficient runs un-scaled
     e = d['e2e']
     assert e['value'] == d['value'] and e['unit'] == d['unit'] and e['h2d_bytes_per_step'] == 0 and e['d2h_bytes_per_step'] == 0
 

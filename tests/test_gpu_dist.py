@@ -14,11 +14,15 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, family, q):
+def _worker(rank, world, port, family, q, backend='gloo'):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    torch.cuda.set_device(0)
-    dist.init_process_group('gloo', rank=rank, world_size=world)
+    if backend == 'nccl':                                # one GPU per rank, NCCL over NVLink (the bench's transport)
+        torch.cuda.set_device(rank)
+        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    else:
+        torch.cuda.set_device(0)
+        dist.init_process_group('gloo', rank=rank, world_size=world)
     from oracle import srgan_oracle as O
     from srgan_b200.dist import Comm, shard
     from tests.gpu_common import runner_from_state, to_cuda
@@ -68,19 +72,47 @@ def _worker(rank, world, port, family, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('family', ['dcgan', 'crowd'])
-def test_two_ranks_on_one_gpu_match_global_batch_oracle(family):
+def _run_ranks(world, family, backend):
+    import queue
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, family, q)) for r in range(2)]
+    port = 29600 + (os.getpid() % 2000) + (7 if backend == 'nccl' else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, family, q, backend)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in procs]
+    res, waited = [], 0
+    while len(res) < world and waited < 900:             # a worker that died must fail the test, not hang it
+        try:
+            res.append(q.get(timeout=5))
+        except queue.Empty:
+            waited += 5
+            if any(p.exitcode not in (None, 0) for p in procs):
+                break
     for p in procs:
         p.join(timeout=120)
-        assert p.exitcode == 0
+        if p.is_alive():
+            p.kill()
+    assert len(res) == world and all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     for rank, serr, perr, calls in res:
         assert serr < 5e-4, (family, rank, 'scalars', serr)          # fp32 mode, 4 steps of drift
         assert perr < 2e-3, (family, rank, 'params', perr)
         assert calls > 0
+
+
+@pytest.mark.parametrize('family', ['dcgan', 'crowd'])
+def test_two_ranks_on_one_gpu_match_global_batch_oracle(family):
+    _run_ranks(2, family, 'gloo')
+
+
+@pytest.mark.parametrize('family', ['dcgan', 'crowd'])
+def test_nccl_ranks_match_global_batch_oracle(family):
+    """One rank per GPU over NCCL, as bench.py runs N > 1: with the global batch fixed (8 / 4 samples), every world size
+    the box offers (2, 4, 8 -- the largest that divides the batch) must reproduce the losses and parameters of the
+    single-process global-batch step, i.e. the step's scalars are equal across N = 1/2/4/8 at equal global batch."""
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip('needs at least two GPUs (gpurun --gpus N)')
+    batch = 8 if family == 'dcgan' else 4
+    for world in (8, 4, 2):
+        if world <= n and batch % world == 0:
+            _run_ranks(world, family, 'nccl')

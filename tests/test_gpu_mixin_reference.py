@@ -1,0 +1,145 @@
+"""GPU: the drop-in seam end to end.  `class Fast(B200StepMixin, <reference Experiment subclass>)` built through the
+reference's own setup path runs two training steps on the B200 and is compared with the reference class's OWN
+dnn_training_step / gan_training_step (srgan.py:259-320, run on the host CPU with identical initial parameters, inputs
+and injected noise): the scalar tags both write through the summary writers, the parameters after the steps, the Adam
+state exported into the reference's torch.optim.Adam objects, and the side effects srgan.py:332-386 leaves on the
+Experiment (`gradient_norm`, `labeled/unlabeled/fake/interpolates_features`, the `Feature Norm/*` tags).
+
+The reference tree comes from baseline/_ref (staged by oracle/stage_reference.py, travels with the snapshot) or from
+/root/reference; without either the tests skip."""
+import pytest
+import torch
+
+from oracle import ref_harness
+from oracle import srgan_oracle as O
+from tests.test_gpu_parity import update_error
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not ref_harness.reference_available(), reason='no staged reference tree (baseline/_ref)')]
+
+TAGS = ('dnn/Discriminator/Labeled Loss', 'gan/Discriminator/Labeled Loss', 'gan/Discriminator/Unlabeled Loss',
+        'gan/Discriminator/Fake Loss', 'gan/Discriminator/Gradient Penalty', 'gan/Discriminator/Gradient Norm',
+        'gan/Generator/Loss', 'gan/Feature Norm/Labeled', 'gan/Feature Norm/Unlabeled', 'dnn/Feature Norm/Labeled')
+
+
+def _case(app):
+    gen = torch.Generator().manual_seed(17)
+    if app.startswith('coefficient'):
+        B, method = 256, ('dggan' if app.endswith('dggan') else 'srgan')
+        st = O.init_coefficient(seed=3, dggan=(method == 'dggan'))
+        for k in ('linear1.weight', 'linear2.weight', 'linear3.weight'):
+            st.D[k] = st.D[k] * 3
+        kw = dict(batch_size=B, learning_rate=1e-3, gradient_penalty_multiplier=10.0)
+
+        def batch():
+            return (torch.randn(B, 50, generator=gen), torch.rand(B, generator=gen) * 2 - 1, torch.randn(B, 50, generator=gen),
+                    torch.randn(B, 10, generator=gen), torch.rand(B, 1, generator=gen), torch.randn(B, 10, generator=gen))
+        return 'coefficient', method, st, kw, batch
+    if app == 'age':
+        B = 8
+        st = O.init_dcgan(seed=2, image_size=64, conv_dim=16, z_dim=32, scale=3.0)
+        kw = dict(batch_size=B, matching_loss_multiplier=1e2, contrasting_loss_multiplier=1e1, gradient_penalty_multiplier=1e2)
+
+        def batch():
+            return (torch.rand(B, 3, 64, 64, generator=gen) * 2 - 1, torch.rand(B, generator=gen) * 85 + 10,
+                    torch.rand(B, 3, 64, 64, generator=gen) * 2 - 1, torch.randn(B, 32, generator=gen),
+                    torch.rand(B, 1, 1, 1, generator=gen), torch.randn(B, 32, generator=gen))
+        return 'age', 'srgan', st, kw, batch
+    B = 2                                                 # crowd: the full DenseNet-201 KnnDenseNetCat + DCGenerator at 224
+    st = O.init_crowd(seed=5, scale=1.56)
+    kw = dict(batch_size=B, matching_loss_multiplier=1e3, contrasting_loss_multiplier=1e2, gradient_penalty_multiplier=1e2,
+              map_multiplier=1e-3)
+    seeds = iter(range(50, 60))
+    return 'crowd', 'srgan', st, kw, lambda: O.synthetic_crowd_batch(B, next(seeds))
+
+
+def _cuda(t):
+    return tuple(e.cuda() for e in t) if isinstance(t, tuple) else t.cuda()
+
+
+@pytest.mark.parametrize('app', ['coefficient', 'coefficient_dggan', 'age', 'crowd'])
+def test_mixin_on_reference_class_matches_reference_step(app):
+    import srgan_b200
+    name, method, st, kw, batch = _case(app)
+    kw = dict(kw, summary_step_period=1)
+    steps = 2
+    batches = [batch() for _ in range(steps)]
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    # ---- the reference's own step, on the CPU
+    ref = ref_harness.workload_experiment(name, kw, device='cpu', state=st.clone(), method=method)
+    ref_side = []
+    for i, (x, y, u, z, alpha, z2) in enumerate(batches):
+        ref.dnn_training_step(x, y, i)
+        with ref_harness.injected_noise(z, alpha, z2):
+            ref.gan_training_step(x, y, u, i)
+        ref_side.append({k: (getattr(ref, k).detach().clone() if getattr(ref, k, None) is not None else None)
+                         for k in ('gradient_norm', 'labeled_features', 'unlabeled_features', 'fake_features',
+                                   'interpolates_features')})
+    ref_sc = ref_harness.last_scalars(ref)
+    # ---- the same reference class with the B200 step mixed in, on the GPU
+    fast = ref_harness.workload_experiment(name, kw, device='cuda', state=st.clone(), method=method,
+                                           base=(srgan_b200.B200StepMixin,))
+    assert isinstance(fast, type(ref)) and next(fast.D.parameters()).is_cuda
+    for i, (x, y, u, z, alpha, z2) in enumerate(batches):
+        fast._b200_noise = (z.cuda(), alpha.cuda(), z2.cuda())
+        fast.dnn_training_step(x.cuda(), _cuda(y), i)
+        fast.gan_training_step(x.cuda(), _cuda(y), u.cuda(), i)
+        # side effects of srgan.py:332-386 after every step
+        side = ref_side[i]
+        assert fast.gradient_norm.shape == side['gradient_norm'].shape
+        assert torch.allclose(fast.gradient_norm.cpu(), side['gradient_norm'], rtol=2e-3, atol=1e-6)
+        for k in ('labeled_features', 'unlabeled_features', 'fake_features', 'interpolates_features'):
+            want = side[k]
+            got = getattr(fast, k)
+            if want is None:
+                assert got is None, k
+                continue
+            assert got is not None and tuple(got.shape) == tuple(want.shape), (k, None if got is None else got.shape, want.shape)
+            err = (got.cpu() - want).abs().max().item() / max(want.abs().max().item(), 1e-12)
+            assert err < 2e-3, (app, i, k, err)
+    assert fast._b200.method == method and fast._b200.precision == 'fp32'
+    fast_sc = ref_harness.last_scalars(fast)
+    for tag in TAGS:
+        if tag not in ref_sc:
+            assert tag not in fast_sc, tag
+            continue
+        want = ref_sc[tag]
+        floor = 1e-3 * max(1e-3, abs(ref_sc['gan/Discriminator/Labeled Loss']))
+        # 'dnn/Feature Norm/Labeled' of the persistent coefficient kernel is evaluated one Adam update later (the kernel
+        # keeps DNN's activations on chip): looser band for that tag only
+        tol = 2e-2 if (tag == 'dnn/Feature Norm/Labeled' and fast._b200.persistent) else 1e-3
+        assert fast_sc[tag] == pytest.approx(want, rel=tol, abs=floor), (app, tag, fast_sc[tag], want)
+    # ---- parameters (same nn.Parameter objects, updated in place) and the exported Adam state
+    for net in ('D', 'G', 'DNN'):
+        init = getattr(st, net)
+        sd_f, sd_r = getattr(fast, net).state_dict(), getattr(ref, net).state_dict()
+        for k, v in sd_r.items():
+            if O.is_buffer_key(k):
+                assert torch.equal(sd_f[k].cpu(), v), k
+                continue
+            err, cos = update_error(sd_f[k].cpu() - init[k], v - init[k])
+            merr = ((sd_f[k].cpu() - v).abs().mean() / ((v - init[k]).abs().mean() + 1e-12)).item()
+            assert merr < 2e-2 and cos > 0.999, (app, net, k, err, merr, cos)
+    fast._b200.export_optimizer_state(fast.d_optimizer, 'D')
+    p0 = next(fast.D.parameters())
+    s_f, s_r = fast.d_optimizer.state[p0], ref.d_optimizer.state[next(ref.D.parameters())]
+    assert float(s_f['step']) == float(s_r['step']) == steps
+    e, c = update_error(s_f['exp_avg'].cpu(), s_r['exp_avg'])
+    assert c > 0.999, (app, 'exp_avg', e, c)
+
+
+def test_mixin_rejects_mismatched_dggan_pairing():
+    """A two-output (DG-GAN) discriminator under an SR-GAN experiment class, or the reverse, must raise instead of
+    training the wrong loss (the method is read from the module AND the class hierarchy)."""
+    import srgan_b200
+    ref_harness.install_shims()
+    from coefficient.srgan import CoefficientExperiment
+    from coefficient.models import DgganMLP, Generator
+    from settings import Settings
+    s = Settings()
+    s.batch_size = 8
+    ref_harness.set_reference_device('cuda')
+    cls = type('Fast', (srgan_b200.B200StepMixin, CoefficientExperiment), {})
+    exp = ref_harness.make_experiment(cls, s, D=DgganMLP(), G=Generator(), DNN=DgganMLP())
+    with pytest.raises(ValueError):
+        exp.dnn_training_step(torch.zeros(8, 50).cuda(), torch.zeros(8).cuda(), 0)

@@ -2,6 +2,8 @@
   (a) the golden vectors produced by the UNMODIFIED reference (tests/golden/), and
   (b) the oracle run on the same seeded inputs on the box's CPU,
 in both precisions.  Tolerances are BASELINE.json's: fp32 mode 1e-4 relative per-step losses / outputs, bf16 mode 2e-2."""
+import os
+
 import pytest
 import torch
 
@@ -37,6 +39,8 @@ def test_cuda_step_matches_reference_golden(name, precision):
     g = Golden(name)
     st, cfg = g.oracle_state(), g.step_config()
     r = runner_from_state(st, cfg, precision)
+    if precision == 'bf16':
+        r.persistent = False          # the persistent coefficient kernel is fp32 in both modes: bf16 = the generic kernels
     tol = TOL[precision]
     # bf16 drifts with every optimizer step (weights are re-rounded): compare the first step tightly, later ones looser
     for i in range(g.steps):
@@ -69,6 +73,10 @@ def test_coefficient_seeded_vs_oracle(method, precision):
     cfg = O.StepConfig(method=method, batch_size=5000, gradient_penalty_multiplier=10.0, learning_rate=1e-3)
     B = 5000
     r = runner_from_state(st, cfg, precision)
+    if precision == 'bf16':
+        r.persistent = False          # really bf16: generic kernels (fp32 case = the persistent kernel)
+    else:
+        assert r.persistent
     for i in range(2):
         x, u = torch.randn(B, 50, generator=gen), torch.randn(B, 50, generator=gen)
         y = torch.rand(B, generator=gen) * 2 - 1
@@ -116,6 +124,108 @@ def test_dcgan_seeded_vs_oracle(precision):
             # Adam's first step is sign-like (|update| = lr): elements whose gradient is ~0 may flip; bound the mean
             merr = (upd - upd_ref).abs().mean().item() / (upd_ref.abs().mean().item() + 1e-12)
             assert merr < (1e-2 if precision == 'fp32' else 0.25), (net, k, err, merr)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_age_full_size_vs_oracle(precision):
+    """BASELINE configs[1] exactly as bench.py runs it (age/models.py:32-80 at 3x128x128, conv_dim 64, B=100: the
+    persistent-tile variants <2,128>, <1,256>, <2,64>, the thin-layer lowering and umma_wgrad the bench launches) against
+    the oracle on the same seeded inputs, D conv weights x3 so that the gradient-penalty hinge is ACTIVE and the double
+    backward contributes to the update.  Losses, D(x) / features / G(z) outputs and the direction of every update."""
+    B = 100
+    gen = torch.Generator().manual_seed(41)
+    st = O.init_dcgan(seed=4, image_size=128, conv_dim=64, z_dim=256, scale=3.0)
+    cfg = O.StepConfig(batch_size=B, matching_loss_multiplier=1e2, contrasting_loss_multiplier=1e1, gradient_penalty_multiplier=1e2)
+    x, u = torch.rand(B, 3, 128, 128, generator=gen) * 2 - 1, torch.rand(B, 3, 128, 128, generator=gen) * 2 - 1
+    y = torch.rand(B, generator=gen) * 85 + 10
+    z, alpha, z2 = torch.randn(B, 256, generator=gen), torch.rand(B, 1, 1, 1, generator=gen), torch.randn(B, 256, generator=gen)
+    r = runner_from_state(st, cfg, precision)
+    st0 = st.clone()
+    torch.set_num_threads(max(1, (os.cpu_count() or 2)))
+    ref = O.training_step(st, cfg, x, y, u, z, alpha, z2, step=0)
+    assert ref['gradient_penalty'] > 0
+    xc, yc, uc, zc, ac, z2c = to_cuda(x, y, u, z, alpha, z2)
+    t = TOL[precision]['scalar']
+    pred, feats = r.predict(xc[:16])
+    p_ref, _, f_ref = O.d_forward(st0.d_spec, st0.D, x[:16])
+    assert rel(pred, p_ref) < t and rel(feats, f_ref) < t
+    assert rel(r.generate(zc[:16]), O.g_forward(st0.g_spec, st0.G, z[:16])) < t
+    t0, f0 = r.engine.ops.tensor_launches, r.engine.ops.simt_fallbacks
+    r.dnn_step(xc, yc)
+    r.gan_step(xc, yc, uc, 0, noise=(zc, ac, z2c))
+    got = r.scalars()
+    if precision == 'bf16':                   # every contraction of the step really ran on the tcgen05 kernels
+        assert r.engine.ops.tensor_launches - t0 >= 60 and r.engine.ops.simt_fallbacks == f0
+    print('age full size', precision, {k: (got[k], ref[k]) for k in SCALARS})
+    check_scalars(got, ref, t, ('age-full', precision))
+    for net, params in (('D', st.D), ('G', st.G), ('DNN', st.DNN)):
+        sd = r.modules[net].state_dict()
+        init = getattr(st0, net)
+        for k, v in params.items():
+            upd_ref, upd = v - init[k], sd[k].cpu() - init[k]
+            merr = (upd - upd_ref).abs().mean().item() / (upd_ref.abs().mean().item() + 1e-12)
+            _, cos = update_error(upd, upd_ref)
+            assert (merr < 1e-2) if precision == 'fp32' else (cos > 0.8), (net, k, merr, cos)
+
+
+def test_draw_noise_moments_mixture_determinism():
+    """StepRunner.draw_noise = the three draws of srgan.py:286-289 (MixtureModel of N(-m,1) / N(+m,1), utility.py:89-107),
+    :364 (alpha ~ U[0,1)) and :301 (z2 ~ N(0,1)) on the device: shapes, moments, the mean_offset mixture branch,
+    determinism per seed and distinct streams per data-parallel rank."""
+    import srgan_b200
+    g = Golden('dcgan_mini')
+    st, cfg = g.oracle_state(), g.step_config()
+    r = runner_from_state(st, cfg, 'fp32')
+    B, zd = 20000, r.engine.g_net.input_chw[0]
+    c = r.config()
+    z, alpha, z2 = r.draw_noise(B, c)
+    assert z.shape == (B, zd) and z2.shape == (B, zd) and alpha.shape == (B,) and z.is_cuda
+    for t in (z, z2):
+        assert abs(t.mean().item()) < 0.01 and abs(t.std().item() - 1) < 0.01
+    assert 0 <= alpha.min().item() and alpha.max().item() < 1 and abs(alpha.mean().item() - 0.5) < 0.01
+    assert abs(alpha.var().item() - 1 / 12) < 0.005
+    # the mixture branch: mean_offset m -> every element is N(+m,1) or N(-m,1) with probability 1/2 (utility.py:102-107)
+    r.settings.mean_offset = 3.0
+    zm = r.draw_noise(B, r.config())[0]
+    assert abs(zm.mean().item()) < 0.05 and abs(zm.var().item() - (1 + 9)) < 0.15
+    pos = (zm > 0).float().mean().item()
+    assert abs(pos - 0.5) < 0.01
+    assert abs(zm[zm > 0].mean().item() - 3.0) < 0.05 and abs(zm.abs().std().item() - 1.0) < 0.05
+    r.settings.mean_offset = 0
+    # determinism: the same seed reproduces the draws; a different rank seed gives a different stream
+    r.generator.manual_seed(123)
+    a = r.draw_noise(64, r.config())
+    r.generator.manual_seed(123)
+    b = r.draw_noise(64, r.config())
+    r.generator.manual_seed(124)
+    d = r.draw_noise(64, r.config())
+    assert all(torch.equal(p, q) for p, q in zip(a, b)) and not torch.equal(a[0], d[0])
+    # a step that draws its own noise runs and is finite
+    x, y, u, *_ = to_cuda(*g.step_inputs(0))
+    r.gan_step(x, y, u, 0)
+    sc = r.scalars()
+    assert all(v == v for v in sc.values())
+
+
+def test_batch_shape_change_recaptures_graphs():
+    """CUDA graphs are keyed by input shape and hold static input buffers per shape; a larger batch reallocates the
+    engine's scratch, which must invalidate the graphs captured on the old buffers: shapes A, B, A, A must agree with
+    an eager runner on every call."""
+    g = Golden('dcgan_mini')
+    st, cfg = g.oracle_state(), g.step_config()
+    ra, rb = runner_from_state(st, cfg, 'fp32'), runner_from_state(st, cfg, 'fp32')
+    rb.use_cuda_graph = False
+    rb.overlap_dnn = False
+    assert ra.use_cuda_graph
+    x, y, u, z, alpha, z2 = to_cuda(*g.step_inputs(0))
+    big = tuple(torch.cat([t, t.flip(0)]) for t in (x, y, u, z, alpha, z2))
+    small = (x, y, u, z, alpha, z2)
+    for i, (bx, by, bu, bz, ba, bz2) in enumerate([small, small, small, big, big, small, small, big]):
+        for r in (ra, rb):
+            r.settings.batch_size = bx.shape[0]
+            r.dnn_step(bx, by)
+            r.gan_step(bx, by, bu, i, noise=(bz, ba, bz2))
+        check_scalars(ra.scalars(), rb.scalars(), 1e-4, ('shape-change', i))
 
 
 def test_age_full_size_properties():
