@@ -51,6 +51,16 @@ typedef struct srgan_geom {
     int R, S, stride, pad;
 } srgan_geom;
 
+/* Channel windows of the two activation operands of a contraction (all zero / NULL = dense tensors).  A DenseNet dense
+ * layer appends its growth_rate new channels to the block's concat buffer (torch.cat at crowd/models.py:353); with a window
+ * the 3x3 convolution writes them in place (pointer = first channel of the window, pitch = channels of the concat buffer,
+ * valid = growth_rate) and its data / weight gradients read that window of the concat delta, instead of copying slices.
+ * Pitches and windows are in elements, multiples of 8; bf16 tcgen05-eligible shapes only (else SRGAN_ERR_ARG). */
+typedef struct srgan_views {
+    int S_pitch, S_valid; /* small side: elements between pixels (0 = Ca), channels that exist in memory (0 = Ca) */
+    int L_pitch, L_valid; /* large side (0 = Cb) */
+} srgan_views;
+
 /* library */
 int srgan_version(void);
 const char* srgan_last_error(void);
@@ -71,11 +81,14 @@ void srgan_set_force_simt(int on);
  * cuBLAS addmm) issued from age/models.py:44-52,68-80, coefficient/models.py:22-28,43-50,65-72,
  * crowd/models.py:139-147 and from `.backward()` / `autograd.grad` at srgan.py:265,280,284,292,295,304,368. */
 int srgan_conv_down(const void* L, const void* Wd, void* S_out, int n, const srgan_geom* g, const float* bias,
-                    int bias_mod, const void* href, int epi, int act, float slope, int dtype, void* stream);
+                    int bias_mod, const void* href, int epi, int act, float slope, int dtype, const srgan_views* views,
+                    void* stream);
 int srgan_conv_up(const void* S, const void* Wu, void* L_out, int n, const srgan_geom* g, const float* bias,
-                  int bias_mod, const void* href, int epi, int act, float slope, int dtype, void* stream);
-/* dW (fp32, Wd layout) += wgrad(S, L) */
-int srgan_conv_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, int dtype, void* stream);
+                  int bias_mod, const void* href, int epi, int act, float slope, int dtype, const srgan_views* views,
+                  void* stream);
+/* dW (fp32, Wd layout) += wgrad(S, L).  `views` (may be NULL): see srgan_views; href shares the output's window. */
+int srgan_conv_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, int dtype, const srgan_views* views,
+                     void* stream);
 
 /* Thin-layer lowering (image layers with <= 4 channels on the large side, age/models.py:48-51 layer4 of G and :61 layer1
  * of D): col[p][k] = L[n, oh*stride-pad+r, ow*stride-pad+s, b], k = (r*S+s)*Cb + b, zero for k >= R*S*Cb (Kpad columns)

@@ -44,8 +44,8 @@ int simt_conv(int mode, const void* src, const void* W, void* out, int n, const 
 int simt_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, int dtype, cudaStream_t st);
 // umma_conv.cu : return 1 if the tensor-core path took the call, 0 if the shape is not eligible, <0 on error
 int umma_conv(int mode, const void* src, const void* W, void* out, int n, const srgan_geom* g, const float* bias,
-              int bias_mod, const void* href, int epi, int act, float slope, cudaStream_t st);
-int umma_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, cudaStream_t st);
+              int bias_mod, const void* href, int epi, int act, float slope, const srgan_views* views, cudaStream_t st);
+int umma_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, const srgan_views* views, cudaStream_t st);
 
 // skinny.cu : few outputs over a long full-extent reduction axis (MapModule.linear1, the count feature layer)
 bool skinny_eligible(const srgan_geom* g);
@@ -78,9 +78,12 @@ long long srgan_tensor_launch_count(void) { return g_tensor_calls.load(); }
 long long srgan_simt_fallback_count(void) { return g_simt_fallbacks.load(); }
 void srgan_set_force_simt(int on) { g_force_simt.store(on); }
 
+static bool has_views(const srgan_views* v) { return v && (v->S_pitch || v->S_valid || v->L_pitch || v->L_valid); }
+
 static int conv_common(int mode, const char* who, const void* src, const void* W, void* out, int n, const srgan_geom* g,
                        const float* bias, int bias_mod, const void* href, int epi, int act, float slope, int dtype,
-                       void* stream) {
+                       const srgan_views* views, void* stream) {
+    if (!has_views(views)) views = nullptr;
     int rc = check_geom(who, g, n);
     if (rc) return rc;
     SRGAN_REQUIRE(src && W && out, "%s: null pointer", who);
@@ -92,28 +95,35 @@ static int conv_common(int mode, const char* who, const void* src, const void* W
     if (n == 0) return SRGAN_OK;
     cudaStream_t st = (cudaStream_t)stream;
     t_last_tensor = 0;
-    if (skinny_eligible(g) && !g_force_simt.load())
+    if (views == nullptr && skinny_eligible(g) && !g_force_simt.load())
         return skinny_conv(mode, src, W, out, n, g, bias, bias_mod, href, epi, act, slope, dtype, st);
     if (dtype == SRGAN_BF16 && !g_force_simt.load()) {
-        int took = umma_conv(mode, src, W, out, n, g, bias, bias_mod, href, epi, act, slope, st);
+        int took = umma_conv(mode, src, W, out, n, g, bias, bias_mod, href, epi, act, slope, views, st);
         if (took < 0) return took;
         if (took == 1) { t_last_tensor = 1; g_tensor_calls.fetch_add(1, std::memory_order_relaxed); return SRGAN_OK; }
         note_simt_fallback(who, g, n);
     }
+    // channel windows are a feature of the TMA-fed kernels (tensor-map strides / epilogue pitch): no second implementation
+    SRGAN_REQUIRE(views == nullptr, "%s: channel windows (srgan_views) need a tcgen05-eligible bf16 shape: both channel counts "
+                  "multiples of 64, pitches / windows multiples of 8", who);
     return simt_conv(mode, src, W, out, n, g, bias, bias_mod, href, epi, act, slope, dtype, st);
 }
 
 int srgan_conv_down(const void* L, const void* Wd, void* S_out, int n, const srgan_geom* g, const float* bias,
-                    int bias_mod, const void* href, int epi, int act, float slope, int dtype, void* stream) {
-    return conv_common(0, "srgan_conv_down", L, Wd, S_out, n, g, bias, bias_mod, href, epi, act, slope, dtype, stream);
+                    int bias_mod, const void* href, int epi, int act, float slope, int dtype, const srgan_views* views,
+                    void* stream) {
+    return conv_common(0, "srgan_conv_down", L, Wd, S_out, n, g, bias, bias_mod, href, epi, act, slope, dtype, views, stream);
 }
 
 int srgan_conv_up(const void* S, const void* Wu, void* L_out, int n, const srgan_geom* g, const float* bias,
-                  int bias_mod, const void* href, int epi, int act, float slope, int dtype, void* stream) {
-    return conv_common(1, "srgan_conv_up", S, Wu, L_out, n, g, bias, bias_mod, href, epi, act, slope, dtype, stream);
+                  int bias_mod, const void* href, int epi, int act, float slope, int dtype, const srgan_views* views,
+                  void* stream) {
+    return conv_common(1, "srgan_conv_up", S, Wu, L_out, n, g, bias, bias_mod, href, epi, act, slope, dtype, views, stream);
 }
 
-int srgan_conv_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, int dtype, void* stream) {
+int srgan_conv_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, int dtype, const srgan_views* views,
+                     void* stream) {
+    if (!has_views(views)) views = nullptr;
     int rc = check_geom("srgan_conv_wgrad", g, n);
     if (rc) return rc;
     SRGAN_REQUIRE(S && L && dW, "srgan_conv_wgrad: null pointer");
@@ -121,13 +131,14 @@ int srgan_conv_wgrad(const void* S, const void* L, float* dW, int n, const srgan
     if (n == 0) return SRGAN_OK;
     cudaStream_t st = (cudaStream_t)stream;
     t_last_tensor = 0;
-    if (skinny_eligible(g) && !g_force_simt.load()) return skinny_wgrad(S, L, dW, n, g, dtype, st);
+    if (views == nullptr && skinny_eligible(g) && !g_force_simt.load()) return skinny_wgrad(S, L, dW, n, g, dtype, st);
     if (dtype == SRGAN_BF16 && !g_force_simt.load()) {
-        int took = umma_wgrad(S, L, dW, n, g, st);
+        int took = umma_wgrad(S, L, dW, n, g, views, st);
         if (took < 0) return took;
         if (took == 1) { t_last_tensor = 1; g_tensor_calls.fetch_add(1, std::memory_order_relaxed); return SRGAN_OK; }
         note_simt_fallback("srgan_conv_wgrad", g, n);
     }
+    SRGAN_REQUIRE(views == nullptr, "srgan_conv_wgrad: channel windows (srgan_views) need a tcgen05-eligible bf16 shape");
     return simt_wgrad(S, L, dW, n, g, dtype, st);
 }
 

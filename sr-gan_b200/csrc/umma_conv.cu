@@ -154,6 +154,8 @@ struct UmmaConvParams {
     int bias_mod;
     const bf16* href;
     bf16* out;
+    int out_pitch;                // elements between consecutive output pixels (= Cout for a dense output; the row pitch of a
+    int out_valid;                // concat buffer when the output is a channel window of it) and the channels that exist there
     int epi, act;
     float slope;
     int stages;
@@ -190,6 +192,19 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&v)[32], const Umm
 #pragma unroll
             for (int e = 0; e < 32; ++e) f[e] = tanhf(f[e]);
         }
+    } else if (p.href != nullptr && p.act == SRGAN_ACT_LEAKY && p.slope == 0.f) {
+        // ReLU mask (the DenseNet trunk's data gradients: HBM-bound GEMMs whose cost is this epilogue): round first, then
+        // AND with the packed comparison mask -- 3 instructions per element pair instead of 8, same bits as the fp32 path
+        // (the mask multiplies by exactly 1 or 0)
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(hv);
+        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+        uint32_t* wo = reinterpret_cast<uint32_t*>(w);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const __nv_bfloat162 d2 = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+            wo[e] = *reinterpret_cast<const uint32_t*>(&d2) & __hgt2_mask(h2[e], zero2);
+        }
+        return;
     } else if (p.href != nullptr && p.act != SRGAN_ACT_NONE) {
         const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(hv);
         if (p.act == SRGAN_ACT_LEAKY) {
@@ -412,8 +427,8 @@ __global__ void __launch_bounds__(PC_THREADS, 1) umma_conv_persistent_kernel(con
                 const int sample = tn_i * p.TN + tn;
                 const int oy = th_i * p.TH + th, ox = tw_i * p.TW + tw;
                 long long o;
-                if (p.mode == 0) o = (((long long)sample * p.Hm + oy) * p.Wm + ox) * p.Cout + c0;
-                else o = (((long long)sample * p.Hout + (oy * p.stride + T.pa)) * p.Wout + (ox * p.stride + T.pb)) * p.Cout + c0;
+                if (p.mode == 0) o = (((long long)sample * p.Hm + oy) * p.Wm + ox) * p.out_pitch + c0;
+                else o = (((long long)sample * p.Hout + (oy * p.stride + T.pa)) * p.Wout + (ox * p.stride + T.pb)) * p.out_pitch + c0;
                 if (sample >= p.n) o = -1;
 #pragma unroll
                 for (int it = 0; it < 4; ++it) o_t[i][it] = __shfl_sync(0xffffffffu, o, 8 * it + t_row);
@@ -429,7 +444,7 @@ __global__ void __launch_bounds__(PC_THREADS, 1) umma_conv_persistent_kernel(con
 #pragma unroll
                         for (int it = 0; it < 4; ++it) {
                             hreg[i][jj][it] = make_uint4(0u, 0u, 0u, 0u);
-                            if (j < BN / 32 && c0 + j * 32 < p.Cout && o_t[i][it] >= 0)
+                            if (j < BN / 32 && c0 + j * 32 + t_unit * 8 < p.out_valid && o_t[i][it] >= 0)
                                 hreg[i][jj][it] = __ldg(reinterpret_cast<const uint4*>(p.href + o_t[i][it] + j * 32 + t_unit * 8));
                         }
                     }
@@ -441,7 +456,7 @@ __global__ void __launch_bounds__(PC_THREADS, 1) umma_conv_persistent_kernel(con
 #pragma unroll
                 for (int jj = 0; jj < NCH; ++jj) {
                     const int j = half + 2 * jj;
-                    if (j >= BN / 32 || c0 + j * 32 >= p.Cout) continue;      // warp-uniform; partial last N tile
+                    if (j >= BN / 32 || c0 + j * 32 >= p.out_valid) continue;      // warp-uniform; partial last N tile / channel window
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + i * BN + j * 32, v);
                     uint4 hv[4];
@@ -465,7 +480,8 @@ __global__ void __launch_bounds__(PC_THREADS, 1) umma_conv_persistent_kernel(con
 #pragma unroll
                     for (int it = 0; it < 4; ++it) {
                         const uint4 x = lds128(stg_addr(stg, 8 * it + t_row, t_unit));
-                        if (o_t[i][it] >= 0) *reinterpret_cast<uint4*>(p.out + o_t[i][it] + j * 32 + t_unit * 8) = x;
+                        if (o_t[i][it] >= 0 && c0 + j * 32 + t_unit * 8 < p.out_valid)
+                            *reinterpret_cast<uint4*>(p.out + o_t[i][it] + j * 32 + t_unit * 8) = x;
                     }
                     __syncwarp();
                 }
@@ -646,15 +662,29 @@ EncodeTiledFn get_encode() {
 }
 
 // NHWC activation [n, H, W, C] bf16 as a 4-D map (C, W, H, n); box (64, bw, bh, bn) with element strides (1, es, es, 1)
-int encode_act(CUtensorMap* tm, const void* base, int n, int H, int W, int C, int bw, int bh, int bn, int es) {
+// pitch (elements between pixels, 0 = C) and valid (channels that exist in memory, 0 = C) describe a channel window of a
+// wider buffer (a slice of a DenseNet concat buffer): the box still spans 64-channel chunks of the logical C channels, the
+// channels beyond `valid` are out of bounds for the map and arrive as zeros.
+int act_l2_promotion() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SRGAN_ACT_L2_PROMOTION"); v = e ? atoi(e) : 256; }
+    return v;
+}
+int encode_act(CUtensorMap* tm, const void* base, int n, int H, int W, int C, int bw, int bh, int bn, int es, int pitch = 0,
+               int valid = 0) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { srgan_set_error("cuTensorMapEncodeTiled is not available from the driver"); return SRGAN_ERR_CUDA; }
-    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
-    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    const cuuint64_t P = pitch > 0 ? pitch : C;
+    cuuint64_t dims[4] = {(cuuint64_t)(valid > 0 ? valid : C), (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+    cuuint64_t strides[3] = {P * 2, (cuuint64_t)W * P * 2, (cuuint64_t)H * W * P * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)(bw * es), (cuuint32_t)(bh * es), (cuuint32_t)bn};
     cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
+    // rows wider than one 128-byte chunk are walked chunk by chunk along K: promoting the L2 fill to 256 bytes fetches the
+    // next chunk with the current one (half the DRAM transactions, twice the page locality)
+    const int promo = act_l2_promotion();
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     promo >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : (promo >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE),
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         srgan_set_error("cuTensorMapEncodeTiled(activation n=%d H=%d W=%d C=%d box=%dx%dx%d es=%d) failed: %d", n, H, W, C, bw, bh,
@@ -732,8 +762,18 @@ int launch_wgrad(const CUtensorMap& tmS, const CUtensorMap& tmL, UmmaWgradParams
 
 // returns 1 = launched on the tensor cores, 0 = shape not eligible (caller uses the SIMT kernel), <0 = error
 int umma_conv(int mode, const void* src, const void* W, void* out, int n, const srgan_geom* g, const float* bias,
-              int bias_mod, const void* href, int epi, int act, float slope, cudaStream_t st) {
+              int bias_mod, const void* href, int epi, int act, float slope, const srgan_views* vw, cudaStream_t st) {
     const int Cin = mode == 0 ? g->Cb : g->Ca, Cout = mode == 0 ? g->Ca : g->Cb;
+    // channel windows: the input side is the TMA-loaded operand, the output side is written (and href read) by the epilogue
+    int in_pitch = 0, in_valid = 0, out_pitch = Cout, out_valid = Cout;
+    if (vw) {
+        in_pitch = mode == 0 ? vw->L_pitch : vw->S_pitch; in_valid = mode == 0 ? vw->L_valid : vw->S_valid;
+        const int op = mode == 0 ? vw->S_pitch : vw->L_pitch, ov = mode == 0 ? vw->S_valid : vw->L_valid;
+        if (op > 0) out_pitch = op;
+        if (ov > 0) out_valid = ov;
+        if ((in_pitch | in_valid | out_pitch | out_valid) & 7) return 0;          // 16-byte granularity
+        if (in_valid > Cin || out_valid > Cout || (in_pitch > 0 && in_pitch < (in_valid > 0 ? in_valid : Cin)) || out_pitch < out_valid) return 0;
+    }
     if (Cin % KCH != 0) return 0;
     int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 0));
     if (BN == 0) return 0;
@@ -760,11 +800,12 @@ int umma_conv(int mode, const void* src, const void* W, void* out, int n, const 
     p.Cin = Cin; p.Cout = Cout; p.R = g->R; p.S = g->S; p.stride = g->stride; p.pad = g->pad;
     p.Hout = mode == 0 ? g->Hs : g->Hl; p.Wout = mode == 0 ? g->Ws : g->Wl;
     p.bias = bias; p.bias_mod = bias_mod; p.href = (const bf16*)href; p.out = (bf16*)out;
+    p.out_pitch = out_pitch; p.out_valid = out_valid;
     p.epi = epi; p.act = act; p.slope = slope;
     CUtensorMap tmA, tmB;
     int rc;
-    if (mode == 0) rc = encode_act(&tmA, src, n, g->Hl, g->Wl, g->Cb, p.TW, p.TH, p.TN, g->stride);
-    else rc = encode_act(&tmA, src, n, g->Hs, g->Ws, g->Ca, p.TW, p.TH, p.TN, 1);
+    if (mode == 0) rc = encode_act(&tmA, src, n, g->Hl, g->Wl, g->Cb, p.TW, p.TH, p.TN, g->stride, in_pitch, in_valid);
+    else rc = encode_act(&tmA, src, n, g->Hs, g->Ws, g->Ca, p.TW, p.TH, p.TN, 1, in_pitch, in_valid);
     if (rc) return rc;
     rc = encode_mat(&tmB, W, Cout, (long long)g->R * g->S * Cin, BN);
     if (rc) return rc;
@@ -792,8 +833,10 @@ int umma_conv(int mode, const void* src, const void* W, void* out, int n, const 
     }
 }
 
-int umma_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, cudaStream_t st) {
+int umma_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, const srgan_views* vw, cudaStream_t st) {
     if (g->Ca % 64 != 0 || g->Cb % 64 != 0) return 0;   // Ca = 64 (mod 128): the upper half tile is TMA zero fill
+    if (vw && ((vw->S_pitch | vw->S_valid | vw->L_pitch | vw->L_valid) & 7)) return 0;
+    if (vw && (vw->S_valid > g->Ca || vw->L_valid > g->Cb)) return 0;
     int BN = g->Cb % 256 == 0 ? 256 : (g->Cb % 128 == 0 ? 128 : 64);
     const int taps = g->R * g->S;
     int NT = 512 / BN;                                         // largest divisor of the tap count that fits TMEM (3 for 3x3)
@@ -844,9 +887,9 @@ int umma_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom*
     p.chunks_per_split = (total_chunks + splits - 1) / splits;
     splits = (total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
     CUtensorMap tmS, tmL;
-    int rc = encode_act(&tmS, S, n, g->Hs, g->Ws, g->Ca, p.TW, p.TH, p.TN, 1);
+    int rc = encode_act(&tmS, S, n, g->Hs, g->Ws, g->Ca, p.TW, p.TH, p.TN, 1, vw ? vw->S_pitch : 0, vw ? vw->S_valid : 0);
     if (rc) return rc;
-    rc = encode_act(&tmL, L, n, g->Hl, g->Wl, g->Cb, p.TW, p.TH, p.TN, g->stride);
+    rc = encode_act(&tmL, L, n, g->Hl, g->Wl, g->Cb, p.TW, p.TH, p.TN, g->stride, vw ? vw->L_pitch : 0, vw ? vw->L_valid : 0);
     if (rc) return rc;
     dim3 grid(out_tiles, 1, splits);
     if (BN == 256) return launch_wgrad<256, 32>(tmS, tmL, p, grid, st);

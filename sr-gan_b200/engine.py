@@ -297,7 +297,7 @@ class Engine:
         return self.buf(('coltmp',), (n * l.geom.Hs * l.geom.Ws * l.kpad,))
 
     def _fwd_layer(self, st: NetState, l: Layer, x, y, n, bias=True, href=None, epi=EPI_BIAS_ACT, act=None, slope=None,
-                   lo=0):
+                   lo=0, views=None):
         act = l.act if act is None else act
         slope = l.slope if slope is None else slope
         b = st.params[l.name + '.bias'] if (bias and l.has_bias) else None
@@ -312,6 +312,10 @@ class Engine:
                 ycol = self._coltmp(l, n)
                 self.ops.conv_up(x, st.wu_[l.name], ycol, n * P, self._lin(l), None, 0, None, EPI_DACT, ACT_NONE, 0.0)
                 self.ops.col2im(ycol, y, n, l.geom, l.kpad, b, href, epi, act, slope)
+        elif views is not None:                # channel window on the output side (dense-layer conv2 -> concat buffer)
+            if l.fwd != 'down':
+                raise ValueError('channel windows are implemented for forward-down layers')
+            self.ops.conv_down(x, st.wd_[l.name], y, n, l.geom, b, l.bias_mod, href, epi, act, slope, views=views)
         elif l.fwd == 'down':
             self.ops.conv_down(x, st.wd_[l.name], y, n, l.geom, b, l.bias_mod, href, epi, act, slope)
         else:
@@ -363,10 +367,13 @@ class Engine:
         return {'count': n, 'ms': ms, 'flops_per_launch': pr['flops'] / n,
                 'bytes_per_launch': pr['elems'] / n * (2 if self.act_dtype == torch.bfloat16 else 4), 'kernel': pr['label']}
 
-    def _bwd_data_layer(self, st: NetState, l: Layer, dy, dx, n, href, act, slope, lo=0, col_ready=False):
+    def _bwd_data_layer(self, st: NetState, l: Layer, dy, dx, n, href, act, slope, lo=0, col_ready=False, views=None):
         """dx = (W_l^T dy) * act'(href)   (act = ACT_NONE: no mask)."""
         timed = self._probe_open('dgrad', st, l, n)
-        self._bwd_data_layer_(st, l, dy, dx, n, href, act, slope, lo, col_ready)
+        if views is not None:                  # dy is a channel window of a concat delta (forward-down layers only)
+            self.ops.conv_up(dy, st.wu_[l.name], dx, n, l.geom, None, 0, href, EPI_DACT, act, slope, views=views)
+        else:
+            self._bwd_data_layer_(st, l, dy, dx, n, href, act, slope, lo, col_ready)
         self._probe_close(timed)
 
     def _bwd_data_layer_(self, st: NetState, l: Layer, dy, dx, n, href, act, slope, lo, col_ready):
@@ -386,9 +393,12 @@ class Engine:
         else:
             self.ops.conv_down(dy, st.wd_[l.name], dx, n, l.geom, None, 0, href, EPI_DACT, act, slope)
 
-    def _wgrad_layer(self, st: NetState, l: Layer, x_in, dy, n, lo=0):
+    def _wgrad_layer(self, st: NetState, l: Layer, x_in, dy, n, lo=0, views=None):
         timed = self._probe_open('wgrad', st, l, n)
-        self._wgrad_layer_(st, l, x_in, dy, n, lo)
+        if views is not None:
+            self.ops.conv_wgrad(dy, x_in, st.g(l.name + '.weight'), n, l.geom, views=views)
+        else:
+            self._wgrad_layer_(st, l, x_in, dy, n, lo)
         self._probe_close(timed)
 
     def _wgrad_layer_(self, st: NetState, l: Layer, x_in, dy, n, lo):
@@ -449,6 +459,12 @@ class Engine:
     def _brows(t, b, lo, hi):
         e = b.rows * b.ch
         return t[lo * e: hi * e]
+
+    @staticmethod
+    def _window(op, net: Net):
+        """srgan_views tuple (S_pitch, S_valid, L_pitch, L_valid) of a conv op whose output is a channel window of its
+        destination buffer, else None."""
+        return (net.bufs[op.dst].ch, op.C, 0, 0) if op.C else None
 
     @staticmethod
     def _in(net: Net, acts):
@@ -534,8 +550,8 @@ class Engine:
         for op in net.graph:
             sb, db = net.bufs[op.src], net.bufs[op.dst]
             if op.kind == 'conv':
-                self._wgrad_layer(st, op.layer, R(acts[op.src], sb, tlo, thi), R(deltas[op.dst], db, tlo, thi),
-                                  n * op.layer.gemm_rows, lo=tlo)
+                self._wgrad_layer(st, op.layer, R(acts[op.src], sb, tlo, thi), R(deltas[op.dst], db, tlo, thi)[op.c0:],
+                                  n * op.layer.gemm_rows, lo=tlo, views=self._window(op, net))
             elif op.kind == 'affine':
                 P, nm = st.params, op.name
                 self.ops.affine_grad(R(deltas[op.dst], db, tlo, thi), db.ch, R(acts[op.src], sb, tlo, thi), sb.ch, op.c0,
@@ -601,10 +617,13 @@ class Engine:
         href = R(acts[op.dst], db, mlo, mlo + n) if tangent else None
         if op.kind == 'conv':
             ng = n * op.layer.gemm_rows
+            vw = self._window(op, net)
+            if vw is not None:                 # the layer's channels of the concat buffer, written in place (no activation)
+                y, href = y[op.c0:], None
             if tangent:
-                self._fwd_layer(st, op.layer, x, y, ng, bias=False, href=href, epi=EPI_DACT, lo=lo)
+                self._fwd_layer(st, op.layer, x, y, ng, bias=False, href=href, epi=EPI_DACT, lo=lo, views=vw)
             else:
-                self._fwd_layer(st, op.layer, x, y, ng, lo=lo)
+                self._fwd_layer(st, op.layer, x, y, ng, lo=lo, views=vw)
         elif op.kind == 'affine':
             nm = op.name
             ops.affine(x, sb.ch, op.c0, y, db.ch, n * sb.rows, op.C, P[nm + '.weight'], P[nm + '.bias'],
@@ -673,10 +692,13 @@ class Engine:
                 hook(op.dst)
             if op.kind == 'conv':
                 l = op.layer
+                vw = self._window(op, net)
+                if vw is not None:
+                    dy = dy[op.c0:]
                 if weight_grads:
-                    def wg(l=l, op=op, sb=sb, db=db, dy=dy):
-                        self._wgrad_layer(st, l, R(acts[op.src], sb, wlo, whi), R(deltas[op.dst], db, wlo, whi),
-                                          (whi - wlo) * l.gemm_rows, lo=wlo)
+                    def wg(l=l, op=op, sb=sb, db=db, dy=dy, vw=vw):
+                        self._wgrad_layer(st, l, R(acts[op.src], sb, wlo, whi), R(deltas[op.dst], db, wlo, whi)[op.c0:],
+                                          (whi - wlo) * l.gemm_rows, lo=wlo, views=vw)
                         if l.has_bias:
                             self._bias_grad(st, l, dy, n * db.rows)
                     if l.name in st.thin and l.fwd != 'down':      # its im2col output is reused by the data gradient below
@@ -688,7 +710,7 @@ class Engine:
                         dinput, ihref, iact = input_grad
                         self._bwd_data_layer(st, l, dy, dinput, n * l.gemm_rows, ihref, iact, 0.0, lo=lo)
                 else:
-                    self._bwd_data_layer(st, l, dy, dx, n * l.gemm_rows, xa, sb.act, sb.slope, lo=lo)
+                    self._bwd_data_layer(st, l, dy, dx, n * l.gemm_rows, xa, sb.act, sb.slope, lo=lo, views=vw)
             elif op.kind == 'affine':
                 nm = op.name
                 mean, var = P[nm + '.running_mean'], P[nm + '.running_var']

@@ -18,6 +18,7 @@ App. E.1), distance callables not in utility.py:201-243, modules without a B200 
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -260,8 +261,10 @@ class StepRunner:
             raise RuntimeError('the B200 step needs the networks on a CUDA device (call gpu_mode() first)')
         self.device = dev
         self.modules = dict(D=D, G=G, DNN=DNN)
-        d_net, g_net = nets.describe_module(D), nets.describe_module(G)
-        if nets.describe_module(DNN) != d_net:
+        # bf16 mode: dense layers write / read their channel window of the concat buffers in place (tcgen05 kernels only)
+        direct = precision == 'bf16' and os.environ.get('SRGAN_NO_DIRECT_CONCAT', '0') != '1'
+        d_net, g_net = nets.describe_module(D, direct), nets.describe_module(G)
+        if nets.describe_module(DNN, direct) != d_net:
             raise ValueError('DNN and D must share an architecture (srgan.py model_setup)')
         if method not in ('srgan', 'dggan'):
             raise ValueError(f'method={method!r}: the B200 path covers srgan and dggan (sgan: SURVEY 8f rank 3)')
@@ -280,7 +283,6 @@ class StepRunner:
         # device noise stream (draw_noise): every rank draws its OWN shard of the global batch's z / alpha / z2
         self.generator = torch.Generator(device=dev)
         self.generator.manual_seed(int(getattr(settings, 'noise_seed', 0)) + (comm.rank if comm is not None else 0))
-        import os
         ug = getattr(settings, 'use_cuda_graph', True)
         # multi-rank steps are captured PIECEWISE: one graph segment between every two collectives, the NCCL all-reduces
         # (feature sums, gradients) are issued eagerly between the segments on the same stream (_capture_segments)

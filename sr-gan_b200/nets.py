@@ -134,7 +134,8 @@ class Buf:
 @dataclass
 class Op:
     """One node of a graph net.  kind:
-      'conv'    layer (dense src -> dense dst, the conv-pair kernels);
+      'conv'    layer (dense src -> dense dst, the conv-pair kernels; C > 0: dst[:, c0:c0+C] is a channel window of a concat
+                buffer, written / read in place through srgan_views);
       'affine'  eval-mode BatchNorm + ReLU: dst[:, :C] = relu(gamma*(src[:, c0:c0+C]-mean)/sqrt(var+eps)+beta), `name` = BN prefix;
       'copy'    dst[:, c0:c0+C] = src (dense C)        (concat write / feature slice write);
       'read'    dst (dense C)   = src[:, c0:c0+C]      (tap of a concat buffer);
@@ -266,14 +267,16 @@ def dcgan_g(image_size=128, conv_dim=64, z_dim=256) -> Net:
 
 
 def knn_densenet_cat(block_config=(6, 12, 48, 32), growth_rate=32, num_init_features=64, bn_size=4, image_size=224,
-                     label_size=224, pad_to=64, n_out=1) -> Net:
+                     label_size=224, pad_to=64, n_out=1, direct_concat=False) -> Net:
     """crowd/models.py:1049-1166 KnnDenseNetCat as a graph.  Buffers: 'x' input; 'c0','n0' stem; 'cat{i}' the in-place
     concat buffer of dense block i (the stem pool / transition pool write its first channels, every dense layer appends
     growth_rate channels); per dense layer 'n1','b','n2','new'; per transition 'tn','tc'; per MapModule 't','map','m1'..
     'm3','h'; 'n5','fp','fcf'; 'features' [1 x 80].  Spatial sizes follow torch: stem conv k7 s2 p3, max-pool k3 s2 p1,
     transitions avg-pool 2.  The operand buffers of the trunk convolutions ('n1', 'new', ...) are padded to multiples of
     `pad_to` channels so that every trunk contraction is tcgen05-eligible (K and N multiples of 64); 1x1 convolutions are
-    declared as [pixels x C] GEMMs (Layer.gemm_rows)."""
+    declared as [pixels x C] GEMMs (Layer.gemm_rows).  direct_concat: the 3x3 convolution of a dense layer writes its
+    growth_rate channels straight into their window of the concat buffer and its gradients read that window of the concat
+    delta (Op.C / Op.c0 on the conv op, srgan_views in the kernels): no 'new' buffer, no slice copies."""
     g, bs = growth_rate, bn_size
 
     def pad(c):
@@ -322,9 +325,13 @@ def knn_densenet_cat(block_config=(6, 12, 48, 32), growth_rate=32, num_init_feat
             conv(pre + '.conv1', 'n1.' + tag, 'b.' + tag, linear_geom(cb, pad(c)), 'down', (bs * g, c, 1, 1), gemm_rows=h * h)
             buf('n2.' + tag, h * h, cb, **RELU)
             ops.append(Op('affine', 'b.' + tag, 'n2.' + tag, name=pre + '.norm2', C=bs * g))
-            buf('new.' + tag, h * h, pad(g))
-            conv(pre + '.conv2', 'n2.' + tag, 'new.' + tag, Geom(h, h, pad(g), h, h, cb, 3, 3, 1, 1), 'down', (g, bs * g, 3, 3))
-            ops.append(Op('copy', 'new.' + tag, cat, C=g, c0=c))
+            if direct_concat:
+                conv(pre + '.conv2', 'n2.' + tag, cat, Geom(h, h, pad(g), h, h, cb, 3, 3, 1, 1), 'down', (g, bs * g, 3, 3))
+                ops[-1].C, ops[-1].c0 = g, c
+            else:
+                buf('new.' + tag, h * h, pad(g))
+                conv(pre + '.conv2', 'n2.' + tag, 'new.' + tag, Geom(h, h, pad(g), h, h, cb, 3, 3, 1, 1), 'down', (g, bs * g, 3, 3))
+                ops.append(Op('copy', 'new.' + tag, cat, C=g, c0=c))
             c += g
         if bi != len(block_config):
             pre = f'transition_layers.transition{bi}'
@@ -383,7 +390,7 @@ def knn_densenet_cat(block_config=(6, 12, 48, 32), growth_rate=32, num_init_feat
                feature_buf='features', head_parts=head_parts, map_bufs=tuple(maps), label_size=L)
 
 
-def describe_module(module) -> Net:
+def describe_module(module, direct_concat=False) -> Net:
     """Maps a reference nn.Module instance (or this package's mirrors) to its Net, by structure, not by import."""
     sd = {k: tuple(v.shape) for k, v in module.state_dict().items()}
     if 'linear4.weight' in sd and 'linear1.weight' in sd:
@@ -408,7 +415,8 @@ def describe_module(module) -> Net:
         label = sd['map_module1.linear1.weight'][2] * 8
         k1 = sd['map_module1.map_transposed_conv_layer.weight'][2]
         image = (label // k1) * 8
-        return knn_densenet_cat(cfg, growth, init, bn_size, image, label, n_out=sd['count_layer.weight'][0])
+        return knn_densenet_cat(cfg, growth, init, bn_size, image, label, n_out=sd['count_layer.weight'][0],
+                                direct_concat=direct_concat and growth % 8 == 0 and init % 8 == 0)
     if 'fc.0.weight' in sd and 'layer4.0.weight' in sd:
         z_dim, c8, k, _ = sd['fc.0.weight']
         return dcgan_g(k * 16, c8 // 8, z_dim)

@@ -21,6 +21,11 @@ class Geom(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int) for k in ('Hs', 'Ws', 'Ca', 'Hl', 'Wl', 'Cb', 'R', 'S', 'stride', 'pad')]
 
 
+class Views(ctypes.Structure):
+    """srgan_views: channel windows of the small / large side operands (0 = dense)."""
+    _fields_ = [(k, ctypes.c_int) for k in ('S_pitch', 'S_valid', 'L_pitch', 'L_valid')]
+
+
 _EXPORTS = (
     'srgan_version', 'srgan_last_error', 'srgan_launch_count', 'srgan_last_path_tensor', 'srgan_set_force_simt',
     'srgan_tensor_launch_count', 'srgan_simt_fallback_count',
@@ -56,10 +61,11 @@ def load_library(path: str = LIB_PATH):
     lib.srgan_last_path_tensor.restype = c_int
     lib.srgan_set_force_simt.argtypes = [c_int]
     lib.srgan_set_force_simt.restype = None
-    conv_args = [vp, vp, vp, c_int, gp, vp, c_int, vp, c_int, c_int, c_f, c_int, vp]
+    vwp = ctypes.POINTER(Views)
+    conv_args = [vp, vp, vp, c_int, gp, vp, c_int, vp, c_int, c_int, c_f, c_int, vwp, vp]
     lib.srgan_conv_down.argtypes = conv_args
     lib.srgan_conv_up.argtypes = conv_args
-    lib.srgan_conv_wgrad.argtypes = [vp, vp, vp, c_int, gp, c_int, vp]
+    lib.srgan_conv_wgrad.argtypes = [vp, vp, vp, c_int, gp, c_int, vwp, vp]
     lib.srgan_colsum.argtypes = [vp, c_ll, c_int, vp, c_int, vp, c_int, vp]
     lib.srgan_rowdot.argtypes = [vp, c_int, c_int, vp, vp, c_int, vp, c_int, vp]
     lib.srgan_seed_rows.argtypes = [vp, c_int, c_int, vp, vp, vp, vp, c_int, c_f, c_int, vp]
@@ -120,6 +126,7 @@ class CudaOps:
         self.lib = load_library()
         self.device = torch.device(device)
         self._geoms = {}
+        self._views_cache = {}
         self._stream_handle = None
         self._tables = {}                          # adam_multi device tables, one per NetState
 
@@ -186,21 +193,35 @@ class CudaOps:
                                        (ctypes.c_longlong * 4)(*s2) if s2 else None, _dt(od), self._stream()),
                  'srgan_repack')
 
-    def conv_down(self, L, Wd, S_out, n, g, bias, bias_mod, href, epi, act, slope):
+    def _views(self, views):
+        """views = (S_pitch, S_valid, L_pitch, L_valid) or None -> cached ctypes struct pointer."""
+        if views is None:
+            return None
+        c = self._views_cache.get(views)
+        if c is None:
+            c = self._views_cache[views] = Views(*views)
+        return ctypes.byref(c)
+
+    @staticmethod
+    def views_supported(g, dtype):
+        """Channel windows are a feature of the TMA-fed tcgen05 kernels (csrc/umma_conv.cu)."""
+        return dtype == torch.bfloat16 and g.Ca % 64 == 0 and g.Cb % 64 == 0
+
+    def conv_down(self, L, Wd, S_out, n, g, bias, bias_mod, href, epi, act, slope, views=None):
         self._ck(self.lib.srgan_conv_down(self._p(L), self._p(Wd, L.dtype), self._p(S_out, L.dtype), n, self._geom(g),
                                           self._p(bias.detach(), torch.float32) if bias is not None else None, bias_mod,
                                           self._p(href, L.dtype) if href is not None else None, epi, act, slope,
-                                          _dt(L.dtype), self._stream()), 'srgan_conv_down')
+                                          _dt(L.dtype), self._views(views), self._stream()), 'srgan_conv_down')
 
-    def conv_up(self, S, Wu, L_out, n, g, bias, bias_mod, href, epi, act, slope):
+    def conv_up(self, S, Wu, L_out, n, g, bias, bias_mod, href, epi, act, slope, views=None):
         self._ck(self.lib.srgan_conv_up(self._p(S), self._p(Wu, S.dtype), self._p(L_out, S.dtype), n, self._geom(g),
                                         self._p(bias.detach(), torch.float32) if bias is not None else None, bias_mod,
                                         self._p(href, S.dtype) if href is not None else None, epi, act, slope,
-                                        _dt(S.dtype), self._stream()), 'srgan_conv_up')
+                                        _dt(S.dtype), self._views(views), self._stream()), 'srgan_conv_up')
 
-    def conv_wgrad(self, S, L, dW, n, g):
+    def conv_wgrad(self, S, L, dW, n, g, views=None):
         self._ck(self.lib.srgan_conv_wgrad(self._p(S), self._p(L, S.dtype), self._p(dW, torch.float32), n,
-                                           self._geom(g), _dt(S.dtype), self._stream()), 'srgan_conv_wgrad')
+                                           self._geom(g), _dt(S.dtype), self._views(views), self._stream()), 'srgan_conv_wgrad')
 
     def colsum(self, X, rows, cols, out, mod, rowscale):
         self._ck(self.lib.srgan_colsum(self._p(X), rows, cols, self._p(out, torch.float32), mod,

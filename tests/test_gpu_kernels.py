@@ -69,8 +69,8 @@ def test_conv_down_up_wgrad(ops, dt, gi):
     Wd = (rnd(gen, g.Ca * g.R * g.S * g.Cb) * 0.3).to(dt)
     Wu = Wd.view(g.Ca, g.R, g.S, g.Cb).permute(3, 1, 2, 0).contiguous().view(-1)
     bias_a, bias_b = rnd(gen, g.Ca), rnd(gen, g.Cb)
-    for epi, act, slope in ((0, 1, 0.05), (0, 2, 0.0), (0, 0, 0.0), (1, 1, 0.01), (1, 2, 0.0), (1, 0, 0.0)):
-        # down
+    for epi, act, slope in ((0, 1, 0.05), (0, 2, 0.0), (0, 0, 0.0), (1, 1, 0.01), (1, 1, 0.0), (1, 2, 0.0), (1, 0, 0.0)):
+        # down            (epi 1, act 1, slope 0 = the ReLU mask: packed fast path of the tcgen05 epilogue)
         href = rnd(gen, S.numel(), dt=dt)
         out_ref = torch.empty_like(S)
         ref.conv_down(L, Wd, out_ref, n, g, bias_a if epi == 0 else None, 0, href if epi == 1 else None, epi, act, slope)
@@ -95,6 +95,64 @@ def test_conv_down_up_wgrad(ops, dt, gi):
     close(dW, dW_ref, tol(dt) * 2, 'wgrad')
     if dt == torch.bfloat16 and gi in WGRAD_TENSOR_ELIGIBLE:
         assert ops.lib.srgan_last_path_tensor() == 1, 'expected the tcgen05 wgrad path'
+
+
+@pytest.mark.parametrize('valid,c0,pitch', [(32, 96, 160), (8, 24, 40), (64, 64, 128)])
+@pytest.mark.parametrize('hw', [14, 7, 8])
+def test_conv_channel_windows(ops, valid, c0, pitch, hw):
+    """srgan_views: a DenseNet dense layer's 3x3 convolution (crowd/models.py:345,353) writes its growth_rate channels in
+    place into their window [c0, c0+valid) of the concat buffer (pitch channels wide) and its data / weight gradients read
+    that window of the concat delta; bf16 tcgen05 path against the dense op-level semantics.  The rest of the concat buffer
+    must stay untouched."""
+    dt = torch.bfloat16
+    g = Geom(hw, hw, 64, hw, hw, 128, 3, 3, 1, 1)          # Ca padded to 64, `valid` of them real
+    n = 37
+    gen = torch.Generator().manual_seed(valid + hw)
+    ref = TorchOps()
+    pix = n * hw * hw
+    L = rnd(gen, pix * g.Cb, dt=dt)
+    Wd4 = (rnd(gen, g.Ca, g.R * g.S * g.Cb) * 0.1)
+    Wd4[valid:] = 0                                          # pad rows of the kernel-layout weights are zero
+    Wd = Wd4.reshape(-1).to(dt)
+    Wu = Wd.view(g.Ca, g.R, g.S, g.Cb).permute(3, 1, 2, 0).contiguous().view(-1)
+    vw = (pitch, valid, 0, 0)
+    cat0 = rnd(gen, pix * pitch, dt=dt)
+    # forward / tangent: window write
+    for epi in (0, 1):
+        cat_ref, cat = cat0.clone(), cat0.clone().cuda()
+        ref.conv_down(L, Wd, cat_ref[c0:], n, g, None, 0, None, epi, 0, 0.0, views=vw)
+        ops.conv_down(L.cuda(), Wd.cuda(), cat[c0:], n, g, None, 0, None, epi, 0, 0.0, views=vw)
+        assert ops.lib.srgan_last_path_tensor() == 1
+        close(cat.view(pix, pitch)[:, c0:c0 + valid], cat_ref.view(pix, pitch)[:, c0:c0 + valid], tol(dt), 'window write')
+        mask = torch.ones(pix, pitch, dtype=torch.bool)
+        mask[:, c0:c0 + valid] = False
+        assert torch.equal(cat.cpu().view(pix, pitch)[mask], cat0.view(pix, pitch)[mask]), 'wrote outside the window'
+    # data gradient: window read (ReLU mask of the dense 128-channel operand)
+    dcat = rnd(gen, pix * pitch, dt=dt)
+    href = rnd(gen, L.numel(), dt=dt)
+    dx_ref, dx = torch.empty_like(L), torch.empty_like(L, device='cuda')
+    ref.conv_up(dcat[c0:], Wu, dx_ref, n, g, None, 0, href, 1, 1, 0.0, views=vw)
+    ops.conv_up(dcat.cuda()[c0:], Wu.cuda(), dx, n, g, None, 0, href.cuda(), 1, 1, 0.0, views=vw)
+    assert ops.lib.srgan_last_path_tensor() == 1
+    close(dx, dx_ref, tol(dt), 'window dgrad')
+    # weight gradient: window read on the small side
+    dW_ref = rnd(gen, Wd.numel())
+    dW = dW_ref.clone().cuda()
+    ref.conv_wgrad(dcat[c0:], L, dW_ref, n, g, views=vw)
+    ops.conv_wgrad(dcat.cuda()[c0:], L.cuda(), dW, n, g, views=vw)
+    assert ops.lib.srgan_last_path_tensor() == 1
+    close(dW, dW_ref, tol(dt) * 2, 'window wgrad')
+
+
+def test_conv_channel_windows_need_the_tensor_path(ops):
+    """No second implementation behind srgan_views: an fp32 call (or a shape that is not tcgen05-eligible) raises."""
+    g = Geom(8, 8, 64, 8, 8, 128, 3, 3, 1, 1)
+    n = 2
+    L = torch.zeros(n * 64 * 128, device='cuda')
+    W = torch.zeros(64 * 9 * 128, device='cuda')
+    out = torch.zeros(n * 64 * 160, device='cuda')
+    with pytest.raises(RuntimeError):
+        ops.conv_down(L, W, out, n, g, None, 0, None, 0, 0, 0.0, views=(160, 32, 0, 0))
 
 
 @pytest.mark.parametrize('dt', DT)

@@ -85,27 +85,61 @@ class TorchOps:
                 flat = flat * dact(href.to(flat.dtype), act, slope)
             out.copy_(flat.to(out.dtype))
 
-    def conv_down(self, L, Wd, S_out, n, g, bias, bias_mod, href, epi, act, slope):
-        self.launches += 1
-        cd = torch.float64 if L.dtype == torch.float64 else torch.float32
-        x = L.view(n, g.Hl, g.Wl, g.Cb).permute(0, 3, 1, 2).to(cd)
-        y = F.conv2d(x, self._w_from_wd(Wd, g).to(cd), None, stride=g.stride, padding=g.pad)
-        self._epilogue(y.permute(0, 2, 3, 1), S_out, bias, bias_mod, href, epi, act, slope)
+    # srgan_views emulation: a channel window (pitch, valid) of a wider buffer <-> the dense [pixels, C] operand
+    @staticmethod
+    def views_supported(g, dtype):
+        return True
 
-    def conv_up(self, S, Wu, L_out, n, g, bias, bias_mod, href, epi, act, slope):
+    @staticmethod
+    def _window_read(t, pixels, C, pitch, valid):
+        if not pitch and not valid:
+            return t[:pixels * C].view(pixels, C)
+        pitch, valid = pitch or C, valid or C
+        w = torch.as_strided(t, (pixels, valid), (pitch, 1))
+        return torch.cat([w, w.new_zeros(pixels, C - valid)], dim=1) if valid < C else w
+
+    @staticmethod
+    def _window_write(t, dense, pixels, C, pitch, valid):
+        """dense: [pixels * C] result; only the window's channels are stored."""
+        pitch, valid = pitch or C, valid or C
+        torch.as_strided(t, (pixels, valid), (pitch, 1)).copy_(dense.view(pixels, C)[:, :valid].to(t.dtype))
+
+    def conv_down(self, L, Wd, S_out, n, g, bias, bias_mod, href, epi, act, slope, views=None):
         self.launches += 1
+        sp, sv, lp, lv = views or (0, 0, 0, 0)
+        cd = torch.float64 if L.dtype == torch.float64 else torch.float32
+        x = self._window_read(L, n * g.Hl * g.Wl, g.Cb, lp, lv).reshape(n, g.Hl, g.Wl, g.Cb).permute(0, 3, 1, 2).to(cd)
+        y = F.conv2d(x, self._w_from_wd(Wd, g).to(cd), None, stride=g.stride, padding=g.pad)
+        if sp or sv:
+            dense = torch.empty(n * g.Hs * g.Ws * g.Ca, dtype=S_out.dtype)
+            hr = None if href is None else self._window_read(href, n * g.Hs * g.Ws, g.Ca, sp, sv).reshape(-1)
+            self._epilogue(y.permute(0, 2, 3, 1), dense, bias, bias_mod, hr, epi, act, slope)
+            self._window_write(S_out, dense, n * g.Hs * g.Ws, g.Ca, sp, sv)
+        else:
+            self._epilogue(y.permute(0, 2, 3, 1), S_out, bias, bias_mod, href, epi, act, slope)
+
+    def conv_up(self, S, Wu, L_out, n, g, bias, bias_mod, href, epi, act, slope, views=None):
+        self.launches += 1
+        sp, sv, lp, lv = views or (0, 0, 0, 0)
         cd = torch.float64 if S.dtype == torch.float64 else torch.float32
-        x = S.view(n, g.Hs, g.Ws, g.Ca).permute(0, 3, 1, 2).to(cd)
+        x = self._window_read(S, n * g.Hs * g.Ws, g.Ca, sp, sv).reshape(n, g.Hs, g.Ws, g.Ca).permute(0, 3, 1, 2).to(cd)
         opad = g.Hl - ((g.Hs - 1) * g.stride - 2 * g.pad + g.R)
         y = F.conv_transpose2d(x, self._w_from_wu(Wu, g).to(cd), None, stride=g.stride, padding=g.pad,
                                output_padding=opad)
-        self._epilogue(y.permute(0, 2, 3, 1), L_out, bias, bias_mod, href, epi, act, slope)
+        if lp or lv:
+            dense = torch.empty(n * g.Hl * g.Wl * g.Cb, dtype=L_out.dtype)
+            hr = None if href is None else self._window_read(href, n * g.Hl * g.Wl, g.Cb, lp, lv).reshape(-1)
+            self._epilogue(y.permute(0, 2, 3, 1), dense, bias, bias_mod, hr, epi, act, slope)
+            self._window_write(L_out, dense, n * g.Hl * g.Wl, g.Cb, lp, lv)
+        else:
+            self._epilogue(y.permute(0, 2, 3, 1), L_out, bias, bias_mod, href, epi, act, slope)
 
-    def conv_wgrad(self, S, L, dW, n, g):
+    def conv_wgrad(self, S, L, dW, n, g, views=None):
         self.launches += 1
+        sp, sv, lp, lv = views or (0, 0, 0, 0)
         cd = dW.dtype
-        s = S.view(n, g.Hs, g.Ws, g.Ca).permute(0, 3, 1, 2).to(cd)
-        l = L.view(n, g.Hl, g.Wl, g.Cb).permute(0, 3, 1, 2).to(cd)
+        s = self._window_read(S, n * g.Hs * g.Ws, g.Ca, sp, sv).reshape(n, g.Hs, g.Ws, g.Ca).permute(0, 3, 1, 2).to(cd)
+        l = self._window_read(L, n * g.Hl * g.Wl, g.Cb, lp, lv).reshape(n, g.Hl, g.Wl, g.Cb).permute(0, 3, 1, 2).to(cd)
         gw = torch.nn.grad.conv2d_weight(l, (g.Ca, g.Cb, g.R, g.S), s, stride=g.stride, padding=g.pad)   # [a,b,r,s]
         dW += gw.permute(0, 2, 3, 1).reshape(-1)
 
