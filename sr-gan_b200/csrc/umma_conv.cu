@@ -159,6 +159,8 @@ struct UmmaConvParams {
     int epi, act;
     float slope;
     int stages;
+    int href_smem;                // 1: the epilogue's href pieces of tile i+1 are fetched with cp.async into a shared-memory
+                                  // landing zone while tile i is processed (short-K GEMMs: the MMAs do not hide the latency)
 };
 
 // Epilogue math on one 32-column chunk of one accumulator row (all branches are warp-uniform and hoisted out of the
@@ -248,6 +250,12 @@ __device__ __forceinline__ uint32_t stg_addr(uint32_t base, int row, int unit) {
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// 16-byte asynchronous global -> shared copy; src_bytes = 0 writes zeros (out-of-range rows / channels)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
@@ -412,14 +420,12 @@ __global__ void __launch_bounds__(PC_THREADS, 1) umma_conv_persistent_kernel(con
         const int t_unit = lane & 3, t_row = lane >> 2;       // transposed role: unit t_unit of rows 8*it + t_row
         const bool use_href = p.epi != SRGAN_EPI_BIAS_ACT && p.href != nullptr && p.act != SRGAN_ACT_NONE;
         constexpr int NCH = (BN / 32 + 1) / 2;   // chunks per sub-tile handled by this warp (BN = 64: one)
-        int tl = 0;
-        for (int tile = blockIdx.x; tile < pp.total_tiles; tile += gridDim.x, ++tl) {
-            const Tile T = decode(tile);
-            const int buf = tl & 1;
-            const uint32_t bph = (tl >> 1) & 1;
+        const bool hsm = use_href && p.href_smem;
+        // landing zone of the cp.async href prefetch: per warp MT x NCH blocks of 32 rows x 64 bytes, XOR-swizzled like stg
+        const uint32_t hz = tiles + (uint32_t)stages * STAGE_BYTES + 8u * EPI_STG_BYTES + (uint32_t)ew * (MT * NCH * EPI_STG_BYTES);
+        // element offsets of the rows this lane moves in the transposed accesses (-1: row beyond the last sample)
+        auto row_offsets = [&](const Tile& T, long long (&o_t)[MT][4]) {
             const int c0 = T.ny * BN;
-            // element offsets of the rows this lane moves in the transposed accesses (-1: row beyond the last sample)
-            long long o_t[MT][4];
 #pragma unroll
             for (int i = 0; i < MT; ++i) {
                 const int ms = T.mt * MT + i;
@@ -433,9 +439,54 @@ __global__ void __launch_bounds__(PC_THREADS, 1) umma_conv_persistent_kernel(con
 #pragma unroll
                 for (int it = 0; it < 4; ++it) o_t[i][it] = __shfl_sync(0xffffffffu, o, 8 * it + t_row);
             }
-            // the tile's href pieces are requested before the accumulator is waited for: their latency hides behind the MMAs
+        };
+        // issue the asynchronous copies of one tile's href pieces into the landing zone (out-of-range pieces are zero-filled)
+        auto href_prefetch = [&](int tile) {
+            const Tile T = decode(tile);
+            const int c0 = T.ny * BN;
+            long long o_n[MT][4];
+            row_offsets(T, o_n);
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int jj = 0; jj < NCH; ++jj) {
+                    const int j = half + 2 * jj;
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const bool ok = j < BN / 32 && c0 + j * 32 + t_unit * 8 < p.out_valid && o_n[i][it] >= 0;
+                        const bf16* src = ok ? p.href + o_n[i][it] + j * 32 + t_unit * 8 : p.href;
+                        cp_async16(stg_addr(hz + (uint32_t)(i * NCH + jj) * EPI_STG_BYTES, 8 * it + t_row, t_unit), src, ok ? 16u : 0u);
+                    }
+                }
+            cp_async_commit();
+        };
+        if (hsm && (int)blockIdx.x < pp.total_tiles) href_prefetch(blockIdx.x);
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < pp.total_tiles; tile += gridDim.x, ++tl) {
+            const Tile T = decode(tile);
+            const int buf = tl & 1;
+            const uint32_t bph = (tl >> 1) & 1;
+            const int c0 = T.ny * BN;
+            long long o_t[MT][4];
+            row_offsets(T, o_t);
+            // hreg: [hsm] this thread's OWN row of every chunk (4 x 16 bytes), read from the landing zone that was filled
+            // while the previous tile was processed; the copies of the NEXT tile are issued right after, so that they are
+            // in flight for a whole tile time.  [!hsm] the transposed pieces, requested before the accumulator is waited
+            // for (their latency hides behind a long K loop).
             uint4 hreg[MT][NCH][4];
-            if (use_href) {
+            if (hsm) {
+                cp_async_wait_all();
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < NCH; ++jj)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            hreg[i][jj][k] = lds128(stg_addr(hz + (uint32_t)(i * NCH + jj) * EPI_STG_BYTES, lane, k));
+                __syncwarp();
+                if (tile + (int)gridDim.x < pp.total_tiles) href_prefetch(tile + gridDim.x);
+            } else if (use_href) {
 #pragma unroll
                 for (int i = 0; i < MT; ++i)
 #pragma unroll
@@ -460,7 +511,10 @@ __global__ void __launch_bounds__(PC_THREADS, 1) umma_conv_persistent_kernel(con
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + i * BN + j * 32, v);
                     uint4 hv[4];
-                    if (use_href) {                           // transposed pieces -> this thread's own row
+                    if (hsm) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) hv[k] = hreg[i][jj][k];
+                    } else if (use_href) {                    // transposed pieces -> this thread's own row
 #pragma unroll
                         for (int it = 0; it < 4; ++it) sts128(stg_addr(stg, 8 * it + t_row, t_unit), hreg[i][jj][it]);
                         __syncwarp();
@@ -724,10 +778,19 @@ bool pick_patch(int W, int H, int rows, int max_w, int& TW, int& TH, int& TN) {
 template <int MT, int BN>
 int launch_conv_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaConvParamsP& pp, cudaStream_t st) {
     constexpr int stage_bytes = MT * A_STAGE_BYTES + BN * KCH * 2;
-    int stages = (212 * 1024) / stage_bytes;
+    // short-K GEMMs with a masking epilogue (the DenseNet trunk's data gradients: K = 128): the epilogue is the critical
+    // path and the href latency is not hidden by the MMAs (ncu: 15 % of all stall samples on the first use of the href
+    // registers) -> prefetch the next tile's href through a shared-memory landing zone (one tile of href bytes)
+    const int k_iters = pp.c.R * pp.c.S * (pp.c.Cin / KCH) / (pp.c.mode == 1 ? pp.c.stride * pp.c.stride : 1);
+    const bool use_href = pp.c.epi != SRGAN_EPI_BIAS_ACT && pp.c.href != nullptr && pp.c.act != SRGAN_ACT_NONE;
+    static const bool href_smem_on = [] { const char* e = getenv("SRGAN_NO_HREF_SMEM"); return !(e && e[0] == '1'); }();
+    pp.c.href_smem = (use_href && k_iters <= 4 && href_smem_on) ? 1 : 0;
+    const int zone = pp.c.href_smem ? MT * TILE_M * BN * 2 : 0;
+    int stages = (212 * 1024 - zone) / stage_bytes;
     if (stages > 12) stages = 12;
+    if (stages < 2) { pp.c.href_smem = 0; stages = (212 * 1024) / stage_bytes; }
     pp.c.stages = stages;
-    size_t smem = (size_t)stages * stage_bytes + 8 * EPI_STG_BYTES + 1024;   // ring + epilogue transposition buffers + alignment
+    size_t smem = (size_t)stages * stage_bytes + 8 * EPI_STG_BYTES + (pp.c.href_smem ? zone : 0) + 1024;   // ring + epilogue transposition buffers + href landing zone + alignment
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(umma_conv_persistent_kernel<MT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,

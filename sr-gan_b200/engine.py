@@ -201,13 +201,6 @@ class Engine:
         # tapped concat delta
         self.branch_streams = self.device.type == 'cuda' and os.environ.get('SRGAN_NO_BRANCH_STREAMS', '0') != '1'
         self._br_streams = {}
-        # graph nets: the discriminator step's two dependency chains -- the x_hat rows (forward -> g-chain -> penalty ->
-        # tangent -> backward: four passes that need nothing from the other rows) and the x | u | fake rows (forward ->
-        # feature sums -> distance losses -> backward) -- are enqueued on two streams.  The crowd step is a chain of ~2800
-        # small dependent launches that under-fill the GPU: two (with the DNN step, three) chains in flight fill it.
-        self.split_chains = self.device.type == 'cuda' and os.environ.get('SRGAN_NO_SPLIT_CHAINS', '0') != '1'
-        self._chain = ''                           # name of the chain being enqueued ('' = the caller's stream)
-        self._chain_streams = {}
         self._probe = None
         # srgan.py:332-386 side effects: keep a copy of the feature rows the reference would leave in
         # self.{labeled,unlabeled,fake,interpolates}_features (rows x | u | fake | x_hat of the D step; the fake block is
@@ -216,33 +209,6 @@ class Engine:
         for st in (self.D, self.G, self.DNN):
             if st is not None:
                 self.repack(st)
-
-    # ------------------------------------------------------------------ dependency chains on their own streams
-    def _chain_begin(self, name):
-        """Directs the following enqueues to chain `name`'s stream, ordered after everything enqueued so far on the
-        current stream.  Returns the token for _chain_end.  Survives CUDA-graph capture as a fork edge."""
-        main = torch.cuda.current_stream(self.device)
-        st = self._chain_streams.get((self._scope, name))
-        if st is None:
-            st = self._chain_streams[(self._scope, name)] = torch.cuda.Stream(self.device)
-        st.wait_stream(main)
-        ctx = torch.cuda.stream(st)
-        ctx.__enter__()
-        token = (ctx, self.ops.use_stream(st), self._chain, st)
-        self._chain = name
-        return token
-
-    def _chain_end(self, token):
-        """Back to the stream that was current at _chain_begin; the chain keeps running.  Returns its stream for
-        _chain_join."""
-        ctx, prev_handle, prev_name, st = token
-        self.ops.restore_stream(prev_handle)
-        self._chain = prev_name
-        ctx.__exit__(None, None, None)
-        return st
-
-    def _chain_join(self, st):
-        torch.cuda.current_stream(self.device).wait_stream(st)
 
     # ------------------------------------------------------------------ buffers
     def buf(self, key, shape, dtype=None, zero=False):
@@ -637,7 +603,7 @@ class Engine:
         """{branch id: stream} of the current scratch scope, or None when side branches run inline."""
         if not (self.branch_streams and hasattr(self.ops, 'use_stream')) or not any(op.branch for op in net.graph):
             return None
-        d = self._br_streams.setdefault((self._scope, self._chain), {})
+        d = self._br_streams.setdefault(self._scope, {})
         for op in net.graph:
             if op.branch and op.branch not in d:
                 d[op.branch] = torch.cuda.Stream(self.device)
@@ -699,9 +665,9 @@ class Engine:
                 R(deltas[name], b, lo, hi).zero_()
         side = None
         if weight_grads and self.wgrad_side_stream and hasattr(ops, 'use_stream'):
-            side = self._wg_streams.get((self._scope, self._chain))
+            side = self._wg_streams.get(self._scope)
             if side is None:
-                side = self._wg_streams[(self._scope, self._chain)] = torch.cuda.Stream(self.device)
+                side = self._wg_streams[self._scope] = torch.cuda.Stream(self.device)
 
         def off_path(fn):
             """fn() enqueues weight-gradient kernels: on the side stream, after everything enqueued so far."""
@@ -970,12 +936,6 @@ class Engine:
         ops.interpolate(self.rows(a_in, E, B, 2 * B), self.rows(a_in, E, 2 * B, 3 * B), alpha,
                         self.rows(a_in, E, 3 * B, 4 * B), B, E)
         self.last_gan_batch = B
-        if self.split_chains and net.graph is not None and hasattr(ops, 'use_stream'):
-            self._d_step_two_chains(acts, deltas, B, Bg, y, cfg, fblk, dblk)
-            self.adam(D, cfg.learning_rate, cfg.weight_decay, cfg.betas, cfg.eps)                 # srgan.py:297
-            if train_generator:
-                self._g_step(acts, deltas, B, Bg, z2, cfg, fblk, dblk)
-            return
         # ---- one D forward over [x; u; fake; x_hat]
         self.forward(D, acts, 0, 4 * B)
         if self.publish_features and not dggan:
@@ -1050,111 +1010,6 @@ class Engine:
         self.adam(D, cfg.learning_rate, cfg.weight_decay, cfg.betas, cfg.eps)                     # srgan.py:297
         if train_generator:
             self._g_step(acts, deltas, B, Bg, z2, cfg, fblk, dblk)
-
-    def _d_step_two_chains(self, acts, deltas, B, Bg, y, cfg, fblk, dblk):
-        """The discriminator step of gan_step (forwards, losses, gradient penalty, backward; everything between the input
-        rows and the Adam update) for graph nets, enqueued as two chains:
-          hat  : rows [3B,4B) = x_hat -- forward, GP target seed, g-chain, norm / hinge / u0, tangent chain, Jacobian seed,
-                 backward of the x_hat rows with the weight gradients of rows [3B,5B) (x_hat + tangent block);
-          real : rows [0,3B) = x | u | fake -- forward, labeled loss, feature sums (-> all-reduce), distance losses, seeds,
-                 backward with the weight gradients of rows [0,3B).
-        Same kernels on the same rows as the single-chain schedule (row ranges are disjoint, parameter gradients are
-        accumulated with atomics); only the launch partition (4B -> 3B + B rows) and the stream assignment differ.
-        Multi-rank: the chains are joined before the feature-sum all-reduce (a piecewise-captured graph segment must not
-        end with forked work in flight) and forked again for the backward passes."""
-        ops, D, net = self.ops, self.D, self.d_net
-        F = net.feature_size
-        E = net.in_elems
-        fact, fslope = net.feature_act
-        dggan = cfg.method == 'dggan'
-        sc = self.scalars
-        a_in = self._in(net, acts)
-        snap = self.buf('feat_snap', (4 * B * F,)) if (self.publish_features and not dggan) else None
-        gamma_L = dblk(4 * B, 5 * B)
-        s_norm = self.buf('s_norm', (B,), self.mdt)
-        g0 = self.buf('g0', (B * E,))
-        gnorm = self.buf('gnorm', (B,), self.mdt)
-        pred = self.buf('pred', (B,), self.mdt)
-        dpred = self.buf('dpred', (B,), self.mdt)
-        w1 = D.whead[F:2 * F] if dggan else None
-
-        def hat_forward_to_tangent():
-            self.forward(D, acts, 3 * B, 4 * B)
-            if snap is not None:
-                snap[3 * B * F:].copy_(fblk(3 * B, 4 * B))
-            if not dggan:            # GP target s = ||f(x_hat)||_2 (srgan.py:377-381): gamma_L = (f/s) * act'
-                ops.feature_norm_seed(fblk(3 * B, 4 * B), B, F, s_norm, gamma_L, fact, fslope)
-            else:                    # DG-GAN: GP target = the raw score (coefficient/dggan.py:52-57, crowd/dggan.py:37-41)
-                ops.seed_rows(gamma_L, B, F, w1, None, None, fblk(3 * B, 4 * B), fact, fslope)
-            self.gchain(D, acts, deltas, B, g0)
-            ops.gradnorm_penalty(g0, B, E, cfg.gradient_penalty_multiplier / Bg, 1.0 / Bg, gnorm, sc[SC_GP:SC_GP + 1],
-                                 sc[SC_GNORM:SC_GNORM + 1], self.rows(a_in, E, 4 * B, 5 * B))
-            self.tangent(D, acts, B)
-            if not dggan:
-                ops.gp_feature_seed(fblk(4 * B, 5 * B), fblk(3 * B, 4 * B), s_norm, dblk(3 * B, 4 * B), B, F, fact, fslope)
-
-        def hat_backward():
-            if not dggan:
-                self.backward(D, acts, deltas, 3 * B, 4 * B, 3 * B, 5 * B)
-            else:                    # the x_hat rows carry no ordinary gradient; dP/dW_head[1,:] = sum_n u_L,n
-                ops.colsum(fblk(4 * B, 5 * B), B, F, self._head_grad_row(D, 1), 0, None)
-                self.tangent_block_grads(D, acts, deltas, 4 * B, 5 * B)
-
-        token = self._chain_begin('hat')
-        hat_forward_to_tangent()
-        if self.comm is None:
-            hat_backward()
-        hat = self._chain_end(token)
-        # ---- real chain, on the caller's stream
-        self.forward(D, acts, 0, 3 * B)
-        if snap is not None:
-            snap[:3 * B * F].copy_(fblk(0, 3 * B))
-        hook = self._labeled(D, acts, deltas, B, y, cfg, Bg, sc[SC_LABELED:SC_LABELED + 1], pred, dpred)
-        if not dggan:
-            sums = self.buf('fsums', (3, F), self.mdt)
-            sums.zero_()
-            for j in range(3):
-                ops.colsum(fblk(j * B, (j + 1) * B), B, F, sums[j], 0, None)
-            if self.comm is not None:
-                self._chain_join(hat)
-                self.comm.all_reduce_sum(sums)
-                token = self._chain_begin('hat')
-                hat_backward()
-                hat = self._chain_end(token)
-            gvec = self.buf('gvec', (3, F), self.mdt)
-            inv = 1.0 / Bg
-            ops.distance(sums[1], sums[0], F, inv, DIST_KINDS[cfg.matching_distance_function],
-                         cfg.matching_loss_multiplier * cfg.srgan_loss_multiplier, sc[SC_UNLABELED:SC_UNLABELED + 1],
-                         gvec[1], gvec[0], False)
-            ops.distance(sums[1], sums[2], F, inv, DIST_KINDS[cfg.contrasting_distance_function],
-                         cfg.contrasting_loss_multiplier * cfg.srgan_loss_multiplier, sc[SC_FAKE:SC_FAKE + 1],
-                         gvec[1], gvec[2], True)
-            ops.seed_rows(dblk(0, B), B, F, gvec[0], dpred, D.whead[0:F], fblk(0, B), fact, fslope)
-            ops.seed_rows(dblk(B, 2 * B), B, F, gvec[1], None, None, fblk(B, 2 * B), fact, fslope)
-            ops.seed_rows(dblk(2 * B, 3 * B), B, F, gvec[2], None, None, fblk(2 * B, 3 * B), fact, fslope)
-        else:
-            if self.comm is not None:            # no feature collective in DG-GAN: the chains simply run to the end
-                token = self._chain_begin('hat')
-                hat_backward()
-                hat = self._chain_end(token)
-            su = self.buf('score_u', (B,), self.mdt)
-            sf = self.buf('score_f', (B,), self.mdt)
-            dsu = self.buf('dscore_u', (B,), self.mdt)
-            dsf = self.buf('dscore_f', (B,), self.mdt)
-            self._head_forward(D, fblk(B, 2 * B), B, 1, su)
-            self._head_forward(D, fblk(2 * B, 3 * B), B, 1, sf)
-            ops.bce_logits(su, B, 0.0, cfg.matching_loss_multiplier * cfg.dggan_loss_multiplier / Bg,
-                           sc[SC_UNLABELED:SC_UNLABELED + 1], dsu)
-            ops.bce_logits(sf, B, 1.0, cfg.contrasting_loss_multiplier * cfg.dggan_loss_multiplier / Bg,
-                           sc[SC_FAKE:SC_FAKE + 1], dsf)
-            ops.seed_rows(dblk(0, B), B, F, None, dpred, D.whead[0:F], fblk(0, B), fact, fslope)
-            ops.seed_rows(dblk(B, 2 * B), B, F, None, dsu, w1, fblk(B, 2 * B), fact, fslope)
-            ops.seed_rows(dblk(2 * B, 3 * B), B, F, None, dsf, w1, fblk(2 * B, 3 * B), fact, fslope)
-            self._head_grads(D, fblk(B, 2 * B), B, 1, dsu)
-            self._head_grads(D, fblk(2 * B, 3 * B), B, 1, dsf)
-        self._head_grads(D, fblk(0, B), B, 0, dpred)
-        self.backward(D, acts, deltas, 0, 3 * B, 0, 3 * B, hook=hook)
-        self._chain_join(hat)
 
     def _g_step(self, acts, deltas, B, Bg, z2, cfg, fblk, dblk):
         """The generator step of gan_step (srgan.py:299-305, :383-391) with the UPDATED discriminator."""
