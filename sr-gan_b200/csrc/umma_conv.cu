@@ -696,6 +696,135 @@ __global__ void __launch_bounds__(WG_THREADS) umma_wgrad_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// wgrad, few small-side channels (DenseNet dense-layer conv2: 3x3, stride 1, Ca = growth_rate = 32 real channels):
+//   dW[a, tap, b] = sum_o S[o, a] * L[o - pad + tap, b] = sum_i L[i, b] * S[i + pad - tap, a]
+// The kernel above would pad a to a 128-row MMA (4x the tensor work) and load the 128-channel L tile once per tap (9x the
+// L2 -> SM traffic; ncu: 492 us per launch at 56x56, 320 samples = 0.5 TB/s algorithmic).  Here the roles are swapped:
+//   M = 128 channels b (A operand = the L tile, loaded ONCE per pixel chunk, unshifted),
+//   N = 32 channels a per tap (B operand = the S tile shifted by pad - tap: 64 real bytes per pixel; out-of-image pixels
+//       and the channels beyond the window are TMA zero fill), all R*S taps side by side in TMEM (R*S*32 <= 512 columns),
+//   K = pixels, split across one wave of CTAs; fp32 reductions into dW (lanes = consecutive b: coalesced).
+// ------------------------------------------------------------------------------------------------------------
+struct UmmaWgradSwapParams {
+    int n, H, W, Ca_valid, Cb, R, S, pad;
+    int TW, TH, TN;               // pixel patch per stage: TW*TH*TN == WS_PIX
+    int tiles_w, tiles_h, tiles_n;
+    int chunks_per_split;
+    float* dW;
+    int stages;
+};
+constexpr int WS_PIX = 32;
+constexpr int WS_N = 32;
+
+__global__ void __launch_bounds__(WG_THREADS) umma_wgrad_swap_kernel(const __grid_constant__ CUtensorMap tmS,
+                                                                     const __grid_constant__ CUtensorMap tmL,
+                                                                     const UmmaWgradSwapParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[8];
+    __shared__ __align__(8) uint64_t empty_bar[8];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_slot;
+
+    constexpr int A_BYTES = 2 * WS_PIX * 128;            // two 64-channel column groups of the L tile
+    constexpr int B_TAP_BYTES = WS_PIX * 128;            // one 64-channel box of S per tap (32 of them used by the MMA)
+    const int taps = p.R * p.S;
+    const int STAGE_BYTES = A_BYTES + taps * B_TAP_BYTES;
+    const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stages = p.stages;
+    const int b0 = blockIdx.x * 128;
+    const int total_chunks = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int ch_begin = blockIdx.z * p.chunks_per_split;
+    int ch_end = ch_begin + p.chunks_per_split;
+    if (ch_end > total_chunks) ch_end = total_chunks;
+    const int n_iters = ch_end - ch_begin;
+    const uint32_t ncols = taps * WS_N <= 32 ? 32 : (taps * WS_N <= 64 ? 64 : (taps * WS_N <= 128 ? 128 : (taps * WS_N <= 256 ? 256 : 512)));
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+        mbar_init(smem_u32(&tmem_full_bar), 1);
+        fence_barrier_init();
+        prefetch_tmap(&tmS);
+        prefetch_tmap(&tmL);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), ncols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (n_iters > 0) {
+        if (warp == 0) {
+            if (elect_one()) {
+                int s = 0;
+                uint32_t ph = 0;
+                for (int it = 0; it < n_iters; ++it) {
+                    int c = ch_begin + it;
+                    const int tw_i = c % p.tiles_w; c /= p.tiles_w;
+                    const int th_i = c % p.tiles_h; c /= p.tiles_h;
+                    const int tn_i = c;
+                    mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+                    const uint32_t fb = smem_u32(&full_bar[s]);
+                    mbar_expect_tx(fb, STAGE_BYTES);
+                    const uint32_t dst = tiles + s * STAGE_BYTES;
+                    const int w0 = tw_i * p.TW, h0 = th_i * p.TH, n0 = tn_i * p.TN;
+                    tma_load_4d(dst, &tmL, fb, b0, w0, h0, n0);
+                    tma_load_4d(dst + WS_PIX * 128, &tmL, fb, b0 + 64, w0, h0, n0);
+                    for (int k = 0; k < taps; ++k) {
+                        const int r = k / p.S, sx = k % p.S;
+                        tma_load_4d(dst + A_BYTES + k * B_TAP_BYTES, &tmS, fb, 0, w0 + p.pad - sx, h0 + p.pad - r, n0);
+                    }
+                    if (++s == stages) { s = 0; ph ^= 1; }
+                }
+            }
+        } else if (warp == 1) {
+            if (elect_one()) {
+                constexpr uint32_t idesc = make_idesc(128, WS_N, 1, 1);
+                const uint64_t desc0 = make_desc(0, WS_PIX * 128, 1024);
+                int s = 0;
+                uint32_t ph = 0;
+                for (int it = 0; it < n_iters; ++it) {
+                    mbar_wait(smem_u32(&full_bar[s]), ph);
+                    tc_fence_after();
+                    const uint32_t a_s = tiles + s * STAGE_BYTES;
+                    const uint64_t ad0 = desc0 + (uint64_t)(a_s >> 4);
+                    for (int k = 0; k < taps; ++k) {
+                        const uint64_t bd0 = desc0 + (uint64_t)((a_s + A_BYTES + k * B_TAP_BYTES) >> 4);
+#pragma unroll
+                        for (int kk = 0; kk < WS_PIX / 16; ++kk)
+                            umma_f16(tmem_base + k * WS_N, ad0 + (uint64_t)(kk * 128), bd0 + (uint64_t)(kk * 128), idesc,
+                                     (it > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    umma_commit(smem_u32(&empty_bar[s]));
+                    if (++s == stages) { s = 0; ph ^= 1; }
+                }
+                umma_commit(smem_u32(&tmem_full_bar));
+            }
+        } else {
+            const int q = warp & 3;
+            const int b = b0 + q * 32 + lane;                 // this thread's accumulator row = channel b
+            mbar_wait(smem_u32(&tmem_full_bar), 0);
+            tc_fence_after();
+            const long long rowN = (long long)taps * p.Cb;
+#pragma unroll 1
+            for (int k = 0; k < taps; ++k) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + k * WS_N, v);
+                tmem_ld_wait();
+                if (b >= p.Cb) continue;
+                float* dst = p.dW + (long long)k * p.Cb + b;       // dW[a][tap][b]: a warp's 32 lanes are 32 consecutive b
+#pragma unroll
+                for (int a = 0; a < WS_N; ++a)
+                    if (a < p.Ca_valid) atomicAdd(dst + (long long)a * rowN, __uint_as_float(v[a]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // host side: tensor maps
 // ------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -900,6 +1029,46 @@ int umma_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom*
     if (g->Ca % 64 != 0 || g->Cb % 64 != 0) return 0;   // Ca = 64 (mod 128): the upper half tile is TMA zero fill
     if (vw && ((vw->S_pitch | vw->S_valid | vw->L_pitch | vw->L_valid) & 7)) return 0;
     if (vw && (vw->S_valid > g->Ca || vw->L_valid > g->Cb)) return 0;
+    {
+        // few real small-side channels, stride 1 (dense-layer conv2): the swapped formulation
+        const int a_valid = (vw && vw->S_valid > 0) ? vw->S_valid : g->Ca;
+        static const bool swap_on = [] { const char* e = getenv("SRGAN_NO_WGRAD_SWAP"); return !(e && e[0] == '1'); }();
+        if (swap_on && a_valid <= WS_N && g->stride == 1 && g->R * g->S * WS_N <= 512 && g->Cb % 64 == 0 && g->Hs == g->Hl &&
+            g->Ws == g->Wl && !(((uintptr_t)S | (uintptr_t)L | (uintptr_t)dW) & 15)) {
+            UmmaWgradSwapParams p;
+            if (pick_patch(g->Wl, g->Hl, WS_PIX, 8, p.TW, p.TH, p.TN)) {
+                p.n = n; p.H = g->Hl; p.W = g->Wl; p.Ca_valid = a_valid; p.Cb = g->Cb; p.R = g->R; p.S = g->S; p.pad = g->pad;
+                p.tiles_w = g->Wl / p.TW; p.tiles_h = g->Hl / p.TH; p.tiles_n = (n + p.TN - 1) / p.TN;
+                p.dW = dW;
+                const int total_chunks = p.tiles_w * p.tiles_h * p.tiles_n;
+                const int m_tiles = (g->Cb + 127) / 128;
+                int splits = kNumSMs / m_tiles;
+                const int max_splits = (total_chunks + 3) / 4;             // at least 4 stages of work per CTA
+                if (splits > max_splits) splits = max_splits;
+                if (splits < 1) splits = 1;
+                p.chunks_per_split = (total_chunks + splits - 1) / splits;
+                splits = (total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
+                CUtensorMap tmS, tmL;
+                int rc = encode_act(&tmS, S, n, g->Hs, g->Ws, g->Ca, p.TW, p.TH, p.TN, 1, vw ? vw->S_pitch : 0, vw ? vw->S_valid : 0);
+                if (rc) return rc;
+                rc = encode_act(&tmL, L, n, g->Hl, g->Wl, g->Cb, p.TW, p.TH, p.TN, 1, vw ? vw->L_pitch : 0, vw ? vw->L_valid : 0);
+                if (rc) return rc;
+                const int stage_bytes = 2 * WS_PIX * 128 + g->R * g->S * WS_PIX * 128;
+                p.stages = (200 * 1024) / stage_bytes;
+                if (p.stages > 8) p.stages = 8;
+                const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+                static bool attr_set = false;
+                if (!attr_set) {
+                    cudaError_t e = cudaFuncSetAttribute(umma_wgrad_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024);
+                    if (e != cudaSuccess) { srgan_set_error("cudaFuncSetAttribute(umma_wgrad_swap_kernel): %s", cudaGetErrorString(e)); return SRGAN_ERR_CUDA; }
+                    attr_set = true;
+                }
+                umma_wgrad_swap_kernel<<<dim3(m_tiles, 1, splits), WG_THREADS, smem, st>>>(tmS, tmL, p);
+                SRGAN_CHECK_LAUNCH("umma_wgrad_swap_kernel");
+                return 1;
+            }
+        }
+    }
     int BN = g->Cb % 256 == 0 ? 256 : (g->Cb % 128 == 0 ? 128 : 64);
     const int taps = g->R * g->S;
     int NT = 512 / BN;                                         // largest divisor of the tap count that fits TMEM (3 for 3x3)
