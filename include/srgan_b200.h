@@ -162,6 +162,14 @@ int srgan_adam(float* param, const float* grad, float* m, float* v, const int* d
  * one CTA per tensor.  Moments and gradients are slices of the flat buffers grad / m / v. */
 int srgan_adam_multi(const long long* table, int n_tensors, const float* grad, float* m, float* v, const float* state3,
                      float beta1, float beta2, float eps, float weight_decay, void* stream);
+/* The same update for every tensor that has kernel-layout copies (convolution / linear weights, prediction heads) in ONE
+ * launch.  table: device array of n_tensors rows of 26 int64: [0] param ptr, [1] gradient offset (elements, into grad),
+ * [2] moment offset (into m and v), [3..6] master dims, [7..10] gradient strides, [11] out1 ptr (or 0), [12..15] out1 strides,
+ * [16] out2 ptr (or 0), [17..20] out2 strides, [21] 1 = this tensor's layout copies are fp32 (else out_dtype), [22] first block of
+ * this tensor (blocks of 2048 elements, ascending), [23] number of elements; total_blocks = blocks of all tensors. */
+int srgan_adam_layout_multi(const long long* table, int n_tensors, long long total_blocks, const float* grad, float* m, float* v,
+                            const float* state3, float beta1, float beta2, float eps, float weight_decay, int out_dtype,
+                            void* stream);
 /* layout copies only (initial weights / after load_models, srgan.py:221-251) */
 int srgan_repack(const float* param, const int* dims4, void* out1, const long long* o1strides4, void* out2,
                  const long long* o2strides4, int out_dtype, void* stream);

@@ -749,7 +749,82 @@ __global__ void __launch_bounds__(128) adam_multi_kernel(const long long* __rest
     }
 }
 
+// Adam + kernel-layout rewrite for MANY tensors in one launch (the crowd discriminator has 200 convolution weights: one
+// adam_kernel launch each was 437 launches / 3 ms per step, and the D update sits on the step's critical path between the
+// discriminator backward and the generator step).  Table row (26 x int64) per tensor:
+//   [0] param ptr  [1] grad offset  [2] moment offset  [3..6] dims  [7..10] grad strides  [11] out1 ptr  [12..15] out1 strides
+//   [16] out2 ptr  [17..20] out2 strides  [21] 1 = the layout copies are fp32 (prediction heads), 0 = bf16/activation dtype
+//   [22] first block of this tensor  [23] number of elements
+// A block handles ADAM_LM_CHUNK consecutive elements of one tensor (binary search of its first-block column).
+constexpr int ADAM_LM_ROW = 26;
+constexpr int ADAM_LM_CHUNK = 2048;
+template <typename TO>
+__global__ void __launch_bounds__(256) adam_layout_multi_kernel(const long long* __restrict__ table, int n_tensors,
+                                                                const float* __restrict__ grad, float* __restrict__ m,
+                                                                float* __restrict__ v, const float* __restrict__ state, float beta1,
+                                                                float beta2, float eps, float wd) {
+    int lo = 0, hi = n_tensors - 1;
+    while (lo < hi) {                                    // last tensor whose first block <= blockIdx.x
+        const int mid = (lo + hi + 1) >> 1;
+        if (table[(long long)mid * ADAM_LM_ROW + 22] <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const long long* row = table + (long long)lo * ADAM_LM_ROW;
+    float* param = reinterpret_cast<float*>(row[0]);
+    const float* g0 = grad + row[1];
+    float* mm = m + row[2];
+    float* vv = v + row[2];
+    const int d1 = (int)row[4], d2 = (int)row[5], d3 = (int)row[6];
+    const long long gs0 = row[7], gs1 = row[8], gs2 = row[9], gs3 = row[10];
+    void* out1 = reinterpret_cast<void*>(row[11]);
+    void* out2 = reinterpret_cast<void*>(row[16]);
+    const bool f32 = row[21] != 0;
+    const long long n = row[23];
+    const long long base = ((long long)blockIdx.x - row[22]) * ADAM_LM_CHUNK;
+    const float step_size = state[1], inv_sqrt_bc2 = state[2];
+    for (int k = threadIdx.x; k < ADAM_LM_CHUNK; k += 256) {
+        const long long i = base + k;
+        if (i >= n) break;
+        long long t = i;
+        const int i3 = (int)(t % d3); t /= d3;
+        const int i2 = (int)(t % d2); t /= d2;
+        const int i1 = (int)(t % d1); t /= d1;
+        const int i0 = (int)t;
+        float p = param[i];
+        float g = g0[i0 * gs0 + i1 * gs1 + i2 * gs2 + i3 * gs3];
+        if (wd != 0.f) g = fmaf(wd, p, g);
+        const float m1 = beta1 * mm[i] + (1.f - beta1) * g;
+        const float v1 = beta2 * vv[i] + (1.f - beta2) * g * g;
+        mm[i] = m1; vv[i] = v1;
+        p = p - step_size * (m1 / (sqrtf(v1) * inv_sqrt_bc2 + eps));
+        param[i] = p;
+        if (out1) {
+            const long long o = i0 * row[12] + i1 * row[13] + i2 * row[14] + i3 * row[15];
+            if (f32) reinterpret_cast<float*>(out1)[o] = p; else reinterpret_cast<TO*>(out1)[o] = from_f<TO>(p);
+        }
+        if (out2) {
+            const long long o = i0 * row[17] + i1 * row[18] + i2 * row[19] + i3 * row[20];
+            if (f32) reinterpret_cast<float*>(out2)[o] = p; else reinterpret_cast<TO*>(out2)[o] = from_f<TO>(p);
+        }
+    }
+}
+
 extern "C" {
+
+int srgan_adam_layout_multi(const long long* table, int n_tensors, long long total_blocks, const float* grad, float* m, float* v,
+                            const float* state3, float beta1, float beta2, float eps, float weight_decay, int out_dtype,
+                            void* stream) {
+    SRGAN_REQUIRE(table && grad && m && v && state3 && n_tensors >= 0 && total_blocks >= 0 && total_blocks < 0x7fffffffLL,
+                  "srgan_adam_layout_multi: bad arguments");
+    SRGAN_REQUIRE(out_dtype == SRGAN_F32 || out_dtype == SRGAN_BF16, "srgan_adam_layout_multi: unknown dtype %d", out_dtype);
+    if (n_tensors == 0 || total_blocks == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_dtype == SRGAN_F32)
+        adam_layout_multi_kernel<float><<<(unsigned)total_blocks, 256, 0, st>>>(table, n_tensors, grad, m, v, state3, beta1, beta2, eps, weight_decay);
+    else
+        adam_layout_multi_kernel<bf16><<<(unsigned)total_blocks, 256, 0, st>>>(table, n_tensors, grad, m, v, state3, beta1, beta2, eps, weight_decay);
+    SRGAN_CHECK_LAUNCH("adam_layout_multi_kernel");
+    return SRGAN_OK;
+}
 
 int srgan_colsum(const void* X, long long rows, int cols, float* out, int mod, const float* rowscale, int dtype,
                  void* stream) {

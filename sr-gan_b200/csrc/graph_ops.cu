@@ -1081,6 +1081,109 @@ int srgan_copy2d(const void* src, int src_pitch, int src_c0, void* dst, int dst_
     return SRGAN_OK;
 }
 
+// ---- 16-byte versions of the index-map kernels (bf16, C a multiple of 8): one block per image row of the output (forward /
+// tangent) or input (backward), threads over (column, 8-channel group) with 32-bit index arithmetic only.  The 4-element
+// kernels above spent their time in 64-bit divisions (ncu launch list: 928 us for the stem pool backward of 256 samples =
+// 1.05 TB/s of the ~1 GB it moves).
+__device__ __forceinline__ void unpack8(const uint4& r, float (&v)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+    uint4 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+    return r;
+}
+
+__global__ void __launch_bounds__(256) maxpool_idx8_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int y_pitch, int y_c0,
+                                                           unsigned char* __restrict__ idx, int write_idx, int H, int W, int C,
+                                                           int Ho, int Wo, int k, int s, int p) {
+    const int CV = C >> 3;
+    const int ho = blockIdx.x % Ho, b = blockIdx.x / Ho;
+    const bf16* xb = x + (long long)b * H * W * C;
+    const long long orow = ((long long)b * Ho + ho) * Wo;
+    const int h0 = ho * s - p;
+    for (int t = threadIdx.x; t < Wo * CV; t += 256) {
+        const int wo = t / CV, c = (t - wo * CV) << 3;
+        const int w0 = wo * s - p;
+        float out[8];
+        if (write_idx) {
+            float best[8];
+            unsigned char win[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { best[q] = -INFINITY; win[q] = 255; out[q] = 0.f; }
+            for (int dh = 0; dh < k; ++dh) {
+                const int h = h0 + dh;
+                if (h < 0 || h >= H) continue;
+                for (int dw = 0; dw < k; ++dw) {
+                    const int w = w0 + dw;
+                    if (w < 0 || w >= W) continue;
+                    float v[8];
+                    unpack8(*reinterpret_cast<const uint4*>(xb + ((long long)h * W + w) * C + c), v);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (v[q] > best[q] || win[q] == 255) { best[q] = v[q]; win[q] = (unsigned char)(dh * k + dw); out[q] = v[q]; }
+                }
+            }
+            uint2 wv;
+            wv.x = win[0] | (win[1] << 8) | (win[2] << 16) | ((unsigned)win[3] << 24);
+            wv.y = win[4] | (win[5] << 8) | (win[6] << 16) | ((unsigned)win[7] << 24);
+            *reinterpret_cast<uint2*>(idx + (orow + wo) * C + c) = wv;
+        } else {
+            const uint2 wv = *reinterpret_cast<const uint2*>(idx + (orow + wo) * C + c);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int wq = ((q < 4 ? wv.x : wv.y) >> (8 * (q & 3))) & 255;
+                out[q] = wq == 255 ? 0.f : to_f(xb[((long long)(h0 + wq / k) * W + (w0 + wq % k)) * C + c + q]);
+            }
+        }
+        *reinterpret_cast<uint4*>(y + (orow + wo) * y_pitch + y_c0 + c) = pack8(out);
+    }
+}
+
+__global__ void __launch_bounds__(256) maxpool_bwd_idx8_kernel(const bf16* __restrict__ xref, const unsigned char* __restrict__ idx,
+                                                               const bf16* __restrict__ dy, int dy_pitch, int dy_c0,
+                                                               bf16* __restrict__ dx, int H, int W, int C, int Ho, int Wo, int k,
+                                                               int s, int p, int act, float slope) {
+    const int CV = C >> 3;
+    const int h = blockIdx.x % H, b = blockIdx.x / H;
+    int ho_lo = (h + p - k + 1 + s - 1) / s, ho_hi = (h + p) / s;
+    if (h + p - k + 1 < 0) ho_lo = 0;
+    ho_hi = min(ho_hi, Ho - 1);
+    const long long xrow = ((long long)b * H + h) * W;
+    for (int t = threadIdx.x; t < W * CV; t += 256) {
+        const int w = t / CV, c = (t - w * CV) << 3;
+        int wo_lo = (w + p - k + 1 + s - 1) / s, wo_hi = (w + p) / s;
+        if (w + p - k + 1 < 0) wo_lo = 0;
+        wo_hi = min(wo_hi, Wo - 1);
+        float acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+        for (int ho = ho_lo; ho <= ho_hi; ++ho)
+            for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+                const unsigned me = (unsigned)((h - (ho * s - p)) * k + (w - (wo * s - p)));   // this input's position inside that window
+                const long long oi = ((long long)b * Ho + ho) * Wo + wo;
+                const uint2 wv = *reinterpret_cast<const uint2*>(idx + oi * C + c);
+                const unsigned ex = wv.x ^ (me * 0x01010101u), ey = wv.y ^ (me * 0x01010101u);      // a zero byte = a match
+                if ((((ex - 0x01010101u) & ~ex) | ((ey - 0x01010101u) & ~ey)) & 0x80808080u) {} else
+                    continue;                                   // no byte of the index map equals `me`: this window routes nothing here
+                float d[8];
+                unpack8(*reinterpret_cast<const uint4*>(dy + oi * dy_pitch + dy_c0 + c), d);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if ((((q < 4 ? wv.x : wv.y) >> (8 * (q & 3))) & 255u) == me) acc[q] += d[q];
+            }
+        float hx[8], o[8];
+        unpack8(*reinterpret_cast<const uint4*>(xref + (xrow + w) * C + c), hx);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] = acc[q] * act_bwd(hx[q], act, slope);
+        *reinterpret_cast<uint4*>(dx + (xrow + w) * C + c) = pack8(o);
+    }
+}
+
 int srgan_maxpool(const void* x, const void* xref, void* y, int y_pitch, int y_c0, unsigned char* idx, int idx_mode, int n, int H,
                   int W, int C, int k, int stride, int pad, int dtype, void* stream) {
     SRGAN_REQUIRE(x && y && n >= 0 && H > 0 && W > 0 && C > 0 && k > 0 && stride > 0 && pad >= 0 && 2 * pad <= k && y_c0 >= 0 &&
@@ -1090,6 +1193,12 @@ int srgan_maxpool(const void* x, const void* xref, void* y, int y_pitch, int y_c
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = vec_ok(C, y_pitch, y_c0);
     SRGAN_REQUIRE(idx_mode >= 0 && idx_mode <= 2 && (idx_mode == 0 || idx) && k * k < 255, "srgan_maxpool: bad index-map arguments");
+    if (idx_mode != 0 && dtype == SRGAN_BF16 && ((C | y_pitch | y_c0) & 7) == 0 && (long long)n * Ho < 0x7fffffffLL) {
+        maxpool_idx8_kernel<<<(unsigned)(n * Ho), 256, 0, st>>>((const bf16*)x, (bf16*)y, y_pitch, y_c0, idx, idx_mode == 1, H, W, C, Ho, Wo,
+                                                              k, stride, pad);
+        SRGAN_CHECK_LAUNCH("maxpool_idx8_kernel");
+        return SRGAN_OK;
+    }
     if (idx_mode != 0) {
         DISPATCH_T(dtype,
                    if (vec) maxpool_idx_kernel<T, 4><<<ew_grid((long long)n * Ho * Wo * C / 4), 256, 0, st>>>((const T*)x, (T*)y, y_pitch, y_c0, idx, idx_mode == 1, n, H, W, C, Ho, Wo, k, stride, pad);
@@ -1112,6 +1221,12 @@ int srgan_maxpool_bwd(const void* xref, const unsigned char* idx, const void* dy
     const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = vec_ok(C, dy_pitch, dy_c0);
+    if (idx && dtype == SRGAN_BF16 && ((C | dy_pitch | dy_c0) & 7) == 0 && (long long)n * H < 0x7fffffffLL) {
+        maxpool_bwd_idx8_kernel<<<(unsigned)(n * H), 256, 0, st>>>((const bf16*)xref, idx, (const bf16*)dy, dy_pitch, dy_c0, (bf16*)dx, H, W,
+                                                                 C, Ho, Wo, k, stride, pad, act, slope);
+        SRGAN_CHECK_LAUNCH("maxpool_bwd_idx8_kernel");
+        return SRGAN_OK;
+    }
     if (idx) {
         DISPATCH_T(dtype,
                    if (vec) maxpool_bwd_idx_kernel<T, 4><<<ew_grid((long long)n * H * W * C / 4), 256, 0, st>>>((const T*)xref, idx, (const T*)dy, dy_pitch, dy_c0, (T*)dx, n, H, W, C, Ho, Wo, k, stride, pad, act, slope);

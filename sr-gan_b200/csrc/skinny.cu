@@ -2,9 +2,9 @@
 // side), e.g. MapModule.linear1 = Conv2d(32, 20, kernel 28) on a 28x28 map (crowd/models.py:774, K = 25088) and
 // final_count_feature_layer = Conv2d(1920, 20, 1) (:1132).  As GEMMs these are M = batch rows, N = 20: a 128x64-tiled kernel runs
 // them on ONE CTA.  They are bandwidth problems: each kernel below streams the long operand once, coalesced.
-//   down : S[n,a]  = epilogue(sum_k L[n,k] * Wd[a,k])          one CTA per ROWS rows, threads stride over k
+//   down : S[n,a]  = epilogue(sum_k L[n,k] * Wd[a,k])          one CTA per ROWS rows, a warp per 4 outputs, lanes stride over k
 //   up   : L[n,k]  = epilogue(sum_a S[n,a] * Wu[b(k)][tap(k)][a])  one thread per (n, k)
-//   wgrad: dW[a,k] += sum_n S[n,a] * L[n,k]                    one thread per k, all a in registers
+//   wgrad: dW[a,k] += sum_n S[n,a] * L[n,k]                    one thread per k and 32-row chunk, all a in registers
 #include "common.cuh"
 
 namespace {
@@ -12,73 +12,91 @@ namespace {
 constexpr int CA_MAX = 32;
 constexpr int ROWS = 2;
 
+// down: one CTA per ROWS rows; warp w owns the outputs a = w, w + 8, w + 16, w + 24 (<= 4 of the <= 32), its lanes stride over K
+// with 16-byte loads (ROWS + <= 4 independent loads per iteration, two iterations in flight).  (The first version gave every thread all 20 outputs: 64 accumulators
+// and a load -> FMA chain per output that the compiler serialised -- ncu launch list: 160 us per launch whatever the batch.)
 template <typename T>
 __global__ void __launch_bounds__(256) skinny_down_kernel(const T* __restrict__ L, const T* __restrict__ Wd, T* __restrict__ out,
                                                           const float* __restrict__ bias, int bias_mod, const T* __restrict__ href,
                                                           int epi, int act, float slope, int n, int Ca, long long K) {
-    __shared__ float red[8][ROWS][CA_MAX];
+    constexpr int V = 16 / sizeof(T);                 // elements per 16-byte load
+    constexpr int AW = CA_MAX / 8;                    // outputs per warp
     const int row0 = blockIdx.x * ROWS;
-    float acc[ROWS][CA_MAX];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float acc[ROWS][AW];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
 #pragma unroll
-        for (int a = 0; a < CA_MAX; ++a) acc[r][a] = 0.f;
-    const bool vec = (K & 3) == 0;
-    if (vec) {
-        for (long long k = (long long)threadIdx.x * 4; k < K; k += 256 * 4) {
-            float4 x[ROWS];
+        for (int j = 0; j < AW; ++j) acc[r][j] = 0.f;
+    auto ldv = [](const T* p, float (&v)[V]) {
+        if constexpr (sizeof(T) == 2) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(p);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
-            for (int r = 0; r < ROWS; ++r) x[r] = row0 + r < n ? ld4(L + (row0 + r) * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
+        } else {
+            const float4 raw = *reinterpret_cast<const float4*>(p);
+            v[0] = raw.x; v[1] = raw.y; v[2] = raw.z; v[3] = raw.w;
+        }
+    };
+    if ((K % V) == 0 && ((reinterpret_cast<uintptr_t>(L) | reinterpret_cast<uintptr_t>(Wd)) & 15) == 0) {
+#pragma unroll 2
+        for (long long k = (long long)lane * V; k < K; k += 32 * V) {
+            float x[ROWS][V];
 #pragma unroll
-            for (int a = 0; a < CA_MAX; ++a) {
+            for (int r = 0; r < ROWS; ++r) {
+                if (row0 + r < n) ldv(L + (long long)(row0 + r) * K + k, x[r]);
+                else {
+#pragma unroll
+                    for (int q = 0; q < V; ++q) x[r][q] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < AW; ++j) {
+                const int a = w + 8 * j;
                 if (a < Ca) {
-                    const float4 w = ld4(Wd + a * K + k);
+                    float wv[V];
+                    ldv(Wd + (long long)a * K + k, wv);
 #pragma unroll
                     for (int r = 0; r < ROWS; ++r)
-                        acc[r][a] += x[r].x * w.x + x[r].y * w.y + x[r].z * w.z + x[r].w * w.w;
+#pragma unroll
+                        for (int q = 0; q < V; ++q) acc[r][j] = fmaf(x[r][q], wv[q], acc[r][j]);
                 }
             }
         }
     } else {
-        for (long long k = threadIdx.x; k < K; k += 256) {
+        for (long long k = lane; k < K; k += 32) {
             float x[ROWS];
 #pragma unroll
-            for (int r = 0; r < ROWS; ++r) x[r] = row0 + r < n ? to_f(L[(row0 + r) * K + k]) : 0.f;
+            for (int r = 0; r < ROWS; ++r) x[r] = row0 + r < n ? to_f(L[(long long)(row0 + r) * K + k]) : 0.f;
 #pragma unroll
-            for (int a = 0; a < CA_MAX; ++a) {
+            for (int j = 0; j < AW; ++j) {
+                const int a = w + 8 * j;
                 if (a < Ca) {
-                    const float w = to_f(Wd[a * K + k]);
+                    const float wv = to_f(Wd[(long long)a * K + k]);
 #pragma unroll
-                    for (int r = 0; r < ROWS; ++r) acc[r][a] = fmaf(x[r], w, acc[r][a]);
+                    for (int r = 0; r < ROWS; ++r) acc[r][j] = fmaf(x[r], wv, acc[r][j]);
                 }
             }
         }
     }
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
 #pragma unroll
-        for (int a = 0; a < CA_MAX; ++a) {
-            const float v = warp_sum(acc[r][a]);
-            if (lane == 0) red[w][r][a] = v;
-        }
-    __syncthreads();
-    if (threadIdx.x < ROWS * CA_MAX) {
-        const int r = threadIdx.x / CA_MAX, a = threadIdx.x % CA_MAX;
-        if (a < Ca && row0 + r < n) {
-            float v = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v += red[k][r][a];
-            const long long o = (long long)(row0 + r) * Ca + a;
-            if (epi == SRGAN_EPI_BIAS_ACT) {
-                if (bias) v += bias[bias_mod ? a % bias_mod : a];
-                v = act_fwd(v, act, slope);
-            } else if (href && act != SRGAN_ACT_NONE) {
-                v *= act_bwd(to_f(href[o]), act, slope);
+        for (int j = 0; j < AW; ++j) {
+            float v = warp_sum(acc[r][j]);
+            const int a = w + 8 * j;
+            if (lane == 0 && a < Ca && row0 + r < n) {
+                const long long o = (long long)(row0 + r) * Ca + a;
+                if (epi == SRGAN_EPI_BIAS_ACT) {
+                    if (bias) v += bias[bias_mod ? a % bias_mod : a];
+                    v = act_fwd(v, act, slope);
+                } else if (href && act != SRGAN_ACT_NONE) {
+                    v *= act_bwd(to_f(href[o]), act, slope);
+                }
+                out[o] = from_f<T>(v);
             }
-            out[o] = from_f<T>(v);
         }
-    }
 }
 
 template <typename T>
@@ -112,35 +130,39 @@ __global__ void __launch_bounds__(256) skinny_up_kernel(const T* __restrict__ S,
     out[o] = from_f<T>(v);
 }
 
-// one thread per k; the n x Ca block of S is staged in shared memory in chunks of NCH rows
+// wgrad: a thread owns one k, a CTA 256 consecutive k and NCH rows of the batch (blockIdx.y): the NCH x Ca block of S sits in
+// shared memory (broadcast reads), the L column is read 8 rows at a time (independent loads), the partial sums of the row
+// chunks are combined with fp32 atomics.  (The first version walked all n rows in one dependent load -> FMA chain per thread:
+// 240 us per launch at 320 rows.)
 template <typename T>
 __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const T* __restrict__ S, const T* __restrict__ L, float* __restrict__ dW,
                                                            int n, int Ca, long long K) {
-    constexpr int NCH = 64;
+    constexpr int NCH = 32, U = 8;
     __shared__ float s[NCH][CA_MAX];
     const long long k = (long long)blockIdx.x * 256 + threadIdx.x;
+    const int n0 = blockIdx.y * NCH;
+    const int nn = min(NCH, n - n0);
+    for (int i = threadIdx.x; i < NCH * CA_MAX; i += 256) {
+        const int r = i / CA_MAX, a = i % CA_MAX;
+        s[r][a] = (r < nn && a < Ca) ? to_f(S[(long long)(n0 + r) * Ca + a]) : 0.f;
+    }
+    __syncthreads();
+    if (k >= K) return;
     float acc[CA_MAX];
 #pragma unroll
     for (int a = 0; a < CA_MAX; ++a) acc[a] = 0.f;
-    for (int n0 = 0; n0 < n; n0 += NCH) {
-        const int nn = min(NCH, n - n0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < nn * Ca; i += 256) s[i / Ca][i % Ca] = to_f(S[(long long)n0 * Ca + i]);
-        __syncthreads();
-        if (k < K) {
-            for (int r = 0; r < nn; ++r) {
-                const float x = to_f(L[(long long)(n0 + r) * K + k]);
+    for (int r0 = 0; r0 < nn; r0 += U) {
+        float x[U];
 #pragma unroll
-                for (int a = 0; a < CA_MAX; ++a)
-                    if (a < Ca) acc[a] = fmaf(s[r][a], x, acc[a]);
-            }
-        }
-    }
-    if (k < K) {
+        for (int u = 0; u < U; ++u) x[u] = r0 + u < nn ? to_f(L[(long long)(n0 + r0 + u) * K + k]) : 0.f;
 #pragma unroll
-        for (int a = 0; a < CA_MAX; ++a)
-            if (a < Ca) atomicAdd(dW + (long long)a * K + k, acc[a]);
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int a = 0; a < CA_MAX; ++a) acc[a] = fmaf(s[r0 + u][a], x[u], acc[a]);
     }
+#pragma unroll
+    for (int a = 0; a < CA_MAX; ++a)
+        if (a < Ca) atomicAdd(dW + (long long)a * K + k, acc[a]);
 }
 
 }  // namespace
@@ -175,7 +197,7 @@ int skinny_conv(int mode, const void* src, const void* W, void* out, int n, cons
 
 int skinny_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, int dtype, cudaStream_t st) {
     const long long K = (long long)g->R * g->S * g->Cb;
-    const unsigned grid = (unsigned)((K + 255) / 256);
+    const dim3 grid((unsigned)((K + 255) / 256), (unsigned)((n + 31) / 32));
     if (dtype == SRGAN_F32) skinny_wgrad_kernel<float><<<grid, 256, 0, st>>>((const float*)S, (const float*)L, dW, n, g->Ca, K);
     else skinny_wgrad_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)S, (const bf16*)L, dW, n, g->Ca, K);
     SRGAN_CHECK_LAUNCH("skinny_wgrad_kernel");

@@ -137,6 +137,7 @@ class NetState:
         # [t, lr/(1-beta1^t), 1/sqrt(1-beta2^t)] in device memory (fp64 in the fp64 schedule tests): see srgan_adam_prepare
         self.adam_state = torch.zeros(3, dtype=mdt, device=device)
         self.plain_entries = None                  # adam_multi table rows, built on the first update
+        self.layout_entries = None                 # adam_layout_multi table rows (tensors with kernel-layout copies)
         self.wd_, self.wu_ = {}, {}
         for l in net.layers:
             n = kl[l.name]
@@ -787,12 +788,13 @@ class Engine:
 
         def plain(k):
             plain_keys.append(k)
+        # tensors with kernel-layout copies: (key, dims, gradient strides, out1, s1, out2, s2)
+        laid = []
         for l in st.net.layers:
             wd_s, wu_s = st.strides(l)
-            k = l.name + '.weight'
             wd, wu = self._needed_layouts(st, l)
-            self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), l.master_dims, wd_s, wd, wd_s if wd is not None else None,
-                          wu, wu_s if wu is not None else None, st.adam_state, betas[0], betas[1], eps, weight_decay)
+            laid.append((l.name + '.weight', l.master_dims, wd_s, wd, wd_s if wd is not None else None, wu,
+                         wu_s if wu is not None else None))
             if l.has_bias:
                 plain(l.name + '.bias')
         for op in st.net.affines:
@@ -800,10 +802,20 @@ class Engine:
             plain(op.name + '.bias')
         if st.net.head:
             for h, dims, s, dst in self._head_part_layouts(st):
-                k = h + '.weight'                  # multi-part heads: st.g(k) starts at the part's first column of row 0
-                self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), dims, s, dst, s, None, None,
-                              st.adam_state, betas[0], betas[1], eps, weight_decay)
+                # multi-part heads: st.g(k) starts at the part's first column of row 0
+                laid.append((h + '.weight', dims, s, dst, s, None, None))
                 plain(h + '.bias')
+        if hasattr(self.ops, 'adam_layout_multi') and len(laid) > 8 and self.mdt == torch.float32:
+            # many tensors (the crowd discriminator: 200 convolution weights): one table-driven launch
+            if st.layout_entries is None:
+                st.layout_entries = [(st.params[k].detach(), st.gslices[k][0], st.slices[k][0], dims, gs, o1, s1, o2, s2)
+                                     for k, dims, gs, o1, s1, o2, s2 in laid]
+            self.ops.adam_layout_multi(st.layout_entries, st.grad, st.exp_avg, st.exp_avg_sq, st.adam_state, betas[0], betas[1],
+                                       eps, weight_decay, st.act_dtype)
+        else:
+            for k, dims, gs, o1, s1, o2, s2 in laid:
+                self.ops.adam(st.params[k], st.g(k), st.m(k), st.v(k), dims, gs, o1, s1, o2, s2, st.adam_state, betas[0],
+                              betas[1], eps, weight_decay)
         # every tensor without kernel-layout copies (biases, BatchNorm weight / bias) in one launch
         if st.plain_entries is None:
             st.plain_entries = [(st.params[k].detach(), st.gslices[k][0], st.slices[k][0], st.params[k].numel())

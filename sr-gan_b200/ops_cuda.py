@@ -35,6 +35,7 @@ _EXPORTS = (
     'srgan_repack', 'srgan_im2col', 'srgan_col2im', 'srgan_adam_prepare', 'srgan_coefficient_step',
     'srgan_coefficient_step_workspace_bytes', 'srgan_affine', 'srgan_affine_bwd', 'srgan_affine_grad', 'srgan_copy2d',
     'srgan_maxpool', 'srgan_maxpool_bwd', 'srgan_avgpool', 'srgan_avgpool_bwd', 'srgan_crowd_loss', 'srgan_crowd_map_grad', 'srgan_depth_to_space', 'srgan_adam_multi', 'srgan_affine_bwd_grad',
+    'srgan_adam_layout_multi',
 )
 
 _lib = None
@@ -98,6 +99,7 @@ def load_library(path: str = LIB_PATH):
     lib.srgan_avgpool_bwd.argtypes = [vp, c_int, c_int, vp, c_int] + [c_int] * 5 + [vp, c_int, c_f, c_int, vp]
     lib.srgan_crowd_loss.argtypes = [vp, vp, pp, c_int, vp, c_int, c_ll, c_int, c_f, c_f, vp, vp, vp, c_int, vp]
     lib.srgan_adam_multi.argtypes = [vp, c_int, vp, vp, vp, vp, c_f, c_f, c_f, c_f, vp]
+    lib.srgan_adam_layout_multi.argtypes = [vp, c_int, c_ll, vp, vp, vp, vp, c_f, c_f, c_f, c_f, c_int, vp]
     lib.srgan_depth_to_space.argtypes = [vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, vp]
     lib.srgan_crowd_map_grad.argtypes = [vp, vp, vp, vp, c_int, c_ll, c_int, c_int, c_f, c_int, vp]
     lib.srgan_tensor_launch_count.restype = c_ll
@@ -415,6 +417,34 @@ class CudaOps:
         f32 = torch.float32
         self._ck(self.lib.srgan_adam_multi(self._p(tbl[0]), len(entries), self._p(grad, f32), self._p(m, f32), self._p(v, f32),
                                            self._p(state, f32), b1, b2, eps, wd, self._stream()), 'srgan_adam_multi')
+
+    ADAM_LM_CHUNK = 2048
+
+    def adam_layout_multi(self, entries, grad, m, v, state, b1, b2, eps, wd, out_dtype):
+        """entries: list of (param, grad offset, moment offset, dims, grad strides, out1, s1, out2, s2) with out1 / out2 the
+        kernel-layout copies (tensors or None); one launch for all of them.  The device table is built once per list."""
+        key = id(entries)
+        tbl = self._tables.get(key)
+        if tbl is None:
+            rows, blk = [], 0
+            for p, go, mo, dims, gs, o1, s1, o2, s2 in entries:
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise TypeError('adam_layout_multi: fp32 contiguous CUDA parameters only')
+                outs = [o for o in (o1, o2) if o is not None]
+                f32 = 1 if outs and all(o.dtype == torch.float32 for o in outs) else 0
+                if any((o.dtype == torch.float32) != bool(f32) for o in outs) or any(o.dtype not in (torch.float32, out_dtype) for o in outs):
+                    raise TypeError('adam_layout_multi: the layout copies of a tensor must share one dtype')
+                n = p.numel()
+                rows.append([p.data_ptr(), go, mo] + list(dims) + list(gs) + [o1.data_ptr() if o1 is not None else 0] +
+                            list(s1 or (0, 0, 0, 0)) + [o2.data_ptr() if o2 is not None else 0] + list(s2 or (0, 0, 0, 0)) +
+                            [f32, blk, n, 0, 0])
+                blk += (n + self.ADAM_LM_CHUNK - 1) // self.ADAM_LM_CHUNK
+            tbl = (torch.tensor(rows, dtype=torch.int64).to(self.device), blk, entries)
+            self._tables[key] = tbl
+        f32 = torch.float32
+        self._ck(self.lib.srgan_adam_layout_multi(self._p(tbl[0]), len(entries), tbl[1], self._p(grad, f32), self._p(m, f32),
+                                                  self._p(v, f32), self._p(state, f32), b1, b2, eps, wd, _dt(out_dtype),
+                                                  self._stream()), 'srgan_adam_layout_multi')
 
     def affine_bwd_grad(self, dy, dy_pitch, x, dx, x_pitch, x_c0, rows, C, gamma, mean, var, eps, dgamma, dbeta, accumulate):
         self._ck(self.lib.srgan_affine_bwd_grad(self._p(dy), dy_pitch, self._p(x, dy.dtype), self._p(dx, dy.dtype), x_pitch, x_c0,

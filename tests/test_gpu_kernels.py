@@ -353,6 +353,62 @@ def test_adam_and_repack(ops, dims, kind):
             close(o2, o2_ref, 5e-6 if od == torch.float32 else 1e-2, 'adam out2')
 
 
+@pytest.mark.parametrize('od', [torch.float32, torch.bfloat16])
+def test_adam_layout_multi_matches_per_tensor_adam(ops, od):
+    """srgan_adam_layout_multi (one table-driven launch for every tensor with kernel-layout copies: the crowd discriminator's
+    200 convolution weights) against srgan_adam tensor by tensor: conv / padded-trunk / fc_up stride patterns, a tensor
+    with only one copy, an fp32 prediction-head copy, tensors that are not a multiple of the 2048-element block."""
+    gen = torch.Generator().manual_seed(19)
+    cases = []
+    for dims, kind in (((32, 128, 3, 3), 'conv'), ((128, 96, 1, 1), 'pad'), ((16, 8, 4, 4), 'fc_up'), ((20, 32, 7, 7), 'conv'),
+                       ((5, 3, 1, 1), 'conv'), ((64, 64, 3, 3), 'one'), ((2, 80, 1, 1), 'head'), ((256, 512, 4, 4), 'conv')):
+        a, b, r, s_ = dims
+        if kind == 'fc_up':
+            zb, c, k = a, b, r
+            wd_s, wu_s, n_out = (1, zb, k * c * zb, c * zb), (k * k * c, 1, k * c, c), a * b * r * s_
+        elif kind == 'pad':                  # channel-padded 1x1 layout: 128 x 128 copies of a 128 x 96 master
+            wd_s, wu_s, n_out = (128, 1, 0, 0), (1, 128, 0, 0), 128 * 128
+        else:
+            wd_s, wu_s, n_out = (r * s_ * b, 1, s_ * b, b), (1, r * s_ * a, s_ * a, a), a * b * r * s_
+        cases.append((dims, kind, wd_s, wu_s, n_out))
+    total = sum(d[0] * d[1] * d[2] * d[3] for d, *_ in cases) + 64
+    gtot = sum(nn for *_, nn in cases) + 64
+    grad = rnd(gen, gtot).cuda()
+    state = torch.zeros(3, device='cuda')
+    runs = []
+    for multi in (False, True):
+        m, v = (rnd(torch.Generator().manual_seed(3), total) * 0.1).cuda(), (rnd(torch.Generator().manual_seed(4), total).abs() * 0.01).cuda()
+        g2 = torch.Generator().manual_seed(5)
+        entries, outs, params = [], [], []
+        po = go = 0
+        for dims, kind, wd_s, wu_s, n_out in cases:
+            p = rnd(g2, *dims).cuda()
+            n = p.numel()
+            odt = torch.float32 if kind == 'head' else od
+            o1 = torch.zeros(n_out, dtype=odt, device='cuda')
+            o2 = None if kind in ('one', 'head') else torch.zeros(n_out, dtype=odt, device='cuda')
+            entries.append((p, go, po, dims, wd_s, o1, wd_s, o2, wu_s if o2 is not None else None))
+            params.append(p); outs.append((o1, o2))
+            po += (n + 3) // 4 * 4
+            go += (n_out + 3) // 4 * 4
+        state.zero_()
+        for step in range(2):
+            ops.adam_prepare(state, 1e-3, 0.9, 0.999)
+            if multi:
+                ops.adam_layout_multi(entries, grad, m, v, state, 0.9, 0.999, 1e-8, 1e-2, od)
+            else:
+                for p, go_, po_, dims, gs, o1, s1, o2, s2 in entries:
+                    n = p.numel()
+                    ops.adam(p, grad[go_:], m[po_:po_ + n], v[po_:po_ + n], dims, gs, o1, s1, o2, s2, state, 0.9, 0.999, 1e-8, 1e-2)
+        runs.append((params, outs, m, v))
+    (pa, oa, ma, va), (pb, ob, mb, vb) = runs
+    assert torch.equal(ma, mb) and torch.equal(va, vb)
+    for x, y in zip(pa, pb):
+        assert torch.equal(x, y)
+    for (a1, a2), (b1, b2) in zip(oa, ob):
+        assert torch.equal(a1, b1) and (a2 is None or torch.equal(a2, b2))
+
+
 @pytest.mark.parametrize('dt', DT)
 @pytest.mark.parametrize('g', [Geom(16, 16, 64, 32, 32, 3, 4, 4, 2, 1), Geom(5, 7, 64, 11, 15, 4, 3, 3, 2, 0),
                                Geom(8, 8, 128, 8, 8, 1, 3, 3, 1, 1)])
