@@ -2,7 +2,7 @@
 // side), e.g. MapModule.linear1 = Conv2d(32, 20, kernel 28) on a 28x28 map (crowd/models.py:774, K = 25088) and
 // final_count_feature_layer = Conv2d(1920, 20, 1) (:1132).  As GEMMs these are M = batch rows, N = 20: a 128x64-tiled kernel runs
 // them on ONE CTA.  They are bandwidth problems: each kernel below streams the long operand once, coalesced.
-//   down : S[n,a]  = epilogue(sum_k L[n,k] * Wd[a,k])          one CTA per ROWS rows, a warp per 4 outputs, lanes stride over k
+//   down : S[n,a]  = epilogue(sum_k L[n,k] * Wd[a,k])          one CTA per ROWS rows, threads stride over k, packed loads first
 //   up   : L[n,k]  = epilogue(sum_a S[n,a] * Wu[b(k)][tap(k)][a])  one thread per (n, k)
 //   wgrad: dW[a,k] += sum_n S[n,a] * L[n,k]                    one thread per k and 32-row chunk, all a in registers
 #include "common.cuh"
@@ -12,70 +12,66 @@ namespace {
 constexpr int CA_MAX = 32;
 constexpr int ROWS = 2;
 
-// down: one CTA per ROWS rows; warp w owns the outputs a = w, w + 8, w + 16, w + 24 (<= 4 of the <= 32), its lanes stride over K
-// with 16-byte loads (ROWS + <= 4 independent loads per iteration, two iterations in flight).  (The first version gave every thread all 20 outputs: 64 accumulators
-// and a load -> FMA chain per output that the compiler serialised -- ncu launch list: 160 us per launch whatever the batch.)
+// down: one CTA per ROWS rows; the 256 threads stride over K with 16-byte loads and every thread accumulates ALL outputs.  Per
+// iteration the ROWS input pieces and the Ca weight pieces are loaded first, kept PACKED (4 registers per 16 bytes), and only
+// then unpacked and multiplied: Ca + ROWS independent 16-byte loads in flight per thread.  (The first version unpacked each
+// weight piece right after its load and the compiler serialised the load -> FMA pairs: 160 us per launch whatever the batch.)
 template <typename T>
 __global__ void __launch_bounds__(256) skinny_down_kernel(const T* __restrict__ L, const T* __restrict__ Wd, T* __restrict__ out,
                                                           const float* __restrict__ bias, int bias_mod, const T* __restrict__ href,
                                                           int epi, int act, float slope, int n, int Ca, long long K) {
     constexpr int V = 16 / sizeof(T);                 // elements per 16-byte load
-    constexpr int AW = CA_MAX / 8;                    // outputs per warp
+    __shared__ float red[8][ROWS][CA_MAX];
     const int row0 = blockIdx.x * ROWS;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    float acc[ROWS][AW];
+    float acc[ROWS][CA_MAX];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
 #pragma unroll
-        for (int j = 0; j < AW; ++j) acc[r][j] = 0.f;
-    auto ldv = [](const T* p, float (&v)[V]) {
+        for (int a = 0; a < CA_MAX; ++a) acc[r][a] = 0.f;
+    auto unpack = [](const uint4& raw, float (&v)[V]) {
         if constexpr (sizeof(T) == 2) {
-            const uint4 raw = *reinterpret_cast<const uint4*>(p);
             const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
             for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
         } else {
-            const float4 raw = *reinterpret_cast<const float4*>(p);
-            v[0] = raw.x; v[1] = raw.y; v[2] = raw.z; v[3] = raw.w;
+            v[0] = __uint_as_float(raw.x); v[1] = __uint_as_float(raw.y); v[2] = __uint_as_float(raw.z); v[3] = __uint_as_float(raw.w);
         }
     };
     if ((K % V) == 0 && ((reinterpret_cast<uintptr_t>(L) | reinterpret_cast<uintptr_t>(Wd)) & 15) == 0) {
-#pragma unroll 2
-        for (long long k = (long long)lane * V; k < K; k += 32 * V) {
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        for (long long k = (long long)threadIdx.x * V; k < K; k += 256 * V) {
+            uint4 xr[ROWS], wr[CA_MAX];
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r)
+                xr[r] = row0 + r < n ? *reinterpret_cast<const uint4*>(L + (long long)(row0 + r) * K + k) : zero;
+#pragma unroll
+            for (int a = 0; a < CA_MAX; ++a)
+                wr[a] = a < Ca ? __ldg(reinterpret_cast<const uint4*>(Wd + (long long)a * K + k)) : zero;
             float x[ROWS][V];
 #pragma unroll
-            for (int r = 0; r < ROWS; ++r) {
-                if (row0 + r < n) ldv(L + (long long)(row0 + r) * K + k, x[r]);
-                else {
+            for (int r = 0; r < ROWS; ++r) unpack(xr[r], x[r]);
 #pragma unroll
-                    for (int q = 0; q < V; ++q) x[r][q] = 0.f;
-                }
-            }
+            for (int a = 0; a < CA_MAX; ++a) {
+                float wv[V];
+                unpack(wr[a], wv);
 #pragma unroll
-            for (int j = 0; j < AW; ++j) {
-                const int a = w + 8 * j;
-                if (a < Ca) {
-                    float wv[V];
-                    ldv(Wd + (long long)a * K + k, wv);
+                for (int r = 0; r < ROWS; ++r)
 #pragma unroll
-                    for (int r = 0; r < ROWS; ++r)
-#pragma unroll
-                        for (int q = 0; q < V; ++q) acc[r][j] = fmaf(x[r][q], wv[q], acc[r][j]);
-                }
+                    for (int q = 0; q < V; ++q) acc[r][a] = fmaf(x[r][q], wv[q], acc[r][a]);
             }
         }
     } else {
-        for (long long k = lane; k < K; k += 32) {
+        for (long long k = threadIdx.x; k < K; k += 256) {
             float x[ROWS];
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) x[r] = row0 + r < n ? to_f(L[(long long)(row0 + r) * K + k]) : 0.f;
 #pragma unroll
-            for (int j = 0; j < AW; ++j) {
-                const int a = w + 8 * j;
+            for (int a = 0; a < CA_MAX; ++a) {
                 if (a < Ca) {
                     const float wv = to_f(Wd[(long long)a * K + k]);
 #pragma unroll
-                    for (int r = 0; r < ROWS; ++r) acc[r][j] = fmaf(x[r], wv, acc[r][j]);
+                    for (int r = 0; r < ROWS; ++r) acc[r][a] = fmaf(x[r], wv, acc[r][a]);
                 }
             }
         }
@@ -83,20 +79,27 @@ __global__ void __launch_bounds__(256) skinny_down_kernel(const T* __restrict__ 
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
 #pragma unroll
-        for (int j = 0; j < AW; ++j) {
-            float v = warp_sum(acc[r][j]);
-            const int a = w + 8 * j;
-            if (lane == 0 && a < Ca && row0 + r < n) {
-                const long long o = (long long)(row0 + r) * Ca + a;
-                if (epi == SRGAN_EPI_BIAS_ACT) {
-                    if (bias) v += bias[bias_mod ? a % bias_mod : a];
-                    v = act_fwd(v, act, slope);
-                } else if (href && act != SRGAN_ACT_NONE) {
-                    v *= act_bwd(to_f(href[o]), act, slope);
-                }
-                out[o] = from_f<T>(v);
-            }
+        for (int a = 0; a < CA_MAX; ++a) {
+            const float v = warp_sum(acc[r][a]);
+            if (lane == 0) red[w][r][a] = v;
         }
+    __syncthreads();
+    if (threadIdx.x < ROWS * CA_MAX) {
+        const int r = threadIdx.x / CA_MAX, a = threadIdx.x % CA_MAX;
+        if (a < Ca && row0 + r < n) {
+            float v = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v += red[k][r][a];
+            const long long o = (long long)(row0 + r) * Ca + a;
+            if (epi == SRGAN_EPI_BIAS_ACT) {
+                if (bias) v += bias[bias_mod ? a % bias_mod : a];
+                v = act_fwd(v, act, slope);
+            } else if (href && act != SRGAN_ACT_NONE) {
+                v *= act_bwd(to_f(href[o]), act, slope);
+            }
+            out[o] = from_f<T>(v);
+        }
+    }
 }
 
 template <typename T>
