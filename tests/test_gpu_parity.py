@@ -19,9 +19,11 @@ TOL = {'fp32': dict(scalar=1e-4, param=1e-4), 'bf16': dict(scalar=2e-2, param=2e
 def check_scalars(got, ref, tol, ctx):
     # gradient penalty / unlabeled loss can be ~0: absolute floor relative to the labeled loss scale.
     # The penalty is a hinge, lam*mean(max(r-1,0)^2): a relative error e on the gradient norm r becomes 2e*r/(r-1) on the
-    # penalty, so in bf16 mode (tol 2e-2 on r itself, checked through gradient_norm_mean) its band is 4x wider.
+    # penalty, so in bf16 mode (tol 2e-2 on r itself, checked through gradient_norm_mean) its band is 2x wider: the ONE
+    # stated exception to BASELINE's 2e-2 (measured first-step errors of every case: profiles/r2_bf16_parity_errors.txt --
+    # all scalars <= 7e-3 except this one, <= 2.1e-2).
     for k in SCALARS:
-        t = tol * 4 if (k == 'gradient_penalty' and tol > 1e-3) else tol
+        t = tol * 2 if (k == 'gradient_penalty' and tol > 1e-3) else tol
         assert got[k] == pytest.approx(ref[k], rel=t, abs=t * max(1e-3, abs(ref['labeled_loss']) * 1e-3)), \
             (ctx, k, got[k], ref[k])
 
@@ -400,8 +402,8 @@ def test_crowd_full_size_matches_reference_golden(precision, method):
     r.dnn_step(x, y)
     r.gan_step(x, y, u, 0, noise=(zz, alpha, z2))
     ref = {k: float(z[f'step0/scalars/{k}']) for k in SCALARS}
-    # 201 layers deep: bf16 rounding compounds (the gradient norm is a product through every layer)
-    t = 1e-4 if precision == 'fp32' else 5e-2
+    # BASELINE's bands: 1e-4 (fp32 mode), 2e-2 (bf16 mode; measured on this case: <= 7e-3, profiles/r2_bf16_parity_errors.txt)
+    t = TOL[precision]['scalar']
     check_scalars(r.scalars(), ref, t, ('crowd-full', precision))
     if precision == 'fp32':
         init = st
