@@ -199,6 +199,22 @@ int srgan_affine_grad(const void* dy, int dy_pitch, const void* x, int x_pitch, 
 int srgan_affine_bwd_grad(const void* dy, int dy_pitch, const void* x, void* dx, int x_pitch, int x_c0, long long rows, int C,
                           const float* gamma, const float* mean, const float* var, float eps, float* dgamma, float* dbeta,
                           int accumulate, int dtype, void* stream);
+/* ---- dense-layer GEMMs with the preceding BatchNorm + ReLU fused in (bf16 / tcgen05 only; SRGAN_ERR_UNSUPPORTED otherwise) ----
+ * _DenseLayer norm1 -> relu1 -> conv1 (crowd/models.py:339-341) and _Transition norm -> relu -> conv (:367-369): the 1x1
+ * convolution is a [rows x C] GEMM over the first C channels of the block's concat buffer x (pitch elements per row).
+ *
+ * srgan_bn_dgrad: backward of that pair in ONE launch, given dy [rows x K] (delta of the convolution output) and Wu [Cout][K]
+ * (Cout = C rounded up to 64, rows >= C zero):
+ *   d[r,c]  = (sum_k dy[r,k] * Wu[c,k]) * [ (x[r,c]-mean[c])*gamma[c]/sqrt(var[c]+eps) + beta[c] > 0 ]
+ *   dx[r,c] (+)= d[r,c] * gamma[c]/sqrt(var[c]+eps)                              (same pitch as x)
+ *   dgamma[c] += sum_r d[r,c]*(x[r,c]-mean[c])/sqrt(var[c]+eps) ; dbeta[c] += sum_r d[r,c]      (dgamma NULL: skipped)
+ *   d_out[r*d_pitch + c] = d[r,c]                                                (d_out NULL: not stored)
+ * It replaces srgan_conv_up (EPI_DACT against the stored ReLU output) + srgan_affine_bwd_grad: the ReLU mask is recomputed
+ * from x, so the normalised activation is not read, and the C-wide intermediate delta is never written. */
+int srgan_bn_dgrad(const void* dy, const void* Wu, void* dx, const void* x, long long rows, int K, int Cout, int C, int pitch,
+                   const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* dgamma,
+                   float* dbeta, void* d_out, int d_pitch, int accumulate, int dtype, void* stream);
+
 /* dst[:, d0:d0+C] (+)= src[:, s0:s0+C] : torch.cat writes / their backward reads, MapModule taps */
 int srgan_copy2d(const void* src, int src_pitch, int src_c0, void* dst, int dst_pitch, int dst_c0, long long rows, int C,
                  int accumulate, int dtype, void* stream);

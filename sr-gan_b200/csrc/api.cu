@@ -47,6 +47,11 @@ int umma_conv(int mode, const void* src, const void* W, void* out, int n, const 
               int bias_mod, const void* href, int epi, int act, float slope, const srgan_views* views, cudaStream_t st);
 int umma_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom* g, const srgan_views* views, cudaStream_t st);
 
+// bn_gemm.cu : dense-layer GEMMs with the preceding eval-mode BatchNorm + ReLU fused in (1 = launched, 0 = not eligible)
+int bn_dgrad(const void* dy, const void* Wu, void* dx, const void* x, long long rows, int K, int Cout, int C, int pitch,
+             const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* dgamma, float* dbeta,
+             void* d_out, int d_pitch, int accumulate, cudaStream_t st);
+
 // skinny.cu : few outputs over a long full-extent reduction axis (MapModule.linear1, the count feature layer)
 bool skinny_eligible(const srgan_geom* g);
 int skinny_conv(int mode, const void* src, const void* W, void* out, int n, const srgan_geom* g, const float* bias, int bias_mod,
@@ -140,6 +145,25 @@ int srgan_conv_wgrad(const void* S, const void* L, float* dW, int n, const srgan
     }
     SRGAN_REQUIRE(views == nullptr, "srgan_conv_wgrad: channel windows (srgan_views) need a tcgen05-eligible bf16 shape");
     return simt_wgrad(S, L, dW, n, g, dtype, st);
+}
+
+int srgan_bn_dgrad(const void* dy, const void* Wu, void* dx, const void* x, long long rows, int K, int Cout, int C, int pitch,
+                   const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* dgamma,
+                   float* dbeta, void* d_out, int d_pitch, int accumulate, int dtype, void* stream) {
+    SRGAN_REQUIRE(dy && Wu && dx && x && gamma && beta && mean && var, "srgan_bn_dgrad: null pointer");
+    SRGAN_REQUIRE(dtype == SRGAN_BF16, "srgan_bn_dgrad: the fused dense-layer kernels are bf16 / tcgen05 only");
+    SRGAN_REQUIRE(rows >= 0 && K > 0 && C > 0 && Cout >= C && pitch >= C, "srgan_bn_dgrad: bad sizes");
+    if (rows == 0) return SRGAN_OK;
+    int took = bn_dgrad(dy, Wu, dx, x, rows, K, Cout, C, pitch, gamma, beta, mean, var, eps, dgamma, dbeta, d_out, d_pitch,
+                        accumulate, (cudaStream_t)stream);
+    if (took < 0) return took;
+    if (took == 0) {
+        srgan_set_error("srgan_bn_dgrad: shape not eligible (K %% 64, Cout %% 64, C %% 8, pitch %% 8, 16-byte aligned pointers)");
+        return SRGAN_ERR_UNSUPPORTED;
+    }
+    t_last_tensor = 1;
+    g_tensor_calls.fetch_add(1, std::memory_order_relaxed);
+    return SRGAN_OK;
 }
 
 }  // extern "C"

@@ -207,6 +207,11 @@ class Engine:
         # self.{labeled,unlabeled,fake,interpolates}_features (rows x | u | fake | x_hat of the D step; the fake block is
         # replaced by the generator step's, srgan.py:386).  Off by default: the mirror Experiment has no reader.
         self.publish_features = False
+        if d_net.graph is not None and any(op.fuse for op in d_net.graph):
+            ok = getattr(ops, 'bn_fusion_supported', None)
+            if ok is None or not ok(act_dtype):
+                raise ValueError('the net description asks for BatchNorm-fused dense-layer kernels (Op.fuse), which exist on '
+                                 'the bf16 tcgen05 path only')
         for st in (self.D, self.G, self.DNN):
             if st is not None:
                 self.repack(st)
@@ -346,8 +351,10 @@ class Engine:
             macs = n * g.Hs * g.Ws * ca * g.R * g.S * cb
         out_side = (small if l.fwd == 'down' else large) if role in ('forward', 'tangent') else (large if l.fwd == 'down' else small)
         # operands once each; the tangent / data-gradient epilogues also read the stored activation of the output side;
-        # the weight gradient reads both activations and writes fp32 weights (counted as 2 elements each)
-        pr['elems'] += small + large + (2 * wts if role == 'wgrad' else wts) + (out_side if role in ('tangent', 'dgrad') else 0)
+        # the weight gradient reads both activations and writes fp32 weights (counted as 2 elements each); the BatchNorm-
+        # fused data gradient reads the concat buffer and reads + writes its delta (3 output-side streams)
+        pr['elems'] += (small + large + (2 * wts if role == 'wgrad' else wts) + (out_side if role in ('tangent', 'dgrad') else 0)
+                        + (2 * out_side if role == 'dgrad_bn' else 0))
         pr['flops'] += 2.0 * macs
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream(self.device))
@@ -518,7 +525,8 @@ class Engine:
         delta rows [4B,5B), masks from the activations of rows [3B,4B); g0 = d s / d x_hat (no mask)."""
         net = st.net
         if net.graph is not None:
-            return self.graph_backward(st, acts, deltas, 4 * B, 5 * B, 3 * B, 0, 0, False, (g0, None, ACT_NONE), None)
+            return self.graph_backward(st, acts, deltas, 4 * B, 5 * B, 3 * B, 0, 0, False, (g0, None, ACT_NONE), None,
+                                       keep_pre=True)
         L = len(net.layers)
         for i in range(L, 1, -1):
             l, lp = net.layers[i - 1], net.layers[i - 2]
@@ -652,13 +660,16 @@ class Engine:
         else:
             raise ValueError(op.kind)
 
-    def graph_backward(self, st: NetState, acts, deltas, lo, hi, mlo, wlo, whi, weight_grads, input_grad, hook):
+    def graph_backward(self, st: NetState, acts, deltas, lo, hi, mlo, wlo, whi, weight_grads, input_grad, hook, keep_pre=False):
         """Reverse pass of a graph net over delta rows [lo,hi); the activations that provide masks and weight-gradient
         inputs are rows [mlo, mlo+n) (== [lo,hi) for an ordinary backward; the x_hat rows for the g-chain).
         Convolution weight gradients cover rows [wlo,whi) of (acts, deltas) in one launch -- ordinary rows plus, when
         whi > hi, the tangent block (u_{l-1}, gamma_l); the BatchNorm-scale gradient of the tangent block is a second call
         (no mean subtraction, no bias term).  input_grad = (dinput, href, act): also d/d(network input).
-        hook(buffer name) is called before the producer of a map buffer is processed (crowd labeled map loss)."""
+        hook(buffer name) is called before the producer of a map buffer is processed (crowd labeled map loss).
+        keep_pre: fused BatchNorm ops (Op.fuse) also store the delta w.r.t. the BatchNorm output's pre-activation, which
+        the unfused pass leaves in the delta buffer of that output (the g-chain: its rows are the tangent block of the
+        BatchNorm-scale gradient)."""
         net, ops, R, P = st.net, self.ops, self._brows, st.params
         n = hi - lo
         for name, b in net.bufs.items():
@@ -710,8 +721,25 @@ class Engine:
                     if input_grad is not None:
                         dinput, ihref, iact = input_grad
                         self._bwd_data_layer(st, l, dy, dinput, n * l.gemm_rows, ihref, iact, 0.0, lo=lo)
+                elif op.pre is not None and op.pre.fuse:
+                    # BatchNorm + ReLU backward fused into this data-gradient GEMM: straight into the concat delta
+                    a = op.pre
+                    cbuf, nm = net.bufs[a.src], a.name
+                    mean, var = P[nm + '.running_mean'], P[nm + '.running_var']
+                    timed = self._probe_open('dgrad_bn', st, l, n * l.gemm_rows)
+                    ops.bn_dgrad(dy, st.wu_[l.name], R(deltas[a.src], cbuf, lo, hi), R(acts[a.src], cbuf, mlo, mlo + n),
+                                 n * l.gemm_rows, l.geom.Ca, l.geom.Cb, a.C, cbuf.ch, P[nm + '.weight'], P[nm + '.bias'], mean, var,
+                                 self.BN_EPS, st.g(nm + '.weight') if weight_grads else None,
+                                 st.g(nm + '.bias') if weight_grads else None, dx if keep_pre else None, sb.ch, cbuf.accumulate)
+                    self._probe_close(timed)
+                    if weight_grads and whi > hi:      # the tangent block's BatchNorm-scale gradient (the g-chain kept its delta)
+                        off_path(lambda a=a, sb=sb, cbuf=cbuf, nm=nm, mean=mean, var=var, op=op: ops.affine_grad(
+                            R(deltas[op.src], sb, hi, whi), sb.ch, R(acts[a.src], cbuf, hi, whi), cbuf.ch, a.c0,
+                            (whi - hi) * cbuf.rows, a.C, mean, var, self.BN_EPS, st.g(nm + '.weight'), None, False))
                 else:
                     self._bwd_data_layer(st, l, dy, dx, n * l.gemm_rows, xa, sb.act, sb.slope, lo=lo, views=vw)
+            elif op.kind == 'affine' and op.fuse:
+                pass                      # carried out by the convolution that consumes its output (above)
             elif op.kind == 'affine':
                 nm = op.name
                 mean, var = P[nm + '.running_mean'], P[nm + '.running_var']

@@ -263,8 +263,10 @@ class StepRunner:
         self.modules = dict(D=D, G=G, DNN=DNN)
         # bf16 mode: dense layers write / read their channel window of the concat buffers in place (tcgen05 kernels only)
         direct = precision == 'bf16' and os.environ.get('SRGAN_NO_DIRECT_CONCAT', '0') != '1'
-        d_net, g_net = nets.describe_module(D, direct), nets.describe_module(G)
-        if nets.describe_module(DNN, direct) != d_net:
+        # ... and the BatchNorm + ReLU in front of every trunk 1x1 convolution is fused into that convolution's kernels
+        fuse = int(os.environ.get('SRGAN_FUSE_BN', '1')) if precision == 'bf16' else 0
+        d_net, g_net = nets.describe_module(D, direct, fuse), nets.describe_module(G)
+        if nets.describe_module(DNN, direct, fuse) != d_net:
             raise ValueError('DNN and D must share an architecture (srgan.py model_setup)')
         if method not in ('srgan', 'dggan'):
             raise ValueError(f'method={method!r}: the B200 path covers srgan and dggan (sgan: SURVEY 8f rank 3)')

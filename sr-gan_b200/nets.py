@@ -154,6 +154,10 @@ class Op:
     stride: int = 0
     pad: int = 0
     branch: int = 0                # 0 = trunk; i > 0 = side branch i (crowd MapModule i): reads a trunk buffer, ends in `features`
+    # BatchNorm fusion (bf16 tcgen05 path, csrc/bn_gemm.cu): an 'affine' op with fuse > 0 is carried out by the 1x1 'conv' op
+    # that consumes its output (that op's `pre` points back at it).  fuse = 1: the backward pass (srgan_bn_dgrad).
+    fuse: int = 0
+    pre: Optional['Op'] = None
 
 
 @dataclass
@@ -267,7 +271,7 @@ def dcgan_g(image_size=128, conv_dim=64, z_dim=256) -> Net:
 
 
 def knn_densenet_cat(block_config=(6, 12, 48, 32), growth_rate=32, num_init_features=64, bn_size=4, image_size=224,
-                     label_size=224, pad_to=64, n_out=1, direct_concat=False) -> Net:
+                     label_size=224, pad_to=64, n_out=1, direct_concat=False, fuse_bn=0) -> Net:
     """crowd/models.py:1049-1166 KnnDenseNetCat as a graph.  Buffers: 'x' input; 'c0','n0' stem; 'cat{i}' the in-place
     concat buffer of dense block i (the stem pool / transition pool write its first channels, every dense layer appends
     growth_rate channels); per dense layer 'n1','b','n2','new'; per transition 'tn','tc'; per MapModule 't','map','m1'..
@@ -276,7 +280,9 @@ def knn_densenet_cat(block_config=(6, 12, 48, 32), growth_rate=32, num_init_feat
     `pad_to` channels so that every trunk contraction is tcgen05-eligible (K and N multiples of 64); 1x1 convolutions are
     declared as [pixels x C] GEMMs (Layer.gemm_rows).  direct_concat: the 3x3 convolution of a dense layer writes its
     growth_rate channels straight into their window of the concat buffer and its gradients read that window of the concat
-    delta (Op.C / Op.c0 on the conv op, srgan_views in the kernels): no 'new' buffer, no slice copies."""
+    delta (Op.C / Op.c0 on the conv op, srgan_views in the kernels): no 'new' buffer, no slice copies.  fuse_bn > 0: norm1 /
+    relu1 of every dense layer and norm / relu of every transition are carried out by the 1x1 convolution that follows them
+    (Op.fuse / Op.pre)."""
     g, bs = growth_rate, bn_size
 
     def pad(c):
@@ -323,6 +329,8 @@ def knn_densenet_cat(block_config=(6, 12, 48, 32), growth_rate=32, num_init_feat
             ops.append(Op('affine', cat, 'n1.' + tag, name=pre + '.norm1', C=c, c0=0))
             buf('b.' + tag, h * h, cb)
             conv(pre + '.conv1', 'n1.' + tag, 'b.' + tag, linear_geom(cb, pad(c)), 'down', (bs * g, c, 1, 1), gemm_rows=h * h)
+            if fuse_bn:
+                ops[-1].pre, ops[-2].fuse = ops[-2], fuse_bn
             buf('n2.' + tag, h * h, cb, **RELU)
             ops.append(Op('affine', 'b.' + tag, 'n2.' + tag, name=pre + '.norm2', C=bs * g))
             if direct_concat:
@@ -339,6 +347,8 @@ def knn_densenet_cat(block_config=(6, 12, 48, 32), growth_rate=32, num_init_feat
             ops.append(Op('affine', cat, f'tn{bi}', name=pre + '.norm', C=c, c0=0))
             buf(f'tc{bi}', h * h, pad(c // 2))
             conv(pre + '.conv', f'tn{bi}', f'tc{bi}', linear_geom(pad(c // 2), pad(c)), 'down', (c // 2, c, 1, 1), gemm_rows=h * h)
+            if fuse_bn:
+                ops[-1].pre, ops[-2].fuse = ops[-2], fuse_bn
             c //= 2
             if h % 2:
                 raise ValueError('transition input must have an even extent')
@@ -390,7 +400,7 @@ def knn_densenet_cat(block_config=(6, 12, 48, 32), growth_rate=32, num_init_feat
                feature_buf='features', head_parts=head_parts, map_bufs=tuple(maps), label_size=L)
 
 
-def describe_module(module, direct_concat=False) -> Net:
+def describe_module(module, direct_concat=False, fuse_bn=0) -> Net:
     """Maps a reference nn.Module instance (or this package's mirrors) to its Net, by structure, not by import."""
     sd = {k: tuple(v.shape) for k, v in module.state_dict().items()}
     if 'linear4.weight' in sd and 'linear1.weight' in sd:
@@ -416,7 +426,8 @@ def describe_module(module, direct_concat=False) -> Net:
         k1 = sd['map_module1.map_transposed_conv_layer.weight'][2]
         image = (label // k1) * 8
         return knn_densenet_cat(cfg, growth, init, bn_size, image, label, n_out=sd['count_layer.weight'][0],
-                                direct_concat=direct_concat and growth % 8 == 0 and init % 8 == 0)
+                                direct_concat=direct_concat and growth % 8 == 0 and init % 8 == 0,
+                                fuse_bn=fuse_bn if (growth % 8 == 0 and init % 8 == 0) else 0)
     if 'fc.0.weight' in sd and 'layer4.0.weight' in sd:
         z_dim, c8, k, _ = sd['fc.0.weight']
         return dcgan_g(k * 16, c8 // 8, z_dim)

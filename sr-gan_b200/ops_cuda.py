@@ -35,7 +35,7 @@ _EXPORTS = (
     'srgan_repack', 'srgan_im2col', 'srgan_col2im', 'srgan_adam_prepare', 'srgan_coefficient_step',
     'srgan_coefficient_step_workspace_bytes', 'srgan_affine', 'srgan_affine_bwd', 'srgan_affine_grad', 'srgan_copy2d',
     'srgan_maxpool', 'srgan_maxpool_bwd', 'srgan_avgpool', 'srgan_avgpool_bwd', 'srgan_crowd_loss', 'srgan_crowd_map_grad', 'srgan_depth_to_space', 'srgan_adam_multi', 'srgan_affine_bwd_grad',
-    'srgan_adam_layout_multi',
+    'srgan_adam_layout_multi', 'srgan_bn_dgrad',
 )
 
 _lib = None
@@ -102,6 +102,7 @@ def load_library(path: str = LIB_PATH):
     lib.srgan_adam_layout_multi.argtypes = [vp, c_int, c_ll, vp, vp, vp, vp, c_f, c_f, c_f, c_f, c_int, vp]
     lib.srgan_depth_to_space.argtypes = [vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, vp]
     lib.srgan_crowd_map_grad.argtypes = [vp, vp, vp, vp, c_int, c_ll, c_int, c_int, c_f, c_int, vp]
+    lib.srgan_bn_dgrad.argtypes = [vp, vp, vp, vp, c_ll, c_int, c_int, c_int, c_int, vp, vp, vp, vp, c_f, vp, vp, vp, c_int, c_int, c_int, vp]
     lib.srgan_tensor_launch_count.restype = c_ll
     lib.srgan_simt_fallback_count.restype = c_ll
     for name in _EXPORTS[7:]:
@@ -451,3 +452,16 @@ class CudaOps:
                                                 rows, C, self._pf(gamma), self._pf(mean), self._pf(var), eps, self._pf(dgamma),
                                                 self._pf(dbeta), int(bool(accumulate)), _dt(dy.dtype), self._stream()),
                  'srgan_affine_bwd_grad')
+
+    # -------------------------------------------------------------- fused dense-layer kernels (csrc/bn_gemm.cu)
+    @staticmethod
+    def bn_fusion_supported(dtype):
+        """The BatchNorm-fused dense-layer GEMMs exist on the bf16 tcgen05 path only."""
+        return dtype == torch.bfloat16
+
+    def bn_dgrad(self, dy, Wu, dx, x, rows, K, Cout, C, pitch, gamma, beta, mean, var, eps, dgamma, dbeta, d_out, d_pitch,
+                 accumulate):
+        self._ck(self.lib.srgan_bn_dgrad(self._p(dy), self._p(Wu, dy.dtype), self._p(dx, dy.dtype), self._p(x, dy.dtype), rows, K, Cout,
+                                         C, pitch, self._pf(gamma), self._pf(beta), self._pf(mean), self._pf(var), eps,
+                                         self._pf(dgamma), self._pf(dbeta), self._p(d_out, dy.dtype) if d_out is not None else None,
+                                         d_pitch, int(bool(accumulate)), _dt(dy.dtype), self._stream()), 'srgan_bn_dgrad')

@@ -103,10 +103,10 @@ def test_thin_layer_lowering_matches_oracle_fp64():
             assert rel(mine.params[k], v) < 1e-8, (net, k, rel(mine.params[k], v))
 
 
-def build_crowd_engine(st, dtype, spec_kwargs, image, z_dim, g_conv_dim, direct_concat=False):
+def build_crowd_engine(st, dtype, spec_kwargs, image, z_dim, g_conv_dim, direct_concat=False, fuse_bn=0):
     d_net = nets.knn_densenet_cat(spec_kwargs['block_config'], spec_kwargs['growth_rate'], spec_kwargs['num_init_features'],
                                   spec_kwargs['bn_size'], image, spec_kwargs['label_patch_size'],
-                                  n_out=2 if st.d_spec.dggan else 1, direct_concat=direct_concat)
+                                  n_out=2 if st.d_spec.dggan else 1, direct_concat=direct_concat, fuse_bn=fuse_bn)
     g_net = nets.dcgan_g(image, g_conv_dim, z_dim)
     D = {k: v.clone() for k, v in st.D.items()}
     G = {k: v.clone() for k, v in st.G.items()}
@@ -114,21 +114,24 @@ def build_crowd_engine(st, dtype, spec_kwargs, image, z_dim, g_conv_dim, direct_
     return engine.Engine(TorchOps(), d_net, g_net, D, G, DNN, act_dtype=dtype, device='cpu')
 
 
-@pytest.mark.parametrize('direct', [False, True])
+@pytest.mark.parametrize('direct,fuse', [(False, 0), (True, 0), (True, 1), (True, 2)])
 @pytest.mark.parametrize('method', ['srgan', 'dggan'])
-def test_crowd_graph_schedule_matches_oracle_fp64(method, direct):
+def test_crowd_graph_schedule_matches_oracle_fp64(method, direct, fuse):
     """Crowd SR-GAN (KnnDenseNetCat graph: eval-mode BatchNorm affine with trainable weight/bias, ReLU, max/avg pools,
     in-place concat, three MapModules, summed count heads, crowd labeled loss incl. the map term) through the explicit
     schedule -- forward, g-chain, tangent chain, one backward with the tangent-block gradients -- against the oracle's
     autograd double-backward, fp64, reduced DenseNet (2,2,2,2) at 64x64 (the full DenseNet-201 is pinned against the
     reference in tests/test_oracle_golden.py).  direct: the dense layers' 3x3 convolutions write / read their channel
-    window of the concat buffers in place (srgan_views; the bf16 product path) instead of going through slice copies."""
+    window of the concat buffers in place (srgan_views; the bf16 product path) instead of going through slice copies.
+    fuse: the BatchNorm + ReLU in front of the trunk's 1x1 convolutions is carried out by those convolutions' kernels
+    (1 = the backward pass, 2 = forward / weight gradient too; csrc/bn_gemm.cu)."""
     dt = torch.float64
     kw = dict(block_config=(2, 2, 2, 2), growth_rate=8, num_init_features=16, bn_size=2, label_patch_size=64)
     st = O.init_crowd(seed=1, image_size=64, z_dim=16, g_conv_dim=8, dtype=dt, scale=2.0, dggan=(method == 'dggan'), **kw)
     cfg = O.StepConfig(method=method, batch_size=3, matching_loss_multiplier=1e3, contrasting_loss_multiplier=1e2,
                        gradient_penalty_multiplier=1e2, map_multiplier=1e-3, weight_decay=1e-3)
-    eng = build_crowd_engine(st, dt, kw, 64, 16, 8, direct_concat=direct)
+    eng = build_crowd_engine(st, dt, kw, 64, 16, 8, direct_concat=direct, fuse_bn=fuse)
+    assert sum(1 for op in eng.d_net.graph if op.fuse) == (11 if fuse else 0)      # 8 dense layers + 3 transitions
     assert any(op.C for op in eng.d_net.graph if op.kind == 'conv') == direct
     assert ('new.1.1' in eng.d_net.bufs) != direct
     B = 3

@@ -1,0 +1,78 @@
+"""GPU: the BatchNorm-fused dense-layer kernels (csrc/bn_gemm.cu) against their op-level semantics in tests/torch_ops.py,
+shapes of the DenseNet trunk (K = 128 bottleneck channels against concat widths that are / are not multiples of the 128-wide
+tile, ragged row counts, concat pitch > C, transition-sized K)."""
+import pytest
+import torch
+
+from tests.torch_ops import TorchOps
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from srgan_b200.ops_cuda import CudaOps
+    return CudaOps()
+
+
+def rnd(gen, *shape, dt=torch.float32):
+    return (torch.rand(*shape, generator=gen) * 2 - 1).to(dt)
+
+
+def close(a, b, t, what='', outliers=0.0):
+    """max error relative to the largest reference magnitude; `outliers` = fraction of elements allowed beyond it (a ReLU mask
+    recomputed in fp32 on both sides may flip for the handful of pre-activations within an ulp of zero)."""
+    a, b = a.float().cpu(), b.float().cpu()
+    err = (a - b).abs()
+    ref = b.abs().max().item() + 1e-12
+    bad = (err / ref > t).float().mean().item()
+    assert bad <= outliers, f'{what}: {bad:.2e} of the elements beyond {t:.0e} (max rel err {err.max().item() / ref:.3e})'
+
+
+def bn_params(gen, C):
+    gamma = rnd(gen, C) + 1.5
+    gamma[::7] *= -0.5                                   # negative scales exist in trained nets
+    return gamma, rnd(gen, C) * 0.3, rnd(gen, C) * 0.2, torch.rand(C, generator=gen) + 0.5
+
+
+@pytest.mark.parametrize('rows,K,C,pitch', [(3001, 128, 96, 256), (12544 + 5, 128, 1056, 1920), (777, 192, 384, 384),
+                                            (50, 128, 64, 64), (4 * 3136, 128, 160, 256), (20000, 64, 128, 136)])
+@pytest.mark.parametrize('acc,grads,keep', [(True, True, False), (False, False, True), (True, False, False), (False, True, True)])
+def test_bn_dgrad(ops, rows, K, C, pitch, acc, grads, keep):
+    gen = torch.Generator().manual_seed(rows + C + K)
+    ref = TorchOps()
+    Cout = (C + 63) // 64 * 64
+    dy = rnd(gen, rows * K, dt=BF)
+    Wu = torch.zeros(Cout, K)
+    Wu[:C] = rnd(gen, C, K) * 0.1
+    Wu = Wu.reshape(-1).to(BF)
+    x = rnd(gen, rows * pitch, dt=BF)
+    gamma, beta, mean, var = bn_params(gen, C)
+    dx_ref = rnd(gen, rows * pitch, dt=BF)
+    dx = dx_ref.clone().cuda()
+    dpitch = Cout
+    d_ref = rnd(gen, rows * dpitch, dt=BF) if keep else None
+    d = d_ref.clone().cuda() if keep else None
+    dg_ref, db_ref = rnd(gen, C), rnd(gen, C)
+    dg, db = dg_ref.clone().cuda(), db_ref.clone().cuda()
+    cu = lambda t: t.cuda()
+    ref.bn_dgrad(dy, Wu, dx_ref, x, rows, K, Cout, C, pitch, gamma, beta, mean, var, 1e-5, dg_ref if grads else None,
+                 db_ref if grads else None, d_ref, dpitch, acc)
+    ops.bn_dgrad(cu(dy), cu(Wu), dx, cu(x), rows, K, Cout, C, pitch, cu(gamma), cu(beta), cu(mean), cu(var), 1e-5,
+                 dg if grads else None, db if grads else None, d, dpitch, acc)
+    torch.cuda.synchronize()
+    close(dx, dx_ref, 2e-2, 'bn_dgrad dx (incl. the untouched columns >= C)', outliers=1e-5)
+    assert torch.equal(dx.cpu().view(rows, pitch)[:, C:], dx_ref.view(rows, pitch)[:, C:])
+    close(dg, dg_ref, 1e-2, 'bn_dgrad dgamma')
+    close(db, db_ref, 1e-2, 'bn_dgrad dbeta')
+    if keep:
+        close(d, d_ref, 2e-2, 'bn_dgrad d_out', outliers=1e-5)
+        assert torch.equal(d.cpu().view(rows, dpitch)[:, C:], d_ref.view(rows, dpitch)[:, C:])
+
+
+def test_bn_dgrad_refuses_ineligible(ops):
+    t = torch.zeros(64 * 100, dtype=BF, device='cuda')
+    f = torch.zeros(100, device='cuda')
+    with pytest.raises(RuntimeError):                    # K not a multiple of 64
+        ops.bn_dgrad(t, t, t, t, 10, 100, 64, 64, 64, f, f, f, f, 1e-5, None, None, None, 0, False)

@@ -458,3 +458,33 @@ class TorchOps:
         self.affine_grad(dy, dy_pitch, x, x_pitch, x_c0, rows, C, mean, var, eps, dgamma, dbeta, True)
         self.affine_bwd(dy, dy_pitch, dx, x_pitch, x_c0, rows, C, gamma, var, eps, accumulate)
         self.launches -= 1
+
+    # ---- fused dense-layer kernels (csrc/bn_gemm.cu)
+    @staticmethod
+    def bn_fusion_supported(dtype):
+        return True
+
+    def bn_dgrad(self, dy, Wu, dx, x, rows, K, Cout, C, pitch, gamma, beta, mean, var, eps, dgamma, dbeta, d_out, d_pitch,
+                 accumulate):
+        """d = (dy . Wu^T)[:, :C] * [bn(x) > 0]; dx[:, :C] (+)= d * gamma/sigma; dgamma += sum d*(x-mean)/sigma; dbeta += sum d;
+        d_out[:, :C] = d (optional).  x / dx: rows of `pitch` elements; dy dense [rows, K]; Wu [Cout, K]."""
+        self.launches += 1
+        cd = self._cd(dy)
+        g, b = gamma.detach().to(cd), beta.detach().to(cd)
+        mu, sig = mean.detach().to(cd), torch.sqrt(var.detach().to(cd) + eps)
+        xs = x.view(rows, pitch)[:, :C].to(cd)
+        prod = dy.view(rows, K).to(cd) @ Wu.view(Cout, K)[:C].to(cd).t()
+        prod = prod.to(dy.dtype).to(cd)                       # the accumulator is rounded to the activation dtype first
+        d = prod * (((xs - mu) * (g / sig) + b) > 0).to(cd)
+        v = d * (g / sig)
+        dxv = dx.view(rows, pitch)
+        if accumulate:
+            dxv[:, :C] = (dxv[:, :C].to(cd) + v).to(dx.dtype)
+        else:
+            dxv[:, :C] = v.to(dx.dtype)
+        if dgamma is not None:
+            dgamma += ((d * (xs - mu)).sum(0) / sig).to(dgamma.dtype)
+            if dbeta is not None:
+                dbeta += d.sum(0).to(dbeta.dtype)
+        if d_out is not None:
+            d_out.view(rows, d_pitch)[:, :C] = d.to(d_out.dtype)
