@@ -154,42 +154,53 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
         const int te = threadIdx.x - 64;         // 0..255 among the epilogue threads
         const uint32_t after_ring = (uint32_t)stages * BD_STAGE_BYTES;
         const uint32_t stg = tiles + after_ring + (uint32_t)ew * EPI_STG_BYTES;
-        const uint32_t zone = tiles + after_ring + 8u * EPI_STG_BYTES + (uint32_t)ew * BD_ZONE_WARP;
+        const uint32_t zone = tiles + after_ring + 8u * EPI_STG_BYTES + (uint32_t)ew * BD_ZONE_WARP + (uint32_t)lane * 16u;
         float* tab = reinterpret_cast<float*>(smem_raw + (tiles - smem_u32(smem_raw)) + after_ring + 8u * EPI_STG_BYTES + 8u * BD_ZONE_WARP);
         float* t_s = tab;                        // gamma / sigma
-        float* t_mu = tab + p.Cpad;
-        float* t_be = tab + 2 * p.Cpad;
+        float* t_t = tab + p.Cpad;               // beta - mean * gamma / sigma
         const bool grads = p.dgamma != nullptr;
+        const bool accum = p.accumulate != 0;
         for (int c = te; c < p.Cpad; c += 256) {
-            float s = 0.f, mu = 0.f, be = 0.f;
-            if (c < p.C) { s = bn_scale_f(__ldg(p.gamma + c), __ldg(p.var + c), p.eps); mu = __ldg(p.mean + c); be = __ldg(p.beta + c); }
-            t_s[c] = s; t_mu[c] = mu; t_be[c] = be;
+            float s = 0.f, t = 0.f;
+            if (c < p.C) { s = bn_scale_f(__ldg(p.gamma + c), __ldg(p.var + c), p.eps); t = bn_shift(__ldg(p.beta + c), __ldg(p.mean + c), s); }
+            t_s[c] = s; t_t[c] = t;
         }
         epi_bar_sync();
 
-        // The cat / dcat pieces travel through a lane-private ring of 8 slots per warp (slot k = chunk k/4, row group k%4;
-        // 32 lanes x 16 bytes x 2 streams each), one cp.async group per slot: a slot is refilled with the NEXT tile's piece
-        // right after it has been consumed, so every piece is in flight for a whole tile time and ~all of the zone (64 KB
-        // per CTA) is outstanding at any moment (Little: 44 GB/s per SM x ~1.5 us).
-        auto issue = [&](int tile, int k) {
-            if (tile < tile_end) {
-                const int mt = tile % p.m_tiles, ny = tile / p.m_tiles;
-                const int cb = ny * BN + (half + 2 * (k >> 2)) * 32 + t_unit * 8;
-                const long long gr = (long long)mt * TILE_M + q * 32 + 8 * (k & 3) + t_row;
-                const bool ok = gr < p.rows && cb < p.C;
-                const long long off = ok ? gr * p.pitch + cb : 0;
-                cp_async16(zone + (uint32_t)(k * 1024 + lane * 16), p.x + off, ok ? 16u : 0u);
-                if (p.accumulate) cp_async16(zone + (uint32_t)(k * 1024 + 512 + lane * 16), p.dx + off, ok ? 16u : 0u);
-            }
+        // Per tile a lane touches 8 pieces ("slots" k = 4*jj + it: chunk half + 2*jj, rows 8*it + t_row of the warp's 32) of 16
+        // bytes of cat and of dcat.  They travel through a lane-private ring of 8 landing slots per warp (32 lanes x 16
+        // bytes x 2 streams each), one cp.async group per slot: a slot is refilled with the NEXT tile's piece right after
+        // it has been consumed, so every piece is in flight for a whole tile time and ~all of the zone (64 KB per CTA) is
+        // outstanding at any moment (Little: 44 GB/s per SM x ~1.5 us).
+        // Geometry of a tile for this lane: element offset of slot 0, rows left below the lane's first row, channel validity.
+        const int pitch8 = 8 * p.pitch;
+        struct Geo { long long off; int rows_left; int c0; };
+        auto geo = [&](int mt, int ny) {
+            Geo g;
+            const long long r = (long long)mt * TILE_M + q * 32 + t_row;
+            const long long left = p.rows - r;
+            g.rows_left = left > 64 ? 64 : (left < 0 ? 0 : (int)left);
+            g.c0 = ny * BN + half * 32 + t_unit * 8;
+            g.off = r * p.pitch + g.c0;
+            return g;
+        };
+        auto issue = [&](const Geo& g, bool live_tile, int k) {
+            const int jj = k >> 2, it = k & 3;
+            const bool ok = live_tile && 8 * it < g.rows_left && g.c0 + jj * 64 < p.C;
+            const long long o = ok ? g.off + jj * 64 + it * pitch8 : 0;
+            cp_async16(zone + (uint32_t)(k * 1024), p.x + o, ok ? 16u : 0u);
+            if (accum) cp_async16(zone + (uint32_t)(k * 1024 + 512), p.dx + o, ok ? 16u : 0u);
             cp_async_commit();                   // always: the group count per slot stays fixed
         };
+        int mt = tile_begin % p.m_tiles, ny = tile_begin / p.m_tiles;
+        Geo gc = geo(mt, ny);
 #pragma unroll
-        for (int k = 0; k < 4 * BD_NCH; ++k) issue(tile_begin, k);
+        for (int k = 0; k < 4 * BD_NCH; ++k) issue(gc, tile_begin < tile_end, k);
 
         // partial sums of dgamma / dbeta stay in registers while consecutive tiles cover the same channels (a CTA walks a
-        // contiguous range of tiles, row tiles fastest): [chunk][0..7] sum d * (x - mean), [chunk][8..15] sum d over the rows
-        // this lane has seen; combined across the 8 lanes that share the channels and added to global memory when the
-        // channel tile changes
+        // contiguous range of tiles, row tiles fastest): [chunk][0..7] sum d * x, [chunk][8..15] sum d over the rows this
+        // lane has seen; (sum d*x - mean * sum d) combined across the 8 lanes that share the channels and added to global
+        // memory when the channel tile changes
         float acc[BD_NCH][16];
 #pragma unroll
         for (int jj = 0; jj < BD_NCH; ++jj)
@@ -199,6 +210,9 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
 #pragma unroll
             for (int jj = 0; jj < BD_NCH; ++jj) {
                 float* a = acc[jj];
+                const int cl = ny * BN + (half + 2 * jj) * 32 + t_unit * 8;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[e] = fmaf(-(cl + e < p.C ? __ldg(p.mean + cl + e) : 0.f), a[8 + e], a[e]);
                 {   // recursive halving over lane bits 4, 3, 2: kind = bit 4 (0: dgamma term, 1: dbeta term),
                     // channel = 4*bit3 + 2*bit2 + {0, 1} of this lane's 8
                     const bool hi = (lane & 16) != 0;
@@ -224,7 +238,7 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
                         a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
                     }
                 }
-                const int c = ny * BN + (half + 2 * jj) * 32 + t_unit * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2;
+                const int c = cl + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     if (c + i < p.C && a[i] != 0.f) {
@@ -236,25 +250,36 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
                 for (int e = 0; e < 16; ++e) a[e] = 0.f;
             }
         };
-        int tl = 0, ny_acc = tile_begin / p.m_tiles;
+        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+        int tl = 0;
         for (int tile = tile_begin; tile < tile_end; ++tile, ++tl) {
-            const int mt = tile % p.m_tiles, ny = tile / p.m_tiles;
             const int buf = tl & 1;
             const uint32_t bph = (tl >> 1) & 1;
-            if (grads && ny != ny_acc) { flush(ny_acc); ny_acc = ny; }
+            // the next tile of this CTA's range (row tiles fastest)
+            int mt_n = mt + 1, ny_n = ny;
+            if (mt_n == p.m_tiles) { mt_n = 0; ++ny_n; }
+            const bool live_n = tile + 1 < tile_end;
+            const Geo gn = geo(mt_n, ny_n);
             mbar_wait(smem_u32(&tmem_full_bar[buf]), bph);
             tc_fence_after();
 #pragma unroll
             for (int jj = 0; jj < BD_NCH; ++jj) {
                 const int j = half + 2 * jj;
-                const int cbase = ny * BN + j * 32;
-                const bool live = cbase < p.C;   // warp-uniform: chunks beyond the last channel (partial last N tile) carry no data
-                const int cb = cbase + t_unit * 8;
-                const bool cok = cb < p.C;
-                float s8[8], mu8[8], be8[8];
+                const bool live = ny * BN + j * 32 < p.C;   // warp-uniform: chunks beyond the last channel (partial last N tile) carry no data
+                const bool cok = gc.c0 + jj * 64 < p.C;
+                float s8[8], t8[8];
                 if (live) {
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + j * 32, v);
+                    const int ct = cok ? gc.c0 + jj * 64 : 0;
+                    const float4* ps = reinterpret_cast<const float4*>(t_s + ct);
+                    const float4* pt = reinterpret_cast<const float4*>(t_t + ct);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float4 a = ps[h], b = pt[h];
+                        s8[4 * h] = a.x; s8[4 * h + 1] = a.y; s8[4 * h + 2] = a.z; s8[4 * h + 3] = a.w;
+                        t8[4 * h] = b.x; t8[4 * h + 1] = b.y; t8[4 * h + 2] = b.z; t8[4 * h + 3] = b.w;
+                    }
                     tmem_ld_wait();
                     // round to bf16 (what the unfused data-gradient kernel stores) and transpose: row-per-lane -> 8 channels x 4 rows
 #pragma unroll
@@ -269,64 +294,366 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
                         sts128(stg_addr(stg, lane, g), w);
                     }
                     __syncwarp();
-                    const int ct = cok ? cb : 0;
-                    const float4* ps = reinterpret_cast<const float4*>(t_s + ct);
-                    const float4* pm = reinterpret_cast<const float4*>(t_mu + ct);
-                    const float4* pb = reinterpret_cast<const float4*>(t_be + ct);
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const float4 a = ps[h], b = pm[h], c = pb[h];
-                        s8[4 * h] = a.x; s8[4 * h + 1] = a.y; s8[4 * h + 2] = a.z; s8[4 * h + 3] = a.w;
-                        mu8[4 * h] = b.x; mu8[4 * h + 1] = b.y; mu8[4 * h + 2] = b.z; mu8[4 * h + 3] = b.w;
-                        be8[4 * h] = c.x; be8[4 * h + 1] = c.y; be8[4 * h + 2] = c.z; be8[4 * h + 3] = c.w;
-                    }
                 }
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
                     const int k = jj * 4 + it;
                     cp_async_wait_group<4 * BD_NCH - 1>();      // the oldest slot = this one has landed (a thread reads back its own copies)
                     if (live) {
-                        const uint4 dr = lds128(stg_addr(stg, 8 * it + t_row, t_unit));
-                        const uint4 xr = lds128(zone + (uint32_t)(k * 1024 + lane * 16));
-                        float d[8], xv[8], o[8], dm[8];
-                        unpack8(dr, d);
+                        uint4 dr = lds128(stg_addr(stg, 8 * it + t_row, t_unit));
+                        const uint4 xr = lds128(zone + (uint32_t)(k * 1024));
+                        float xv[8], o[8], d[8];
                         unpack8(xr, xv);
-                        if (p.accumulate) {
-                            const uint4 cr = lds128(zone + (uint32_t)(k * 1024 + 512 + lane * 16));
+                        if (accum) {
+                            const uint4 cr = lds128(zone + (uint32_t)(k * 1024 + 512));
                             unpack8(cr, o);
                         } else {
 #pragma unroll
                             for (int e = 0; e < 8; ++e) o[e] = 0.f;
                         }
+                        // ReLU mask: bn(x) rounded to bf16 > 0 -- exactly the stored activation's sign -- ANDed into the packed delta
+                        uint32_t* dw = reinterpret_cast<uint32_t*>(&dr);
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float xm = xv[e] - mu8[e];
-                            const float dd = fmaf(xm, s8[e], be8[e]) > 0.f ? d[e] : 0.f;
-                            acc[jj][e] = fmaf(dd, xm, acc[jj][e]);
-                            acc[jj][8 + e] += dd;
-                            o[e] = fmaf(dd, s8[e], o[e]);
-                            dm[e] = dd;
+                        for (int h = 0; h < 4; ++h) {
+                            const __nv_bfloat162 pre = __floats2bfloat162_rn(bn_apply(xv[2 * h], s8[2 * h], t8[2 * h]),
+                                                                             bn_apply(xv[2 * h + 1], s8[2 * h + 1], t8[2 * h + 1]));
+                            dw[h] &= __hgt2_mask(pre, zero2);
                         }
-                        const long long gr = (long long)mt * TILE_M + q * 32 + 8 * it + t_row;
-                        if (cok && gr < p.rows) {
-                            *reinterpret_cast<uint4*>(p.dx + gr * p.pitch + cb) = pack8(o);
-                            if (p.d_out != nullptr) *reinterpret_cast<uint4*>(p.d_out + gr * p.d_pitch + cb) = pack8(dm);
+                        unpack8(dr, d);
+                        if (grads) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) { acc[jj][e] = fmaf(d[e], xv[e], acc[jj][e]); acc[jj][8 + e] += d[e]; }
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = fmaf(d[e], s8[e], o[e]);
+                        if (cok && 8 * it < gc.rows_left) {
+                            const long long off = gc.off + jj * 64 + it * pitch8;
+                            *reinterpret_cast<uint4*>(p.dx + off) = pack8(o);
+                            if (p.d_out != nullptr)
+                                *reinterpret_cast<uint4*>(p.d_out + ((long long)mt * TILE_M + q * 32 + 8 * it + t_row) * p.d_pitch + gc.c0 + jj * 64) = dr;
                         }
                     }
-                    issue(tile + 1, k);
+                    issue(gn, live_n, k);
                 }
                 __syncwarp();                    // the transposition buffer is rewritten by the next chunk
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
+            if (grads && live_n && ny_n != ny) flush(ny);
+            mt = mt_n; ny = ny_n; gc = gn;
         }
         cp_async_wait_all();
-        if (grads) flush(ny_acc);
+        if (grads && tile_end > tile_begin) flush(ny - (mt == 0 ? 1 : 0));
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// bn_conv_down_kernel   out[r, :] = relu(bn(x[r, :C])) . Wd^T      (norm1 -> relu1 -> conv1 forward, crowd/models.py:339-341)
+//   The A operand is the RAW concat buffer: every K chunk (128 rows x 64 channels) is TMA-loaded into the swizzled ring
+//   stage, four transform warps apply the BatchNorm affine + ReLU to it IN PLACE in shared memory (generic-proxy writes,
+//   fence.proxy.async, then a second mbarrier releases the stage to the MMA thread), so the normalised activation n1 never
+//   has to exist in HBM: 1 C-wide stream per pixel instead of 3 (affine: read cat, write n1 | GEMM: read n1).  When a later
+//   consumer still wants n1 (the weight-gradient GEMM and the tangent pass of the rows they cover), the transform threads
+//   also store their transformed 16-byte units to n1_out (2 C-wide streams).
+//   Optional second BatchNorm + ReLU in the epilogue (norm2 -> relu2 on the 128 bottleneck channels): out2 = relu(bn2(out)).
+//   warp 0 TMA, warp 1 MMA + TMEM, warps 2..9 epilogue, warps 10..13 transform.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int BF_THREADS = 448;
+constexpr int BF_BN = 128;
+
+struct BnFpropParams {
+    long long rows;
+    int C;                        // BatchNorm channels = real K
+    int Kpad;                     // K rounded up to 64 (the weight matrix's row length; rows of Wd beyond C are zero)
+    int pitch;                    // elements between rows of x
+    int Cout;                     // output channels that exist (a multiple of 8)
+    int out_pitch;
+    const float *gamma, *beta, *mean, *var;
+    float eps;
+    bf16* out;
+    bf16* n1_out;                 // nullptr, or: the transformed operand, rows of n1_pitch elements (columns < Kpad written)
+    int n1_pitch;
+    const float *gamma2, *beta2, *mean2, *var2;      // nullptr, or the BatchNorm that follows the convolution ...
+    bf16* out2;                   // ... and where relu(bn2(out)) goes (same pitch as out)
+    int m_tiles, n_tiles, total_tiles, stages;
+};
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int MT>
+__global__ void __launch_bounds__(BF_THREADS, 1) bn_conv_down_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                    const __grid_constant__ CUtensorMap tmB,
+                                                                    const BnFpropParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[8];
+    __shared__ __align__(8) uint64_t ready_bar[8];
+    __shared__ __align__(8) uint64_t empty_bar[8];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_slot;
+
+    constexpr int BN = BF_BN;
+    constexpr int STAGE_BYTES = MT * A_STAGE_BYTES + BN * KCH * 2;
+    constexpr int ACC_COLS = MT * BN;
+    constexpr int TMEM_COLS = 2 * ACC_COLS;
+    const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* const tiles_g = smem_raw + (tiles - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stages = p.stages;
+    const int nch = p.Kpad / KCH;
+    float* const t_s = reinterpret_cast<float*>(tiles_g + (size_t)stages * STAGE_BYTES + 8 * EPI_STG_BYTES);
+    float* const t_t = t_s + p.Kpad;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&ready_bar[s]), 4); mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tmem_full_bar[b]), 1); mbar_init(smem_u32(&tmem_empty_bar[b]), 8); }
+        fence_barrier_init();
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS);
+    // per-channel tables of the fused BatchNorm (channels >= C: scale = shift = 0, so the zero-filled K tail stays zero)
+    for (int c = threadIdx.x; c < p.Kpad; c += BF_THREADS) {
+        float s = 0.f, t = 0.f;
+        if (c < p.C) { s = bn_scale_f(__ldg(p.gamma + c), __ldg(p.var + c), p.eps); t = bn_shift(__ldg(p.beta + c), __ldg(p.mean + c), s); }
+        t_s[c] = s; t_t[c] = t;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (elect_one()) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int ny = tile % p.n_tiles, mt = tile / p.n_tiles;
+                for (int ch = 0; ch < nch; ++ch) {
+                    mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+                    const uint32_t fb = smem_u32(&full_bar[s]);
+                    mbar_expect_tx(fb, STAGE_BYTES);
+                    const uint32_t dst = tiles + s * STAGE_BYTES;
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) tma_load_2d(dst + i * A_STAGE_BYTES, &tmA, fb, ch * KCH, (mt * MT + i) * TILE_M);
+                    tma_load_2d(dst + MT * A_STAGE_BYTES, &tmB, fb, ch * KCH, ny * BN);
+                    if (++s == stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc(TILE_M, BN, 0, 0);
+            const uint64_t desc0 = make_desc(0, 16, 1024);
+            int s = 0, tl = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+                const int buf = tl & 1;
+                const uint32_t bph = (tl >> 1) & 1;
+                mbar_wait(smem_u32(&tmem_empty_bar[buf]), bph ^ 1);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + buf * ACC_COLS;
+                for (int k_it = 0; k_it < nch; ++k_it) {
+                    mbar_wait(smem_u32(&ready_bar[s]), ph);          // transformed (implies landed)
+                    tc_fence_after();
+                    const uint32_t a_s = tiles + s * STAGE_BYTES;
+                    const uint64_t ad0 = desc0 + (uint64_t)(a_s >> 4);
+                    const uint64_t bd0 = desc0 + (uint64_t)((a_s + MT * A_STAGE_BYTES) >> 4);
+#pragma unroll
+                    for (int i = 0; i < MT; ++i)
+#pragma unroll
+                        for (int k = 0; k < KCH / 16; ++k)
+                            umma_f16(acc + i * BN, ad0 + (uint64_t)(i * (A_STAGE_BYTES >> 4) + k * 2), bd0 + (uint64_t)(k * 2), idesc,
+                                     (k_it > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(smem_u32(&empty_bar[s]));
+                    if (++s == stages) { s = 0; ph ^= 1; }
+                }
+                umma_commit(smem_u32(&tmem_full_bar[buf]));
+            }
+        }
+    } else if (warp >= 10) {
+        // ================= transform (4 warps): BatchNorm affine + ReLU on the landed A tile, in place =================
+        // thread -> 16-byte unit u (8 channels) of rows r0 + 16*i: the unit's swizzled position (u ^ (row & 7)) is the same
+        // for all of its rows, the eight lanes of a row cover its 128 bytes (bank-conflict free)
+        const int tt = threadIdx.x - 320;
+        const int u = tt & 7, r0 = tt >> 3;
+        const uint32_t toff = (uint32_t)(r0 * 128 + ((u ^ (r0 & 7)) << 4));
+        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int ny = tile % p.n_tiles, mt = tile / p.n_tiles;
+            const bool keep = p.n1_out != nullptr && ny == 0;
+            for (int ch = 0; ch < nch; ++ch) {
+                const int cb = ch * KCH + u * 8;
+                float s8[8], t8[8];
+                {
+                    const float4* ps = reinterpret_cast<const float4*>(t_s + cb);
+                    const float4* pt = reinterpret_cast<const float4*>(t_t + cb);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float4 a = ps[h], b = pt[h];
+                        s8[4 * h] = a.x; s8[4 * h + 1] = a.y; s8[4 * h + 2] = a.z; s8[4 * h + 3] = a.w;
+                        t8[4 * h] = b.x; t8[4 * h + 1] = b.y; t8[4 * h + 2] = b.z; t8[4 * h + 3] = b.w;
+                    }
+                }
+                mbar_wait(smem_u32(&full_bar[s]), ph);
+                const uint32_t base = tiles + s * STAGE_BYTES + toff;
+#pragma unroll
+                for (int i = 0; i < MT; ++i) {
+                    const long long gr0 = (long long)(mt * MT + i) * TILE_M + r0;
+                    bf16* const n1p = keep ? p.n1_out + gr0 * p.n1_pitch + cb : nullptr;
+#pragma unroll
+                    for (int hb = 0; hb < 2; ++hb) {
+                        uint4 raw[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) raw[k] = lds128(base + (uint32_t)(i * A_STAGE_BYTES + (hb * 4 + k) * 2048));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            float xv[8];
+                            unpack8(raw[k], xv);
+                            uint4 w;
+                            uint32_t* ww = reinterpret_cast<uint32_t*>(&w);
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                const __nv_bfloat162 y = __hmax2(__floats2bfloat162_rn(bn_apply(xv[2 * h], s8[2 * h], t8[2 * h]),
+                                                                                       bn_apply(xv[2 * h + 1], s8[2 * h + 1], t8[2 * h + 1])), zero2);
+                                ww[h] = *reinterpret_cast<const uint32_t*>(&y);
+                            }
+                            sts128(base + (uint32_t)(i * A_STAGE_BYTES + (hb * 4 + k) * 2048), w);
+                            if (keep && gr0 + 16 * (hb * 4 + k) < p.rows && cb < p.n1_pitch)
+                                *reinterpret_cast<uint4*>(n1p + (long long)(16 * (hb * 4 + k)) * p.n1_pitch) = w;
+                        }
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&ready_bar[s]));
+                if (++s == stages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // ================= epilogue (8 warps) =================
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        const int t_unit = lane & 3, t_row = lane >> 2;
+        const uint32_t stg = tiles + (uint32_t)stages * STAGE_BYTES + (uint32_t)ew * EPI_STG_BYTES;
+        const bool bn2 = p.out2 != nullptr;
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+            const int ny = tile % p.n_tiles, mt = tile / p.n_tiles;
+            const int buf = tl & 1;
+            const uint32_t bph = (tl >> 1) & 1;
+            mbar_wait(smem_u32(&tmem_full_bar[buf]), bph);
+            tc_fence_after();
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+#pragma unroll
+                for (int jj = 0; jj < BN / 64; ++jj) {
+                    const int j = half + 2 * jj;
+                    const int cbase = ny * BN + j * 32;
+                    if (cbase >= p.Cout) continue;              // warp-uniform
+                    const int cb = cbase + t_unit * 8;
+                    const bool cok = cb < p.Cout;
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + i * BN + j * 32, v);
+                    float s8[8], t8[8];
+                    if (bn2) {
+                        const int ct = cok ? cb : 0;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            s8[e] = bn_scale_f(__ldg(p.gamma2 + ct + e), __ldg(p.var2 + ct + e), p.eps);
+                            t8[e] = bn_shift(__ldg(p.beta2 + ct + e), __ldg(p.mean2 + ct + e), s8[e]);
+                        }
+                    }
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 w;
+                        __nv_bfloat162 b0 = __floats2bfloat162_rn(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+                        __nv_bfloat162 b1 = __floats2bfloat162_rn(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+                        __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+                        __nv_bfloat162 b3 = __floats2bfloat162_rn(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+                        w.x = *reinterpret_cast<uint32_t*>(&b0); w.y = *reinterpret_cast<uint32_t*>(&b1);
+                        w.z = *reinterpret_cast<uint32_t*>(&b2); w.w = *reinterpret_cast<uint32_t*>(&b3);
+                        sts128(stg_addr(stg, lane, g), w);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const uint4 x = lds128(stg_addr(stg, 8 * it + t_row, t_unit));
+                        const long long gr = (long long)(mt * MT + i) * TILE_M + q * 32 + 8 * it + t_row;
+                        if (cok && gr < p.rows) {
+                            *reinterpret_cast<uint4*>(p.out + gr * p.out_pitch + cb) = x;
+                            if (bn2) {
+                                float xv[8];
+                                unpack8(x, xv);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) xv[e] = fmaxf(bn_apply(xv[e], s8[e], t8[e]), 0.f);
+                                *reinterpret_cast<uint4*>(p.out2 + gr * p.out_pitch + cb) = pack8(xv);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// [rows x cols] bf16 matrix whose rows are `pitch` elements apart (a channel window of a wider buffer) as a 2-D map
+int encode_mat_pitch(CUtensorMap* tm, const void* base, long long rows, long long cols, long long pitch, int brows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { srgan_set_error("cuTensorMapEncodeTiled is not available from the driver"); return SRGAN_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)brows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        srgan_set_error("cuTensorMapEncodeTiled(matrix %lldx%lld pitch %lld box %d) failed: %d", rows, cols, pitch, brows, (int)r);
+        return SRGAN_ERR_CUDA;
+    }
+    return SRGAN_OK;
+}
+
+template <int MT>
+int launch_bn_conv_down(const CUtensorMap& tmA, const CUtensorMap& tmB, BnFpropParams& p, cudaStream_t st) {
+    constexpr int stage_bytes = MT * A_STAGE_BYTES + BF_BN * KCH * 2;
+    const int fixed = 8 * EPI_STG_BYTES + 2 * p.Kpad * 4 + 1024;
+    int stages = (220 * 1024 - fixed) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) return 0;
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + fixed;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(bn_conv_down_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        if (e != cudaSuccess) { srgan_set_error("cudaFuncSetAttribute(bn_conv_down_kernel): %s", cudaGetErrorString(e)); return SRGAN_ERR_CUDA; }
+        attr_set = true;
+    }
+    const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+    bn_conv_down_kernel<MT><<<grid, BF_THREADS, smem, st>>>(tmA, tmB, p);
+    SRGAN_CHECK_LAUNCH("bn_conv_down_kernel");
+    return 1;
 }
 
 }  // namespace
@@ -348,7 +675,7 @@ int bn_dgrad(const void* dy, const void* Wu, void* dx, const void* x, long long 
     const long long n_tiles = (C + BD_BN - 1) / BD_BN;
     if (m_tiles * n_tiles > 0x7fffffffLL) return 0;
     p.m_tiles = (int)m_tiles; p.total_tiles = (int)(m_tiles * n_tiles);
-    const int fixed = 8 * EPI_STG_BYTES + 8 * BD_ZONE_WARP + 3 * p.Cpad * 4 + 1024;
+    const int fixed = 8 * EPI_STG_BYTES + 8 * BD_ZONE_WARP + 2 * p.Cpad * 4 + 1024;
     int stages = (226 * 1024 - fixed) / BD_STAGE_BYTES;
     if (stages > 8) stages = 8;
     if (stages < 2) return 0;
@@ -369,4 +696,37 @@ int bn_dgrad(const void* dy, const void* Wu, void* dx, const void* x, long long 
     bn_dgrad_kernel<<<grid, BD_THREADS, smem, st>>>(tmA, tmB, p);
     SRGAN_CHECK_LAUNCH("bn_dgrad_kernel");
     return 1;
+}
+
+// returns 1 = launched, 0 = shape not eligible, <0 = error
+int bn_conv_down(const void* x, const void* Wd, void* out, long long rows, int Kpad, int Cout, int C, int pitch, const float* gamma,
+                 const float* beta, const float* mean, const float* var, float eps, void* n1_out, int n1_pitch,
+                 const float* gamma2, const float* beta2, const float* mean2, const float* var2, void* out2, cudaStream_t st) {
+    if (Kpad % KCH != 0 || C > Kpad || C <= 0 || (C & 7) || (pitch & 7) || pitch < C || (Cout & 7) || Cout <= 0 || rows <= 0) return 0;
+    if (((uintptr_t)x | (uintptr_t)Wd | (uintptr_t)out | (uintptr_t)n1_out | (uintptr_t)out2) & 15) return 0;
+    if (n1_out != nullptr && ((n1_pitch & 7) || n1_pitch < C)) return 0;
+    if (Kpad > 4096) return 0;
+    BnFpropParams p;
+    p.rows = rows; p.C = C; p.Kpad = Kpad; p.pitch = pitch; p.Cout = Cout; p.out_pitch = Cout;
+    p.gamma = gamma; p.beta = beta; p.mean = mean; p.var = var; p.eps = eps;
+    p.out = (bf16*)out; p.n1_out = (bf16*)n1_out; p.n1_pitch = n1_pitch;
+    p.gamma2 = gamma2; p.beta2 = beta2; p.mean2 = mean2; p.var2 = var2; p.out2 = (bf16*)out2;
+    const long long sub = (rows + TILE_M - 1) / TILE_M;
+    p.n_tiles = (Cout + BF_BN - 1) / BF_BN;
+    // 256-row CTA tiles share every weight tile between two sub-tiles, unless 128-row tiles finish in fewer rounds on 148 CTAs
+    int MT = 2;
+    {
+        const long long t1 = sub * p.n_tiles, t2 = ((sub + 1) / 2) * p.n_tiles;
+        const long long r1 = (t1 + kNumSMs - 1) / kNumSMs, r2 = (t2 + kNumSMs - 1) / kNumSMs;
+        if (r1 < 2 * r2) MT = 1;
+    }
+    const long long m_tiles = (sub + MT - 1) / MT;
+    if (m_tiles * p.n_tiles > 0x7fffffffLL) return 0;
+    p.m_tiles = (int)m_tiles; p.total_tiles = (int)(m_tiles * p.n_tiles);
+    CUtensorMap tmA, tmB;
+    int rc = encode_mat_pitch(&tmA, x, rows, C, pitch, TILE_M);
+    if (rc) return rc;
+    rc = encode_mat(&tmB, Wd, Cout, Kpad, BF_BN);
+    if (rc) return rc;
+    return MT == 2 ? launch_bn_conv_down<2>(tmA, tmB, p, st) : launch_bn_conv_down<1>(tmA, tmB, p, st);
 }

@@ -73,6 +73,12 @@ __device__ __forceinline__ float act_bwd(float h, int act, float slope) {
     return 1.f;
 }
 
+// ---- eval-mode BatchNorm forward, ONE formula for every kernel that evaluates it (the streaming affine kernels, the
+// transform-on-load of bn_conv_down / bn_conv_wgrad and the ReLU mask that bn_dgrad recomputes must agree bit for bit):
+//   y = fma(x, s, t),  s = gamma / sqrt(var + eps),  t = fma(-mean, s, beta)
+__device__ __forceinline__ float bn_shift(float beta, float mean, float s) { return fmaf(-mean, s, beta); }
+__device__ __forceinline__ float bn_apply(float x, float s, float t) { return fmaf(x, s, t); }
+
 // ---- reductions
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -47,8 +47,8 @@ __global__ void __launch_bounds__(256) affine_kernel(const T* __restrict__ x, in
             float4 o;
             if (mode == 0) {
                 const float4 m = ld4f(mean + c), b = ld4f(beta + c);
-                o.x = act_fwd((xv.x - m.x) * s.x + b.x, act, slope); o.y = act_fwd((xv.y - m.y) * s.y + b.y, act, slope);
-                o.z = act_fwd((xv.z - m.z) * s.z + b.z, act, slope); o.w = act_fwd((xv.w - m.w) * s.w + b.w, act, slope);
+                o.x = act_fwd(bn_apply(xv.x, s.x, bn_shift(b.x, m.x, s.x)), act, slope); o.y = act_fwd(bn_apply(xv.y, s.y, bn_shift(b.y, m.y, s.y)), act, slope);
+                o.z = act_fwd(bn_apply(xv.z, s.z, bn_shift(b.z, m.z, s.z)), act, slope); o.w = act_fwd(bn_apply(xv.w, s.w, bn_shift(b.w, m.w, s.w)), act, slope);
             } else {
                 const float4 h = ld4(href + r * y_pitch + c);
                 o.x = xv.x * s.x * act_bwd(h.x, act, slope); o.y = xv.y * s.y * act_bwd(h.y, act, slope);
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) affine_kernel(const T* __restrict__ x, in
             const float s = bn_scale(gamma[c], var[c], eps);
             const float xv = to_f(*xp);
             float o;
-            if (mode == 0) o = act_fwd((xv - mean[c]) * s + beta[c], act, slope);
+            if (mode == 0) o = act_fwd(bn_apply(xv, s, bn_shift(beta[c], mean[c], s)), act, slope);
             else o = xv * s * act_bwd(to_f(href[r * y_pitch + c]), act, slope);
             *yp = from_f<T>(o);
         }
@@ -620,7 +620,11 @@ __global__ void __launch_bounds__(256, 2) affine2d_kernel(const T* __restrict__ 
     ldp<W>(var, c, m);
 #pragma unroll
     for (int q = 0; q < W; ++q) s[q] = bn_scale(s[q], m[q], eps);
-    if (MODE == 0) { ldp<W>(mean, c, m); ldp<W>(beta, c, b); }
+    if (MODE == 0) {
+        ldp<W>(mean, c, m); ldp<W>(beta, c, b);
+#pragma unroll
+        for (int q = 0; q < W; ++q) b[q] = bn_shift(b[q], m[q], s[q]);
+    }
     const T* xp = x + x_c0 + c;
     const T* hp = href + c;
     T* yp = y + c;
@@ -629,7 +633,7 @@ __global__ void __launch_bounds__(256, 2) affine2d_kernel(const T* __restrict__ 
         unpack(xr, xv);
         if (MODE == 0) {
 #pragma unroll
-            for (int q = 0; q < W; ++q) o[q] = act_fwd((xv[q] - m[q]) * s[q] + b[q], act, slope);
+            for (int q = 0; q < W; ++q) o[q] = act_fwd(bn_apply(xv[q], s[q], b[q]), act, slope);
         } else {
             float h[W];
             unpack(hr, h);

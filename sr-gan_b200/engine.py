@@ -482,11 +482,12 @@ class Engine:
     def _feat(net: Net, t):
         return t[net.feature_buf] if net.graph is not None else t[len(net.layers)]
 
-    def forward(self, st: NetState, acts, lo, hi):
-        """Runs the network on sample rows [lo, hi) of the buffers."""
+    def forward(self, st: NetState, acts, lo, hi, keep_pre=True):
+        """Runs the network on sample rows [lo, hi) of the buffers.  keep_pre=False: no weight gradient / tangent pass will
+        read these rows, so operands that fused kernels produce on the fly (Op.fuse >= 2) are not stored."""
         net = st.net
         if net.graph is not None:
-            return self.graph_forward(st, acts, lo, hi)
+            return self.graph_forward(st, acts, lo, hi, keep_pre=keep_pre)
         n = hi - lo
         for i, l in enumerate(net.layers, 1):
             self._fwd_layer(st, l, self.rows(acts[i - 1], l.in_elems, lo, hi), self.rows(acts[i], l.out_elems, lo, hi), n,
@@ -570,7 +571,7 @@ class Engine:
     # ------------------------------------------------------------------ graph nets (crowd KnnDenseNetCat)
     BN_EPS = 1e-5          # nn.BatchNorm2d default, crowd/models.py:339,343,367,1077,1092
 
-    def graph_forward(self, st: NetState, acts, lo, hi, tangent=False, mlo=None):
+    def graph_forward(self, st: NetState, acts, lo, hi, tangent=False, mlo=None, keep_pre=True):
         """Forward (tangent=False) or tangent pass (tangent=True: linear parts only, activation derivatives taken from the
         stored activations of rows [mlo, mlo+n)) of a graph net over sample rows [lo,hi)."""
         net, ops, R, P = st.net, self.ops, self._brows, st.params
@@ -583,7 +584,7 @@ class Engine:
             run = list(run)
             if not streams or branch == 0:
                 for op in run:
-                    self._graph_forward_op(st, acts, op, lo, hi, n, tangent, mlo)
+                    self._graph_forward_op(st, acts, op, lo, hi, n, tangent, mlo, keep_pre)
                     if streams and op.dst in taps and op.dst not in tap_ev:      # first writer of a tapped buffer (the pool)
                         ev = torch.cuda.Event()
                         ev.record(main)
@@ -599,7 +600,7 @@ class Engine:
                 prev = ops.use_stream(s)
                 try:
                     for op in run:
-                        self._graph_forward_op(st, acts, op, lo, hi, n, tangent, mlo)
+                        self._graph_forward_op(st, acts, op, lo, hi, n, tangent, mlo, keep_pre)
                 finally:
                     ops.restore_stream(prev)
                 ev = torch.cuda.Event()
@@ -618,7 +619,7 @@ class Engine:
                 d[op.branch] = torch.cuda.Stream(self.device)
         return d
 
-    def _graph_forward_op(self, st: NetState, acts, op, lo, hi, n, tangent, mlo):
+    def _graph_forward_op(self, st: NetState, acts, op, lo, hi, n, tangent, mlo, keep_pre=True):
         """One op of graph_forward over sample rows [lo,hi) (n = hi - lo), on the current stream."""
         net, ops, R, P = st.net, self.ops, self._brows, st.params
         sb, db = net.bufs[op.src], net.bufs[op.dst]
@@ -631,8 +632,20 @@ class Engine:
                 y, href = y[op.c0:], None
             if tangent:
                 self._fwd_layer(st, op.layer, x, y, ng, bias=False, href=href, epi=EPI_DACT, lo=lo, views=vw)
+            elif op.pre is not None and op.pre.fuse >= 2:
+                # BatchNorm + ReLU applied to the operand tiles on their way into the GEMM: reads the concat buffer directly;
+                # the normalised operand is stored only for the rows a weight gradient / tangent pass will read
+                a, l = op.pre, op.layer
+                cbuf, nm = net.bufs[a.src], a.name
+                timed = self._probe_open('forward_bn', st, l, ng)
+                ops.bn_conv_down(R(acts[a.src], cbuf, lo, hi), st.wd_[l.name], y, ng, l.geom.Cb, l.geom.Ca, a.C, cbuf.ch,
+                                 P[nm + '.weight'], P[nm + '.bias'], P[nm + '.running_mean'], P[nm + '.running_var'], self.BN_EPS,
+                                 x if keep_pre else None, sb.ch)
+                self._probe_close(timed)
             else:
                 self._fwd_layer(st, op.layer, x, y, ng, lo=lo, views=vw)
+        elif op.kind == 'affine' and op.fuse >= 2 and not tangent:
+            pass                          # carried out by the convolution that consumes its output (above)
         elif op.kind == 'affine':
             nm = op.name
             ops.affine(x, sb.ch, op.c0, y, db.ch, n * sb.rows, op.C, P[nm + '.weight'], P[nm + '.bias'],
@@ -1066,7 +1079,7 @@ class Engine:
         self.load_input(gnet, z2, gacts[0], B)
         self.forward(G, gacts, 0, B)
         if not dggan:
-            self.forward(D, acts, 0, 2 * B)                     # rows [B,2B) still hold u
+            self.forward(D, acts, 0, 2 * B, keep_pre=False)     # rows [B,2B) still hold u
             if self.publish_features:
                 self.buf('feat_snap', (4 * B * F,))[2 * B * F:3 * B * F].copy_(fblk(0, B))      # srgan.py:386
             sums = self.buf('fsums', (3, F), self.mdt)
@@ -1080,7 +1093,7 @@ class Engine:
                          cfg.matching_loss_multiplier, sc[SC_GEN:SC_GEN + 1], gvec[1], gvec[0], False)
             ops.seed_rows(dblk(0, B), B, F, gvec[0], None, None, fblk(0, B), fact, fslope)
         else:
-            self.forward(D, acts, 0, B)
+            self.forward(D, acts, 0, B, keep_pre=False)
             sf = self.buf('score_f', (B,), self.mdt)
             dsf = self.buf('dscore_f', (B,), self.mdt)
             self._head_forward(D, fblk(0, B), B, 1, sf)
@@ -1230,7 +1243,7 @@ class Engine:
         for m in range(nm):
             g_inputs(m)
             self.load_input(net, u[m * b:(m + 1) * b], self.rows(a_in, E, b, 2 * b), b)
-            self.forward(D, acts, 0, 2 * b)
+            self.forward(D, acts, 0, 2 * b, keep_pre=False)
             ops.colsum(fblk(0, b), b, F, sums[0], 0, None)
             ops.colsum(fblk(b, 2 * b), b, F, sums[1], 0, None)
         if self.comm is not None:
@@ -1241,7 +1254,7 @@ class Engine:
         gdeltas = self.alloc_deltas('G', gnet, b)
         for m in range(nm):
             gacts = g_inputs(m)
-            self.forward(D, acts, 0, b)
+            self.forward(D, acts, 0, b, keep_pre=False)
             ops.seed_rows(dblk(0, b), b, F, gvec[0], None, None, fblk(0, b), fact, fslope)
             self.backward(D, acts, deltas, 0, b, need_input_grad=True, dinput=gdeltas[len(gl)], input_href=gacts[-1],
                           input_act=gl[-1].act, weight_grads=False)
@@ -1258,7 +1271,7 @@ class Engine:
         B = x.shape[0]
         acts = self.alloc_acts('D', net, B if st is self.DNN else 5 * B)
         self.load_input(net, x, self.rows(self._in(net, acts), net.in_elems, 0, B), B)
-        self.forward(st, acts, 0, B)
+        self.forward(st, acts, 0, B, keep_pre=False)
         feats = self._brows_feat(net, acts, 0, B)
         pred = self.buf('pred', (B,), self.mdt)
         self._head_forward(st, feats, B, 0, pred)

@@ -76,3 +76,36 @@ def test_bn_dgrad_refuses_ineligible(ops):
     f = torch.zeros(100, device='cuda')
     with pytest.raises(RuntimeError):                    # K not a multiple of 64
         ops.bn_dgrad(t, t, t, t, 10, 100, 64, 64, 64, f, f, f, f, 1e-5, None, None, None, 0, False)
+
+
+@pytest.mark.parametrize('rows,C,pitch,Cout', [(3001, 96, 256, 128), (12544 + 5, 1056, 1920, 128), (777, 384, 384, 192),
+                                               (50, 64, 64, 128), (4 * 3136, 160, 256, 128), (40000, 256, 256, 128),
+                                               (2 * 148 * 128 + 17, 1888, 1920, 128), (5000, 512, 512, 256)])
+@pytest.mark.parametrize('keep,bn2', [(True, False), (False, False), (False, True), (True, True)])
+def test_bn_conv_down(ops, rows, C, pitch, Cout, keep, bn2):
+    """norm1 -> relu1 -> conv1 forward in one launch (the operand tiles are normalised in shared memory on their way into the
+    GEMM) against affine + GEMM semantics; optional store of the normalised operand, optional second BatchNorm + ReLU."""
+    gen = torch.Generator().manual_seed(rows + C + Cout)
+    ref = TorchOps()
+    Kpad = (C + 63) // 64 * 64
+    x = rnd(gen, rows * pitch, dt=BF)
+    Wd = torch.zeros(Cout, Kpad)
+    Wd[:, :C] = rnd(gen, Cout, C) * 0.1
+    Wd = Wd.reshape(-1).to(BF)
+    gamma, beta, mean, var = bn_params(gen, C)
+    p2 = bn_params(gen, Cout) if bn2 else None
+    out_ref, out = torch.zeros(rows * Cout, dtype=BF), torch.zeros(rows * Cout, dtype=BF, device='cuda')
+    o2_ref = torch.zeros(rows * Cout, dtype=BF) if bn2 else None
+    o2 = torch.zeros(rows * Cout, dtype=BF, device='cuda') if bn2 else None
+    n1_ref = rnd(gen, rows * Kpad, dt=BF) if keep else None
+    n1 = n1_ref.clone().cuda() if keep else None
+    cu = lambda t: t.cuda()
+    ref.bn_conv_down(x, Wd, out_ref, rows, Kpad, Cout, C, pitch, gamma, beta, mean, var, 1e-5, n1_ref, Kpad, p2, o2_ref)
+    ops.bn_conv_down(cu(x), cu(Wd), out, rows, Kpad, Cout, C, pitch, cu(gamma), cu(beta), cu(mean), cu(var), 1e-5, n1, Kpad,
+                     tuple(cu(t) for t in p2) if bn2 else None, o2)
+    torch.cuda.synchronize()
+    close(out, out_ref, 1e-2, 'bn_conv_down out')
+    if keep:
+        close(n1, n1_ref, 8e-3, 'bn_conv_down n1_out')
+    if bn2:
+        close(o2, o2_ref, 2e-2, 'bn_conv_down out2', outliers=1e-5)

@@ -488,3 +488,23 @@ class TorchOps:
                 dbeta += d.sum(0).to(dbeta.dtype)
         if d_out is not None:
             d_out.view(rows, d_pitch)[:, :C] = d.to(d_out.dtype)
+
+    def bn_conv_down(self, x, Wd, out, rows, Kpad, Cout, C, pitch, gamma, beta, mean, var, eps, n1_out=None, n1_pitch=0, bn2=None,
+                     out2=None):
+        """n1 = relu(bn(x[:, :C])) rounded to the activation dtype; out = n1 @ Wd[:, :C]^T; n1_out (optional) = n1, zeros in
+        the padding columns [C, min(Kpad, n1_pitch)); out2 (optional) = relu(bn2(out))."""
+        self.launches += 1
+        cd = self._cd(x)
+        s = gamma.detach().to(cd) / torch.sqrt(var.detach().to(cd) + eps)
+        t = beta.detach().to(cd) - mean.detach().to(cd) * s
+        n1 = torch.relu(x.view(rows, pitch)[:, :C].to(cd) * s + t).to(x.dtype)
+        o = (n1.to(cd) @ Wd.view(Cout, Kpad)[:, :C].to(cd).t()).to(out.dtype)
+        out.view(rows, Cout)[:] = o
+        if n1_out is not None:
+            v = n1_out.view(rows, n1_pitch)
+            v[:, :C] = n1
+            v[:, C:min(Kpad, n1_pitch)] = 0
+        if out2 is not None:
+            g2, b2, m2, v2 = (q.detach().to(cd) for q in bn2)
+            s2 = g2 / torch.sqrt(v2 + eps)
+            out2.view(rows, Cout)[:] = torch.relu(o.to(cd) * s2 + (b2 - m2 * s2)).to(out2.dtype)

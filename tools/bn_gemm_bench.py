@@ -65,6 +65,9 @@ for rows, C, pitch in ((256 * 196, 1024, 1792), (256 * 784, 320, 512), (256 * 49
         def fused_fwd(k):
             ops.bn_conv_down(cat[k], Wd, b[k], rows, Cp, 128, C, pitch, gamma, beta, mean, var, 1e-5)
 
+        def fused_fwd_keep(k):
+            ops.bn_conv_down(cat[k], Wd, b[k], rows, Cp, 128, C, pitch, gamma, beta, mean, var, 1e-5, n1[k], Cp)
+
         def unfused_wg(k):
             ops.conv_wgrad(db[k], n1[k], dW, rows, g)
 
@@ -72,8 +75,10 @@ for rows, C, pitch in ((256 * 196, 1024, 1792), (256 * 784, 320, 512), (256 * 49
             ops.bn_conv_wgrad(db[k], cat[k], dW, rows, 128, Cp, C, pitch, gamma, beta, mean, var, 1e-5)
         cases += [('unfused affine + conv1 forward ', rows * (128 + 3 * C) * e, unfused_fwd),
                   ('bn_conv_down                   ', rows * (128 + C) * e, fused_fwd),
-                  ('conv1 weight gradient (n1)     ', rows * (128 + C) * e, unfused_wg),
-                  ('bn_conv_wgrad (from cat)       ', rows * (128 + C) * e, fused_wg)]
+                  ('bn_conv_down (+ n1 stored)     ', rows * (128 + 2 * C) * e, fused_fwd_keep)]
+        if hasattr(ops, 'bn_conv_wgrad'):
+            cases += [('conv1 weight gradient (n1)     ', rows * (128 + C) * e, unfused_wg),
+                      ('bn_conv_wgrad (from cat)       ', rows * (128 + C) * e, fused_wg)]
     for name, nbytes, fn in cases:
         t = timeit(fn)
         print(f'rows={rows:7d} C={C:5d}  {name}: {t * 1e3:7.1f} us  {nbytes / 1e6:7.1f} MB algorithmic  {nbytes / t / 1e6:6.0f} GB/s', flush=True)
