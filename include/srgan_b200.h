@@ -220,15 +220,23 @@ int srgan_bn_dgrad(const void* dy, const void* Wu, void* dx, const void* x, long
  * n1 = relu(bn(x)) need not exist in memory:
  *   n1[r,c]  = max(0, fma(x[r,c], s[c], t[c])) rounded to bf16,  s = gamma/sqrt(var+eps), t = beta - mean*s   (c < C)
  *   out[r,o] = sum_c n1[r,c] * Wd[o*Kpad + c]                      (o < Cout; Wd [Cout][Kpad], columns >= C zero)
- *   n1_out[r*n1_pitch + c] = n1[r,c] for c < min(Kpad, n1_pitch), zeros for c >= C   (n1_out NULL: not stored; the weight
- *                            gradient and the gradient-penalty tangent pass of the same rows are its consumers)
- *   out2[r,o] = max(0, fma(out[r,o], s2[o], t2[o]))                (gamma2 .. out2 NULL: skipped) -- the BatchNorm + ReLU that
- *                            FOLLOWS the convolution (norm2 -> relu2, crowd/models.py:343-344), applied to the rounded out.
+ *   n1_out[r*n1_pitch + c] = n1[r,c] for c < min(Kpad, n1_pitch), zeros for c >= C, rows r >= n1_first_row only
+ *                            (n1_out NULL: not stored; the gradient-penalty tangent pass reads it for the interpolate rows)
+ *   out2[r,o] = max(0, fma(out[r,o], s2[o], t2[o])) for o < C2, 0 for C2 <= o < Cout   (gamma2 .. out2 NULL: skipped) -- the
+ *                            BatchNorm + ReLU that FOLLOWS the convolution (norm2 -> relu2, crowd/models.py:343-344; C2 of its
+ *                            channels exist), applied to the rounded out.
  * Replaces srgan_affine (norm1) + srgan_conv_down (+ srgan_affine (norm2)). */
 int srgan_bn_conv_down(const void* x, const void* Wd, void* out, long long rows, int Kpad, int Cout, int C, int pitch,
                        const float* gamma, const float* beta, const float* mean, const float* var, float eps, void* n1_out,
-                       int n1_pitch, const float* gamma2, const float* beta2, const float* mean2, const float* var2, void* out2,
-                       int dtype, void* stream);
+                       int n1_pitch, long long n1_first_row, const float* gamma2, const float* beta2, const float* mean2,
+                       const float* var2, void* out2, int C2, int dtype, void* stream);
+/* srgan_bn_conv_wgrad: weight gradient of the pair from the RAW concat buffer (same transform-on-load):
+ *   dW[a*Kpad + c] += sum_r dy[r*Ca + a] * n1[r,c]            (a < Ca, c < Kpad; fp32 reductions, dW is accumulated into)
+ * Replaces srgan_conv_wgrad on the stored n1.  The rows of a gradient-penalty tangent block (whose operand is not
+ * relu(bn(x))) still go through srgan_conv_wgrad. */
+int srgan_bn_conv_wgrad(const void* dy, const void* x, float* dW, long long rows, int Ca, int Kpad, int C, int pitch,
+                        const float* gamma, const float* beta, const float* mean, const float* var, float eps, int dtype,
+                        void* stream);
 
 /* dst[:, d0:d0+C] (+)= src[:, s0:s0+C] : torch.cat writes / their backward reads, MapModule taps */
 int srgan_copy2d(const void* src, int src_pitch, int src_c0, void* dst, int dst_pitch, int dst_c0, long long rows, int C,

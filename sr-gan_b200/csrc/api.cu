@@ -53,8 +53,10 @@ int bn_dgrad(const void* dy, const void* Wu, void* dx, const void* x, long long 
              void* d_out, int d_pitch, int accumulate, cudaStream_t st);
 
 int bn_conv_down(const void* x, const void* Wd, void* out, long long rows, int Kpad, int Cout, int C, int pitch, const float* gamma,
-                 const float* beta, const float* mean, const float* var, float eps, void* n1_out, int n1_pitch,
-                 const float* gamma2, const float* beta2, const float* mean2, const float* var2, void* out2, cudaStream_t st);
+                 const float* beta, const float* mean, const float* var, float eps, void* n1_out, int n1_pitch, long long n1_first_row,
+                 const float* gamma2, const float* beta2, const float* mean2, const float* var2, void* out2, int C2, cudaStream_t st);
+int bn_conv_wgrad(const void* dy, const void* x, float* dW, long long rows, int Ca, int Kpad, int C, int pitch, const float* gamma,
+                  const float* beta, const float* mean, const float* var, float eps, cudaStream_t st);
 
 // skinny.cu : few outputs over a long full-extent reduction axis (MapModule.linear1, the count feature layer)
 bool skinny_eligible(const srgan_geom* g);
@@ -172,20 +174,39 @@ int srgan_bn_dgrad(const void* dy, const void* Wu, void* dx, const void* x, long
 
 int srgan_bn_conv_down(const void* x, const void* Wd, void* out, long long rows, int Kpad, int Cout, int C, int pitch,
                        const float* gamma, const float* beta, const float* mean, const float* var, float eps, void* n1_out,
-                       int n1_pitch, const float* gamma2, const float* beta2, const float* mean2, const float* var2, void* out2,
-                       int dtype, void* stream) {
+                       int n1_pitch, long long n1_first_row, const float* gamma2, const float* beta2, const float* mean2,
+                       const float* var2, void* out2, int C2, int dtype, void* stream) {
     SRGAN_REQUIRE(x && Wd && out && gamma && beta && mean && var, "srgan_bn_conv_down: null pointer");
     SRGAN_REQUIRE(dtype == SRGAN_BF16, "srgan_bn_conv_down: the fused dense-layer kernels are bf16 / tcgen05 only");
     SRGAN_REQUIRE(rows >= 0 && Kpad >= C && C > 0 && Cout > 0 && pitch >= C, "srgan_bn_conv_down: bad sizes");
     SRGAN_REQUIRE((out2 == nullptr) == (gamma2 == nullptr) && (gamma2 == nullptr) == (beta2 == nullptr) &&
                       (gamma2 == nullptr) == (mean2 == nullptr) && (gamma2 == nullptr) == (var2 == nullptr),
                   "srgan_bn_conv_down: the second BatchNorm needs gamma2, beta2, mean2, var2 and out2 together");
+    SRGAN_REQUIRE(out2 == nullptr || (C2 > 0 && C2 <= Cout), "srgan_bn_conv_down: C2 must be in (0, Cout]");
     if (rows == 0) return SRGAN_OK;
-    int took = bn_conv_down(x, Wd, out, rows, Kpad, Cout, C, pitch, gamma, beta, mean, var, eps, n1_out, n1_pitch, gamma2, beta2,
-                            mean2, var2, out2, (cudaStream_t)stream);
+    int took = bn_conv_down(x, Wd, out, rows, Kpad, Cout, C, pitch, gamma, beta, mean, var, eps, n1_out, n1_pitch, n1_first_row,
+                            gamma2, beta2, mean2, var2, out2, C2, (cudaStream_t)stream);
     if (took < 0) return took;
     if (took == 0) {
         srgan_set_error("srgan_bn_conv_down: shape not eligible (Kpad %% 64, C %% 8, Cout %% 8, pitch %% 8, 16-byte aligned pointers)");
+        return SRGAN_ERR_UNSUPPORTED;
+    }
+    t_last_tensor = 1;
+    g_tensor_calls.fetch_add(1, std::memory_order_relaxed);
+    return SRGAN_OK;
+}
+
+int srgan_bn_conv_wgrad(const void* dy, const void* x, float* dW, long long rows, int Ca, int Kpad, int C, int pitch,
+                        const float* gamma, const float* beta, const float* mean, const float* var, float eps, int dtype,
+                        void* stream) {
+    SRGAN_REQUIRE(dy && x && dW && gamma && beta && mean && var, "srgan_bn_conv_wgrad: null pointer");
+    SRGAN_REQUIRE(dtype == SRGAN_BF16, "srgan_bn_conv_wgrad: the fused dense-layer kernels are bf16 / tcgen05 only");
+    SRGAN_REQUIRE(rows >= 0 && Kpad >= C && C > 0 && Ca > 0 && pitch >= C, "srgan_bn_conv_wgrad: bad sizes");
+    if (rows == 0) return SRGAN_OK;
+    int took = bn_conv_wgrad(dy, x, dW, rows, Ca, Kpad, C, pitch, gamma, beta, mean, var, eps, (cudaStream_t)stream);
+    if (took < 0) return took;
+    if (took == 0) {
+        srgan_set_error("srgan_bn_conv_wgrad: shape not eligible (Kpad %% 64, C %% 8, Ca %% 8, pitch %% 8, 16-byte aligned pointers)");
         return SRGAN_ERR_UNSUPPORTED;
     }
     t_last_tensor = 1;

@@ -361,9 +361,10 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
 //   consumer still wants n1 (the weight-gradient GEMM and the tangent pass of the rows they cover), the transform threads
 //   also store their transformed 16-byte units to n1_out (2 C-wide streams).
 //   Optional second BatchNorm + ReLU in the epilogue (norm2 -> relu2 on the 128 bottleneck channels): out2 = relu(bn2(out)).
-//   warp 0 TMA, warp 1 MMA + TMEM, warps 2..9 epilogue, warps 10..13 transform.
+//   warp 0 TMA, warp 1 MMA + TMEM, warps 2..9 epilogue, warps 10.. transform (BF_NG groups of 4).
 // ------------------------------------------------------------------------------------------------------------
-constexpr int BF_THREADS = 448;
+constexpr int BF_NG = 2;                         // transform groups of 4 warps; group g owns the K chunks c = g (mod BF_NG)
+constexpr int BF_THREADS = 320 + 128 * BF_NG;
 constexpr int BF_BN = 128;
 
 struct BnFpropParams {
@@ -376,11 +377,14 @@ struct BnFpropParams {
     const float *gamma, *beta, *mean, *var;
     float eps;
     bf16* out;
-    bf16* n1_out;                 // nullptr, or: the transformed operand, rows of n1_pitch elements (columns < Kpad written)
-    int n1_pitch;
+    bf16* n1_out;                 // nullptr, or: the transformed operand, rows of n1_pitch elements (columns < Kpad written),
+    int n1_pitch;                 // stored for the GEMM rows >= n1_first_row only
+    long long n1_first_row;
     const float *gamma2, *beta2, *mean2, *var2;      // nullptr, or the BatchNorm that follows the convolution ...
-    bf16* out2;                   // ... and where relu(bn2(out)) goes (same pitch as out)
+    bf16* out2;                   // ... and where relu(bn2(out)) goes (same pitch as out); channels >= C2 get zeros
+    int C2;
     int m_tiles, n_tiles, total_tiles, stages;
+    int dbg_noxf;                 // SRGAN_BF_NOXF=1 (measurement only): the transform groups pass the stages on untouched
 };
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -481,19 +485,27 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bn_conv_down_kernel(const __gri
             }
         }
     } else if (warp >= 10) {
-        // ================= transform (4 warps): BatchNorm affine + ReLU on the landed A tile, in place =================
+        // ================= transform (BF_NG x 4 warps): BatchNorm affine + ReLU on the landed A tile, in place =================
         // thread -> 16-byte unit u (8 channels) of rows r0 + 16*i: the unit's swizzled position (u ^ (row & 7)) is the same
         // for all of its rows, the eight lanes of a row cover its 128 bytes (bank-conflict free)
-        const int tt = threadIdx.x - 320;
+        // (consecutive chunks are transformed concurrently by different groups: the per-chunk chain wait -> LDS -> math -> STS ->
+        // proxy fence -> arrive is latency-bound for a single group)
+        const int tt = (threadIdx.x - 320) & 127, grp = (threadIdx.x - 320) >> 7;
         const int u = tt & 7, r0 = tt >> 3;
         const uint32_t toff = (uint32_t)(r0 * 128 + ((u ^ (r0 & 7)) << 4));
         const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
-        int s = 0;
+        int s = 0, turn = 0;
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int ny = tile % p.n_tiles, mt = tile / p.n_tiles;
-            const bool keep = p.n1_out != nullptr && ny == 0;
+            const bool keep = p.n1_out != nullptr && ny == 0 && (long long)(mt + 1) * MT * TILE_M > p.n1_first_row;
             for (int ch = 0; ch < nch; ++ch) {
+                const bool mine = turn == grp;
+                if (++turn == BF_NG) turn = 0;
+                if (!mine) {
+                    if (++s == stages) { s = 0; ph ^= 1; }
+                    continue;
+                }
                 const int cb = ch * KCH + u * 8;
                 float s8[8], t8[8];
                 {
@@ -510,6 +522,7 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bn_conv_down_kernel(const __gri
                 const uint32_t base = tiles + s * STAGE_BYTES + toff;
 #pragma unroll
                 for (int i = 0; i < MT; ++i) {
+                    if (p.dbg_noxf) break;
                     const long long gr0 = (long long)(mt * MT + i) * TILE_M + r0;
                     bf16* const n1p = keep ? p.n1_out + gr0 * p.n1_pitch + cb : nullptr;
 #pragma unroll
@@ -530,7 +543,7 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bn_conv_down_kernel(const __gri
                                 ww[h] = *reinterpret_cast<const uint32_t*>(&y);
                             }
                             sts128(base + (uint32_t)(i * A_STAGE_BYTES + (hb * 4 + k) * 2048), w);
-                            if (keep && gr0 + 16 * (hb * 4 + k) < p.rows && cb < p.n1_pitch)
+                            if (keep && gr0 + 16 * (hb * 4 + k) < p.rows && gr0 + 16 * (hb * 4 + k) >= p.n1_first_row && cb < p.n1_pitch)
                                 *reinterpret_cast<uint4*>(n1p + (long long)(16 * (hb * 4 + k)) * p.n1_pitch) = w;
                         }
                     }
@@ -572,8 +585,11 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bn_conv_down_kernel(const __gri
                         const int ct = cok ? cb : 0;
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            s8[e] = bn_scale_f(__ldg(p.gamma2 + ct + e), __ldg(p.var2 + ct + e), p.eps);
-                            t8[e] = bn_shift(__ldg(p.beta2 + ct + e), __ldg(p.mean2 + ct + e), s8[e]);
+                            s8[e] = 0.f; t8[e] = 0.f;
+                            if (ct + e < p.C2) {
+                                s8[e] = bn_scale_f(__ldg(p.gamma2 + ct + e), __ldg(p.var2 + ct + e), p.eps);
+                                t8[e] = bn_shift(__ldg(p.beta2 + ct + e), __ldg(p.mean2 + ct + e), s8[e]);
+                            }
                         }
                     }
                     tmem_ld_wait();
@@ -641,6 +657,13 @@ int launch_bn_conv_down(const CUtensorMap& tmA, const CUtensorMap& tmB, BnFpropP
     const int fixed = 8 * EPI_STG_BYTES + 2 * p.Kpad * 4 + 1024;
     int stages = (220 * 1024 - fixed) / stage_bytes;
     if (stages > 8) stages = 8;
+    static const int dbg_stages = [] { const char* e = getenv("SRGAN_BF_STAGES"); return e ? atoi(e) : 0; }();
+    static const int dbg_noxf = [] { const char* e = getenv("SRGAN_BF_NOXF"); return e ? atoi(e) : 0; }();
+    if (dbg_stages > 0 && dbg_stages < stages) stages = dbg_stages;
+    p.dbg_noxf = dbg_noxf;
+    // a multiple of the number of transform groups: every ring stage then belongs to ONE group, which sees all of that
+    // stage's mbarrier phases in order (a group that skipped a phase could pass a parity wait one phase early)
+    stages -= stages % BF_NG;
     if (stages < 2) return 0;
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + fixed;
@@ -654,6 +677,200 @@ int launch_bn_conv_down(const CUtensorMap& tmA, const CUtensorMap& tmB, BnFpropP
     bn_conv_down_kernel<MT><<<grid, BF_THREADS, smem, st>>>(tmA, tmB, p);
     SRGAN_CHECK_LAUNCH("bn_conv_down_kernel");
     return 1;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// bn_conv_wgrad_kernel   dW[a, b] += sum_r dy[r, a] * relu(bn(x[r, b]))      (weight gradient of conv1 from the RAW concat buffer)
+//   M = 128 channels a of dy (A operand MN-major: two [WG pixels x 64 channels] boxes), N = BN channels b per sub-problem
+//   (B operand MN-major), NS sub-problems side by side in TMEM (NS * BN <= 512 columns) so that one dy tile feeds all of
+//   them, K = pixels, split across one wave of CTAs; fp32 reductions into dW.  The x boxes are normalised + rectified in
+//   place in shared memory by the transform groups (same scheme as bn_conv_down_kernel; a thread's 16 units per stage all
+//   belong to the same 8 channels, so its scale / shift live in registers for the whole kernel).
+//   warp 0 TMA, warp 1 MMA + TMEM, warps 2.. transform (BW_NG groups of 4 warps); warps 2..5 also drain TMEM at the end.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int BW_NG = 2;
+constexpr int BW_THREADS = 64 + 128 * BW_NG;
+constexpr int BW_PIX = 32;                       // pixels (K) per stage
+constexpr int BW_BOX = BW_PIX * 128;             // one [32 pixels x 64 channels] box: 4 KB
+
+struct BnWgradParams {
+    long long rows;
+    int C, Kpad;                  // BatchNorm channels (real b), dW row length
+    int BN, NS;                   // channels per sub-problem (64 / 128 / 256), sub-problems per CTA
+    int chunks_per_split, total_chunks;
+    const float *gamma, *beta, *mean, *var;
+    float eps;
+    float* dW;                    // [Ca][Kpad] fp32
+    int Ca;                       // channels of dy that exist (128 per blockIdx.y)
+    int stages;
+};
+
+__global__ void __launch_bounds__(BW_THREADS, 1) bn_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmS,
+                                                                     const __grid_constant__ CUtensorMap tmL,
+                                                                     const BnWgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[8];
+    __shared__ __align__(8) uint64_t ready_bar[8];
+    __shared__ __align__(8) uint64_t empty_bar[8];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_slot;
+
+    constexpr int A_BYTES = 2 * BW_BOX;
+    const int nbox = p.NS * (p.BN / 64);                 // x boxes per stage (<= 8)
+    const int STAGE_BYTES = A_BYTES + nbox * BW_BOX;
+    const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stages = p.stages;
+    const int b0 = blockIdx.x * p.NS * p.BN;
+    const int a0 = blockIdx.y * 128;
+    const int ch_begin = blockIdx.z * p.chunks_per_split;
+    int ch_end = ch_begin + p.chunks_per_split;
+    if (ch_end > p.total_chunks) ch_end = p.total_chunks;
+    const int n_iters = ch_end - ch_begin;
+    const int used = p.NS * p.BN;
+    const uint32_t ncols = used <= 32 ? 32 : (used <= 64 ? 64 : (used <= 128 ? 128 : (used <= 256 ? 256 : 512)));
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&ready_bar[s]), 4); mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        mbar_init(smem_u32(&tmem_full_bar), 1);
+        fence_barrier_init();
+        prefetch_tmap(&tmS);
+        prefetch_tmap(&tmL);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), ncols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (n_iters > 0) {
+        if (warp == 0) {
+            if (elect_one()) {
+                int s = 0;
+                uint32_t ph = 0;
+                for (int it = 0; it < n_iters; ++it) {
+                    const int r = (ch_begin + it) * BW_PIX;
+                    mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+                    const uint32_t fb = smem_u32(&full_bar[s]);
+                    mbar_expect_tx(fb, STAGE_BYTES);
+                    const uint32_t dst = tiles + s * STAGE_BYTES;
+                    tma_load_2d(dst, &tmS, fb, a0, r);
+                    tma_load_2d(dst + BW_BOX, &tmS, fb, a0 + 64, r);
+                    for (int k = 0; k < nbox; ++k) tma_load_2d(dst + A_BYTES + k * BW_BOX, &tmL, fb, b0 + k * 64, r);
+                    if (++s == stages) { s = 0; ph ^= 1; }
+                }
+            }
+        } else if (warp == 1) {
+            if (elect_one()) {
+                const uint32_t idesc = make_idesc(128, p.BN, 1, 1);
+                const uint64_t desc0 = make_desc(0, BW_BOX, 1024);
+                const int sub_bytes = (p.BN / 64) * BW_BOX;
+                int s = 0;
+                uint32_t ph = 0;
+                for (int it = 0; it < n_iters; ++it) {
+                    mbar_wait(smem_u32(&ready_bar[s]), ph);
+                    tc_fence_after();
+                    const uint32_t a_s = tiles + s * STAGE_BYTES;
+                    const uint64_t ad0 = desc0 + (uint64_t)(a_s >> 4);
+                    for (int k = 0; k < p.NS; ++k) {
+                        const uint64_t bd0 = desc0 + (uint64_t)((a_s + A_BYTES + k * sub_bytes) >> 4);
+#pragma unroll
+                        for (int kk = 0; kk < BW_PIX / 16; ++kk)      // 16 K rows (pixels) = 2048 B further into every column group
+                            umma_f16(tmem_base + k * p.BN, ad0 + (uint64_t)(kk * 128), bd0 + (uint64_t)(kk * 128), idesc,
+                                     (it > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    umma_commit(smem_u32(&empty_bar[s]));
+                    if (++s == stages) { s = 0; ph ^= 1; }
+                }
+                umma_commit(smem_u32(&tmem_full_bar));
+            }
+        } else {
+            // ================= transform: thread -> box bx, 16-byte unit u, rows rh*16 .. rh*16+15 =================
+            {
+                const int tt = (threadIdx.x - 64) & 127, grp = (threadIdx.x - 64) >> 7;
+                const int u = tt & 7, rh = (tt >> 3) & 1, bx = tt >> 4;
+                const int cb = b0 + bx * 64 + u * 8;
+                float s8[8], t8[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    s8[e] = 0.f; t8[e] = 0.f;
+                    if (cb + e < p.C) {
+                        s8[e] = bn_scale_f(__ldg(p.gamma + cb + e), __ldg(p.var + cb + e), p.eps);
+                        t8[e] = bn_shift(__ldg(p.beta + cb + e), __ldg(p.mean + cb + e), s8[e]);
+                    }
+                }
+                const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+                const bool active = bx < nbox;
+                int s = 0, turn = 0;
+                uint32_t ph = 0;
+                for (int it = 0; it < n_iters; ++it) {
+                    const bool mine = turn == grp;
+                    if (++turn == BW_NG) turn = 0;
+                    if (mine) {
+                        mbar_wait(smem_u32(&full_bar[s]), ph);
+                        if (active) {
+                            const uint32_t base = tiles + s * STAGE_BYTES + A_BYTES + bx * BW_BOX + rh * 2048;
+#pragma unroll
+                            for (int hb = 0; hb < 4; ++hb) {
+                                uint4 raw[4];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const int r = hb * 4 + k;                  // row within the half box; swizzle by the row's low 3 bits
+                                    raw[k] = lds128(base + (uint32_t)(r * 128 + ((u ^ (r & 7)) << 4)));
+                                }
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const int r = hb * 4 + k;
+                                    float xv[8];
+                                    unpack8(raw[k], xv);
+                                    uint4 w;
+                                    uint32_t* ww = reinterpret_cast<uint32_t*>(&w);
+#pragma unroll
+                                    for (int h = 0; h < 4; ++h) {
+                                        const __nv_bfloat162 y = __hmax2(__floats2bfloat162_rn(bn_apply(xv[2 * h], s8[2 * h], t8[2 * h]),
+                                                                                               bn_apply(xv[2 * h + 1], s8[2 * h + 1], t8[2 * h + 1])), zero2);
+                                        ww[h] = *reinterpret_cast<const uint32_t*>(&y);
+                                    }
+                                    sts128(base + (uint32_t)(r * 128 + ((u ^ (r & 7)) << 4)), w);
+                                }
+                            }
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&ready_bar[s]));
+                    }
+                    if (++s == stages) { s = 0; ph ^= 1; }
+                }
+            }
+            if (warp < 6) {
+                // ================= drain: TMEM -> fp32 reductions into dW =================
+                const int q = warp & 3;
+                const int a = a0 + q * 32 + lane;                 // this thread's output row (channel a of dy)
+                mbar_wait(smem_u32(&tmem_full_bar), 0);
+                tc_fence_after();
+#pragma unroll 1
+                for (int j = 0; j < used / 32; ++j) {
+                    const int bcol = b0 + j * 32;
+                    if (bcol >= p.Kpad) break;                    // warp-uniform: zero-filled tail of the last b group
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + j * 32, v);
+                    tmem_ld_wait();
+                    if (a >= p.Ca) continue;
+                    float* dst = p.dW + (long long)a * p.Kpad + bcol;
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        red_add_v4(dst + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
+                                   __uint_as_float(v[e + 3]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, ncols);
 }
 
 }  // namespace
@@ -700,8 +917,8 @@ int bn_dgrad(const void* dy, const void* Wu, void* dx, const void* x, long long 
 
 // returns 1 = launched, 0 = shape not eligible, <0 = error
 int bn_conv_down(const void* x, const void* Wd, void* out, long long rows, int Kpad, int Cout, int C, int pitch, const float* gamma,
-                 const float* beta, const float* mean, const float* var, float eps, void* n1_out, int n1_pitch,
-                 const float* gamma2, const float* beta2, const float* mean2, const float* var2, void* out2, cudaStream_t st) {
+                 const float* beta, const float* mean, const float* var, float eps, void* n1_out, int n1_pitch, long long n1_first_row,
+                 const float* gamma2, const float* beta2, const float* mean2, const float* var2, void* out2, int C2, cudaStream_t st) {
     if (Kpad % KCH != 0 || C > Kpad || C <= 0 || (C & 7) || (pitch & 7) || pitch < C || (Cout & 7) || Cout <= 0 || rows <= 0) return 0;
     if (((uintptr_t)x | (uintptr_t)Wd | (uintptr_t)out | (uintptr_t)n1_out | (uintptr_t)out2) & 15) return 0;
     if (n1_out != nullptr && ((n1_pitch & 7) || n1_pitch < C)) return 0;
@@ -709,8 +926,8 @@ int bn_conv_down(const void* x, const void* Wd, void* out, long long rows, int K
     BnFpropParams p;
     p.rows = rows; p.C = C; p.Kpad = Kpad; p.pitch = pitch; p.Cout = Cout; p.out_pitch = Cout;
     p.gamma = gamma; p.beta = beta; p.mean = mean; p.var = var; p.eps = eps;
-    p.out = (bf16*)out; p.n1_out = (bf16*)n1_out; p.n1_pitch = n1_pitch;
-    p.gamma2 = gamma2; p.beta2 = beta2; p.mean2 = mean2; p.var2 = var2; p.out2 = (bf16*)out2;
+    p.out = (bf16*)out; p.n1_out = (bf16*)n1_out; p.n1_pitch = n1_pitch; p.n1_first_row = n1_first_row;
+    p.gamma2 = gamma2; p.beta2 = beta2; p.mean2 = mean2; p.var2 = var2; p.out2 = (bf16*)out2; p.C2 = C2;
     const long long sub = (rows + TILE_M - 1) / TILE_M;
     p.n_tiles = (Cout + BF_BN - 1) / BF_BN;
     // 256-row CTA tiles share every weight tile between two sub-tiles, unless 128-row tiles finish in fewer rounds on 148 CTAs
@@ -719,6 +936,8 @@ int bn_conv_down(const void* x, const void* Wd, void* out, long long rows, int K
         const long long t1 = sub * p.n_tiles, t2 = ((sub + 1) / 2) * p.n_tiles;
         const long long r1 = (t1 + kNumSMs - 1) / kNumSMs, r2 = (t2 + kNumSMs - 1) / kNumSMs;
         if (r1 < 2 * r2) MT = 1;
+        static const int dbg_mt = [] { const char* e = getenv("SRGAN_BF_MT"); return e ? atoi(e) : 0; }();
+        if (dbg_mt == 1 || dbg_mt == 2) MT = dbg_mt;
     }
     const long long m_tiles = (sub + MT - 1) / MT;
     if (m_tiles * p.n_tiles > 0x7fffffffLL) return 0;
@@ -729,4 +948,60 @@ int bn_conv_down(const void* x, const void* Wd, void* out, long long rows, int K
     rc = encode_mat(&tmB, Wd, Cout, Kpad, BF_BN);
     if (rc) return rc;
     return MT == 2 ? launch_bn_conv_down<2>(tmA, tmB, p, st) : launch_bn_conv_down<1>(tmA, tmB, p, st);
+}
+
+// returns 1 = launched, 0 = shape not eligible, <0 = error
+int bn_conv_wgrad(const void* dy, const void* x, float* dW, long long rows, int Ca, int Kpad, int C, int pitch, const float* gamma,
+                  const float* beta, const float* mean, const float* var, float eps, cudaStream_t st) {
+    if (Kpad % KCH != 0 || C > Kpad || C <= 0 || (C & 7) || (pitch & 7) || pitch < C || Ca <= 0 || (Ca & 7) || rows <= 0) return 0;
+    if (((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dW) & 15) return 0;
+    BnWgradParams p;
+    p.rows = rows; p.C = C; p.Kpad = Kpad; p.Ca = Ca;
+    p.gamma = gamma; p.beta = beta; p.mean = mean; p.var = var; p.eps = eps; p.dW = dW;
+    const long long chunks = (rows + BW_PIX - 1) / BW_PIX;
+    if (chunks > 0x7fffffffLL) return 0;
+    p.total_chunks = (int)chunks;
+    // (BN, NS) by the traffic model of umma_wgrad: t output tiles re-read dy t times, the K split over one wave of CTAs adds
+    // 148 / t partial sums into dW with fp32 reductions (a reduced byte weighted 4x a read byte)
+    const int a_tiles = (Ca + 127) / 128;
+    double best = -1.0;
+    int best_bn = 64, best_ns = 1;
+    for (int bn = 64; bn <= 256; bn *= 2)
+        for (int ns = 1; ns * bn <= 512; ++ns) {
+            if (ns > 1 && (ns - 1) * bn >= Kpad) break;
+            if (bn > 64 && bn / 2 >= Kpad) continue;
+            const int t = a_tiles * ((Kpad + ns * bn - 1) / (ns * bn));
+            double splits = kNumSMs / t < 1 ? 1 : kNumSMs / t;
+            if (splits > (chunks + 7) / 8) splits = (double)((chunks + 7) / 8);
+            if (splits < 1) splits = 1;
+            const double cost = (double)rows * 128 * 2.0 * t + 4.0 * (4.0 * Ca * Kpad) * splits;
+            if (best < 0 || cost < best) { best = cost; best_bn = bn; best_ns = ns; }
+        }
+    p.BN = best_bn; p.NS = best_ns;
+    const int out_tiles = (Kpad + p.NS * p.BN - 1) / (p.NS * p.BN);
+    int splits = kNumSMs / (out_tiles * a_tiles);
+    const int max_splits = (int)((chunks + 7) / 8);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p.chunks_per_split = (p.total_chunks + splits - 1) / splits;
+    splits = (p.total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
+    const int stage_bytes = 2 * BW_BOX + p.NS * (p.BN / 64) * BW_BOX;
+    p.stages = (200 * 1024) / stage_bytes;
+    if (p.stages > 8) p.stages = 8;
+    p.stages -= p.stages % BW_NG;                // every ring stage belongs to one transform group (see launch_bn_conv_down)
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    CUtensorMap tmS, tmL;
+    int rc = encode_mat_pitch(&tmS, dy, rows, Ca, Ca, BW_PIX);
+    if (rc) return rc;
+    rc = encode_mat_pitch(&tmL, x, rows, C, pitch, BW_PIX);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(bn_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024);
+        if (e != cudaSuccess) { srgan_set_error("cudaFuncSetAttribute(bn_conv_wgrad_kernel): %s", cudaGetErrorString(e)); return SRGAN_ERR_CUDA; }
+        attr_set = true;
+    }
+    bn_conv_wgrad_kernel<<<dim3(out_tiles, a_tiles, splits), BW_THREADS, smem, st>>>(tmS, tmL, p);
+    SRGAN_CHECK_LAUNCH("bn_conv_wgrad_kernel");
+    return 1;
 }

@@ -483,8 +483,11 @@ class Engine:
         return t[net.feature_buf] if net.graph is not None else t[len(net.layers)]
 
     def forward(self, st: NetState, acts, lo, hi, keep_pre=True):
-        """Runs the network on sample rows [lo, hi) of the buffers.  keep_pre=False: no weight gradient / tangent pass will
-        read these rows, so operands that fused kernels produce on the fly (Op.fuse >= 2) are not stored."""
+        """Runs the network on sample rows [lo, hi) of the buffers.  keep_pre: which rows of the operands that fused kernels
+        produce on the fly (Op.fuse >= 2: the normalised input of the trunk's 1x1 convolutions) are also stored -- True: all
+        (a weight gradient over the stored operand follows), False: none (forward / data gradient only), a sample index k:
+        samples >= k (nets whose weight gradients read the concat buffer themselves, Op.fuse >= 4: only the tangent pass
+        of the interpolate rows reads the stored operand)."""
         net = st.net
         if net.graph is not None:
             return self.graph_forward(st, acts, lo, hi, keep_pre=keep_pre)
@@ -619,6 +622,10 @@ class Engine:
                 d[op.branch] = torch.cuda.Stream(self.device)
         return d
 
+    @staticmethod
+    def _bn_params(P, nm):
+        return P[nm + '.weight'], P[nm + '.bias'], P[nm + '.running_mean'], P[nm + '.running_var']
+
     def _graph_forward_op(self, st: NetState, acts, op, lo, hi, n, tangent, mlo, keep_pre=True):
         """One op of graph_forward over sample rows [lo,hi) (n = hi - lo), on the current stream."""
         net, ops, R, P = st.net, self.ops, self._brows, st.params
@@ -638,14 +645,22 @@ class Engine:
                 a, l = op.pre, op.layer
                 cbuf, nm = net.bufs[a.src], a.name
                 timed = self._probe_open('forward_bn', st, l, ng)
+                if keep_pre is True:
+                    first = 0
+                elif keep_pre is False or a.fuse < 4:          # (a sample index only means something when the weight
+                    first = 0 if keep_pre is not False else None   # gradient reads the concat buffer too: fuse >= 4)
+                else:
+                    first = max(0, keep_pre - lo) * l.gemm_rows
                 ops.bn_conv_down(R(acts[a.src], cbuf, lo, hi), st.wd_[l.name], y, ng, l.geom.Cb, l.geom.Ca, a.C, cbuf.ch,
                                  P[nm + '.weight'], P[nm + '.bias'], P[nm + '.running_mean'], P[nm + '.running_var'], self.BN_EPS,
-                                 x if keep_pre else None, sb.ch)
+                                 x if first is not None and first < ng else None, sb.ch, n1_first_row=first or 0,
+                                 bn2=self._bn_params(P, op.post.name) if op.post is not None else None,
+                                 out2=R(acts[op.post.dst], net.bufs[op.post.dst], lo, hi) if op.post is not None else None)
                 self._probe_close(timed)
             else:
                 self._fwd_layer(st, op.layer, x, y, ng, lo=lo, views=vw)
-        elif op.kind == 'affine' and op.fuse >= 2 and not tangent:
-            pass                          # carried out by the convolution that consumes its output (above)
+        elif op.kind == 'affine' and (op.fuse >= 2 or op.absorbed) and not tangent:
+            pass                          # carried out by the convolution that consumes its output / produces its input (above)
         elif op.kind == 'affine':
             nm = op.name
             ops.affine(x, sb.ch, op.c0, y, db.ch, n * sb.rows, op.C, P[nm + '.weight'], P[nm + '.bias'],
@@ -722,8 +737,23 @@ class Engine:
                     dy = dy[op.c0:]
                 if weight_grads:
                     def wg(l=l, op=op, sb=sb, db=db, dy=dy, vw=vw):
-                        self._wgrad_layer(st, l, R(acts[op.src], sb, wlo, whi), R(deltas[op.dst], db, wlo, whi)[op.c0:],
-                                          (whi - wlo) * l.gemm_rows, lo=wlo, views=vw)
+                        w0 = wlo
+                        if op.pre is not None and op.pre.fuse >= 4:
+                            # the ordinary rows straight from the concat buffer (BatchNorm + ReLU applied on load); the
+                            # tangent block's operand is not relu(bn(.)): it stays a plain weight gradient over its rows
+                            a = op.pre
+                            cbuf, nm = net.bufs[a.src], a.name
+                            w0 = min(whi, hi)
+                            if w0 > wlo:
+                                timed = self._probe_open('wgrad_bn', st, l, (w0 - wlo) * l.gemm_rows)
+                                ops.bn_conv_wgrad(R(deltas[op.dst], db, wlo, w0), R(acts[a.src], cbuf, wlo, w0),
+                                                  st.g(l.name + '.weight'), (w0 - wlo) * l.gemm_rows, l.geom.Ca, l.geom.Cb, a.C,
+                                                  cbuf.ch, P[nm + '.weight'], P[nm + '.bias'], P[nm + '.running_mean'],
+                                                  P[nm + '.running_var'], self.BN_EPS)
+                                self._probe_close(timed)
+                        if whi > w0:
+                            self._wgrad_layer(st, l, R(acts[op.src], sb, w0, whi), R(deltas[op.dst], db, w0, whi)[op.c0:],
+                                              (whi - w0) * l.gemm_rows, lo=w0, views=vw)
                         if l.has_bias:
                             self._bias_grad(st, l, dy, n * db.rows)
                     if l.name in st.thin and l.fwd != 'down':      # its im2col output is reused by the data gradient below
@@ -942,7 +972,7 @@ class Engine:
         acts = self.alloc_acts('D', net, B)
         deltas = self.alloc_deltas('D', net, B)
         self.load_input(net, x, self.rows(self._in(net, acts), net.in_elems, 0, B), B)
-        self.forward(st, acts, 0, B)
+        self.forward(st, acts, 0, B, keep_pre=B)
         feats = self._brows_feat(net, acts, 0, B)
         pred = self.buf('pred', (B,), self.mdt)
         dpred = self.buf('dpred', (B,), self.mdt)
@@ -990,7 +1020,7 @@ class Engine:
                         self.rows(a_in, E, 3 * B, 4 * B), B, E)
         self.last_gan_batch = B
         # ---- one D forward over [x; u; fake; x_hat]
-        self.forward(D, acts, 0, 4 * B)
+        self.forward(D, acts, 0, 4 * B, keep_pre=3 * B)
         if self.publish_features and not dggan:
             self.buf('feat_snap', (4 * B * F,)).copy_(fblk(0, 4 * B))
         # ---- labeled loss (srgan.py:329-335, :414-417)
@@ -1137,7 +1167,7 @@ class Engine:
         for m in range(B // mb):
             r0, r1 = m * mb, (m + 1) * mb
             self.load_input(net, x[r0:r1], self.rows(self._in(net, acts), net.in_elems, 0, mb), mb)
-            self.forward(st, acts, 0, mb)
+            self.forward(st, acts, 0, mb, keep_pre=mb)
             feats = self._brows_feat(net, acts, 0, mb)
             hook = self._labeled(st, acts, deltas, mb, self._ysl(y, r0, r1), cfg, Bg, self.scalars[SC_DNN:SC_DNN + 1], pred, dpred)
             self.ops.seed_rows(self._brows_feat(net, deltas, 0, mb), mb, F, None, dpred, st.whead[0:F], feats, fact, fslope)
@@ -1191,7 +1221,7 @@ class Engine:
         sums.zero_()
         for m in range(nm):
             d_inputs(m, False)
-            self.forward(D, acts, 0, 3 * b)
+            self.forward(D, acts, 0, 3 * b, keep_pre=False)
             for j in range(3):
                 ops.colsum(fblk(j * b, (j + 1) * b), b, F, sums[j], 0, None)
         if self.comm is not None:
@@ -1213,7 +1243,7 @@ class Engine:
         for m in range(nm):
             r0, r1 = m * b, (m + 1) * b
             d_inputs(m, True)
-            self.forward(D, acts, 0, 4 * b)
+            self.forward(D, acts, 0, 4 * b, keep_pre=3 * b)
             hook = self._labeled(D, acts, deltas, b, self._ysl(y, r0, r1), cfg, Bg, sc[SC_LABELED:SC_LABELED + 1], pred, dpred)
             ops.seed_rows(dblk(0, b), b, F, gvec[0], dpred, D.whead[0:F], fblk(0, b), fact, fslope)
             ops.seed_rows(dblk(b, 2 * b), b, F, gvec[1], None, None, fblk(b, 2 * b), fact, fslope)

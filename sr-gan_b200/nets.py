@@ -155,9 +155,15 @@ class Op:
     pad: int = 0
     branch: int = 0                # 0 = trunk; i > 0 = side branch i (crowd MapModule i): reads a trunk buffer, ends in `features`
     # BatchNorm fusion (bf16 tcgen05 path, csrc/bn_gemm.cu): an 'affine' op with fuse > 0 is carried out by the 1x1 'conv' op
-    # that consumes its output (that op's `pre` points back at it).  fuse = 1: the backward pass (srgan_bn_dgrad).
+    # that consumes its output (that op's `pre` points back at it).  fuse >= 1: the data gradient (srgan_bn_dgrad); >= 2: the
+    # forward pass too (srgan_bn_conv_down: the normalised operand is stored only where a later pass reads it); >= 4: the
+    # weight gradient too (srgan_bn_conv_wgrad: only the tangent pass of the interpolate rows still reads a stored operand).
     fuse: int = 0
     pre: Optional['Op'] = None
+    # fuse >= 3: the BatchNorm + ReLU that FOLLOWS such a convolution (norm2 / relu2 of a dense layer) is carried out by the
+    # convolution's epilogue in the forward pass: conv.post = that 'affine' op, whose `absorbed` flag is set
+    post: Optional['Op'] = None
+    absorbed: bool = False
 
 
 @dataclass
@@ -333,6 +339,8 @@ def knn_densenet_cat(block_config=(6, 12, 48, 32), growth_rate=32, num_init_feat
                 ops[-1].pre, ops[-2].fuse = ops[-2], fuse_bn
             buf('n2.' + tag, h * h, cb, **RELU)
             ops.append(Op('affine', 'b.' + tag, 'n2.' + tag, name=pre + '.norm2', C=bs * g))
+            if fuse_bn >= 3:
+                ops[-2].post, ops[-1].absorbed = ops[-1], True
             if direct_concat:
                 conv(pre + '.conv2', 'n2.' + tag, cat, Geom(h, h, pad(g), h, h, cb, 3, 3, 1, 1), 'down', (g, bs * g, 3, 3))
                 ops[-1].C, ops[-1].c0 = g, c

@@ -35,7 +35,7 @@ _EXPORTS = (
     'srgan_repack', 'srgan_im2col', 'srgan_col2im', 'srgan_adam_prepare', 'srgan_coefficient_step',
     'srgan_coefficient_step_workspace_bytes', 'srgan_affine', 'srgan_affine_bwd', 'srgan_affine_grad', 'srgan_copy2d',
     'srgan_maxpool', 'srgan_maxpool_bwd', 'srgan_avgpool', 'srgan_avgpool_bwd', 'srgan_crowd_loss', 'srgan_crowd_map_grad', 'srgan_depth_to_space', 'srgan_adam_multi', 'srgan_affine_bwd_grad',
-    'srgan_adam_layout_multi', 'srgan_bn_dgrad', 'srgan_bn_conv_down',
+    'srgan_adam_layout_multi', 'srgan_bn_dgrad', 'srgan_bn_conv_down', 'srgan_bn_conv_wgrad',
 )
 
 _lib = None
@@ -103,7 +103,8 @@ def load_library(path: str = LIB_PATH):
     lib.srgan_depth_to_space.argtypes = [vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, vp]
     lib.srgan_crowd_map_grad.argtypes = [vp, vp, vp, vp, c_int, c_ll, c_int, c_int, c_f, c_int, vp]
     lib.srgan_bn_dgrad.argtypes = [vp, vp, vp, vp, c_ll, c_int, c_int, c_int, c_int, vp, vp, vp, vp, c_f, vp, vp, vp, c_int, c_int, c_int, vp]
-    lib.srgan_bn_conv_down.argtypes = [vp, vp, vp, c_ll, c_int, c_int, c_int, c_int, vp, vp, vp, vp, c_f, vp, c_int, vp, vp, vp, vp, vp, c_int, vp]
+    lib.srgan_bn_conv_down.argtypes = [vp, vp, vp, c_ll, c_int, c_int, c_int, c_int, vp, vp, vp, vp, c_f, vp, c_int, c_ll, vp, vp, vp, vp, vp, c_int, c_int, vp]
+    lib.srgan_bn_conv_wgrad.argtypes = [vp, vp, vp, c_ll, c_int, c_int, c_int, c_int, vp, vp, vp, vp, c_f, c_int, vp]
     lib.srgan_tensor_launch_count.restype = c_ll
     lib.srgan_simt_fallback_count.restype = c_ll
     for name in _EXPORTS[7:]:
@@ -468,12 +469,19 @@ class CudaOps:
                                          d_pitch, int(bool(accumulate)), _dt(dy.dtype), self._stream()), 'srgan_bn_dgrad')
 
     def bn_conv_down(self, x, Wd, out, rows, Kpad, Cout, C, pitch, gamma, beta, mean, var, eps, n1_out=None, n1_pitch=0, bn2=None,
-                     out2=None):
-        """out = relu(bn(x[:, :C])) @ Wd^T in one launch; n1_out: also store the normalised operand; bn2 = (gamma2, beta2,
-        mean2, var2) + out2: relu(bn2(out)) from the epilogue (include/srgan_b200.h)."""
+                     out2=None, n1_first_row=0):
+        """out = relu(bn(x[:, :C])) @ Wd^T in one launch; n1_out: also store the normalised operand (rows >= n1_first_row);
+        bn2 = (gamma2, beta2, mean2, var2) + out2: relu(bn2(out)) from the epilogue (include/srgan_b200.h)."""
         g2 = [self._pf(t) for t in bn2] if bn2 is not None else [None] * 4
         self._ck(self.lib.srgan_bn_conv_down(self._p(x), self._p(Wd, x.dtype), self._p(out, x.dtype), rows, Kpad, Cout, C, pitch,
                                              self._pf(gamma), self._pf(beta), self._pf(mean), self._pf(var), eps,
-                                             self._p(n1_out, x.dtype) if n1_out is not None else None, n1_pitch, *g2,
-                                             self._p(out2, x.dtype) if out2 is not None else None, _dt(x.dtype), self._stream()),
+                                             self._p(n1_out, x.dtype) if n1_out is not None else None, n1_pitch, n1_first_row, *g2,
+                                             self._p(out2, x.dtype) if out2 is not None else None,
+                                             bn2[0].numel() if bn2 is not None else 0, _dt(x.dtype), self._stream()),
                  'srgan_bn_conv_down')
+
+    def bn_conv_wgrad(self, dy, x, dW, rows, Ca, Kpad, C, pitch, gamma, beta, mean, var, eps):
+        """dW[Ca, Kpad] += dy^T @ relu(bn(x[:, :C])) from the raw concat buffer (include/srgan_b200.h)."""
+        self._ck(self.lib.srgan_bn_conv_wgrad(self._p(dy), self._p(x, dy.dtype), self._pf(dW), rows, Ca, Kpad, C, pitch,
+                                              self._pf(gamma), self._pf(beta), self._pf(mean), self._pf(var), eps, _dt(dy.dtype),
+                                              self._stream()), 'srgan_bn_conv_wgrad')

@@ -109,3 +109,46 @@ def test_bn_conv_down(ops, rows, C, pitch, Cout, keep, bn2):
         close(n1, n1_ref, 8e-3, 'bn_conv_down n1_out')
     if bn2:
         close(o2, o2_ref, 2e-2, 'bn_conv_down out2', outliers=1e-5)
+
+
+def test_bn_conv_down_first_row(ops):
+    """n1_first_row: the normalised operand is stored for the GEMM rows >= n1_first_row only, the rest of n1_out is untouched."""
+    gen = torch.Generator().manual_seed(5)
+    ref = TorchOps()
+    rows, C, pitch, Cout, Kpad, first = 4 * 196 * 3 + 7, 160, 256, 128, 192, 3 * 196 * 3
+    x = rnd(gen, rows * pitch, dt=BF)
+    Wd = (rnd(gen, Cout * Kpad) * 0.1).to(BF)
+    gamma, beta, mean, var = bn_params(gen, C)
+    out_ref, out = torch.zeros(rows * Cout, dtype=BF), torch.zeros(rows * Cout, dtype=BF, device='cuda')
+    n1_ref = rnd(gen, rows * Kpad, dt=BF)
+    n1 = n1_ref.clone().cuda()
+    cu = lambda t: t.cuda()
+    ref.bn_conv_down(x, Wd, out_ref, rows, Kpad, Cout, C, pitch, gamma, beta, mean, var, 1e-5, n1_ref, Kpad, n1_first_row=first)
+    ops.bn_conv_down(cu(x), cu(Wd), out, rows, Kpad, Cout, C, pitch, cu(gamma), cu(beta), cu(mean), cu(var), 1e-5, n1, Kpad,
+                     n1_first_row=first)
+    torch.cuda.synchronize()
+    close(out, out_ref, 1e-2, 'bn_conv_down out')
+    close(n1, n1_ref, 8e-3, 'bn_conv_down n1_out (rows >= first)')
+    assert torch.equal(n1.cpu()[:first * Kpad], n1_ref[:first * Kpad])
+
+
+@pytest.mark.parametrize('rows,C,pitch,Ca', [(3001, 96, 256, 128), (12544 + 5, 1056, 1920, 128), (777, 384, 384, 192),
+                                             (50, 64, 64, 128), (4 * 3136, 160, 256, 128), (40000, 256, 256, 128),
+                                             (2 * 148 * 128 + 17, 1888, 1920, 128), (5000, 512, 512, 256), (9000, 1792, 1792, 896)])
+def test_bn_conv_wgrad(ops, rows, C, pitch, Ca):
+    """Weight gradient of norm1 -> relu1 -> conv1 from the raw concat buffer (operand normalised in shared memory on load),
+    accumulated into dW; several a tiles (transitions), ragged rows, concat pitch > C, C not a multiple of the tile widths."""
+    gen = torch.Generator().manual_seed(rows + C + Ca)
+    ref = TorchOps()
+    Kpad = (C + 63) // 64 * 64
+    x = rnd(gen, rows * pitch, dt=BF)
+    dy = rnd(gen, rows * Ca, dt=BF)
+    gamma, beta, mean, var = bn_params(gen, C)
+    dW_ref = rnd(gen, Ca * Kpad)
+    dW = dW_ref.clone().cuda()
+    cu = lambda t: t.cuda()
+    ref.bn_conv_wgrad(dy, x, dW_ref, rows, Ca, Kpad, C, pitch, gamma, beta, mean, var, 1e-5)
+    ops.bn_conv_wgrad(cu(dy), cu(x), dW, rows, Ca, Kpad, C, pitch, cu(gamma), cu(beta), cu(mean), cu(var), 1e-5)
+    torch.cuda.synchronize()
+    close(dW, dW_ref, 2e-3, 'bn_conv_wgrad dW')
+    assert torch.equal(dW.cpu().view(Ca, Kpad)[:, C:], dW_ref.view(Ca, Kpad)[:, C:])

@@ -490,7 +490,7 @@ class TorchOps:
             d_out.view(rows, d_pitch)[:, :C] = d.to(d_out.dtype)
 
     def bn_conv_down(self, x, Wd, out, rows, Kpad, Cout, C, pitch, gamma, beta, mean, var, eps, n1_out=None, n1_pitch=0, bn2=None,
-                     out2=None):
+                     out2=None, n1_first_row=0):
         """n1 = relu(bn(x[:, :C])) rounded to the activation dtype; out = n1 @ Wd[:, :C]^T; n1_out (optional) = n1, zeros in
         the padding columns [C, min(Kpad, n1_pitch)); out2 (optional) = relu(bn2(out))."""
         self.launches += 1
@@ -502,9 +502,19 @@ class TorchOps:
         out.view(rows, Cout)[:] = o
         if n1_out is not None:
             v = n1_out.view(rows, n1_pitch)
-            v[:, :C] = n1
-            v[:, C:min(Kpad, n1_pitch)] = 0
+            v[n1_first_row:, :C] = n1[n1_first_row:]
+            v[n1_first_row:, C:min(Kpad, n1_pitch)] = 0
         if out2 is not None:
             g2, b2, m2, v2 = (q.detach().to(cd) for q in bn2)
-            s2 = g2 / torch.sqrt(v2 + eps)
-            out2.view(rows, Cout)[:] = torch.relu(o.to(cd) * s2 + (b2 - m2 * s2)).to(out2.dtype)
+            s2, C2 = g2 / torch.sqrt(v2 + eps), g2.numel()
+            out2.view(rows, Cout)[:, :C2] = torch.relu(o[:, :C2].to(cd) * s2 + (b2 - m2 * s2)).to(out2.dtype)
+            out2.view(rows, Cout)[:, C2:] = 0
+
+    def bn_conv_wgrad(self, dy, x, dW, rows, Ca, Kpad, C, pitch, gamma, beta, mean, var, eps):
+        """dW[Ca, Kpad][:, :C] += dy^T @ relu(bn(x[:, :C])) (the operand rounded to the activation dtype first)."""
+        self.launches += 1
+        cd = self._cd(dy)
+        s = gamma.detach().to(cd) / torch.sqrt(var.detach().to(cd) + eps)
+        t = beta.detach().to(cd) - mean.detach().to(cd) * s
+        n1 = torch.relu(x.view(rows, pitch)[:, :C].to(cd) * s + t).to(x.dtype).to(cd)
+        dW.view(Ca, Kpad)[:, :C] += (dy.view(rows, Ca).to(cd).t() @ n1).to(dW.dtype)
