@@ -215,6 +215,15 @@ int srgan_bn_dgrad(const void* dy, const void* Wu, void* dx, const void* x, long
                    const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* dgamma,
                    float* dbeta, void* d_out, int d_pitch, int accumulate, int dtype, void* stream);
 
+/* srgan_bn_conv_dgrad: the same backward with the product a stride-1, same-size R x S transposed convolution instead of a
+ * GEMM -- norm2 -> relu2 -> conv2 (3x3) of _DenseLayer (crowd/models.py:343-346): dy is an NHWC activation [n, H, W, .] (a
+ * channel window: dy_pitch elements between pixels, dy_valid channels exist, Cin channels per tap counted by Wu), Wu
+ * [Cout][R*S*Cin], x / dx [n*H*W rows x pitch].  Replaces srgan_conv_up (EPI_DACT) + srgan_affine_bwd_grad / srgan_affine_bwd. */
+int srgan_bn_conv_dgrad(const void* dy, int dy_pitch, int dy_valid, const void* Wu, void* dx, const void* x, int n, int H, int W,
+                        int R, int S, int pad, int Cin, int Cout, int C, int pitch, const float* gamma, const float* beta,
+                        const float* mean, const float* var, float eps, float* dgamma, float* dbeta, void* d_out, int d_pitch,
+                        int accumulate, int dtype, void* stream);
+
 /* srgan_bn_conv_down: forward of the pair in ONE launch.  The GEMM reads the RAW concat buffer x; every operand tile is
  * normalised + rectified in shared memory between its TMA arrival and the tcgen05.mma that consumes it, so the activation
  * n1 = relu(bn(x)) need not exist in memory:

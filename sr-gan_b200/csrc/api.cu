@@ -52,6 +52,9 @@ int bn_dgrad(const void* dy, const void* Wu, void* dx, const void* x, long long 
              const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* dgamma, float* dbeta,
              void* d_out, int d_pitch, int accumulate, cudaStream_t st);
 
+int bn_conv_dgrad(const void* dy, int dy_pitch, int dy_valid, const void* Wu, void* dx, const void* x, int n, int H, int W, int R,
+                  int S, int pad, int Cin, int Cout, int C, int pitch, const float* gamma, const float* beta, const float* mean,
+                  const float* var, float eps, float* dgamma, float* dbeta, void* d_out, int d_pitch, int accumulate, cudaStream_t st);
 int bn_conv_down(const void* x, const void* Wd, void* out, long long rows, int Kpad, int Cout, int C, int pitch, const float* gamma,
                  const float* beta, const float* mean, const float* var, float eps, void* n1_out, int n1_pitch, long long n1_first_row,
                  const float* gamma2, const float* beta2, const float* mean2, const float* var2, void* out2, int C2, cudaStream_t st);
@@ -165,6 +168,27 @@ int srgan_bn_dgrad(const void* dy, const void* Wu, void* dx, const void* x, long
     if (took < 0) return took;
     if (took == 0) {
         srgan_set_error("srgan_bn_dgrad: shape not eligible (K %% 64, Cout %% 64, C %% 8, pitch %% 8, 16-byte aligned pointers)");
+        return SRGAN_ERR_UNSUPPORTED;
+    }
+    t_last_tensor = 1;
+    g_tensor_calls.fetch_add(1, std::memory_order_relaxed);
+    return SRGAN_OK;
+}
+
+int srgan_bn_conv_dgrad(const void* dy, int dy_pitch, int dy_valid, const void* Wu, void* dx, const void* x, int n, int H, int W,
+                        int R, int S, int pad, int Cin, int Cout, int C, int pitch, const float* gamma, const float* beta,
+                        const float* mean, const float* var, float eps, float* dgamma, float* dbeta, void* d_out, int d_pitch,
+                        int accumulate, int dtype, void* stream) {
+    SRGAN_REQUIRE(dy && Wu && dx && x && gamma && beta && mean && var, "srgan_bn_conv_dgrad: null pointer");
+    SRGAN_REQUIRE(dtype == SRGAN_BF16, "srgan_bn_conv_dgrad: the fused dense-layer kernels are bf16 / tcgen05 only");
+    SRGAN_REQUIRE(n >= 0 && H > 0 && W > 0 && Cin > 0 && C > 0 && Cout >= C && pitch >= C, "srgan_bn_conv_dgrad: bad sizes");
+    if (n == 0) return SRGAN_OK;
+    int took = bn_conv_dgrad(dy, dy_pitch, dy_valid, Wu, dx, x, n, H, W, R, S, pad, Cin, Cout, C, pitch, gamma, beta, mean, var, eps,
+                             dgamma, dbeta, d_out, d_pitch, accumulate, (cudaStream_t)stream);
+    if (took < 0) return took;
+    if (took == 0) {
+        srgan_set_error("srgan_bn_conv_dgrad: shape not eligible (odd R = S = 2 pad + 1, Cin %% 64, Cout %% 64, C %% 8, pitches %% 8, "
+                        "power-of-two pixel patches, 16-byte aligned pointers)");
         return SRGAN_ERR_UNSUPPORTED;
     }
     t_last_tensor = 1;

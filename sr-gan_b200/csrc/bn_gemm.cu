@@ -65,8 +65,13 @@ struct BnDgradParams {
                                   // tangent block's BatchNorm-scale gradient
     int accumulate;               // dx += (else dx =)
     int m_tiles, total_tiles, stages;
+    // CONV variant: dy is an NHWC activation [n, H, W, .] and the product a stride-1 transposed convolution over R x S taps
+    // (the data gradient of a same-size convolution); a row tile is a TW x TH x TN patch (powers of two) of pixels x samples
+    int n, H, W, R, S, pad, Cin;  // Cin = channels of dy per tap as the weight matrix counts them (a multiple of 64)
+    int TW, TH, TN, lgTW, lgTH, tiles_w, tiles_h;
 };
 
+template <bool CONV>
 __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB, const BnDgradParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -106,14 +111,31 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
             uint32_t ph = 0;
             for (int tile = tile_begin; tile < tile_end; ++tile) {
                 const int mt = tile % p.m_tiles, ny = tile / p.m_tiles;
-                for (int ch = 0; ch < nch; ++ch) {
-                    mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
-                    const uint32_t fb = smem_u32(&full_bar[s]);
-                    mbar_expect_tx(fb, BD_STAGE_BYTES);
-                    const uint32_t dst = tiles + s * BD_STAGE_BYTES;
-                    tma_load_2d(dst, &tmA, fb, ch * KCH, mt * TILE_M);
-                    tma_load_2d(dst + A_STAGE_BYTES, &tmB, fb, ch * KCH, ny * BN);
-                    if (++s == stages) { s = 0; ph ^= 1; }
+                if constexpr (CONV) {
+                    const int w0 = (mt % p.tiles_w) * p.TW, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.TH;
+                    const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.TN;
+                    const int cpt = p.Cin / KCH;             // K chunks per tap
+                    for (int tr = 0; tr < p.R; ++tr)
+                        for (int ts = 0; ts < p.S; ++ts)
+                            for (int ch = 0; ch < cpt; ++ch) {
+                                mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+                                const uint32_t fb = smem_u32(&full_bar[s]);
+                                mbar_expect_tx(fb, BD_STAGE_BYTES);
+                                const uint32_t dst = tiles + s * BD_STAGE_BYTES;
+                                tma_load_4d(dst, &tmA, fb, ch * KCH, w0 + p.pad - ts, h0 + p.pad - tr, n0);
+                                tma_load_2d(dst + A_STAGE_BYTES, &tmB, fb, (tr * p.S + ts) * p.Cin + ch * KCH, ny * BN);
+                                if (++s == stages) { s = 0; ph ^= 1; }
+                            }
+                } else {
+                    for (int ch = 0; ch < nch; ++ch) {
+                        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+                        const uint32_t fb = smem_u32(&full_bar[s]);
+                        mbar_expect_tx(fb, BD_STAGE_BYTES);
+                        const uint32_t dst = tiles + s * BD_STAGE_BYTES;
+                        tma_load_2d(dst, &tmA, fb, ch * KCH, mt * TILE_M);
+                        tma_load_2d(dst + A_STAGE_BYTES, &tmB, fb, ch * KCH, ny * BN);
+                        if (++s == stages) { s = 0; ph ^= 1; }
+                    }
                 }
             }
         }
@@ -173,21 +195,35 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
         // it has been consumed, so every piece is in flight for a whole tile time and ~all of the zone (64 KB per CTA) is
         // outstanding at any moment (Little: 44 GB/s per SM x ~1.5 us).
         // Geometry of a tile for this lane: element offset of slot 0, rows left below the lane's first row, channel validity.
-        const int pitch8 = 8 * p.pitch;
-        struct Geo { long long off; int rows_left; int c0; };
+        // (pix[it] = index of the pixel row that the lane's slot `it` belongs to, ok = bit it set when that row exists)
+        struct Geo { int pix[4]; int ok; int c0; };
         auto geo = [&](int mt, int ny) {
             Geo g;
-            const long long r = (long long)mt * TILE_M + q * 32 + t_row;
-            const long long left = p.rows - r;
-            g.rows_left = left > 64 ? 64 : (left < 0 ? 0 : (int)left);
+            g.ok = 0;
             g.c0 = ny * BN + half * 32 + t_unit * 8;
-            g.off = r * p.pitch + g.c0;
+            if (CONV) {
+                const int w0 = (mt % p.tiles_w) * p.TW, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.TH;
+                const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.TN;
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int r = q * 32 + 8 * it + t_row;
+                    const int sample = n0 + (r >> (p.lgTW + p.lgTH));
+                    g.pix[it] = (sample * p.H + h0 + ((r >> p.lgTW) & (p.TH - 1))) * p.W + w0 + (r & (p.TW - 1));
+                    if (sample < p.n) g.ok |= 1 << it;
+                }
+            } else {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    g.pix[it] = mt * TILE_M + q * 32 + 8 * it + t_row;
+                    if (g.pix[it] < p.rows) g.ok |= 1 << it;
+                }
+            }
             return g;
         };
         auto issue = [&](const Geo& g, bool live_tile, int k) {
             const int jj = k >> 2, it = k & 3;
-            const bool ok = live_tile && 8 * it < g.rows_left && g.c0 + jj * 64 < p.C;
-            const long long o = ok ? g.off + jj * 64 + it * pitch8 : 0;
+            const bool ok = live_tile && ((g.ok >> it) & 1) && g.c0 + jj * 64 < p.C;
+            const long long o = ok ? (long long)g.pix[it] * p.pitch + g.c0 + jj * 64 : 0;
             cp_async16(zone + (uint32_t)(k * 1024), p.x + o, ok ? 16u : 0u);
             if (accum) cp_async16(zone + (uint32_t)(k * 1024 + 512), p.dx + o, ok ? 16u : 0u);
             cp_async_commit();                   // always: the group count per slot stays fixed
@@ -326,11 +362,10 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
                         }
 #pragma unroll
                         for (int e = 0; e < 8; ++e) o[e] = fmaf(d[e], s8[e], o[e]);
-                        if (cok && 8 * it < gc.rows_left) {
-                            const long long off = gc.off + jj * 64 + it * pitch8;
-                            *reinterpret_cast<uint4*>(p.dx + off) = pack8(o);
+                        if (cok && ((gc.ok >> it) & 1)) {
+                            *reinterpret_cast<uint4*>(p.dx + (long long)gc.pix[it] * p.pitch + gc.c0 + jj * 64) = pack8(o);
                             if (p.d_out != nullptr)
-                                *reinterpret_cast<uint4*>(p.d_out + ((long long)mt * TILE_M + q * 32 + 8 * it + t_row) * p.d_pitch + gc.c0 + jj * 64) = dr;
+                                *reinterpret_cast<uint4*>(p.d_out + (long long)gc.pix[it] * p.d_pitch + gc.c0 + jj * 64) = dr;
                         }
                     }
                     issue(gn, live_n, k);
@@ -903,15 +938,68 @@ int bn_dgrad(const void* dy, const void* Wu, void* dx, const void* x, long long 
     if (rc) return rc;
     rc = encode_mat(&tmB, Wu, Cout, K, BD_BN);
     if (rc) return rc;
+    p.n = p.H = p.W = p.R = p.S = p.pad = p.Cin = p.TW = p.TH = p.TN = p.lgTW = p.lgTH = p.tiles_w = p.tiles_h = 0;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(bn_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(bn_dgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) { srgan_set_error("cudaFuncSetAttribute(bn_dgrad_kernel): %s", cudaGetErrorString(e)); return SRGAN_ERR_CUDA; }
         attr_set = true;
     }
     const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-    bn_dgrad_kernel<<<grid, BD_THREADS, smem, st>>>(tmA, tmB, p);
+    bn_dgrad_kernel<false><<<grid, BD_THREADS, smem, st>>>(tmA, tmB, p);
     SRGAN_CHECK_LAUNCH("bn_dgrad_kernel");
+    return 1;
+}
+
+// The same with dy an NHWC activation and the product a stride-1 R x S transposed convolution (the data gradient of a same-size
+// convolution: conv2 of a dense layer, whose input is relu2(norm2(.))).  dy may be a channel window (dy_pitch elements between
+// pixels, dy_valid channels exist, the rest of the Cin channels per tap is zero fill).  returns 1 / 0 / <0 as above
+int bn_conv_dgrad(const void* dy, int dy_pitch, int dy_valid, const void* Wu, void* dx, const void* x, int n, int H, int W, int R,
+                  int S, int pad, int Cin, int Cout, int C, int pitch, const float* gamma, const float* beta, const float* mean,
+                  const float* var, float eps, float* dgamma, float* dbeta, void* d_out, int d_pitch, int accumulate, cudaStream_t st) {
+    if (Cin % KCH != 0 || Cout % 64 != 0 || C > Cout || C <= 0 || (C & 7) || (pitch & 7) || pitch < C || n <= 0) return 0;
+    if ((dy_pitch | dy_valid) & 7) return 0;
+    if (dy_valid > Cin || (dy_pitch > 0 && dy_pitch < (dy_valid > 0 ? dy_valid : Cin))) return 0;
+    if (((uintptr_t)dy | (uintptr_t)Wu | (uintptr_t)dx | (uintptr_t)x | (uintptr_t)d_out) & 15) return 0;
+    if (d_out != nullptr && ((d_pitch & 7) || d_pitch < C)) return 0;
+    if (R <= 0 || S <= 0 || pad < 0 || pad >= R || pad >= S || 2 * pad + 1 != R || 2 * pad + 1 != S) return 0;     // same-size, stride 1
+    BnDgradParams p;
+    if (!pick_patch(W, H, TILE_M, 16, p.TW, p.TH, p.TN)) return 0;
+    if ((p.TW & (p.TW - 1)) || (p.TH & (p.TH - 1))) return 0;
+    p.lgTW = 0; while ((1 << p.lgTW) < p.TW) ++p.lgTW;
+    p.lgTH = 0; while ((1 << p.lgTH) < p.TH) ++p.lgTH;
+    p.tiles_w = W / p.TW; p.tiles_h = H / p.TH;
+    const long long tiles_n = (n + p.TN - 1) / p.TN;
+    const long long m_tiles = (long long)p.tiles_w * p.tiles_h * tiles_n;
+    const long long n_tiles = (C + BD_BN - 1) / BD_BN;
+    if (m_tiles * n_tiles > 0x7fffffffLL || (long long)(tiles_n * p.TN) * H * W > 0x7fffffffLL) return 0;
+    p.n = n; p.H = H; p.W = W; p.R = R; p.S = S; p.pad = pad; p.Cin = Cin;
+    p.rows = (long long)n * H * W; p.K = R * S * Cin; p.C = C; p.Cpad = (C + 31) / 32 * 32; p.pitch = pitch;
+    p.x = (const bf16*)x; p.dx = (bf16*)dx;
+    p.gamma = gamma; p.beta = beta; p.mean = mean; p.var = var; p.eps = eps;
+    p.dgamma = dgamma; p.dbeta = dbeta; p.accumulate = accumulate;
+    p.d_out = (bf16*)d_out; p.d_pitch = d_pitch;
+    p.m_tiles = (int)m_tiles; p.total_tiles = (int)(m_tiles * n_tiles);
+    const int fixed = 8 * EPI_STG_BYTES + 8 * BD_ZONE_WARP + 2 * p.Cpad * 4 + 1024;
+    int stages = (226 * 1024 - fixed) / BD_STAGE_BYTES;
+    if (stages > 8) stages = 8;
+    if (stages < 2) return 0;
+    p.stages = stages;
+    const size_t smem = (size_t)stages * BD_STAGE_BYTES + fixed;
+    CUtensorMap tmA, tmB;
+    int rc = encode_act(&tmA, dy, n, H, W, Cin, p.TW, p.TH, p.TN, 1, dy_pitch, dy_valid);
+    if (rc) return rc;
+    rc = encode_mat(&tmB, Wu, Cout, (long long)R * S * Cin, BD_BN);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(bn_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        if (e != cudaSuccess) { srgan_set_error("cudaFuncSetAttribute(bn_dgrad_kernel<conv>): %s", cudaGetErrorString(e)); return SRGAN_ERR_CUDA; }
+        attr_set = true;
+    }
+    const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+    bn_dgrad_kernel<true><<<grid, BD_THREADS, smem, st>>>(tmA, tmB, p);
+    SRGAN_CHECK_LAUNCH("bn_dgrad_kernel<conv>");
     return 1;
 }
 

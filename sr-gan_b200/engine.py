@@ -486,7 +486,7 @@ class Engine:
         """Runs the network on sample rows [lo, hi) of the buffers.  keep_pre: which rows of the operands that fused kernels
         produce on the fly (Op.fuse >= 2: the normalised input of the trunk's 1x1 convolutions) are also stored -- True: all
         (a weight gradient over the stored operand follows), False: none (forward / data gradient only), a sample index k:
-        samples >= k (nets whose weight gradients read the concat buffer themselves, Op.fuse >= 4: only the tangent pass
+        samples >= k (nets whose weight gradients read the concat buffer themselves, Op.fuse >= 5: only the tangent pass
         of the interpolate rows reads the stored operand)."""
         net = st.net
         if net.graph is not None:
@@ -647,8 +647,8 @@ class Engine:
                 timed = self._probe_open('forward_bn', st, l, ng)
                 if keep_pre is True:
                     first = 0
-                elif keep_pre is False or a.fuse < 4:          # (a sample index only means something when the weight
-                    first = 0 if keep_pre is not False else None   # gradient reads the concat buffer too: fuse >= 4)
+                elif keep_pre is False or a.fuse < 5:          # (a sample index only means something when the weight
+                    first = 0 if keep_pre is not False else None   # gradient reads the concat buffer too: fuse >= 5)
                 else:
                     first = max(0, keep_pre - lo) * l.gemm_rows
                 ops.bn_conv_down(R(acts[a.src], cbuf, lo, hi), st.wd_[l.name], y, ng, l.geom.Cb, l.geom.Ca, a.C, cbuf.ch,
@@ -738,7 +738,7 @@ class Engine:
                 if weight_grads:
                     def wg(l=l, op=op, sb=sb, db=db, dy=dy, vw=vw):
                         w0 = wlo
-                        if op.pre is not None and op.pre.fuse >= 4:
+                        if op.pre is not None and op.pre.fuse >= 5:
                             # the ordinary rows straight from the concat buffer (BatchNorm + ReLU applied on load); the
                             # tangent block's operand is not relu(bn(.)): it stays a plain weight gradient over its rows
                             a = op.pre
@@ -779,9 +779,26 @@ class Engine:
                         off_path(lambda a=a, sb=sb, cbuf=cbuf, nm=nm, mean=mean, var=var, op=op: ops.affine_grad(
                             R(deltas[op.src], sb, hi, whi), sb.ch, R(acts[a.src], cbuf, hi, whi), cbuf.ch, a.c0,
                             (whi - hi) * cbuf.rows, a.C, mean, var, self.BN_EPS, st.g(nm + '.weight'), None, False))
+                elif op.bwd_pre is not None:
+                    # norm2 + relu2 backward fused into the 3x3 convolution's data gradient: dy is the layer's channel window
+                    # of the concat delta, the result goes straight into the delta of the bottleneck buffer
+                    a = op.bwd_pre
+                    bbuf, nm = net.bufs[a.src], a.name
+                    mean, var = P[nm + '.running_mean'], P[nm + '.running_var']
+                    timed = self._probe_open('dgrad_bn3', st, l, n)
+                    ops.bn_conv_dgrad(dy, db.ch if vw is not None else 0, op.C if vw is not None else 0, st.wu_[l.name],
+                                      R(deltas[a.src], bbuf, lo, hi), R(acts[a.src], bbuf, mlo, mlo + n), n, l.geom, a.C, bbuf.ch,
+                                      P[nm + '.weight'], P[nm + '.bias'], mean, var, self.BN_EPS,
+                                      st.g(nm + '.weight') if weight_grads else None, st.g(nm + '.bias') if weight_grads else None,
+                                      dx if keep_pre else None, sb.ch, bbuf.accumulate)
+                    self._probe_close(timed)
+                    if weight_grads and whi > hi:      # the tangent block's BatchNorm-scale gradient (the g-chain kept its delta)
+                        off_path(lambda a=a, sb=sb, bbuf=bbuf, nm=nm, mean=mean, var=var, op=op: ops.affine_grad(
+                            R(deltas[op.src], sb, hi, whi), sb.ch, R(acts[a.src], bbuf, hi, whi), bbuf.ch, a.c0,
+                            (whi - hi) * bbuf.rows, a.C, mean, var, self.BN_EPS, st.g(nm + '.weight'), None, False))
                 else:
                     self._bwd_data_layer(st, l, dy, dx, n * l.gemm_rows, xa, sb.act, sb.slope, lo=lo, views=vw)
-            elif op.kind == 'affine' and op.fuse:
+            elif op.kind == 'affine' and (op.fuse or op.bwd_fused):
                 pass                      # carried out by the convolution that consumes its output (above)
             elif op.kind == 'affine':
                 nm = op.name

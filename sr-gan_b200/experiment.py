@@ -264,7 +264,7 @@ class StepRunner:
         # bf16 mode: dense layers write / read their channel window of the concat buffers in place (tcgen05 kernels only)
         direct = precision == 'bf16' and os.environ.get('SRGAN_NO_DIRECT_CONCAT', '0') != '1'
         # ... and the BatchNorm + ReLU in front of every trunk 1x1 convolution is fused into that convolution's kernels
-        fuse = int(os.environ.get('SRGAN_FUSE_BN', '3')) if precision == 'bf16' else 0
+        fuse = int(os.environ.get('SRGAN_FUSE_BN', '4')) if precision == 'bf16' else 0
         d_net, g_net = nets.describe_module(D, direct, fuse), nets.describe_module(G)
         if nets.describe_module(DNN, direct, fuse) != d_net:
             raise ValueError('DNN and D must share an architecture (srgan.py model_setup)')

@@ -156,7 +156,7 @@ class Op:
     branch: int = 0                # 0 = trunk; i > 0 = side branch i (crowd MapModule i): reads a trunk buffer, ends in `features`
     # BatchNorm fusion (bf16 tcgen05 path, csrc/bn_gemm.cu): an 'affine' op with fuse > 0 is carried out by the 1x1 'conv' op
     # that consumes its output (that op's `pre` points back at it).  fuse >= 1: the data gradient (srgan_bn_dgrad); >= 2: the
-    # forward pass too (srgan_bn_conv_down: the normalised operand is stored only where a later pass reads it); >= 4: the
+    # forward pass too (srgan_bn_conv_down: the normalised operand is stored only where a later pass reads it); >= 5: the
     # weight gradient too (srgan_bn_conv_wgrad: only the tangent pass of the interpolate rows still reads a stored operand).
     fuse: int = 0
     pre: Optional['Op'] = None
@@ -164,6 +164,10 @@ class Op:
     # convolution's epilogue in the forward pass: conv.post = that 'affine' op, whose `absorbed` flag is set
     post: Optional['Op'] = None
     absorbed: bool = False
+    # fuse >= 4: the backward pass of the BatchNorm + ReLU in front of a dense layer's 3x3 convolution (norm2 / relu2) is carried
+    # out by that convolution's data-gradient kernel (srgan_bn_conv_dgrad): conv.bwd_pre = the 'affine' op, whose bwd_fused is set
+    bwd_pre: Optional['Op'] = None
+    bwd_fused: bool = False
 
 
 @dataclass
@@ -344,6 +348,8 @@ def knn_densenet_cat(block_config=(6, 12, 48, 32), growth_rate=32, num_init_feat
             if direct_concat:
                 conv(pre + '.conv2', 'n2.' + tag, cat, Geom(h, h, pad(g), h, h, cb, 3, 3, 1, 1), 'down', (g, bs * g, 3, 3))
                 ops[-1].C, ops[-1].c0 = g, c
+                if fuse_bn >= 4:
+                    ops[-1].bwd_pre, ops[-2].bwd_fused = ops[-2], True
             else:
                 buf('new.' + tag, h * h, pad(g))
                 conv(pre + '.conv2', 'n2.' + tag, 'new.' + tag, Geom(h, h, pad(g), h, h, cb, 3, 3, 1, 1), 'down', (g, bs * g, 3, 3))

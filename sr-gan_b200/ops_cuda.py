@@ -35,7 +35,7 @@ _EXPORTS = (
     'srgan_repack', 'srgan_im2col', 'srgan_col2im', 'srgan_adam_prepare', 'srgan_coefficient_step',
     'srgan_coefficient_step_workspace_bytes', 'srgan_affine', 'srgan_affine_bwd', 'srgan_affine_grad', 'srgan_copy2d',
     'srgan_maxpool', 'srgan_maxpool_bwd', 'srgan_avgpool', 'srgan_avgpool_bwd', 'srgan_crowd_loss', 'srgan_crowd_map_grad', 'srgan_depth_to_space', 'srgan_adam_multi', 'srgan_affine_bwd_grad',
-    'srgan_adam_layout_multi', 'srgan_bn_dgrad', 'srgan_bn_conv_down', 'srgan_bn_conv_wgrad',
+    'srgan_adam_layout_multi', 'srgan_bn_dgrad', 'srgan_bn_conv_down', 'srgan_bn_conv_wgrad', 'srgan_bn_conv_dgrad',
 )
 
 _lib = None
@@ -104,6 +104,8 @@ def load_library(path: str = LIB_PATH):
     lib.srgan_crowd_map_grad.argtypes = [vp, vp, vp, vp, c_int, c_ll, c_int, c_int, c_f, c_int, vp]
     lib.srgan_bn_dgrad.argtypes = [vp, vp, vp, vp, c_ll, c_int, c_int, c_int, c_int, vp, vp, vp, vp, c_f, vp, vp, vp, c_int, c_int, c_int, vp]
     lib.srgan_bn_conv_down.argtypes = [vp, vp, vp, c_ll, c_int, c_int, c_int, c_int, vp, vp, vp, vp, c_f, vp, c_int, c_ll, vp, vp, vp, vp, vp, c_int, c_int, vp]
+    lib.srgan_bn_conv_dgrad.argtypes = [vp, c_int, c_int, vp, vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                        vp, vp, vp, vp, c_f, vp, vp, vp, c_int, c_int, c_int, vp]
     lib.srgan_bn_conv_wgrad.argtypes = [vp, vp, vp, c_ll, c_int, c_int, c_int, c_int, vp, vp, vp, vp, c_f, c_int, vp]
     lib.srgan_tensor_launch_count.restype = c_ll
     lib.srgan_simt_fallback_count.restype = c_ll
@@ -485,3 +487,12 @@ class CudaOps:
         self._ck(self.lib.srgan_bn_conv_wgrad(self._p(dy), self._p(x, dy.dtype), self._pf(dW), rows, Ca, Kpad, C, pitch,
                                               self._pf(gamma), self._pf(beta), self._pf(mean), self._pf(var), eps, _dt(dy.dtype),
                                               self._stream()), 'srgan_bn_conv_wgrad')
+
+    def bn_conv_dgrad(self, dy, dy_pitch, dy_valid, Wu, dx, x, n, g, C, pitch, gamma, beta, mean, var, eps, dgamma, dbeta, d_out,
+                      d_pitch, accumulate):
+        """bn_dgrad with the product a stride-1 same-size transposed convolution of geometry g (conv2 of a dense layer)."""
+        self._ck(self.lib.srgan_bn_conv_dgrad(self._p(dy), dy_pitch, dy_valid, self._p(Wu, dy.dtype), self._p(dx, dy.dtype),
+                                              self._p(x, dy.dtype), n, g.Hl, g.Wl, g.R, g.S, g.pad, g.Ca, g.Cb, C, pitch,
+                                              self._pf(gamma), self._pf(beta), self._pf(mean), self._pf(var), eps, self._pf(dgamma),
+                                              self._pf(dbeta), self._p(d_out, dy.dtype) if d_out is not None else None, d_pitch,
+                                              int(bool(accumulate)), _dt(dy.dtype), self._stream()), 'srgan_bn_conv_dgrad')

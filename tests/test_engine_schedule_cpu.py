@@ -114,7 +114,7 @@ def build_crowd_engine(st, dtype, spec_kwargs, image, z_dim, g_conv_dim, direct_
     return engine.Engine(TorchOps(), d_net, g_net, D, G, DNN, act_dtype=dtype, device='cpu')
 
 
-@pytest.mark.parametrize('direct,fuse', [(False, 0), (True, 0), (True, 1), (True, 2), (True, 3), (True, 4)])
+@pytest.mark.parametrize('direct,fuse', [(False, 0), (True, 0), (True, 1), (True, 2), (True, 3), (True, 4), (True, 5)])
 @pytest.mark.parametrize('method', ['srgan', 'dggan'])
 def test_crowd_graph_schedule_matches_oracle_fp64(method, direct, fuse):
     """Crowd SR-GAN (KnnDenseNetCat graph: eval-mode BatchNorm affine with trainable weight/bias, ReLU, max/avg pools,
@@ -124,7 +124,7 @@ def test_crowd_graph_schedule_matches_oracle_fp64(method, direct, fuse):
     reference in tests/test_oracle_golden.py).  direct: the dense layers' 3x3 convolutions write / read their channel
     window of the concat buffers in place (srgan_views; the bf16 product path) instead of going through slice copies.
     fuse: the BatchNorm + ReLU in front of the trunk's 1x1 convolutions is carried out by those convolutions' kernels
-    (1 = the data gradient, 2 = the forward pass too, 3 = norm2 / relu2 in conv1's forward epilogue, 4 = the weight gradient too; csrc/bn_gemm.cu)."""
+    (1 = the data gradient, 2 = the forward pass too, 3 = norm2 / relu2 in conv1's forward epilogue, 4 = norm2 / relu2 backward in conv2's data gradient, 5 = conv1's weight gradient from the concat buffer; csrc/bn_gemm.cu)."""
     dt = torch.float64
     kw = dict(block_config=(2, 2, 2, 2), growth_rate=8, num_init_features=16, bn_size=2, label_patch_size=64)
     st = O.init_crowd(seed=1, image_size=64, z_dim=16, g_conv_dim=8, dtype=dt, scale=2.0, dggan=(method == 'dggan'), **kw)

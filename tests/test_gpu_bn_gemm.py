@@ -152,3 +152,40 @@ def test_bn_conv_wgrad(ops, rows, C, pitch, Ca):
     torch.cuda.synchronize()
     close(dW, dW_ref, 2e-3, 'bn_conv_wgrad dW')
     assert torch.equal(dW.cpu().view(Ca, Kpad)[:, C:], dW_ref.view(Ca, Kpad)[:, C:])
+
+
+@pytest.mark.parametrize('n,H,cat_ch,c0,C', [(5, 14, 256, 160, 128), (130, 7, 1920, 1888 - 32, 128), (3, 56, 256, 64, 128),
+                                             (9, 28, 512, 480, 128), (67, 14, 96, 64, 64)])
+@pytest.mark.parametrize('acc,grads,keep', [(False, True, False), (False, False, True), (True, True, True)])
+def test_bn_conv_dgrad(ops, n, H, cat_ch, c0, C, acc, grads, keep):
+    """norm2 -> relu2 -> conv2 (3x3) backward in one launch: dy is the layer's 32-channel window of the concat delta (TMA zero
+    fill up to the 64 channels per tap the weight matrix counts), the result lands in the bottleneck delta; pixel-patch row
+    tiles at every trunk resolution, ragged sample counts."""
+    from srgan_b200.nets import Geom
+    gen = torch.Generator().manual_seed(n + H + cat_ch)
+    ref = TorchOps()
+    g = Geom(H, H, 64, H, H, (C + 63) // 64 * 64, 3, 3, 1, 1)
+    rows, pitch, growth = n * H * H, g.Cb, 32
+    dcat = rnd(gen, rows * cat_ch, dt=BF)
+    Wu = torch.zeros(g.Cb, 3, 3, 64)
+    Wu[:C, :, :, :growth] = rnd(gen, C, 3, 3, growth) * 0.1
+    Wu = Wu.reshape(-1).to(BF)
+    x = rnd(gen, rows * pitch, dt=BF)
+    gamma, beta, mean, var = bn_params(gen, C)
+    dx_ref = rnd(gen, rows * pitch, dt=BF)
+    dx = dx_ref.clone().cuda()
+    d_ref = rnd(gen, rows * pitch, dt=BF) if keep else None
+    d = d_ref.clone().cuda() if keep else None
+    dg_ref, db_ref = rnd(gen, C), rnd(gen, C)
+    dg, db = dg_ref.clone().cuda(), db_ref.clone().cuda()
+    cu = lambda t: t.cuda()
+    ref.bn_conv_dgrad(dcat[c0:], cat_ch, growth, Wu, dx_ref, x, n, g, C, pitch, gamma, beta, mean, var, 1e-5,
+                      dg_ref if grads else None, db_ref if grads else None, d_ref, pitch, acc)
+    ops.bn_conv_dgrad(cu(dcat)[c0:], cat_ch, growth, cu(Wu), dx, cu(x), n, g, C, pitch, cu(gamma), cu(beta), cu(mean), cu(var), 1e-5,
+                      dg if grads else None, db if grads else None, d, pitch, acc)
+    torch.cuda.synchronize()
+    close(dx, dx_ref, 2e-2, 'bn_conv_dgrad dx', outliers=1e-5)
+    close(dg, dg_ref, 1e-2, 'bn_conv_dgrad dgamma')
+    close(db, db_ref, 1e-2, 'bn_conv_dgrad dbeta')
+    if keep:
+        close(d, d_ref, 2e-2, 'bn_conv_dgrad d_out', outliers=1e-5)

@@ -472,9 +472,13 @@ class TorchOps:
         cd = self._cd(dy)
         g, b = gamma.detach().to(cd), beta.detach().to(cd)
         mu, sig = mean.detach().to(cd), torch.sqrt(var.detach().to(cd) + eps)
-        xs = x.view(rows, pitch)[:, :C].to(cd)
         prod = dy.view(rows, K).to(cd) @ Wu.view(Cout, K)[:C].to(cd).t()
         prod = prod.to(dy.dtype).to(cd)                       # the accumulator is rounded to the activation dtype first
+        self._bn_bwd_tail(prod, dx, x, rows, C, pitch, g, b, mu, sig, dgamma, dbeta, d_out, d_pitch, accumulate, cd)
+
+    @staticmethod
+    def _bn_bwd_tail(prod, dx, x, rows, C, pitch, g, b, mu, sig, dgamma, dbeta, d_out, d_pitch, accumulate, cd):
+        xs = x.view(rows, pitch)[:, :C].to(cd)
         d = prod * (((xs - mu) * (g / sig) + b) > 0).to(cd)
         v = d * (g / sig)
         dxv = dx.view(rows, pitch)
@@ -518,3 +522,17 @@ class TorchOps:
         t = beta.detach().to(cd) - mean.detach().to(cd) * s
         n1 = torch.relu(x.view(rows, pitch)[:, :C].to(cd) * s + t).to(x.dtype).to(cd)
         dW.view(Ca, Kpad)[:, :C] += (dy.view(rows, Ca).to(cd).t() @ n1).to(dW.dtype)
+
+    def bn_conv_dgrad(self, dy, dy_pitch, dy_valid, Wu, dx, x, n, g, C, pitch, gamma, beta, mean, var, eps, dgamma, dbeta, d_out,
+                      d_pitch, accumulate):
+        """bn_dgrad with the product a stride-1 same-size transposed convolution (geometry g: dy is the small side, a channel
+        window dy_pitch / dy_valid; x / dx the large side with `pitch` channels per pixel)."""
+        cd = self._cd(dy)
+        rows = n * g.Hl * g.Wl
+        prod = torch.empty(rows * g.Cb, dtype=dy.dtype)
+        self.launches -= 1                                    # one launch on the device
+        self.conv_up(dy, Wu, prod, n, g, None, 0, None, 1, 0, 0.0, views=(dy_pitch, dy_valid, 0, 0) if (dy_pitch or dy_valid) else None)
+        prod = prod.view(rows, g.Cb)[:, :C].to(cd)
+        gm, b = gamma.detach().to(cd), beta.detach().to(cd)
+        mu, sig = mean.detach().to(cd), torch.sqrt(var.detach().to(cd) + eps)
+        self._bn_bwd_tail(prod, dx, x, rows, C, pitch, gm, b, mu, sig, dgamma, dbeta, d_out, d_pitch, accumulate, cd)
