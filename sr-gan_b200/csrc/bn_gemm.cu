@@ -65,6 +65,9 @@ struct BnDgradParams {
                                   // tangent block's BatchNorm-scale gradient
     int accumulate;               // dx += (else dx =)
     int m_tiles, total_tiles, stages;
+    int resb;                     // 1: the weight tile of the current channel tile (K/64 x 16 KB) stays RESIDENT in shared memory
+                                  // and is re-loaded only when the CTA's tile range moves on to the next channel tile; the ring
+                                  // stages then carry the dy tile only (GEMM variant, K <= 256)
     // CONV variant: dy is an NHWC activation [n, H, W, .] and the product a stride-1 transposed convolution over R x S taps
     // (the data gradient of a same-size convolution); a row tile is a TW x TH x TN patch (powers of two) of pixels x samples
     int n, H, W, R, S, pad, Cin;  // Cin = channels of dy per tap as the weight matrix counts them (a multiple of 64)
@@ -79,14 +82,20 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
     __shared__ __align__(8) uint64_t empty_bar[8];
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ __align__(8) uint64_t b_full_bar, b_empty_bar;
     __shared__ uint32_t tmem_slot;
 
     constexpr int BN = BD_BN;
     constexpr int TMEM_COLS = 2 * BN;
-    const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    constexpr int B_TILE_BYTES = BN * KCH * 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stages = p.stages;
     const int nch = p.K / KCH;
+    const bool resb = !CONV && p.resb != 0;
+    // shared memory: [resident weight tiles] [ring] [epilogue buffers]
+    const uint32_t b_res = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t tiles = b_res + (resb ? (uint32_t)(nch * B_TILE_BYTES) : 0u);
+    const int stage_bytes = resb ? A_STAGE_BYTES : BD_STAGE_BYTES;
     // a CTA walks a contiguous range of the tile list (row tiles fastest): its consecutive tiles cover the same channels
     const int tile_begin = (int)((long long)p.total_tiles * blockIdx.x / gridDim.x);
     const int tile_end = (int)((long long)p.total_tiles * (blockIdx.x + 1) / gridDim.x);
@@ -94,6 +103,8 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tmem_full_bar[b]), 1); mbar_init(smem_u32(&tmem_empty_bar[b]), 8); }
+        mbar_init(smem_u32(&b_full_bar), 1);
+        mbar_init(smem_u32(&b_empty_bar), 1);
         fence_barrier_init();
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
@@ -107,10 +118,18 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
     if (warp == 0) {
         // ================= TMA producer =================
         if (elect_one()) {
-            int s = 0;
-            uint32_t ph = 0;
+            int s = 0, ny_res = -1;
+            uint32_t ph = 0, bph = 0;
             for (int tile = tile_begin; tile < tile_end; ++tile) {
                 const int mt = tile % p.m_tiles, ny = tile / p.m_tiles;
+                if (resb && ny != ny_res) {
+                    // next channel tile: its weights replace the resident ones once every MMA that reads those has completed
+                    if (ny_res >= 0) { mbar_wait(smem_u32(&b_empty_bar), bph); bph ^= 1; }
+                    const uint32_t bb = smem_u32(&b_full_bar);
+                    mbar_expect_tx(bb, (uint32_t)(nch * B_TILE_BYTES));
+                    for (int ch = 0; ch < nch; ++ch) tma_load_2d(b_res + (uint32_t)(ch * B_TILE_BYTES), &tmB, bb, ch * KCH, ny * BN);
+                    ny_res = ny;
+                }
                 if constexpr (CONV) {
                     const int w0 = (mt % p.tiles_w) * p.TW, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.TH;
                     const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.TN;
@@ -130,10 +149,10 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
                     for (int ch = 0; ch < nch; ++ch) {
                         mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
                         const uint32_t fb = smem_u32(&full_bar[s]);
-                        mbar_expect_tx(fb, BD_STAGE_BYTES);
-                        const uint32_t dst = tiles + s * BD_STAGE_BYTES;
+                        mbar_expect_tx(fb, (uint32_t)stage_bytes);
+                        const uint32_t dst = tiles + s * stage_bytes;
                         tma_load_2d(dst, &tmA, fb, ch * KCH, mt * TILE_M);
-                        tma_load_2d(dst + A_STAGE_BYTES, &tmB, fb, ch * KCH, ny * BN);
+                        if (!resb) tma_load_2d(dst + A_STAGE_BYTES, &tmB, fb, ch * KCH, ny * BN);
                         if (++s == stages) { s = 0; ph ^= 1; }
                     }
                 }
@@ -144,20 +163,22 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc(TILE_M, BN, 0, 0);
             const uint64_t desc0 = make_desc(0, 16, 1024);
-            int s = 0, tl = 0;
-            uint32_t ph = 0;
+            int s = 0, tl = 0, ny_res = -1;
+            uint32_t ph = 0, bfph = 0;
             for (int tile = tile_begin; tile < tile_end; ++tile, ++tl) {
                 const int buf = tl & 1;
                 const uint32_t bph = (tl >> 1) & 1;
+                const int ny = tile / p.m_tiles;
                 mbar_wait(smem_u32(&tmem_empty_bar[buf]), bph ^ 1);
+                if (resb && ny != ny_res) { mbar_wait(smem_u32(&b_full_bar), bfph); bfph ^= 1; ny_res = ny; }
                 tc_fence_after();
                 const uint32_t acc = tmem_base + buf * BN;
                 for (int k_it = 0; k_it < nch; ++k_it) {
                     mbar_wait(smem_u32(&full_bar[s]), ph);
                     tc_fence_after();
-                    const uint32_t a_s = tiles + s * BD_STAGE_BYTES;
+                    const uint32_t a_s = tiles + s * stage_bytes;
                     const uint64_t ad0 = desc0 + (uint64_t)(a_s >> 4);
-                    const uint64_t bd0 = desc0 + (uint64_t)((a_s + A_STAGE_BYTES) >> 4);
+                    const uint64_t bd0 = desc0 + (uint64_t)((resb ? b_res + (uint32_t)(k_it * B_TILE_BYTES) : a_s + A_STAGE_BYTES) >> 4);
 #pragma unroll
                     for (int k = 0; k < KCH / 16; ++k)
                         umma_f16(acc, ad0 + (uint64_t)(k * 2), bd0 + (uint64_t)(k * 2), idesc, (k_it > 0 || k > 0) ? 1u : 0u);
@@ -165,6 +186,8 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
                 umma_commit(smem_u32(&tmem_full_bar[buf]));
+                // last tile of this channel tile in the CTA's range: the resident weights may be replaced when these MMAs are done
+                if (resb && tile + 1 < tile_end && (tile + 1) / p.m_tiles != ny) umma_commit(smem_u32(&b_empty_bar));
             }
         }
     } else {
@@ -174,18 +197,51 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
         const int half = ew >> 2;                // which half of the tile's 32-column chunks
         const int t_unit = lane & 3, t_row = lane >> 2;       // transposed role: 16-byte unit t_unit of rows 8*it + t_row
         const int te = threadIdx.x - 64;         // 0..255 among the epilogue threads
-        const uint32_t after_ring = (uint32_t)stages * BD_STAGE_BYTES;
+        const uint32_t after_ring = (uint32_t)(stages * stage_bytes);
         const uint32_t stg = tiles + after_ring + (uint32_t)ew * EPI_STG_BYTES;
         const uint32_t zone = tiles + after_ring + 8u * EPI_STG_BYTES + (uint32_t)ew * BD_ZONE_WARP + (uint32_t)lane * 16u;
-        float* tab = reinterpret_cast<float*>(smem_raw + (tiles - smem_u32(smem_raw)) + after_ring + 8u * EPI_STG_BYTES + 8u * BD_ZONE_WARP);
-        float* t_s = tab;                        // gamma / sigma
-        float* t_t = tab + p.Cpad;               // beta - mean * gamma / sigma
+        // Per-channel tables, all bf16 so that the hot loop stays in packed arithmetic (the epilogue is bound by the number of
+        // instructions its 8 warps execute, not by bytes):
+        //   t_sg = sign of the scale s (+-1), t_T = the ReLU threshold in u = x * sign: bn(x) rounded to bf16 > 0  <=>  u >= T,
+        //          found EXACTLY per channel below (the predicate is monotone in u), so the mask is still the stored
+        //          activation's sign bit for bit but costs a packed multiply + compare per channel pair;
+        //   t_sb = s rounded to bf16: dx (+)= d * s as one packed fma per channel pair (the increment carries a 2^-9 relative
+        //          rounding of s, below the rounding of the bf16 result itself).
+        uint16_t* tab = reinterpret_cast<uint16_t*>(smem_raw + (tiles - smem_u32(smem_raw)) + after_ring + 8u * EPI_STG_BYTES + 8u * BD_ZONE_WARP);
+        uint16_t* t_T = tab;
+        uint16_t* t_sg = tab + p.Cpad;
+        uint16_t* t_sb = tab + 2 * p.Cpad;
         const bool grads = p.dgamma != nullptr;
         const bool accum = p.accumulate != 0;
         for (int c = te; c < p.Cpad; c += 256) {
-            float s = 0.f, t = 0.f;
-            if (c < p.C) { s = bn_scale_f(__ldg(p.gamma + c), __ldg(p.var + c), p.eps); t = bn_shift(__ldg(p.beta + c), __ldg(p.mean + c), s); }
-            t_s[c] = s; t_t[c] = t;
+            uint16_t Tb = 0x7F80, sgb = 0x3F80, sbb = 0;          // +inf: never active; +1; 0
+            if (c < p.C) {
+                const float s = bn_scale_f(__ldg(p.gamma + c), __ldg(p.var + c), p.eps);
+                const float t = bn_shift(__ldg(p.beta + c), __ldg(p.mean + c), s);
+                sbb = __bfloat16_as_ushort(__float2bfloat16_rn(s));
+                auto val = [](int m) { return __bfloat162float(__ushort_as_bfloat16((uint16_t)(m < 0 ? (0x8000 | (-m)) : m))); };
+                const float sg = s < 0.f ? -1.f : 1.f;
+                auto pred = [&](int m) { return __bfloat162float(__float2bfloat16_rn(bn_apply(val(m) * sg, s, t))) > 0.f; };
+                if (s == 0.f) {
+                    Tb = t > 0.f && __bfloat162float(__float2bfloat16_rn(t)) > 0.f ? 0xFF80 : 0x7F80;            // -inf / +inf
+                } else {
+                    if (s < 0.f) sgb = 0xBF80;
+                    const float u0 = -t / fabsf(s);
+                    int m;                         // bf16 values in monotone integer order: m = +-(magnitude bits)
+                    if (!(u0 == u0)) m = 0x7F80;
+                    else {
+                        const uint16_t b = __bfloat16_as_ushort(__float2bfloat16_rn(u0));
+                        m = (b & 0x8000) ? -(int)(b & 0x7FFF) : (int)(b & 0x7FFF);
+                        if (m > 0x7F80) m = 0x7F80;
+                        if (m < -0x7F80) m = -0x7F80;
+                    }
+                    for (int i = 0; i < 64 && m < 0x7F80 && !pred(m); ++i) ++m;
+                    for (int i = 0; i < 64 && m > -0x7F80 && pred(m - 1); ++i) --m;
+                    if (!pred(m)) m = 0x7F80;
+                    Tb = (uint16_t)(m < 0 ? (0x8000 | (-m)) : m);
+                }
+            }
+            t_T[c] = Tb; t_sg[c] = sgb; t_sb[c] = sbb;
         }
         epi_bar_sync();
 
@@ -196,7 +252,7 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
         // outstanding at any moment (Little: 44 GB/s per SM x ~1.5 us).
         // Geometry of a tile for this lane: element offset of slot 0, rows left below the lane's first row, channel validity.
         // (pix[it] = index of the pixel row that the lane's slot `it` belongs to, ok = bit it set when that row exists)
-        struct Geo { int pix[4]; int ok; int c0; };
+        struct Geo { long long off[4]; int pix[4]; int ok; int c0; };     // off = element offset of (pixel row, channel c0) in x / dx
         auto geo = [&](int mt, int ny) {
             Geo g;
             g.ok = 0;
@@ -218,12 +274,14 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
                     if (g.pix[it] < p.rows) g.ok |= 1 << it;
                 }
             }
+#pragma unroll
+            for (int it = 0; it < 4; ++it) g.off[it] = (long long)g.pix[it] * p.pitch + g.c0;
             return g;
         };
         auto issue = [&](const Geo& g, bool live_tile, int k) {
             const int jj = k >> 2, it = k & 3;
             const bool ok = live_tile && ((g.ok >> it) & 1) && g.c0 + jj * 64 < p.C;
-            const long long o = ok ? (long long)g.pix[it] * p.pitch + g.c0 + jj * 64 : 0;
+            const long long o = ok ? g.off[it] + jj * 64 : 0;
             cp_async16(zone + (uint32_t)(k * 1024), p.x + o, ok ? 16u : 0u);
             if (accum) cp_async16(zone + (uint32_t)(k * 1024 + 512), p.dx + o, ok ? 16u : 0u);
             cp_async_commit();                   // always: the group count per slot stays fixed
@@ -303,19 +361,14 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
                 const int j = half + 2 * jj;
                 const bool live = ny * BN + j * 32 < p.C;   // warp-uniform: chunks beyond the last channel (partial last N tile) carry no data
                 const bool cok = gc.c0 + jj * 64 < p.C;
-                float s8[8], t8[8];
+                uint4 T8 = make_uint4(0u, 0u, 0u, 0u), sg8 = T8, sb8 = T8;
                 if (live) {
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + j * 32, v);
                     const int ct = cok ? gc.c0 + jj * 64 : 0;
-                    const float4* ps = reinterpret_cast<const float4*>(t_s + ct);
-                    const float4* pt = reinterpret_cast<const float4*>(t_t + ct);
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const float4 a = ps[h], b = pt[h];
-                        s8[4 * h] = a.x; s8[4 * h + 1] = a.y; s8[4 * h + 2] = a.z; s8[4 * h + 3] = a.w;
-                        t8[4 * h] = b.x; t8[4 * h + 1] = b.y; t8[4 * h + 2] = b.z; t8[4 * h + 3] = b.w;
-                    }
+                    T8 = *reinterpret_cast<const uint4*>(t_T + ct);
+                    sg8 = *reinterpret_cast<const uint4*>(t_sg + ct);
+                    sb8 = *reinterpret_cast<const uint4*>(t_sb + ct);
                     tmem_ld_wait();
                     // round to bf16 (what the unfused data-gradient kernel stores) and transpose: row-per-lane -> 8 channels x 4 rows
 #pragma unroll
@@ -338,32 +391,32 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
                     if (live) {
                         uint4 dr = lds128(stg_addr(stg, 8 * it + t_row, t_unit));
                         const uint4 xr = lds128(zone + (uint32_t)(k * 1024));
-                        float xv[8], o[8], d[8];
-                        unpack8(xr, xv);
-                        if (accum) {
-                            const uint4 cr = lds128(zone + (uint32_t)(k * 1024 + 512));
-                            unpack8(cr, o);
-                        } else {
+                        uint4 orw = make_uint4(0u, 0u, 0u, 0u);
+                        if (accum) orw = lds128(zone + (uint32_t)(k * 1024 + 512));
+                        // ReLU mask ANDed into the packed delta, then dx (+)= d * s: packed bf16 pairs throughout
+                        {
+                            uint32_t* dw = reinterpret_cast<uint32_t*>(&dr);
+                            const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(&xr);
+                            const __nv_bfloat162* T2 = reinterpret_cast<const __nv_bfloat162*>(&T8);
+                            const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&sg8);
+                            const __nv_bfloat162* s2 = reinterpret_cast<const __nv_bfloat162*>(&sb8);
+                            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&orw);
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) o[e] = 0.f;
+                            for (int h = 0; h < 4; ++h) {
+                                dw[h] &= __hge2_mask(__hmul2(x2[h], g2[h]), T2[h]);
+                                const __nv_bfloat162 d2 = *reinterpret_cast<const __nv_bfloat162*>(&dw[h]);
+                                o2[h] = accum ? __hfma2(d2, s2[h], o2[h]) : __hmul2(d2, s2[h]);
+                            }
                         }
-                        // ReLU mask: bn(x) rounded to bf16 > 0 -- exactly the stored activation's sign -- ANDed into the packed delta
-                        uint32_t* dw = reinterpret_cast<uint32_t*>(&dr);
-#pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            const __nv_bfloat162 pre = __floats2bfloat162_rn(bn_apply(xv[2 * h], s8[2 * h], t8[2 * h]),
-                                                                             bn_apply(xv[2 * h + 1], s8[2 * h + 1], t8[2 * h + 1]));
-                            dw[h] &= __hgt2_mask(pre, zero2);
-                        }
-                        unpack8(dr, d);
                         if (grads) {
+                            float xv[8], d[8];
+                            unpack8(xr, xv);
+                            unpack8(dr, d);
 #pragma unroll
                             for (int e = 0; e < 8; ++e) { acc[jj][e] = fmaf(d[e], xv[e], acc[jj][e]); acc[jj][8 + e] += d[e]; }
                         }
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) o[e] = fmaf(d[e], s8[e], o[e]);
                         if (cok && ((gc.ok >> it) & 1)) {
-                            *reinterpret_cast<uint4*>(p.dx + (long long)gc.pix[it] * p.pitch + gc.c0 + jj * 64) = pack8(o);
+                            *reinterpret_cast<uint4*>(p.dx + gc.off[it] + jj * 64) = orw;
                             if (p.d_out != nullptr)
                                 *reinterpret_cast<uint4*>(p.d_out + (long long)gc.pix[it] * p.d_pitch + gc.c0 + jj * 64) = dr;
                         }
@@ -927,12 +980,16 @@ int bn_dgrad(const void* dy, const void* Wu, void* dx, const void* x, long long 
     const long long n_tiles = (C + BD_BN - 1) / BD_BN;
     if (m_tiles * n_tiles > 0x7fffffffLL) return 0;
     p.m_tiles = (int)m_tiles; p.total_tiles = (int)(m_tiles * n_tiles);
-    const int fixed = 8 * EPI_STG_BYTES + 8 * BD_ZONE_WARP + 2 * p.Cpad * 4 + 1024;
-    int stages = (226 * 1024 - fixed) / BD_STAGE_BYTES;
+    const int fixed = 8 * EPI_STG_BYTES + 8 * BD_ZONE_WARP + 3 * p.Cpad * 2 + 1024;
+    static const bool resb_on = [] { const char* e = getenv("SRGAN_NO_RESIDENT_B"); return !(e && e[0] == '1'); }();
+    p.resb = (resb_on && K <= 256) ? 1 : 0;
+    const int b_bytes = p.resb ? (K / KCH) * BD_BN * KCH * 2 : 0;
+    const int stage_bytes = p.resb ? A_STAGE_BYTES : BD_STAGE_BYTES;
+    int stages = (226 * 1024 - fixed - b_bytes) / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) return 0;
     p.stages = stages;
-    const size_t smem = (size_t)stages * BD_STAGE_BYTES + fixed;
+    const size_t smem = (size_t)stages * stage_bytes + b_bytes + fixed;
     CUtensorMap tmA, tmB;
     int rc = encode_mat(&tmA, dy, rows, K, TILE_M);
     if (rc) return rc;
@@ -979,8 +1036,8 @@ int bn_conv_dgrad(const void* dy, int dy_pitch, int dy_valid, const void* Wu, vo
     p.gamma = gamma; p.beta = beta; p.mean = mean; p.var = var; p.eps = eps;
     p.dgamma = dgamma; p.dbeta = dbeta; p.accumulate = accumulate;
     p.d_out = (bf16*)d_out; p.d_pitch = d_pitch;
-    p.m_tiles = (int)m_tiles; p.total_tiles = (int)(m_tiles * n_tiles);
-    const int fixed = 8 * EPI_STG_BYTES + 8 * BD_ZONE_WARP + 2 * p.Cpad * 4 + 1024;
+    p.m_tiles = (int)m_tiles; p.total_tiles = (int)(m_tiles * n_tiles); p.resb = 0;
+    const int fixed = 8 * EPI_STG_BYTES + 8 * BD_ZONE_WARP + 3 * p.Cpad * 2 + 1024;
     int stages = (226 * 1024 - fixed) / BD_STAGE_BYTES;
     if (stages > 8) stages = 8;
     if (stages < 2) return 0;

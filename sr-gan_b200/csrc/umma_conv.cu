@@ -719,6 +719,10 @@ int launch_wgrad(const CUtensorMap& tmS, const CUtensorMap& tmL, UmmaWgradParams
 
 }  // namespace
 
+// flat3x3.cu
+int flat3x3_conv(const void* src, const void* Wd, void* out, int n, const srgan_geom* g, int in_pitch, int in_valid,
+                 int out_pitch, int out_valid, cudaStream_t st);
+
 // returns 1 = launched on the tensor cores, 0 = shape not eligible (caller uses the SIMT kernel), <0 = error
 int umma_conv(int mode, const void* src, const void* W, void* out, int n, const srgan_geom* g, const float* bias,
               int bias_mod, const void* href, int epi, int act, float slope, const srgan_views* vw, cudaStream_t st) {
@@ -734,6 +738,11 @@ int umma_conv(int mode, const void* src, const void* W, void* out, int n, const 
         if (in_valid > Cin || out_valid > Cout || (in_pitch > 0 && in_pitch < (in_valid > 0 ? in_valid : Cin)) || out_pitch < out_valid) return 0;
     }
     if (Cin % KCH != 0) return 0;
+    // 3x3 / stride 1 / same size with few output channels and a plain epilogue (dense-layer conv2): every input pixel once
+    if (mode == 0 && bias == nullptr && (epi == SRGAN_EPI_BIAS_ACT ? act == SRGAN_ACT_NONE : (href == nullptr || act == SRGAN_ACT_NONE))) {
+        const int took = flat3x3_conv(src, W, out, n, g, in_pitch, in_valid, out_pitch, out_valid, st);
+        if (took != 0) return took;
+    }
     int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 0));
     if (BN == 0) return 0;
     // Cout = 64 (mod 128) with three or more 64-wide tiles (the DenseNet trunk's 1x1 data gradients: every second concat
