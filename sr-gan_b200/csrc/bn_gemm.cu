@@ -43,6 +43,11 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }     // the 8 epilogue warps
 
+int bn_packed_scale() {
+    static const int v = [] { const char* e = getenv("SRGAN_BN_PACKED_SCALE"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
 constexpr int BD_THREADS = 320;                  // warp 0 TMA, warp 1 MMA + TMEM, warps 2..9 epilogue
 constexpr int BD_BN = 128;                       // output channels per tile
 constexpr int BD_STAGE_BYTES = A_STAGE_BYTES + BD_BN * KCH * 2;
@@ -65,6 +70,10 @@ struct BnDgradParams {
                                   // tangent block's BatchNorm-scale gradient
     int accumulate;               // dx += (else dx =)
     int m_tiles, total_tiles, stages;
+    int packed_s;                 // 0 (default): dx (+)= d * s with the fp32 scale, bit-identical to the unfused affine backward;
+                                  // 1 (SRGAN_BN_PACKED_SCALE=1): one packed bf16 fma per channel pair with s rounded to bf16 --
+                                  // 2 % faster on the crowd step, but the gradient-penalty error of the reduced crowd case
+                                  // grows from 2.1e-2 to 3.4e-2 (profiles/r2_bf16_parity_errors.txt)
     int resb;                     // 1: the weight tile of the current channel tile (K/64 x 16 KB) stays RESIDENT in shared memory
                                   // and is re-loaded only when the CTA's tile range moves on to the next channel tile; the ring
                                   // stages then carry the dy tile only (GEMM variant, K <= 256)
@@ -205,12 +214,12 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
         //   t_sg = sign of the scale s (+-1), t_T = the ReLU threshold in u = x * sign: bn(x) rounded to bf16 > 0  <=>  u >= T,
         //          found EXACTLY per channel below (the predicate is monotone in u), so the mask is still the stored
         //          activation's sign bit for bit but costs a packed multiply + compare per channel pair;
-        //   t_sb = s rounded to bf16: dx (+)= d * s as one packed fma per channel pair (the increment carries a 2^-9 relative
-        //          rounding of s, below the rounding of the bf16 result itself).
+        //   t_sb = s rounded to bf16 (packed_s: dx (+)= d * s as one packed fma per channel pair); t_sf = s in fp32 (default).
         uint16_t* tab = reinterpret_cast<uint16_t*>(smem_raw + (tiles - smem_u32(smem_raw)) + after_ring + 8u * EPI_STG_BYTES + 8u * BD_ZONE_WARP);
         uint16_t* t_T = tab;
         uint16_t* t_sg = tab + p.Cpad;
         uint16_t* t_sb = tab + 2 * p.Cpad;
+        float* t_sf = reinterpret_cast<float*>(tab + 3 * p.Cpad);      // s in fp32
         const bool grads = p.dgamma != nullptr;
         const bool accum = p.accumulate != 0;
         for (int c = te; c < p.Cpad; c += 256) {
@@ -242,6 +251,7 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
                 }
             }
             t_T[c] = Tb; t_sg[c] = sgb; t_sb[c] = sbb;
+            t_sf[c] = c < p.C ? bn_scale_f(__ldg(p.gamma + c), __ldg(p.var + c), p.eps) : 0.f;
         }
         epi_bar_sync();
 
@@ -362,13 +372,18 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
                 const bool live = ny * BN + j * 32 < p.C;   // warp-uniform: chunks beyond the last channel (partial last N tile) carry no data
                 const bool cok = gc.c0 + jj * 64 < p.C;
                 uint4 T8 = make_uint4(0u, 0u, 0u, 0u), sg8 = T8, sb8 = T8;
+                float s8[8];
                 if (live) {
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + j * 32, v);
                     const int ct = cok ? gc.c0 + jj * 64 : 0;
                     T8 = *reinterpret_cast<const uint4*>(t_T + ct);
                     sg8 = *reinterpret_cast<const uint4*>(t_sg + ct);
-                    sb8 = *reinterpret_cast<const uint4*>(t_sb + ct);
+                    if (p.packed_s) sb8 = *reinterpret_cast<const uint4*>(t_sb + ct);
+                    else {
+                        const float4 a = *reinterpret_cast<const float4*>(t_sf + ct), b = *reinterpret_cast<const float4*>(t_sf + ct + 4);
+                        s8[0] = a.x; s8[1] = a.y; s8[2] = a.z; s8[3] = a.w; s8[4] = b.x; s8[5] = b.y; s8[6] = b.z; s8[7] = b.w;
+                    }
                     tmem_ld_wait();
                     // round to bf16 (what the unfused data-gradient kernel stores) and transpose: row-per-lane -> 8 channels x 4 rows
 #pragma unroll
@@ -402,18 +417,31 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
                             const __nv_bfloat162* s2 = reinterpret_cast<const __nv_bfloat162*>(&sb8);
                             __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&orw);
 #pragma unroll
-                            for (int h = 0; h < 4; ++h) {
-                                dw[h] &= __hge2_mask(__hmul2(x2[h], g2[h]), T2[h]);
-                                const __nv_bfloat162 d2 = *reinterpret_cast<const __nv_bfloat162*>(&dw[h]);
-                                o2[h] = accum ? __hfma2(d2, s2[h], o2[h]) : __hmul2(d2, s2[h]);
+                            for (int h = 0; h < 4; ++h) dw[h] &= __hge2_mask(__hmul2(x2[h], g2[h]), T2[h]);
+                            if (p.packed_s) {
+#pragma unroll
+                                for (int h = 0; h < 4; ++h) {
+                                    const __nv_bfloat162 d2 = *reinterpret_cast<const __nv_bfloat162*>(&dw[h]);
+                                    o2[h] = accum ? __hfma2(d2, s2[h], o2[h]) : __hmul2(d2, s2[h]);
+                                }
                             }
                         }
-                        if (grads) {
-                            float xv[8], d[8];
-                            unpack8(xr, xv);
+                        if (grads || !p.packed_s) {
+                            float d[8];
                             unpack8(dr, d);
+                            if (!p.packed_s) {
+                                float o[8];
+                                unpack8(orw, o);
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) { acc[jj][e] = fmaf(d[e], xv[e], acc[jj][e]); acc[jj][8 + e] += d[e]; }
+                                for (int e = 0; e < 8; ++e) o[e] = fmaf(d[e], s8[e], o[e]);
+                                orw = pack8(o);
+                            }
+                            if (grads) {
+                                float xv[8];
+                                unpack8(xr, xv);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) { acc[jj][e] = fmaf(d[e], xv[e], acc[jj][e]); acc[jj][8 + e] += d[e]; }
+                            }
                         }
                         if (cok && ((gc.ok >> it) & 1)) {
                             *reinterpret_cast<uint4*>(p.dx + gc.off[it] + jj * 64) = orw;
@@ -980,7 +1008,8 @@ int bn_dgrad(const void* dy, const void* Wu, void* dx, const void* x, long long 
     const long long n_tiles = (C + BD_BN - 1) / BD_BN;
     if (m_tiles * n_tiles > 0x7fffffffLL) return 0;
     p.m_tiles = (int)m_tiles; p.total_tiles = (int)(m_tiles * n_tiles);
-    const int fixed = 8 * EPI_STG_BYTES + 8 * BD_ZONE_WARP + 3 * p.Cpad * 2 + 1024;
+    p.packed_s = bn_packed_scale();
+    const int fixed = 8 * EPI_STG_BYTES + 8 * BD_ZONE_WARP + 3 * p.Cpad * 2 + p.Cpad * 4 + 1024;
     static const bool resb_on = [] { const char* e = getenv("SRGAN_NO_RESIDENT_B"); return !(e && e[0] == '1'); }();
     p.resb = (resb_on && K <= 256) ? 1 : 0;
     const int b_bytes = p.resb ? (K / KCH) * BD_BN * KCH * 2 : 0;
@@ -1037,7 +1066,8 @@ int bn_conv_dgrad(const void* dy, int dy_pitch, int dy_valid, const void* Wu, vo
     p.dgamma = dgamma; p.dbeta = dbeta; p.accumulate = accumulate;
     p.d_out = (bf16*)d_out; p.d_pitch = d_pitch;
     p.m_tiles = (int)m_tiles; p.total_tiles = (int)(m_tiles * n_tiles); p.resb = 0;
-    const int fixed = 8 * EPI_STG_BYTES + 8 * BD_ZONE_WARP + 3 * p.Cpad * 2 + 1024;
+    p.packed_s = bn_packed_scale();
+    const int fixed = 8 * EPI_STG_BYTES + 8 * BD_ZONE_WARP + 3 * p.Cpad * 2 + p.Cpad * 4 + 1024;
     int stages = (226 * 1024 - fixed) / BD_STAGE_BYTES;
     if (stages > 8) stages = 8;
     if (stages < 2) return 0;
