@@ -328,8 +328,9 @@ def probe_selector(name, eng, B):
                 f'D layer2.0 forward conv (64->128 k4 s2) over {4 * B} samples (umma_conv_persistent_kernel)')
     if name == 'crowd':
         return (lambda role, st, l, n: role in ('dgrad', 'dgrad_bn') and l.name.endswith('.conv1'),
-                'DenseNet trunk 1x1 data-gradient GEMMs (every dense layer conv1, all passes; umma_conv_persistent_kernel): '
-                '[pixels x 128] x [128 x C] with the BatchNorm + ReLU backward of norm1 in the epilogue (bn_dgrad_kernel)')
+                'DenseNet trunk 1x1 data-gradient GEMMs with the BatchNorm + ReLU backward of norm1 in the epilogue '
+                '(bn_dgrad_kernel<false>, csrc/bn_gemm.cu; every dense layer / transition conv1, all passes): '
+                '[pixels x 128] x [128 x C], algorithmic bytes rows x (128 + 3 C) x 2')
     return None, None
 
 

@@ -295,8 +295,11 @@ class StepRunner:
         # enqueued on its own stream and overlaps the GAN step that follows it; gan_step joins the two streams at its end,
         # so everything is ordered on the caller's stream again when a step pair returns.  The crowd step is thousands of
         # launches that under-fill the GPU (7x7 / 14x14 stages): two independent chains in flight fill the gaps.
-        self.overlap_dnn = (comm is None and bool(getattr(settings, 'overlap_dnn_step', True))
-                            and os.environ.get('SRGAN_NO_OVERLAP', '0') != '1')
+        # Multi-rank as well: the DNN step's gradient all-reduce (a deferred group on the side stream) is issued before the GAN
+        # step's collectives on every rank, and NCCL orders the collectives of one communicator across streams, so the GAN
+        # step's first feature-sum all-reduce (after its D forward) waits for the DNN backward at most.
+        self.overlap_dnn = (bool(getattr(settings, 'overlap_dnn_step', True)) and os.environ.get('SRGAN_NO_OVERLAP', '0') != '1'
+                            and (comm is None or os.environ.get('SRGAN_NO_OVERLAP_MULTI', '0') != '1'))
         self._dnn_stream, self._dnn_done = None, None
         # coefficient application: one persistent cooperative kernel per step method (csrc/coef_step.cu) instead of
         # ~150 generic launches; single rank only (the feature sums are combined inside the kernel)
