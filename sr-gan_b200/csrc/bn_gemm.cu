@@ -58,7 +58,7 @@ struct BnDgradParams {
     long long rows;               // GEMM rows (pixels x samples)
     int K;                        // reduction length = channels of dy (a multiple of 64)
     int C;                        // output channels that exist (the BatchNorm's channels; a multiple of 8)
-    int Cpad;                     // C rounded up to 32: length of the shared-memory tables
+    int Cpad;                     // C rounded up to 32
     int pitch;                    // elements between consecutive rows of x / dx (the concat buffer's channel count)
     const bf16* x;                // BatchNorm input (the concat buffer), rows aligned with the GEMM rows
     bf16* dx;                     // its delta
@@ -216,13 +216,19 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
         //          activation's sign bit for bit but costs a packed multiply + compare per channel pair;
         //   t_sb = s rounded to bf16 (packed_s: dx (+)= d * s as one packed fma per channel pair); t_sf = s in fp32 (default).
         uint16_t* tab = reinterpret_cast<uint16_t*>(smem_raw + (tiles - smem_u32(smem_raw)) + after_ring + 8u * EPI_STG_BYTES + 8u * BD_ZONE_WARP);
+        // The tables hold the BN channels of the CURRENT channel tile only (a CTA's tile range is contiguous, row tiles fastest:
+        // it crosses a channel-tile boundary a few times per launch at most) and are rebuilt there by the first 128 epilogue
+        // threads -- filling them for all C channels up front cost 3-4 us of every launch (7 dependent parameter loads per thread).
         uint16_t* t_T = tab;
-        uint16_t* t_sg = tab + p.Cpad;
-        uint16_t* t_sb = tab + 2 * p.Cpad;
-        float* t_sf = reinterpret_cast<float*>(tab + 3 * p.Cpad);      // s in fp32
+        uint16_t* t_sg = tab + BN;
+        uint16_t* t_sb = tab + 2 * BN;
+        float* t_sf = reinterpret_cast<float*>(tab + 3 * BN);          // s in fp32
         const bool grads = p.dgamma != nullptr;
         const bool accum = p.accumulate != 0;
-        for (int c = te; c < p.Cpad; c += 256) {
+        auto fill_tables = [&](int ny_t) {
+            epi_bar_sync();                      // nobody still reads the previous channel tile's entries
+            if (te < BN) {
+            const int cl = te, c = ny_t * BN + te;
             uint16_t Tb = 0x7F80, sgb = 0x3F80, sbb = 0;          // +inf: never active; +1; 0
             if (c < p.C) {
                 const float s = bn_scale_f(__ldg(p.gamma + c), __ldg(p.var + c), p.eps);
@@ -250,10 +256,11 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
                     Tb = (uint16_t)(m < 0 ? (0x8000 | (-m)) : m);
                 }
             }
-            t_T[c] = Tb; t_sg[c] = sgb; t_sb[c] = sbb;
-            t_sf[c] = c < p.C ? bn_scale_f(__ldg(p.gamma + c), __ldg(p.var + c), p.eps) : 0.f;
-        }
-        epi_bar_sync();
+            t_T[cl] = Tb; t_sg[cl] = sgb; t_sb[cl] = sbb;
+            t_sf[cl] = c < p.C ? bn_scale_f(__ldg(p.gamma + c), __ldg(p.var + c), p.eps) : 0.f;
+            }
+            epi_bar_sync();
+        };
 
         // Per tile a lane touches 8 pieces ("slots" k = 4*jj + it: chunk half + 2*jj, rows 8*it + t_row of the warp's 32) of 16
         // bytes of cat and of dcat.  They travel through a lane-private ring of 8 landing slots per warp (32 lanes x 16
@@ -354,11 +361,11 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
                 for (int e = 0; e < 16; ++e) a[e] = 0.f;
             }
         };
-        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
-        int tl = 0;
+        int tl = 0, ny_tab = -1;
         for (int tile = tile_begin; tile < tile_end; ++tile, ++tl) {
             const int buf = tl & 1;
             const uint32_t bph = (tl >> 1) & 1;
+            if (ny != ny_tab) { fill_tables(ny); ny_tab = ny; }
             // the next tile of this CTA's range (row tiles fastest)
             int mt_n = mt + 1, ny_n = ny;
             if (mt_n == p.m_tiles) { mt_n = 0; ++ny_n; }
@@ -376,7 +383,7 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
                 if (live) {
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + j * 32, v);
-                    const int ct = cok ? gc.c0 + jj * 64 : 0;
+                    const int ct = cok ? gc.c0 + jj * 64 - ny * BN : 0;     // index within the channel tile
                     T8 = *reinterpret_cast<const uint4*>(t_T + ct);
                     sg8 = *reinterpret_cast<const uint4*>(t_sg + ct);
                     if (p.packed_s) sb8 = *reinterpret_cast<const uint4*>(t_sb + ct);
@@ -540,6 +547,7 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bn_conv_down_kernel(const __gri
     }
     if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS);
     // per-channel tables of the fused BatchNorm (channels >= C: scale = shift = 0, so the zero-filled K tail stays zero)
+#pragma unroll 4
     for (int c = threadIdx.x; c < p.Kpad; c += BF_THREADS) {
         float s = 0.f, t = 0.f;
         if (c < p.C) { s = bn_scale_f(__ldg(p.gamma + c), __ldg(p.var + c), p.eps); t = bn_shift(__ldg(p.beta + c), __ldg(p.mean + c), s); }
@@ -1009,7 +1017,7 @@ int bn_dgrad(const void* dy, const void* Wu, void* dx, const void* x, long long 
     if (m_tiles * n_tiles > 0x7fffffffLL) return 0;
     p.m_tiles = (int)m_tiles; p.total_tiles = (int)(m_tiles * n_tiles);
     p.packed_s = bn_packed_scale();
-    const int fixed = 8 * EPI_STG_BYTES + 8 * BD_ZONE_WARP + 3 * p.Cpad * 2 + p.Cpad * 4 + 1024;
+    const int fixed = 8 * EPI_STG_BYTES + 8 * BD_ZONE_WARP + 3 * BD_BN * 2 + BD_BN * 4 + 1024;
     static const bool resb_on = [] { const char* e = getenv("SRGAN_NO_RESIDENT_B"); return !(e && e[0] == '1'); }();
     p.resb = (resb_on && K <= 256) ? 1 : 0;
     const int b_bytes = p.resb ? (K / KCH) * BD_BN * KCH * 2 : 0;
@@ -1067,7 +1075,7 @@ int bn_conv_dgrad(const void* dy, int dy_pitch, int dy_valid, const void* Wu, vo
     p.d_out = (bf16*)d_out; p.d_pitch = d_pitch;
     p.m_tiles = (int)m_tiles; p.total_tiles = (int)(m_tiles * n_tiles); p.resb = 0;
     p.packed_s = bn_packed_scale();
-    const int fixed = 8 * EPI_STG_BYTES + 8 * BD_ZONE_WARP + 3 * p.Cpad * 2 + p.Cpad * 4 + 1024;
+    const int fixed = 8 * EPI_STG_BYTES + 8 * BD_ZONE_WARP + 3 * BD_BN * 2 + BD_BN * 4 + 1024;
     int stages = (226 * 1024 - fixed) / BD_STAGE_BYTES;
     if (stages > 8) stages = 8;
     if (stages < 2) return 0;
@@ -1105,12 +1113,13 @@ int bn_conv_down(const void* x, const void* Wd, void* out, long long rows, int K
     p.gamma2 = gamma2; p.beta2 = beta2; p.mean2 = mean2; p.var2 = var2; p.out2 = (bf16*)out2; p.C2 = C2;
     const long long sub = (rows + TILE_M - 1) / TILE_M;
     p.n_tiles = (Cout + BF_BN - 1) / BF_BN;
-    // 256-row CTA tiles share every weight tile between two sub-tiles, unless 128-row tiles finish in fewer rounds on 148 CTAs
+    // 256-row CTA tiles share every weight tile between two sub-tiles (measured: 10 % less time per sub-tile), unless 128-row
+    // tiles finish sooner because of the wave quantisation on 148 CTAs: time ~ rounds x rows per tile x (0.9 for 256 rows)
     int MT = 2;
     {
         const long long t1 = sub * p.n_tiles, t2 = ((sub + 1) / 2) * p.n_tiles;
         const long long r1 = (t1 + kNumSMs - 1) / kNumSMs, r2 = (t2 + kNumSMs - 1) / kNumSMs;
-        if (r1 < 2 * r2) MT = 1;
+        if (10 * r1 < 18 * r2) MT = 1;
         static const int dbg_mt = [] { const char* e = getenv("SRGAN_BF_MT"); return e ? atoi(e) : 0; }();
         if (dbg_mt == 1 || dbg_mt == 2) MT = dbg_mt;
     }
