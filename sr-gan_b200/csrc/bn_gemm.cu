@@ -41,17 +41,19 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
     for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
     return r;
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }     // the 8 epilogue warps
+constexpr int BD_EW = 8;                         // epilogue warps of bn_dgrad_kernel (16 = four per TMEM lane quarter was measured: no gain, 91 vs 90 us, and spills)
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(BD_EW * 32) : "memory"); }     // the epilogue warps
 
 int bn_packed_scale() {
     static const int v = [] { const char* e = getenv("SRGAN_BN_PACKED_SCALE"); return e ? atoi(e) : 0; }();
     return v;
 }
 
-constexpr int BD_THREADS = 320;                  // warp 0 TMA, warp 1 MMA + TMEM, warps 2..9 epilogue
+constexpr int BD_THREADS = 64 + BD_EW * 32;      // warp 0 TMA, warp 1 MMA + TMEM, warps 2.. epilogue
 constexpr int BD_BN = 128;                       // output channels per tile
 constexpr int BD_STAGE_BYTES = A_STAGE_BYTES + BD_BN * KCH * 2;
-constexpr int BD_NCH = BD_BN / 64;               // 32-column chunks per epilogue warp and tile
+constexpr int BD_CS = BD_EW / 4;                 // chunk stride: warp ew owns the 32-column chunks (ew >> 2) + BD_CS * jj
+constexpr int BD_NCH = BD_BN / 32 / BD_CS;       // 32-column chunks per epilogue warp and tile
 constexpr int BD_ZONE_WARP = BD_NCH * 2 * EPI_STG_BYTES;      // per warp: chunks x {cat, dcat} x (4 row groups x 32 lanes x 16 B)
 
 struct BnDgradParams {
@@ -81,6 +83,8 @@ struct BnDgradParams {
     // (the data gradient of a same-size convolution); a row tile is a TW x TH x TN patch (powers of two) of pixels x samples
     int n, H, W, R, S, pad, Cin;  // Cin = channels of dy per tap as the weight matrix counts them (a multiple of 64)
     int TW, TH, TN, lgTW, lgTH, tiles_w, tiles_h;
+    int k32;                      // CONV: at most 32 channels of dy exist per tap (a dense layer's growth): the stage holds 64-byte
+                                  // rows (SWIZZLE_64B boxes of 32 channels, two K steps) -- half the L2 -> SM bytes per tap
 };
 
 template <bool CONV>
@@ -104,14 +108,15 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
     // shared memory: [resident weight tiles] [ring] [epilogue buffers]
     const uint32_t b_res = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t tiles = b_res + (resb ? (uint32_t)(nch * B_TILE_BYTES) : 0u);
-    const int stage_bytes = resb ? A_STAGE_BYTES : BD_STAGE_BYTES;
+    const bool k32 = CONV && p.k32 != 0;
+    const int stage_bytes = resb ? A_STAGE_BYTES : (k32 ? BD_STAGE_BYTES / 2 : BD_STAGE_BYTES);
     // a CTA walks a contiguous range of the tile list (row tiles fastest): its consecutive tiles cover the same channels
     const int tile_begin = (int)((long long)p.total_tiles * blockIdx.x / gridDim.x);
     const int tile_end = (int)((long long)p.total_tiles * (blockIdx.x + 1) / gridDim.x);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tmem_full_bar[b]), 1); mbar_init(smem_u32(&tmem_empty_bar[b]), 8); }
+        for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&tmem_full_bar[b]), 1); mbar_init(smem_u32(&tmem_empty_bar[b]), BD_EW); }
         mbar_init(smem_u32(&b_full_bar), 1);
         mbar_init(smem_u32(&b_empty_bar), 1);
         fence_barrier_init();
@@ -148,10 +153,10 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
                             for (int ch = 0; ch < cpt; ++ch) {
                                 mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
                                 const uint32_t fb = smem_u32(&full_bar[s]);
-                                mbar_expect_tx(fb, BD_STAGE_BYTES);
-                                const uint32_t dst = tiles + s * BD_STAGE_BYTES;
+                                mbar_expect_tx(fb, (uint32_t)stage_bytes);
+                                const uint32_t dst = tiles + s * stage_bytes;
                                 tma_load_4d(dst, &tmA, fb, ch * KCH, w0 + p.pad - ts, h0 + p.pad - tr, n0);
-                                tma_load_2d(dst + A_STAGE_BYTES, &tmB, fb, (tr * p.S + ts) * p.Cin + ch * KCH, ny * BN);
+                                tma_load_2d(dst + (k32 ? A_STAGE_BYTES / 2 : A_STAGE_BYTES), &tmB, fb, (tr * p.S + ts) * p.Cin + ch * KCH, ny * BN);
                                 if (++s == stages) { s = 0; ph ^= 1; }
                             }
                 } else {
@@ -171,7 +176,9 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
         // ================= MMA issuer =================
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc(TILE_M, BN, 0, 0);
-            const uint64_t desc0 = make_desc(0, 16, 1024);
+            // 128-byte rows in 1024-byte swizzle atoms, or (k32) 64-byte rows in 512-byte atoms of SWIZZLE_64B
+            const uint64_t desc0 = k32 ? ((make_desc(0, 16, 512) & ~((uint64_t)7 << 61)) | ((uint64_t)4 << 61)) : make_desc(0, 16, 1024);
+            const int a_bytes = k32 ? A_STAGE_BYTES / 2 : A_STAGE_BYTES, ksteps = k32 ? 2 : KCH / 16;
             int s = 0, tl = 0, ny_res = -1;
             uint32_t ph = 0, bfph = 0;
             for (int tile = tile_begin; tile < tile_end; ++tile, ++tl) {
@@ -187,9 +194,9 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
                     tc_fence_after();
                     const uint32_t a_s = tiles + s * stage_bytes;
                     const uint64_t ad0 = desc0 + (uint64_t)(a_s >> 4);
-                    const uint64_t bd0 = desc0 + (uint64_t)((resb ? b_res + (uint32_t)(k_it * B_TILE_BYTES) : a_s + A_STAGE_BYTES) >> 4);
-#pragma unroll
-                    for (int k = 0; k < KCH / 16; ++k)
+                    const uint64_t bd0 = desc0 + (uint64_t)((resb ? b_res + (uint32_t)(k_it * B_TILE_BYTES) : a_s + a_bytes) >> 4);
+#pragma unroll 4
+                    for (int k = 0; k < ksteps; ++k)
                         umma_f16(acc, ad0 + (uint64_t)(k * 2), bd0 + (uint64_t)(k * 2), idesc, (k_it > 0 || k > 0) ? 1u : 0u);
                     umma_commit(smem_u32(&empty_bar[s]));
                     if (++s == stages) { s = 0; ph ^= 1; }
@@ -203,19 +210,19 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
         // ================= epilogue (8 warps) =================
         const int ew = warp - 2;
         const int q = warp & 3;                  // TMEM lane quarter this warp may access
-        const int half = ew >> 2;                // which half of the tile's 32-column chunks
+        const int half = ew >> 2;                // first of the tile's 32-column chunks this warp owns (then every BD_CS-th)
         const int t_unit = lane & 3, t_row = lane >> 2;       // transposed role: 16-byte unit t_unit of rows 8*it + t_row
         const int te = threadIdx.x - 64;         // 0..255 among the epilogue threads
         const uint32_t after_ring = (uint32_t)(stages * stage_bytes);
         const uint32_t stg = tiles + after_ring + (uint32_t)ew * EPI_STG_BYTES;
-        const uint32_t zone = tiles + after_ring + 8u * EPI_STG_BYTES + (uint32_t)ew * BD_ZONE_WARP + (uint32_t)lane * 16u;
+        const uint32_t zone = tiles + after_ring + (uint32_t)(BD_EW * EPI_STG_BYTES) + (uint32_t)ew * BD_ZONE_WARP + (uint32_t)lane * 16u;
         // Per-channel tables, all bf16 so that the hot loop stays in packed arithmetic (the epilogue is bound by the number of
         // instructions its 8 warps execute, not by bytes):
         //   t_sg = sign of the scale s (+-1), t_T = the ReLU threshold in u = x * sign: bn(x) rounded to bf16 > 0  <=>  u >= T,
         //          found EXACTLY per channel below (the predicate is monotone in u), so the mask is still the stored
         //          activation's sign bit for bit but costs a packed multiply + compare per channel pair;
         //   t_sb = s rounded to bf16 (packed_s: dx (+)= d * s as one packed fma per channel pair); t_sf = s in fp32 (default).
-        uint16_t* tab = reinterpret_cast<uint16_t*>(smem_raw + (tiles - smem_u32(smem_raw)) + after_ring + 8u * EPI_STG_BYTES + 8u * BD_ZONE_WARP);
+        uint16_t* tab = reinterpret_cast<uint16_t*>(smem_raw + (tiles - smem_u32(smem_raw)) + after_ring + (uint32_t)(BD_EW * EPI_STG_BYTES) + (uint32_t)(BD_EW * BD_ZONE_WARP));
         // The tables hold the BN channels of the CURRENT channel tile only (a CTA's tile range is contiguous, row tiles fastest:
         // it crosses a channel-tile boundary a few times per launch at most) and are rebuilt there by the first 128 epilogue
         // threads -- filling them for all C channels up front cost 3-4 us of every launch (7 dependent parameter loads per thread).
@@ -273,7 +280,7 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
         auto geo = [&](int mt, int ny) {
             Geo g;
             g.ok = 0;
-            g.c0 = ny * BN + half * 32 + t_unit * 8;
+            g.c0 = ny * BN + half * 32 + t_unit * 8;      // slot chunk jj adds BD_CS * 32 channels
             if (CONV) {
                 const int w0 = (mt % p.tiles_w) * p.TW, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.TH;
                 const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.TN;
@@ -297,8 +304,8 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
         };
         auto issue = [&](const Geo& g, bool live_tile, int k) {
             const int jj = k >> 2, it = k & 3;
-            const bool ok = live_tile && ((g.ok >> it) & 1) && g.c0 + jj * 64 < p.C;
-            const long long o = ok ? g.off[it] + jj * 64 : 0;
+            const bool ok = live_tile && ((g.ok >> it) & 1) && g.c0 + jj * (BD_CS * 32) < p.C;
+            const long long o = ok ? g.off[it] + jj * (BD_CS * 32) : 0;
             cp_async16(zone + (uint32_t)(k * 1024), p.x + o, ok ? 16u : 0u);
             if (accum) cp_async16(zone + (uint32_t)(k * 1024 + 512), p.dx + o, ok ? 16u : 0u);
             cp_async_commit();                   // always: the group count per slot stays fixed
@@ -321,7 +328,7 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
 #pragma unroll
             for (int jj = 0; jj < BD_NCH; ++jj) {
                 float* a = acc[jj];
-                const int cl = ny * BN + (half + 2 * jj) * 32 + t_unit * 8;
+                const int cl = ny * BN + (half + BD_CS * jj) * 32 + t_unit * 8;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) a[e] = fmaf(-(cl + e < p.C ? __ldg(p.mean + cl + e) : 0.f), a[8 + e], a[e]);
                 {   // recursive halving over lane bits 4, 3, 2: kind = bit 4 (0: dgamma term, 1: dbeta term),
@@ -375,15 +382,15 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
             tc_fence_after();
 #pragma unroll
             for (int jj = 0; jj < BD_NCH; ++jj) {
-                const int j = half + 2 * jj;
+                const int j = half + BD_CS * jj;
                 const bool live = ny * BN + j * 32 < p.C;   // warp-uniform: chunks beyond the last channel (partial last N tile) carry no data
-                const bool cok = gc.c0 + jj * 64 < p.C;
+                const bool cok = gc.c0 + jj * (BD_CS * 32) < p.C;
                 uint4 T8 = make_uint4(0u, 0u, 0u, 0u), sg8 = T8, sb8 = T8;
                 float s8[8];
                 if (live) {
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + j * 32, v);
-                    const int ct = cok ? gc.c0 + jj * 64 - ny * BN : 0;     // index within the channel tile
+                    const int ct = cok ? gc.c0 + jj * (BD_CS * 32) - ny * BN : 0;     // index within the channel tile
                     T8 = *reinterpret_cast<const uint4*>(t_T + ct);
                     sg8 = *reinterpret_cast<const uint4*>(t_sg + ct);
                     if (p.packed_s) sb8 = *reinterpret_cast<const uint4*>(t_sb + ct);
@@ -451,9 +458,9 @@ __global__ void __launch_bounds__(BD_THREADS, 1) bn_dgrad_kernel(const __grid_co
                             }
                         }
                         if (cok && ((gc.ok >> it) & 1)) {
-                            *reinterpret_cast<uint4*>(p.dx + gc.off[it] + jj * 64) = orw;
+                            *reinterpret_cast<uint4*>(p.dx + gc.off[it] + jj * (BD_CS * 32)) = orw;
                             if (p.d_out != nullptr)
-                                *reinterpret_cast<uint4*>(p.d_out + (long long)gc.pix[it] * p.d_pitch + gc.c0 + jj * 64) = dr;
+                                *reinterpret_cast<uint4*>(p.d_out + (long long)gc.pix[it] * p.d_pitch + gc.c0 + jj * (BD_CS * 32)) = dr;
                         }
                     }
                     issue(gn, live_n, k);
@@ -775,6 +782,36 @@ int encode_mat_pitch(CUtensorMap* tm, const void* base, long long rows, long lon
     return SRGAN_OK;
 }
 
+// 32-channel boxes with SWIZZLE_64B (64-byte rows): an NHWC activation window whose first `valid` <= 32 channels exist ...
+int encode_act32(CUtensorMap* tm, const void* base, int n, int H, int W, int bw, int bh, int bn, int pitch, int valid) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { srgan_set_error("cuTensorMapEncodeTiled is not available from the driver"); return SRGAN_ERR_CUDA; }
+    const cuuint64_t P = pitch;
+    cuuint64_t dims[4] = {(cuuint64_t)valid, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+    cuuint64_t strides[3] = {P * 2, (cuuint64_t)W * P * 2, (cuuint64_t)H * W * P * 2};
+    cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { srgan_set_error("cuTensorMapEncodeTiled(activation32) failed: %d", (int)r); return SRGAN_ERR_CUDA; }
+    return SRGAN_OK;
+}
+// ... and the matching weight boxes: 32 of every tap's 64 K columns, brows rows
+int encode_mat32(CUtensorMap* tm, const void* base, long long rows, long long cols, int brows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { srgan_set_error("cuTensorMapEncodeTiled is not available from the driver"); return SRGAN_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {32, (cuuint32_t)brows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { srgan_set_error("cuTensorMapEncodeTiled(matrix32) failed: %d", (int)r); return SRGAN_ERR_CUDA; }
+    return SRGAN_OK;
+}
+
 template <int MT>
 int launch_bn_conv_down(const CUtensorMap& tmA, const CUtensorMap& tmB, BnFpropParams& p, cudaStream_t st) {
     constexpr int stage_bytes = MT * A_STAGE_BYTES + BF_BN * KCH * 2;
@@ -1017,7 +1054,7 @@ int bn_dgrad(const void* dy, const void* Wu, void* dx, const void* x, long long 
     if (m_tiles * n_tiles > 0x7fffffffLL) return 0;
     p.m_tiles = (int)m_tiles; p.total_tiles = (int)(m_tiles * n_tiles);
     p.packed_s = bn_packed_scale();
-    const int fixed = 8 * EPI_STG_BYTES + 8 * BD_ZONE_WARP + 3 * BD_BN * 2 + BD_BN * 4 + 1024;
+    const int fixed = BD_EW * EPI_STG_BYTES + BD_EW * BD_ZONE_WARP + 3 * BD_BN * 2 + BD_BN * 4 + 1024;
     static const bool resb_on = [] { const char* e = getenv("SRGAN_NO_RESIDENT_B"); return !(e && e[0] == '1'); }();
     p.resb = (resb_on && K <= 256) ? 1 : 0;
     const int b_bytes = p.resb ? (K / KCH) * BD_BN * KCH * 2 : 0;
@@ -1032,6 +1069,7 @@ int bn_dgrad(const void* dy, const void* Wu, void* dx, const void* x, long long 
     if (rc) return rc;
     rc = encode_mat(&tmB, Wu, Cout, K, BD_BN);
     if (rc) return rc;
+    p.k32 = 0;
     p.n = p.H = p.W = p.R = p.S = p.pad = p.Cin = p.TW = p.TH = p.TN = p.lgTW = p.lgTH = p.tiles_w = p.tiles_h = 0;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1075,16 +1113,20 @@ int bn_conv_dgrad(const void* dy, int dy_pitch, int dy_valid, const void* Wu, vo
     p.d_out = (bf16*)d_out; p.d_pitch = d_pitch;
     p.m_tiles = (int)m_tiles; p.total_tiles = (int)(m_tiles * n_tiles); p.resb = 0;
     p.packed_s = bn_packed_scale();
-    const int fixed = 8 * EPI_STG_BYTES + 8 * BD_ZONE_WARP + 3 * BD_BN * 2 + BD_BN * 4 + 1024;
-    int stages = (226 * 1024 - fixed) / BD_STAGE_BYTES;
+    static const bool k32_on = [] { const char* e = getenv("SRGAN_NO_K32"); return !(e && e[0] == '1'); }();
+    p.k32 = (k32_on && Cin == KCH && dy_valid > 0 && dy_valid <= 32) ? 1 : 0;
+    const int stage_bytes = p.k32 ? BD_STAGE_BYTES / 2 : BD_STAGE_BYTES;
+    const int fixed = BD_EW * EPI_STG_BYTES + BD_EW * BD_ZONE_WARP + 3 * BD_BN * 2 + BD_BN * 4 + 1024;
+    int stages = (226 * 1024 - fixed) / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) return 0;
     p.stages = stages;
-    const size_t smem = (size_t)stages * BD_STAGE_BYTES + fixed;
+    const size_t smem = (size_t)stages * stage_bytes + fixed;
     CUtensorMap tmA, tmB;
-    int rc = encode_act(&tmA, dy, n, H, W, Cin, p.TW, p.TH, p.TN, 1, dy_pitch, dy_valid);
+    int rc = p.k32 ? encode_act32(&tmA, dy, n, H, W, p.TW, p.TH, p.TN, dy_pitch, dy_valid)
+                   : encode_act(&tmA, dy, n, H, W, Cin, p.TW, p.TH, p.TN, 1, dy_pitch, dy_valid);
     if (rc) return rc;
-    rc = encode_mat(&tmB, Wu, Cout, (long long)R * S * Cin, BD_BN);
+    rc = p.k32 ? encode_mat32(&tmB, Wu, Cout, (long long)R * S * Cin, BD_BN) : encode_mat(&tmB, Wu, Cout, (long long)R * S * Cin, BD_BN);
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
