@@ -304,6 +304,43 @@ int srgan_coefficient_step(const float* const* d_ptrs, const float* const* g_ptr
                            float beta1, float beta2, float eps, int phases, int train_g, void* workspace,
                            size_t workspace_bytes, float* scalars, float* publish, void* stream);
 
+/* ---- crowd input pipeline and sliding-window inference on the device ------------------
+ * The full images (uint8 HWC), density labels and kNN maps (fp32 HW) of a dataset split stay resident in device memory,
+ * concatenated image after image: image i starts at pixel pixel_offset[i] (byte 3*pixel_offset[i] of `images`, element
+ * pixel_offset[i] of `labels` / `maps`) and is heights[i] x widths[i].
+ *
+ * srgan_crowd_extract_patches: one launch = one batch of the reference's per-sample host transform chain
+ *   ExtractPatchForPosition(patch, patch, allow_padded=True)  crowd/data.py:370-492 (window centred at (y, x); outside the
+ *                                                             image: constant 0 for image, label and map, :426-452)
+ *   -> RandomHorizontalFlip                                   crowd/data.py:92-112 (np.flip(axis=1) of image, label, map)
+ *   -> NegativeOneToOneNormalizeImage                         crowd/data.py:115-128 ((u8 -> fp32) / 127.5 - 1)
+ *   -> NumpyArraysToTorchTensors                              crowd/data.py:41-63 (HWC -> CHW, fp32)
+ * as ShanghaiTechTransformedDataset.__getitem__ (crowd/shanghai_tech_data.py:73-104) and ImageSlidingWindowDataset.__getitem__
+ * (crowd/data.py:541-557) compose it.  pos: [B][4] int32 = {image index, y, x, flip}; outputs img_out [B,3,patch,patch],
+ * label_out / map_out [B,patch,patch] fp32 (NULL together with their source: the sliding-window dataset has neither).
+ * Bit-exact with the reference's numpy arithmetic.  label_patch_size != image_patch_size (scipy.misc.imresize, removed
+ * from SciPy) is not supported: BASELINE's crowd configuration uses 224 / 224. */
+int srgan_crowd_extract_patches(const uint8_t* images, const float* labels, const float* maps, const long long* pixel_offset,
+                                const int* heights, const int* widths, int n_images, const int* pos, int B, int patch,
+                                float* img_out, float* label_out, float* map_out, void* stream);
+/* CrowdExperiment.predict_full_example, crowd/srgan.py:345-395: merges the per-patch predictions of a sliding window over
+ * one H x W image.  Window (yi, xi) is patch yi*nx + xi and covers rows [ys[yi]-patch/2, ys[yi]+patch/2) (clipped to the
+ * image), columns likewise.  full_label[Y,X] = mean over the covering patches of their predicted density at that pixel
+ * (patch_labels [ny*nx, patch, patch] fp32; NULL = all zeros, what KnnDenseNetCat returns, crowd/models.py:1153);
+ * *full_count = sum over pixels of the mean of count_p / patch^2 (double).  Per-pixel sums run in patch order in fp32 like
+ * the reference's `+=`; pixels no window covers divide by 1 (:391).  workspace: srgan_sliding_window_workspace_bytes(). */
+size_t srgan_sliding_window_workspace_bytes(void);
+int srgan_sliding_window_merge(const float* patch_labels, const float* patch_counts, const int* ys, int ny, const int* xs,
+                               int nx, int H, int W, int patch, float* full_label, double* full_count, void* workspace,
+                               size_t workspace_bytes, void* stream);
+/* CrowdExperiment.evaluation_epoch, crowd/srgan.py:149-191: the float64 reductions behind Validation ME / MAE / MSE and
+ * kNN MAE / MSE over n samples: out[0*n+b] = sum(densities[b]) ([n, HW] fp32; NULL: skipped), out[1*n+b] = sum over the
+ * nmaps predicted maps and HW of |pred_maps[b,c] - maps[b]|, out[2*n+b] = the same with squares ([n,nmaps,HW] vs [n,HW];
+ * both NULL: skipped).  workspace: srgan_crowd_eval_workspace_bytes(n). */
+size_t srgan_crowd_eval_workspace_bytes(int n);
+int srgan_crowd_eval_sums(const float* densities, const float* pred_maps, int nmaps, const float* maps, int n, long long HW,
+                          double* out, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

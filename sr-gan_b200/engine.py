@@ -1309,7 +1309,7 @@ class Engine:
         self.adam(G, cfg.learning_rate, 0.0, cfg.betas, cfg.eps, deferrable='G')
 
     # ------------------------------------------------------------------ inference-style helpers
-    def d_features(self, x, st: Optional[NetState] = None):
+    def d_features(self, x, st: Optional[NetState] = None, with_maps=False):
         """D(x) forward only: returns (prediction [B], features rows [B, F] in NHWC order)."""
         self.ops.begin()
         st = st or self.D
@@ -1322,6 +1322,8 @@ class Engine:
         feats = self._brows_feat(net, acts, 0, B)
         pred = self.buf('pred', (B,), self.mdt)
         self._head_forward(st, feats, B, 0, pred)
+        if with_maps:           # crowd: the three predicted maps, [B, label_size^2] each (crowd/models.py:1155-1165)
+            return pred, feats, [self._brows(acts[m], net.bufs[m], 0, B) for m in net.map_bufs]
         return pred, feats
 
     def g_generate(self, z):

@@ -683,6 +683,19 @@ class StepRunner:
         pred, feats = self.engine.d_features(x, st)
         return pred.clone(), self.features_nchw(feats, x.shape[0])
 
+    def predict_crowd(self, x, net='D'):
+        """KnnDenseNetCat.forward's return values (crowd/models.py:1138-1166) on the kernels: (density = None for the zeros
+        tensor of :1153, count [B], map [B, 3, L, L]) -- the `network(images)` callable of crowd_data.predict_full_example /
+        evaluation_epoch (crowd/srgan.py:256-259,359)."""
+        if self.engine.d_net.family != 'crowd':
+            raise ValueError('predict_crowd() is the crowd application\'s forward')
+        self._wait_pending()
+        self._fresh_layouts()
+        st = self.engine.D if net == 'D' else self.engine.DNN
+        pred, _, maps = self.engine.d_features(x, st, with_maps=True)
+        L = self.engine.d_net.label_size
+        return None, pred.clone(), torch.stack([m.reshape(x.shape[0], L, L) for m in maps], dim=1).to(torch.float32)
+
     def features_nchw(self, feats_flat, B):
         """`.features` in the reference's order: out.view(B, -1) of an NCHW tensor (age/models.py:74)."""
         c, h, w = self.engine.d_net.feature_chw

@@ -36,6 +36,8 @@ _EXPORTS = (
     'srgan_coefficient_step_workspace_bytes', 'srgan_affine', 'srgan_affine_bwd', 'srgan_affine_grad', 'srgan_copy2d',
     'srgan_maxpool', 'srgan_maxpool_bwd', 'srgan_avgpool', 'srgan_avgpool_bwd', 'srgan_crowd_loss', 'srgan_crowd_map_grad', 'srgan_depth_to_space', 'srgan_adam_multi', 'srgan_affine_bwd_grad',
     'srgan_adam_layout_multi', 'srgan_bn_dgrad', 'srgan_bn_conv_down', 'srgan_bn_conv_wgrad', 'srgan_bn_conv_dgrad',
+    'srgan_crowd_extract_patches', 'srgan_sliding_window_merge', 'srgan_crowd_eval_sums',
+    'srgan_sliding_window_workspace_bytes', 'srgan_crowd_eval_workspace_bytes',
 )
 
 _lib = None
@@ -107,11 +109,17 @@ def load_library(path: str = LIB_PATH):
     lib.srgan_bn_conv_dgrad.argtypes = [vp, c_int, c_int, vp, vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                         vp, vp, vp, vp, c_f, vp, vp, vp, c_int, c_int, c_int, vp]
     lib.srgan_bn_conv_wgrad.argtypes = [vp, vp, vp, c_ll, c_int, c_int, c_int, c_int, vp, vp, vp, vp, c_f, c_int, vp]
+    lib.srgan_crowd_extract_patches.argtypes = [vp, vp, vp, vp, vp, vp, c_int, vp, c_int, c_int, vp, vp, vp, vp]
+    lib.srgan_sliding_window_merge.argtypes = [vp, vp, vp, c_int, vp, c_int, c_int, c_int, c_int, vp, vp, vp, ctypes.c_size_t, vp]
+    lib.srgan_crowd_eval_sums.argtypes = [vp, vp, c_int, vp, c_int, c_ll, vp, vp, ctypes.c_size_t, vp]
+    lib.srgan_crowd_eval_workspace_bytes.argtypes = [c_int]
     lib.srgan_tensor_launch_count.restype = c_ll
     lib.srgan_simt_fallback_count.restype = c_ll
     for name in _EXPORTS[7:]:
         getattr(lib, name).restype = c_int
     lib.srgan_coefficient_step_workspace_bytes.restype = ctypes.c_size_t
+    lib.srgan_sliding_window_workspace_bytes.restype = ctypes.c_size_t
+    lib.srgan_crowd_eval_workspace_bytes.restype = ctypes.c_size_t
     _lib = lib
     return lib
 

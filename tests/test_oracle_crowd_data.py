@@ -1,0 +1,65 @@
+"""Pins oracle/crowd_data_oracle.py (crowd input transforms, sliding-window inference,
+evaluation sums) against tests/golden/crowd_data.npz, produced by the UNMODIFIED reference classes
+(oracle/make_golden_data.py).  CPU only."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import crowd_data_oracle as C
+from oracle.make_golden_data import fake_network
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'crowd_data.npz')
+
+
+@pytest.fixture(scope='module')
+def g():
+    return np.load(GOLDEN)
+
+
+def examples(g):
+    return [(g[f'image{i}'], g[f'label{i}'], g[f'map{i}']) for i in range(int(g['n_images']))]
+
+
+def test_patch_transform_chain_bit_exact(g):
+    ex, patch = examples(g), int(g['patch'])
+    for k, (i, y, x, flip) in enumerate(g['f1_pos']):
+        image, label, map_ = C.extract_patch(*ex[i], int(y), int(x), patch)
+        image, label, map_ = C.random_horizontal_flip(image, label, map_, bool(flip))
+        image = C.to_chw_float32(C.normalize_image(image))
+        assert np.array_equal(image, g['f1_images'][k]), (k, i, y, x, flip)
+        assert np.array_equal(label, g['f1_labels'][k]) and np.array_equal(map_, g['f1_maps'][k]), (k, i, y, x, flip)
+
+
+def test_transformed_dataset_items_bit_exact_with_the_reference_draws(g):
+    ex, patch = examples(g), int(g['patch'])
+    store = [ex[i] for i in g['f1b_store']]
+    _, length = C.start_indexes([e[0].shape[:2] for e in store], patch)
+    assert length == int(g['f1b_length'])
+    random.seed(int(g['f1b_seed']))
+    for k in range(len(g['f1b_images'])):
+        index_ = random.randrange(length)                  # crowd/shanghai_tech_data.py:80
+        flip = random.choice([True, False])                # crowd/data.py:104
+        image, label, map_ = C.transformed_item(store, patch, index_, flip)
+        assert np.array_equal(image, g['f1b_images'][k]), k
+        assert np.array_equal(label, g['f1b_labels'][k]) and np.array_equal(map_, g['f1b_maps'][k]), k
+
+
+def test_sliding_window_positions_and_full_example_prediction(g):
+    ex, patch, step = examples(g), int(g['patch']), int(g['step'])
+    for i, (image, _, _) in enumerate(ex):
+        H, W = image.shape[:2]
+        assert C.sliding_positions(H, patch, step) == list(g[f'f2_ys{i}'])
+        assert C.sliding_positions(W, patch, step) == list(g[f'f2_xs{i}'])
+        count, label = C.predict_full_example(image, lambda im: [t.numpy() for t in fake_network(im)], patch, step, 7)
+        # the reference walks its windows in list(set(..)) order, this oracle in sorted order: same sums up to fp32 rounding
+        np.testing.assert_allclose(label, g[f'f2_label{i}'], rtol=2e-6, atol=1e-8)
+        assert float(count) == pytest.approx(float(g[f'f2_count{i}']), rel=2e-6)
+
+
+def test_evaluation_sums(g):
+    labels, counts, maps = [t.numpy() for t in fake_network(g['f1_images'][:15])]
+    out = C.evaluation_sums(counts, g['f1_labels'][:15], maps[:5], g['f1_maps'][:5])      # maps: first batch only (:170-175)
+    for tag, v in out.items():
+        assert v == pytest.approx(float(g['f2b_' + tag.replace(' ', '_')]), rel=1e-12), tag
