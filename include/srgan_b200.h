@@ -341,6 +341,23 @@ size_t srgan_crowd_eval_workspace_bytes(int n);
 int srgan_crowd_eval_sums(const float* densities, const float* pred_maps, int nmaps, const float* maps, int n, long long HW,
                           double* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- crowd label preprocessing on the device ------------------------------------------------
+ * head_yx: [n_heads][2] float64 (y, x) annotations, the array crowd/shanghai_tech_data.py:132-137 hands to
+ * DatabasePreprocessor.generate_labels_for_example (crowd/database_preprocessor.py:64-99).
+ *
+ * srgan_knn_maps = generate_knn_map (crowd/database_preprocessor.py:258-290) for k = 1..kmax (<= 8) in one sweep: a brute-force
+ * float64 search instead of the scikit-learn ball tree.  knn[k-1][y][x] = mean of the min(k, n_heads) smallest Euclidean
+ * distances from pixel (y, x) to a head, each clipped to upper_bound first when upper_bound > 0 (:282-283); distances are
+ * sqrt(dy*dy + dx*dx) without FMA contraction and the mean adds them in ascending order like numpy's mean(axis=1), so the
+ * maps carry the reference's bits.  iknn_f16 (may be NULL; so may knn): the [kmax][H][W] float16 maps the preprocessor saves,
+ * 1 / (knn + epsilon) (:92-99; epsilon = 1). */
+int srgan_knn_maps(const double* head_yx, int n_heads, int H, int W, int kmax, double upper_bound, double epsilon, double* knn,
+                   void* iknn_f16, void* stream);
+/* generate_point_density_map (crowd/database_preprocessor.py:246-256): density[round(y)][round(x)] += 1 per head (round half to
+ * even, negative indexes wrap once like Python's); *out_of_bounds = heads that fall outside.  density [H][W] fp32 and the
+ * counter are cleared by the call. */
+int srgan_point_density_map(const double* head_yx, int n_heads, int H, int W, float* density, int* out_of_bounds, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,6 +87,22 @@ class CrowdStore:
     def __len__(self):
         return len(self.shapes)
 
+    def _upload_table(self, table):
+        """Host position table -> device through one of two persistent pinned staging buffers (allocating pinned memory per
+        batch cost more than the gather itself); a buffer is reused only after the copy that last read it has completed."""
+        n = table.shape[0]
+        ring = self.__dict__.setdefault('_staging', [None, None])
+        self._turn = (getattr(self, '_turn', 0) + 1) % 2
+        slot = ring[self._turn]
+        if slot is None or slot[0].shape[0] < n:
+            slot = ring[self._turn] = (torch.empty(max(n, 256), 4, dtype=torch.int32, pin_memory=True), torch.cuda.Event())
+        else:
+            slot[1].synchronize()
+        slot[0][:n].copy_(table)
+        dev = slot[0][:n].to(self.device, non_blocking=True)
+        slot[1].record(torch.cuda.current_stream(self.device))
+        return dev
+
     def extract(self, positions, patch, with_labels=True):
         """positions: [B,4] int32 {image index, y, x, flip} (host array or device tensor).  Returns (images [B,3,P,P],
         labels [B,P,P] | None, maps [B,P,P] | None), fp32 on the device: the tensors `training_loop` hands to the step."""
@@ -98,7 +114,7 @@ class CrowdStore:
             bad = (positions[:, 0] < 0) | (positions[:, 0] >= len(self))
             if bool(bad.any()):
                 raise IndexError(f'image index out of range for a store of {len(self)} images')
-            positions = positions.pin_memory().to(self.device, non_blocking=True)
+            positions = self._upload_table(positions)
         B = positions.shape[0]
         f32 = torch.float32
         images = torch.empty(B, 3, patch, patch, device=self.device, dtype=f32)

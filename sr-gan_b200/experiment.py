@@ -824,13 +824,34 @@ class B200StepMixin:
                 w.add_scalar('Feature Norm/Unlabeled', self.unlabeled_features.mean(0).norm().item())
 
     def save_models(self, step):
-        """srgan.py:88-97 with the Adam moments exported into the torch optimizers first."""
+        """srgan.py:88-97 with the Adam moments exported into the torch optimizers first.  `settings.async_checkpoint`
+        (opt-in) hands the same dict to checkpoint.AsyncWriter: device -> pinned-host copies on a side stream, pickling and
+        the disk write on a background thread; under data parallelism each rank then writes its round-robin shard of the
+        tensors (checkpoint.shard).  `wait_for_checkpoints()` (also run before every later save) completes them."""
         r = getattr(self, '_b200', None)
         if r is not None:
             r.export_optimizer_state(self.d_optimizer, 'D')
             r.export_optimizer_state(self.g_optimizer, 'G')
             r.export_optimizer_state(self.dnn_optimizer, 'DNN')
-        super().save_models(step)
+        if not getattr(self.settings, 'async_checkpoint', False):
+            return super().save_models(step)
+        from . import checkpoint
+        model = {'DNN': self.DNN.state_dict(), 'dnn_optimizer': self.dnn_optimizer.state_dict(),
+                 'D': self.D.state_dict(), 'd_optimizer': self.d_optimizer.state_dict(),
+                 'G': self.G.state_dict(), 'g_optimizer': self.g_optimizer.state_dict(), 'step': step}
+        path = os.path.join(self.trial_directory, f'model_{step}.pth')
+        comm = r.engine.comm if r is not None else None
+        if comm is not None and comm.world_size > 1:
+            model, path = (checkpoint.shard(model, comm.rank, comm.world_size),
+                           checkpoint.shard_path(path, comm.rank, comm.world_size))
+        if getattr(self, '_checkpoint_writer', None) is None:
+            self._checkpoint_writer = checkpoint.AsyncWriter()
+        self._checkpoint_writer.save(model, path)
+
+    def wait_for_checkpoints(self):
+        w = getattr(self, '_checkpoint_writer', None)
+        if w is not None:
+            w.wait()
 
 
 class Experiment:

@@ -149,3 +149,40 @@ def test_mixin_rejects_mismatched_dggan_pairing():
     exp = ref_harness.make_experiment(cls, s, D=DgganMLP(), G=Generator(), DNN=DgganMLP())
     with pytest.raises(ValueError):
         exp.dnn_training_step(torch.zeros(8, 50).cuda(), torch.zeros(8).cuda(), 0)
+
+
+def test_mixin_async_checkpoint_loads_in_the_reference(tmp_path):
+    """settings.async_checkpoint: save_models returns before the file exists, training goes on, and the completed
+    model_{step}.pth holds the parameters and Adam state AS OF the save -- loadable by the unmodified reference's
+    load_models (srgan.py:182-199)."""
+    import os
+    import srgan_b200
+    name, method, st, kw, batch = _case('coefficient')
+    fast = ref_harness.workload_experiment(name, dict(kw, async_checkpoint=True), device='cuda', state=st.clone(), method=method,
+                                           base=(srgan_b200.B200StepMixin,))
+    fast.trial_directory = str(tmp_path)
+    x, y, u, z, alpha, z2 = batch()
+
+    def step(i):
+        fast._b200_noise = (z.cuda(), alpha.cuda(), z2.cuda())
+        fast.dnn_training_step(x.cuda(), y.cuda(), i)
+        fast.gan_training_step(x.cuda(), y.cuda(), u.cuda(), i)
+    step(0)
+    fast.save_models(step=1)
+    at_save = {k: v.detach().cpu().clone() for k, v in fast.D.state_dict().items()}
+    step(1)                                                   # overwrites the parameters while the writer may still run
+    fast.wait_for_checkpoints()
+    path = os.path.join(str(tmp_path), 'model_1.pth')
+    assert os.path.exists(path)
+    loaded = torch.load(path, map_location='cpu', weights_only=False)
+    assert set(loaded) == {'DNN', 'dnn_optimizer', 'D', 'd_optimizer', 'G', 'g_optimizer', 'step'} and loaded['step'] == 1
+    for k, v in at_save.items():
+        assert torch.equal(loaded['D'][k], v), k
+    assert any(not torch.equal(fast.D.state_dict()[k].cpu(), v) for k, v in at_save.items())
+    # the unmodified reference loads it
+    ref = ref_harness.workload_experiment(name, kw, device='cpu', state=st.clone(), method=method)
+    ref.settings.load_model_path = str(tmp_path)
+    ref.load_models()
+    for k, v in at_save.items():
+        assert torch.equal(ref.D.state_dict()[k], v), k
+    assert float(ref.d_optimizer.state[next(ref.D.parameters())]['step']) == 1.0

@@ -88,6 +88,29 @@ def main():
     torch.cuda.synchronize()
     print(f'predict_full_example (extract + merge, {sw.length} windows, stand-in network): '
           f'{(time.perf_counter() - t0) / 10 * 1e3:.3f} ms/image')
+    # label preprocessing (row f4): every pixel's 1..5-NN distance maps of a 768 x 1024 label with 1 500 heads
+    from srgan_b200 import crowd_labels
+    heads = rng.rand(1500, 2) * np.array([H, W], dtype=np.float64)
+    crowd_labels.generate_knn_maps(heads, (H, W), 5)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        crowd_labels.generate_knn_maps(heads, (H, W), 5)
+    e1.record()
+    e1.synchronize()
+    gpu_ms = e0.elapsed_time(e1) / 5
+    evals = H * W * 1500
+    print(f'generate_knn_maps k=1..5, {H}x{W}, 1500 heads: {gpu_ms:.3f} ms = {evals / gpu_ms / 1e6:.0f} G distance evaluations/s (fp64)')
+    try:                                                              # the reference's call: one ball-tree query per k
+        from sklearn.neighbors import NearestNeighbors
+        pos = np.stack(np.meshgrid(np.arange(H), np.arange(W), indexing='ij'), -1).reshape(-1, 2)
+        t0 = time.perf_counter()
+        NearestNeighbors(n_neighbors=5, algorithm='ball_tree').fit(heads).kneighbors(pos)
+        cpu_s = time.perf_counter() - t0
+        print(f'scikit-learn ball tree, ONE k=5 query of the same label on the host: {cpu_s:.2f} s (the preprocessor runs k=1..5: '
+              f'5 queries) -> >= {cpu_s * 1e3 / gpu_ms:.0f}x')
+    except ImportError:
+        print('scikit-learn not importable here: no host timing')
 
 
 if __name__ == '__main__':
