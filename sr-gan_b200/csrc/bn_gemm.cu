@@ -828,11 +828,11 @@ int launch_bn_conv_down(const CUtensorMap& tmA, const CUtensorMap& tmB, BnFpropP
     if (stages < 2) return 0;
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + fixed;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static srgan_per_device_once attr_set;
+    if (attr_set.need()) {
         cudaError_t e = cudaFuncSetAttribute(bn_conv_down_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) { srgan_set_error("cudaFuncSetAttribute(bn_conv_down_kernel): %s", cudaGetErrorString(e)); return SRGAN_ERR_CUDA; }
-        attr_set = true;
+        attr_set.done();
     }
     const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
     bn_conv_down_kernel<MT><<<grid, BF_THREADS, smem, st>>>(tmA, tmB, p);
@@ -1071,11 +1071,11 @@ int bn_dgrad(const void* dy, const void* Wu, void* dx, const void* x, long long 
     if (rc) return rc;
     p.k32 = 0;
     p.n = p.H = p.W = p.R = p.S = p.pad = p.Cin = p.TW = p.TH = p.TN = p.lgTW = p.lgTH = p.tiles_w = p.tiles_h = 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static srgan_per_device_once attr_set;
+    if (attr_set.need()) {
         cudaError_t e = cudaFuncSetAttribute(bn_dgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) { srgan_set_error("cudaFuncSetAttribute(bn_dgrad_kernel): %s", cudaGetErrorString(e)); return SRGAN_ERR_CUDA; }
-        attr_set = true;
+        attr_set.done();
     }
     const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
     bn_dgrad_kernel<false><<<grid, BD_THREADS, smem, st>>>(tmA, tmB, p);
@@ -1128,11 +1128,11 @@ int bn_conv_dgrad(const void* dy, int dy_pitch, int dy_valid, const void* Wu, vo
     if (rc) return rc;
     rc = p.k32 ? encode_mat32(&tmB, Wu, Cout, (long long)R * S * Cin, BD_BN) : encode_mat(&tmB, Wu, Cout, (long long)R * S * Cin, BD_BN);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static srgan_per_device_once attr_set;
+    if (attr_set.need()) {
         cudaError_t e = cudaFuncSetAttribute(bn_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) { srgan_set_error("cudaFuncSetAttribute(bn_dgrad_kernel<conv>): %s", cudaGetErrorString(e)); return SRGAN_ERR_CUDA; }
-        attr_set = true;
+        attr_set.done();
     }
     const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
     bn_dgrad_kernel<true><<<grid, BD_THREADS, smem, st>>>(tmA, tmB, p);
@@ -1221,11 +1221,11 @@ int bn_conv_wgrad(const void* dy, const void* x, float* dW, long long rows, int 
     if (rc) return rc;
     rc = encode_mat_pitch(&tmL, x, rows, C, pitch, BW_PIX);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static srgan_per_device_once attr_set;
+    if (attr_set.need()) {
         cudaError_t e = cudaFuncSetAttribute(bn_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024);
         if (e != cudaSuccess) { srgan_set_error("cudaFuncSetAttribute(bn_conv_wgrad_kernel): %s", cudaGetErrorString(e)); return SRGAN_ERR_CUDA; }
-        attr_set = true;
+        attr_set.done();
     }
     bn_conv_wgrad_kernel<<<dim3(out_tiles, a_tiles, splits), BW_THREADS, smem, st>>>(tmS, tmL, p);
     SRGAN_CHECK_LAUNCH("bn_conv_wgrad_kernel");

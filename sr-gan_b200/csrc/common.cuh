@@ -34,6 +34,19 @@ extern std::atomic<long long> g_launches;
         }                                      \
     } while (0)
 
+// ---- a kernel attribute (cudaFuncSetAttribute: dynamic shared memory opt-in) belongs to the DEVICE the call was made on:
+// remembered per device, not per process (two devices driven from one process each need their own call)
+struct srgan_per_device_once {
+    std::atomic<unsigned long long> mask{0};
+    static unsigned long long bit() {
+        int d = 0;
+        cudaGetDevice(&d);
+        return 1ull << (d & 63);
+    }
+    bool need() const { return !(mask.load(std::memory_order_acquire) & bit()); }
+    void done() { mask.fetch_or(bit(), std::memory_order_release); }
+};
+
 // ---- element conversion
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }

@@ -264,11 +264,11 @@ int flat3x3_conv(const void* src, const void* Wd, void* out, int n, const srgan_
     if (rc) return rc;
     rc = encode_mat(&tmB, Wd, g->Ca, (long long)9 * g->Cb, F3_N);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static srgan_per_device_once attr_set;
+    if (attr_set.need()) {
         cudaError_t e = cudaFuncSetAttribute(flat3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) { srgan_set_error("cudaFuncSetAttribute(flat3x3_kernel): %s", cudaGetErrorString(e)); return SRGAN_ERR_CUDA; }
-        attr_set = true;
+        attr_set.done();
     }
     const int grid = p.total_patches < kNumSMs ? p.total_patches : kNumSMs;
     flat3x3_kernel<<<grid, F3_THREADS, smem, st>>>(tmA, tmB, p);

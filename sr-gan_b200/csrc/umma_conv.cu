@@ -687,12 +687,12 @@ int launch_conv_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, UmmaC
     if (stages < 2) { pp.c.href_smem = 0; stages = (212 * 1024) / stage_bytes; }
     pp.c.stages = stages;
     size_t smem = (size_t)stages * stage_bytes + 8 * EPI_STG_BYTES + (pp.c.href_smem ? zone : 0) + 1024;   // ring + epilogue transposition buffers + href landing zone + alignment
-    static bool attr_set = false;
-    if (!attr_set) {
+    static srgan_per_device_once attr_set;
+    if (attr_set.need()) {
         cudaError_t e = cudaFuncSetAttribute(umma_conv_persistent_kernel<MT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              226 * 1024);
         if (e != cudaSuccess) { srgan_set_error("cudaFuncSetAttribute(umma_conv_persistent_kernel): %s", cudaGetErrorString(e)); return SRGAN_ERR_CUDA; }
-        attr_set = true;
+        attr_set.done();
     }
     int grid = pp.total_tiles < kNumSMs ? pp.total_tiles : kNumSMs;
     umma_conv_persistent_kernel<MT, BN><<<grid, PC_THREADS, smem, st>>>(tmA, tmB, pp);
@@ -706,11 +706,11 @@ int launch_wgrad(const CUtensorMap& tmS, const CUtensorMap& tmL, UmmaWgradParams
     p.stages = (200 * 1024) / stage_bytes;
     if (p.stages > 8) p.stages = 8;
     size_t smem = (size_t)p.stages * stage_bytes + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static srgan_per_device_once attr_set;
+    if (attr_set.need()) {
         cudaError_t e = cudaFuncSetAttribute(umma_wgrad_kernel<BN, WG_PIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024);
         if (e != cudaSuccess) { srgan_set_error("cudaFuncSetAttribute(umma_wgrad_kernel): %s", cudaGetErrorString(e)); return SRGAN_ERR_CUDA; }
-        attr_set = true;
+        attr_set.done();
     }
     umma_wgrad_kernel<BN, WG_PIX><<<grid, WG_THREADS, smem, st>>>(tmS, tmL, p);
     SRGAN_CHECK_LAUNCH("umma_wgrad_kernel");
@@ -833,11 +833,11 @@ int umma_wgrad(const void* S, const void* L, float* dW, int n, const srgan_geom*
                 p.stages = (200 * 1024) / stage_bytes;
                 if (p.stages > 8) p.stages = 8;
                 const size_t smem = (size_t)p.stages * stage_bytes + 1024;
-                static bool attr_set = false;
-                if (!attr_set) {
+                static srgan_per_device_once attr_set;
+                if (attr_set.need()) {
                     cudaError_t e = cudaFuncSetAttribute(umma_wgrad_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024);
                     if (e != cudaSuccess) { srgan_set_error("cudaFuncSetAttribute(umma_wgrad_swap_kernel): %s", cudaGetErrorString(e)); return SRGAN_ERR_CUDA; }
-                    attr_set = true;
+                    attr_set.done();
                 }
                 umma_wgrad_swap_kernel<<<dim3(m_tiles, 1, splits), WG_THREADS, smem, st>>>(tmS, tmL, p);
                 SRGAN_CHECK_LAUNCH("umma_wgrad_swap_kernel");
