@@ -358,6 +358,25 @@ int srgan_knn_maps(const double* head_yx, int n_heads, int H, int W, int kmax, d
  * counter are cleared by the call. */
 int srgan_point_density_map(const double* head_yx, int n_heads, int H, int W, float* density, int* out_of_bounds, void* stream);
 
+/* ---- SGAN method: K-logit head (sgan.py:18-67, age/sgan.py, coefficient/sgan.py) ----------
+ * Logit-shaped arrays are TRANSPOSED: [K][rows] fp32, K <= 16 (settings.py:67 number_of_bins = 10).
+ * srgan_head_logits: logitsT[k][r] = X[r,:] . W[k,:] + bias[k]  (the K-output head: age/models.py:65,79 layer5 with
+ *   number_of_outputs = K as a full-extent conv, coefficient/models.py:83,92 linear4); X is read once for all K. */
+int srgan_head_logits(const void* X, int rows, int cols, const float* W, const float* bias, int K, float* logitsT, int dtype,
+                      void* stream);
+/* mode 0: nn.CrossEntropyLoss(logits, real_numbers_to_bin_indexes(y, bins)) (sgan.py:20-31, utility.py:141-144; mean over the
+ *   batch folded into `scale`): loss += scale * sum_r (logsumexp(l_r) - l_r[bin_r]), dlogitsT = scale * (softmax - onehot);
+ * mode 1: nn.BCEWithLogitsLoss(logsumexp(logits), target) (sgan.py:33-67): loss += scale * sum_r (softplus(z_r) - target z_r),
+ *   dlogitsT = scale * (sigmoid(z_r) - target) * softmax(l_r).   loss / dlogitsT may be NULL. */
+int srgan_sgan_loss(const float* logitsT, int K, int n, int mode, const float* y, const float* bins, float target, float scale,
+                    float* loss, float* dlogitsT, void* stream);
+/* Double backward of the SGAN gradient penalty (srgan.py:360-375 over sgan.py:51-58): qT = H tangentT per sample, H the Hessian
+ * of c * softplus(logsumexp(l)) w.r.t. the K logits -- the ordinary-backward seed the penalty leaves on the x_hat rows. */
+int srgan_sgan_gp_second(const float* logitsT, const float* tangentT, int K, int n, float c, float* qT, void* stream);
+/* out[r,c] = (sum_k dT[k][r] * W[k][c]) * act'(href[r,c]): srgan_seed_rows for a K-output head */
+int srgan_seed_rows_multi(void* out, int rows, int cols, const float* dT, const float* W, int K, const void* href, int act,
+                          float slope, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -170,9 +170,54 @@ def crowd_case(method='srgan', d_scale=1.56):
     print(f'crowd_{method}', {k: float(v) for k, v in data.items() if '/scalars/' in k}, os.path.getsize(path), 'bytes')
 
 
+def sgan_cases():
+    """SGAN method (sgan.py:10-67): AgeSganExperiment with a reduced DCGAN pair
+    (Discriminator(number_of_outputs=10), age/sgan.py:16-20) and CoefficientSganExperiment with its own SganMLP (hidden 100,
+    coefficient/models.py:75-93).  `bins` (a plain list in the config) is the experiment's own linspace."""
+    torch.set_num_threads(1)
+    from age.models import Generator, Discriminator
+    from age.sgan import AgeSganExperiment
+    from coefficient.sgan import CoefficientSganExperiment
+    cfg = dict(method='sgan', family='dcgan', batch_size=4, learning_rate=1e-4, weight_decay=0.0, labeled_loss_multiplier=1.0,
+               matching_loss_multiplier=1.0, gradient_penalty_multiplier=1e2, image_size=32, conv_dim=8, z_dim=16, number_of_bins=10)
+    D = Discriminator(image_size=32, conv_dim=8, number_of_outputs=10)
+    DNN = Discriminator(image_size=32, conv_dim=8, number_of_outputs=10)
+    G = Generator(z_dim=16, image_size=32, conv_dim=8)
+    with torch.no_grad():
+        for k, p in D.named_parameters():
+            if k.endswith('weight'):
+                p.mul_(3.0)
+    exp = ref_harness.make_experiment(AgeSganExperiment, settings_for(cfg), D=D, G=G, DNN=DNN)
+    cfg['bins'] = [float(v) for v in exp.bins]
+    gen = torch.Generator().manual_seed(12)
+    batches = []
+    for _ in range(3):
+        x = torch.rand(4, 3, 32, 32, generator=gen) * 2 - 1
+        u = torch.rand(4, 3, 32, 32, generator=gen) * 2 - 1
+        y = torch.rand(4, generator=gen) * 85 + 10
+        z = torch.randn(4, 16, generator=gen)
+        alpha = torch.rand(4, 1, 1, 1, generator=gen)
+        z2 = torch.randn(4, 16, generator=gen)
+        batches.append((x, y, u, z, alpha, z2))
+    run_case('dcgan_sgan_mini', exp, cfg, batches, steps=3)
+
+    cfg = dict(method='sgan', family='coefficient', batch_size=64, learning_rate=1e-3, weight_decay=1e-3,
+               labeled_loss_multiplier=1.0, matching_loss_multiplier=1.0, gradient_penalty_multiplier=1e3, number_of_bins=10)
+    exp = ref_harness.make_experiment(CoefficientSganExperiment, settings_for(cfg))
+    with torch.no_grad():
+        for k, p in exp.D.named_parameters():
+            if k.endswith('weight'):
+                p.mul_(2.0)
+    cfg['bins'] = [float(v) for v in exp.bins]
+    run_case('coefficient_sgan', exp, cfg, coefficient_batches(64, 3, seed=10), steps=3)
+
+
 def main():
     ref_harness.install_shims()
     os.makedirs(OUT, exist_ok=True)
+    if 'sgan' in sys.argv[1:]:
+        sgan_cases()
+        return
     if 'crowd' in sys.argv[1:]:
         crowd_case()
         return

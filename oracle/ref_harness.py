@@ -41,7 +41,8 @@ def set_reference_device(device):
     dev = torch.device(device)
     import utility
     utility.gpu = dev
-    for name in ('srgan', 'dnn', 'coefficient.srgan', 'coefficient.dggan', 'age.srgan', 'driving.srgan', 'crowd.srgan'):
+    for name in ('srgan', 'dnn', 'sgan', 'coefficient.srgan', 'coefficient.dggan', 'coefficient.sgan', 'age.srgan', 'age.sgan',
+                 'driving.srgan', 'crowd.srgan'):
         m = sys.modules.get(name)
         if m is not None and hasattr(m, 'gpu'):
             m.gpu = dev
@@ -159,6 +160,9 @@ def workload_experiment(name, settings_kwargs, device='cpu', state=None, method=
         from coefficient.models import Generator, MLP, DgganMLP
         cls = CoefficientDgganExperiment if method == 'dggan' else CoefficientExperiment
         mk = DgganMLP if method == 'dggan' else MLP
+        if method == 'sgan':                                    # coefficient/sgan.py:11-21
+            from coefficient.sgan import CoefficientSganExperiment as cls
+            from coefficient.models import SganMLP as mk
         D, DNN, G = mk(), mk(), Generator()
     elif name in ('age', 'driving'):
         if name == 'age':
@@ -167,9 +171,12 @@ def workload_experiment(name, settings_kwargs, device='cpu', state=None, method=
         else:
             from driving.srgan import DrivingExperiment as cls
             from driving.models import Generator, Discriminator
+        if method == 'sgan':                                    # age/sgan.py:10-20
+            from age.sgan import AgeSganExperiment as cls
         if state is not None:
             z_dim, c8, k, _ = state.G['fc.0.weight'].shape
-            D, DNN = Discriminator(image_size=k * 16, conv_dim=c8 // 8), Discriminator(image_size=k * 16, conv_dim=c8 // 8)
+            n_out = state.D['layer5.0.weight'].shape[0]
+            D, DNN = (Discriminator(image_size=k * 16, conv_dim=c8 // 8, number_of_outputs=n_out) for _ in range(2))
             G = Generator(z_dim=z_dim, image_size=k * 16, conv_dim=c8 // 8)
         else:
             D, DNN, G = Discriminator(), Discriminator(), Generator()

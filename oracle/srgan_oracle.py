@@ -42,7 +42,7 @@ DISTANCES = {
 @dataclass
 class StepConfig:
     """The subset of settings.py:12-67 the step reads, with the same defaults."""
-    method: str = 'srgan'                    # 'srgan' | 'dggan'   (settings.py:123-127)
+    method: str = 'srgan'                    # 'srgan' | 'dggan' | 'sgan'   (settings.py:123-127; sgan.py)
     batch_size: int = 1000                   # srgan.py:363 uses settings.batch_size for the alpha shape
     learning_rate: float = 1e-4
     weight_decay: float = 0.0
@@ -59,6 +59,7 @@ class StepConfig:
     map_multiplier: float = 1e-6             # crowd only
     betas: Tuple[float, float] = (0.9, 0.999)   # torch.optim.Adam defaults, srgan.py:136-138
     eps: float = 1e-8
+    bins: Tuple[float, ...] = ()             # sgan: the bin centres (age/sgan.py:14 linspace(10, 95, number_of_bins))
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -86,7 +87,7 @@ def coefficient_d_forward(p: Params, x: torch.Tensor, dggan: bool = False):
     out = F.linear(h, p['linear4.weight'], p['linear4.bias'])
     if dggan:
         return (out[:, 0].squeeze(), out[:, 1].squeeze()), h
-    return out.squeeze(), h
+    return out.squeeze(), h             # SganMLP (coefficient/models.py:75-93): [B, number_of_bins] logits
 
 
 def coefficient_g_forward(p: Params, z: torch.Tensor):
@@ -104,6 +105,8 @@ def dcgan_d_forward(p: Params, x: torch.Tensor):
         h = F.leaky_relu(F.conv2d(h, p[f'layer{i}.0.weight'], p[f'layer{i}.0.bias'], stride=2, padding=1), 0.05)
     features = h.reshape(h.size(0), -1)
     out = F.conv2d(h, p['layer5.0.weight'], p['layer5.0.bias'], stride=1, padding=0)
+    if out.size(1) > 1:                 # number_of_outputs = number_of_bins (age/sgan.py:18-19, age/models.py:76-79)
+        return out.reshape(-1, out.size(1)), features
     return out.reshape(-1), features
 
 
@@ -239,6 +242,22 @@ def bce_with_logits(scores, target_value: float):
     return F.binary_cross_entropy_with_logits(scores, torch.full_like(scores, target_value))
 
 
+def real_numbers_to_bin_indexes(real_numbers, bins):
+    """utility.py:141-144."""
+    return (real_numbers.reshape(-1, 1) - bins.reshape(1, -1)).abs().min(dim=1)[1]
+
+
+def sgan_labeled_loss(cfg: 'StepConfig', logits, labels):
+    """sgan.py:20-31: cross entropy against the label's bin."""
+    bins = torch.tensor(cfg.bins, dtype=logits.dtype)
+    return F.cross_entropy(logits, real_numbers_to_bin_indexes(labels, bins)) * cfg.labeled_loss_multiplier
+
+
+def sgan_binary_loss(logits, target_value: float):
+    """sgan.py:33-67: BCE-with-logits on logsumexp over the class logits (utility.py:161-185)."""
+    return bce_with_logits(torch.logsumexp(logits, dim=1), target_value)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # Adam exactly as torch.optim.Adam runs it (SURVEY App. C.4; srgan.py:131-138).
 # ----------------------------------------------------------------------------------------------------------------
@@ -314,7 +333,10 @@ def dnn_training_step(st: OracleState, cfg: StepConfig, x, y, step: int = 0):
     """srgan.py:259-271 + dnn_loss_calculation :322-327 (DG-GAN: coefficient/dggan.py:22-27)."""
     leaf = _leaf(st.DNN)
     pred, _, _ = d_forward(st.d_spec, leaf, x)
-    loss = labeled_loss(st.d_spec, cfg, pred, y) * cfg.labeled_loss_multiplier
+    if cfg.method == 'sgan':
+        loss = sgan_labeled_loss(cfg, pred, y)
+    else:
+        loss = labeled_loss(st.d_spec, cfg, pred, y) * cfg.labeled_loss_multiplier
     g = _grads(loss, leaf)
     adam_update(st.DNN, g, st.dnn_adam, dnn_lr(cfg, step), cfg.weight_decay, cfg.betas, cfg.eps)
     return {'dnn_loss': float(loss.detach())}
@@ -324,9 +346,11 @@ def gradient_penalty(st_spec: ModelSpec, leafD: Params, cfg: StepConfig, fake, u
     """srgan.py:360-375 + interpolate_loss_calculation :377-381 (DG-GAN target = raw fake score,
     coefficient/dggan.py:54-57)."""
     interp = (alpha * u.detach() + (1 - alpha) * fake.detach()).requires_grad_(True)
-    _, score, feats = d_forward(st_spec, leafD, interp)
+    logits, score, feats = d_forward(st_spec, leafD, interp)
     if cfg.method == 'dggan':
         target = score
+    elif cfg.method == 'sgan':              # sgan.py:51-58: a scalar, already times the penalty multiplier
+        target = sgan_binary_loss(logits, 0.0) * cfg.gradient_penalty_multiplier
     else:
         target = feats.norm(dim=1)
     grads = torch.autograd.grad(target, interp, torch.ones_like(target), create_graph=True)[0]
@@ -344,13 +368,19 @@ def gan_training_step(st: OracleState, cfg: StepConfig, x, y, u, z, alpha, z2, s
     spec = st.d_spec
     # -- labeled  (:279, :329-335 | dggan.py:29-34)
     pred, _, f_x = d_forward(spec, leafD, x)
-    labeled = labeled_loss(spec, cfg, pred, y) * cfg.labeled_loss_multiplier
-    # -- unlabeled (:283, :337-346 | dggan.py:36-43)
-    _, score_u, f_u = d_forward(spec, leafD, u)
+    if cfg.method == 'sgan':
+        labeled = sgan_labeled_loss(cfg, pred, y)
+    else:
+        labeled = labeled_loss(spec, cfg, pred, y) * cfg.labeled_loss_multiplier
+    # -- unlabeled (:283, :337-346 | dggan.py:36-43 | sgan.py:33-40)
+    logits_u, score_u, f_u = d_forward(spec, leafD, u)
     with torch.no_grad():
         fake = g_forward(st.g_spec, st.G, z)                    # :290  (graph unused: fake is detached / G grads zeroed)
-    _, score_f, f_f = d_forward(spec, leafD, fake)
-    if cfg.method == 'dggan':
+    logits_f, score_f, f_f = d_forward(spec, leafD, fake)
+    if cfg.method == 'sgan':                # sgan.py:33-49: both terms use matching_loss_multiplier
+        unlabeled = sgan_binary_loss(logits_u, 1.0) * cfg.matching_loss_multiplier
+        fake_loss = sgan_binary_loss(logits_f, 0.0) * cfg.matching_loss_multiplier
+    elif cfg.method == 'dggan':
         unlabeled = bce_with_logits(score_u, 0.0) * cfg.matching_loss_multiplier * cfg.dggan_loss_multiplier
         fake_loss = bce_with_logits(score_f, 1.0) * cfg.contrasting_loss_multiplier * cfg.dggan_loss_multiplier
     else:
@@ -374,8 +404,10 @@ def gan_training_step(st: OracleState, cfg: StepConfig, x, y, u, z, alpha, z2, s
     if step % cfg.generator_training_step_period == 0:
         leafG = _leaf(st.G)
         fake2 = g_forward(st.g_spec, leafG, z2)
-        _, score_f2, f_f2 = d_forward(spec, st.D, fake2)
-        if cfg.method == 'dggan':
+        logits_f2, score_f2, f_f2 = d_forward(spec, st.D, fake2)
+        if cfg.method == 'sgan':            # sgan.py:60-67
+            g_loss = -sgan_binary_loss(logits_f2, 0.0)
+        elif cfg.method == 'dggan':
             g_loss = bce_with_logits(score_f2, 0.0)
         else:
             with torch.no_grad():
@@ -403,7 +435,7 @@ def _uniform(gen, shape, bound, dtype):
     return ((torch.rand(shape, generator=gen, dtype=torch.float64) * 2 - 1) * bound).to(dtype)
 
 
-def init_coefficient(seed=0, hidden=10, dggan=False, dtype=torch.float32) -> OracleState:
+def init_coefficient(seed=0, hidden=10, dggan=False, dtype=torch.float32, n_out=None) -> OracleState:
     """Shapes of coefficient/models.py:12-72 (input 50 = observation_count 10 x irrelevant_data_multiplier 5)."""
     gen = torch.Generator().manual_seed(seed)
 
@@ -414,13 +446,13 @@ def init_coefficient(seed=0, hidden=10, dggan=False, dtype=torch.float32) -> Ora
             p[f'linear{i}.weight'] = _uniform(gen, (b, a), bound, dtype)
             p[f'linear{i}.bias'] = _uniform(gen, (b,), bound, dtype)
         return p
-    d = mlp([50, hidden, hidden, hidden, 2 if dggan else 1])
+    d = mlp([50, hidden, hidden, hidden, n_out or (2 if dggan else 1)])     # n_out = number_of_bins: SganMLP (hidden 100)
     dnn = {k: v.clone() for k, v in d.items()}               # D and DNN start identical
     g = mlp([10, hidden, hidden, hidden, 50])
     return OracleState(ModelSpec('coefficient', dggan=dggan), ModelSpec('coefficient'), d, g, dnn)
 
 
-def init_dcgan(seed=0, image_size=128, conv_dim=64, z_dim=256, dtype=torch.float32, scale=1.0) -> OracleState:
+def init_dcgan(seed=0, image_size=128, conv_dim=64, z_dim=256, dtype=torch.float32, scale=1.0, n_out=1) -> OracleState:
     """Shapes of age/models.py:32-80 (crowd DCGenerator: image_size=224, crowd/models.py:127-147)."""
     gen = torch.Generator().manual_seed(seed)
     k = image_size // 16
@@ -431,8 +463,8 @@ def init_dcgan(seed=0, image_size=128, conv_dim=64, z_dim=256, dtype=torch.float
         d[f'layer{i}.0.weight'] = _uniform(gen, (chans[i], chans[i - 1], 4, 4), bound, dtype) * scale
         d[f'layer{i}.0.bias'] = _uniform(gen, (chans[i],), bound, dtype)
     bound = 1 / math.sqrt(chans[4] * k * k)
-    d['layer5.0.weight'] = _uniform(gen, (1, chans[4], k, k), bound, dtype)
-    d['layer5.0.bias'] = _uniform(gen, (1,), bound, dtype)
+    d['layer5.0.weight'] = _uniform(gen, (n_out, chans[4], k, k), bound, dtype)
+    d['layer5.0.bias'] = _uniform(gen, (n_out,), bound, dtype)
     dnn = {kk: v.clone() for kk, v in d.items()}
     bound = 1 / math.sqrt(conv_dim * 8 * k * k)
     g['fc.0.weight'] = _uniform(gen, (z_dim, conv_dim * 8, k, k), bound, dtype)

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libsrgan_b200.so')
 SOURCES = ['api.cu', 'simt_conv.cu', 'elementwise.cu', 'umma_conv.cu', 'coef_step.cu', 'graph_ops.cu', 'skinny.cu', 'bn_gemm.cu', 'flat3x3.cu',
-           'crowd_data.cu', 'crowd_labels.cu']
+           'crowd_data.cu', 'crowd_labels.cu', 'sgan.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '--use_fast_math=false',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-O2']
 

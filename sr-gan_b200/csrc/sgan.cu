@@ -1,0 +1,185 @@
+// SGAN method (sgan.py:18-67): the discriminator's head has K class logits (K = number_of_bins)
+// instead of one regression output.  Labeled loss = cross entropy against the bin of the real label; the GAN terms are
+// BCE-with-logits on logsumexp(logits); the gradient penalty differentiates BCE(logsumexp(logits(x_hat)), 0), a NONLINEAR
+// function of the logits, so its double backward needs the Hessian-vector product of that loss.  The trunk passes are the
+// SR-GAN step's (umma_conv.cu etc.); these kernels are the K-wide head: HBM-bound reads of the [rows, F] feature block
+// (age: F = 32 768) and per-sample K-vector arithmetic.  Logit-shaped arrays are stored TRANSPOSED, [K][rows], so that one
+// output's per-sample column is contiguous (it doubles as the row-scale vector of srgan_colsum for the head gradients).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxK = 16;
+
+// logitsT[k][r] = sum_c X[r,c] * W[k][c] + bias[k] : one block per row, the row is read ONCE for all K outputs
+template <typename T>
+__global__ void __launch_bounds__(256) head_logits_kernel(const T* __restrict__ X, int rows, int cols, const float* __restrict__ W,
+                                                          const float* __restrict__ bias, int K, float* __restrict__ out) {
+    __shared__ float red[32];
+    const int r = blockIdx.x;
+    const T* x = X + (long long)r * cols;
+    float acc[kMaxK];
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k) acc[k] = 0.f;
+    if (cols % 4 == 0) {
+        for (int c = 4 * threadIdx.x; c < cols; c += 4 * blockDim.x) {
+            const float4 v = ld4(x + c);
+#pragma unroll
+            for (int k = 0; k < kMaxK; ++k) {
+                if (k < K) {
+                    const float4 w = ld4(W + (long long)k * cols + c);
+                    acc[k] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[k]))));
+                }
+            }
+        }
+    } else {
+        for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+            const float v = to_f(x[c]);
+#pragma unroll
+            for (int k = 0; k < kMaxK; ++k)
+                if (k < K) acc[k] = fmaf(v, W[(long long)k * cols + c], acc[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k) {
+        if (k < K) {                                    // K is uniform over the block: no divergence around the barriers
+            const float s = block_sum(acc[k], red);
+            if (threadIdx.x == 0) out[(long long)k * rows + r] = s + (bias ? bias[k] : 0.f);
+        }
+    }
+}
+
+__device__ __forceinline__ float sigmoidf_(float z) { return z >= 0.f ? 1.f / (1.f + expf(-z)) : expf(z) / (1.f + expf(z)); }
+
+// softmax p[k] and z = logsumexp(l) of one sample's K logits (column r of the transposed array)
+__device__ __forceinline__ float softmax_lse(const float* __restrict__ lT, int K, int n, int r, float* p) {
+    float m = -INFINITY;
+    for (int k = 0; k < K; ++k) m = fmaxf(m, lT[(long long)k * n + r]);
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) {
+        p[k] = expf(lT[(long long)k * n + r] - m);
+        s += p[k];
+    }
+    const float inv = 1.f / s;
+    for (int k = 0; k < K; ++k) p[k] *= inv;
+    return m + logf(s);
+}
+
+// mode 0: cross entropy against the bin of y (nn.CrossEntropyLoss, sgan.py:20-31; bin = first minimum of |y - bins[k]|,
+//         utility.py:141-144): loss += scale * (lse - l[bin]), dl = scale * (p - onehot)
+// mode 1: nn.BCEWithLogitsLoss(logsumexp(l), target) (sgan.py:33-67): loss += scale * (softplus(z) - target * z),
+//         dl = scale * (sigmoid(z) - target) * p
+__global__ void __launch_bounds__(256) sgan_loss_kernel(const float* __restrict__ lT, int K, int n, int mode,
+                                                        const float* __restrict__ y, const float* __restrict__ bins, float target,
+                                                        float scale, float* __restrict__ loss, float* __restrict__ dlT) {
+    __shared__ float red[32];
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    float local = 0.f;
+    if (r < n) {
+        float p[kMaxK];
+        const float z = softmax_lse(lT, K, n, r, p);
+        if (mode == 0) {
+            int bin = 0;
+            float best = fabsf(y[r] - bins[0]);
+            for (int k = 1; k < K; ++k) {
+                const float d = fabsf(y[r] - bins[k]);
+                if (d < best) best = d, bin = k;
+            }
+            local = z - lT[(long long)bin * n + r];
+            if (dlT)
+                for (int k = 0; k < K; ++k) dlT[(long long)k * n + r] = scale * (p[k] - (k == bin ? 1.f : 0.f));
+        } else {
+            local = fmaxf(z, 0.f) - target * z + log1pf(expf(-fabsf(z)));
+            const float dz = sigmoidf_(z) - target;
+            if (dlT)
+                for (int k = 0; k < K; ++k) dlT[(long long)k * n + r] = scale * dz * p[k];
+        }
+    }
+    const float s = block_sum(local, red);
+    if (threadIdx.x == 0 && loss) atomicAdd(loss, scale * s);
+}
+
+// Hessian-vector product of L = c * softplus(logsumexp(l)) per sample: with p = softmax(l), sg = sigmoid(z), a = p . t,
+//   q = c * [ sg (1 - sg) a p + sg (p * t - a p) ]      (d/dl of sum_k s_k(l) t_k, s = dL/dl = c sg p)
+__global__ void __launch_bounds__(256) sgan_gp_second_kernel(const float* __restrict__ lT, const float* __restrict__ tT, int K, int n,
+                                                             float c, float* __restrict__ qT) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    float p[kMaxK];
+    const float z = softmax_lse(lT, K, n, r, p);
+    const float sg = sigmoidf_(z);
+    float a = 0.f;
+    for (int k = 0; k < K; ++k) a = fmaf(p[k], tT[(long long)k * n + r], a);
+    for (int k = 0; k < K; ++k) {
+        const float t = tT[(long long)k * n + r];
+        qT[(long long)k * n + r] = c * (sg * (1.f - sg) * a * p[k] + sg * (p[k] * t - a * p[k]));
+    }
+}
+
+// out[r,c] = (sum_k dT[k][r] * W[k][c]) * act'(href[r,c]) : the K-output form of srgan_seed_rows
+template <typename T>
+__global__ void __launch_bounds__(256) seed_rows_multi_kernel(T* __restrict__ out, int rows, int cols, const float* __restrict__ dT,
+                                                              const float* __restrict__ W, int K, const T* __restrict__ href, int act,
+                                                              float slope) {
+    const long long total = (long long)rows * cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / cols), c = (int)(i % cols);
+        float s = 0.f;
+        for (int k = 0; k < K; ++k) s = fmaf(dT[(long long)k * rows + r], W[(long long)k * cols + c], s);
+        out[i] = from_f<T>(s * act_bwd(to_f(href[i]), act, slope));
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int srgan_head_logits(const void* X, int rows, int cols, const float* W, const float* bias, int K, float* logitsT, int dtype,
+                      void* stream) {
+    SRGAN_REQUIRE(X && W && logitsT && rows >= 0 && cols > 0, "srgan_head_logits: bad arguments");
+    SRGAN_REQUIRE(K >= 1 && K <= kMaxK, "srgan_head_logits: K = %d outside 1..%d", K, kMaxK);
+    if (rows == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == SRGAN_F32) head_logits_kernel<float><<<rows, 256, 0, st>>>((const float*)X, rows, cols, W, bias, K, logitsT);
+    else head_logits_kernel<bf16><<<rows, 256, 0, st>>>((const bf16*)X, rows, cols, W, bias, K, logitsT);
+    SRGAN_CHECK_LAUNCH("head_logits_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_sgan_loss(const float* logitsT, int K, int n, int mode, const float* y, const float* bins, float target, float scale,
+                    float* loss, float* dlogitsT, void* stream) {
+    SRGAN_REQUIRE(logitsT && n >= 0, "srgan_sgan_loss: bad arguments");
+    SRGAN_REQUIRE(K >= 1 && K <= kMaxK, "srgan_sgan_loss: K = %d outside 1..%d", K, kMaxK);
+    SRGAN_REQUIRE(mode == 1 || (mode == 0 && y && bins), "srgan_sgan_loss: the cross-entropy mode needs labels and bins");
+    if (n == 0) return SRGAN_OK;
+    sgan_loss_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(logitsT, K, n, mode, y, bins, target, scale, loss, dlogitsT);
+    SRGAN_CHECK_LAUNCH("sgan_loss_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_sgan_gp_second(const float* logitsT, const float* tangentT, int K, int n, float c, float* qT, void* stream) {
+    SRGAN_REQUIRE(logitsT && tangentT && qT && n >= 0, "srgan_sgan_gp_second: bad arguments");
+    SRGAN_REQUIRE(K >= 1 && K <= kMaxK, "srgan_sgan_gp_second: K = %d outside 1..%d", K, kMaxK);
+    if (n == 0) return SRGAN_OK;
+    sgan_gp_second_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(logitsT, tangentT, K, n, c, qT);
+    SRGAN_CHECK_LAUNCH("sgan_gp_second_kernel");
+    return SRGAN_OK;
+}
+
+int srgan_seed_rows_multi(void* out, int rows, int cols, const float* dT, const float* W, int K, const void* href, int act,
+                          float slope, int dtype, void* stream) {
+    SRGAN_REQUIRE(out && dT && W && href && rows >= 0 && cols > 0, "srgan_seed_rows_multi: bad arguments");
+    SRGAN_REQUIRE(K >= 1 && K <= kMaxK, "srgan_seed_rows_multi: K = %d outside 1..%d", K, kMaxK);
+    if (rows == 0) return SRGAN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)rows * cols;
+    const int grid = (int)((total + 255) / 256 < 8LL * kNumSMs ? (total + 255) / 256 : 8LL * kNumSMs);
+    if (dtype == SRGAN_F32)
+        seed_rows_multi_kernel<float><<<grid, 256, 0, st>>>((float*)out, rows, cols, dT, W, K, (const float*)href, act, slope);
+    else
+        seed_rows_multi_kernel<bf16><<<grid, 256, 0, st>>>((bf16*)out, rows, cols, dT, W, K, (const bf16*)href, act, slope);
+    SRGAN_CHECK_LAUNCH("seed_rows_multi_kernel");
+    return SRGAN_OK;
+}
+
+}  // extern "C"

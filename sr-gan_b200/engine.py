@@ -44,7 +44,7 @@ def partial_scalar_slots(method: str):
     """Scalar slots that hold per-rank PARTIAL sums (per-sample loss terms, already divided by the global batch) and must
     be summed across ranks before they are read; the SR-GAN feature-distance losses are computed from all-reduced
     feature sums and are already global on every rank.  In DG-GAN every loss is a per-sample BCE mean."""
-    if method == 'dggan':
+    if method in ('dggan', 'sgan'):            # SGAN: cross entropy / BCE-of-logsumexp means, per sample as well
         return (SC_DNN, SC_LABELED, SC_UNLABELED, SC_FAKE, SC_GP, SC_GNORM, SC_GEN)
     return (SC_DNN, SC_LABELED, SC_GP, SC_GNORM)
 
@@ -947,6 +947,46 @@ class Engine:
         for h, _ in parts:
             self.ops.colsum(drow, n, 1, st.g(h + '.bias')[out_index:out_index + 1], 0, None)
 
+    # ------------------------------------------------------------------ SGAN K-logit head (sgan.py:18-67; csrc/sgan.cu)
+    def _logits(self, st: NetState, feats, n, name, bias=True):
+        """[K, n] fp32 class logits of `n` feature rows (bias=False: the tangent of the logits, W u_L)."""
+        net = st.net
+        out = self.buf(name, (net.head_outputs, n), self.mdt)
+        b = (st.hbias if net.head_parts is not None else st.params[net.head + '.bias']) if bias else None
+        self.ops.head_logits(feats, n, net.feature_size, st.whead, b, net.head_outputs, out)
+        return out
+
+    def _sgan_bins(self, cfg):
+        bins = tuple(float(v) for v in cfg.bins)
+        if len(bins) != self.d_net.head_outputs:
+            raise ValueError(f'SGAN: {len(bins)} bins for a discriminator with {self.d_net.head_outputs} class logits')
+        t = getattr(self, '_bins_cache', None)
+        if t is None or t[0] != bins:
+            t = self._bins_cache = (bins, torch.tensor(bins, dtype=torch.float32, device=self.device))
+        return t[1]
+
+    def _sgan_head_grads(self, st: NetState, feats, n, dT, bias=True):
+        """dW_k += sum_r dT[k][r] * feats[r,:] (and db_k += sum_r dT[k][r]) for the K outputs of the head."""
+        F = st.net.feature_size
+        for k in range(st.net.head_outputs):
+            if bias:
+                self._head_grads(st, feats, n, k, dT[k])
+            else:
+                self.ops.colsum(feats, n, F, self._head_grad_row(st, k), 0, dT[k])
+
+    def _sgan_labeled(self, st: NetState, feats, dfeats, n, y, cfg, Bg, loss_slot, tag):
+        """sgan.py:20-31: cross entropy of the K logits against the bin of the real label, seeds the backward pass."""
+        net, ops = st.net, self.ops
+        if isinstance(y, (tuple, list)):
+            raise ValueError('SGAN labels are real numbers [B] (age/sgan.py, coefficient/sgan.py)')
+        K, F = net.head_outputs, net.feature_size
+        fact, fslope = net.feature_act
+        lg = self._logits(st, feats, n, 'lg_' + tag)
+        dl = self.buf('dlg_' + tag, (K, n), self.mdt)
+        ops.sgan_loss(lg, K, n, 0, y, self._sgan_bins(cfg), 0.0, cfg.labeled_loss_multiplier / Bg, loss_slot, dl)
+        ops.seed_rows_multi(dfeats, n, F, dl, st.whead, K, feats, fact, fslope)
+        self._sgan_head_grads(st, feats, n, dl)
+
     # ------------------------------------------------------------------ labeled loss (srgan.py:414-417 | crowd/srgan.py:247-254)
     def _labeled(self, st: NetState, acts, deltas, B, y, cfg, Bg, loss_slot, pred, dpred):
         """Labeled loss on rows [0,B): writes the loss scalar and dLoss/dprediction; for the crowd application also
@@ -994,9 +1034,13 @@ class Engine:
         pred = self.buf('pred', (B,), self.mdt)
         dpred = self.buf('dpred', (B,), self.mdt)
         self.scalars[SC_DNN:SC_DNN + 1].zero_()
-        hook = self._labeled(st, acts, deltas, B, y, cfg, Bg, self.scalars[SC_DNN:SC_DNN + 1], pred, dpred)
-        self.ops.seed_rows(self._brows_feat(net, deltas, 0, B), B, F, None, dpred, st.whead[0:F], feats, fact, fslope)
-        self._head_grads(st, feats, B, 0, dpred)
+        if cfg.method == 'sgan':
+            self._sgan_labeled(st, feats, self._brows_feat(net, deltas, 0, B), B, y, cfg, Bg, self.scalars[SC_DNN:SC_DNN + 1], 'dnn')
+            hook = None
+        else:
+            hook = self._labeled(st, acts, deltas, B, y, cfg, Bg, self.scalars[SC_DNN:SC_DNN + 1], pred, dpred)
+            self.ops.seed_rows(self._brows_feat(net, deltas, 0, B), B, F, None, dpred, st.whead[0:F], feats, fact, fslope)
+            self._head_grads(st, feats, B, 0, dpred)
         self.backward(st, acts, deltas, 0, B, hook=hook)
         self.adam(st, lr, weight_decay, cfg.betas, cfg.eps, deferrable='DNN')
 
@@ -1038,15 +1082,32 @@ class Engine:
         self.last_gan_batch = B
         # ---- one D forward over [x; u; fake; x_hat]
         self.forward(D, acts, 0, 4 * B, keep_pre=3 * B)
-        if self.publish_features and not dggan:
+        if self.publish_features and cfg.method == 'srgan':
             self.buf('feat_snap', (4 * B * F,)).copy_(fblk(0, 4 * B))
         # ---- labeled loss (srgan.py:329-335, :414-417)
         pred = self.buf('pred', (B,), self.mdt)
         dpred = self.buf('dpred', (B,), self.mdt)
-        hook = self._labeled(D, acts, deltas, B, y, cfg, Bg, sc[SC_LABELED:SC_LABELED + 1], pred, dpred)
+        sgan = cfg.method == 'sgan'
+        hook = None if sgan else self._labeled(D, acts, deltas, B, y, cfg, Bg, sc[SC_LABELED:SC_LABELED + 1], pred, dpred)
         gamma_L = dblk(4 * B, 5 * B)
         s_norm = self.buf('s_norm', (B,), self.mdt)
-        if not dggan:
+        if sgan:
+            # ---- SGAN (sgan.py:20-58): cross entropy on x; BCE(logsumexp(logits), 1 | 0) on u | fake, both times the
+            # matching multiplier; GP target = BCE(logsumexp(logits(x_hat)), 0) * penalty multiplier, a scalar over the batch
+            K = net.head_outputs
+            self._sgan_labeled(D, fblk(0, B), dblk(0, B), B, y, cfg, Bg, sc[SC_LABELED:SC_LABELED + 1], 'x')
+            gp_c = cfg.gradient_penalty_multiplier / Bg
+            lg_h = self._logits(D, fblk(3 * B, 4 * B), B, 'lg_h')
+            s_h = self.buf('dlg_h', (K, B), self.mdt)
+            for tag, lo, target, slot in (('u', B, 1.0, SC_UNLABELED), ('f', 2 * B, 0.0, SC_FAKE)):
+                lg = self._logits(D, fblk(lo, lo + B), B, 'lg_' + tag)
+                dl = self.buf('dlg_' + tag, (K, B), self.mdt)
+                ops.sgan_loss(lg, K, B, 1, None, None, target, cfg.matching_loss_multiplier / Bg, sc[slot:slot + 1], dl)
+                ops.seed_rows_multi(dblk(lo, lo + B), B, F, dl, D.whead, K, fblk(lo, lo + B), fact, fslope)
+                self._sgan_head_grads(D, fblk(lo, lo + B), B, dl)
+            ops.sgan_loss(lg_h, K, B, 1, None, None, 0.0, gp_c, None, s_h)          # s = d(interpolates_loss)/d(logits)
+            ops.seed_rows_multi(gamma_L, B, F, s_h, D.whead, K, fblk(3 * B, 4 * B), fact, fslope)
+        elif not dggan:
             # ---- feature sums -> (all-reduce) -> distance losses (srgan.py:337-358, :438-449)
             sums = self.buf('fsums', (3, F), self.mdt)
             sums.zero_()
@@ -1088,7 +1149,8 @@ class Engine:
             self._head_grads(D, fblk(B, 2 * B), B, 1, dsu)
             self._head_grads(D, fblk(2 * B, 3 * B), B, 1, dsf)
             ops.seed_rows(gamma_L, B, F, w1, None, None, fblk(3 * B, 4 * B), fact, fslope)
-        self._head_grads(D, fblk(0, B), B, 0, dpred)
+        if not sgan:
+            self._head_grads(D, fblk(0, B), B, 0, dpred)
         # ---- gradient penalty (srgan.py:360-375) without autograd: SURVEY App. C.3
         g0 = self.buf('g0', (B * E,))
         self.gchain(D, acts, deltas, B, g0)
@@ -1097,7 +1159,18 @@ class Engine:
         ops.gradnorm_penalty(g0, B, E, cfg.gradient_penalty_multiplier / Bg, 1.0 / Bg, gnorm, sc[SC_GP:SC_GP + 1],
                              sc[SC_GNORM:SC_GNORM + 1], u0)
         self.tangent(D, acts, B)
-        if not dggan:
+        if sgan:
+            # <u0, g> = sum_k s_k (W_k . u_L): its parameter gradient has three parts -- through the Jacobian (the tangent
+            # block of the weight-gradient launches, like SR-GAN), through W explicitly (s_k-weighted sums of the tangent
+            # features), and through s(logits(x_hat)): q = Hessian . (W u_L) is an ordinary backward seed on the x_hat rows
+            lg_t = self._logits(D, fblk(4 * B, 5 * B), B, 'lg_t', bias=False)
+            q = self.buf('q_h', (K, B), self.mdt)
+            ops.sgan_gp_second(lg_h, lg_t, K, B, gp_c, q)
+            ops.seed_rows_multi(dblk(3 * B, 4 * B), B, F, q, D.whead, K, fblk(3 * B, 4 * B), fact, fslope)
+            self._sgan_head_grads(D, fblk(3 * B, 4 * B), B, q)
+            self._sgan_head_grads(D, fblk(4 * B, 5 * B), B, s_h, bias=False)
+            self.backward(D, acts, deltas, 0, 4 * B, 0, 5 * B, hook=None)
+        elif not dggan:
             ops.gp_feature_seed(fblk(4 * B, 5 * B), fblk(3 * B, 4 * B), s_norm, dblk(3 * B, 4 * B), B, F, fact, fslope)
             # ---- one backward over [x; u; fake; x_hat], weight gradients also over the tangent block
             self.backward(D, acts, deltas, 0, 4 * B, 0, 5 * B, hook=hook)
@@ -1125,7 +1198,15 @@ class Engine:
         gacts[-1] = fake2
         self.load_input(gnet, z2, gacts[0], B)
         self.forward(G, gacts, 0, B)
-        if not dggan:
+        if cfg.method == 'sgan':
+            # sgan.py:60-67: generator loss = -BCE(logsumexp(logits(G(z2))), 0), no multiplier
+            K = net.head_outputs
+            self.forward(D, acts, 0, B, keep_pre=False)
+            lg = self._logits(D, fblk(0, B), B, 'lg_x')
+            dl = self.buf('dlg_x', (K, B), self.mdt)
+            ops.sgan_loss(lg, K, B, 1, None, None, 0.0, -1.0 / Bg, sc[SC_GEN:SC_GEN + 1], dl)
+            ops.seed_rows_multi(dblk(0, B), B, F, dl, D.whead, K, fblk(0, B), fact, fslope)
+        elif not dggan:
             self.forward(D, acts, 0, 2 * B, keep_pre=False)     # rows [B,2B) still hold u
             if self.publish_features:
                 self.buf('feat_snap', (4 * B * F,))[2 * B * F:3 * B * F].copy_(fblk(0, B))      # srgan.py:386
@@ -1167,6 +1248,8 @@ class Engine:
         return tuple(t[r0:r1] for t in y) if isinstance(y, (tuple, list)) else y[r0:r1]
 
     def dnn_step_micro(self, x, y, cfg, lr, weight_decay, mb):
+        if cfg.method == 'sgan':
+            raise NotImplementedError('micro-batched steps cover srgan and dggan')
         self.ops.begin()
         self._scope = 'dnn'
         st, net = self.DNN, self.d_net
@@ -1193,6 +1276,8 @@ class Engine:
         self.adam(st, lr, weight_decay, cfg.betas, cfg.eps, deferrable='DNN')
 
     def gan_step_micro(self, x, y, u, z, alpha, z2, cfg, train_generator, mb):
+        if cfg.method == 'sgan':
+            raise NotImplementedError('micro-batched steps cover srgan and dggan')
         ops, D, G, net, gnet = self.ops, self.D, self.G, self.d_net, self.g_net
         ops.begin()
         self._scope = 'gan'

@@ -121,6 +121,9 @@ class StepConfig:
             setattr(self, k, name)
         self.betas = (0.9, 0.999)
         self.eps = 1e-8
+        # sgan: the bin centres the experiment builds in __init__ (age/sgan.py:14, coefficient/sgan.py:15)
+        bins = getattr(settings, 'bins', None)
+        self.bins = tuple(float(v) for v in bins) if bins is not None else ()
 
 
 # ------------------------------------------------------------------------------------------------ parameter containers
@@ -268,8 +271,15 @@ class StepRunner:
         d_net, g_net = nets.describe_module(D, direct, fuse), nets.describe_module(G)
         if nets.describe_module(DNN, direct, fuse) != d_net:
             raise ValueError('DNN and D must share an architecture (srgan.py model_setup)')
-        if method not in ('srgan', 'dggan'):
-            raise ValueError(f'method={method!r}: the B200 path covers srgan and dggan (sgan: SURVEY 8f rank 3)')
+        if method not in ('srgan', 'dggan', 'sgan'):
+            raise ValueError(f'method={method!r}: the B200 path covers srgan, dggan and sgan')
+        if method == 'sgan':
+            if d_net.family not in ('dcgan', 'coefficient') or not 3 <= d_net.head_outputs <= 16:
+                raise ValueError('SGAN (sgan.py) is covered for the class-logit discriminators of age/sgan.py, driving and '
+                                 'coefficient/sgan.py with 3..16 bins; crowd/sgan.py\'s JointDCDiscriminator is not')
+            if len(getattr(settings, 'bins', None) or ()) != d_net.head_outputs:
+                raise ValueError(f'SGAN: settings.bins must hold the {d_net.head_outputs} bin centres of the experiment '
+                                 '(AgeSganExperiment.bins, age/sgan.py:14); the mix-in copies them from self.bins')
         if method == 'dggan' and d_net.head_outputs != 2:
             raise ValueError('DG-GAN needs the two-output discriminator (coefficient/models.py:53-72, crowd/models.py:929-1046)')
         if method == 'srgan' and d_net.head_outputs != 1:
@@ -303,7 +313,7 @@ class StepRunner:
         self._dnn_stream, self._dnn_done = None, None
         # coefficient application: one persistent cooperative kernel per step method (csrc/coef_step.cu) instead of
         # ~150 generic launches; single rank only (the feature sums are combined inside the kernel)
-        self.persistent = (self._persistent_shape_ok(d_net, g_net) and comm is None
+        self.persistent = (method != 'sgan' and self._persistent_shape_ok(d_net, g_net) and comm is None
                            and bool(getattr(settings, 'use_persistent_kernel', True))
                            and os.environ.get('SRGAN_NO_PERSISTENT', '0') != '1')
         self._coef_tables = None
@@ -630,7 +640,7 @@ class StepRunner:
         G(z2) under the updated discriminator when the generator was trained (srgan.py:332-386).  Needs
         engine.publish_features (set before the step); a per-rank shard under data parallelism."""
         eng = self.engine
-        if not eng.publish_features or self.method == 'dggan':
+        if not eng.publish_features or self.method != 'srgan':
             return None
         self._wait_pending()
         F = eng.d_net.feature_size
@@ -759,12 +769,17 @@ class B200StepMixin:
         """DG-GAN = the experiment overrides the loss hooks the way coefficient/dggan.py:22-64 / crowd/dggan.py:17-49 do;
         recognised by the discriminator's second head output (DgganMLP, KnnDenseNetCatDggan), cross-checked against the
         class hierarchy so that a mismatched pair raises instead of training the wrong loss."""
-        by_module = nets.describe_module(self.D).head_outputs == 2
-        by_class = any('dggan' in c.__name__.lower() for c in type(self).__mro__)
+        outputs = nets.describe_module(self.D).head_outputs
+        names = [c.__name__.lower() for c in type(self).__mro__]
+        # SGAN = a subclass of sgan.py's SganExperiment with a K-logit discriminator (age/sgan.py:16-20, coefficient/sgan.py:17-21)
+        by_class = 'dggan' if any('dggan' in n for n in names) else 'sgan' if any('sgan' in n for n in names) else 'srgan'
+        by_module = 'dggan' if outputs == 2 else 'sgan' if outputs > 2 else 'srgan'
         if by_module != by_class:
-            raise ValueError(f'{type(self).__name__}: discriminator has {2 if by_module else 1} head output(s) but the '
-                             f'experiment class is {"" if by_class else "not "}a DG-GAN experiment')
-        return 'dggan' if by_module else 'srgan'
+            raise ValueError(f'{type(self).__name__}: discriminator has {outputs} head output(s) ({by_module}) but the '
+                             f'experiment class is a {by_class} experiment')
+        if by_class == 'sgan':
+            self.settings.bins = tuple(float(v) for v in self.bins)
+        return by_class
 
     def _b200_runner(self) -> StepRunner:
         r = getattr(self, '_b200', None)
@@ -786,7 +801,9 @@ class B200StepMixin:
         r.dnn_step(examples, labels, lr=group['lr'], weight_decay=group['weight_decay'])
         if self.dnn_summary_writer.is_summary_step():
             self.dnn_summary_writer.add_scalar('Discriminator/Labeled Loss', r.scalars()['dnn_loss'])
-            if r.method != 'dggan' or r.engine.d_net.family == 'coefficient':     # srgan.py:270-271 (KnnDenseNetCatDggan publishes no .features)
+            # srgan.py:270-271: only when the module sets `.features` (KnnDenseNetCatDggan and SganMLP do not)
+            fam = r.engine.d_net.family
+            if (r.method == 'srgan') or (r.method == 'dggan' and fam == 'coefficient') or (r.method == 'sgan' and fam == 'dcgan'):
                 f = r.dnn_step_features(examples)
                 self.DNN.features = f
                 self.dnn_summary_writer.add_scalar('Feature Norm/Labeled', f.norm(dim=1).mean().item())
@@ -802,7 +819,7 @@ class B200StepMixin:
                              'd_optimizer.param_groups was changed away from them')
         # side effects of srgan.py:332-386 (device tensors; per-rank shards under data parallelism)
         self.gradient_norm = r.gradient_norm()
-        if r.engine.publish_features and r.method != 'dggan':
+        if r.engine.publish_features and r.method == 'srgan':
             self.labeled_features = r.step_features('labeled')
             self.unlabeled_features = r.step_features('unlabeled')
             self.fake_features = r.step_features('fake')

@@ -176,7 +176,7 @@ class Net:
     family: str                    # 'coefficient' | 'dcgan' | 'crowd'
     layers: List[Layer]
     head: Optional[str] = None     # state_dict prefix of the prediction head (D only)
-    head_outputs: int = 0          # 1 (srgan) or 2 (dggan)
+    head_outputs: int = 0          # 1 (srgan), 2 (dggan) or the number of bins (sgan)
     head_master_kind: str = 'linear'   # 'linear' [out, F] | 'conv_full' [out, C, H, W] -> NHWC feature order
     input_chw: Tuple[int, int, int] = (0, 1, 1)    # (C, H, W) of the reference-side input
     feature_chw: Tuple[int, int, int] = (0, 1, 1)  # (C, H, W) of `.features` before flattening
@@ -234,12 +234,12 @@ def linear_geom(n_out, n_in):
     return Geom(1, 1, n_out, 1, 1, n_in, 1, 1, 1, 0)
 
 
-def coefficient_d(hidden=10, n_in=50, dggan=False) -> Net:
-    """coefficient/models.py:31-72."""
+def coefficient_d(hidden=10, n_in=50, dggan=False, n_out=None) -> Net:
+    """coefficient/models.py:31-72; n_out = number_of_bins: SganMLP (:75-93, hidden 100)."""
     sizes = [n_in, hidden, hidden, hidden]
     layers = [Layer(f'linear{i}', 'down', linear_geom(b, a), ACT_LEAKY, 0.01, (b, a, 1, 1))
               for i, (a, b) in enumerate(zip(sizes[:-1], sizes[1:]), 1)]
-    return Net('D', 'coefficient', layers, head='linear4', head_outputs=2 if dggan else 1,
+    return Net('D', 'coefficient', layers, head='linear4', head_outputs=n_out or (2 if dggan else 1),
                input_chw=(n_in, 1, 1), feature_chw=(hidden, 1, 1))
 
 
@@ -422,9 +422,7 @@ def describe_module(module, direct_concat=False, fuse_bn=0) -> Net:
         n_out = sd['linear4.weight'][0]
         if hasattr(module, 'input_size'):                       # coefficient Generator
             return coefficient_g(h, n_in, n_out)
-        if n_out > 2:
-            raise NotImplementedError('SganMLP (sgan.py) is outside the SR-GAN hot path (SURVEY 8f rank 3)')
-        return coefficient_d(h, n_in, dggan=(n_out == 2))
+        return coefficient_d(h, n_in, dggan=(n_out == 2), n_out=n_out)
     if 'conv_layer1.conv0.weight' in sd and 'map_module3.linear1.weight' in sd and 'final_count_feature_layer.weight' in sd:
         import re
         blocks = {}

@@ -38,6 +38,7 @@ _EXPORTS = (
     'srgan_adam_layout_multi', 'srgan_bn_dgrad', 'srgan_bn_conv_down', 'srgan_bn_conv_wgrad', 'srgan_bn_conv_dgrad',
     'srgan_crowd_extract_patches', 'srgan_sliding_window_merge', 'srgan_crowd_eval_sums',
     'srgan_knn_maps', 'srgan_point_density_map',
+    'srgan_head_logits', 'srgan_sgan_loss', 'srgan_sgan_gp_second', 'srgan_seed_rows_multi',
     'srgan_sliding_window_workspace_bytes', 'srgan_crowd_eval_workspace_bytes',
 )
 
@@ -117,6 +118,10 @@ def load_library(path: str = LIB_PATH):
     c_d = ctypes.c_double
     lib.srgan_knn_maps.argtypes = [vp, c_int, c_int, c_int, c_int, c_d, c_d, vp, vp, vp]
     lib.srgan_point_density_map.argtypes = [vp, c_int, c_int, c_int, vp, vp, vp]
+    lib.srgan_head_logits.argtypes = [vp, c_int, c_int, vp, vp, c_int, vp, c_int, vp]
+    lib.srgan_sgan_loss.argtypes = [vp, c_int, c_int, c_int, vp, vp, c_f, c_f, vp, vp, vp]
+    lib.srgan_sgan_gp_second.argtypes = [vp, vp, c_int, c_int, c_f, vp, vp]
+    lib.srgan_seed_rows_multi.argtypes = [vp, c_int, c_int, vp, vp, c_int, vp, c_int, c_f, c_int, vp]
     lib.srgan_tensor_launch_count.restype = c_ll
     lib.srgan_simt_fallback_count.restype = c_ll
     for name in _EXPORTS[7:]:
@@ -399,6 +404,29 @@ class CudaOps:
         self._ck(self.lib.srgan_avgpool_bwd(self._p(dy), dy_pitch, dy_c0, self._p(dx, dy.dtype), x_pitch, n, H, W, C, k,
                                             self._p(href, dy.dtype) if href is not None else None, act, slope, _dt(dy.dtype),
                                             self._stream()), 'srgan_avgpool_bwd')
+
+    # ---- SGAN K-logit head (csrc/sgan.cu); logit-shaped tensors are [K, rows] fp32
+    def head_logits(self, X, rows, cols, W, bias, K, out):
+        f32 = torch.float32
+        self._ck(self.lib.srgan_head_logits(self._p(X), rows, cols, self._p(W, f32), self._p(bias.detach() if bias is not None else None, f32),
+                                            K, self._p(out, f32), _dt(X.dtype), self._stream()), 'srgan_head_logits')
+
+    def sgan_loss(self, logitsT, K, n, mode, y, bins, target, scale, loss_out, dlogitsT):
+        f32 = torch.float32
+        self._ck(self.lib.srgan_sgan_loss(self._p(logitsT, f32), K, n, mode, self._p(y.detach() if y is not None else None, f32),
+                                          self._p(bins, f32), target, scale, self._p(loss_out, f32), self._p(dlogitsT, f32),
+                                          self._stream()), 'srgan_sgan_loss')
+
+    def sgan_gp_second(self, logitsT, tangentT, K, n, c, qT):
+        f32 = torch.float32
+        self._ck(self.lib.srgan_sgan_gp_second(self._p(logitsT, f32), self._p(tangentT, f32), K, n, c, self._p(qT, f32),
+                                               self._stream()), 'srgan_sgan_gp_second')
+
+    def seed_rows_multi(self, out, rows, cols, dT, W, K, href, act, slope):
+        f32 = torch.float32
+        self._ck(self.lib.srgan_seed_rows_multi(self._p(out), rows, cols, self._p(dT, f32), self._p(W, f32), K,
+                                                self._p(href, out.dtype), act, slope, _dt(out.dtype), self._stream()),
+                 'srgan_seed_rows_multi')
 
     def crowd_loss(self, pred, density, maps, map_label, B, HW, order, scale, map_mult, loss_out, dpred, dm):
         f32 = torch.float32

@@ -33,7 +33,7 @@ class Golden:
         c = O.StepConfig()
         for k, v in self.cfg.items():
             if hasattr(c, k):
-                setattr(c, k, v)
+                setattr(c, k, tuple(v) if isinstance(v, list) else v)
         return c
 
     def oracle_state(self, dtype=torch.float32) -> O.OracleState:
@@ -47,4 +47,4 @@ class Golden:
                              self.group('init/DNN', dtype))
 
 
-ALL = ('coefficient_srgan', 'coefficient_srgan_altdist', 'coefficient_dggan', 'dcgan_mini')
+ALL = ('coefficient_srgan', 'coefficient_srgan_altdist', 'coefficient_dggan', 'dcgan_mini', 'dcgan_sgan_mini', 'coefficient_sgan')

@@ -14,13 +14,15 @@ def settings_from_cfg(cfg: O.StepConfig, precision='fp32'):
     s.matching_distance_function = getattr(srgan_b200, cfg.matching_distance_function)
     s.contrasting_distance_function = getattr(srgan_b200, cfg.contrasting_distance_function)
     s.precision = precision
+    s.bins = tuple(cfg.bins)
     return s
 
 
 def modules_from_state(st: O.OracleState, **dcgan_kwargs):
     if st.d_spec.family == 'coefficient':
-        n_out = 2 if st.d_spec.dggan else 1
-        D, DNN, G = srgan_b200.CoefficientMLP(10, n_out), srgan_b200.CoefficientMLP(10, n_out), srgan_b200.CoefficientGenerator(10)
+        n_out, hidden = st.D['linear4.weight'].shape                     # 1 | 2 (DgganMLP) | number_of_bins (SganMLP, hidden 100)
+        D, DNN = srgan_b200.CoefficientMLP(hidden, n_out), srgan_b200.CoefficientMLP(hidden, n_out)
+        G = srgan_b200.CoefficientGenerator(st.G['linear1.weight'].shape[0])
     elif st.d_spec.family == 'crowd':
         sp = st.d_spec
         z_dim, c8, k, _ = st.G['fc.0.weight'].shape
@@ -31,8 +33,9 @@ def modules_from_state(st: O.OracleState, **dcgan_kwargs):
         G = srgan_b200.DcganGenerator(z_dim, k * 16, c8 // 8)
     else:
         z_dim, c8, k, _ = st.G['fc.0.weight'].shape
-        D = srgan_b200.DcganDiscriminator(k * 16, c8 // 8)
-        DNN = srgan_b200.DcganDiscriminator(k * 16, c8 // 8)
+        n_out = st.D['layer5.0.weight'].shape[0]                          # number_of_bins for the SGAN discriminator
+        D = srgan_b200.DcganDiscriminator(k * 16, c8 // 8, n_out)
+        DNN = srgan_b200.DcganDiscriminator(k * 16, c8 // 8, n_out)
         G = srgan_b200.DcganGenerator(z_dim, k * 16, c8 // 8)
     D.load_state_dict({k: v.float() for k, v in st.D.items()})
     G.load_state_dict({k: v.float() for k, v in st.G.items()})

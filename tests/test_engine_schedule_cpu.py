@@ -14,10 +14,11 @@ from tests.torch_ops import TorchOps
 
 def build_engine(st: O.OracleState, dtype, image_size=None, conv_dim=None, z_dim=None, comm=None):
     if st.d_spec.family == 'coefficient':
-        d_net = nets.coefficient_d(10, 50, st.d_spec.dggan)
-        g_net = nets.coefficient_g(10, 10, 50)
+        n_out, hidden = st.D['linear4.weight'].shape
+        d_net = nets.coefficient_d(hidden, 50, st.d_spec.dggan, n_out=n_out)
+        g_net = nets.coefficient_g(st.G['linear1.weight'].shape[0], 10, 50)
     else:
-        d_net = nets.dcgan_d(image_size, conv_dim)
+        d_net = nets.dcgan_d(image_size, conv_dim, n_out=st.D['layer5.0.weight'].shape[0])
         g_net = nets.dcgan_g(image_size, conv_dim, z_dim)
     D = {k: v.clone() for k, v in st.D.items()}
     G = {k: v.clone() for k, v in st.G.items()}
@@ -35,7 +36,8 @@ def read_scalars(eng):
                 gradient_norm_mean=s[5], generator_loss=s[6])
 
 
-@pytest.mark.parametrize('name', ['coefficient_srgan', 'coefficient_srgan_altdist', 'coefficient_dggan', 'dcgan_mini'])
+@pytest.mark.parametrize('name', ['coefficient_srgan', 'coefficient_srgan_altdist', 'coefficient_dggan', 'dcgan_mini',
+                                  'dcgan_sgan_mini', 'coefficient_sgan'])
 def test_schedule_matches_oracle_fp64(name):
     g = Golden(name)
     dt = torch.float64

@@ -35,16 +35,19 @@ def _case(app):
             return (torch.randn(B, 50, generator=gen), torch.rand(B, generator=gen) * 2 - 1, torch.randn(B, 50, generator=gen),
                     torch.randn(B, 10, generator=gen), torch.rand(B, 1, generator=gen), torch.randn(B, 10, generator=gen))
         return 'coefficient', method, st, kw, batch
-    if app == 'age':
+    if app in ('age', 'age_sgan'):
         B = 8
-        st = O.init_dcgan(seed=2, image_size=64, conv_dim=16, z_dim=32, scale=3.0)
+        sgan = app == 'age_sgan'                          # AgeSganExperiment (age/sgan.py): 10 class logits
+        st = O.init_dcgan(seed=2, image_size=64, conv_dim=16, z_dim=32, scale=3.0, n_out=10 if sgan else 1)
         kw = dict(batch_size=B, matching_loss_multiplier=1e2, contrasting_loss_multiplier=1e1, gradient_penalty_multiplier=1e2)
+        if sgan:
+            kw.update(matching_loss_multiplier=1.0, number_of_bins=10)
 
         def batch():
             return (torch.rand(B, 3, 64, 64, generator=gen) * 2 - 1, torch.rand(B, generator=gen) * 85 + 10,
                     torch.rand(B, 3, 64, 64, generator=gen) * 2 - 1, torch.randn(B, 32, generator=gen),
                     torch.rand(B, 1, 1, 1, generator=gen), torch.randn(B, 32, generator=gen))
-        return 'age', 'srgan', st, kw, batch
+        return 'age', ('sgan' if sgan else 'srgan'), st, kw, batch
     B = 2                                                 # crowd: the full DenseNet-201 KnnDenseNetCat + DCGenerator at 224
     st = O.init_crowd(seed=5, scale=1.56)
     kw = dict(batch_size=B, matching_loss_multiplier=1e3, contrasting_loss_multiplier=1e2, gradient_penalty_multiplier=1e2,
@@ -57,7 +60,7 @@ def _cuda(t):
     return tuple(e.cuda() for e in t) if isinstance(t, tuple) else t.cuda()
 
 
-@pytest.mark.parametrize('app', ['coefficient', 'coefficient_dggan', 'age', 'crowd'])
+@pytest.mark.parametrize('app', ['coefficient', 'coefficient_dggan', 'age', 'age_sgan', 'crowd'])
 def test_mixin_on_reference_class_matches_reference_step(app):
     import srgan_b200
     name, method, st, kw, batch = _case(app)

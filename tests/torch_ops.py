@@ -180,6 +180,47 @@ class TorchOps:
         r = a * u.view(n, E).to(a.dtype) + (1 - a) * fake.view(n, E).to(a.dtype)
         out.copy_(r.reshape(-1).to(out.dtype))
 
+    # ---- SGAN K-logit head (csrc/sgan.cu); logit-shaped tensors are [K, rows]
+    def head_logits(self, X, rows, cols, W, bias, K, out):
+        self.launches += 1
+        x = X[:rows * cols].view(rows, cols).to(out.dtype)
+        l = x @ W[:K * cols].view(K, cols).to(out.dtype).t()
+        if bias is not None:
+            l = l + bias.detach().reshape(-1)[:K].to(out.dtype).view(1, K)
+        out.copy_(l.t())
+
+    def sgan_loss(self, logitsT, K, n, mode, y, bins, target, scale, loss_out, dlogitsT):
+        self.launches += 1
+        l = logitsT.t()
+        p = torch.softmax(l, dim=1)
+        z = torch.logsumexp(l, dim=1)
+        if mode == 0:
+            idx = (y.to(l.dtype).reshape(-1, 1) - bins.to(l.dtype).reshape(1, -1)).abs().min(dim=1)[1]
+            loss = (z - l.gather(1, idx.view(-1, 1)).squeeze(1)).sum()
+            d = p - torch.nn.functional.one_hot(idx, K).to(l.dtype)
+        else:
+            loss = (torch.clamp(z, min=0) - z * target + torch.log1p(torch.exp(-z.abs()))).sum()
+            d = (torch.sigmoid(z) - target).view(-1, 1) * p
+        if loss_out is not None:
+            loss_out += scale * loss
+        if dlogitsT is not None:
+            dlogitsT.copy_((scale * d).t())
+
+    def sgan_gp_second(self, logitsT, tangentT, K, n, c, qT):
+        self.launches += 1
+        l, t = logitsT.t(), tangentT.t()
+        p = torch.softmax(l, dim=1)
+        sg = torch.sigmoid(torch.logsumexp(l, dim=1)).view(-1, 1)
+        a = (p * t).sum(1, keepdim=True)
+        qT.copy_((c * (sg * (1 - sg) * a * p + sg * (p * t - a * p))).t())
+
+    def seed_rows_multi(self, out, rows, cols, dT, W, K, href, act, slope):
+        self.launches += 1
+        cd = href.dtype if href.dtype == torch.float64 else torch.float32
+        v = dT.to(cd).t() @ W[:K * cols].view(K, cols).to(cd)
+        v = v * dact(href[:rows * cols].view(rows, cols).to(cd), act, slope)
+        out.copy_(v.reshape(-1).to(out.dtype))
+
     def labeled_loss(self, pred, y, n, order, scale, loss_out, dpred):
         self.launches += 1
         d = pred - y.to(pred.dtype)
