@@ -465,6 +465,52 @@ def run_workload(name, args, dev, comm, world, rank, local_rank, steps, warmup, 
     d2h = eng.scalars.numel() * 4
     overlap_flag = bool(exp.runner.overlap_dnn)
 
+    # ---------------- crowd: the same loop fed by the device-side input pipeline (sr-gan_b200/crowd_data.py): the
+    # full images / density labels / kNN maps stay resident in HBM and every step gathers its labeled and unlabeled patches
+    # with srgan_crowd_extract_patches from freshly drawn positions; only the two [B,4] position tables cross PCIe
+    pipeline = None
+    if name == 'crowd':
+        import random
+        import numpy as np
+        from srgan_b200 import crowd_data
+        rs = np.random.RandomState(11 + rank)
+        shape = (768, 1024)                                # ShanghaiTech part A images are up to 768 x 1024
+        full = [(rs.randint(0, 256, size=shape + (3,)).astype(np.uint8),
+                 (rs.rand(*shape) < 6.5e-4).astype(np.float32), (1.0 / (1.0 + 50.0 * rs.rand(*shape))).astype(np.float32))
+                for _ in range(16)]
+        store = crowd_data.CrowdStore(full, device=dev)
+        dataset = crowd_data.TransformedDataset(store, 224, 224, rng=random.Random(rank))
+
+        def next_batches():
+            # train_dataset_loader's and unlabeled_dataset_loader's batches (crowd/srgan.py:59-68): host draws, then one gather each
+            return dataset.batch(B), dataset.batch(B)
+
+        def pipe_loop(n):
+            sc_ = None
+            nxt = next_batches()
+            for i in range(n):
+                (xi, li, mi), (ui, _, _) = nxt
+                step(i, xi, (li, mi), ui)
+                if i + 1 < n:
+                    nxt = next_batches()                   # drawn while the step runs, gathered right behind it (a loader's prefetch)
+                sc_ = exp.runner.scalars()
+            return sc_
+        pipe_loop(3)
+        barrier()
+        e0.record()
+        pipe_loop(steps)
+        e1.record()
+        barrier()
+        tp = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        pipeline = {'value': world * 1e3 / (float(tp.item()) / steps), 'unit': 'steps/s',
+                    'h2d_bytes_per_step': 2 * B * 16, 'd2h_bytes_per_step': int(d2h),
+                    'resident_store_bytes': int(store.pixels * 11),
+                    'what': 'e2e with the device-side input pipeline: random 224x224 patches (+ flip, normalise) of 16 resident '
+                            '768x1024 examples gathered on the GPU every step for the labeled and the unlabeled batch'}
+        del store, dataset, full
+
     # release the engine's buffers before the baselines / the secondary workload allocate theirs
     del exp, eng, x, y, u, slots
     gc.collect()
@@ -523,6 +569,8 @@ def run_workload(name, args, dev, comm, world, rank, local_rank, steps, warmup, 
             'e2e': {'value': e2e_value, 'unit': 'steps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
             # the losses of the last timed step (global-batch values: equal across N at equal global batch, tests/test_gpu_dist.py)
             'last_scalars': sc, 'last_scalars_resident': scalars_resident}
+    if pipeline is not None:
+        line['e2e_device_pipeline'] = pipeline
     if world == 1 and with_gpu_baseline:
         line['gpu_baseline'] = gpu_baseline(name, B, dev)
     if world == 1 and with_cpu_baseline:
