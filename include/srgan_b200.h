@@ -323,6 +323,12 @@ int srgan_coefficient_step(const float* const* d_ptrs, const float* const* g_ptr
 int srgan_crowd_extract_patches(const uint8_t* images, const float* labels, const float* maps, const long long* pixel_offset,
                                 const int* heights, const int* widths, int n_images, const int* pos, int B, int patch,
                                 float* img_out, float* label_out, float* map_out, void* stream);
+/* Age / driving datasets: one batch of AgeDataset.__getitem__ (age/data.py:52-60: imageio HWC uint8 -> transpose -> fp32 ->
+ * utility.to_normalized_range, utility.py:129-132) or SteeringAngleDataset.__getitem__ (driving/data.py:44-51: CHW uint8 .npy)
+ * from the decoded dataset resident in device memory: out[b] = images[index[b]] as [C,H,W] fp32 in [-1, 1] (IEEE division by
+ * 127.5, then - 1: bit-exact), labels_out[b] = labels[index[b]] (both may be NULL).  hwc != 0: stored samples are [H,W,C]. */
+int srgan_image_batch(const uint8_t* images, int hwc, const long long* index, int B, int C, int H, int W, float* out,
+                      const float* labels, float* labels_out, void* stream);
 /* CrowdExperiment.predict_full_example, crowd/srgan.py:345-395: merges the per-patch predictions of a sliding window over
  * one H x W image.  Window (yi, xi) is patch yi*nx + xi and covers rows [ys[yi]-patch/2, ys[yi]+patch/2) (clipped to the
  * image), columns likewise.  full_label[Y,X] = mean over the covering patches of their predicted density at that pixel

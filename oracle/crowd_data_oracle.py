@@ -14,6 +14,7 @@ computes on the host for SURVEY section 8 rows f1 (input pipeline) and f2 (valid
   sliding_positions        crowd/data.py:525-539 (ImageSlidingWindowDataset.__init__; sorted instead of list(set(..)) order)
   predict_full_example     crowd/srgan.py:332-395 (scipy.misc.imresize to the SAME size = identity: patch 224, label 224)
   evaluation_sums          crowd/srgan.py:149-191 (the float64 reductions behind ME / MAE / MSE, kNN MAE / MSE)
+  image_label_item         age/data.py:52-60, driving/data.py:44-51 (+ utility.to_normalized_range, utility.py:129-132)
 
 Parity pinned: oracle/make_golden_data.py runs the unmodified reference classes (crowd/data.py, crowd/shanghai_tech_data.py,
 crowd/srgan.py) on seeded synthetic examples and commits inputs + outputs as tests/golden/crowd_data.npz;
@@ -160,3 +161,11 @@ def evaluation_sums(predicted_counts, densities, predicted_maps, maps):
             'kNN MAE': np.abs(predicted_maps - maps).mean(),
             'MSE': (np.abs(predicted_counts - true_counts) ** 2).mean(),
             'kNN MSE': (np.abs(predicted_maps - maps) ** 2).mean()}
+
+
+def image_label_item(image, label, hwc=True):
+    """AgeDataset.__getitem__ (age/data.py:52-60: imageio HWC uint8 -> transpose((2, 0, 1)) -> float32 -> to_normalized_range,
+    utility.py:129-132) / SteeringAngleDataset.__getitem__ (driving/data.py:44-51: the stored array is already CHW)."""
+    if hwc:
+        image = image.transpose((2, 0, 1))
+    return (image.astype(np.float32) / np.float32(127.5)) - np.float32(1), np.float32(label)

@@ -148,6 +148,32 @@ def main():
         out['f2b_' + tag.replace(' ', '_')] = np.float64(writer.scalars[f'Validation/{tag}'][-1][1])
     assert abs(mae - out['f2b_MAE']) < 1e-12
 
+    # ---- f1c: age / driving samples.  SteeringAngleDataset.__getitem__ (driving/data.py:44-51) runs as is over CHW .npy files;
+    # AgeDataset.__getitem__ (age/data.py:52-60) needs imageio to decode a JPEG, so its remaining lines are run here on the
+    # decoded array with the reference's own utility.to_normalized_range
+    from driving.data import SteeringAngleDataset
+    from utility import to_normalized_range
+    rng = np.random.RandomState(31)
+    hwc = rng.randint(0, 256, size=(5, 16, 16, 3)).astype(np.uint8)
+    hwc[0] = np.arange(256, dtype=np.uint8).repeat(3).reshape(16, 16, 3)        # every byte value
+    values = (rng.rand(5) * 90 - 45).astype(np.float32)
+    out['f1c_hwc'], out['f1c_labels'] = hwc, values
+    age_items = []
+    for image in hwc:
+        t = torch.tensor(image.transpose((2, 0, 1)).astype(np.float32))
+        age_items.append(to_normalized_range(t).numpy())
+    out['f1c_age_images'] = np.stack(age_items)
+    with tempfile.TemporaryDirectory() as tmp:
+        names = []
+        for k, image in enumerate(hwc):
+            names.append(f'{k}.jpg')
+            np.save(os.path.join(tmp, f'{k}.npy'), np.ascontiguousarray(image.transpose((2, 0, 1))))
+        ds = object.__new__(SteeringAngleDataset)
+        ds.dataset_path, ds.image_names, ds.angles, ds.length = tmp, np.array(names), values, len(names)
+        items = [ds[k] for k in range(len(names))]
+        out['f1c_driving_images'] = np.stack([t[0].numpy() for t in items])
+        out['f1c_driving_angles'] = np.stack([t[1].numpy() for t in items])
+
     path = os.path.join(os.path.dirname(HERE), 'tests', 'golden', 'crowd_data.npz')
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), 'bytes;', len(pos), 'patches,', len(examples), 'full examples')

@@ -274,3 +274,53 @@ def evaluation_epoch(network, batches, batch_size, summary_writer=None, summary_
         for tag, v in scalars.items():
             summary_writer.add_scalar(f'{summary_name}/{tag}', v)
     return scalars
+
+
+class ImageLabelStore:
+    """Age / driving datasets resident on the device (age/data.py:21-60 AgeDataset, driving/data.py:22-51
+    SteeringAngleDataset): `images` [N,H,W,3] (imageio order, age) or [N,3,H,W] (the driving .npy files) uint8, `labels` [N]
+    fp32.  `batch(index)` is one launch of srgan_image_batch: the reference's __getitem__ + default collate + `.to(gpu)` for the
+    samples `index`; `loader(batch_size, shuffle)` walks the dataset with torch's own RandomSampler / BatchSampler, i.e. the
+    index stream of `DataLoader(dataset, batch_size, shuffle=True)` (age/srgan.py:27-35) under the same torch seed."""
+
+    def __init__(self, images, labels, hwc=True, device='cuda:0'):
+        if not torch.cuda.is_available():
+            raise RuntimeError('ImageLabelStore needs a CUDA device; the input pipeline has no CPU path')
+        self.lib, self.device, self.hwc = load_library(), torch.device(device), bool(hwc)
+        images = np.ascontiguousarray(images)
+        if images.dtype != np.uint8 or images.ndim != 4 or images.shape[3 if hwc else 1] != 3:
+            raise TypeError('images must be uint8 [N,H,W,3] (hwc=True) or [N,3,H,W] (hwc=False)')
+        self.n = images.shape[0]
+        self.chw = (3,) + (tuple(images.shape[1:3]) if hwc else tuple(images.shape[2:4]))
+        labels = np.ascontiguousarray(labels, dtype=np.float32)
+        if labels.shape != (self.n,):
+            raise ValueError('one label per image')
+        self.images = torch.from_numpy(images).pin_memory().to(self.device, non_blocking=True)
+        self.labels = torch.from_numpy(labels).to(self.device)
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def __len__(self):
+        return self.n
+
+    def batch(self, index):
+        index = torch.as_tensor(index, dtype=torch.int64)
+        if not index.is_cuda:
+            if index.numel() and (int(index.min()) < 0 or int(index.max()) >= self.n):
+                raise IndexError(f'sample index out of range for {self.n} images')
+            index = index.to(self.device)
+        B, (C, H, W) = index.numel(), self.chw
+        out = torch.empty(B, C, H, W, device=self.device, dtype=torch.float32)
+        labels = torch.empty(B, device=self.device, dtype=torch.float32)
+        _ck(self.lib, self.lib.srgan_image_batch(self.images.data_ptr(), int(self.hwc), index.data_ptr(), B, C, H, W,
+                                                 out.data_ptr(), self.labels.data_ptr(), labels.data_ptr(),
+                                                 _stream(self.device)), 'srgan_image_batch')
+        return out, labels
+
+    def loader(self, batch_size, shuffle=True, drop_last=False):
+        from torch.utils.data import BatchSampler, RandomSampler, SequentialSampler
+        # a DataLoader iterator draws its base seed from the default generator before its sampler draws its own
+        # (torch/utils/data/dataloader.py, _BaseDataLoaderIter.__init__): consume that draw so the index stream is the same
+        torch.empty((), dtype=torch.int64).random_()
+        sampler = RandomSampler(range(self.n)) if shuffle else SequentialSampler(range(self.n))
+        for index in BatchSampler(sampler, batch_size, drop_last):
+            yield self.batch(index)

@@ -173,3 +173,43 @@ def test_predict_full_example_through_the_crowd_discriminator():
     assert m.shape == (2, 3, 64, 64)
     assert (m.cpu() - m_ref).abs().max().item() < 1e-4 * max(m_ref.abs().max().item(), 1.0)
     assert (c.cpu() - c_ref).abs().max().item() < 1e-4 * max(c_ref.abs().max().item(), 1.0)
+
+
+def test_age_and_driving_batches_bit_exact_with_reference_golden(g):
+    """srgan_image_batch: AgeDataset (HWC store) and SteeringAngleDataset (CHW store) samples gathered by index on the device."""
+    from srgan_b200 import crowd_data
+    hwc, labels = g['f1c_hwc'], g['f1c_labels']
+    index = [4, 0, 2, 2, 1, 3]
+    age = crowd_data.ImageLabelStore(hwc, labels, hwc=True)
+    images, y = age.batch(index)
+    assert torch.equal(images.cpu(), torch.tensor(g['f1c_age_images'][index])) and torch.equal(y.cpu(), torch.tensor(labels[index]))
+    driving = crowd_data.ImageLabelStore(np.ascontiguousarray(hwc.transpose(0, 3, 1, 2)), labels, hwc=False)
+    images, y = driving.batch(index)
+    assert torch.equal(images.cpu(), torch.tensor(g['f1c_driving_images'][index]))
+    assert torch.equal(y.cpu(), torch.tensor(g['f1c_driving_angles'][index]))
+    # the loader is DataLoader(dataset, batch_size, shuffle=True)'s index stream (torch's own samplers) under the same seed
+    from torch.utils.data import DataLoader, TensorDataset
+    torch.manual_seed(5)
+    want = [b[0] for b in DataLoader(TensorDataset(torch.arange(5)), batch_size=2, shuffle=True)]
+    torch.manual_seed(5)
+    got = list(age.loader(2, shuffle=True))
+    assert len(got) == len(want) == 3
+    for (im, yy), idx in zip(got, want):
+        assert torch.equal(im.cpu(), torch.tensor(g['f1c_age_images'][idx.numpy()])) and torch.equal(yy.cpu(), torch.tensor(labels[idx.numpy()]))
+    with pytest.raises(IndexError):
+        age.batch([5])
+
+
+def test_age_full_size_batch_vs_oracle():
+    """BASELINE's age shapes: 100 samples of 3 x 128 x 128 from a 512-image resident store."""
+    from srgan_b200 import crowd_data
+    rng = np.random.RandomState(3)
+    images = rng.randint(0, 256, size=(512, 128, 128, 3)).astype(np.uint8)
+    labels = (rng.rand(512) * 85 + 10).astype(np.float32)
+    store = crowd_data.ImageLabelStore(images, labels, hwc=True)
+    index = rng.randint(0, 512, size=100)
+    out, y = store.batch(index)
+    for b in (0, 17, 99):
+        want, lab = C.image_label_item(images[index[b]], labels[index[b]])
+        assert np.array_equal(out[b].cpu().numpy(), want) and float(y[b]) == float(lab)
+    assert torch.equal(y.cpu(), torch.tensor(labels[index]))

@@ -63,3 +63,12 @@ def test_evaluation_sums(g):
     out = C.evaluation_sums(counts, g['f1_labels'][:15], maps[:5], g['f1_maps'][:5])      # maps: first batch only (:170-175)
     for tag, v in out.items():
         assert v == pytest.approx(float(g['f2b_' + tag.replace(' ', '_')]), rel=1e-12), tag
+
+
+def test_age_and_driving_items_bit_exact(g):
+    """image_label_item vs the reference's AgeDataset / SteeringAngleDataset sample path (incl. every byte value)."""
+    for k, image in enumerate(g['f1c_hwc']):
+        a, _ = C.image_label_item(image, g['f1c_labels'][k], hwc=True)
+        assert np.array_equal(a, g['f1c_age_images'][k]), k
+        d, v = C.image_label_item(np.ascontiguousarray(image.transpose((2, 0, 1))), g['f1c_labels'][k], hwc=False)
+        assert np.array_equal(d, g['f1c_driving_images'][k]) and v == g['f1c_driving_angles'][k], k
