@@ -359,6 +359,16 @@ int srgan_crowd_eval_sums(const float* densities, const float* pred_maps, int nm
  * 1 / (knn + epsilon) (:92-99; epsilon = 1). */
 int srgan_knn_maps(const double* head_yx, int n_heads, int H, int W, int kmax, double upper_bound, double epsilon, double* knn,
                    void* iknn_f16, void* stream);
+/* generate_density_label (crowd/database_preprocessor.py:113-225) as generate_labels_for_example calls it (:81-89: perspective
+ * None, perspective_resizing, yx_order, no body, count-normalised; run.py:67 trains crowd on the beta = 0.3 maps): every head adds
+ * a unit-sum square Gaussian with sigma = beta x mean distance to its min(11, n) nearest heads (itself included), half-width
+ * int(2 sigma), clipped at the borders; label [H][W] fp32 = n_heads x label / sum(label); label_f16 (may be NULL) = the float16
+ * copy the preprocessor saves.  Per pixel the heads are accumulated in annotation order in fp32 like the reference's
+ * `label += person_label`; device exp() and the float64 sums differ from numpy's in the last bits, so the result matches the
+ * reference to ~1e-6 relative, not bit for bit.  workspace: srgan_density_label_workspace_bytes(n_heads, H, W). */
+size_t srgan_density_label_workspace_bytes(int n_heads, int H, int W);
+int srgan_density_label(const double* head_yx, int n_heads, int H, int W, double beta, float* label, void* label_f16,
+                        void* workspace, size_t workspace_bytes, void* stream);
 /* generate_point_density_map (crowd/database_preprocessor.py:246-256): density[round(y)][round(x)] += 1 per head (round half to
  * even, negative indexes wrap once like Python's); *out_of_bounds = heads that fall outside.  density [H][W] fp32 and the
  * counter are cleared by the call. */

@@ -41,3 +41,47 @@ def generate_point_density_map(head_positions, label_size):
         else:
             out_of_bounds_count += 1
     return density_map, out_of_bounds_count
+
+
+def head_spreads(head_positions, number_of_neighbors=11):
+    """crowd/database_preprocessor.py:146-149: mean distance of every head to its min(11, n) nearest heads, ITSELF included
+    (distance 0), the MCNN-style geometry-adaptive kernel width."""
+    heads = np.asarray(head_positions, dtype=np.float64)
+    d = heads[:, None, :] - heads[None, :, :]
+    distances = np.sqrt(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1])
+    k = min(number_of_neighbors, len(heads))
+    return np.ascontiguousarray(np.sort(distances, axis=1)[:, :k]).mean(axis=1)
+
+
+def make_gaussian(standard_deviation):
+    """crowd/database_preprocessor.py:228-243 for a scalar standard deviation."""
+    off = int(standard_deviation * 2)
+    line = np.linspace(-off, off, off * 2 + 1)
+    x, y = np.meshgrid(line, line)
+    return np.exp(-((x ** 2) / (2.0 * standard_deviation ** 2) + (y ** 2) / (2.0 * standard_deviation ** 2)))
+
+
+def generate_density_label(head_positions, label_size, neighbor_deviation_beta=0.15):
+    """crowd/database_preprocessor.py:113-225 as generate_labels_for_example calls it (:87-88): perspective=None,
+    perspective_resizing=True, yx_order=True, no body, force_full_image_count_normalize=True.  Positions are rounded to
+    uint32 like the reference (np.rint(..).astype(np.uint32)); the window arithmetic is in Python ints, which is what the
+    reference's expressions evaluate to under the NumPy 1.x promotion rules it was written for (under NumPy >= 2 `y - off` stays
+    uint32, wraps for heads within `off` pixels of the top / left border, and the reference raises a broadcasting error)."""
+    spreads = head_spreads(head_positions)
+    label = np.zeros(shape=label_size, dtype=np.float32)
+    head_count = 0
+    for head_index, head_position in enumerate(head_positions):
+        y, x = (int(v) for v in np.rint(head_position).astype(np.uint32))
+        gaussian = make_gaussian(spreads[head_index] * neighbor_deviation_beta)
+        gaussian = gaussian / gaussian.sum()
+        head_count += 1
+        off = int((gaussian.shape[0] - 1) / 2)
+        y0, y1 = max(off - y, 0), max(y + off + 1 - label_size[0], 0)
+        x0, x1 = max(off - x, 0), max(x + off + 1 - label_size[1], 0)
+        if gaussian.shape[0] <= max(y0, y1) or gaussian.shape[1] <= max(x0, x1):
+            continue                                         # 'Offset out of head gaussian bounds. Skipping person.' (:189-191)
+        person = np.zeros_like(label)
+        person[y - off + y0:y + off + 1 - y1, x - off + x0:x + off + 1 - x1] += gaussian[y0:gaussian.shape[0] - y1,
+                                                                                         x0:gaussian.shape[1] - x1]
+        label += person
+    return head_count * (label / label.sum())

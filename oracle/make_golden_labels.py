@@ -44,6 +44,19 @@ def main():
             out[f'{name}/knn{k}'] = generate_knn_map(heads, list(size), number_of_neighbors=k, upper_bound=ub)
         density, oob = generate_point_density_map(heads, size)
         out[f'{name}/density'], out[f'{name}/oob'] = density, np.int64(oob)
+    # ---- Gaussian density labels (generate_density_label as generate_labels_for_example calls it, :81-89).  Under NumPy >= 2 the
+    # reference's `y - off_center_size` stays uint32 and the function raises for heads within `off` pixels of the top / left
+    # border (it was written for the NumPy 1.x promotion rules), so these cases keep every head at least its own kernel
+    # half-width away from those two borders; clipping at the bottom / right border and heads beyond them ARE exercised.
+    from crowd.database_preprocessor import generate_density_label
+    rng = np.random.RandomState(7)
+    size = (72, 96)
+    heads = np.concatenate([rng.rand(40, 2) * np.array([40.0, 60.0]) + np.array([30.0, 34.0]),       # interior + bottom / right
+                            np.array([[71.4, 95.2], [70.0, 50.5], [45.5, 95.0], [73.6, 60.0]])])   # on / just past the far borders
+    out['density/heads'], out['density/size'] = heads, np.array(size)
+    for beta in (0.05, 0.1, 0.3, 0.5):
+        out[f'density/beta{beta}'] = generate_density_label(heads, size, perspective_resizing=True, yx_order=True,
+                                                            neighbor_deviation_beta=beta)
     path = os.path.join(os.path.dirname(HERE), 'tests', 'golden', 'crowd_labels.npz')
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), 'bytes')

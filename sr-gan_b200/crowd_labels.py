@@ -60,3 +60,24 @@ def generate_point_density_map(head_positions, label_size, device='cuda:0'):
                                          density.data_ptr(), oob.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
         'srgan_point_density_map')
     return density, int(oob.item())
+
+
+def generate_density_label(head_positions, label_size, neighbor_deviation_beta=0.15, device='cuda:0', half=False):
+    """crowd/database_preprocessor.py:113-225 in the form generate_labels_for_example uses (:87-88: no perspective map, yx order,
+    count-normalised): the geometry-adaptive Gaussian density label, [H, W] fp32 on the device (half=True: also the float16
+    copy the `density{beta}` directories hold -- the maps run.py:67 trains the crowd application on)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError('crowd_labels needs a CUDA device (no CPU path)')
+    lib, dev = load_library(), torch.device(device)
+    heads = _heads(head_positions, dev)
+    if heads.shape[0] == 0:
+        raise ValueError('no head positions (sklearn NearestNeighbors.fit raises on an empty array in the reference)')
+    H, W = int(label_size[0]), int(label_size[1])
+    label = torch.empty(H, W, device=dev, dtype=torch.float32)
+    f16 = torch.empty(H, W, device=dev, dtype=torch.float16) if half else None
+    ws_bytes = lib.srgan_density_label_workspace_bytes(heads.shape[0], H, W)
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    _ck(lib, lib.srgan_density_label(heads.data_ptr(), heads.shape[0], H, W, float(neighbor_deviation_beta), label.data_ptr(),
+                                     None if f16 is None else f16.data_ptr(), ws.data_ptr(), ws_bytes,
+                                     torch.cuda.current_stream(dev).cuda_stream), 'srgan_density_label')
+    return (label, f16) if half else label

@@ -83,9 +83,183 @@ __global__ void point_density_kernel(const double* __restrict__ head_yx, int n_h
     atomicAdd(density + y * W + x, 1.0f);           // whole numbers: exact in any order
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// generate_density_label (crowd/database_preprocessor.py:113-225) as generate_labels_for_example calls it (:81-89; run.py:67
+// trains the crowd application on the beta = 0.3 maps): every head adds a normalised square Gaussian whose standard deviation
+// is beta x the mean distance to its min(11, n) nearest heads (itself included), clipped at the label's borders; the sum is
+// rescaled to the head count.  Three launches: per-head geometry (thread per head, brute-force neighbours), per-head kernel
+// sum (block per head), then a GATHER per pixel over the heads in annotation order -- the order the reference's
+// `label += person_label` runs in, so the fp32 accumulation is the same sequence of additions.
+struct head_geom {
+    long long y, x;       // np.rint(position).astype(np.uint32)
+    int off, skip;        // kernel half-width int(2 sigma); 'Offset out of head gaussian bounds' (:189-191)
+    double two_s2, sum;   // 2 sigma^2; sum of the full (unclipped) kernel
+};
+
+constexpr int kSpreadK = 11;
+
+__global__ void __launch_bounds__(128)
+head_geometry_kernel(const double* __restrict__ head_yx, int n, int H, int W, double beta, head_geom* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double py = head_yx[2 * i], px = head_yx[2 * i + 1];
+    double best[kSpreadK];
+#pragma unroll
+    for (int k = 0; k < kSpreadK; ++k) best[k] = __longlong_as_double(0x7ff0000000000000LL);
+    for (int j = 0; j < n; ++j) {
+        const double dy = __dsub_rn(py, head_yx[2 * j]), dx = __dsub_rn(px, head_yx[2 * j + 1]);
+        double d = __dadd_rn(__dmul_rn(dy, dy), __dmul_rn(dx, dx));
+        if (d < best[kSpreadK - 1]) {
+#pragma unroll
+            for (int k = 0; k < kSpreadK; ++k) {
+                const double lo = fmin(best[k], d);
+                d = fmax(best[k], d);
+                best[k] = lo;
+            }
+        }
+    }
+    const int k = n < kSpreadK ? n : kSpreadK;
+    double a[kSpreadK];
+#pragma unroll
+    for (int j = 0; j < kSpreadK; ++j) a[j] = j < k ? sqrt(best[j]) : 0.0;
+    // numpy's mean over the k contiguous columns: a plain loop below 8 elements, else 8 running sums combined pairwise and
+    // the remainder added in order (numpy/core/src/umath/loops_utils.h pairwise sum)
+    double sum;
+    if (k < 8) {
+        sum = 0.0;
+        for (int j = 0; j < k; ++j) sum = __dadd_rn(sum, a[j]);
+    } else {
+        sum = __dadd_rn(__dadd_rn(__dadd_rn(a[0], a[1]), __dadd_rn(a[2], a[3])), __dadd_rn(__dadd_rn(a[4], a[5]), __dadd_rn(a[6], a[7])));
+        for (int j = 8; j < k; ++j) sum = __dadd_rn(sum, a[j]);
+    }
+    const double sigma = __dmul_rn(__ddiv_rn(sum, (double)k), beta);
+    head_geom g;
+    g.y = (long long)(unsigned int)(long long)rint(py);
+    g.x = (long long)(unsigned int)(long long)rint(px);
+    g.off = (int)__dmul_rn(sigma, 2.0);
+    g.two_s2 = __dmul_rn(2.0, __dmul_rn(sigma, sigma));
+    const long long size = 2LL * g.off + 1;
+    const long long y0 = g.off - g.y > 0 ? g.off - g.y : 0, y1 = g.y + g.off + 1 - H > 0 ? g.y + g.off + 1 - H : 0;
+    const long long x0 = g.off - g.x > 0 ? g.off - g.x : 0, x1 = g.x + g.off + 1 - W > 0 ? g.x + g.off + 1 - W : 0;
+    g.skip = (size <= (y0 > y1 ? y0 : y1)) || (size <= (x0 > x1 ? x0 : x1));
+    g.sum = 0.0;
+    out[i] = g;
+}
+
+__device__ __forceinline__ double gaussian_value(long long dy, long long dx, double two_s2) {
+    const double fy = (double)dy, fx = (double)dx;       // exp(-(x^2 / (2 s^2) + y^2 / (2 s^2))), :238-241
+    return exp(-__dadd_rn(__ddiv_rn(__dmul_rn(fx, fx), two_s2), __ddiv_rn(__dmul_rn(fy, fy), two_s2)));
+}
+
+__global__ void __launch_bounds__(128) head_kernel_sum_kernel(head_geom* __restrict__ geoms) {
+    __shared__ double red[4];
+    head_geom& g = geoms[blockIdx.x];
+    const int size = 2 * g.off + 1;
+    double local = 0.0;
+    for (int e = threadIdx.x; e < size * size; e += blockDim.x)
+        local += gaussian_value(e / size - g.off, e % size - g.off, g.two_s2);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) g.sum = (red[0] + red[1]) + (red[2] + red[3]);
+}
+
+constexpr int kDensityThreads = 256;
+constexpr int kGeomTile = 256;
+
+__global__ void __launch_bounds__(kDensityThreads)
+density_label_kernel(const head_geom* __restrict__ geoms, int n, int H, int W, float* __restrict__ label,
+                     double* __restrict__ partials) {
+    __shared__ head_geom tile[kGeomTile];
+    __shared__ double red[kDensityThreads / 32];
+    const long long total = (long long)H * W;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < total;
+    const long long Y = live ? i / W : 0, X = live ? i % W : 0;
+    float acc = 0.f;
+    for (int base = 0; base < n; base += kGeomTile) {
+        const int m = min(kGeomTile, n - base);
+        __syncthreads();
+        for (int j = threadIdx.x; j < m; j += blockDim.x) tile[j] = geoms[base + j];
+        __syncthreads();
+        for (int j = 0; j < m; ++j) {
+            const head_geom& g = tile[j];
+            if (g.skip) continue;
+            const long long dy = Y - g.y, dx = X - g.x;
+            if (dy < -g.off || dy > g.off || dx < -g.off || dx > g.off) continue;
+            // person_label (float32 zeros) += gaussian / gaussian.sum()  ->  label += person_label
+            acc = __fadd_rn(acc, (float)__ddiv_rn(gaussian_value(dy, dx, g.two_s2), g.sum));
+        }
+    }
+    if (live) label[i] = acc;
+    double local = live ? (double)acc : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < kDensityThreads / 32; ++w) s += red[w];
+        partials[blockIdx.x] = s;
+    }
+}
+
+// label = head_count * (label / label.sum())  in float32 (:223-224); one block first folds the per-block partial sums
+__global__ void __launch_bounds__(256)
+density_normalise_kernel(float* __restrict__ label, long long total, const double* __restrict__ partials, int n_partials,
+                         float head_count, __half* __restrict__ label_f16) {
+    __shared__ double red[8];
+    __shared__ float s_sum;
+    double local = 0.0;
+    for (int j = threadIdx.x; j < n_partials; j += blockDim.x) local += partials[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        s_sum = (float)s;
+    }
+    __syncthreads();
+    const float sum = s_sum;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const float v = __fmul_rn(head_count, __fdiv_rn(label[i], sum));
+        label[i] = v;
+        if (label_f16) label_f16[i] = __float2half_rn(v);
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+size_t srgan_density_label_workspace_bytes(int n_heads, int H, int W) {
+    const long long blocks = ((long long)H * W + kDensityThreads - 1) / kDensityThreads;
+    return sizeof(head_geom) * (size_t)(n_heads > 0 ? n_heads : 0) + sizeof(double) * (size_t)blocks;
+}
+
+int srgan_density_label(const double* head_yx, int n_heads, int H, int W, double beta, float* label, void* label_f16,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    SRGAN_REQUIRE(head_yx && label && workspace, "srgan_density_label: null pointer");
+    SRGAN_REQUIRE(n_heads > 0 && H > 0 && W > 0, "srgan_density_label: empty problem");
+    SRGAN_REQUIRE(workspace_bytes >= srgan_density_label_workspace_bytes(n_heads, H, W), "srgan_density_label: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)H * W;
+    const int blocks = (int)((total + kDensityThreads - 1) / kDensityThreads);
+    double* partials = (double*)workspace;                                  // 8-byte aligned first, the head table behind it
+    head_geom* geoms = (head_geom*)(partials + blocks);
+    head_geometry_kernel<<<(n_heads + 127) / 128, 128, 0, st>>>(head_yx, n_heads, H, W, beta, geoms);
+    SRGAN_CHECK_LAUNCH("srgan_density_label(geometry)");
+    head_kernel_sum_kernel<<<n_heads, 128, 0, st>>>(geoms);
+    SRGAN_CHECK_LAUNCH("srgan_density_label(kernel sums)");
+    density_label_kernel<<<blocks, kDensityThreads, 0, st>>>(geoms, n_heads, H, W, label, partials);
+    SRGAN_CHECK_LAUNCH("srgan_density_label(gather)");
+    density_normalise_kernel<<<2 * kNumSMs, 256, 0, st>>>(label, total, partials, blocks, (float)n_heads, (__half*)label_f16);
+    SRGAN_CHECK_LAUNCH("srgan_density_label(normalise)");
+    return 0;
+}
 
 int srgan_knn_maps(const double* head_yx, int n_heads, int H, int W, int kmax, double upper_bound, double epsilon, double* knn,
                    void* iknn_f16, void* stream) {

@@ -37,7 +37,7 @@ _EXPORTS = (
     'srgan_maxpool', 'srgan_maxpool_bwd', 'srgan_avgpool', 'srgan_avgpool_bwd', 'srgan_crowd_loss', 'srgan_crowd_map_grad', 'srgan_depth_to_space', 'srgan_adam_multi', 'srgan_affine_bwd_grad',
     'srgan_adam_layout_multi', 'srgan_bn_dgrad', 'srgan_bn_conv_down', 'srgan_bn_conv_wgrad', 'srgan_bn_conv_dgrad',
     'srgan_crowd_extract_patches', 'srgan_sliding_window_merge', 'srgan_crowd_eval_sums', 'srgan_image_batch',
-    'srgan_knn_maps', 'srgan_point_density_map',
+    'srgan_knn_maps', 'srgan_point_density_map', 'srgan_density_label', 'srgan_density_label_workspace_bytes',
     'srgan_head_logits', 'srgan_sgan_loss', 'srgan_sgan_gp_second', 'srgan_seed_rows_multi',
     'srgan_sliding_window_workspace_bytes', 'srgan_crowd_eval_workspace_bytes',
 )
@@ -119,6 +119,8 @@ def load_library(path: str = LIB_PATH):
     c_d = ctypes.c_double
     lib.srgan_knn_maps.argtypes = [vp, c_int, c_int, c_int, c_int, c_d, c_d, vp, vp, vp]
     lib.srgan_point_density_map.argtypes = [vp, c_int, c_int, c_int, vp, vp, vp]
+    lib.srgan_density_label.argtypes = [vp, c_int, c_int, c_int, c_d, vp, vp, vp, ctypes.c_size_t, vp]
+    lib.srgan_density_label_workspace_bytes.argtypes = [c_int, c_int, c_int]
     lib.srgan_head_logits.argtypes = [vp, c_int, c_int, vp, vp, c_int, vp, c_int, vp]
     lib.srgan_sgan_loss.argtypes = [vp, c_int, c_int, c_int, vp, vp, c_f, c_f, vp, vp, vp]
     lib.srgan_sgan_gp_second.argtypes = [vp, vp, c_int, c_int, c_f, vp, vp]
@@ -130,6 +132,7 @@ def load_library(path: str = LIB_PATH):
     lib.srgan_coefficient_step_workspace_bytes.restype = ctypes.c_size_t
     lib.srgan_sliding_window_workspace_bytes.restype = ctypes.c_size_t
     lib.srgan_crowd_eval_workspace_bytes.restype = ctypes.c_size_t
+    lib.srgan_density_label_workspace_bytes.restype = ctypes.c_size_t
     _lib = lib
     return lib
 

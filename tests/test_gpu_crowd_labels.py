@@ -60,3 +60,38 @@ def test_label_generation_argument_errors():
         crowd_labels.generate_knn_maps(np.zeros((3, 2)), (8, 8), k_max=9)
     density, oob = crowd_labels.generate_point_density_map(np.zeros((0, 2)), (8, 8))
     assert float(density.abs().sum()) == 0.0 and oob == 0
+
+
+def test_density_label_matches_reference_golden():
+    """srgan_density_label vs the reference's generate_density_label for the four betas the preprocessor writes: fp32 within
+    2e-6 of the label's peak (device exp / sums differ from numpy's in the last bits), the saved float16 copy equal except for
+    rare one-ulp roundings, and the label sums to the head count."""
+    from srgan_b200 import crowd_labels
+    g = np.load(GOLDEN)
+    heads, size = g['density/heads'], tuple(int(v) for v in g['density/size'])
+    for beta in (0.05, 0.1, 0.3, 0.5):
+        ref = g[f'density/beta{beta}']
+        label, f16 = crowd_labels.generate_density_label(heads, size, beta, half=True)
+        got = label.cpu().numpy()
+        assert np.abs(got - ref).max() <= 2e-6 * ref.max(), (beta, np.abs(got - ref).max(), ref.max())
+        assert (got == 0).sum() == (ref == 0).sum()                       # the same support: clipping and skipped heads
+        ref16, got16 = ref.astype(np.float16), f16.cpu().numpy()
+        differ = got16 != ref16
+        assert differ.mean() < 2e-3, (beta, differ.mean())
+        assert np.abs(got16[differ].astype(np.float32) - ref16[differ].astype(np.float32)).max(initial=0) <= 2e-3 * ref.max()
+        assert float(label.sum()) == pytest.approx(len(heads), rel=1e-5)
+
+
+def test_density_label_full_size_vs_oracle_strip():
+    """768 x 1024 label, 600 heads incl. some next to every border (the oracle uses the NumPy-1.x integer semantics the
+    reference was written for): the whole map against the oracle, and mass conservation."""
+    from srgan_b200 import crowd_labels
+    rng = np.random.RandomState(9)
+    H, W = 768, 1024
+    heads = rng.rand(600, 2) * np.array([H, W], dtype=np.float64)
+    heads[:8] = [[0.2, 0.3], [1.0, 500.0], [400.0, 0.6], [767.4, 1023.2], [766.0, 3.0], [2.5, 1022.5], [383.5, 511.5], [0.0, 0.0]]
+    ref = L.generate_density_label(heads, (H, W), 0.3)
+    got = crowd_labels.generate_density_label(heads, (H, W), 0.3).cpu().numpy()
+    assert np.abs(got - ref).max() <= 2e-6 * ref.max()
+    assert (got == 0).sum() == (ref == 0).sum()
+    assert float(got.astype(np.float64).sum()) == pytest.approx(600.0, rel=1e-5)

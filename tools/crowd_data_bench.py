@@ -111,6 +111,21 @@ def main():
               f'5 queries) -> >= {cpu_s * 1e3 / gpu_ms:.0f}x')
     except ImportError:
         print('scikit-learn not importable here: no host timing')
+    # the Gaussian density label (run.py:67 trains on the beta = 0.3 maps), same label and heads
+    crowd_labels.generate_density_label(heads, (H, W), 0.3)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        crowd_labels.generate_density_label(heads, (H, W), 0.3)
+    e1.record()
+    e1.synchronize()
+    gpu_ms = e0.elapsed_time(e1) / 5
+    from oracle import crowd_labels_oracle as LO                       # the reference's per-head numpy loop, restated
+    t0 = time.perf_counter()
+    LO.generate_density_label(heads, (H, W), 0.3)
+    cpu_s = time.perf_counter() - t0
+    print(f'generate_density_label beta=0.3, {H}x{W}, 1500 heads: {gpu_ms:.3f} ms on the device; the per-head numpy loop on the host '
+          f'{cpu_s:.2f} s -> {cpu_s * 1e3 / gpu_ms:.0f}x')
 
 
 if __name__ == '__main__':
