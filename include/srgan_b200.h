@@ -389,6 +389,9 @@ int srgan_sgan_loss(const float* logitsT, int K, int n, int mode, const float* y
 /* Double backward of the SGAN gradient penalty (srgan.py:360-375 over sgan.py:51-58): qT = H tangentT per sample, H the Hessian
  * of c * softplus(logsumexp(l)) w.r.t. the K logits -- the ordinary-backward seed the penalty leaves on the x_hat rows. */
 int srgan_sgan_gp_second(const float* logitsT, const float* tangentT, int K, int n, float c, float* qT, void* stream);
+/* dW[k][c] += sum_r dT[k][r] * X[r,c], db[k] += sum_r dT[k][r] (db may be NULL): the head's weight / bias gradients for all K
+ * outputs in one pass over the feature rows (autograd of the K-output layer5 / linear4); cols must be a multiple of 4. */
+int srgan_head_wgrad(const void* X, int rows, int cols, const float* dT, int K, float* dW, float* db, int dtype, void* stream);
 /* out[r,c] = (sum_k dT[k][r] * W[k][c]) * act'(href[r,c]): srgan_seed_rows for a K-output head */
 int srgan_seed_rows_multi(void* out, int rows, int cols, const float* dT, const float* W, int K, const void* href, int act,
                           float slope, int dtype, void* stream);

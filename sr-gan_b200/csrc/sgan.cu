@@ -130,9 +130,79 @@ __global__ void __launch_bounds__(256) seed_rows_multi_kernel(T* __restrict__ ou
     }
 }
 
+// dW[k][c] += sum_r dT[k][r] * X[r,c]  and  db[k] += sum_r dT[k][r]  for all K outputs in ONE pass over the feature block (as K
+// row-scaled column sums the block was read K times).  A thread owns 4 columns x K accumulators; the 8 warps of a block take
+// interleaved rows of the block's row range; partial sums meet in shared memory and leave with one atomicAdd per (k, column).
+template <typename T>
+__global__ void __launch_bounds__(256) head_wgrad_kernel(const T* __restrict__ X, int rows, int cols, const float* __restrict__ dT, int K,
+                                                         float* __restrict__ dW, float* __restrict__ db) {
+    __shared__ float red[8][32][4];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + lane) * 4;
+    const int r0 = (int)(((long long)rows * blockIdx.y) / gridDim.y), r1 = (int)(((long long)rows * (blockIdx.y + 1)) / gridDim.y);
+    float4 acc[kMaxK];
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < cols) {
+        for (int r = r0 + w; r < r1; r += 8) {
+            const float4 v = ld4(X + (long long)r * cols + c);
+#pragma unroll
+            for (int k = 0; k < kMaxK; ++k) {
+                if (k < K) {
+                    const float sc = dT[(long long)k * rows + r];
+                    acc[k].x = fmaf(sc, v.x, acc[k].x); acc[k].y = fmaf(sc, v.y, acc[k].y);
+                    acc[k].z = fmaf(sc, v.z, acc[k].z); acc[k].w = fmaf(sc, v.w, acc[k].w);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k) {
+        if (k < K) {                                          // K is uniform over the block
+            __syncthreads();
+            red[w][lane][0] = acc[k].x; red[w][lane][1] = acc[k].y; red[w][lane][2] = acc[k].z; red[w][lane][3] = acc[k].w;
+            __syncthreads();
+            if (threadIdx.x < 128) {
+                const int g = threadIdx.x >> 2, j = threadIdx.x & 3;
+                const int cc = (blockIdx.x * 32 + g) * 4 + j;
+                if (cc < cols) {
+                    float sum = 0.f;
+#pragma unroll
+                    for (int y = 0; y < 8; ++y) sum += red[y][g][j];
+                    atomicAdd(dW + (long long)k * cols + cc, sum);
+                }
+            }
+        }
+    }
+    if (db && blockIdx.x == 0 && blockIdx.y == 0 && w < K && w < 8) {        // bias sums: warp k (and k + 8) over the rows
+        for (int k = w; k < K; k += 8) {
+            float s = 0.f;
+            for (int r = lane; r < rows; r += 32) s += dT[(long long)k * rows + r];
+            s = warp_sum(s);
+            if (lane == 0) atomicAdd(db + k, s);
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int srgan_head_wgrad(const void* X, int rows, int cols, const float* dT, int K, float* dW, float* db, int dtype, void* stream) {
+    SRGAN_REQUIRE(X && dT && dW && rows >= 0 && cols > 0, "srgan_head_wgrad: bad arguments");
+    SRGAN_REQUIRE(K >= 1 && K <= kMaxK, "srgan_head_wgrad: K = %d outside 1..%d", K, kMaxK);
+    SRGAN_REQUIRE(cols % 4 == 0, "srgan_head_wgrad: cols = %d is not a multiple of 4", cols);
+    if (rows == 0) return SRGAN_OK;
+    const int gx = cdiv(cols, 128);
+    long long gy = (2LL * kNumSMs + gx - 1) / gx;
+    if (gy > (rows + 15) / 16) gy = (rows + 15) / 16;          // at least ~2 rows per warp
+    if (gy < 1) gy = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == SRGAN_F32) head_wgrad_kernel<float><<<dim3(gx, (unsigned)gy), 256, 0, st>>>((const float*)X, rows, cols, dT, K, dW, db);
+    else head_wgrad_kernel<bf16><<<dim3(gx, (unsigned)gy), 256, 0, st>>>((const bf16*)X, rows, cols, dT, K, dW, db);
+    SRGAN_CHECK_LAUNCH("head_wgrad_kernel");
+    return SRGAN_OK;
+}
 
 int srgan_head_logits(const void* X, int rows, int cols, const float* W, const float* bias, int K, float* logitsT, int dtype,
                       void* stream) {

@@ -565,7 +565,14 @@ class StepRunner:
         wd = cfg.weight_decay if weight_decay is None else weight_decay
         self._wait_pending(('DNN',))
         if self.persistent:
-            self._coef_step(1, examples, labels, lr_dnn=lr, wd=wd)
+            if not self.use_cuda_graph or os.environ.get('SRGAN_NO_COEF_GRAPH', '0') == '1':
+                self._coef_step(1, examples, labels, lr_dnn=lr, wd=wd)
+                return
+            # the cooperative launch replayed from a CUDA graph (north_star: "one persistent CUDA-graph kernel")
+            xs, ys = self._static('cx', examples), self._static('cy', labels.reshape(-1))
+            key = ('coef_dnn', tuple(examples.shape), lr, wd, repr(sorted(vars(cfg).items())))
+            self._graphed(key, [(xs, examples), (ys, labels.reshape(-1))], lambda: self._coef_step(1, xs, ys, lr_dnn=lr, wd=wd))
+            self._layouts_stale = True              # (a replay does not pass through _coef_step)
             return
         mb = cfg.micro_batch if 0 < cfg.micro_batch < examples.shape[0] else 0
 
@@ -595,7 +602,18 @@ class StepRunner:
         train_g = (step % cfg.generator_training_step_period == 0)
         self._wait_pending(('G',))
         if self.persistent:
-            self._coef_step(2, labeled_examples, labels, unlabeled_examples, z, alpha.reshape(-1), z2, train_g=train_g)
+            if not self.use_cuda_graph or os.environ.get('SRGAN_NO_COEF_GRAPH', '0') == '1':
+                self._coef_step(2, labeled_examples, labels, unlabeled_examples, z, alpha.reshape(-1), z2, train_g=train_g)
+                return
+            al, yl = alpha.reshape(-1), labels.reshape(-1)
+            st = [(self._static('cx', labeled_examples), labeled_examples), (self._static('cy', yl), yl),
+                  (self._static('cu', unlabeled_examples), unlabeled_examples), (self._static('cz', z), z),
+                  (self._static('calpha', al), al), (self._static('cz2', z2), z2)]
+            xs, ys, us, zs, als, z2s = (d for d, _ in st)
+            key = ('coef_gan', tuple(labeled_examples.shape), train_g, bool(self.engine.publish_features),
+                   repr(sorted(vars(cfg).items())))
+            self._graphed(key, st, lambda: self._coef_step(2, xs, ys, us, zs, als, z2s, train_g=train_g))
+            self._layouts_stale = True
             return
         mb = cfg.micro_batch if 0 < cfg.micro_batch < B else 0
 

@@ -38,7 +38,7 @@ _EXPORTS = (
     'srgan_adam_layout_multi', 'srgan_bn_dgrad', 'srgan_bn_conv_down', 'srgan_bn_conv_wgrad', 'srgan_bn_conv_dgrad',
     'srgan_crowd_extract_patches', 'srgan_sliding_window_merge', 'srgan_crowd_eval_sums', 'srgan_image_batch',
     'srgan_knn_maps', 'srgan_point_density_map', 'srgan_density_label', 'srgan_density_label_workspace_bytes',
-    'srgan_head_logits', 'srgan_sgan_loss', 'srgan_sgan_gp_second', 'srgan_seed_rows_multi',
+    'srgan_head_logits', 'srgan_sgan_loss', 'srgan_sgan_gp_second', 'srgan_seed_rows_multi', 'srgan_head_wgrad',
     'srgan_sliding_window_workspace_bytes', 'srgan_crowd_eval_workspace_bytes',
 )
 
@@ -125,6 +125,7 @@ def load_library(path: str = LIB_PATH):
     lib.srgan_sgan_loss.argtypes = [vp, c_int, c_int, c_int, vp, vp, c_f, c_f, vp, vp, vp]
     lib.srgan_sgan_gp_second.argtypes = [vp, vp, c_int, c_int, c_f, vp, vp]
     lib.srgan_seed_rows_multi.argtypes = [vp, c_int, c_int, vp, vp, c_int, vp, c_int, c_f, c_int, vp]
+    lib.srgan_head_wgrad.argtypes = [vp, c_int, c_int, vp, c_int, vp, vp, c_int, vp]
     lib.srgan_tensor_launch_count.restype = c_ll
     lib.srgan_simt_fallback_count.restype = c_ll
     for name in _EXPORTS[7:]:
@@ -425,6 +426,11 @@ class CudaOps:
         f32 = torch.float32
         self._ck(self.lib.srgan_sgan_gp_second(self._p(logitsT, f32), self._p(tangentT, f32), K, n, c, self._p(qT, f32),
                                                self._stream()), 'srgan_sgan_gp_second')
+
+    def head_wgrad(self, X, rows, cols, dT, K, dW, db):
+        f32 = torch.float32
+        self._ck(self.lib.srgan_head_wgrad(self._p(X), rows, cols, self._p(dT, f32), K, self._p(dW, f32), self._p(db, f32),
+                                           _dt(X.dtype), self._stream()), 'srgan_head_wgrad')
 
     def seed_rows_multi(self, out, rows, cols, dT, W, K, href, act, slope):
         f32 = torch.float32

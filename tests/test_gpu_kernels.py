@@ -666,3 +666,50 @@ def test_depth_to_space_and_scalar_bias_gemm(ops, dt):
     ref.conv_wgrad(S, L, dW_ref, n, g)
     ops.conv_wgrad(S.cuda(), L.cuda(), dW, n, g)
     close(dW, dW_ref, tol(dt) * 2, 'skinny wgrad')
+
+
+# ------------------------------------------------------------------------------------------------ SGAN K-logit head (sgan.cu)
+@pytest.mark.parametrize('dt', DT)
+@pytest.mark.parametrize('rows,cols,K', [(100, 32768, 10), (64, 100, 10), (5, 36, 3), (257, 512, 16), (1, 8, 4)])
+def test_sgan_head_kernels(ops, dt, rows, cols, K):
+    """srgan_head_logits / srgan_sgan_loss (cross entropy, BCE of logsumexp) / srgan_sgan_gp_second / srgan_seed_rows_multi /
+    srgan_head_wgrad against the op-level torch semantics; shapes: the age head (F = 32 768, 10 bins), SganMLP (F = 100), ragged."""
+    gen = torch.Generator().manual_seed(rows + cols + K)
+    ref = TorchOps()
+    t = 1e-4 if dt == torch.float32 else 1e-2
+    X = rnd(gen, rows * cols, dt=dt)
+    W, bias = rnd(gen, K * cols) * (4.0 / cols ** 0.5), rnd(gen, K)
+    for b in (bias, None):
+        l_ref, l = torch.empty(K, rows), torch.empty(K, rows, device='cuda')
+        ref.head_logits(X, rows, cols, W, b, K, l_ref)
+        ops.head_logits(X.cuda(), rows, cols, W.cuda(), b.cuda() if b is not None else None, K, l)
+        close(l, l_ref, t, 'head_logits')
+    logits = rnd(gen, K, rows) * 3
+    y, bins = rnd(gen, rows) * 50 + 50, torch.linspace(10, 95, K)
+    for mode, target, scale in ((0, 0.0, 0.37), (1, 1.0, 1.0 / rows), (1, 0.0, -2.5)):
+        loss_ref, d_ref = torch.full((1,), 0.25), torch.empty(K, rows)
+        loss, d = loss_ref.clone().cuda(), torch.empty(K, rows, device='cuda')
+        ref.sgan_loss(logits, K, rows, mode, y, bins, target, scale, loss_ref, d_ref)
+        ops.sgan_loss(logits.cuda(), K, rows, mode, y.cuda(), bins.cuda(), target, scale, loss, d)
+        close(loss, loss_ref, 2e-5, f'sgan_loss mode {mode}')
+        close(d, d_ref, 2e-5, f'sgan_loss gradient mode {mode}')
+    ops.sgan_loss(logits.cuda(), K, rows, 1, None, None, 0.0, 1.0, None, d)          # gradient only (the penalty's seed)
+    tang = rnd(gen, K, rows)
+    q_ref, q = torch.empty(K, rows), torch.empty(K, rows, device='cuda')
+    ref.sgan_gp_second(logits, tang, K, rows, 0.7, q_ref)
+    ops.sgan_gp_second(logits.cuda(), tang.cuda(), K, rows, 0.7, q)
+    close(q, q_ref, 2e-5, 'sgan_gp_second')
+    dT = rnd(gen, K, rows)
+    for act, slope in ((1, 0.05), (0, 0.0)):
+        o_ref, o = torch.empty(rows * cols, dtype=dt), torch.empty(rows * cols, dtype=dt, device='cuda')
+        ref.seed_rows_multi(o_ref, rows, cols, dT, W, K, X, act, slope)
+        ops.seed_rows_multi(o, rows, cols, dT.cuda(), W.cuda(), K, X.cuda(), act, slope)
+        close(o, o_ref, tol(dt), 'seed_rows_multi')
+    if cols % 4 == 0:
+        for with_bias in (True, False):
+            dW_ref, db_ref = rnd(gen, K * cols), rnd(gen, K)
+            dW, db = dW_ref.clone().cuda(), db_ref.clone().cuda()
+            ref.head_wgrad(X, rows, cols, dT, K, dW_ref, db_ref if with_bias else None)
+            ops.head_wgrad(X.cuda(), rows, cols, dT.cuda(), K, dW, db if with_bias else None)
+            close(dW, dW_ref, t, 'head_wgrad')
+            close(db, db_ref, 1e-4, 'head_wgrad bias')

@@ -214,6 +214,13 @@ class TorchOps:
         a = (p * t).sum(1, keepdim=True)
         qT.copy_((c * (sg * (1 - sg) * a * p + sg * (p * t - a * p))).t())
 
+    def head_wgrad(self, X, rows, cols, dT, K, dW, db):
+        self.launches += 1
+        x = X[:rows * cols].view(rows, cols).to(dW.dtype)
+        dW[:K * cols].view(K, cols).add_(dT.to(dW.dtype) @ x)
+        if db is not None:
+            db[:K].add_(dT.to(db.dtype).sum(1))
+
     def seed_rows_multi(self, out, rows, cols, dT, W, K, href, act, slope):
         self.launches += 1
         cd = href.dtype if href.dtype == torch.float64 else torch.float32
