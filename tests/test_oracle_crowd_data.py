@@ -72,3 +72,36 @@ def test_age_and_driving_items_bit_exact(g):
         assert np.array_equal(a, g['f1c_age_images'][k]), k
         d, v = C.image_label_item(np.ascontiguousarray(image.transpose((2, 0, 1))), g['f1c_labels'][k], hwc=False)
         assert np.array_equal(d, g['f1c_driving_images'][k]) and v == g['f1c_driving_angles'][k], k
+
+
+def test_product_host_logic_matches_oracle_without_a_gpu(g):
+    """The host side of the input pipeline (no kernels): TransformedDataset's flat-index arithmetic and random draws, and the
+    SlidingWindow positions, against the oracle / the reference golden -- on a stand-in store that only carries the image shapes."""
+    from srgan_b200 import crowd_data
+    ex, patch, step = examples(g), int(g['patch']), int(g['step'])
+    store_ids = [int(i) for i in g['f1b_store']]
+    shapes = [ex[i][0].shape[:2] for i in store_ids]
+    fake_store = type('ShapesOnly', (), {'shapes': shapes})()
+    ds = crowd_data.TransformedDataset(fake_store, patch, patch)
+    starts, length = C.start_indexes(shapes, patch)
+    assert ds.start_indexes == starts and len(ds) == length == int(g['f1b_length'])
+    for index_ in list(range(0, length, 37)) + [length - 1] + starts:
+        assert ds.position(index_) == C.transformed_position(shapes, patch, index_), index_
+    # the draws: random.randrange then random.choice per sample, like the reference's __getitem__ + RandomHorizontalFlip
+    random.seed(int(g['f1b_seed']))
+    table = ds.draw(24)
+    random.seed(int(g['f1b_seed']))
+    for b in range(24):
+        f, y, x = C.transformed_position(shapes, patch, random.randrange(length))
+        assert tuple(table[b]) == (f, y, x, int(random.choice([True, False]))), b
+    for i, (image, _, _) in enumerate(ex):
+        sw = crowd_data.SlidingWindow(*image.shape[:2], patch, step)
+        assert sw.y_positions == list(g[f'f2_ys{i}']) and sw.x_positions == list(g[f'f2_xs{i}'])
+        assert sw.table(3).shape == (sw.length, 4) and int(sw.table(3)[0, 0]) == 3
+    with pytest.raises(NotImplementedError):
+        crowd_data.TransformedDataset(fake_store, patch, patch // 2)
+    with pytest.raises(RuntimeError):
+        import torch
+        if torch.cuda.is_available():
+            raise RuntimeError('GPU present: the refusal below is the CPU-only behaviour')
+        crowd_data.CrowdStore([ex[0]])
