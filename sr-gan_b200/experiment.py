@@ -565,7 +565,7 @@ class StepRunner:
         wd = cfg.weight_decay if weight_decay is None else weight_decay
         self._wait_pending(('DNN',))
         if self.persistent:
-            if not self.use_cuda_graph or os.environ.get('SRGAN_NO_COEF_GRAPH', '0') == '1':
+            if not self.use_cuda_graph or os.environ.get('SRGAN_COEF_GRAPH', '0') != '1':
                 self._coef_step(1, examples, labels, lr_dnn=lr, wd=wd)
                 return
             # the cooperative launch replayed from a CUDA graph (north_star: "one persistent CUDA-graph kernel")
@@ -602,7 +602,7 @@ class StepRunner:
         train_g = (step % cfg.generator_training_step_period == 0)
         self._wait_pending(('G',))
         if self.persistent:
-            if not self.use_cuda_graph or os.environ.get('SRGAN_NO_COEF_GRAPH', '0') == '1':
+            if not self.use_cuda_graph or os.environ.get('SRGAN_COEF_GRAPH', '0') != '1':
                 self._coef_step(2, labeled_examples, labels, unlabeled_examples, z, alpha.reshape(-1), z2, train_g=train_g)
                 return
             al, yl = alpha.reshape(-1), labels.reshape(-1)
