@@ -968,7 +968,7 @@ class Engine:
     def _sgan_head_grads(self, st: NetState, feats, n, dT, bias=True):
         """dW_k += sum_r dT[k][r] * feats[r,:] (and db_k += sum_r dT[k][r]) for the K outputs of the head."""
         F, K = st.net.feature_size, st.net.head_outputs
-        if st.net.head_parts is None and F % 4 == 0 and os.environ.get('SRGAN_HEAD_WGRAD', '0') == '1':
+        if st.net.head_parts is None and F % 4 == 0 and os.environ.get('SRGAN_NO_HEAD_WGRAD', '0') != '1':
             # one [K, F] head tensor: a single pass over the feature rows
             self.ops.head_wgrad(feats, n, F, dT, K, st.g(st.net.head + '.weight'), st.g(st.net.head + '.bias') if bias else None)
             return

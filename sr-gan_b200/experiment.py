@@ -568,7 +568,10 @@ class StepRunner:
             if not self.use_cuda_graph or os.environ.get('SRGAN_COEF_GRAPH', '0') != '1':
                 self._coef_step(1, examples, labels, lr_dnn=lr, wd=wd)
                 return
-            # the cooperative launch replayed from a CUDA graph (north_star: "one persistent CUDA-graph kernel")
+            # SRGAN_COEF_GRAPH=1: the cooperative launch replayed from a CUDA graph (north_star: "one persistent CUDA-graph
+            # kernel").  Opt-in because it measures SLOWER: the step is device-bound (two launches of ~115 us, the host needs
+            # ~40 us for both), and a replay adds the copies into the static inputs: 262.5 vs 235.7 us/step at B = 5000
+            # (profiles/r2_final_coef_graph.txt)
             xs, ys = self._static('cx', examples), self._static('cy', labels.reshape(-1))
             key = ('coef_dnn', tuple(examples.shape), lr, wd, repr(sorted(vars(cfg).items())))
             self._graphed(key, [(xs, examples), (ys, labels.reshape(-1))], lambda: self._coef_step(1, xs, ys, lr_dnn=lr, wd=wd))
