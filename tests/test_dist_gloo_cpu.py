@@ -49,7 +49,7 @@ def _worker(rank, world, port, name, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('name', ['coefficient_srgan', 'coefficient_dggan', 'dcgan_mini'])
+@pytest.mark.parametrize('name', ['coefficient_srgan', 'coefficient_dggan', 'dcgan_mini', 'dcgan_sgan_mini'])
 def test_two_rank_step_equals_global_batch_step(name):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
