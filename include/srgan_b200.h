@@ -377,9 +377,11 @@ int srgan_point_density_map(const double* head_yx, int n_heads, int H, int W, fl
 /* ---- SGAN method: K-logit head (sgan.py:18-67, age/sgan.py, coefficient/sgan.py) ----------
  * Logit-shaped arrays are TRANSPOSED: [K][rows] fp32, K <= 16 (settings.py:67 number_of_bins = 10).
  * srgan_head_logits: logitsT[k][r] = X[r,:] . W[k,:] + bias[k]  (the K-output head: age/models.py:65,79 layer5 with
- *   number_of_outputs = K as a full-extent conv, coefficient/models.py:83,92 linear4); X is read once for all K. */
-int srgan_head_logits(const void* X, int rows, int cols, const float* W, const float* bias, int K, float* logitsT, int dtype,
-                      void* stream);
+ *   number_of_outputs = K as a full-extent conv, coefficient/models.py:83,92 linear4); X is read once for all K; per-column-range
+ *   partial sums go through `workspace` (srgan_head_logits_workspace_bytes) and are added in a fixed order: reproducible. */
+size_t srgan_head_logits_workspace_bytes(int rows, int cols, int K);
+int srgan_head_logits(const void* X, int rows, int cols, const float* W, const float* bias, int K, float* logitsT, void* workspace,
+                      size_t workspace_bytes, int dtype, void* stream);
 /* mode 0: nn.CrossEntropyLoss(logits, real_numbers_to_bin_indexes(y, bins)) (sgan.py:20-31, utility.py:141-144; mean over the
  *   batch folded into `scale`): loss += scale * sum_r (logsumexp(l_r) - l_r[bin_r]), dlogitsT = scale * (softmax - onehot);
  * mode 1: nn.BCEWithLogitsLoss(logsumexp(logits), target) (sgan.py:33-67): loss += scale * sum_r (softplus(z_r) - target z_r),

@@ -11,29 +11,38 @@ namespace {
 
 constexpr int kMaxK = 16;
 
-// logitsT[k][r] = sum_c X[r,c] * W[k][c] + bias[k] : one block per row, the row is read ONCE for all K outputs
+// logitsT[k][r] = sum_c X[r,c] * W[k][c] + bias[k].  A warp owns (one row, one range of kLogitCols columns): it reads its piece of
+// the row once, keeps K partial dot products per lane, warp-reduces them and writes them to partials[range][k][row]; a second
+// small kernel adds the ranges in a FIXED order (+ bias), so the logits are bit-reproducible (no atomics).  The 8 warps of a
+// block take 8 ROWS of the SAME column range, so the K weight rows of that range (K x 8 KB) are fetched once per block and
+// served from L1 to the other warps.  First version: one block per row -- 100 CTAs each re-reading all K weight rows from
+// L2: 124 us for 100 x 32 768 (ncu); this one is grid = column ranges x row groups.
+constexpr int kLogitCols = 2048;
+
 template <typename T>
 __global__ void __launch_bounds__(256) head_logits_kernel(const T* __restrict__ X, int rows, int cols, const float* __restrict__ W,
-                                                          const float* __restrict__ bias, int K, float* __restrict__ out) {
-    __shared__ float red[32];
-    const int r = blockIdx.x;
+                                                          int K, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int r = blockIdx.y * 8 + w;
+    if (r >= rows) return;
+    const int c0 = blockIdx.x * kLogitCols, c1 = min(cols, c0 + kLogitCols);
     const T* x = X + (long long)r * cols;
     float acc[kMaxK];
 #pragma unroll
     for (int k = 0; k < kMaxK; ++k) acc[k] = 0.f;
     if (cols % 4 == 0) {
-        for (int c = 4 * threadIdx.x; c < cols; c += 4 * blockDim.x) {
+        for (int c = c0 + 4 * lane; c < c1; c += 128) {
             const float4 v = ld4(x + c);
 #pragma unroll
             for (int k = 0; k < kMaxK; ++k) {
                 if (k < K) {
-                    const float4 w = ld4(W + (long long)k * cols + c);
-                    acc[k] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[k]))));
+                    const float4 wv = ld4(W + (long long)k * cols + c);
+                    acc[k] = fmaf(v.x, wv.x, fmaf(v.y, wv.y, fmaf(v.z, wv.z, fmaf(v.w, wv.w, acc[k]))));
                 }
             }
         }
     } else {
-        for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+        for (int c = c0 + lane; c < c1; c += 32) {
             const float v = to_f(x[c]);
 #pragma unroll
             for (int k = 0; k < kMaxK; ++k)
@@ -42,11 +51,20 @@ __global__ void __launch_bounds__(256) head_logits_kernel(const T* __restrict__ 
     }
 #pragma unroll
     for (int k = 0; k < kMaxK; ++k) {
-        if (k < K) {                                    // K is uniform over the block: no divergence around the barriers
-            const float s = block_sum(acc[k], red);
-            if (threadIdx.x == 0) out[(long long)k * rows + r] = s + (bias ? bias[k] : 0.f);
+        if (k < K) {
+            const float s = warp_sum(acc[k]);
+            if (lane == 0) out[((long long)blockIdx.x * K + k) * rows + r] = s;       // out = partials[range][k][row]
         }
     }
+}
+
+__global__ void __launch_bounds__(256) logits_reduce_kernel(const float* __restrict__ partials, int ranges, int K, int rows,
+                                                            const float* __restrict__ bias, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * rows) return;
+    float s = 0.f;
+    for (int g = 0; g < ranges; ++g) s += partials[(long long)g * K * rows + i];
+    out[i] = s + (bias ? bias[i / rows] : 0.f);
 }
 
 __device__ __forceinline__ float sigmoidf_(float z) { return z >= 0.f ? 1.f / (1.f + expf(-z)) : expf(z) / (1.f + expf(z)); }
@@ -116,17 +134,41 @@ __global__ void __launch_bounds__(256) sgan_gp_second_kernel(const float* __rest
     }
 }
 
-// out[r,c] = (sum_k dT[k][r] * W[k][c]) * act'(href[r,c]) : the K-output form of srgan_seed_rows
+// out[r,c] = (sum_k dT[k][r] * W[k][c]) * act'(href[r,c]) : the K-output form of srgan_seed_rows.  A thread owns 4 columns: the K
+// weight quads stay in registers over the thread's rows (blockIdx.y = row range), the K per-row coefficients are warp-uniform
+// loads.  First version: one thread per element re-reading K weights per element -- 38 us for 100 x 32 768 (ncu).
 template <typename T>
 __global__ void __launch_bounds__(256) seed_rows_multi_kernel(T* __restrict__ out, int rows, int cols, const float* __restrict__ dT,
                                                               const float* __restrict__ W, int K, const T* __restrict__ href, int act,
                                                               float slope) {
-    const long long total = (long long)rows * cols;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int r = (int)(i / cols), c = (int)(i % cols);
-        float s = 0.f;
-        for (int k = 0; k < K; ++k) s = fmaf(dT[(long long)k * rows + r], W[(long long)k * cols + c], s);
-        out[i] = from_f<T>(s * act_bwd(to_f(href[i]), act, slope));
+    const int r0 = (int)(((long long)rows * blockIdx.y) / gridDim.y), r1 = (int)(((long long)rows * (blockIdx.y + 1)) / gridDim.y);
+    if (cols % 4 == 0) {
+        const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+        if (c >= cols) return;
+        float4 wv[kMaxK];
+#pragma unroll
+        for (int k = 0; k < kMaxK; ++k) wv[k] = k < K ? ld4(W + (long long)k * cols + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = r0; r < r1; ++r) {
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < kMaxK; ++k) {
+                if (k < K) {
+                    const float d = dT[(long long)k * rows + r];
+                    s.x = fmaf(d, wv[k].x, s.x); s.y = fmaf(d, wv[k].y, s.y); s.z = fmaf(d, wv[k].z, s.z); s.w = fmaf(d, wv[k].w, s.w);
+                }
+            }
+            const float4 h = ld4(href + (long long)r * cols + c);
+            st4(out + (long long)r * cols + c, make_float4(s.x * act_bwd(h.x, act, slope), s.y * act_bwd(h.y, act, slope),
+                                                          s.z * act_bwd(h.z, act, slope), s.w * act_bwd(h.w, act, slope)));
+        }
+    } else {
+        const int c = blockIdx.x * blockDim.x + threadIdx.x;
+        if (c >= cols) return;
+        for (int r = r0; r < r1; ++r) {
+            float s = 0.f;
+            for (int k = 0; k < K; ++k) s = fmaf(dT[(long long)k * rows + r], W[(long long)k * cols + c], s);
+            out[(long long)r * cols + c] = from_f<T>(s * act_bwd(to_f(href[(long long)r * cols + c]), act, slope));
+        }
     }
 }
 
@@ -204,15 +246,25 @@ int srgan_head_wgrad(const void* X, int rows, int cols, const float* dT, int K, 
     return SRGAN_OK;
 }
 
-int srgan_head_logits(const void* X, int rows, int cols, const float* W, const float* bias, int K, float* logitsT, int dtype,
-                      void* stream) {
+size_t srgan_head_logits_workspace_bytes(int rows, int cols, int K) {
+    return sizeof(float) * (size_t)cdiv(cols > 0 ? cols : 1, kLogitCols) * (size_t)(K > 0 ? K : 0) * (size_t)(rows > 0 ? rows : 0);
+}
+
+int srgan_head_logits(const void* X, int rows, int cols, const float* W, const float* bias, int K, float* logitsT, void* workspace,
+                      size_t workspace_bytes, int dtype, void* stream) {
     SRGAN_REQUIRE(X && W && logitsT && rows >= 0 && cols > 0, "srgan_head_logits: bad arguments");
     SRGAN_REQUIRE(K >= 1 && K <= kMaxK, "srgan_head_logits: K = %d outside 1..%d", K, kMaxK);
     if (rows == 0) return SRGAN_OK;
+    SRGAN_REQUIRE(workspace && workspace_bytes >= srgan_head_logits_workspace_bytes(rows, cols, K), "srgan_head_logits: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == SRGAN_F32) head_logits_kernel<float><<<rows, 256, 0, st>>>((const float*)X, rows, cols, W, bias, K, logitsT);
-    else head_logits_kernel<bf16><<<rows, 256, 0, st>>>((const bf16*)X, rows, cols, W, bias, K, logitsT);
+    const int ranges = cdiv(cols, kLogitCols);
+    const dim3 grid(ranges, cdiv(rows, 8));
+    float* partials = (float*)workspace;
+    if (dtype == SRGAN_F32) head_logits_kernel<float><<<grid, 256, 0, st>>>((const float*)X, rows, cols, W, K, partials);
+    else head_logits_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)X, rows, cols, W, K, partials);
     SRGAN_CHECK_LAUNCH("head_logits_kernel");
+    logits_reduce_kernel<<<cdiv((long long)K * rows, 256), 256, 0, st>>>(partials, ranges, K, rows, bias, logitsT);
+    SRGAN_CHECK_LAUNCH("logits_reduce_kernel");
     return SRGAN_OK;
 }
 
@@ -242,8 +294,11 @@ int srgan_seed_rows_multi(void* out, int rows, int cols, const float* dT, const 
     SRGAN_REQUIRE(K >= 1 && K <= kMaxK, "srgan_seed_rows_multi: K = %d outside 1..%d", K, kMaxK);
     if (rows == 0) return SRGAN_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const long long total = (long long)rows * cols;
-    const int grid = (int)((total + 255) / 256 < 8LL * kNumSMs ? (total + 255) / 256 : 8LL * kNumSMs);
+    const int gx = cdiv(cols % 4 == 0 ? cols / 4 : cols, 256);
+    long long gy = (4LL * kNumSMs + gx - 1) / gx;               // row ranges: ~4 waves of blocks, at least 4 rows each
+    if (gy > (rows + 3) / 4) gy = (rows + 3) / 4;
+    if (gy < 1) gy = 1;
+    const dim3 grid(gx, (unsigned)gy);
     if (dtype == SRGAN_F32)
         seed_rows_multi_kernel<float><<<grid, 256, 0, st>>>((float*)out, rows, cols, dT, W, K, (const float*)href, act, slope);
     else

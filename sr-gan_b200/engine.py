@@ -953,7 +953,8 @@ class Engine:
         net = st.net
         out = self.buf(name, (net.head_outputs, n), self.mdt)
         b = (st.hbias if net.head_parts is not None else st.params[net.head + '.bias']) if bias else None
-        self.ops.head_logits(feats, n, net.feature_size, st.whead, b, net.head_outputs, out)
+        ws = self.buf('lg_ws', (self.ops.head_logits_workspace(n, net.feature_size, net.head_outputs),), self.mdt)
+        self.ops.head_logits(feats, n, net.feature_size, st.whead, b, net.head_outputs, out, ws)
         return out
 
     def _sgan_bins(self, cfg):

@@ -38,7 +38,7 @@ _EXPORTS = (
     'srgan_adam_layout_multi', 'srgan_bn_dgrad', 'srgan_bn_conv_down', 'srgan_bn_conv_wgrad', 'srgan_bn_conv_dgrad',
     'srgan_crowd_extract_patches', 'srgan_sliding_window_merge', 'srgan_crowd_eval_sums', 'srgan_image_batch',
     'srgan_knn_maps', 'srgan_point_density_map', 'srgan_density_label', 'srgan_density_label_workspace_bytes',
-    'srgan_head_logits', 'srgan_sgan_loss', 'srgan_sgan_gp_second', 'srgan_seed_rows_multi', 'srgan_head_wgrad',
+    'srgan_head_logits', 'srgan_head_logits_workspace_bytes', 'srgan_sgan_loss', 'srgan_sgan_gp_second', 'srgan_seed_rows_multi', 'srgan_head_wgrad',
     'srgan_sliding_window_workspace_bytes', 'srgan_crowd_eval_workspace_bytes',
 )
 
@@ -121,7 +121,8 @@ def load_library(path: str = LIB_PATH):
     lib.srgan_point_density_map.argtypes = [vp, c_int, c_int, c_int, vp, vp, vp]
     lib.srgan_density_label.argtypes = [vp, c_int, c_int, c_int, c_d, vp, vp, vp, ctypes.c_size_t, vp]
     lib.srgan_density_label_workspace_bytes.argtypes = [c_int, c_int, c_int]
-    lib.srgan_head_logits.argtypes = [vp, c_int, c_int, vp, vp, c_int, vp, c_int, vp]
+    lib.srgan_head_logits.argtypes = [vp, c_int, c_int, vp, vp, c_int, vp, vp, ctypes.c_size_t, c_int, vp]
+    lib.srgan_head_logits_workspace_bytes.argtypes = [c_int, c_int, c_int]
     lib.srgan_sgan_loss.argtypes = [vp, c_int, c_int, c_int, vp, vp, c_f, c_f, vp, vp, vp]
     lib.srgan_sgan_gp_second.argtypes = [vp, vp, c_int, c_int, c_f, vp, vp]
     lib.srgan_seed_rows_multi.argtypes = [vp, c_int, c_int, vp, vp, c_int, vp, c_int, c_f, c_int, vp]
@@ -134,6 +135,7 @@ def load_library(path: str = LIB_PATH):
     lib.srgan_sliding_window_workspace_bytes.restype = ctypes.c_size_t
     lib.srgan_crowd_eval_workspace_bytes.restype = ctypes.c_size_t
     lib.srgan_density_label_workspace_bytes.restype = ctypes.c_size_t
+    lib.srgan_head_logits_workspace_bytes.restype = ctypes.c_size_t
     _lib = lib
     return lib
 
@@ -411,10 +413,15 @@ class CudaOps:
                                             self._stream()), 'srgan_avgpool_bwd')
 
     # ---- SGAN K-logit head (csrc/sgan.cu); logit-shaped tensors are [K, rows] fp32
-    def head_logits(self, X, rows, cols, W, bias, K, out):
+    def head_logits_workspace(self, rows, cols, K):
+        """fp32 elements of the partial-sum workspace srgan_head_logits needs."""
+        return self.lib.srgan_head_logits_workspace_bytes(rows, cols, K) // 4
+
+    def head_logits(self, X, rows, cols, W, bias, K, out, ws):
         f32 = torch.float32
         self._ck(self.lib.srgan_head_logits(self._p(X), rows, cols, self._p(W, f32), self._p(bias.detach() if bias is not None else None, f32),
-                                            K, self._p(out, f32), _dt(X.dtype), self._stream()), 'srgan_head_logits')
+                                            K, self._p(out, f32), self._p(ws, f32), ws.numel() * 4, _dt(X.dtype), self._stream()),
+                 'srgan_head_logits')
 
     def sgan_loss(self, logitsT, K, n, mode, y, bins, target, scale, loss_out, dlogitsT):
         f32 = torch.float32

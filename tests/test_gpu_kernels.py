@@ -682,7 +682,8 @@ def test_sgan_head_kernels(ops, dt, rows, cols, K):
     for b in (bias, None):
         l_ref, l = torch.empty(K, rows), torch.empty(K, rows, device='cuda')
         ref.head_logits(X, rows, cols, W, b, K, l_ref)
-        ops.head_logits(X.cuda(), rows, cols, W.cuda(), b.cuda() if b is not None else None, K, l)
+        ws = torch.empty(ops.head_logits_workspace(rows, cols, K), device='cuda')
+        ops.head_logits(X.cuda(), rows, cols, W.cuda(), b.cuda() if b is not None else None, K, l, ws)
         close(l, l_ref, t, 'head_logits')
     logits = rnd(gen, K, rows) * 3
     y, bins = rnd(gen, rows) * 50 + 50, torch.linspace(10, 95, K)

@@ -181,7 +181,11 @@ class TorchOps:
         out.copy_(r.reshape(-1).to(out.dtype))
 
     # ---- SGAN K-logit head (csrc/sgan.cu); logit-shaped tensors are [K, rows]
-    def head_logits(self, X, rows, cols, W, bias, K, out):
+    @staticmethod
+    def head_logits_workspace(rows, cols, K):
+        return 1
+
+    def head_logits(self, X, rows, cols, W, bias, K, out, ws=None):
         self.launches += 1
         x = X[:rows * cols].view(rows, cols).to(out.dtype)
         l = x @ W[:K * cols].view(K, cols).to(out.dtype).t()
