@@ -87,6 +87,9 @@ class Settings:
         self.matching_distance_function = abs_mean
         self.hidden_size = 10
         self.map_multiplier = 1e-6
+        self.number_of_bins = 10         # settings.py:67 (SGAN)
+        self.bins = None                 # SGAN: the bin centres (the reference experiments build them: age/sgan.py:14)
+        self.async_checkpoint = False    # save_models through checkpoint.AsyncWriter (off = the reference's blocking torch.save)
         # new knobs (added attributes only, defaults = reference behaviour): SURVEY section 5
         self.precision = 'fp32'          # 'fp32' (SIMT, 1e-4 parity) | 'bf16' (tcgen05 tensor cores, 2e-2 parity)
         self.use_cuda_graph = True       # replay the step methods from CUDA graphs (piecewise around collectives)
@@ -894,19 +897,31 @@ class B200StepMixin:
 
 class Experiment:
     """Stand-alone mirror of the reference Experiment's step API (srgan.py:24-50, 259-320) for the supported model
-    families; `application` in {'coefficient', 'age', 'driving', 'crowd'}, `method` in {'srgan', 'dggan'}."""
+    families; `application` in {'coefficient', 'age', 'driving', 'crowd'}, `method` in {'srgan', 'dggan', 'sgan'} (sgan: the
+    class-logit experiments of age/sgan.py and coefficient/sgan.py, with their bins)."""
 
     def __init__(self, settings: Settings, application='age', method='srgan', device='cuda:0', comm=None, **model_kwargs):
         self.settings = settings
         dev = torch.device(device)
+        bins = int(getattr(settings, 'number_of_bins', 10))                 # settings.py:67
+        if method == 'sgan':
+            if application not in ('age', 'coefficient'):
+                raise NotImplementedError(f'SGAN for {application!r}: the reference has age/sgan.py, coefficient/sgan.py and '
+                                          'crowd/sgan.py; the first two have a B200 path')
+            if getattr(settings, 'bins', None) is None:                     # age/sgan.py:14, coefficient/sgan.py:15
+                lo, hi = (10.0, 95.0) if application == 'age' else (-3.0, 3.0)
+                settings.bins = tuple(torch.linspace(lo, hi, bins).tolist())
         if application == 'coefficient':
-            n_out = 2 if method == 'dggan' else 1
-            self.D = CoefficientMLP(settings.hidden_size, n_out)
-            self.DNN = CoefficientMLP(settings.hidden_size, n_out)
+            n_out = bins if method == 'sgan' else 2 if method == 'dggan' else 1
+            hidden = 100 if method == 'sgan' else settings.hidden_size     # SganMLP: coefficient/models.py:80-83
+            self.D = CoefficientMLP(hidden, n_out)
+            self.DNN = CoefficientMLP(hidden, n_out)
             self.G = CoefficientGenerator(settings.hidden_size)
         elif application in ('age', 'driving'):
             self.G = DcganGenerator(**{k: v for k, v in model_kwargs.items() if k in ('z_dim', 'image_size', 'conv_dim')})
             dk = {k: v for k, v in model_kwargs.items() if k in ('image_size', 'conv_dim')}
+            if method == 'sgan':
+                dk['number_of_outputs'] = bins                              # age/sgan.py:18-19
             self.D = DcganDiscriminator(**dk)
             self.DNN = DcganDiscriminator(**dk)
         elif application == 'crowd':                                        # crowd/srgan.py:92-96 model_setup

@@ -546,3 +546,36 @@ def test_sgan_tensor_core_size_vs_oracle(precision):
     with pytest.raises(ValueError):
         bad = O.StepConfig(method='sgan', batch_size=8, bins=bins[:5])
         runner_from_state(st0, bad, precision)
+
+
+@pytest.mark.parametrize('application', ['age', 'coefficient'])
+def test_mirror_experiment_runs_sgan(application):
+    """srgan_b200.Experiment(..., method='sgan'): the stand-alone mirror builds the class-logit networks and the application's
+    bins (age/sgan.py:14-19, coefficient/sgan.py:15-21) and steps; two identically seeded runs agree bit for bit (the K-logit
+    head kernels reduce in a fixed order)."""
+    import srgan_b200
+    outs = []
+    for _ in range(2):
+        s = srgan_b200.Settings()
+        s.batch_size, s.gradient_penalty_multiplier, s.precision = 16, 1e2, 'fp32'
+        kw = dict(image_size=32, conv_dim=8, z_dim=16) if application == 'age' else {}
+        exp = srgan_b200.Experiment(s, application, 'sgan', **kw)
+        assert exp.runner.method == 'sgan' and len(exp.runner.config().bins) == 10 and not exp.runner.persistent
+        gen = torch.Generator().manual_seed(3)
+        if application == 'age':
+            x, u = torch.rand(16, 3, 32, 32, generator=gen) * 2 - 1, torch.rand(16, 3, 32, 32, generator=gen) * 2 - 1
+            y, zd = torch.rand(16, generator=gen) * 85 + 10, 16
+            alpha = torch.rand(16, 1, 1, 1, generator=gen)
+        else:
+            x, u = torch.randn(16, 50, generator=gen), torch.randn(16, 50, generator=gen)
+            y, zd = torch.rand(16, generator=gen) * 4 - 2, 10
+            alpha = torch.rand(16, 1, generator=gen)
+        z, z2 = torch.randn(16, zd, generator=gen), torch.randn(16, zd, generator=gen)
+        for i in range(2):
+            exp.dnn_training_step(x.cuda(), y.cuda(), i)
+            exp.gan_training_step(x.cuda(), y.cuda(), u.cuda(), i, noise=(z.cuda(), alpha.cuda(), z2.cuda()))
+        sc = exp.runner.scalars()
+        assert all(v == v and abs(v) < 1e6 for v in sc.values()), sc
+        assert sc['labeled_loss'] > 0 and sc['generator_loss'] < 0            # cross entropy > 0, -BCE < 0
+        outs.append(sc)
+    assert outs[0] == outs[1]
