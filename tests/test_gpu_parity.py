@@ -551,8 +551,8 @@ def test_sgan_tensor_core_size_vs_oracle(precision):
 @pytest.mark.parametrize('application', ['age', 'coefficient'])
 def test_mirror_experiment_runs_sgan(application):
     """srgan_b200.Experiment(..., method='sgan'): the stand-alone mirror builds the class-logit networks and the application's
-    bins (age/sgan.py:14-19, coefficient/sgan.py:15-21) and steps; two identically seeded runs agree bit for bit (the K-logit
-    head kernels reduce in a fixed order)."""
+    bins (age/sgan.py:14-19, coefficient/sgan.py:15-21) and steps; two identically seeded runs agree (to fp32 reduction-order
+    noise: the weight-gradient kernels add partial sums with atomics)."""
     import srgan_b200
     outs = []
     for _ in range(2):
@@ -578,4 +578,5 @@ def test_mirror_experiment_runs_sgan(application):
         assert all(v == v and abs(v) < 1e6 for v in sc.values()), sc
         assert sc['labeled_loss'] > 0 and sc['generator_loss'] < 0            # cross entropy > 0, -BCE < 0
         outs.append(sc)
-    assert outs[0] == outs[1]
+    for k in outs[0]:
+        assert outs[0][k] == pytest.approx(outs[1][k], rel=1e-4, abs=1e-6), k
