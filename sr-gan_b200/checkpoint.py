@@ -43,14 +43,18 @@ def snapshot(model: dict, stream=None):
         host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
         host.copy_(t.detach(), non_blocking=True)
         return host
-    if not torch.cuda.is_available():
+    devices = []
+    _map_tensors(model, lambda t: devices.append(t.device) if t.is_cuda else None)
+    if not devices:
         return _map_tensors(model, to_host), None
-    stream = stream or torch.cuda.Stream()
-    stream.wait_stream(torch.cuda.current_stream())            # the parameters as of the steps enqueued so far
-    with torch.cuda.stream(stream):
-        host = _map_tensors(model, to_host)
-        event = torch.cuda.Event()
-        event.record(stream)
+    dev = devices[0]                                           # one process drives one GPU: the checkpoint lives on it
+    with torch.cuda.device(dev):
+        stream = stream or torch.cuda.Stream(dev)
+        stream.wait_stream(torch.cuda.current_stream(dev))     # the parameters as of the steps enqueued so far
+        with torch.cuda.stream(stream):
+            host = _map_tensors(model, to_host)
+            event = torch.cuda.Event()
+            event.record(stream)
     return host, (event if cuda[0] else None)
 
 
@@ -66,8 +70,6 @@ class AsyncWriter:
 
     def save(self, model: dict, path: str):
         self.wait()
-        if torch.cuda.is_available() and self._stream is None:
-            self._stream = torch.cuda.Stream()
         host, event = snapshot(model, self._stream)
 
         def write():
