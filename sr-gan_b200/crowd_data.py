@@ -205,6 +205,10 @@ def predict_full_example(store: CrowdStore, image_index, network, image_patch_si
     lib, dev = store.lib, store.device
     H, W = store.shapes[image_index]
     sw = SlidingWindow(H, W, image_patch_size, window_step_size)
+    if sw.length == 0:
+        # a side of at most patch/2 pixels: the reference's position lists are empty (crowd/data.py:530-537), no patch is
+        # predicted and its sums stay zero (crowd/srgan.py:345-347,391-394)
+        return torch.zeros((), device=dev, dtype=torch.float64), torch.zeros(H, W, device=dev, dtype=torch.float32)
     table = torch.as_tensor(sw.table(image_index)).pin_memory().to(dev, non_blocking=True)
     counts = torch.empty(sw.length, device=dev, dtype=torch.float32)
     labels = None

@@ -127,6 +127,20 @@ def test_sliding_window_constant_network_property_at_full_size():
     assert float(label.abs().max()) == 0.0 and count.item() == pytest.approx(7.0 * 768 * 1024 / 224 ** 2, rel=1e-6)
 
 
+def test_sliver_image_has_no_windows_like_the_reference():
+    """A side of at most patch / 2 pixels: ImageSlidingWindowDataset yields no window (crowd/data.py:530-537) and the reference
+    returns zero sums; so does the device path (no kernel launch with an empty window list)."""
+    from srgan_b200 import crowd_data
+    image = np.full((3, 50, 3), 7, dtype=np.uint8)
+    store = crowd_data.CrowdStore([(image, None, None)])
+    assert crowd_data.SlidingWindow(3, 50, 32, 12).length == 0 and C.sliding_positions(3, 32, 12) == []
+    count, label = crowd_data.predict_full_example(store, 0, lambda im: (None, torch.ones(im.shape[0], device='cuda'), None), 32, 12)
+    o_count, o_label = C.predict_full_example(image, lambda im: (np.zeros((im.shape[0], 32, 32), np.float32), np.ones(im.shape[0]), None),
+                                              32, 12, 4)
+    assert count.item() == float(o_count) == 0.0 and label.shape == (3, 50) and float(label.abs().max()) == 0.0
+    assert float(np.abs(o_label).max()) == 0.0
+
+
 def test_evaluation_epoch_matches_reference_golden(g):
     from srgan_b200 import crowd_data
     t = lambda k: torch.tensor(g[k][:15]).cuda()
