@@ -174,6 +174,32 @@ def main():
         out['f1c_driving_images'] = np.stack([t[0].numpy() for t in items])
         out['f1c_driving_angles'] = np.stack([t[1].numpy() for t in items])
 
+    # ---- f1d: WorldExpoTransformedDataset.__getitem__ (crowd/world_expo_data.py:124-162): cameras hold stacks of equally sized
+    # frames, the flat index decomposes into (camera, frame, position) and the label doubles as the map (:146).  The object is
+    # built without __init__ (which reads the undownloadable archive) from two synthetic cameras.
+    from crowd.world_expo_data import WorldExpoTransformedDataset, CameraData
+    rng = np.random.RandomState(41)
+    cameras = []
+    for c, (frames, h, w) in enumerate(((3, 40, 48), (2, 36, 64))):
+        images = rng.randint(0, 256, size=(frames, h, w, 3)).astype(np.uint8)
+        labels = rng.rand(frames, h, w).astype(np.float32)
+        out[f'f1d_images{c}'], out[f'f1d_labels{c}'] = images, labels
+        cameras.append(CameraData(images=images, labels=labels, roi=None, perspective=None))
+    ds = object.__new__(WorldExpoTransformedDataset)
+    ds.camera_data_list, ds.image_patch_size, ds.label_patch_size = cameras, PATCH, PATCH
+    ds.middle_transform = rdata.RandomHorizontalFlip()
+    half, ds.length, ds.start_indexes = PATCH // 2, 0, []
+    for cam in cameras:                                                # crowd/world_expo_data.py:113-118
+        per_image = len(range(half, cam.images.shape[1] - half + 1)) * len(range(half, cam.images.shape[2] - half + 1))
+        ds.start_indexes.append(ds.length)
+        ds.length += cam.images.shape[0] * per_image
+    random.seed(23)
+    items = [ds[k] for k in range(20)]
+    out['f1d_seed'], out['f1d_length'], out['f1d_cameras'] = np.int64(23), np.int64(ds.length), np.int64(len(cameras))
+    out['f1d_out_images'] = np.stack([t[0].numpy() for t in items])
+    out['f1d_out_labels'] = np.stack([t[1].numpy() for t in items])
+    out['f1d_out_maps'] = np.stack([t[2].numpy() for t in items])
+
     path = os.path.join(os.path.dirname(HERE), 'tests', 'golden', 'crowd_data.npz')
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), 'bytes;', len(pos), 'patches,', len(examples), 'full examples')

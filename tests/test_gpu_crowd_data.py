@@ -227,3 +227,17 @@ def test_age_full_size_batch_vs_oracle():
         want, lab = C.image_label_item(images[index[b]], labels[index[b]])
         assert np.array_equal(out[b].cpu().numpy(), want) and float(y[b]) == float(lab)
     assert torch.equal(y.cpu(), torch.tensor(labels[index]))
+
+
+def test_world_expo_dataset_draw_for_draw(g):
+    """WorldExpoTransformedDataset (cameras of equally sized frames, label = map) through the same CrowdStore + TransformedDataset:
+    the reference's 20 samples under the same `random` seed, bit for bit."""
+    from srgan_b200 import crowd_data
+    from tests.test_oracle_crowd_data import world_expo_frames
+    store = crowd_data.CrowdStore(world_expo_frames(g))
+    ds = crowd_data.TransformedDataset(store, int(g['patch']), int(g['patch']))
+    assert len(ds) == int(g['f1d_length'])
+    random.seed(int(g['f1d_seed']))
+    images, labels, maps = ds.batch(len(g['f1d_out_images']))
+    assert torch.equal(images.cpu(), torch.tensor(g['f1d_out_images']))
+    assert torch.equal(labels.cpu(), torch.tensor(g['f1d_out_labels'])) and torch.equal(maps.cpu(), torch.tensor(g['f1d_out_maps']))

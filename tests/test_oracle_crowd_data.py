@@ -105,3 +105,29 @@ def test_product_host_logic_matches_oracle_without_a_gpu(g):
         if torch.cuda.is_available():
             raise RuntimeError('GPU present: the refusal below is the CPU-only behaviour')
         crowd_data.CrowdStore([ex[0]])
+
+
+def world_expo_frames(g):
+    """The frames of every synthetic camera, flattened camera after camera; the label doubles as the map
+    (crowd/world_expo_data.py:146)."""
+    frames = []
+    for c in range(int(g['f1d_cameras'])):
+        for image, label in zip(g[f'f1d_images{c}'], g[f'f1d_labels{c}']):
+            frames.append((image, label, label))
+    return frames
+
+
+def test_world_expo_items_are_the_same_flat_index_over_flattened_frames(g):
+    """WorldExpoTransformedDataset decomposes its flat index into (camera, frame, position); frames of a camera are equally
+    sized, so that is the per-example decomposition of the ShanghaiTech dataset over the frames laid out camera after camera:
+    the same oracle (and the same CrowdStore + TransformedDataset on the device) serves it."""
+    frames, patch = world_expo_frames(g), int(g['patch'])
+    _, length = C.start_indexes([f[0].shape[:2] for f in frames], patch)
+    assert length == int(g['f1d_length'])
+    random.seed(int(g['f1d_seed']))
+    for k in range(len(g['f1d_out_images'])):
+        index_ = random.randrange(length)
+        flip = random.choice([True, False])
+        image, label, map_ = C.transformed_item(frames, patch, index_, flip)
+        assert np.array_equal(image, g['f1d_out_images'][k]), k
+        assert np.array_equal(label, g['f1d_out_labels'][k]) and np.array_equal(map_, g['f1d_out_maps'][k]), k
