@@ -40,3 +40,13 @@ def test_product_path_refuses_cpu():
         pytest.skip('GPU present')
     with pytest.raises(RuntimeError):
         ops_cuda.CudaOps()
+    # the widened rows (input pipeline, label preprocessing) have no CPU path either
+    import numpy as np
+    from srgan_b200 import crowd_data, crowd_labels
+    with pytest.raises(RuntimeError):
+        crowd_data.CrowdStore([(np.zeros((8, 8, 3), np.uint8), None, None)])
+    with pytest.raises(RuntimeError):
+        crowd_data.ImageLabelStore(np.zeros((2, 8, 8, 3), np.uint8), np.zeros(2, np.float32))
+    for fn in (crowd_labels.generate_knn_maps, crowd_labels.generate_density_label, crowd_labels.generate_point_density_map):
+        with pytest.raises(RuntimeError):
+            fn(np.ones((3, 2)), (8, 8))
